@@ -1,0 +1,226 @@
+/*
+ * kukeon_gpuload.h — C ABI of libkukeon_gpuload.so, the Blackwell-native model-hub weight loader.
+ *
+ * This is the drop-in boundary of the hot path named by BASELINE.json's north_star: kukeond keeps a Go
+ * API (modelhub.Pull / Load / Mount, gpupool, the Cell hooks) and every one of those calls bottoms
+ * out in one of the functions below through cgo.  The reference (eminwux/kukeon @ 4be245a) has NO
+ * loader and NO FFI today, so each entry point cites the nearest reference seam it
+ * would be bound next to rather than a function it replaces:
+ *
+ *   kk_open / kk_close      pool lifetime == daemon lifetime.  internal/daemon/server.go:87 (NewServer)
+ *                           and :242 (Stop); options threaded like runner.Options, runner/runner.go:173-194.
+ *   kk_index                modelhub.Pull [NOT IN REFERENCE].  Nearest analogue: OCI image pull,
+ *                           internal/ctr/image.go:91-157.  CPU only; no device is touched.
+ *   kk_load / kk_load_ex    modelhub.Load [NOT IN REFERENCE].  Nearest analogue: ctr.LoadImage,
+ *                           internal/ctr/image.go:166-188.  Called from runner.StartCell beside
+ *                           attachableBuildOpts, internal/controller/runner/start.go:785-790 and
+ *                           provision.go:1560-1570.
+ *   kk_export               modelhub.Mount [NOT IN REFERENCE].  The manifest it renders is staged the way
+ *                           secrets are (internal/ctr/secrets.go:105-127) and bind-mounted read-only through a
+ *                           ctr.BuildOption (internal/ctr/spec.go:176), env named like kukeonDefaultEnv
+ *                           (internal/ctr/spec.go:464-482).
+ *   kk_acquire / kk_release per-Cell refcount ("N concurrent Sessions share one HBM copy").  Acquire in
+ *                           StartCell (runner/start.go:252); release in KillCell (runner/kill.go:31),
+ *                           StopCell (runner/stop.go:34), DeleteCell (runner/delete_cell.go:33).
+ *   kk_last_error           errors surface as Go sentinels wrapped with %w, internal/errdefs/errdefs.go:23-.
+ *
+ * Contract:
+ *   - every function returns 0 (KK_OK) or a negative kk_status; kk_last_error() returns a thread-local,
+ *     NUL-terminated description valid until the next failing call on the same thread;
+ *   - no C++ exception crosses the boundary; all entry points are thread-safe (kukeond serves one
+ *     goroutine per connection, internal/daemon/server.go:236, so calls arrive on arbitrary OS threads);
+ *   - the caller owns every input buffer and every out-struct it passes; the library owns device memory,
+ *     pinned buffers, streams and opaque handles until the matching kk_release / kk_close;
+ *   - plain pointers and sizes only: no torch, no C++ types;
+ *   - there is NO CPU fallback: a load on a machine without a usable CUDA device fails with KK_ECUDA.
+ */
+#ifndef KUKEON_GPULOAD_H
+#define KUKEON_GPULOAD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KK_ABI_VERSION 1
+#define KK_MAX_DEVICES 8
+#define KK_MAX_DIMS 8
+#define KK_NAME_MAX 256
+#define KK_IPC_HANDLE_BYTES 64 /* sizeof(cudaIpcMemHandle_t) */
+#define KK_POOL_ALIGN 256      /* every tensor slot in a pool starts on a 256-byte boundary */
+
+typedef enum kk_status {
+  KK_OK = 0,
+  KK_EINVAL = -1,       /* bad argument (NULL, out of range, unknown enum) */
+  KK_ENOENT = -2,       /* path / shard / tensor not found */
+  KK_EFORMAT = -3,      /* malformed safetensors / GGUF / index.json */
+  KK_EIO = -4,          /* open/read failed or short read */
+  KK_ENOMEM = -5,       /* host or device allocation failed, or pool budget exceeded */
+  KK_ECUDA = -6,        /* CUDA runtime/driver error, or no usable device */
+  KK_EUNSUPPORTED = -7, /* dtype / mode / fan-out not supported on this build or machine */
+  KK_EBUSY = -8,        /* object still referenced */
+  KK_ERANGE = -9,       /* caller buffer too small; required size is reported where documented */
+  KK_ESTATE = -10       /* call not valid in the object's current state */
+} kk_status;
+
+/* File dtypes.  0..19 follow safetensors' Dtype enum order; 32.. are GGUF block-quantised types. */
+typedef enum kk_dtype {
+  KK_BOOL = 0, KK_F4 = 1, KK_F6_E2M3 = 2, KK_F6_E3M2 = 3, KK_U8 = 4, KK_I8 = 5, KK_F8_E5M2 = 6,
+  KK_F8_E4M3 = 7, KK_F8_E8M0 = 8, KK_I16 = 9, KK_U16 = 10, KK_F16 = 11, KK_BF16 = 12, KK_I32 = 13,
+  KK_U32 = 14, KK_F32 = 15, KK_C64 = 16, KK_F64 = 17, KK_I64 = 18, KK_U64 = 19,
+  KK_Q4_0 = 32, KK_Q4_1 = 33, KK_Q5_0 = 34, KK_Q5_1 = 35, KK_Q8_0 = 36, KK_Q2_K = 37, KK_Q3_K = 38,
+  KK_Q4_K = 39, KK_Q5_K = 40, KK_Q6_K = 41, KK_Q8_K = 42
+} kk_dtype;
+
+typedef enum kk_mode {
+  KK_MODE_SINGLE = 0,    /* whole checkpoint into the pool of devices[0] */
+  KK_MODE_BROADCAST = 1, /* every device ends with the whole pool: sharded ingest + fused P2P fan-out */
+  KK_MODE_SCATTER = 2    /* device g keeps only its slice (dim0 for column-parallel, dim1 for row-parallel) */
+} kk_mode;
+
+typedef enum kk_fanout {
+  KK_FANOUT_P2P = 0,  /* convert kernel stores every output vector to all peer-mapped pools (NVLink/NVSwitch) */
+  KK_FANOUT_NVLS = 1, /* multimem.st on an NVLS multicast mapping of the pools (when the host exposes it) */
+  KK_FANOUT_NONE = 2, /* local pool only; the caller runs its own collective (e.g. the NCCL comparison) */
+  KK_FANOUT_RAW = 3   /* fan out the *file* bytes (e.g. q4_K blocks) to peers, every device converts locally */
+} kk_fanout;
+
+/* kk_config.flags */
+#define KK_CFG_ZEROCOPY 0x1u     /* convert kernels read the pinned host ring directly (no H2D copy engine hop) */
+#define KK_CFG_NO_PEER_ACCESS 0x2u /* do not enable peer access between devices (forces replicas) */
+
+/* kk_load_opts.flags */
+#define KK_LOAD_GPT2_CONV1D_T 0x1u /* transpose HF GPT-2 Conv1D weights ([in,out] -> [out,in]) while loading */
+#define KK_LOAD_KEEP_F32 0x2u      /* keep F32 tensors as F32 in the pool (default: convert to bf16) */
+#define KK_LOAD_DEFER 0x4u         /* index + plan + allocate pools only; data moves on kk_load_part */
+
+typedef struct kk_ctx kk_ctx;     /* one per process (kukeond lifetime) */
+typedef struct kk_model kk_model; /* refcounted; one per (checkpoint identity, mode, flags) */
+
+typedef struct kk_config {
+  int32_t n_devices;                /* 1..KK_MAX_DEVICES */
+  int32_t devices[KK_MAX_DEVICES];  /* CUDA ordinals */
+  uint64_t pool_bytes_per_device;   /* budget across all resident models; 0 = no limit */
+  uint32_t n_staging_buffers;       /* pinned ring slots per device; 0 = default (8) */
+  uint64_t staging_buffer_bytes;    /* bytes per slot; 0 = default (64 MiB); rounded up to 2 MiB */
+  uint32_t n_reader_threads;        /* host reader threads per device; 0 = default (4) */
+  uint32_t flags;                   /* KK_CFG_* */
+} kk_config;
+
+typedef struct kk_tensor_meta {
+  char name[KK_NAME_MAX];
+  uint32_t dtype;             /* kk_dtype as stored in the file */
+  uint32_t n_dims;
+  uint64_t shape[KK_MAX_DIMS]; /* row-major, outermost first (GGUF ne[] is reversed into this order) */
+  uint32_t shard;             /* index into the shard list (kk_index_shard) */
+  uint32_t reserved;
+  uint64_t file_offset;       /* absolute byte offset of the tensor's data inside its shard file */
+  uint64_t nbytes;            /* bytes in the file */
+} kk_tensor_meta;
+
+typedef struct kk_placement {
+  int32_t device;             /* CUDA ordinal */
+  uint32_t dtype;             /* dtype in the pool (KK_BF16 for every float tensor by default) */
+  uint64_t pool_offset;       /* byte offset inside that device's pool, multiple of KK_POOL_ALIGN */
+  uint64_t nbytes;            /* bytes in the pool */
+  uint32_t n_dims;
+  uint32_t slice_dim;         /* KK_MODE_SCATTER: dimension sliced, or 0xFFFFFFFF when replicated/whole */
+  uint64_t shape[KK_MAX_DIMS]; /* shape in the pool (after transpose / slice) */
+  uint64_t slice_begin;       /* first index kept along slice_dim (0 when not sliced) */
+} kk_placement;
+
+typedef struct kk_load_opts {
+  int32_t mode;      /* kk_mode */
+  int32_t fanout;    /* kk_fanout */
+  uint32_t flags;    /* KK_LOAD_* */
+  /* Multi-process operation (one rank per GPU, e.g. under torchrun): this process ingests part
+   * `part_index` of `part_count` of the checkpoint and, in BROADCAST mode, fans it out to the pools
+   * attached with kk_peer_attach.  part_count <= 1 means "this process ingests everything its ctx's
+   * devices need". In SCATTER mode part_index/part_count select which slice this rank keeps. */
+  int32_t part_index;
+  int32_t part_count;
+  uint32_t reserved[3];
+} kk_load_opts;
+
+typedef struct kk_model_info {
+  uint64_t n_tensors;
+  uint64_t n_shards;
+  uint64_t file_bytes;   /* sum of tensor bytes in the files */
+  uint64_t pool_bytes;   /* bytes of one device's pool (max over devices for SCATTER) */
+  int32_t n_devices;
+  int32_t devices[KK_MAX_DEVICES];
+  int32_t mode;
+  int32_t refcount;
+  int32_t loaded;        /* 1 once every pool holds its data */
+  int32_t reserved;
+} kk_model_info;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+int kk_abi_version(void);
+const char* kk_last_error(void);
+const char* kk_status_name(int status);
+
+int kk_open(const kk_config* cfg, kk_ctx** out);
+int kk_close(kk_ctx* ctx); /* KK_EBUSY while any model is still referenced */
+
+/* ---- Pull: index a checkpoint (CPU only; ctx may be NULL) ------------------------------------ */
+/* path: a directory (model.safetensors.index.json | model.safetensors | *.gguf inside) or one file.
+ * Records come back sorted by (shard, file_offset).  Free with kk_free_index. */
+int kk_index(kk_ctx* ctx, const char* path, kk_tensor_meta** out, size_t* n);
+int kk_free_index(kk_tensor_meta* recs);
+/* Shard file names (absolute paths) of the last-level index of `path`; *n_out receives the count.
+ * buf receives name `i`; returns KK_ERANGE if cap is too small. */
+int kk_index_shard(kk_ctx* ctx, const char* path, size_t i, char* buf, size_t cap, size_t* n_out);
+
+/* ---- Load ------------------------------------------------------------------------------------ */
+int kk_load(kk_ctx* ctx, const char* path, int mode, int fanout, kk_model** out);
+int kk_load_ex(kk_ctx* ctx, const char* path, const kk_load_opts* opts, kk_model** out);
+/* Deferred / multi-process loading: after kk_load_ex(...KK_LOAD_DEFER...) and any kk_peer_attach calls,
+ * move the data.  May be called again to re-load (pools are overwritten with identical bytes). */
+int kk_load_part(kk_model* m);
+/* Attach the pool of another process's model (same checkpoint/plan) as fan-out destination `rank`.
+ * ipc_handle is the 64-byte handle that process got from kk_export.  rank must differ from part_index. */
+int kk_peer_attach(kk_model* m, int rank, const void* ipc_handle_64B);
+int kk_peer_detach_all(kk_model* m);
+
+int kk_model_get_info(kk_model* m, kk_model_info* out);
+int kk_placements(kk_model* m, const char* tensor, kk_placement* out, size_t cap, size_t* n);
+/* Tensor metadata of a loaded model by position (0 <= i < n_tensors), same order as kk_index. */
+int kk_model_tensor(kk_model* m, size_t i, kk_tensor_meta* out);
+
+/* ---- Mount: export to an agent container ----------------------------------------------------- */
+/* ipc_handle_64B receives the cudaIpcMemHandle_t of `device`'s pool; manifest_json receives the pool
+ * manifest (name -> offset/shape/dtype).  If cap is too small returns KK_ERANGE and, when
+ * required != NULL, the needed size.  Either output may be NULL to skip it. */
+int kk_export(kk_model* m, int device, void* ipc_handle_64B, char* manifest_json, size_t cap);
+int kk_export_size(kk_model* m, int device, size_t* required);
+/* Same-process consumers: raw device pointer of the pool. */
+int kk_pool_ptr(kk_model* m, int device, void** dev_ptr, uint64_t* nbytes);
+
+/* ---- Session refcount ------------------------------------------------------------------------ */
+int kk_acquire(kk_model* m);
+int kk_release(kk_model* m); /* frees pools when the count reaches 0 */
+
+/* ---- Observability / verification ------------------------------------------------------------ */
+int kk_stats(kk_model* m, char* json, size_t cap);
+/* Copy pool bytes back to the host (verification only; not on the hot path). */
+int kk_read(kk_model* m, int device, uint64_t pool_offset, uint64_t nbytes, void* host_dst);
+/* 64-bit order-sensitive checksum of a pool range computed on the device (see oracle for the definition):
+ * sum over 8-byte little-endian words w_i (zero-padded tail) of mix(w_i + i*0x9E3779B97F4A7C15). */
+int kk_checksum(kk_model* m, int device, uint64_t pool_offset, uint64_t nbytes, uint64_t* out);
+
+/* ---- Kernel-stage measurement (inputs resident in HBM) --------------------------------------- */
+/* Stage this model's (part of the) checkpoint bytes into a device-resident image (untimed), then
+ * kk_convert_resident runs exactly the convert/fan-out launches of a load — one launch per shard — from
+ * that image, timed with CUDA events on the launching stream.  ms_total receives the elapsed time of
+ * all launches; ms_per_launch (cap entries, may be NULL) each launch's own duration; n_launches the count. */
+int kk_stage_resident(kk_model* m);
+int kk_convert_resident(kk_model* m, float* ms_total, float* ms_per_launch, size_t cap, size_t* n_launches);
+int kk_unstage_resident(kk_model* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KUKEON_GPULOAD_H */

@@ -1,0 +1,592 @@
+// sm_100a kernels of the weight loader: one persistent, warp-specialised convert / fan-out kernel
+// plus a checksum kernel.  No tensor cores — the path has no contraction; it is HBM / NVLink bound.
+//
+// kk_convert_kernel:
+//   warp 0 (one elected lane) = TMA producer. It walks this CTA's tiles, resolves tile -> segment,
+//     publishes a TileDesc and pulls the tile's source bytes into a 4-stage shared-memory ring with
+//     cp.async.bulk (UBLKCP) completing on an mbarrier.
+//   warps 1..8 = consumers. Depending on the segment op they
+//       COPY, aligned     : one lane fires cp.async.bulk shared->global stores, one per destination pool
+//                           (local pool + peer-mapped pools: the fused fan-out), no register traffic;
+//       F32/F16 -> BF16   : ld.shared.v4, cvt.rn.bf16x2.f32, st.global.v4 (16 B per lane, coalesced);
+//       Q4_K -> BF16      : one warp per 256-weight super-block; the 8 (scale,min) pairs are decoded once
+//                           and handed to the lanes with __shfl_sync; nibbles become floats with a PRMT
+//                           + FADD magic-number trick; every lane stores 16 B of bf16;
+//       2-D transposes    : shared-memory tile transpose (GPT-2 Conv1D weights).
+//   Every output vector is stored to n_dst pools; dst[1..] are NVLink peer mappings, so conversion and
+//   broadcast are ONE kernel and the source bytes are read from HBM exactly once.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "kk_kernels.cuh"
+
+namespace kk {
+
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kConsumerWarps = 8;
+constexpr int kConsumerThreads = kConsumerWarps * 32;
+constexpr int kThreads = 32 + kConsumerThreads;  // 288
+constexpr uint32_t kStageBytes = KK_TILE_SRC_BYTES + KK_STAGE_PAD;
+
+struct __align__(16) TileDesc {
+  uint32_t op;
+  uint32_t pay_off;  // payload offset inside the stage buffer (0..15 for TMA tiles)
+  uint32_t n_units;  // units in this tile (bytes / elements / blocks); transposes: rows | cols<<16
+  uint32_t bulk;     // 1: aligned copy, bulk-store from shared memory
+  uint64_t dst_off;  // pool byte offset of the tile's first output (transposes: dst tensor origin)
+  uint64_t src_off;  // transposes: byte offset of source element (r0, c0) from L.src
+  uint32_t C;        // transposes: source columns
+  uint32_t R;        // transposes: destination row length
+  uint32_t col0;     // transposes: first source column of the tile
+  uint32_t row0;     // transposes: first destination column (= global source row) of the tile
+  uint32_t pad[4];
+};
+static_assert(sizeof(TileDesc) == 64, "TileDesc");
+
+constexpr uint32_t kSmemFixed = kStages * kStageBytes + kStages * sizeof(TileDesc) + 2 * kStages * 8;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "KK_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra KK_DONE_%=;\n\t"
+      "bra KK_WAIT_%=;\n\t"
+      "KK_DONE_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy (TMA, non-tensor form). src, dst and bytes are multiples of 16.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// shared -> global bulk copy.
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void stg128(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void stmm128(void* p, const uint4& v) {  // NVLS multicast store
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(__uint_as_float(v.x)),
+               "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+               : "memory");
+}
+__device__ __forceinline__ void named_bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
+
+// Two floats -> packed bf16x2 (a in the low half), round-to-nearest-even; NaN -> 0x7FFF.
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ uint16_t to_bf16(float a) { return (uint16_t)(pack_bf16x2(a, 0.f) & 0xFFFFu); }
+
+struct Dsts {
+  uint8_t* p[KK_MAX_DST];
+  uint32_t n;
+  bool multimem;
+};
+
+// 16-byte store of one output vector to every destination pool.
+__device__ __forceinline__ void store16_all(const Dsts& D, uint64_t off, const uint4& v) {
+  if (D.multimem) {
+    stmm128(D.p[0] + off, v);
+    return;
+  }
+#pragma unroll
+  for (int d = 0; d < KK_MAX_DST; ++d)
+    if (d < (int)D.n) stg128(D.p[d] + off, v);
+}
+__device__ __forceinline__ void store2_all(const Dsts& D, uint64_t off, uint16_t v) {
+  if (D.multimem) {
+    // multimem.st has no 16-bit form: scalar tails go through a 32-bit read-free path is impossible, so
+    // the host never selects multimem for launches whose segments have sub-4-byte tails (planner rule).
+    return;
+  }
+#pragma unroll
+  for (int d = 0; d < KK_MAX_DST; ++d)
+    if (d < (int)D.n) *reinterpret_cast<uint16_t*>(D.p[d] + off) = v;
+}
+__device__ __forceinline__ void store1_all(const Dsts& D, uint64_t off, uint8_t v) {
+  if (D.multimem) return;
+#pragma unroll
+  for (int d = 0; d < KK_MAX_DST; ++d)
+    if (d < (int)D.n) D.p[d][off] = v;
+}
+__device__ __forceinline__ void store4_all(const Dsts& D, uint64_t off, uint32_t v) {
+  if (D.multimem) {
+    asm volatile("multimem.st.weak.global.b32 [%0], %1;" ::"l"(D.p[0] + off), "r"(v) : "memory");
+    return;
+  }
+#pragma unroll
+  for (int d = 0; d < KK_MAX_DST; ++d)
+    if (d < (int)D.n) *reinterpret_cast<uint32_t*>(D.p[d] + off) = v;
+}
+
+// ---- consumer bodies --------------------------------------------------------------------------
+// ctid: 0..255 within the consumer warps.
+
+__device__ __forceinline__ void consume_copy(const Dsts& D, uint32_t pay, uint32_t n, uint64_t dst_off, int ctid) {
+  const uint32_t nvec = n >> 4;
+  if ((pay & 15u) == 0) {
+    for (uint32_t i = ctid; i < nvec; i += kConsumerThreads) store16_all(D, dst_off + ((uint64_t)i << 4), lds128(pay + (i << 4)));
+  } else {
+    for (uint32_t i = ctid; i < nvec; i += kConsumerThreads) {
+      uint32_t w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint32_t a = pay + (i << 4) + 4 * k;
+        w[k] = lds8(a) | (lds8(a + 1) << 8) | (lds8(a + 2) << 16) | (lds8(a + 3) << 24);
+      }
+      store16_all(D, dst_off + ((uint64_t)i << 4), make_uint4(w[0], w[1], w[2], w[3]));
+    }
+  }
+  const uint32_t tail = n & 15u;
+  if (ctid < (int)tail) store1_all(D, dst_off + ((uint64_t)nvec << 4) + ctid, (uint8_t)lds8(pay + (nvec << 4) + ctid));
+}
+
+__device__ __forceinline__ float lds_f32_any(uint32_t a) {
+  uint32_t w;
+  if ((a & 3u) == 0) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(a));
+  else w = lds8(a) | (lds8(a + 1) << 8) | (lds8(a + 2) << 16) | (lds8(a + 3) << 24);
+  return __uint_as_float(w);
+}
+__device__ __forceinline__ float lds_f16_any(uint32_t a) {
+  uint32_t h;
+  if ((a & 1u) == 0) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(h) : "r"(a));
+  else h = lds8(a) | (lds8(a + 1) << 8);
+  return __half2float(__ushort_as_half((unsigned short)h));
+}
+
+__device__ __forceinline__ void consume_f32(const Dsts& D, uint32_t pay, uint32_t n, uint64_t dst_off, int ctid) {
+  const uint32_t ngrp = n >> 3;  // 8 elements -> 16 B out
+  if ((pay & 15u) == 0) {
+    for (uint32_t g = ctid; g < ngrp; g += kConsumerThreads) {
+      uint4 a = lds128(pay + (g << 5)), b = lds128(pay + (g << 5) + 16);
+      uint4 o;
+      o.x = pack_bf16x2(__uint_as_float(a.x), __uint_as_float(a.y));
+      o.y = pack_bf16x2(__uint_as_float(a.z), __uint_as_float(a.w));
+      o.z = pack_bf16x2(__uint_as_float(b.x), __uint_as_float(b.y));
+      o.w = pack_bf16x2(__uint_as_float(b.z), __uint_as_float(b.w));
+      store16_all(D, dst_off + ((uint64_t)g << 4), o);
+    }
+  } else {
+    for (uint32_t g = ctid; g < ngrp; g += kConsumerThreads) {
+      float f[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = lds_f32_any(pay + (g << 5) + 4 * k);
+      store16_all(D, dst_off + ((uint64_t)g << 4),
+                  make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7])));
+    }
+  }
+  const uint32_t tail = n & 7u, base = ngrp << 3;
+  if (ctid < (int)tail) store2_all(D, dst_off + 2ull * (base + ctid), to_bf16(lds_f32_any(pay + 4 * (base + ctid))));
+}
+
+__device__ __forceinline__ void consume_f16(const Dsts& D, uint32_t pay, uint32_t n, uint64_t dst_off, int ctid) {
+  const uint32_t ngrp = n >> 3;
+  if ((pay & 15u) == 0) {
+    for (uint32_t g = ctid; g < ngrp; g += kConsumerThreads) {
+      uint4 a = lds128(pay + (g << 4));
+      const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+        o[k] = pack_bf16x2(f.x, f.y);
+      }
+      store16_all(D, dst_off + ((uint64_t)g << 4), make_uint4(o[0], o[1], o[2], o[3]));
+    }
+  } else {
+    for (uint32_t g = ctid; g < ngrp; g += kConsumerThreads) {
+      float f[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = lds_f16_any(pay + (g << 4) + 2 * k);
+      store16_all(D, dst_off + ((uint64_t)g << 4),
+                  make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7])));
+    }
+  }
+  const uint32_t tail = n & 7u, base = ngrp << 3;
+  if (ctid < (int)tail) store2_all(D, dst_off + 2ull * (base + ctid), to_bf16(lds_f16_any(pay + 2 * (base + ctid))));
+}
+
+// Q4_K super-block (144 B): d f16 | dmin f16 | scales[12] | qs[128]  ->  256 bf16.
+// y = (d*sc_j)*q - (dmin*m_j), every product and the difference rounded to fp32 separately (no FMA
+// contraction) so the result is bit-identical to the oracle's gguf-py restatement, then RNE to bf16.
+__device__ __forceinline__ void consume_q4k(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
+  const bool al = (pay & 15u) == 0;
+  for (uint32_t b = cwarp; b < nblk; b += kConsumerWarps) {
+    const uint32_t blk = pay + b * KK_Q4K_BLOCK_BYTES;
+    uint32_t h0, s0, s1, s2;
+    if (al) {
+      uint4 h = lds128(blk);
+      h0 = h.x; s0 = h.y; s1 = h.z; s2 = h.w;
+    } else {
+      uint32_t w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) w[k] = lds8(blk + 4 * k) | (lds8(blk + 4 * k + 1) << 8) | (lds8(blk + 4 * k + 2) << 16) | (lds8(blk + 4 * k + 3) << 24);
+      h0 = w[0]; s0 = w[1]; s1 = w[2]; s2 = w[3];
+    }
+    const float d = __half2float(__ushort_as_half((unsigned short)(h0 & 0xFFFFu)));
+    const float dmin = __half2float(__ushort_as_half((unsigned short)(h0 >> 16)));
+    // (scale, min) of sub-block j = lane & 7, decoded by every lane (no divergence), then distributed.
+    const int j = lane & 7, sh = (j & 3) * 8;
+    const uint32_t b_lo = (s0 >> sh) & 0xFFu, b_mid = (s1 >> sh) & 0xFFu, b_hi = (s2 >> sh) & 0xFFu;
+    const uint32_t sc = (j < 4) ? (b_lo & 63u) : ((b_hi & 0xFu) | ((b_lo >> 6) << 4));
+    const uint32_t mn = (j < 4) ? (b_mid & 63u) : ((b_hi >> 4) | ((b_mid >> 6) << 4));
+    const float dsc_j = __fmul_rn(d, (float)sc);
+    const float dmn_j = __fmul_rn(dmin, (float)mn);
+    const int myj = lane >> 2;  // this lane's 8 outputs live in sub-block myj
+    const float dsc = __shfl_sync(0xffffffffu, dsc_j, myj);
+    const float dmn = __shfl_sync(0xffffffffu, dmn_j, myj);
+    // 8 quant bytes: chunk c = myj/2 (32 bytes hold sub-blocks 2c (low nibbles) and 2c+1 (high nibbles)).
+    const uint32_t qa = blk + 16 + 32 * (myj >> 1) + 8 * (lane & 3);
+    uint32_t q0, q1;
+    if (al) {
+      uint2 q = lds64(qa);
+      q0 = q.x; q1 = q.y;
+    } else {
+      q0 = lds8(qa) | (lds8(qa + 1) << 8) | (lds8(qa + 2) << 16) | (lds8(qa + 3) << 24);
+      q1 = lds8(qa + 4) | (lds8(qa + 5) << 8) | (lds8(qa + 6) << 16) | (lds8(qa + 7) << 24);
+    }
+    const int nsh = (myj & 1) * 4;
+    q0 = (q0 >> nsh) & 0x0F0F0F0Fu;
+    q1 = (q1 >> nsh) & 0x0F0F0F0Fu;
+    float y[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      // 0x4B0000qq is the float 2^23 + q; subtracting 2^23 gives q exactly (PRMT + FADD, no I2F).
+      const uint32_t bits = __byte_perm(k < 4 ? q0 : q1, 0x4B000000u, 0x7440u | (uint32_t)(k & 3));
+      const float q = __fsub_rn(__uint_as_float(bits), 8388608.0f);
+      y[k] = __fsub_rn(__fmul_rn(dsc, q), dmn);
+    }
+    store16_all(D, dst_off + (uint64_t)b * 512u + (uint32_t)lane * 16u,
+                make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7])));
+  }
+}
+
+// 2-D transpose tile read straight from global memory (source rows may be arbitrarily aligned).
+template <int ES, int OES, int CONV>  // CONV: 0 verbatim, 1 f32->bf16, 2 f16->bf16
+__device__ __forceinline__ void consume_transpose(const Dsts& D, const uint8_t* src, const TileDesc& t, uint32_t scratch, int ctid) {
+  const uint32_t nr = t.n_units & 0xFFFFu, nc = t.n_units >> 16;
+  const uint8_t* s0 = src + t.src_off;
+  for (uint32_t i = ctid; i < KK_T_ROWS * KK_T_COLS; i += kConsumerThreads) {
+    const uint32_t r = i / KK_T_COLS, c = i % KK_T_COLS;
+    if (r < nr && c < nc) {
+      const uint8_t* p = s0 + ((uint64_t)r * t.C + c) * ES;
+      uint32_t w = 0;
+      if (((uintptr_t)p & (ES - 1)) == 0) {
+        if (ES == 4) w = *reinterpret_cast<const uint32_t*>(p);
+        else w = *reinterpret_cast<const uint16_t*>(p);
+      } else {
+#pragma unroll
+        for (int k = 0; k < ES; ++k) w |= (uint32_t)p[k] << (8 * k);
+      }
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(scratch + 4 * (c * (KK_T_ROWS + 1) + r)), "r"(w) : "memory");
+    }
+  }
+  named_bar_consumers();
+  for (uint32_t i = ctid; i < KK_T_ROWS * KK_T_COLS; i += kConsumerThreads) {
+    const uint32_t c = i / KK_T_ROWS, r = i % KK_T_ROWS;
+    if (r < nr && c < nc) {
+      uint32_t w;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(scratch + 4 * (c * (KK_T_ROWS + 1) + r)));
+      const uint64_t off = t.dst_off + ((uint64_t)(t.col0 + c) * t.R + t.row0 + r) * OES;
+      if (CONV == 1) store2_all(D, off, to_bf16(__uint_as_float(w)));
+      else if (CONV == 2) store2_all(D, off, to_bf16(__half2float(__ushort_as_half((unsigned short)w))));
+      else if (OES == 2) store2_all(D, off, (uint16_t)w);
+      else store4_all(D, off, w);
+    }
+  }
+}
+
+__device__ __forceinline__ KKSeg load_seg(const KKSeg* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+  KKSeg s;
+  s.src_off = ((uint64_t)a.y << 32) | a.x;
+  s.dst_off = ((uint64_t)a.w << 32) | a.z;
+  s.units = ((uint64_t)b.y << 32) | b.x;
+  s.op = b.z;
+  s.tile_begin = b.w;
+  s.p0 = c.x; s.p1 = c.y; s.p2 = c.z; s.p3 = c.w;
+  return s;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLaunch L) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* stage_buf = smem;
+  TileDesc* descs = reinterpret_cast<TileDesc*>(smem + kStages * kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + kStages * sizeof(TileDesc));
+  uint32_t* tile_begin = reinterpret_cast<uint32_t*>(smem + kSmemFixed);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kStages);
+
+  for (uint32_t i = tid; i < L.n_segs; i += kThreads) tile_begin[i] = L.segs[i].tile_begin;
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, kConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // ===== producer =====
+    if (lane == 0) {
+      uint32_t cur = 0;
+      KKSeg seg = load_seg(L.segs);
+      uint32_t it = 0;
+      for (uint32_t tile = blockIdx.x; tile < L.n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+        mbar_wait(empty0 + 8 * s, ph ^ 1u);
+        uint32_t nxt = cur;
+        while (nxt + 1 < L.n_segs && tile_begin[nxt + 1] <= tile) ++nxt;
+        if (nxt != cur) { cur = nxt; seg = load_seg(L.segs + cur); }
+        const uint32_t t = tile - seg.tile_begin;
+        TileDesc d;
+        d.op = seg.op; d.bulk = 0; d.C = 0; d.R = 0; d.col0 = 0; d.row0 = 0; d.src_off = 0;
+        uint32_t in_bytes = 0;          // source bytes of this tile (TMA ops)
+        uint64_t in_off = 0;            // their offset from L.src
+        switch (seg.op) {
+          case KK_OP_COPY: {
+            const uint64_t o = (uint64_t)t * KK_TILE_SRC_BYTES;
+            const uint64_t rem = seg.units - o;
+            d.n_units = rem < KK_TILE_SRC_BYTES ? (uint32_t)rem : KK_TILE_SRC_BYTES;
+            in_bytes = d.n_units; in_off = seg.src_off + o; d.dst_off = seg.dst_off + o;
+            break;
+          }
+          case KK_OP_F32_BF16: {
+            const uint64_t e = (uint64_t)t * (KK_TILE_SRC_BYTES / 4);
+            const uint64_t rem = seg.units - e;
+            d.n_units = rem < KK_TILE_SRC_BYTES / 4 ? (uint32_t)rem : KK_TILE_SRC_BYTES / 4;
+            in_bytes = d.n_units * 4; in_off = seg.src_off + e * 4; d.dst_off = seg.dst_off + e * 2;
+            break;
+          }
+          case KK_OP_F16_BF16: {
+            const uint64_t e = (uint64_t)t * (KK_TILE_SRC_BYTES / 2);
+            const uint64_t rem = seg.units - e;
+            d.n_units = rem < KK_TILE_SRC_BYTES / 2 ? (uint32_t)rem : KK_TILE_SRC_BYTES / 2;
+            in_bytes = d.n_units * 2; in_off = seg.src_off + e * 2; d.dst_off = seg.dst_off + e * 2;
+            break;
+          }
+          case KK_OP_Q4K_BF16: {
+            const uint64_t b = (uint64_t)t * KK_Q4K_TILE_BLOCKS;
+            const uint64_t rem = seg.units - b;
+            d.n_units = rem < KK_Q4K_TILE_BLOCKS ? (uint32_t)rem : KK_Q4K_TILE_BLOCKS;
+            in_bytes = d.n_units * KK_Q4K_BLOCK_BYTES; in_off = seg.src_off + b * KK_Q4K_BLOCK_BYTES;
+            d.dst_off = seg.dst_off + b * 512u;
+            break;
+          }
+          default: {  // transposes: no TMA, consumers read global memory directly
+            const uint32_t C = seg.p0;
+            const uint32_t ct = (C + KK_T_COLS - 1) / KK_T_COLS;
+            const uint32_t tr = t / ct, tc = t % ct;
+            const uint64_t r0 = (uint64_t)tr * KK_T_ROWS;
+            const uint32_t c0 = tc * KK_T_COLS;
+            const uint64_t rrem = seg.units - r0;
+            const uint32_t nr = rrem < KK_T_ROWS ? (uint32_t)rrem : KK_T_ROWS;
+            const uint32_t nc = (C - c0) < KK_T_COLS ? (C - c0) : KK_T_COLS;
+            const uint32_t es = (seg.op == KK_OP_T_F32_BF16 || seg.op == KK_OP_T_B32) ? 4u : 2u;
+            d.n_units = nr | (nc << 16);
+            d.C = C; d.R = seg.p1; d.col0 = c0; d.row0 = seg.p2 + (uint32_t)r0;
+            d.src_off = seg.src_off + (r0 * C + c0) * es;
+            d.dst_off = seg.dst_off;
+            break;
+          }
+        }
+        uint32_t tx = 0;
+        const uint8_t* g = L.src + in_off;
+        if (in_bytes) {
+          const uint32_t mis = (uint32_t)((uintptr_t)g & 15u);
+          d.pay_off = mis;
+          tx = (mis + in_bytes + 15u) & ~15u;
+          if (seg.op == KK_OP_COPY && mis == 0 && (in_bytes & 15u) == 0 && !(L.flags & (KK_LAUNCH_NO_BULK_STORE | KK_LAUNCH_MULTIMEM)))
+            d.bulk = 1;
+          g -= mis;
+        } else {
+          d.pay_off = 0;
+        }
+        descs[s] = d;
+        if (tx) {
+          mbar_arrive_expect_tx(full0 + 8 * s, tx);
+          bulk_g2s(smem_u32(stage_buf + s * kStageBytes), g, tx, full0 + 8 * s);
+        } else {
+          mbar_arrive(full0 + 8 * s);
+        }
+      }
+    }
+  } else {
+    // ===== consumers =====
+    const int cwarp = warp - 1, ctid = tid - 32;
+    Dsts D;
+#pragma unroll
+    for (int i = 0; i < KK_MAX_DST; ++i) D.p[i] = L.dst[i];
+    D.n = L.n_dst;
+    D.multimem = (L.flags & KK_LAUNCH_MULTIMEM) != 0;
+    int pending = -1;  // stage whose bulk stores may still be reading shared memory (warp 1 lane 0 only)
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < L.n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+      mbar_wait(full0 + 8 * s, ph);
+      const TileDesc t = descs[s];
+      const uint32_t sbase = smem_u32(stage_buf + s * kStageBytes);
+      const uint32_t pay = sbase + t.pay_off;
+      if (t.bulk) {
+        if (cwarp == 0) {
+          if (lane == 0) {
+            fence_proxy_async();
+#pragma unroll
+            for (int dd = 0; dd < KK_MAX_DST; ++dd)
+              if (dd < (int)D.n) bulk_s2g(D.p[dd] + t.dst_off, pay, t.n_units);
+            bulk_commit();
+            if (pending >= 0) {
+              bulk_wait_read<1>();
+              mbar_arrive(empty0 + 8 * pending);
+            }
+            pending = (int)s;
+          }
+        } else {
+          if (lane == 0) mbar_arrive(empty0 + 8 * s);
+        }
+        continue;
+      }
+      if (cwarp == 0 && lane == 0 && pending >= 0) {
+        bulk_wait_read<0>();
+        mbar_arrive(empty0 + 8 * pending);
+        pending = -1;
+      }
+      switch (t.op) {
+        case KK_OP_COPY: consume_copy(D, pay, t.n_units, t.dst_off, ctid); break;
+        case KK_OP_F32_BF16: consume_f32(D, pay, t.n_units, t.dst_off, ctid); break;
+        case KK_OP_F16_BF16: consume_f16(D, pay, t.n_units, t.dst_off, ctid); break;
+        case KK_OP_Q4K_BF16: consume_q4k(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
+        case KK_OP_T_F32_BF16: consume_transpose<4, 2, 1>(D, L.src, t, sbase, ctid); break;
+        case KK_OP_T_F16_BF16: consume_transpose<2, 2, 2>(D, L.src, t, sbase, ctid); break;
+        case KK_OP_T_B16: consume_transpose<2, 2, 0>(D, L.src, t, sbase, ctid); break;
+        case KK_OP_T_B32: consume_transpose<4, 4, 0>(D, L.src, t, sbase, ctid); break;
+        default: break;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty0 + 8 * s);
+    }
+    if (cwarp == 0 && lane == 0) {
+      if (pending >= 0) {
+        bulk_wait_read<0>();
+        mbar_arrive(empty0 + 8 * pending);
+      }
+      bulk_wait_all();  // all bulk stores globally performed before the CTA retires
+    }
+  }
+}
+
+// ---- checksum ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27; x *= 0x94d049bb133111ebull;
+  x ^= x >> 31;
+  return x;
+}
+
+__global__ void __launch_bounds__(256) kk_checksum_kernel(const uint8_t* __restrict__ p, uint64_t nbytes, unsigned long long* out) {
+  const uint64_t nwords = nbytes >> 3;
+  const uint64_t* w = reinterpret_cast<const uint64_t*>(p);
+  uint64_t acc = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (uint64_t)gridDim.x * blockDim.x)
+    acc += mix64(__ldg(w + i) + i * 0x9E3779B97F4A7C15ull);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && (nbytes & 7)) {
+    uint64_t last = 0;
+    for (uint32_t k = 0; k < (nbytes & 7); ++k) last |= (uint64_t)p[(nwords << 3) + k] << (8 * k);
+    acc += mix64(last + nwords * 0x9E3779B97F4A7C15ull);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, (unsigned long long)acc);
+}
+
+__global__ void __launch_bounds__(256) kk_ldg_copy_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, uint64_t nvec) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < nvec; i += 4 * stride) {
+    uint4 a = __ldcs(src + i), b = __ldcs(src + i + stride), c = __ldcs(src + i + 2 * stride), d = __ldcs(src + i + 3 * stride);
+    __stcs(dst + i, a); __stcs(dst + i + stride, b); __stcs(dst + i + 2 * stride, c); __stcs(dst + i + 3 * stride, d);
+  }
+  for (; i < nvec; i += stride) __stcs(dst + i, __ldcs(src + i));
+}
+
+}  // namespace
+
+cudaError_t kernels_init_device() {
+  return cudaFuncSetAttribute(kk_convert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)(kSmemFixed + 4 * kMaxSegsPerLaunch + 128));
+}
+
+cudaError_t launch_convert(const ConvertLaunch& L, int sm_count, cudaStream_t stream) {
+  if (L.n_tiles == 0) return cudaSuccess;
+  if (L.n_segs == 0 || L.n_segs > kMaxSegsPerLaunch || L.n_dst == 0 || L.n_dst > KK_MAX_DST) return cudaErrorInvalidValue;
+  const uint32_t grid = L.n_tiles < (uint32_t)sm_count ? L.n_tiles : (uint32_t)sm_count;
+  const size_t smem = kSmemFixed + 4 * (size_t)L.n_segs + 16;
+  kk_convert_kernel<<<grid, kThreads, smem, stream>>>(L);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_checksum(const uint8_t* p, uint64_t nbytes, unsigned long long* out, int sm_count, cudaStream_t stream) {
+  if (nbytes == 0) return cudaSuccess;
+  uint64_t want = (nbytes / 8 + 255) / 256;
+  uint32_t grid = (uint32_t)(want < (uint64_t)sm_count * 8 ? (want ? want : 1) : (uint64_t)sm_count * 8);
+  kk_checksum_kernel<<<grid, 256, 0, stream>>>(p, nbytes, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ldg_copy(const uint8_t* src, uint8_t* dst, uint64_t nbytes, int sm_count, cudaStream_t stream) {
+  if (nbytes == 0) return cudaSuccess;
+  if ((nbytes & 15) || ((uintptr_t)src & 15) || ((uintptr_t)dst & 15)) return cudaErrorInvalidValue;
+  kk_ldg_copy_kernel<<<sm_count * 8, 256, 0, stream>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), nbytes >> 4);
+  return cudaGetLastError();
+}
+
+}  // namespace kk

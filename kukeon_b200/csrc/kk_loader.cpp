@@ -1,0 +1,659 @@
+// Host side of the loader: staging pipeline (pread -> pinned ring -> H2D -> convert/fan-out kernel),
+// pool allocation, refcounted model registry, IPC export, resident-image measurement mode.
+//
+// Pipeline per ingesting device:
+//   R reader threads, each with its own CUDA stream and >= 2 pinned slots (+ matching device staging
+//   buffers).  A thread claims the next chunk, waits for its slot's previous kernel (event), preads the
+//   chunk's file ranges into the pinned slot, enqueues H2D + the convert kernel on its stream and moves
+//   on.  Disk/page-cache reads, PCIe DMA and the kernels of different threads overlap.  The kernel writes
+//   bf16 into the local pool and, in BROADCAST mode, into every peer pool over NVLink in the same pass.
+#include "kk_loader.hpp"
+
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cstring>
+#include <exception>
+#include <sstream>
+#include <thread>
+
+#include "kk_json.hpp"
+
+namespace kk {
+
+namespace {
+
+double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct FdSet {
+  std::vector<int> fds;
+  explicit FdSet(const std::vector<std::string>& paths) {
+    for (auto& p : paths) {
+      int fd = ::open(p.c_str(), O_RDONLY | O_CLOEXEC);
+      if (fd < 0) {
+        int e = errno;
+        for (int f : fds) ::close(f);
+        fail(e == ENOENT ? KK_ENOENT : KK_EIO, "open %s: %s", p.c_str(), strerror(e));
+      }
+      fds.push_back(fd);
+    }
+  }
+  ~FdSet() {
+    for (int f : fds) ::close(f);
+  }
+};
+
+void pread_full(int fd, uint8_t* dst, uint64_t len, uint64_t off, const std::string& name) {
+  while (len) {
+    ssize_t r = ::pread(fd, dst, len > (1ull << 30) ? (1ull << 30) : len, (off_t)off);
+    if (r < 0) {
+      if (errno == EINTR) continue;
+      fail(KK_EIO, "pread %s @%llu: %s", name.c_str(), (unsigned long long)off, strerror(errno));
+    }
+    if (r == 0) fail(KK_EIO, "pread %s @%llu: unexpected end of file", name.c_str(), (unsigned long long)off);
+    dst += r;
+    off += (uint64_t)r;
+    len -= (uint64_t)r;
+  }
+}
+
+struct ErrorSink {
+  std::mutex mu;
+  std::exception_ptr first;
+  std::atomic<bool> stop{false};
+  void capture() {
+    std::lock_guard<std::mutex> g(mu);
+    if (!first) first = std::current_exception();
+    stop = true;
+  }
+  void rethrow() {
+    if (first) std::rethrow_exception(first);
+  }
+};
+
+// Fill the slot with the chunk's file bytes.
+void read_chunk(const Chunk& c, const FdSet& fds, const Index& ix, uint8_t* pinned) {
+  for (auto& r : c.reads) pread_full(fds.fds[c.shard], pinned + r.buf_off, r.len, r.file_off, ix.shards[c.shard]);
+}
+
+uint64_t seg_base_of(const Plan& P, int part) {
+  uint64_t b = 0;
+  for (int i = 0; i < part; ++i) b += P.parts[(size_t)i].segs.size();
+  return b;
+}
+
+// Destination pools a convert launch on local device `li` writes to.
+void fill_dsts(kk_model* m, int li, ConvertLaunch& L) {
+  L.n_dst = 0;
+  L.flags = 0;
+  for (auto& d : L.dst) d = nullptr;
+  L.dst[L.n_dst++] = m->pools[(size_t)li];
+  if (m->plan.mode != KK_MODE_BROADCAST) return;
+  if (m->opts.fanout == KK_FANOUT_NONE) return;
+  if (m->opts.part_count > 1) {
+    for (int r = 0; r < KK_MAX_DEVICES; ++r)
+      if (m->peer_ptr[r]) L.dst[L.n_dst++] = (uint8_t*)m->peer_ptr[r];
+  } else if (m->ctx->peer_ok) {
+    for (size_t j = 0; j < m->pools.size(); ++j)
+      if ((int)j != li) L.dst[L.n_dst++] = m->pools[j];
+  }
+}
+
+// Ingest plan part `part` on local device `li`.
+void run_part(kk_model* m, int li, int part, const FdSet& fds) {
+  kk_ctx* c = m->ctx;
+  Device& dev = c->devs[(size_t)m->dev_idx[(size_t)li]];
+  const PartPlan& pp = m->plan.parts[(size_t)part];
+  if (pp.chunks.empty()) return;
+  const KKSeg* d_segs = m->d_segs[(size_t)li] + seg_base_of(m->plan, part);
+  ConvertLaunch base{};
+  fill_dsts(m, li, base);
+  const bool zerocopy = (c->cfg.flags & KK_CFG_ZEROCOPY) != 0;
+  std::atomic<size_t> next{0};
+  ErrorSink sink;
+  auto worker = [&](Reader* rd) {
+    try {
+      KK_CUDA(cudaSetDevice(dev.ordinal));
+      size_t k = 0;
+      for (;;) {
+        if (sink.stop) break;
+        size_t ci = next.fetch_add(1);
+        if (ci >= pp.chunks.size()) break;
+        const Chunk& ch = pp.chunks[ci];
+        Slot& s = rd->slots[k++ % rd->slots.size()];
+        KK_CUDA(cudaEventSynchronize(s.done));
+        read_chunk(ch, fds, m->plan.index, s.pinned);
+        ConvertLaunch L = base;
+        if (zerocopy) {
+          L.src = s.pinned;
+        } else {
+          KK_CUDA(cudaMemcpyAsync(s.dev, s.pinned, ch.buf_bytes, cudaMemcpyHostToDevice, rd->stream));
+          L.src = s.dev;
+        }
+        L.segs = d_segs + ch.seg_begin;
+        L.n_segs = ch.seg_count;
+        L.n_tiles = ch.n_tiles;
+        KK_CUDA(launch_convert(L, dev.sm_count, rd->stream));
+        KK_CUDA(cudaEventRecord(s.done, rd->stream));
+      }
+      KK_CUDA(cudaStreamSynchronize(rd->stream));
+    } catch (...) {
+      sink.capture();
+    }
+  };
+  std::vector<std::thread> th;
+  for (size_t r = 1; r < dev.readers.size(); ++r) th.emplace_back(worker, &dev.readers[r]);
+  worker(&dev.readers[0]);
+  for (auto& t : th) t.join();
+  if (sink.first) {
+    // leave the streams quiet before reporting
+    cudaSetDevice(dev.ordinal);
+    for (auto& r : dev.readers) cudaStreamSynchronize(r.stream);
+  }
+  sink.rethrow();
+}
+
+void free_resident(kk_model* m) {
+  for (size_t li = 0; li < m->resident.size(); ++li) {
+    auto& R = m->resident[li];
+    if (R.image || R.d_segs) {
+      cudaSetDevice(m->ctx->devs[(size_t)m->dev_idx[li]].ordinal);
+      if (R.image) cudaFree(R.image);
+      if (R.d_segs) cudaFree(R.d_segs);
+    }
+  }
+  m->resident.clear();
+}
+
+void destroy_model(kk_model* m) {
+  kk_ctx* c = m->ctx;
+  free_resident(m);
+  for (int r = 0; r < KK_MAX_DEVICES; ++r)
+    if (m->peer_ptr[r]) {
+      cudaSetDevice(c->devs[(size_t)m->dev_idx[0]].ordinal);
+      cudaIpcCloseMemHandle(m->peer_ptr[r]);
+      m->peer_ptr[r] = nullptr;
+    }
+  for (size_t i = 0; i < m->pools.size(); ++i) {
+    Device& d = c->devs[(size_t)m->dev_idx[i]];
+    cudaSetDevice(d.ordinal);
+    if (m->pools[i]) {
+      cudaFree(m->pools[i]);
+      d.pool_in_use -= m->pool_bytes[i];
+    }
+    if (i < m->d_segs.size() && m->d_segs[i]) cudaFree(m->d_segs[i]);
+  }
+  delete m;
+}
+
+std::string canon(const std::string& p) {
+  char buf[4096];
+  if (realpath(p.c_str(), buf)) return buf;
+  return p;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+kk_ctx* ctx_open(const kk_config& cfg_in) {
+  kk_config cfg = cfg_in;
+  if (cfg.n_devices < 1 || cfg.n_devices > KK_MAX_DEVICES) fail(KK_EINVAL, "n_devices %d out of range 1..%d", cfg.n_devices, KK_MAX_DEVICES);
+  for (int i = 0; i < cfg.n_devices; ++i)
+    for (int j = 0; j < i; ++j)
+      if (cfg.devices[i] == cfg.devices[j]) fail(KK_EINVAL, "device %d listed twice", cfg.devices[i]);
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    fail(KK_ECUDA, "no usable CUDA device (%s); this library has no CPU path", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  for (int i = 0; i < cfg.n_devices; ++i)
+    if (cfg.devices[i] < 0 || cfg.devices[i] >= count) fail(KK_EINVAL, "device ordinal %d not present (%d devices)", cfg.devices[i], count);
+  if (cfg.n_staging_buffers == 0) cfg.n_staging_buffers = 8;
+  if (cfg.n_reader_threads == 0) cfg.n_reader_threads = 4;
+  if (cfg.n_reader_threads > 64) fail(KK_EINVAL, "n_reader_threads %u too large", cfg.n_reader_threads);
+  if (cfg.n_staging_buffers < cfg.n_reader_threads) cfg.n_staging_buffers = cfg.n_reader_threads;
+  if (cfg.staging_buffer_bytes == 0) cfg.staging_buffer_bytes = 64ull << 20;
+  if (cfg.staging_buffer_bytes < (1ull << 20)) fail(KK_EINVAL, "staging_buffer_bytes must be at least 1 MiB");
+
+  std::unique_ptr<kk_ctx> c(new kk_ctx);
+  c->cfg = cfg;
+  c->slot_bytes = align_up(cfg.staging_buffer_bytes, 2ull << 20);
+  c->devs.resize((size_t)cfg.n_devices);
+  try {
+    for (int i = 0; i < cfg.n_devices; ++i) {
+      Device& d = c->devs[(size_t)i];
+      d.ordinal = cfg.devices[i];
+      KK_CUDA(cudaSetDevice(d.ordinal));
+      cudaDeviceProp prop;
+      KK_CUDA(cudaGetDeviceProperties(&prop, d.ordinal));
+      if (prop.major < 10) fail(KK_EUNSUPPORTED, "device %d is sm_%d%d; this build carries sm_100a code only", d.ordinal, prop.major, prop.minor);
+      d.sm_count = prop.multiProcessorCount;
+      KK_CUDA(kernels_init_device());
+      d.kernels_ready = true;
+      KK_CUDA(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+      d.readers.resize(cfg.n_reader_threads);
+      for (uint32_t r = 0; r < cfg.n_reader_threads; ++r) {
+        Reader& rd = d.readers[r];
+        KK_CUDA(cudaStreamCreateWithFlags(&rd.stream, cudaStreamNonBlocking));
+        uint32_t ns = cfg.n_staging_buffers / cfg.n_reader_threads + (r < cfg.n_staging_buffers % cfg.n_reader_threads ? 1 : 0);
+        rd.slots.resize(ns);
+        for (auto& s : rd.slots) {
+          KK_CUDA(cudaHostAlloc((void**)&s.pinned, c->slot_bytes + 256, cudaHostAllocPortable | cudaHostAllocMapped));
+          if (!(cfg.flags & KK_CFG_ZEROCOPY)) KK_CUDA(cudaMalloc((void**)&s.dev, c->slot_bytes + 256));
+          KK_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        }
+      }
+    }
+    c->peer_ok = cfg.n_devices > 1 && !(cfg.flags & KK_CFG_NO_PEER_ACCESS);
+    if (c->peer_ok) {
+      for (int i = 0; i < cfg.n_devices && c->peer_ok; ++i)
+        for (int j = 0; j < cfg.n_devices; ++j) {
+          if (i == j) continue;
+          int can = 0;
+          KK_CUDA(cudaDeviceCanAccessPeer(&can, cfg.devices[i], cfg.devices[j]));
+          if (!can) { c->peer_ok = false; break; }
+          KK_CUDA(cudaSetDevice(cfg.devices[i]));
+          cudaError_t pe = cudaDeviceEnablePeerAccess(cfg.devices[j], 0);
+          if (pe == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+          else if (pe != cudaSuccess) { cudaGetLastError(); c->peer_ok = false; break; }
+        }
+    }
+  } catch (...) {
+    ctx_close(c.release());
+    throw;
+  }
+  return c.release();
+}
+
+void ctx_close(kk_ctx* c) {
+  if (!c) return;
+  {
+    std::lock_guard<std::mutex> g(c->mu);
+    if (!c->models.empty()) fail(KK_EBUSY, "%zu model(s) still referenced", c->models.size());
+  }
+  for (auto& d : c->devs) {
+    if (d.ordinal < 0) continue;
+    cudaSetDevice(d.ordinal);
+    for (auto& rd : d.readers) {
+      for (auto& s : rd.slots) {
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.dev) cudaFree(s.dev);
+        if (s.pinned) cudaFreeHost(s.pinned);
+      }
+      if (rd.stream) cudaStreamDestroy(rd.stream);
+    }
+    if (d.stream) cudaStreamDestroy(d.stream);
+  }
+  delete c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// model
+// ---------------------------------------------------------------------------------------------
+static void do_load(kk_model* m) {
+  const double t0 = now_s();
+  FdSet fds(m->plan.index.shards);
+  const size_t nl = m->dev_idx.size();
+  m->t_part.assign(nl, 0.0);
+  const bool multi_proc = m->opts.part_count > 1;
+  const bool replicas = !multi_proc && m->plan.mode == KK_MODE_BROADCAST && nl > 1 &&
+                        (m->opts.fanout == KK_FANOUT_NONE || !m->ctx->peer_ok);
+  ErrorSink sink;
+  auto per_dev = [&](int li) {
+    try {
+      const double a = now_s();
+      if (replicas) {
+        for (int p = 0; p < m->plan.n_parts; ++p) run_part(m, li, p, fds);
+      } else {
+        run_part(m, li, m->local_parts[(size_t)li], fds);
+      }
+      m->t_part[(size_t)li] = now_s() - a;
+    } catch (...) {
+      sink.capture();
+    }
+  };
+  std::vector<std::thread> th;
+  for (size_t li = 1; li < nl; ++li) th.emplace_back(per_dev, (int)li);
+  per_dev(0);
+  for (auto& t : th) t.join();
+  sink.rethrow();
+  m->t_load = now_s() - t0;
+  m->n_loads++;
+}
+
+kk_model* model_load(kk_ctx* c, const std::string& path, const kk_load_opts& opts_in) {
+  kk_load_opts opts = opts_in;
+  if (opts.part_count <= 1) { opts.part_count = 1; opts.part_index = 0; }
+  if (opts.part_index < 0 || opts.part_index >= opts.part_count || opts.part_count > KK_MAX_DEVICES)
+    fail(KK_EINVAL, "part %d of %d out of range", opts.part_index, opts.part_count);
+  if (opts.mode < KK_MODE_SINGLE || opts.mode > KK_MODE_SCATTER) fail(KK_EINVAL, "unknown mode %d", opts.mode);
+  if (opts.fanout < KK_FANOUT_P2P || opts.fanout > KK_FANOUT_RAW) fail(KK_EINVAL, "unknown fanout %d", opts.fanout);
+  if (opts.fanout == KK_FANOUT_NVLS || opts.fanout == KK_FANOUT_RAW)
+    fail(KK_EUNSUPPORTED, "fan-out %s is not available in this build", opts.fanout == KK_FANOUT_NVLS ? "NVLS" : "RAW");
+  const bool multi_proc = opts.part_count > 1;
+  if (multi_proc && c->cfg.n_devices != 1) fail(KK_EINVAL, "multi-process parts need a one-device context (got %d devices)", c->cfg.n_devices);
+  if (multi_proc && opts.mode == KK_MODE_SINGLE) fail(KK_EINVAL, "KK_MODE_SINGLE cannot be split into parts");
+
+  std::ostringstream ks;
+  ks << canon(path) << "|m" << opts.mode << "|f" << opts.fanout << "|x" << (opts.flags & ~KK_LOAD_DEFER) << "|p" << opts.part_index << "/" << opts.part_count;
+  const std::string key = ks.str();
+
+  kk_model* m = nullptr;
+  {
+    std::unique_lock<std::mutex> lk(c->mu);
+    for (;;) {
+      auto it = c->models.find(key);
+      if (it == c->models.end()) break;
+      if (it->second->loading) { c->cv.wait(lk); continue; }
+      it->second->refcount++;
+      return it->second;
+    }
+    m = new kk_model;
+    m->ctx = c;
+    m->key = key;
+    m->opts = opts;
+    m->refcount = 1;
+    m->loading = true;
+    c->models[key] = m;
+  }
+  try {
+    double t0 = now_s();
+    Index ix = index_path(path);
+    m->t_index = now_s() - t0;
+    t0 = now_s();
+    int n_parts = 1;
+    if (opts.mode != KK_MODE_SINGLE) n_parts = multi_proc ? opts.part_count : c->cfg.n_devices;
+    int mode = opts.mode;
+    m->plan = build_plan(std::move(ix), mode, opts.flags & ~KK_LOAD_DEFER, n_parts, c->slot_bytes);
+    m->t_plan = now_s() - t0;
+    t0 = now_s();
+    if (multi_proc || opts.mode == KK_MODE_SINGLE) {
+      m->dev_idx = {0};
+      m->local_parts = {multi_proc ? opts.part_index : 0};
+    } else {
+      for (int i = 0; i < c->cfg.n_devices; ++i) { m->dev_idx.push_back(i); m->local_parts.push_back(i); }
+    }
+    // concatenated segment table of all parts
+    std::vector<KKSeg> all;
+    for (auto& pp : m->plan.parts) all.insert(all.end(), pp.segs.begin(), pp.segs.end());
+    m->pools.assign(m->dev_idx.size(), nullptr);
+    m->pool_bytes.assign(m->dev_idx.size(), 0);
+    m->d_segs.assign(m->dev_idx.size(), nullptr);
+    for (size_t li = 0; li < m->dev_idx.size(); ++li) {
+      Device& d = c->devs[(size_t)m->dev_idx[li]];
+      KK_CUDA(cudaSetDevice(d.ordinal));
+      const uint64_t pb = m->plan.pool_bytes_of_part(m->local_parts[li]);
+      {
+        std::lock_guard<std::mutex> g(c->mu);
+        if (c->cfg.pool_bytes_per_device && d.pool_in_use + pb > c->cfg.pool_bytes_per_device)
+          fail(KK_ENOMEM, "device %d: pool budget exceeded (%llu in use + %llu > %llu)", d.ordinal, (unsigned long long)d.pool_in_use,
+               (unsigned long long)pb, (unsigned long long)c->cfg.pool_bytes_per_device);
+        d.pool_in_use += pb;
+        m->pool_bytes[li] = pb;
+      }
+      cudaError_t e = cudaMalloc((void**)&m->pools[li], pb);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        m->pools[li] = nullptr;
+        std::lock_guard<std::mutex> g(c->mu);
+        d.pool_in_use -= pb;
+        m->pool_bytes[li] = 0;
+        fail(KK_ENOMEM, "device %d: cudaMalloc(%llu) for the pool failed: %s", d.ordinal, (unsigned long long)pb, cudaGetErrorString(e));
+      }
+      if (!all.empty()) {
+        KK_CUDA(cudaMalloc((void**)&m->d_segs[li], all.size() * sizeof(KKSeg)));
+        KK_CUDA(cudaMemcpy(m->d_segs[li], all.data(), all.size() * sizeof(KKSeg), cudaMemcpyHostToDevice));
+      }
+    }
+    m->t_alloc = now_s() - t0;
+    if (!(opts.flags & KK_LOAD_DEFER)) {
+      do_load(m);
+      m->loaded = true;
+    }
+  } catch (...) {
+    {
+      std::lock_guard<std::mutex> g(c->mu);
+      c->models.erase(key);
+    }
+    c->cv.notify_all();
+    destroy_model(m);
+    throw;
+  }
+  {
+    std::lock_guard<std::mutex> g(c->mu);
+    m->loading = false;
+  }
+  c->cv.notify_all();
+  return m;
+}
+
+void model_load_part(kk_model* m) {
+  do_load(m);
+  std::lock_guard<std::mutex> g(m->ctx->mu);
+  m->loaded = true;
+}
+
+void model_release(kk_model* m) {
+  kk_ctx* c = m->ctx;
+  {
+    std::lock_guard<std::mutex> g(c->mu);
+    if (m->refcount <= 0) fail(KK_ESTATE, "release of a model with refcount %d", m->refcount);
+    if (--m->refcount > 0) return;
+    c->models.erase(m->key);
+  }
+  destroy_model(m);
+}
+
+void model_peer_attach(kk_model* m, int rank, const void* handle) {
+  if (m->opts.part_count <= 1) fail(KK_ESTATE, "peer attach needs a multi-process (part_count > 1) model");
+  if (rank < 0 || rank >= m->opts.part_count || rank == m->opts.part_index) fail(KK_EINVAL, "bad peer rank %d", rank);
+  if (m->plan.mode != KK_MODE_BROADCAST) fail(KK_ESTATE, "peer attach only applies to BROADCAST models");
+  if (m->peer_ptr[rank]) fail(KK_ESTATE, "peer rank %d already attached", rank);
+  Device& d = m->ctx->devs[(size_t)m->dev_idx[0]];
+  KK_CUDA(cudaSetDevice(d.ordinal));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  void* p = nullptr;
+  KK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  m->peer_ptr[rank] = p;
+}
+
+void model_peer_detach_all(kk_model* m) {
+  Device& d = m->ctx->devs[(size_t)m->dev_idx[0]];
+  cudaSetDevice(d.ordinal);
+  for (int r = 0; r < KK_MAX_DEVICES; ++r)
+    if (m->peer_ptr[r]) {
+      cudaIpcCloseMemHandle(m->peer_ptr[r]);
+      m->peer_ptr[r] = nullptr;
+    }
+}
+
+int model_local_device(kk_model* m, int ordinal) {
+  for (size_t li = 0; li < m->dev_idx.size(); ++li)
+    if (m->ctx->devs[(size_t)m->dev_idx[li]].ordinal == ordinal) return (int)li;
+  fail(KK_EINVAL, "device %d holds no pool of this model", ordinal);
+}
+
+std::string model_manifest(kk_model* m, int li) {
+  const auto& pl = m->plan.placement_of_part(m->local_parts[(size_t)li]);
+  const auto& T = m->plan.index.tensors;
+  std::ostringstream o;
+  o << "{\"apiVersion\":\"kukeon.gpupool/v1\",\"kind\":\"PoolManifest\",\"device\":" << m->ctx->devs[(size_t)m->dev_idx[(size_t)li]].ordinal
+    << ",\"poolBytes\":" << m->pool_bytes[(size_t)li] << ",\"mode\":" << m->plan.mode << ",\"format\":\"" << m->plan.index.format
+    << "\",\"align\":" << KK_POOL_ALIGN << ",\"tensors\":[";
+  for (size_t i = 0; i < T.size(); ++i) {
+    const DtypeInfo* di = dtype_info(pl[i].dtype);
+    if (i) o << ",";
+    o << "{\"name\":\"" << json_escape(T[i].name) << "\",\"dtype\":\"" << (di ? di->name : "?") << "\",\"shape\":[";
+    for (size_t d = 0; d < pl[i].shape.size(); ++d) o << (d ? "," : "") << pl[i].shape[d];
+    o << "],\"offset\":" << pl[i].pool_offset << ",\"nbytes\":" << pl[i].nbytes;
+    if (pl[i].slice_dim != kNoSlice) o << ",\"sliceDim\":" << pl[i].slice_dim << ",\"sliceBegin\":" << pl[i].slice_begin;
+    o << "}";
+  }
+  o << "]}";
+  return o.str();
+}
+
+std::string model_stats(kk_model* m) {
+  std::ostringstream o;
+  o.precision(9);
+  uint64_t src = 0, out = 0;
+  for (size_t li = 0; li < m->local_parts.size(); ++li) {
+    const PartPlan& pp = m->plan.parts[(size_t)m->local_parts[li]];
+    src += pp.src_bytes;
+    out += pp.out_bytes;
+  }
+  o << "{\"n_tensors\":" << m->plan.index.tensors.size() << ",\"n_shards\":" << m->plan.index.shards.size()
+    << ",\"file_bytes\":" << m->plan.file_bytes << ",\"pool_bytes\":" << m->plan.pool_bytes_of_part(m->local_parts[0])
+    << ",\"n_parts\":" << m->plan.n_parts << ",\"local_src_bytes\":" << src << ",\"local_out_bytes\":" << out
+    << ",\"index_s\":" << m->t_index << ",\"plan_s\":" << m->t_plan << ",\"alloc_s\":" << m->t_alloc << ",\"load_s\":" << m->t_load
+    << ",\"n_loads\":" << m->n_loads << ",\"load_gbps\":" << (m->t_load > 0 ? (double)src / m->t_load / 1e9 : 0.0) << ",\"parts\":[";
+  for (size_t li = 0; li < m->local_parts.size(); ++li) {
+    const int part = m->local_parts[li];
+    const PartPlan& pp = m->plan.parts[(size_t)part];
+    // pool range this part produces (contiguous for SINGLE/BROADCAST because pool order == file order)
+    uint64_t lo = UINT64_MAX, hi = 0;
+    for (auto& s : pp.segs) {
+      uint64_t b = s.dst_off, e;
+      switch (s.op) {
+        case KK_OP_COPY: e = b + s.units; break;
+        case KK_OP_F32_BF16: case KK_OP_F16_BF16: e = b + s.units * 2; break;
+        case KK_OP_Q4K_BF16: e = b + s.units * 512; break;
+        case KK_OP_T_B32: e = b + (uint64_t)s.p0 * s.p1 * 4; break;
+        default: e = b + (uint64_t)s.p0 * s.p1 * 2; break;
+      }
+      if (b < lo) lo = b;
+      if (e > hi) hi = e;
+    }
+    if (lo == UINT64_MAX) lo = 0;
+    uint64_t tiles = 0;
+    for (auto& ch : pp.chunks) tiles += ch.n_tiles;
+    if (li) o << ",";
+    o << "{\"part\":" << part << ",\"device\":" << m->ctx->devs[(size_t)m->dev_idx[li]].ordinal << ",\"chunks\":" << pp.chunks.size()
+      << ",\"segs\":" << pp.segs.size() << ",\"tiles\":" << tiles << ",\"src_bytes\":" << pp.src_bytes << ",\"out_bytes\":" << pp.out_bytes
+      << ",\"pool_lo\":" << lo << ",\"pool_hi\":" << hi << ",\"seconds\":" << (li < m->t_part.size() ? m->t_part[li] : 0.0) << "}";
+  }
+  o << "]}";
+  return o.str();
+}
+
+// ---------------------------------------------------------------------------------------------
+// resident image: kernel-stage measurement with the source bytes already in HBM
+// ---------------------------------------------------------------------------------------------
+void model_stage_resident(kk_model* m) {
+  free_resident(m);
+  kk_ctx* c = m->ctx;
+  FdSet fds(m->plan.index.shards);
+  m->resident.resize(m->dev_idx.size());
+  for (size_t li = 0; li < m->dev_idx.size(); ++li) {
+    Device& dev = c->devs[(size_t)m->dev_idx[li]];
+    KK_CUDA(cudaSetDevice(dev.ordinal));
+    const PartPlan& pp = m->plan.parts[(size_t)m->local_parts[li]];
+    auto& R = m->resident[li];
+    std::vector<uint64_t> img_off(pp.chunks.size());
+    uint64_t tot = 0;
+    for (size_t i = 0; i < pp.chunks.size(); ++i) {
+      img_off[i] = tot;
+      tot += align_up(pp.chunks[i].buf_bytes + 64, 256);
+    }
+    R.image_bytes = tot ? tot : 256;
+    cudaError_t e = cudaMalloc((void**)&R.image, R.image_bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); R.image = nullptr; fail(KK_ENOMEM, "device %d: cudaMalloc(%llu) for the resident image failed", dev.ordinal, (unsigned long long)R.image_bytes); }
+    // copy the chunk bytes exactly as the streaming path stages them
+    Reader& rd = dev.readers[0];
+    size_t k = 0;
+    for (size_t i = 0; i < pp.chunks.size(); ++i) {
+      Slot& s = rd.slots[k++ % rd.slots.size()];
+      KK_CUDA(cudaEventSynchronize(s.done));
+      read_chunk(pp.chunks[i], fds, m->plan.index, s.pinned);
+      KK_CUDA(cudaMemcpyAsync(R.image + img_off[i], s.pinned, pp.chunks[i].buf_bytes, cudaMemcpyHostToDevice, rd.stream));
+      KK_CUDA(cudaEventRecord(s.done, rd.stream));
+    }
+    KK_CUDA(cudaStreamSynchronize(rd.stream));
+    // one launch per shard (split only if a launch would exceed the segment-table limit)
+    std::vector<KKSeg> segs;
+    for (size_t i = 0; i < pp.chunks.size(); ++i) {
+      const Chunk& ch = pp.chunks[i];
+      bool fresh = R.launches.empty() || pp.chunks[i - 1].shard != ch.shard ||
+                   R.launches.back().n_segs + ch.seg_count > kMaxSegsPerLaunch ||
+                   (uint64_t)R.launches.back().n_tiles + ch.n_tiles > 0xFFFFFFF0ull;
+      if (fresh) R.launches.push_back({(uint32_t)segs.size(), 0, 0, 0, 0});
+      auto& L = R.launches.back();
+      for (uint32_t j = 0; j < ch.seg_count; ++j) {
+        KKSeg s = pp.segs[ch.seg_begin + j];
+        s.src_off += img_off[i];
+        s.tile_begin += L.n_tiles;
+        segs.push_back(s);
+      }
+      L.n_segs += ch.seg_count;
+      L.n_tiles += ch.n_tiles;
+      L.src_bytes += ch.src_bytes;
+      L.out_bytes += ch.out_bytes;
+    }
+    // tile_begin above was offset by the launch's tile count *before* adding this chunk: fix ordering
+    // (n_tiles is bumped after the chunk's segments are rebased, so the rebasing is already correct).
+    if (!segs.empty()) {
+      KK_CUDA(cudaMalloc((void**)&R.d_segs, segs.size() * sizeof(KKSeg)));
+      KK_CUDA(cudaMemcpy(R.d_segs, segs.data(), segs.size() * sizeof(KKSeg), cudaMemcpyHostToDevice));
+    }
+  }
+}
+
+void model_unstage_resident(kk_model* m) { free_resident(m); }
+
+void model_convert_resident(kk_model* m, float* ms_total, float* ms_per_launch, size_t cap, size_t* n_launches) {
+  if (m->resident.size() != m->dev_idx.size()) fail(KK_ESTATE, "kk_stage_resident has not been called");
+  kk_ctx* c = m->ctx;
+  const size_t nl = m->dev_idx.size();
+  std::vector<std::vector<cudaEvent_t>> evs(nl);
+  size_t max_launches = 0;
+  // enqueue on every local device first (they run concurrently), then collect
+  for (size_t li = 0; li < nl; ++li) {
+    Device& dev = c->devs[(size_t)m->dev_idx[li]];
+    auto& R = m->resident[li];
+    KK_CUDA(cudaSetDevice(dev.ordinal));
+    evs[li].resize(R.launches.size() + 1);
+    for (auto& e : evs[li]) KK_CUDA(cudaEventCreate(&e));
+    ConvertLaunch base{};
+    fill_dsts(m, (int)li, base);
+    for (size_t k = 0; k < R.launches.size(); ++k) {
+      KK_CUDA(cudaEventRecord(evs[li][k], dev.stream));
+      ConvertLaunch L = base;
+      L.src = R.image;
+      L.segs = R.d_segs + R.launches[k].seg_begin;
+      L.n_segs = R.launches[k].n_segs;
+      L.n_tiles = R.launches[k].n_tiles;
+      KK_CUDA(launch_convert(L, dev.sm_count, dev.stream));
+    }
+    KK_CUDA(cudaEventRecord(evs[li][R.launches.size()], dev.stream));
+    if (R.launches.size() > max_launches) max_launches = R.launches.size();
+  }
+  float worst = 0.f;
+  std::vector<float> per(max_launches, 0.f);
+  for (size_t li = 0; li < nl; ++li) {
+    Device& dev = c->devs[(size_t)m->dev_idx[li]];
+    KK_CUDA(cudaSetDevice(dev.ordinal));
+    KK_CUDA(cudaStreamSynchronize(dev.stream));
+    const size_t n = evs[li].size() - 1;
+    float tot = 0.f;
+    if (n) KK_CUDA(cudaEventElapsedTime(&tot, evs[li][0], evs[li][n]));
+    if (tot > worst) worst = tot;
+    for (size_t k = 0; k < n; ++k) {
+      float ms = 0.f;
+      KK_CUDA(cudaEventElapsedTime(&ms, evs[li][k], evs[li][k + 1]));
+      if (ms > per[k]) per[k] = ms;
+    }
+    for (auto& e : evs[li]) cudaEventDestroy(e);
+  }
+  if (ms_total) *ms_total = worst;
+  if (n_launches) *n_launches = max_launches;
+  if (ms_per_launch)
+    for (size_t k = 0; k < max_launches && k < cap; ++k) ms_per_launch[k] = per[k];
+}
+
+}  // namespace kk

@@ -1,0 +1,110 @@
+// Context (daemon-lifetime GPU pool manager) and model (one resident checkpoint) objects behind the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kk_common.hpp"
+#include "kk_kernels.cuh"
+#include "kk_plan.hpp"
+
+namespace kk {
+
+#define KK_CUDA(expr)                                                                               \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) ::kk::fail(KK_ECUDA, "%s: %s (%s)", #expr, cudaGetErrorString(_e), cudaGetErrorName(_e)); \
+  } while (0)
+
+struct Slot {
+  uint8_t* pinned = nullptr;  // cudaHostAlloc'd, also mapped into the device address space
+  uint8_t* dev = nullptr;     // device staging buffer of the same size
+  cudaEvent_t done = nullptr; // recorded after the convert kernel that consumed this slot
+};
+
+struct Reader {
+  cudaStream_t stream = nullptr;
+  std::vector<Slot> slots;
+};
+
+struct Device {
+  int ordinal = -1;
+  int sm_count = 0;
+  std::vector<Reader> readers;
+  cudaStream_t stream = nullptr;  // resident launches, checksum, misc
+  uint64_t pool_in_use = 0;
+  bool kernels_ready = false;
+};
+
+struct Model;
+
+}  // namespace kk
+
+struct kk_ctx {
+  kk_config cfg{};
+  uint64_t slot_bytes = 0;
+  std::vector<kk::Device> devs;
+  bool peer_ok = false;  // every device pair has peer access enabled
+  std::mutex mu;
+  std::condition_variable cv;
+  std::map<std::string, kk_model*> models;
+};
+
+struct kk_model {
+  kk_ctx* ctx = nullptr;
+  std::string key;
+  kk::Plan plan;
+  kk_load_opts opts{};
+  // local devices that hold a pool, as indices into ctx->devs; local_parts[i] is the plan part device i ingests
+  std::vector<int> dev_idx;
+  std::vector<int> local_parts;
+  std::vector<uint8_t*> pools;       // per local device
+  std::vector<uint64_t> pool_bytes;  // per local device
+  std::vector<KKSeg*> d_segs;        // per local device: device copy of its part's segment table
+  // multi-process fan-out destinations (BROADCAST): IPC-opened peer pools by rank
+  void* peer_ptr[KK_MAX_DEVICES] = {};
+  // resident image (kernel-stage measurement)
+  struct Resident {
+    uint8_t* image = nullptr;
+    uint64_t image_bytes = 0;
+    KKSeg* d_segs = nullptr;
+    struct Launch { uint32_t seg_begin, n_segs, n_tiles; uint64_t src_bytes, out_bytes; };
+    std::vector<Launch> launches;
+  };
+  std::vector<Resident> resident;  // per local device
+  // state
+  int refcount = 0;
+  bool loading = true;
+  bool loaded = false;
+  int load_error = 0;
+  std::string load_error_msg;
+  // stats
+  double t_index = 0, t_plan = 0, t_alloc = 0, t_load = 0;
+  uint64_t n_loads = 0;
+  std::vector<double> t_part;  // per local device wall seconds of the last load
+};
+
+namespace kk {
+
+kk_ctx* ctx_open(const kk_config& cfg);
+void ctx_close(kk_ctx* c);
+
+kk_model* model_load(kk_ctx* c, const std::string& path, const kk_load_opts& opts);
+void model_load_part(kk_model* m);
+void model_release(kk_model* m);
+void model_peer_attach(kk_model* m, int rank, const void* handle);
+void model_peer_detach_all(kk_model* m);
+int model_local_device(kk_model* m, int ordinal);  // index into m->dev_idx or throws
+std::string model_manifest(kk_model* m, int local);
+std::string model_stats(kk_model* m);
+void model_stage_resident(kk_model* m);
+void model_unstage_resident(kk_model* m);
+void model_convert_resident(kk_model* m, float* ms_total, float* ms_per_launch, size_t cap, size_t* n_launches);
+
+}  // namespace kk
