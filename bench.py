@@ -1,0 +1,473 @@
+#!/usr/bin/env python
+"""bench.py — model-load throughput of the kukeon GPU weight loader (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm  (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the oracle port on host cores
+
+Workload (config.workload): Llama-3-8B bf16, 291 tensors / 4 safetensors shards / 16,060,522,496 B, synthetic
+content, files warm in tmpfs/page cache.  A "step" = one pass of the hot path over the whole checkpoint:
+
+* `value`  (GB/s): kernel stage with the checkpoint bytes already resident in HBM — one convert/fan-out launch
+  per shard, timed with CUDA events on the launching stream inside the library (kk_convert_resident), max over
+  ranks.  At N > 1 every rank converts 1/N of the checkpoint and the same kernel stores it into all N pools over
+  NVLink (P2P), so value counts N x checkpoint bytes made resident per step ("weak": bytes per pool fixed).
+* `e2e`    (GB/s): the same through the public call a user makes (modelhub.Load -> kk_load_part) with HOST
+  buffers: pread from the warm files into the pinned ring, H2D copies, kernels, and a device->host read of a
+  result (pool checksum word) plus kk_export, all inside the timed region.
+* `roofline`: dominant kernel kk_convert_kernel; algorithmic bytes = 2 x shard bytes (2 B read + 2 B written per
+  bf16 element) / its CUDA-event duration, against MEASURED_PEAKS.json's hbm_gbs.
+* `cpu_baseline`: the oracle's C port (oracle/kk_oracle.c, OpenMP, all host threads) on a bounded sample.
+
+The reference (eminwux/kukeon) has no loader and Go is absent, so `--impl reference` times that same CPU port
+(kind "port") — see DESIGN.md.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "model_load_GBps"
+UNIT = "GB/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="llama3-8b", choices=["llama3-8b", "mixtral-q4k", "gpt2", "llama3-70b-scatter"])
+    ap.add_argument("--layers", type=int, default=0, help="override the layer count (reported in config; 0 = full size)")
+    ap.add_argument("--data-dir", default="")
+    ap.add_argument("--keep-data", action="store_true")
+    ap.add_argument("--readers", type=int, default=0)
+    ap.add_argument("--slots", type=int, default=0)
+    ap.add_argument("--slot-mb", type=int, default=0)
+    ap.add_argument("--zerocopy", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-compare", action="store_true", help="also time an NCCL all-gather of the pools (comparison collective)")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# workload files
+# ---------------------------------------------------------------------------------------------
+def workload_spec(args):
+    from tools import synth
+    if args.workload == "llama3-8b":
+        cfg = dict(synth.LLAMA3_8B)
+        if args.layers:
+            cfg["layers"] = args.layers
+        t = synth.llama_tensors(**cfg)
+        name = "Llama-3-8B bf16 safetensors" + (f" (REDUCED to {args.layers} layers)" if args.layers else "")
+        return dict(kind="llama", cfg=cfg, tensors=t, name=name, mode="broadcast")
+    if args.workload == "llama3-70b-scatter":
+        cfg = dict(synth.LLAMA3_70B)
+        if args.layers:
+            cfg["layers"] = args.layers
+        t = synth.llama_tensors(**cfg)
+        name = "Llama-3-70B bf16 safetensors scatter" + (f" (REDUCED to {args.layers} layers)" if args.layers else "")
+        return dict(kind="llama", cfg=cfg, tensors=t, name=name, mode="scatter")
+    if args.workload == "mixtral-q4k":
+        kw = dict(layers=args.layers) if args.layers else {}
+        t = synth.mixtral_gguf_tensors(**kw)
+        name = "Mixtral-8x7B GGUF q4_K -> bf16" + (f" (REDUCED to {args.layers} layers)" if args.layers else "")
+        return dict(kind="gguf", tensors=t, name=name, mode="broadcast")
+    t = synth.gpt2_tensors()
+    return dict(kind="gpt2", tensors=t, name="GPT-2-small f32 safetensors", mode="broadcast")
+
+
+def pick_data_dir(args, need_bytes: int) -> str:
+    if args.data_dir:
+        return args.data_dir
+    for base in ("/dev/shm", "/tmp"):
+        try:
+            st = os.statvfs(base)
+            if st.f_bavail * st.f_frsize > need_bytes * 1.15 + (2 << 30):
+                return os.path.join(base, f"kk_bench_{args.workload}_{args.layers}")
+        except OSError:
+            pass
+    raise SystemExit(f"no directory with {need_bytes / 1e9:.1f} GB free for the synthetic checkpoint")
+
+
+def make_files(spec, d: str) -> str:
+    from tools import synth
+    marker = os.path.join(d, ".complete")
+    if os.path.exists(marker):
+        return d if spec["kind"] != "gguf" else os.path.join(d, "model.gguf")
+    shutil.rmtree(d, ignore_errors=True)
+    os.makedirs(d)
+    if spec["kind"] == "llama":
+        synth.write_sharded(d, spec["tensors"], 8001, 5_000_000_000)
+    elif spec["kind"] == "gguf":
+        synth.write_gguf(os.path.join(d, "model.gguf"), spec["tensors"], 8007)
+    else:
+        synth.write_safetensors(os.path.join(d, "model.safetensors"), spec["tensors"], 1234)
+    open(marker, "w").write("ok")
+    return d if spec["kind"] != "gguf" else os.path.join(d, "model.gguf")
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu: int):
+        self.gpu, self.rows, self.p = gpu, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 8] or [r for _, r in self.rows if len(r) >= 8]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = [float(r[1]) for r in rows]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in rows for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "reasons": reasons, "samples": len(rows),
+                "power_w_max": max(float(r[3]) for r in rows)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm (oracle port) — the only place bench.py touches oracle/
+# ---------------------------------------------------------------------------------------------
+def cpu_port_setup(path: str, sample_bytes: int):
+    from oracle import coracle, oracle
+    shards, recs = oracle.index_path(path)
+    plan, total = oracle.plan_pool(recs)
+    jobs, src = coracle.make_jobs(recs, plan, job_bytes=8 << 20, max_src_bytes=sample_bytes)
+    out_of = {coracle.OP_COPY: lambda n: n, coracle.OP_F32_BF16: lambda n: n // 2, coracle.OP_F16_BF16: lambda n: n,
+              coracle.OP_Q4K_BF16: lambda n: n // 144 * 512}
+    hi = max((j.dst_off + out_of[j.op](j.nbytes) for j in jobs), default=0)
+    pool = np.empty(min(total, hi) + 4096, np.uint8)
+    pool[::4096] = 0  # first touch outside the timed region
+    return coracle, shards, jobs, src, pool
+
+
+def cpu_port_step(ctx) -> float:
+    coracle, shards, jobs, src, pool = ctx
+    t = time.perf_counter()
+    coracle.cpu_load(shards, jobs, pool, threads=0)
+    return time.perf_counter() - t
+
+
+def run_reference(args, spec, path, file_bytes):
+    """--impl reference: the CPU port of the load path on all host threads (kind "port": the reference has no
+    loader and cannot be built here)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = min(file_bytes, 4 << 30)
+    ctx = cpu_port_setup(path, sample)
+    cores = ctx[0].max_threads()
+    for _ in range(max(args.warmup, 1)):
+        cpu_port_step(ctx)
+    ts = [cpu_port_step(ctx) for _ in range(args.steps)]
+    tot = sum(ts)
+    v = ctx[3] * args.steps / tot / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": tot / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic", "config": {"workload": spec["name"], "file_bytes": file_bytes, "files": "warm in tmpfs/page cache"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"first {ctx[3] / 1e9:.2f} GB of the checkpoint per step, pread + convert into host memory (oracle/kk_oracle.c, OpenMP)"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    spec = workload_spec(args)
+    from tools import synth
+    file_bytes = synth.total_bytes(spec["tensors"])
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    N = args.gpus
+    if world != N and not (world == 1 and N == 1):
+        if args.impl == "reference" and world == 1:
+            pass
+        else:
+            raise SystemExit(f"--gpus {N} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {N}")
+
+    d = pick_data_dir(args, file_bytes)
+    if args.impl == "reference":
+        if rank == 0:
+            path = make_files(spec, d)
+            run_reference(args, spec, path, file_bytes)
+            if not args.keep_data:
+                shutil.rmtree(d, ignore_errors=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from kukeon_b200 import gpupool, modelhub
+
+    gpupool.lib()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (our arm) needs a CUDA device: the loader has no CPU path")
+    torch.cuda.set_device(local)
+    gloo = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        gloo = dist.new_group(backend="gloo")
+
+    def barrier():
+        if world > 1:
+            dist.barrier(group=gloo)
+
+    def allmax(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=gloo)
+        return float(t.item())
+
+    def allsum(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=gloo)
+        return float(t.item())
+
+    t_gen = time.time()
+    if rank == 0:
+        path = make_files(spec, d)
+    barrier()
+    path = d if spec["kind"] != "gguf" else os.path.join(d, "model.gguf")
+    t_gen = time.time() - t_gen
+
+    mode = gpupool.MODE_SINGLE if world == 1 else (gpupool.MODE_SCATTER if spec["mode"] == "scatter" else gpupool.MODE_BROADCAST)
+    flags = gpupool.CFG_ZEROCOPY if args.zerocopy else 0
+    t0 = time.time()
+    pool = gpupool.Pool([local], n_staging_buffers=args.slots, staging_buffer_bytes=args.slot_mb << 20, n_reader_threads=args.readers, flags=flags)
+    t_open = time.time() - t0
+
+    # ---- cold path once: index + plan + pool allocation (+ peer exchange), then time-to-agent-ready ----------
+    barrier()
+    t_ready0 = time.time()
+    ref = modelhub.Pull(path)
+    m = modelhub.Load(pool, ref, mode=mode, fanout=gpupool.FANOUT_P2P, flags=gpupool.LOAD_DEFER,
+                      part_index=rank if world > 1 else 0, part_count=world if world > 1 else 0)
+    if world > 1 and mode == gpupool.MODE_BROADCAST:
+        h, _ = m.export(local)
+        hs = [None] * world
+        dist.all_gather_object(hs, h, group=gloo)
+        for r, hh in enumerate(hs):
+            if r != rank:
+                m.peer_attach(r, hh)
+    barrier()
+    m.load_part()
+    handle, manifest = m.export(local)
+    barrier()
+    t_ready = allmax(time.time() - t_ready0)
+    st0 = m.stats()
+
+    # ---- verification against the files (product-only: bf16 passthrough == file bytes) -------------------
+    verified = None
+    if spec["kind"] == "llama" and mode != gpupool.MODE_SCATTER:
+        verified = True
+        for r in (ref.tensors[0], ref.tensors[len(ref.tensors) // 2], ref.tensors[-1]):
+            pl = m.placements(r["name"])[0]
+            n = min(pl.nbytes, 8 << 20)
+            raw = np.fromfile(ref.shards[r["shard"]], np.uint8, count=n, offset=r["file_offset"] + pl.nbytes - n)
+            got = m.read(local, pl.pool_offset + pl.nbytes - n, n)
+            verified = verified and bool(np.array_equal(raw, got))
+        if not verified:
+            raise SystemExit("pool contents differ from the checkpoint files")
+
+    info = m.info()
+    pool_bytes = info["pool_bytes"]
+    part = st0["parts"][0]
+    local_src = part["src_bytes"]
+
+    # ---- e2e: public API with host buffers (pread -> pinned -> H2D -> kernels -> export + D2H result) ---------
+    first = m.placements(ref.tensors[0]["name"])[0]
+
+    def e2e_step():
+        barrier()
+        t = time.perf_counter()
+        m.load_part()
+        m.export(local)
+        m.checksum(local, first.pool_offset, min(first.nbytes, 1 << 20))  # 8-byte D2H result read
+        dt = time.perf_counter() - t
+        barrier()
+        return dt
+
+    for _ in range(args.warmup):
+        e2e_step()
+    e2e_ts = [allmax(e2e_step()) for _ in range(args.steps)]
+    e2e_time = sum(e2e_ts)
+    delivered = (pool_bytes if mode == gpupool.MODE_SCATTER else file_bytes) * (1 if mode == gpupool.MODE_SCATTER else world)
+    if mode == gpupool.MODE_SCATTER:
+        delivered = allsum(float(part["out_bytes"]))
+    e2e_val = delivered * args.steps / e2e_time / 1e9
+    chunks_per_load = part["chunks"]
+
+    # ---- value: kernel stage from the HBM-resident image ---------------------------------------------------
+    m.stage_resident()
+    barrier()
+    for _ in range(max(args.warmup, 3)):
+        barrier()
+        m.convert_resident()
+    clocks = ClockSampler(local)
+    clocks.start()
+    time.sleep(0.25)
+    torch.cuda.synchronize()
+    barrier()
+    tc0 = time.time()
+    step_ms, launch_ms = [], []
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        barrier()
+        tot, per = m.convert_resident()
+        step_ms.append(tot)
+        launch_ms.append(per)
+    torch.cuda.synchronize()
+    barrier()
+    wall = time.perf_counter() - wall0
+    tc1 = time.time()
+    ck = clocks.stop(tc0, tc1)
+    dev_ms = allmax(sum(step_ms))
+    value = delivered * args.steps / (dev_ms / 1e3) / 1e9
+    n_launch = len(launch_ms[0])
+
+    # ---- roofline of the dominant kernel (this rank's launches) -------------------------------------------
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+    avg_launch_ms = sum(sum(p) for p in launch_ms) / (len(launch_ms) * max(n_launch, 1))
+    # algorithmic HBM bytes of this rank per launch: source read once + pool writes landing in THIS GPU's HBM
+    alg_per_step = local_src + part["out_bytes"] * (1 if mode == gpupool.MODE_SCATTER else world) if mode != gpupool.MODE_SINGLE else local_src + part["out_bytes"]
+    alg_per_launch = alg_per_step / max(n_launch, 1)
+    achieved = alg_per_launch / (avg_launch_ms / 1e3) / 1e9 if avg_launch_ms > 0 else 0.0
+    traffic = None
+    tf = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tf):
+        try:
+            traffic = json.load(open(tf)).get(args.workload, {}).get("dram_bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "kk_convert_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_per_launch, "avg_launch_ms": avg_launch_ms,
+                "launches_per_step": n_launch,
+                "write_only_frac_of_peak": (part["out_bytes"] / max(n_launch, 1)) / (avg_launch_ms / 1e3) / 1e9 / peak if avg_launch_ms > 0 else 0.0}
+    nvlink = None
+    if world > 1 and mode == gpupool.MODE_BROADCAST:
+        egress = part["out_bytes"] * (world - 1)
+        gbps = egress / (sum(step_ms) / len(step_ms) / 1e3) / 1e9
+        nvlink = {"egress_bytes_per_step_per_gpu": egress, "achieved_GBps_per_gpu": gbps, "peak_measured": 770.0, "peak_nominal": 900.0,
+                  "frac_of_measured": gbps / 770.0, "frac_of_nominal": gbps / 900.0, "form": "sharded ingest + fused P2P all-gather stores"}
+
+    # ---- optional NCCL comparison collective ----------------------------------------------------------------
+    nccl = None
+    if args.nccl_compare and world > 1 and mode == gpupool.MODE_BROADCAST:
+        nccl = nccl_compare(torch, dist, file_bytes, world, local, args)
+
+    # ---- CPU baseline beside it (rank 0, N == 1) ------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            m.unstage_resident()
+            ctx = cpu_port_setup(path, min(file_bytes, 4 << 30))
+            cpu_port_step(ctx)
+            ts = [cpu_port_step(ctx) for _ in range(3)]
+            cpu = {"value": ctx[3] * len(ts) / sum(ts) / 1e9, "unit": UNIT, "cores": ctx[0].max_threads(), "kind": "port",
+                   "sample": f"first {ctx[3] / 1e9:.2f} GB of the checkpoint x{len(ts)}, pread + convert into host memory, all OpenMP threads"}
+        except Exception as e:  # noqa: BLE001
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if spec["kind"] != "gpt2" else "f32->bf16",
+        "data": "synthetic",
+        "config": {"workload": spec["name"], "file_bytes": file_bytes, "tensors": len(ref.tensors), "shards": len(ref.shards),
+                   "mode": {0: "single", 1: "broadcast (sharded ingest + fused P2P fan-out)", 2: "scatter"}[mode], "pool_bytes_per_gpu": pool_bytes,
+                   "l2": "inputs (>= 2 GB per GPU) far larger than the 126 MB L2; no flush needed", "files": f"warm in {os.path.dirname(d) or d}",
+                   "staging": "zero-copy pinned reads" if args.zerocopy else "pinned ring + H2D copy engine", "verified_vs_files": verified},
+        "clocks": ck,
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(allsum(float(local_src))), "d2h_bytes_per_step": 8 * world,
+                "ms_per_step": e2e_time / args.steps * 1e3, "what": "kk_load_part (pread->pinned->H2D->kernels) + kk_export + checksum word D2H"},
+        "gpu_launches": n_launch * args.steps,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "time_to_agent_ready_s": t_ready,
+        "wall_ms_per_step": wall / args.steps * 1e3,
+        "setup": {"synth_s": t_gen, "kk_open_s": t_open, "index_s": st0["index_s"], "plan_s": st0["plan_s"], "alloc_s": st0["alloc_s"],
+                  "first_load_s": st0["load_s"], "chunks_per_load": chunks_per_load},
+    }
+    if nvlink:
+        line["nvlink"] = nvlink
+    if nccl:
+        line["nccl_compare"] = nccl
+    m.release()
+    pool.close()
+    barrier()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+        if not args.keep_data:
+            shutil.rmtree(d, ignore_errors=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def nccl_compare(torch, dist, file_bytes, world, local, args):
+    """Comparison collective only (north_star): all-gather of equal 1/N slices with NCCL, timed with CUDA events."""
+    per = (file_bytes // world + 255) // 256 * 256
+    src = torch.empty(per, dtype=torch.uint8, device=f"cuda:{local}")
+    dst = torch.empty(per * world, dtype=torch.uint8, device=f"cuda:{local}")
+    for _ in range(3):
+        dist.all_gather_into_tensor(dst, src)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    e0.record()
+    for _ in range(args.steps):
+        dist.all_gather_into_tensor(dst, src)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return {"collective": "ncclAllGather", "ms": ms, "GBps_delivered_total": per * world * world / (ms / 1e3) / 1e9,
+            "egress_GBps_per_gpu": per * (world - 1) / (ms / 1e3) / 1e9}
+
+
+if __name__ == "__main__":
+    main()

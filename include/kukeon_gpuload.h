@@ -174,6 +174,13 @@ int kk_free_index(kk_tensor_meta* recs);
  * buf receives name `i`; returns KK_ERANGE if cap is too small. */
 int kk_index_shard(kk_ctx* ctx, const char* path, size_t i, char* buf, size_t cap, size_t* n_out);
 
+/* Describe, without touching a device, what a load would do: pool layout(s) and, per ingesting part, the
+ * staging chunks (file reads) and conversion segments.  n_parts is the number of ingesting devices/ranks
+ * (1 for KK_MODE_SINGLE), chunk_bytes the staging slot size (0 = default 64 MiB).  JSON into `json`;
+ * KK_ERANGE (and *required) when cap is too small.  CPU only; ctx may be NULL. */
+int kk_plan_describe(kk_ctx* ctx, const char* path, const kk_load_opts* opts, int n_parts, uint64_t chunk_bytes,
+                     char* json, size_t cap, size_t* required);
+
 /* ---- Load ------------------------------------------------------------------------------------ */
 int kk_load(kk_ctx* ctx, const char* path, int mode, int fanout, kk_model** out);
 int kk_load_ex(kk_ctx* ctx, const char* path, const kk_load_opts* opts, kk_model** out);

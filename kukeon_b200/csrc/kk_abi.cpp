@@ -124,6 +124,21 @@ int kk_index_shard(kk_ctx*, const char* path, size_t i, char* buf, size_t cap, s
   });
 }
 
+int kk_plan_describe(kk_ctx*, const char* path, const kk_load_opts* opts, int n_parts, uint64_t chunk_bytes, char* json,
+                     size_t cap, size_t* required) {
+  return guard([&] {
+    need(path, "path");
+    need(opts, "opts");
+    if (chunk_bytes == 0) chunk_bytes = 64ull << 20;
+    kk::Plan P = kk::build_plan(kk::index_path(path), opts->mode, opts->flags & ~KK_LOAD_DEFER, n_parts, chunk_bytes);
+    std::string s = kk::plan_to_json(P);
+    if (required) *required = s.size() + 1;
+    if (!json) return;
+    if (s.size() + 1 > cap) kk::fail(KK_ERANGE, "plan description needs %zu bytes", s.size() + 1);
+    memcpy(json, s.c_str(), s.size() + 1);
+  });
+}
+
 int kk_load(kk_ctx* ctx, const char* path, int mode, int fanout, kk_model** out) {
   kk_load_opts o{};
   o.mode = mode;

@@ -4,6 +4,9 @@
 
 #include <algorithm>
 #include <cstring>
+#include <sstream>
+
+#include "kk_json.hpp"
 
 namespace kk {
 
@@ -361,6 +364,52 @@ Plan build_plan(Index index, int mode, uint32_t flags, int n_parts, uint64_t chu
     }
   }
   return P;
+}
+
+std::string plan_to_json(const Plan& P) {
+  std::ostringstream o;
+  o << "{\"mode\":" << P.mode << ",\"flags\":" << P.flags << ",\"n_parts\":" << P.n_parts << ",\"file_bytes\":" << P.file_bytes
+    << ",\"format\":\"" << P.index.format << "\",\"shards\":[";
+  for (size_t i = 0; i < P.index.shards.size(); ++i) o << (i ? "," : "") << "\"" << json_escape(P.index.shards[i]) << "\"";
+  o << "],\"layouts\":[";
+  for (size_t L = 0; L < P.placements.size(); ++L) {
+    o << (L ? "," : "") << "{\"pool_bytes\":" << P.pool_bytes[L] << ",\"tensors\":[";
+    for (size_t i = 0; i < P.placements[L].size(); ++i) {
+      const Placement& p = P.placements[L][i];
+      const DtypeInfo* di = dtype_info(p.dtype);
+      o << (i ? "," : "") << "{\"name\":\"" << json_escape(P.index.tensors[i].name) << "\",\"dtype\":\"" << (di ? di->name : "?")
+        << "\",\"shape\":[";
+      for (size_t d = 0; d < p.shape.size(); ++d) o << (d ? "," : "") << p.shape[d];
+      o << "],\"pool_offset\":" << p.pool_offset << ",\"nbytes\":" << p.nbytes << ",\"slice_dim\":";
+      if (p.slice_dim == kNoSlice) o << "null";
+      else o << p.slice_dim;
+      o << ",\"slice_begin\":" << p.slice_begin << "}";
+    }
+    o << "]}";
+  }
+  o << "],\"parts\":[";
+  for (size_t g = 0; g < P.parts.size(); ++g) {
+    const PartPlan& pp = P.parts[g];
+    o << (g ? "," : "") << "{\"src_bytes\":" << pp.src_bytes << ",\"out_bytes\":" << pp.out_bytes << ",\"chunks\":[";
+    for (size_t c = 0; c < pp.chunks.size(); ++c) {
+      const Chunk& ch = pp.chunks[c];
+      o << (c ? "," : "") << "{\"shard\":" << ch.shard << ",\"buf_bytes\":" << ch.buf_bytes << ",\"n_tiles\":" << ch.n_tiles
+        << ",\"src_bytes\":" << ch.src_bytes << ",\"out_bytes\":" << ch.out_bytes << ",\"reads\":[";
+      for (size_t r = 0; r < ch.reads.size(); ++r)
+        o << (r ? "," : "") << "[" << ch.reads[r].file_off << "," << ch.reads[r].len << "," << ch.reads[r].buf_off << "]";
+      o << "],\"segs\":[";
+      for (uint32_t s = 0; s < ch.seg_count; ++s) {
+        const KKSeg& sg = pp.segs[ch.seg_begin + s];
+        o << (s ? "," : "") << "{\"src_off\":" << sg.src_off << ",\"dst_off\":" << sg.dst_off << ",\"units\":" << sg.units
+          << ",\"op\":" << sg.op << ",\"tile_begin\":" << sg.tile_begin << ",\"p0\":" << sg.p0 << ",\"p1\":" << sg.p1
+          << ",\"p2\":" << sg.p2 << "}";
+      }
+      o << "]}";
+    }
+    o << "]}";
+  }
+  o << "]}";
+  return o.str();
 }
 
 }  // namespace kk

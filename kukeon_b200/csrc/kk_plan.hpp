@@ -67,6 +67,9 @@ Plan build_plan(Index index, int mode, uint32_t flags, int n_parts, uint64_t chu
 // column-parallel weights along dim 0, row-parallel weights along dim 1.
 uint32_t scatter_slice_dim(const TensorRec& t, int n_parts);
 
+// JSON description of a plan (kk_plan_describe).
+std::string plan_to_json(const Plan& P);
+
 // True when KK_LOAD_GPT2_CONV1D_T applies to this tensor.
 bool is_gpt2_conv1d(const TensorRec& t);
 

@@ -1,0 +1,123 @@
+"""Host-side mirror of the Go API the north_star adds to kukeon's `internal/modelhub`:
+`Pull`, `Load`, `Mount` plus the per-Cell acquire/release hooks.
+
+None of these exist in the reference; the shapes below follow the seams they would
+sit next to so that the Go shim in INTEGRATION.md is a line-for-line transliteration:
+
+* `Pull`   — local-path resolution + tensor index (nearest analogue: ctr image pull, internal/ctr/image.go:91).
+* `Load`   — one call into the C ABI per checkpoint; N concurrent callers share one load
+             (runner.StartCell call site, internal/controller/runner/start.go:785-790).
+* `Mount`  — stages `<cell metadata dir>/gpupool/{manifest.json,ipc.handle}` atomically
+             (internal/metadata/metadata.go:105-140) and returns the OCI bind mount
+             (`bindVolumeMount`, internal/ctr/spec.go:526-543) and `KUKEON_GPUPOOL_*` env entries
+             (`kukeonDefaultEnv`, internal/ctr/spec.go:464-482) a `ctr.BuildOption` would add.
+
+All data movement happens in libkukeon_gpuload.so; this file never touches tensor bytes.
+"""
+from __future__ import annotations
+
+import json
+import os
+import tempfile
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+from . import gpupool
+from .gpupool import FANOUT_NONE, FANOUT_P2P, MODE_BROADCAST, MODE_SCATTER, MODE_SINGLE  # noqa: F401
+
+CONTAINER_GPUPOOL_DIR = "/run/kukeon/gpupool"  # bind-mount target inside the agent container
+ENV_MANIFEST = "KUKEON_GPUPOOL_MANIFEST"
+ENV_IPC_HANDLE = "KUKEON_GPUPOOL_IPC_HANDLE"
+ENV_DEVICE = "KUKEON_GPUPOOL_DEVICE"
+
+
+@dataclass
+class ModelRef:
+    """Result of Pull: where the checkpoint lives and what is in it."""
+    path: str
+    shards: List[str]
+    tensors: List[dict]
+
+    @property
+    def file_bytes(self) -> int:
+        return sum(t["nbytes"] for t in self.tensors)
+
+
+def Pull(path: str) -> ModelRef:
+    """Resolve a local checkpoint (directory with model.safetensors.index.json / model.safetensors /
+    *.gguf, or a single file) and index it.  No network: "pull" is local-path only."""
+    return ModelRef(path=os.path.realpath(path), shards=gpupool.index_shards(path), tensors=gpupool.index(path))
+
+
+def Load(pool: gpupool.Pool, ref: ModelRef | str, mode: int = MODE_SINGLE, fanout: int = FANOUT_P2P, flags: int = 0,
+         part_index: int = 0, part_count: int = 0) -> gpupool.Model:
+    """Make the checkpoint resident in the pool(s).  Returns a refcounted Model; a second Load of the same
+    checkpoint returns the same resident copy with its count bumped."""
+    path = ref.path if isinstance(ref, ModelRef) else ref
+    return pool.load(path, mode=mode, fanout=fanout, flags=flags, part_index=part_index, part_count=part_count)
+
+
+@dataclass
+class MountSpec:
+    """What a `ctr.WithGPUWeights(...)` BuildOption would append to the container's OCI spec."""
+    mounts: List[dict] = field(default_factory=list)
+    env: List[str] = field(default_factory=list)
+    host_dir: str = ""
+
+
+def _atomic_write(path: str, data: bytes, mode: int = 0o644) -> None:
+    d = os.path.dirname(path)
+    fd, tmp = tempfile.mkstemp(prefix=".meta-", suffix=".tmp", dir=d)
+    try:
+        os.fchmod(fd, mode)
+        os.write(fd, data)
+        os.fsync(fd)
+    finally:
+        os.close(fd)
+    os.rename(tmp, path)
+    try:
+        dfd = os.open(d, os.O_RDONLY)
+        os.fsync(dfd)
+        os.close(dfd)
+    except OSError:
+        pass
+
+
+def Mount(model: gpupool.Model, device: int, container_dir: str) -> MountSpec:
+    """Export `device`'s pool for one agent container: write the manifest + IPC handle under
+    `<container_dir>/gpupool/` and describe the read-only bind mount and env that expose them."""
+    handle, manifest = model.export(device)
+    host_dir = os.path.join(container_dir, "gpupool")
+    os.makedirs(host_dir, mode=0o750, exist_ok=True)
+    _atomic_write(os.path.join(host_dir, "manifest.json"), json.dumps(manifest, separators=(",", ":")).encode())
+    _atomic_write(os.path.join(host_dir, "ipc.handle"), handle, 0o640)
+    return MountSpec(
+        mounts=[{"destination": CONTAINER_GPUPOOL_DIR, "type": "bind", "source": host_dir, "options": ["rbind", "ro"]}],
+        env=[f"{ENV_MANIFEST}={CONTAINER_GPUPOOL_DIR}/manifest.json", f"{ENV_IPC_HANDLE}={CONTAINER_GPUPOOL_DIR}/ipc.handle",
+             f"{ENV_DEVICE}={device}"],
+        host_dir=host_dir,
+    )
+
+
+class CellHooks:
+    """Per-Cell reference counting ("N concurrent agent Sessions" == N Cells).
+    acquire() in StartCell; release() from KillCell / StopCell / DeleteCell — idempotent per cell because
+    those teardown paths overlap in the reference (markCellFailed calls KillCell, runner/start.go:192-242)."""
+
+    def __init__(self, model: gpupool.Model):
+        self.model = model
+        self._cells: Dict[str, bool] = {}
+
+    def start_cell(self, cell_id: str) -> None:
+        if self._cells.get(cell_id):
+            return
+        self.model.acquire()
+        self._cells[cell_id] = True
+
+    def stop_cell(self, cell_id: str) -> None:
+        if self._cells.pop(cell_id, None):
+            self.model.release()
+
+    @property
+    def active(self) -> int:
+        return len(self._cells)

@@ -1,0 +1,146 @@
+"""ctypes front-end of oracle/kk_oracle.c (TEST INFRASTRUCTURE ONLY — see oracle/oracle.py header)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import List, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libkk_oracle.so")
+_lib = None
+
+OP_COPY, OP_F32_BF16, OP_F16_BF16, OP_Q4K_BF16 = 0, 1, 2, 3
+
+
+class OrcJob(C.Structure):
+    _fields_ = [("shard", C.c_uint32), ("op", C.c_uint32), ("file_off", C.c_uint64), ("nbytes", C.c_uint64), ("dst_off", C.c_uint64)]
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "kk_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = C.CDLL(_SO)
+        u8p, u16p, u32p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint16), C.POINTER(C.c_uint32)
+        L.orc_f32_to_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.orc_f16_to_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.orc_q4k_to_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.orc_checksum.argtypes = [C.c_void_p, C.c_uint64]
+        L.orc_checksum.restype = C.c_uint64
+        for fn in ("orc_fill_bytes", "orc_fill_bf16_finite", "orc_fill_f32", "orc_fill_q4k"):
+            getattr(L, fn).argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+            getattr(L, fn).restype = None
+        L.orc_cpu_load.argtypes = [C.POINTER(C.c_char_p), C.c_uint32, C.POINTER(OrcJob), C.c_uint64, C.c_void_p, C.c_uint64, C.c_int]
+        L.orc_cpu_load.restype = C.c_int
+        L.orc_max_threads.restype = C.c_int
+        _lib = L
+        del u8p, u16p, u32p
+    return _lib
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def f32_to_bf16(u32: np.ndarray) -> np.ndarray:
+    src = np.ascontiguousarray(u32).view(np.uint32).reshape(-1)
+    out = np.empty(src.size, np.uint16)
+    lib().orc_f32_to_bf16(_ptr(src), _ptr(out), src.size)
+    return out
+
+
+def f16_to_bf16(u16: np.ndarray) -> np.ndarray:
+    src = np.ascontiguousarray(u16).view(np.uint16).reshape(-1)
+    out = np.empty(src.size, np.uint16)
+    lib().orc_f16_to_bf16(_ptr(src), _ptr(out), src.size)
+    return out
+
+
+def q4k_to_bf16(blocks: np.ndarray) -> np.ndarray:
+    src = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1)
+    assert src.size % 144 == 0
+    n = src.size // 144
+    out = np.empty(n * 256, np.uint16)
+    lib().orc_q4k_to_bf16(_ptr(src), _ptr(out), n)
+    return out.reshape(n, 256)
+
+
+def checksum(a: np.ndarray) -> int:
+    src = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+    return int(lib().orc_checksum(_ptr(src), src.size))
+
+
+def fill(kind: str, n: int, seed: int) -> np.ndarray:
+    """kind: 'bytes' (n bytes), 'bf16' (n elems), 'f32' (n elems), 'q4k' (n blocks)."""
+    L = lib()
+    if kind == "bytes":
+        a = np.empty(n, np.uint8); L.orc_fill_bytes(_ptr(a), n, seed)
+    elif kind == "bf16":
+        a = np.empty(n, np.uint16); L.orc_fill_bf16_finite(_ptr(a), n, seed)
+    elif kind == "f32":
+        a = np.empty(n, np.float32); L.orc_fill_f32(_ptr(a), n, seed)
+    elif kind == "q4k":
+        a = np.empty(n * 144, np.uint8); L.orc_fill_q4k(_ptr(a), n, seed)
+    else:
+        raise ValueError(kind)
+    return a
+
+
+def fill_into(kind: str, dst: np.ndarray, seed: int) -> None:
+    L = lib()
+    d = dst.reshape(-1)
+    if kind == "bytes":
+        L.orc_fill_bytes(_ptr(d), d.view(np.uint8).size, seed)
+    elif kind == "bf16":
+        L.orc_fill_bf16_finite(_ptr(d), d.view(np.uint16).size, seed)
+    elif kind == "f32":
+        L.orc_fill_f32(_ptr(d), d.view(np.float32).size, seed)
+    elif kind == "q4k":
+        L.orc_fill_q4k(_ptr(d), d.view(np.uint8).size // 144, seed)
+    else:
+        raise ValueError(kind)
+
+
+_OPS = {"BF16": OP_COPY, "F32": OP_F32_BF16, "F16": OP_F16_BF16, "Q4_K": OP_Q4K_BF16}
+
+
+def make_jobs(recs: Sequence[dict], plan: Sequence[dict], job_bytes: int = 8 << 20, max_src_bytes: int | None = None):
+    """Split every tensor into <= job_bytes pieces on unit boundaries (non-transposed, unsliced plans)."""
+    jobs: List[OrcJob] = []
+    total = 0
+    for r, p in zip(recs, plan):
+        op = _OPS.get(r["dtype"], OP_COPY)
+        unit, out_unit = {OP_COPY: (256, 256), OP_F32_BF16: (4, 2), OP_F16_BF16: (2, 2), OP_Q4K_BF16: (144, 512)}[op]
+        step = max(unit, job_bytes // unit * unit)
+        off = 0
+        while off < r["nbytes"]:
+            n = min(step, r["nbytes"] - off)
+            if max_src_bytes is not None and total + n > max_src_bytes:
+                return jobs, total
+            jobs.append(OrcJob(r["shard"], op, r["file_offset"] + off, n, p["pool_offset"] + off // unit * out_unit))
+            total += n
+            off += n
+    return jobs, total
+
+
+def cpu_load(shards: Sequence[str], jobs: Sequence[OrcJob], pool: np.ndarray, threads: int = 0, scratch: int = 16 << 20) -> None:
+    arr = (OrcJob * len(jobs))(*jobs)
+    paths = (C.c_char_p * len(shards))(*[s.encode() for s in shards])
+    rc = lib().orc_cpu_load(paths, len(shards), arr, len(jobs), _ptr(pool), scratch, threads)
+    if rc != 0:
+        raise OSError("orc_cpu_load failed")
+
+
+def max_threads() -> int:
+    return int(lib().orc_max_threads())

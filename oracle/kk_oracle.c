@@ -1,0 +1,246 @@
+/*
+ * kk_oracle.c — C twin of oracle/oracle.py's value arithmetic plus a multi-threaded CPU loader.
+ * TEST INFRASTRUCTURE ONLY: linked/loaded by tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs; never by the product.
+ *
+ * PARITY UNPINNED AGAINST THE REFERENCE (eminwux/kukeon has no weight loader — SURVEY.md §0); pinned
+ * against safetensors 0.7.0 / gguf 0.19.0 (gguf/quants.py:475-521) / torch RNE through oracle.py, which
+ * tests/test_oracle_values.py checks this file against bit for bit.
+ *
+ * Build: see oracle/Makefile (gcc -O3 -fopenmp -ffp-contract=off).
+ */
+#define _GNU_SOURCE
+#include <errno.h>
+#include <fcntl.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+static inline uint16_t f32bits_to_bf16(uint32_t u) {
+  if ((u & 0x7FFFFFFFu) > 0x7F800000u) return 0x7FFF; /* NaN -> canonical (PTX cvt.rn.bf16.f32) */
+  uint32_t lsb = (u >> 16) & 1u;
+  return (uint16_t)((u + 0x7FFFu + lsb) >> 16);
+}
+static inline uint16_t f32_to_bf16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return f32bits_to_bf16(u);
+}
+static inline float f16bits_to_f32(uint16_t h) {
+  _Float16 x;
+  memcpy(&x, &h, 2);
+  return (float)x;
+}
+
+void orc_f32_to_bf16(const uint32_t* src, uint16_t* dst, uint64_t n) {
+#pragma omp parallel for schedule(static)
+  for (uint64_t i = 0; i < n; ++i) dst[i] = f32bits_to_bf16(src[i]);
+}
+
+void orc_f16_to_bf16(const uint16_t* src, uint16_t* dst, uint64_t n) {
+#pragma omp parallel for schedule(static)
+  for (uint64_t i = 0; i < n; ++i) dst[i] = f32_to_bf16(f16bits_to_f32(src[i]));
+}
+
+/* One Q4_K super-block: d f16 | dmin f16 | scales[12] | qs[128] -> 256 bf16.
+ * y = (d*sc_j)*q - (dmin*m_j); every operation rounds to fp32 (no FMA: -ffp-contract=off). */
+static void q4k_block(const uint8_t* b, uint16_t* out) {
+  uint16_t hd, hm;
+  memcpy(&hd, b, 2);
+  memcpy(&hm, b + 2, 2);
+  const float d = f16bits_to_f32(hd), dmin = f16bits_to_f32(hm);
+  const uint8_t* s = b + 4;
+  const uint8_t* qs = b + 16;
+  for (int j = 0; j < 8; ++j) {
+    uint8_t sc, m;
+    if (j < 4) {
+      sc = s[j] & 63;
+      m = s[j + 4] & 63;
+    } else {
+      sc = (uint8_t)((s[j + 4] & 0x0F) | ((s[j - 4] >> 6) << 4));
+      m = (uint8_t)((s[j + 4] >> 4) | ((s[j] >> 6) << 4));
+    }
+    volatile float dsc = d * (float)sc;
+    volatile float dmn = dmin * (float)m;
+    const uint8_t* q = qs + 32 * (j >> 1);
+    const int sh = (j & 1) * 4;
+    for (int i = 0; i < 32; ++i) {
+      volatile float p = dsc * (float)((q[i] >> sh) & 0x0F);
+      float y = p - dmn;
+      out[32 * j + i] = f32_to_bf16(y);
+    }
+  }
+}
+
+void orc_q4k_to_bf16(const uint8_t* blocks, uint16_t* dst, uint64_t nblocks) {
+#pragma omp parallel for schedule(static)
+  for (uint64_t i = 0; i < nblocks; ++i) q4k_block(blocks + 144 * i, dst + 256 * i);
+}
+
+static inline uint64_t mix64(uint64_t x) {
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27; x *= 0x94d049bb133111ebull;
+  x ^= x >> 31;
+  return x;
+}
+
+uint64_t orc_checksum(const uint8_t* p, uint64_t nbytes) {
+  const uint64_t nw = nbytes >> 3;
+  uint64_t acc = 0;
+#pragma omp parallel for schedule(static) reduction(+ : acc)
+  for (uint64_t i = 0; i < nw; ++i) {
+    uint64_t w;
+    memcpy(&w, p + 8 * i, 8);
+    acc += mix64(w + i * 0x9E3779B97F4A7C15ull);
+  }
+  if (nbytes & 7) {
+    uint64_t last = 0;
+    memcpy(&last, p + 8 * nw, nbytes & 7);
+    acc += mix64(last + nw * 0x9E3779B97F4A7C15ull);
+  }
+  return acc;
+}
+
+/* ---- synthetic content (counter-based, reproducible per (seed, index)) ------------------------ */
+static inline uint64_t ctr_rand(uint64_t seed, uint64_t i) { return mix64(seed * 0xD1B54A32D192ED03ull + i * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull); }
+
+void orc_fill_bytes(uint8_t* dst, uint64_t n, uint64_t seed) {
+  const uint64_t nw = n >> 3;
+#pragma omp parallel for schedule(static)
+  for (uint64_t i = 0; i < nw; ++i) {
+    uint64_t r = ctr_rand(seed, i);
+    memcpy(dst + 8 * i, &r, 8);
+  }
+  if (n & 7) {
+    uint64_t r = ctr_rand(seed, nw);
+    memcpy(dst + 8 * nw, &r, n & 7);
+  }
+}
+
+/* Uniform 16-bit patterns with the exponent clamped so every value is a finite bf16. */
+void orc_fill_bf16_finite(uint16_t* dst, uint64_t n, uint64_t seed) {
+#pragma omp parallel for schedule(static)
+  for (uint64_t i = 0; i < (n + 3) / 4; ++i) {
+    uint64_t r = ctr_rand(seed, i);
+    for (int k = 0; k < 4 && 4 * i + k < n; ++k) {
+      uint16_t v = (uint16_t)(r >> (16 * k));
+      if ((v & 0x7F80) == 0x7F80) v &= (uint16_t)~0x0080; /* exponent 0xFF -> 0xFE */
+      dst[4 * i + k] = v;
+    }
+  }
+}
+
+/* fp32 values ~ U(-0.04, 0.04) plus a sprinkle of exact ties/denormals; all finite. */
+void orc_fill_f32(float* dst, uint64_t n, uint64_t seed) {
+#pragma omp parallel for schedule(static)
+  for (uint64_t i = 0; i < n; ++i) {
+    uint64_t r = ctr_rand(seed, i);
+    uint32_t u = (uint32_t)r;
+    float f = ((float)(u >> 8) * (1.0f / 16777216.0f) - 0.5f) * 0.08f;
+    if ((r >> 60) == 0) { /* 1/16 of the values: raw finite bit pattern (exercises RNE ties, subnormals) */
+      uint32_t b = (uint32_t)(r >> 16);
+      if ((b & 0x7F800000u) == 0x7F800000u) b &= ~0x00800000u;
+      memcpy(&f, &b, 4);
+    }
+    dst[i] = f;
+  }
+}
+
+/* Q4_K blocks: random bytes, d and dmin overwritten with finite fp16 in [2^-10, 2^-4]. */
+void orc_fill_q4k(uint8_t* dst, uint64_t nblocks, uint64_t seed) {
+#pragma omp parallel for schedule(static)
+  for (uint64_t b = 0; b < nblocks; ++b) {
+    uint8_t* p = dst + 144 * b;
+    for (int w = 0; w < 18; ++w) {
+      uint64_t r = ctr_rand(seed, b * 18 + w);
+      memcpy(p + 8 * w, &r, 8);
+    }
+    uint64_t r = ctr_rand(seed ^ 0xABCDEF, b);
+    /* fp16: exponent field e in [5, 11] => 2^(e-15) in [2^-10, 2^-4]; random mantissa; positive */
+    uint16_t d = (uint16_t)((((r & 0xFF) % 7 + 5) << 10) | ((r >> 8) & 0x3FF));
+    uint16_t m = (uint16_t)(((((r >> 20) & 0xFF) % 7 + 5) << 10) | ((r >> 28) & 0x3FF));
+    memcpy(p, &d, 2);
+    memcpy(p + 2, &m, 2);
+  }
+}
+
+/* ---- CPU loader ("port" of the hot path for the cpu_baseline legs) ---------------------------- */
+enum { ORC_COPY = 0, ORC_F32_BF16 = 1, ORC_F16_BF16 = 2, ORC_Q4K_BF16 = 3 };
+
+typedef struct {
+  uint32_t shard;
+  uint32_t op;
+  uint64_t file_off;
+  uint64_t nbytes; /* source bytes */
+  uint64_t dst_off;
+} orc_job;
+
+static int pread_full(int fd, uint8_t* dst, uint64_t len, uint64_t off) {
+  while (len) {
+    ssize_t r = pread(fd, dst, len, (off_t)off);
+    if (r < 0) {
+      if (errno == EINTR) continue;
+      return -1;
+    }
+    if (r == 0) return -1;
+    dst += r; off += (uint64_t)r; len -= (uint64_t)r;
+  }
+  return 0;
+}
+
+/* Reads every job's bytes from its shard and writes the converted bf16 (or verbatim bytes) into `pool`
+ * (host memory).  Jobs must be small enough for a per-thread scratch buffer of `scratch_bytes`.
+ * Returns 0, or -1 on I/O error.  threads <= 0: OpenMP default. */
+int orc_cpu_load(const char* const* shard_paths, uint32_t n_shards, const orc_job* jobs, uint64_t n_jobs, uint8_t* pool,
+                 uint64_t scratch_bytes, int threads) {
+  int* fds = (int*)malloc(sizeof(int) * n_shards);
+  int err = 0;
+  for (uint32_t i = 0; i < n_shards; ++i) {
+    fds[i] = open(shard_paths[i], O_RDONLY);
+    if (fds[i] < 0) err = -1;
+  }
+#ifdef _OPENMP
+  if (threads > 0) omp_set_num_threads(threads);
+#endif
+  if (!err) {
+#pragma omp parallel
+    {
+      uint8_t* scratch = (uint8_t*)malloc(scratch_bytes ? scratch_bytes : 1);
+#pragma omp for schedule(dynamic, 1)
+      for (uint64_t j = 0; j < n_jobs; ++j) {
+        const orc_job* J = &jobs[j];
+        if (J->nbytes > scratch_bytes && J->op != ORC_COPY) { err = -1; continue; }
+        if (J->op == ORC_COPY) { /* straight into the pool */
+          if (pread_full(fds[J->shard], pool + J->dst_off, J->nbytes, J->file_off)) err = -1;
+          continue;
+        }
+        if (pread_full(fds[J->shard], scratch, J->nbytes, J->file_off)) { err = -1; continue; }
+        uint16_t* out = (uint16_t*)(pool + J->dst_off);
+        if (J->op == ORC_F32_BF16) {
+          for (uint64_t i = 0; i < J->nbytes / 4; ++i) { uint32_t u; memcpy(&u, scratch + 4 * i, 4); out[i] = f32bits_to_bf16(u); }
+        } else if (J->op == ORC_F16_BF16) {
+          for (uint64_t i = 0; i < J->nbytes / 2; ++i) { uint16_t h; memcpy(&h, scratch + 2 * i, 2); out[i] = f32_to_bf16(f16bits_to_f32(h)); }
+        } else if (J->op == ORC_Q4K_BF16) {
+          for (uint64_t i = 0; i < J->nbytes / 144; ++i) q4k_block(scratch + 144 * i, out + 256 * i);
+        } else err = -1;
+      }
+      free(scratch);
+    }
+  }
+  for (uint32_t i = 0; i < n_shards; ++i)
+    if (fds[i] >= 0) close(fds[i]);
+  free(fds);
+  return err;
+}
+
+int orc_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}

@@ -1,0 +1,475 @@
+"""CPU oracle for the model-hub weight-load path.  TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may import this module.  The product (``kukeon_b200`` / ``libkukeon_gpuload.so``) never does, and has
+no CPU fallback.
+
+PARITY UNPINNED AGAINST THE REFERENCE: eminwux/kukeon @ 4be245a contains no weight loader at all
+(``internal/modelhub`` is the orchestrator's resource data model — ``internal/modelhub/cell.go:21``,
+``container.go:21``) and its ``go.mod`` pulls no safetensors/GGUF module, so there is no
+reference code, call site, test or golden vector for this path.  The oracle is therefore a restatement of
+the *published file formats*, pinned instead against the format owners' own libraries installed in the
+image:
+
+* safetensors 0.7.0  — header layout, validation rules  (``tests/test_oracle_index.py``)
+* gguf 0.19.0        — GGUF v3 header, ``quants.Q4_K.dequantize_blocks`` (gguf/quants.py:475-521)
+* torch 2.11         — fp32/fp16 -> bf16 round-to-nearest-even
+
+Everything here is plain Python/numpy so that it can be read next to those sources.  Heavy loops have a
+C twin in ``oracle/kk_oracle.c`` (same arithmetic, OpenMP) used for full-size checks and the CPU baseline.
+"""
+from __future__ import annotations
+
+import json
+import os
+import struct
+from typing import Dict, List, Tuple
+
+import numpy as np
+
+# ---------------------------------------------------------------------------------------------
+# dtypes
+# ---------------------------------------------------------------------------------------------
+# safetensors Dtype names -> bits per element (safetensors/src/tensor.rs `Dtype::bitsize`)
+ST_BITS = {
+    "BOOL": 8, "F4": 4, "F6_E2M3": 6, "F6_E3M2": 6, "U8": 8, "I8": 8, "F8_E5M2": 8, "F8_E4M3": 8,
+    "F8_E8M0": 8, "I16": 16, "U16": 16, "F16": 16, "BF16": 16, "I32": 32, "U32": 32, "F32": 32,
+    "C64": 64, "F64": 64, "I64": 64, "U64": 64,
+}
+# ggml type id -> (name, elements per block, bytes per block)   (gguf/constants.py GGML_QUANT_SIZES)
+GGML_TYPES = {
+    0: ("F32", 1, 4), 1: ("F16", 1, 2), 2: ("Q4_0", 32, 18), 3: ("Q4_1", 32, 20), 6: ("Q5_0", 32, 22),
+    7: ("Q5_1", 32, 24), 8: ("Q8_0", 32, 34), 10: ("Q2_K", 256, 84), 11: ("Q3_K", 256, 110),
+    12: ("Q4_K", 256, 144), 13: ("Q5_K", 256, 176), 14: ("Q6_K", 256, 210), 15: ("Q8_K", 256, 292),
+    24: ("I8", 1, 1), 25: ("I16", 1, 2), 26: ("I32", 1, 4), 27: ("I64", 1, 8), 28: ("F64", 1, 8),
+    30: ("BF16", 1, 2),
+}
+POOL_ALIGN = 256
+
+
+class OracleError(ValueError):
+    """Malformed checkpoint (what the product reports as KK_EFORMAT / KK_EUNSUPPORTED)."""
+
+
+# ---------------------------------------------------------------------------------------------
+# index ("Pull")
+# ---------------------------------------------------------------------------------------------
+def index_safetensors(path: str, shard: int = 0) -> List[dict]:
+    """safetensors layout: u64 LE N | N bytes JSON | data.  Validation = the reader's rules probed in
+    SURVEY.md Appendix C.3: offsets sorted, gap-free from 0, covering the data section exactly;
+    byte size == prod(shape) * dtype bits / 8; header <= 100,000,000 bytes."""
+    size = os.path.getsize(path)
+    with open(path, "rb") as f:
+        head = f.read(8)
+        if len(head) < 8:
+            raise OracleError("header too small")
+        (n,) = struct.unpack("<Q", head)
+        if n > 100_000_000:
+            raise OracleError("header too large")
+        if n > size - 8:
+            raise OracleError("invalid header length")
+        raw = f.read(n)
+    if not raw.startswith(b"{"):
+        raise OracleError("invalid header start")
+    try:
+        pairs = json.loads(raw.decode("utf-8"), object_pairs_hook=list)
+    except Exception as e:  # noqa: BLE001
+        raise OracleError(f"invalid header deserialization: {e}") from e
+    ents = []
+    seen = set()
+    for name, info in pairs:
+        if name == "__metadata__":
+            if not isinstance(info, list) or any(not isinstance(v, str) for _, v in info):
+                raise OracleError("bad __metadata__")
+            continue
+        if name in seen:
+            raise OracleError(f"duplicate tensor {name}")
+        seen.add(name)
+        d = dict(info) if isinstance(info, list) else None
+        if d is None or "dtype" not in d or "shape" not in d or "data_offsets" not in d:
+            raise OracleError(f"bad tensor entry {name}")
+        if d["dtype"] not in ST_BITS:
+            raise OracleError(f"unknown variant `{d['dtype']}`")
+        b, e = d["data_offsets"]
+        ents.append((b, e, name, d["dtype"], [int(x) for x in d["shape"]]))
+    ents.sort(key=lambda t: (t[0], t[1]))
+    data_start = 8 + n
+    cur = 0
+    out = []
+    for b, e, name, dt, shape in ents:
+        if b != cur or e < b:
+            raise OracleError(f"invalid offset for tensor `{name}`")
+        cur = e
+        nel = 1
+        for s in shape:
+            nel *= s
+        nbits = nel * ST_BITS[dt]
+        if nbits % 8 or nbits // 8 != e - b:
+            raise OracleError(f"invalid shape, data type, or offset for tensor `{name}`")
+        out.append(dict(name=name, dtype=dt, shape=shape, shard=shard, file_offset=data_start + b, nbytes=e - b))
+    if data_start + cur != size:
+        raise OracleError("incomplete metadata, file not fully covered")
+    return out
+
+
+def _gguf_skip(buf: memoryview, off: int, vt: int) -> int:
+    scalar = {0: 1, 1: 1, 7: 1, 2: 2, 3: 2, 4: 4, 5: 4, 6: 4, 10: 8, 11: 8, 12: 8}
+    if vt in scalar:
+        return off + scalar[vt]
+    if vt == 8:
+        (ln,) = struct.unpack_from("<Q", buf, off)
+        return off + 8 + ln
+    if vt == 9:
+        et, cnt = struct.unpack_from("<IQ", buf, off)
+        off += 12
+        if et in scalar:
+            return off + scalar[et] * cnt
+        for _ in range(cnt):
+            off = _gguf_skip(buf, off, et)
+        return off
+    raise OracleError(f"unknown GGUF value type {vt}")
+
+
+def index_gguf(path: str, shard: int = 0) -> List[dict]:
+    """GGUF v2/v3 (gguf-py gguf_reader.py:132-186, :259-345): `<IIQQ` magic/version/n_tensors/n_kv, KVs,
+    tensor infos (name, n_dims, ne[] innermost-first, ggml type, offset), data at the next multiple of
+    general.alignment (default 32).  Shapes are reported outermost-first."""
+    size = os.path.getsize(path)
+    with open(path, "rb") as f:
+        buf = memoryview(f.read(min(size, 1 << 28)))  # headers are far smaller than 256 MiB
+    if len(buf) < 24:
+        raise OracleError("too small for a GGUF header")
+    magic, version, n_tensors, n_kv = struct.unpack_from("<IIQQ", buf, 0)
+    if magic != 0x46554747:
+        raise OracleError("GGUF magic invalid")
+    if version not in (2, 3):
+        raise OracleError(f"GGUF version {version} unsupported")
+    off = 24
+    alignment = 32
+    try:
+        for _ in range(n_kv):
+            (kl,) = struct.unpack_from("<Q", buf, off)
+            key = bytes(buf[off + 8: off + 8 + kl]).decode("utf-8")
+            off += 8 + kl
+            (vt,) = struct.unpack_from("<I", buf, off)
+            off += 4
+            if key == "general.alignment":
+                if vt != 4:
+                    raise OracleError("bad type for general.alignment")
+                (alignment,) = struct.unpack_from("<I", buf, off)
+                if alignment == 0 or alignment & (alignment - 1):
+                    raise OracleError("invalid alignment")
+            off = _gguf_skip(buf, off, vt)
+        infos = []
+        for _ in range(n_tensors):
+            (nl,) = struct.unpack_from("<Q", buf, off)
+            name = bytes(buf[off + 8: off + 8 + nl]).decode("utf-8")
+            off += 8 + nl
+            (nd,) = struct.unpack_from("<I", buf, off)
+            off += 4
+            ne = list(struct.unpack_from(f"<{nd}Q", buf, off))
+            off += 8 * nd
+            gt, rel = struct.unpack_from("<IQ", buf, off)
+            off += 12
+            infos.append((name, ne, gt, rel))
+    except struct.error as e:
+        raise OracleError(f"truncated GGUF header: {e}") from e
+    data_start = (off + alignment - 1) // alignment * alignment
+    out = []
+    names = set()
+    for name, ne, gt, rel in infos:
+        if name in names:
+            raise OracleError(f"duplicated tensor {name}")
+        names.add(name)
+        if gt not in GGML_TYPES:
+            raise OracleError(f"ggml type {gt} unsupported")
+        tname, bel, bby = GGML_TYPES[gt]
+        nel = 1
+        for d in ne:
+            nel *= d
+        if bel > 1 and (not ne or ne[0] % bel):
+            raise OracleError(f"tensor {name}: row not a multiple of the block size")
+        nbytes = nel // bel * bby
+        if rel % alignment:
+            raise OracleError(f"tensor {name}: misaligned data offset")
+        if data_start + rel + nbytes > size:
+            raise OracleError(f"tensor {name}: data out of file bounds")
+        out.append(dict(name=name, dtype=tname, shape=list(reversed(ne)), shard=shard,
+                        file_offset=data_start + rel, nbytes=nbytes))
+    return out
+
+
+def _canon_sort(recs: List[dict]) -> List[dict]:
+    return sorted(recs, key=lambda r: (r["shard"], r["file_offset"], r["nbytes"], r["name"]))
+
+
+def index_path(path: str) -> Tuple[List[str], List[dict]]:
+    """Resolve a checkpoint path exactly the way kk_index documents it; returns (shard paths, records
+    sorted by (shard, file_offset))."""
+    path = os.path.realpath(path)
+    if os.path.isdir(path):
+        idx = os.path.join(path, "model.safetensors.index.json")
+        if os.path.isfile(idx):
+            return _index_sharded(idx)
+        if os.path.isfile(os.path.join(path, "model.safetensors")):
+            files, kind = ["model.safetensors"], "st"
+        else:
+            st = sorted(f for f in os.listdir(path) if f.endswith(".safetensors") and os.path.isfile(os.path.join(path, f)))
+            gg = sorted(f for f in os.listdir(path) if f.endswith(".gguf") and os.path.isfile(os.path.join(path, f)))
+            if st:
+                files, kind = st, "st"
+            elif gg:
+                files, kind = gg, "gguf"
+            else:
+                raise FileNotFoundError(path)
+        shards = [os.path.join(path, f) for f in files]
+    else:
+        if not os.path.isfile(path):
+            raise FileNotFoundError(path)
+        if path.endswith(".index.json"):
+            return _index_sharded(path)
+        with open(path, "rb") as f:
+            sniff = f.read(4)
+        kind = "gguf" if (path.endswith(".gguf") or sniff == b"GGUF") and not path.endswith(".safetensors") else "st"
+        shards = [path]
+    recs: List[dict] = []
+    for i, s in enumerate(shards):
+        recs += index_gguf(s, i) if kind == "gguf" else index_safetensors(s, i)
+    _check_unique(recs)
+    return shards, _canon_sort(recs)
+
+
+def _check_unique(recs):
+    names = set()
+    for r in recs:
+        if r["name"] in names:
+            raise OracleError(f"tensor {r['name']} appears in more than one shard")
+        names.add(r["name"])
+
+
+def _index_sharded(index_json: str) -> Tuple[List[str], List[dict]]:
+    """HF sharded layout: weight_map name -> shard file; shards numbered in
+    file-name order."""
+    with open(index_json, "rb") as f:
+        doc = json.loads(f.read().decode("utf-8"))
+    wm = doc.get("weight_map") if isinstance(doc, dict) else None
+    if not isinstance(wm, dict) or not wm:
+        raise OracleError("no weight_map")
+    files = sorted(set(wm.values()))
+    d = os.path.dirname(index_json)
+    shards = [os.path.join(d, f) for f in files]
+    recs: List[dict] = []
+    for i, s in enumerate(shards):
+        recs += index_safetensors(s, i)
+    _check_unique(recs)
+    where = {r["name"]: r["shard"] for r in recs}
+    for name, fn in wm.items():
+        if name not in where or where[name] != files.index(fn):
+            raise OracleError(f"weight_map entry {name} does not match shard contents")
+    return shards, _canon_sort(recs)
+
+
+# ---------------------------------------------------------------------------------------------
+# value conversions (bit-level, numpy)
+# ---------------------------------------------------------------------------------------------
+def f32_bits_to_bf16(u32: np.ndarray) -> np.ndarray:
+    """fp32 bit patterns -> bf16 bit patterns, round-to-nearest-even; any NaN -> 0x7FFF (the canonical
+    NaN of PTX `cvt.rn.bf16x2.f32`, which the product uses; torch's CPU cast agrees on every non-NaN)."""
+    u = u32.astype(np.uint32, copy=False)
+    nan = (u & np.uint32(0x7FFFFFFF)) > np.uint32(0x7F800000)
+    lsb = (u >> np.uint32(16)) & np.uint32(1)
+    r = ((u.astype(np.uint64) + np.uint64(0x7FFF) + lsb.astype(np.uint64)) >> np.uint64(16)).astype(np.uint16)
+    r[nan] = 0x7FFF
+    return r
+
+
+def f32_to_bf16(x: np.ndarray) -> np.ndarray:
+    return f32_bits_to_bf16(np.ascontiguousarray(x, dtype=np.float32).view(np.uint32))
+
+
+def f16_bits_to_bf16(u16: np.ndarray) -> np.ndarray:
+    """fp16 -> fp32 is exact (subnormals become normals), then RNE to bf16."""
+    return f32_to_bf16(np.ascontiguousarray(u16, dtype=np.uint16).view(np.float16).astype(np.float32))
+
+
+def q4k_scale_min(scales: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """6-bit packed (scale, min) of the 8 sub-blocks; gguf/quants.py:479-501 restated with explicit
+    indices (j<4: sc=s[j]&63, m=s[j+4]&63; j>=4: sc=(s[j+4]&15)|((s[j-4]>>6)<<4), m=(s[j+4]>>4)|((s[j]>>6)<<4))."""
+    s = scales.astype(np.uint8)
+    sc = np.empty(s.shape[:-1] + (8,), np.uint8)
+    mn = np.empty_like(sc)
+    for j in range(8):
+        if j < 4:
+            sc[..., j] = s[..., j] & 63
+            mn[..., j] = s[..., j + 4] & 63
+        else:
+            sc[..., j] = (s[..., j + 4] & 0x0F) | ((s[..., j - 4] >> 6) << 4)
+            mn[..., j] = (s[..., j + 4] >> 4) | ((s[..., j] >> 6) << 4)
+    return sc, mn
+
+
+def dequant_q4k_f32(blocks: np.ndarray) -> np.ndarray:
+    """[n,144] uint8 -> [n,256] float32, y = (d*sc)*q - (dmin*m) with each product and the difference
+    rounded to fp32 separately (gguf/quants.py:504-521)."""
+    b = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, 144)
+    n = b.shape[0]
+    d = b[:, 0:2].copy().view(np.float16).astype(np.float32).reshape(n, 1)
+    dmin = b[:, 2:4].copy().view(np.float16).astype(np.float32).reshape(n, 1)
+    sc, mn = q4k_scale_min(b[:, 4:16])
+    with np.errstate(all="ignore"):
+        dsc = (d * sc.astype(np.float32)).astype(np.float32)   # [n,8]
+        dmn = (dmin * mn.astype(np.float32)).astype(np.float32)
+        qs = b[:, 16:144].reshape(n, 4, 32)
+        q = np.empty((n, 8, 32), np.float32)
+        q[:, 0::2, :] = (qs & 0x0F).astype(np.float32)
+        q[:, 1::2, :] = (qs >> 4).astype(np.float32)
+        prod = (dsc[:, :, None] * q).astype(np.float32)
+        y = (prod - dmn[:, :, None]).astype(np.float32)
+    return y.reshape(n, 256)
+
+
+def dequant_q4k_bf16(blocks: np.ndarray) -> np.ndarray:
+    return f32_to_bf16(dequant_q4k_f32(blocks)).reshape(-1, 256)
+
+
+_MASK = (1 << 64) - 1
+
+
+def checksum(data: bytes | np.ndarray) -> int:
+    """kk_checksum: sum_i mix(w_i + i*0x9E3779B97F4A7C15) mod 2^64 over little-endian 8-byte words
+    (tail zero-padded); mix = splitmix64 finaliser."""
+    a = np.frombuffer(bytes(data) if not isinstance(data, np.ndarray) else data.tobytes(), dtype=np.uint8)
+    pad = (-len(a)) % 8
+    if pad:
+        a = np.concatenate([a, np.zeros(pad, np.uint8)])
+    w = a.view("<u8").astype(np.uint64)
+    i = np.arange(len(w), dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        x = w + i * np.uint64(0x9E3779B97F4A7C15)
+        x ^= x >> np.uint64(30)
+        x *= np.uint64(0xBF58476D1CE4E5B9)
+        x ^= x >> np.uint64(27)
+        x *= np.uint64(0x94D049BB133111EB)
+        x ^= x >> np.uint64(31)
+        return int(np.sum(x, dtype=np.uint64))
+
+
+# ---------------------------------------------------------------------------------------------
+# pool layout + expected pool contents ("Load")
+# ---------------------------------------------------------------------------------------------
+GPT2_CONV1D = ("attn.c_attn.weight", "attn.c_proj.weight", "mlp.c_fc.weight", "mlp.c_proj.weight")
+SCATTER_DIM0 = ("q_proj.weight", "k_proj.weight", "v_proj.weight", "gate_proj.weight", "up_proj.weight",
+                "embed_tokens.weight", "lm_head.weight", "attn_q.weight", "attn_k.weight", "attn_v.weight",
+                "ffn_gate.weight", "ffn_up.weight", "token_embd.weight", "output.weight")
+SCATTER_DIM1 = ("o_proj.weight", "down_proj.weight", "attn_output.weight", "ffn_down.weight")
+MODE_SINGLE, MODE_BROADCAST, MODE_SCATTER = 0, 1, 2
+LOAD_GPT2_CONV1D_T, LOAD_KEEP_F32 = 0x1, 0x2
+_ELEM_BYTES = {k: v // 8 for k, v in ST_BITS.items() if v % 8 == 0}
+_ELEM_BYTES.update({"F32": 4, "F16": 2, "BF16": 2, "I8": 1, "I16": 2, "I32": 4, "I64": 8, "F64": 8})
+
+
+def pool_dtype(dt: str, flags: int = 0) -> str:
+    if dt in ("F16", "BF16", "Q4_K"):
+        return "BF16"
+    if dt == "F32":
+        return "F32" if flags & LOAD_KEEP_F32 else "BF16"
+    return dt
+
+
+def slice_dim(rec: dict, n_parts: int):
+    """[PROPOSED] scatter rule: column-parallel weights sliced along dim 0,
+    row-parallel along dim 1, everything else (1-D, >2-D, indivisible, dim-1 of block-quantised) whole."""
+    if n_parts <= 1 or len(rec["shape"]) != 2:
+        return None
+    n = rec["name"]
+    dim = None
+    if any(n.endswith(s) for s in SCATTER_DIM1):
+        dim = 1
+    elif any(n.endswith(s) for s in SCATTER_DIM0) and "norm" not in n:
+        dim = 0
+    if dim is None or rec["shape"][dim] % n_parts:
+        return None
+    if rec["dtype"] in ("F4", "F6_E2M3", "F6_E3M2"):
+        return None
+    if rec["dtype"].startswith("Q") and dim == 1:
+        return None
+    return dim
+
+
+def plan_pool(recs: List[dict], mode: int = MODE_SINGLE, flags: int = 0, n_parts: int = 1, part: int = 0) -> Tuple[List[dict], int]:
+    """Pool placement of every tensor for one device: index order, 256-byte aligned slots."""
+    off = 0
+    out = []
+    for r in recs:
+        pdt = pool_dtype(r["dtype"], flags)
+        shape = list(r["shape"])
+        p = dict(name=r["name"], dtype=pdt, slice_dim=None, slice_begin=0)
+        tr = bool(flags & LOAD_GPT2_CONV1D_T) and mode != MODE_SCATTER and len(shape) == 2 and \
+            any(r["name"].endswith(s) for s in GPT2_CONV1D) and r["dtype"] in ("F32", "F16", "BF16", "I16", "U16", "I32", "U32")
+        if tr:
+            shape = [shape[1], shape[0]]
+        sd = slice_dim(r, n_parts) if mode == MODE_SCATTER else None
+        if sd is not None:
+            k = shape[sd] // n_parts
+            p["slice_dim"], p["slice_begin"] = sd, k * part
+            shape[sd] = k
+        nel = 1
+        for s in shape:
+            nel *= s
+        if r["dtype"].startswith("Q"):
+            nbytes = nel * 2
+        elif pdt in _ELEM_BYTES:
+            nbytes = nel * _ELEM_BYTES[pdt]
+        else:  # sub-byte verbatim
+            nbytes = r["nbytes"]
+        p.update(shape=shape, transposed=tr, pool_offset=off, nbytes=nbytes)
+        out.append(p)
+        off = (off + nbytes + POOL_ALIGN - 1) // POOL_ALIGN * POOL_ALIGN
+    return out, (off or POOL_ALIGN)
+
+
+def convert_tensor(rec: dict, raw: bytes, flags: int = 0) -> np.ndarray:
+    """File bytes of one tensor -> pool bytes (uint8 array), before any slicing/transposition."""
+    dt = rec["dtype"]
+    a = np.frombuffer(raw, dtype=np.uint8)
+    if dt == "F32" and not (flags & LOAD_KEEP_F32):
+        return f32_bits_to_bf16(a.view("<u4")).view(np.uint8)
+    if dt == "F16":
+        return f16_bits_to_bf16(a.view("<u2")).view(np.uint8)
+    if dt == "Q4_K":
+        return dequant_q4k_bf16(a.reshape(-1, 144)).reshape(-1).view(np.uint8)
+    if dt.startswith("Q"):
+        raise OracleError(f"{dt} dequantisation not defined by this oracle")
+    return a.copy()
+
+
+def expected_pool(shards: List[str], recs: List[dict], mode: int = MODE_SINGLE, flags: int = 0,
+                  n_parts: int = 1, part: int = 0) -> Tuple[np.ndarray, List[dict]]:
+    """Whole expected pool of one device as a uint8 array (gaps zero).  Small checkpoints only."""
+    plan, total = plan_pool(recs, mode, flags, n_parts, part)
+    pool = np.zeros(total, np.uint8)
+    fhs = [open(s, "rb") for s in shards]
+    try:
+        for r, p in zip(recs, plan):
+            fh = fhs[r["shard"]]
+            fh.seek(r["file_offset"])
+            raw = fh.read(r["nbytes"])
+            assert len(raw) == r["nbytes"]
+            out = convert_tensor(r, raw, flags)
+            es = out.size // max(1, int(np.prod(r["shape"]))) if int(np.prod(r["shape"])) else 1
+            if p["transposed"]:
+                R, C = r["shape"]
+                out = np.ascontiguousarray(out.reshape(R, C, es).transpose(1, 0, 2)).reshape(-1)
+            elif p["slice_dim"] is not None:
+                R, C = r["shape"]
+                v = out.reshape(R, C, es)
+                k = p["shape"][p["slice_dim"]]
+                b = p["slice_begin"]
+                v = v[b:b + k] if p["slice_dim"] == 0 else v[:, b:b + k]
+                out = np.ascontiguousarray(v).reshape(-1)
+            assert out.size == p["nbytes"], (r["name"], out.size, p["nbytes"])
+            pool[p["pool_offset"]: p["pool_offset"] + out.size] = out
+    finally:
+        for fh in fhs:
+            fh.close()
+    return pool, plan

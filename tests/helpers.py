@@ -1,0 +1,99 @@
+"""Test helpers: small checkpoint builders and a CPU emulator of kk_plan_describe output."""
+from __future__ import annotations
+
+import json
+import os
+import struct
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+
+from oracle import oracle
+
+OP_COPY, OP_F32, OP_F16, OP_Q4K, OP_T_F32_BF16, OP_T_F16_BF16, OP_T_B16, OP_T_B32 = range(8)
+
+
+def emulate_part(plan: dict, part: int, pool_bytes: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Execute one part of a kk_plan_describe plan on the CPU with the oracle's arithmetic.
+    Returns (pool, written-mask).  This checks the planner (reads, segments, offsets), not the kernels."""
+    pool = np.zeros(pool_bytes, np.uint8)
+    mask = np.zeros(pool_bytes, bool)
+    fhs = [open(s, "rb") for s in plan["shards"]]
+    try:
+        for ch in plan["parts"][part]["chunks"]:
+            buf = np.zeros(ch["buf_bytes"] + 64, np.uint8)
+            fh = fhs[ch["shard"]]
+            for fo, ln, bo in ch["reads"]:
+                fh.seek(fo)
+                raw = fh.read(ln)
+                assert len(raw) == ln
+                buf[bo:bo + ln] = np.frombuffer(raw, np.uint8)
+            tiles = 0
+            for sg in ch["segs"]:
+                assert sg["tile_begin"] == tiles, "tile_begin must be the running tile count of the chunk"
+                op, so, do, u = sg["op"], sg["src_off"], sg["dst_off"], sg["units"]
+                assert do % 16 == 0
+                if op == OP_COPY:
+                    out = buf[so:so + u]
+                    tiles += -(-u // 32768)
+                elif op == OP_F32:
+                    out = oracle.f32_bits_to_bf16(buf[so:so + 4 * u].copy().view("<u4")).view(np.uint8)
+                    tiles += -(-u // 8192)
+                elif op == OP_F16:
+                    out = oracle.f16_bits_to_bf16(buf[so:so + 2 * u].copy().view("<u2")).view(np.uint8)
+                    tiles += -(-u // 16384)
+                elif op == OP_Q4K:
+                    out = oracle.dequant_q4k_bf16(buf[so:so + 144 * u].reshape(-1, 144)).reshape(-1).view(np.uint8)
+                    tiles += -(-u // 224)
+                else:
+                    C, R, r0 = sg["p0"], sg["p1"], sg["p2"]
+                    es = 4 if op in (OP_T_F32_BF16, OP_T_B32) else 2
+                    src = buf[so:so + u * C * es].reshape(u, C, es)
+                    if op == OP_T_F32_BF16:
+                        v = oracle.f32_bits_to_bf16(src.reshape(-1).copy().view("<u4")).view(np.uint8).reshape(u, C, 2)
+                    elif op == OP_T_F16_BF16:
+                        v = oracle.f16_bits_to_bf16(src.reshape(-1).copy().view("<u2")).view(np.uint8).reshape(u, C, 2)
+                    else:
+                        v = src
+                    oes = v.shape[2]
+                    dst = pool[do:do + C * R * oes].reshape(C, R, oes)
+                    dst[:, r0:r0 + u, :] = v.transpose(1, 0, 2)
+                    mask[do:do + C * R * oes].reshape(C, R, oes)[:, r0:r0 + u, :] = True
+                    tiles += -(-u // 32) * -(-C // 64)
+                    continue
+                assert not mask[do:do + out.size].any(), "segment overlaps an earlier one"
+                pool[do:do + out.size] = out
+                mask[do:do + out.size] = True
+            assert tiles == ch["n_tiles"]
+    finally:
+        for fh in fhs:
+            fh.close()
+    return pool, mask
+
+
+def expected_mask(plan_pool: List[dict], total: int) -> np.ndarray:
+    m = np.zeros(total, bool)
+    for p in plan_pool:
+        m[p["pool_offset"]:p["pool_offset"] + p["nbytes"]] = True
+    return m
+
+
+def write_raw_safetensors(path: str, header: dict | bytes, data: bytes, n_override: int | None = None) -> None:
+    raw = header if isinstance(header, bytes) else json.dumps(header, separators=(",", ":")).encode()
+    with open(path, "wb") as f:
+        f.write(struct.pack("<Q", len(raw) if n_override is None else n_override))
+        f.write(raw)
+        f.write(data)
+
+
+def mixed_safetensors(path: str, seed: int = 11, pad_header: bool = True) -> List[Tuple[str, str, List[int]]]:
+    """A small file that exercises every op: bf16 copy, f32/f16 casts, verbatim ints, ragged tails,
+    zero-size and scalar tensors."""
+    from tools import synth
+    tensors = [
+        ("a.bf16", "BF16", [33, 77]), ("b.f32", "F32", [129, 65]), ("c.f16", "F16", [7, 1001]), ("d.i64", "I64", [5, 3]),
+        ("e.u8", "U8", [1021]), ("f.empty", "F32", [0]), ("g.scalar", "F32", []), ("h.bf16.big", "BF16", [700, 1024]),
+        ("i.f32.odd", "F32", [3]), ("j.f16.one", "F16", [1]), ("k.bool", "BOOL", [13]),
+    ]
+    synth.write_safetensors(path, tensors, seed, pad_header=pad_header)
+    return tensors

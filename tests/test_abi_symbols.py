@@ -1,0 +1,61 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/kukeon_gpuload.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from kukeon_b200 import gpupool
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "kukeon_gpuload.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(kk_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_symbols_all_exported(native):
+    syms = declared_symbols()
+    assert len(syms) >= 25
+    L = ctypes.CDLL(gpupool.lib_path())
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+    assert sorted(gpupool.ABI_SYMBOLS) == syms, "gpupool.ABI_SYMBOLS must list exactly the header's functions"
+
+
+def test_abi_version_and_status_names(native):
+    assert native.kk_abi_version() == 1
+    assert native.kk_status_name(0) == b"KK_OK"
+    assert native.kk_status_name(-6) == b"KK_ECUDA"
+    assert native.kk_status_name(-3) == b"KK_EFORMAT"
+
+
+def test_struct_sizes_match_header():
+    # layouts the Go/cgo side would mirror; sizes computed from the header by hand
+    assert ctypes.sizeof(gpupool.KKConfig) == 4 + 32 + 4 + 8 + 4 + 4 + 8 + 4 + 4  # with natural padding = 72
+    assert ctypes.sizeof(gpupool.KKTensorMeta) == 256 + 4 + 4 + 64 + 4 + 4 + 8 + 8
+    assert ctypes.sizeof(gpupool.KKPlacement) == 4 + 4 + 8 + 8 + 4 + 4 + 64 + 8
+    assert ctypes.sizeof(gpupool.KKLoadOpts) == 32
+
+
+def test_null_arguments_are_rejected_not_crashed(native):
+    assert native.kk_open(None, None) == -1
+    assert b"NULL" in native.kk_last_error()
+    assert native.kk_close(None) == -1
+    assert native.kk_release(None) == -1
+    assert native.kk_index(None, None, None, None) == -1
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(gpupool, "_lib", None)
+    monkeypatch.setattr(gpupool, "lib_path", lambda: str(tmp_path / "nope.so"))
+    with pytest.raises(ImportError, match="no CPU fallback"):
+        gpupool.lib()
+
+
+@pytest.mark.skipif(__import__("torch").cuda.is_available(), reason="CPU-only behaviour")
+def test_no_gpu_means_error_not_fallback(native):
+    with pytest.raises(gpupool.ErrCUDA):
+        gpupool.Pool([0])

@@ -1,0 +1,313 @@
+"""GPU parity tests: everything goes through the C ABI (ctypes) and is compared bit for bit with the oracle."""
+import json
+import os
+import subprocess
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+from kukeon_b200 import gpupool, modelhub
+from oracle import oracle
+from tests import helpers
+from tools import synth
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MB = 1 << 20
+
+
+def assert_pool_matches(m, device, shards, recs, mode=0, flags=0, n_parts=1, part=0):
+    exp, plan = oracle.expected_pool(shards, recs, mode, flags, n_parts, part)
+    got = m.read(device, 0, len(exp))
+    for p in plan:
+        a, b = p["pool_offset"], p["pool_offset"] + p["nbytes"]
+        if not np.array_equal(got[a:b], exp[a:b]):
+            bad = np.flatnonzero(got[a:b] != exp[a:b])
+            raise AssertionError(f"{p['name']} ({p['dtype']} {p['shape']}): {bad.size} bytes differ, first at +{bad[0]}")
+    return exp, plan
+
+
+def load_and_check(pool, path, **kw):
+    shards, recs = oracle.index_path(path)
+    m = pool.load(path, **kw)
+    try:
+        assert m.tensors() == recs
+        exp, plan = assert_pool_matches(m, pool.devices[0], shards, recs, flags=kw.get("flags", 0))
+        for p in plan[:4]:
+            assert m.checksum(pool.devices[0], p["pool_offset"], p["nbytes"]) == oracle.checksum(exp[p["pool_offset"]:p["pool_offset"] + p["nbytes"]])
+        return m.stats()
+    finally:
+        m.release()
+
+
+def test_mixed_safetensors_every_op(pool, tmp_path):
+    p = str(tmp_path / "m.safetensors")
+    helpers.mixed_safetensors(p)
+    st = load_and_check(pool, p)
+    assert st["n_loads"] == 1 and st["file_bytes"] == sum(r["nbytes"] for r in oracle.index_path(p)[1])
+
+
+def test_unpadded_header_exercises_the_misaligned_path(pool, tmp_path):
+    # an unpadded header shifts every tensor off 16-byte alignment relative to its neighbours' sizes
+    for pad in (False, True):
+        p = str(tmp_path / f"m{int(pad)}.safetensors")
+        tensors = [("a", "BF16", [7]), ("b", "BF16", [33, 77]), ("c", "F32", [129, 65]), ("d", "F16", [7, 1001]), ("e", "U8", [3]),
+                   ("f", "BF16", [4099]), ("g", "F32", [5]), ("h", "F16", [2, 3]), ("i", "U8", [1021]), ("j", "BF16", [64, 512])]
+        synth.write_safetensors(p, tensors, 5, pad_header=pad)
+        load_and_check(pool, p)
+
+
+def test_golden_files(pool):
+    load_and_check(pool, os.path.join(G, "st_mixed.safetensors"))
+    load_and_check(pool, os.path.join(G, "sharded"))
+    load_and_check(pool, os.path.join(G, "q4k.gguf"))
+
+
+def test_golden_q4k_values_vs_gguf_py_fixture(pool):
+    p = os.path.join(G, "q4k.gguf")
+    outs = np.load(p + ".bf16.npz")
+    m = pool.load(p)
+    try:
+        for name in outs.files:
+            pl = m.placements(name)[0]
+            got = m.read(0, pl.pool_offset, pl.nbytes).view(np.uint16)
+            assert pl.dtype == "BF16" and np.array_equal(got, outs[name]), name
+    finally:
+        m.release()
+
+
+def test_llama_multishard_small_chunks(native, tmp_path):
+    d = str(tmp_path / "llama")
+    synth.make_llama(d, dict(hidden=256, ffn=704, layers=3, kv_dim=64, vocab=3000), max_shard_bytes=3_000_000)
+    with gpupool.Pool([0], n_staging_buffers=4, staging_buffer_bytes=1 * MB, n_reader_threads=2) as pl:
+        st = load_and_check(pl, d)
+        assert st["parts"][0]["chunks"] > 8
+        load_and_check(pl, d, mode=gpupool.MODE_BROADCAST)  # one device: degenerates to a single load
+
+
+def test_mixtral_style_gguf_q4k(pool, tmp_path):
+    p = str(tmp_path / "mix.gguf")
+    synth.write_gguf(p, synth.mixtral_gguf_tensors(hidden=256, ffn=768, layers=2, experts=2, vocab=512, kv_dim=256), 7)
+    load_and_check(pool, p)
+
+
+def test_q4k_many_blocks_vs_c_oracle(pool, tmp_path, coracle):
+    p = str(tmp_path / "big.gguf")
+    synth.write_gguf(p, [("w", "Q4_K", [2048, 4096]), ("n", "F32", [4096])], 11)  # 32768 blocks, 16 MiB of bf16
+    shards, recs = oracle.index_path(p)
+    m = pool.load(p)
+    try:
+        r = [x for x in recs if x["name"] == "w"][0]
+        raw = np.fromfile(p, np.uint8, count=r["nbytes"], offset=r["file_offset"])
+        want = coracle.q4k_to_bf16(raw).reshape(-1)
+        pl = m.placements("w")[0]
+        got = m.read(0, pl.pool_offset, pl.nbytes).view(np.uint16)
+        assert np.array_equal(got, want)
+        assert m.checksum(0, pl.pool_offset, pl.nbytes) == coracle.checksum(want)
+    finally:
+        m.release()
+
+
+def test_gpt2_conv1d_transpose(pool, tmp_path):
+    p = str(tmp_path / "gpt2.safetensors")
+    synth.make_gpt2(p, n_layer=2, d=96, vocab=301, n_pos=40)
+    load_and_check(pool, p, flags=gpupool.LOAD_GPT2_CONV1D_T)
+    load_and_check(pool, p, flags=gpupool.LOAD_GPT2_CONV1D_T | gpupool.LOAD_KEEP_F32)
+    for dt in ("F16", "BF16"):
+        q = str(tmp_path / f"gpt2_{dt}.safetensors")
+        synth.write_safetensors(q, synth.gpt2_tensors(n_layer=1, d=40, vocab=50, n_pos=8, dtype=dt), 3)
+        load_and_check(pool, q, flags=gpupool.LOAD_GPT2_CONV1D_T)
+
+
+def test_special_values_nan_inf_subnormal(pool, tmp_path):
+    v = np.load(os.path.join(G, "cast_vectors.npz"))
+    f32 = np.concatenate([v["f32_in"], np.array([0x7FC00000, 0xFFC00000, 0x7F800001, 0xFFFFFFFF, 0x7F800000, 0xFF800000], np.uint32)])
+    f16 = np.arange(0, 1 << 16, dtype=np.uint16)  # every half, NaNs included
+    bf = np.arange(0, 1 << 16, dtype=np.uint16)   # every bf16 pattern must pass through verbatim
+    hdr, data, off = {}, b"", 0
+    for name, dt, arr in (("f32", "F32", f32), ("f16", "F16", f16), ("bf16", "BF16", bf)):
+        raw = arr.tobytes()
+        hdr[name] = {"dtype": dt, "shape": [len(arr)], "data_offsets": [off, off + len(raw)]}
+        data += raw
+        off += len(raw)
+    p = str(tmp_path / "special.safetensors")
+    helpers.write_raw_safetensors(p, hdr, data)
+    m = pool.load(p)
+    try:
+        g = lambda n: m.read(0, m.placements(n)[0].pool_offset, m.placements(n)[0].nbytes).view(np.uint16)
+        assert np.array_equal(g("f32"), oracle.f32_bits_to_bf16(f32))
+        assert np.array_equal(g("f16"), oracle.f16_bits_to_bf16(f16))
+        assert np.array_equal(g("bf16"), bf)
+    finally:
+        m.release()
+    # Q4_K with non-finite / zero / subnormal super-block scales
+    blocks = np.frombuffer(np.random.default_rng(1).bytes(144 * 64), np.uint8).reshape(64, 144).copy()
+    specials = [0x7C00, 0xFC00, 0x7E00, 0x0000, 0x8000, 0x0001, 0x7BFF, 0x03FF]
+    for i, s in enumerate(specials):
+        blocks[i, 0:2] = np.array([s], "<u2").view(np.uint8)
+        blocks[8 + i, 2:4] = np.array([s], "<u2").view(np.uint8)
+    q = str(tmp_path / "special.gguf")
+    import struct
+    head = struct.pack("<IIQQ", 0x46554747, 3, 1, 0) + struct.pack("<Q", 1) + b"w" + struct.pack("<I", 2) + struct.pack("<2Q", 256, 64) + struct.pack("<IQ", 12, 0)
+    head += b"\0" * ((-len(head)) % 32)
+    open(q, "wb").write(head + blocks.tobytes())
+    m = pool.load(q)
+    try:
+        pl = m.placements("w")[0]
+        got = m.read(0, pl.pool_offset, pl.nbytes).view(np.uint16).reshape(64, 256)
+        assert np.array_equal(got, oracle.dequant_q4k_bf16(blocks))
+    finally:
+        m.release()
+
+
+def test_eight_concurrent_sessions_share_one_load(pool, tmp_path):
+    d = str(tmp_path / "llama")
+    synth.make_llama(d, dict(hidden=128, ffn=352, layers=2, kv_dim=32, vocab=1000), max_shard_bytes=10_000_000)
+    out, errs = [None] * 8, []
+
+    def session(i):
+        try:
+            out[i] = pool.load(d)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=session, args=(i,)) for i in range(8)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs
+    assert len({m.handle for m in out}) == 1, "all sessions must get the same resident model"
+    info = out[0].info()
+    assert info["refcount"] == 8 and info["loaded"] and out[0].stats()["n_loads"] == 1
+    hooks = modelhub.CellHooks(out[0])
+    hooks.start_cell("cell-a"); hooks.start_cell("cell-a"); hooks.start_cell("cell-b")
+    assert out[0].info()["refcount"] == 10 and hooks.active == 2
+    hooks.stop_cell("cell-a"); hooks.stop_cell("cell-a"); hooks.stop_cell("cell-b")
+    assert out[0].info()["refcount"] == 8
+    with pytest.raises(gpupool.ErrBusy):
+        pool.close()
+    for m in out[:-1]:
+        m.release()
+    assert out[-1].info()["refcount"] == 1
+    shards, recs = oracle.index_path(d)
+    assert_pool_matches(out[-1], 0, shards, recs)  # still resident and intact
+    out[-1].release()
+    m2 = pool.load(d)  # a fresh load after the last release
+    assert m2.stats()["n_loads"] == 1
+    m2.release()
+
+
+_CHILD = r'''
+import sys, json, numpy as np
+from cuda.bindings import runtime as cudart
+hpath, off, n = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+h = cudart.cudaIpcMemHandle_t(); h.reserved = open(hpath, "rb").read()
+err, = cudart.cudaSetDevice(0); assert err == 0, err
+err, ptr = cudart.cudaIpcOpenMemHandle(h, cudart.cudaIpcMemLazyEnablePeerAccess); assert err == 0, err
+buf = np.empty(n, np.uint8)
+err, = cudart.cudaMemcpy(buf.ctypes.data, ptr + off, n, cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost); assert err == 0, err
+sys.stdout.write(buf.tobytes().hex())
+cudart.cudaIpcCloseMemHandle(ptr)
+'''
+
+
+def test_mount_exports_manifest_and_ipc_handle_to_another_process(pool, tmp_path):
+    p = str(tmp_path / "m.safetensors")
+    helpers.mixed_safetensors(p)
+    shards, recs = oracle.index_path(p)
+    m = pool.load(p)
+    try:
+        spec = modelhub.Mount(m, 0, str(tmp_path / "cell" / "container"))
+        man = json.load(open(os.path.join(spec.host_dir, "manifest.json")))
+        want, total = oracle.plan_pool(recs)
+        assert man["kind"] == "PoolManifest" and man["poolBytes"] == total and man["device"] == 0
+        for w, g in zip(want, man["tensors"]):
+            assert (g["name"], g["dtype"], g["shape"], g["offset"], g["nbytes"]) == (w["name"], w["dtype"], w["shape"], w["pool_offset"], w["nbytes"])
+        assert spec.mounts == [{"destination": "/run/kukeon/gpupool", "type": "bind", "source": spec.host_dir, "options": ["rbind", "ro"]}]
+        assert any(e.startswith("KUKEON_GPUPOOL_MANIFEST=") for e in spec.env)
+        assert os.path.getsize(os.path.join(spec.host_dir, "ipc.handle")) == 64
+        t = want[7]  # h.bf16.big
+        r = subprocess.run([sys.executable, "-c", _CHILD, os.path.join(spec.host_dir, "ipc.handle"), str(t["pool_offset"]), "4096"],
+                           capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr[-2000:]
+        exp, _ = oracle.expected_pool(shards, recs)
+        assert bytes.fromhex(r.stdout) == exp[t["pool_offset"]:t["pool_offset"] + 4096].tobytes()
+    finally:
+        m.release()
+
+
+def test_resident_convert_equals_streaming_load(native, tmp_path):
+    d = str(tmp_path / "llama")
+    synth.make_llama(d, dict(hidden=256, ffn=704, layers=3, kv_dim=64, vocab=3000), max_shard_bytes=3_000_000)
+    shards, recs = oracle.index_path(d)
+    with gpupool.Pool([0], n_staging_buffers=2, staging_buffer_bytes=1 * MB, n_reader_threads=1) as pl:
+        m = pl.load(d, flags=gpupool.LOAD_DEFER)
+        try:
+            assert not m.info()["loaded"]
+            m.stage_resident()
+            tot, per = m.convert_resident()
+            assert tot > 0 and len(per) == len(shards), "one launch per shard"
+            assert_pool_matches(m, 0, shards, recs)
+            m.unstage_resident()
+            with pytest.raises(gpupool.ErrState):
+                m.convert_resident()
+            m.load_part()
+            assert m.info()["loaded"]
+            assert_pool_matches(m, 0, shards, recs)
+        finally:
+            m.release()
+
+
+def test_zero_copy_staging_matches(native, tmp_path):
+    p = str(tmp_path / "m.safetensors")
+    helpers.mixed_safetensors(p)
+    with gpupool.Pool([0], n_staging_buffers=2, staging_buffer_bytes=2 * MB, n_reader_threads=1, flags=gpupool.CFG_ZEROCOPY) as pl:
+        load_and_check(pl, p)
+        load_and_check(pl, os.path.join(G, "q4k.gguf"))
+
+
+def test_pool_budget_and_error_paths(native, tmp_path):
+    p = str(tmp_path / "m.safetensors")
+    helpers.mixed_safetensors(p)
+    with gpupool.Pool([0], pool_bytes_per_device=4096, n_staging_buffers=2, staging_buffer_bytes=1 * MB, n_reader_threads=1) as pl:
+        with pytest.raises(gpupool.ErrNoMemory, match="budget"):
+            pl.load(p)
+        with pytest.raises(gpupool.ErrNotFound):
+            pl.load(str(tmp_path / "missing"))
+        with pytest.raises(gpupool.ErrInvalid):
+            pl.load(p, mode=9)
+        with pytest.raises(gpupool.ErrUnsupported):
+            pl.load(p, fanout=gpupool.FANOUT_NVLS)
+    with pytest.raises(gpupool.ErrInvalid):
+        gpupool.Pool([99])
+    with pytest.raises(gpupool.ErrInvalid):
+        gpupool.Pool([0, 0])
+
+
+def test_medium_checkpoint_checksum_of_checksums(native, tmp_path, coracle):
+    """~1 GB bf16 llama slice: size-independent property — the pool's device-side checksum per tensor equals the
+    oracle checksum of the file bytes (passthrough), and a checksum over the per-tensor checksums agrees."""
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") else str(tmp_path)
+    d = os.path.join(shm, f"kk_medium_{os.getpid()}")
+    try:
+        synth.make_llama(d, dict(hidden=2048, ffn=5632, layers=6, kv_dim=512, vocab=32000), max_shard_bytes=300_000_000)
+        shards, recs = oracle.index_path(d)
+        with gpupool.Pool([0]) as pl:
+            m = pl.load(d)
+            try:
+                sums_gpu, sums_cpu = [], []
+                for r in recs:
+                    p = m.placements(r["name"])[0]
+                    sums_gpu.append(m.checksum(0, p.pool_offset, p.nbytes))
+                    raw = np.fromfile(shards[r["shard"]], np.uint8, count=r["nbytes"], offset=r["file_offset"])
+                    sums_cpu.append(coracle.checksum(raw))
+                assert sums_gpu == sums_cpu
+                assert oracle.checksum(np.array(sums_gpu, np.uint64)) == oracle.checksum(np.array(sums_cpu, np.uint64))
+                st = m.stats()
+                assert st["file_bytes"] == sum(r["nbytes"] for r in recs) and st["load_gbps"] > 0
+            finally:
+                m.release()
+    finally:
+        import shutil
+        shutil.rmtree(d, ignore_errors=True)

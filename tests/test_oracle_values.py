@@ -1,0 +1,109 @@
+"""Pins the oracle's value arithmetic: numpy restatement == C twin == committed golden vectors ==
+format owners' libraries (torch RNE, gguf-py Q4_K) run live."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def bits16(t):
+    return t.contiguous().view(torch.int16).numpy().view(np.uint16)
+
+
+def test_f32_golden_vectors(coracle):
+    v = np.load(os.path.join(G, "cast_vectors.npz"))
+    assert (oracle.f32_bits_to_bf16(v["f32_in"]) == v["f32_out"]).all()
+    assert (coracle.f32_to_bf16(v["f32_in"]) == v["f32_out"]).all()
+
+
+def test_f16_golden_vectors_every_finite_half(coracle):
+    v = np.load(os.path.join(G, "cast_vectors.npz"))
+    assert len(v["f16_in"]) > 63000
+    assert (oracle.f16_bits_to_bf16(v["f16_in"]) == v["f16_out"]).all()
+    assert (coracle.f16_to_bf16(v["f16_in"]) == v["f16_out"]).all()
+
+
+def test_f32_random_vs_torch_live(coracle):
+    rng = np.random.default_rng(3)
+    u = rng.integers(0, 1 << 32, size=200_000, dtype=np.uint64).astype(np.uint32)
+    u = u[(u & 0x7FFFFFFF) <= 0x7F800000]  # NaN handling is implementation-defined; pinned separately below
+    ref = bits16(torch.from_numpy(u.view(np.float32).copy()).to(torch.bfloat16))
+    assert (oracle.f32_bits_to_bf16(u) == ref).all()
+    assert (coracle.f32_to_bf16(u) == ref).all()
+
+
+def test_nan_rule_is_canonical_7fff(coracle):
+    u = np.array([0x7FC00000, 0xFFC00000, 0x7F800001, 0xFFFFFFFF, 0x7FBFFFFF], np.uint32)
+    assert (oracle.f32_bits_to_bf16(u) == 0x7FFF).all()
+    assert (coracle.f32_to_bf16(u) == 0x7FFF).all()
+    h = np.array([0x7E00, 0xFE00, 0x7C01], np.uint16)
+    assert (oracle.f16_bits_to_bf16(h) == 0x7FFF).all()
+    assert (coracle.f16_to_bf16(h) == 0x7FFF).all()
+
+
+def test_q4k_golden_file_vs_gguf_py():
+    import json
+    exp = json.load(open(os.path.join(G, "q4k.gguf.expected.json")))
+    outs = np.load(os.path.join(G, "q4k.gguf.bf16.npz"))
+    raw = open(os.path.join(G, "q4k.gguf"), "rb").read()
+    n = 0
+    for t in exp["tensors"]:
+        if t["dtype"] != "Q4_K":
+            continue
+        blocks = np.frombuffer(raw[t["file_offset"]:t["file_offset"] + t["nbytes"]], np.uint8).reshape(-1, 144)
+        assert (oracle.dequant_q4k_bf16(blocks).reshape(-1) == outs[t["name"]]).all()
+        n += 1
+    assert n == 2
+
+
+def test_q4k_random_blocks_vs_gguf_py_live_bit_exact(coracle):
+    from gguf import GGMLQuantizationType, quants
+    q = coracle.fill("q4k", 4096, 12345).reshape(-1, 144)
+    ref = bits16(torch.from_numpy(quants.dequantize(q, GGMLQuantizationType.Q4_K)).to(torch.bfloat16))
+    assert (oracle.dequant_q4k_bf16(q) == ref).all()
+    assert (coracle.q4k_to_bf16(q) == ref).all()
+
+
+def test_q4k_scale_min_unpack_vs_gguf_py():
+    from gguf.quants import Q4_K
+    rng = np.random.default_rng(5)
+    s = rng.integers(0, 256, size=(1000, 12), dtype=np.uint8)
+    sc, mn = oracle.q4k_scale_min(s)
+    rsc, rmn = Q4_K.get_scale_min(s)
+    assert (sc == rsc).all() and (mn == rmn).all()
+
+
+def test_q4k_extreme_scales(coracle):
+    # all-ones scales (63/63), zero d, max nibbles: exercises every bit of the 6-bit unpack
+    b = np.zeros((3, 144), np.uint8)
+    b[0, 4:16] = 0xFF; b[0, 16:] = 0xFF; b[0, 0:4] = np.array([0x3C00, 0x3C00], "<u2").view(np.uint8)  # d=dmin=1
+    b[1, 4:16] = 0xAA; b[1, 16:] = 0x5A; b[1, 0:4] = np.array([0x0400, 0x0001], "<u2").view(np.uint8)  # tiny / subnormal
+    b[2, 4:16] = 0x3F; b[2, 16:] = 0xF0
+    from gguf import GGMLQuantizationType, quants
+    ref = bits16(torch.from_numpy(quants.dequantize(b, GGMLQuantizationType.Q4_K)).to(torch.bfloat16))
+    assert (oracle.dequant_q4k_bf16(b) == ref).all()
+    assert (coracle.q4k_to_bf16(b) == ref).all()
+
+
+def test_checksum_c_matches_numpy_and_is_position_sensitive(coracle):
+    rng = np.random.default_rng(9)
+    for n in (0, 1, 7, 8, 9, 4096, 100_003):
+        a = rng.integers(0, 256, size=n, dtype=np.uint8)
+        assert coracle.checksum(a) == oracle.checksum(a)
+    a = rng.integers(0, 256, size=64, dtype=np.uint8)
+    b = a.copy(); b[:8], b[8:16] = a[8:16].copy(), a[:8].copy()
+    assert oracle.checksum(a) != oracle.checksum(b)
+
+
+def test_fill_generators_are_finite_and_reproducible(coracle):
+    a = coracle.fill("bf16", 100_000, 1)
+    assert ((a & 0x7F80) != 0x7F80).all()
+    assert (a == coracle.fill("bf16", 100_000, 1)).all() and (a != coracle.fill("bf16", 100_000, 2)).any()
+    q = coracle.fill("q4k", 100, 1).reshape(-1, 144)
+    d = q[:, 0:4].copy().view(np.float16).astype(np.float32)
+    assert np.isfinite(d).all() and (d >= 2.0 ** -10).all() and (d < 2.0 ** -3).all()

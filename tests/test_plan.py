@@ -1,0 +1,167 @@
+"""Host planner (kk_plan_describe, CPU only): pool layout == oracle.plan_pool, and executing the planned
+reads + segments with the oracle's arithmetic reproduces oracle.expected_pool bit for bit — for SINGLE,
+BROADCAST (parts partition the pool) and SCATTER (per-rank slices), with chunk sizes small enough to force
+tensors to be split across chunks."""
+import os
+
+import numpy as np
+import pytest
+
+from kukeon_b200 import gpupool
+from oracle import oracle
+from tests import helpers
+from tools import synth
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MB = 1 << 20
+
+
+def check_layout(plan, recs, mode, flags, n_parts):
+    n_layouts = n_parts if mode == gpupool.MODE_SCATTER else 1
+    assert len(plan["layouts"]) == n_layouts
+    for L in range(n_layouts):
+        want, total = oracle.plan_pool(recs, mode, flags, n_parts, L)
+        lay = plan["layouts"][L]
+        assert lay["pool_bytes"] == total
+        for w, g in zip(want, lay["tensors"]):
+            assert (g["name"], g["dtype"], g["shape"], g["pool_offset"], g["nbytes"]) == \
+                   (w["name"], w["dtype"], w["shape"], w["pool_offset"], w["nbytes"])
+            assert g["slice_dim"] == w["slice_dim"] and g["slice_begin"] == w["slice_begin"]
+            assert g["pool_offset"] % 256 == 0
+
+
+def run_case(path, mode=gpupool.MODE_SINGLE, flags=0, n_parts=1, chunk=2 * MB):
+    shards, recs = oracle.index_path(path)
+    plan = gpupool.plan_describe(path, mode=mode, flags=flags, n_parts=n_parts, chunk_bytes=chunk)
+    check_layout(plan, recs, mode, flags, n_parts)
+    if mode == gpupool.MODE_SCATTER:
+        for g in range(n_parts):
+            exp, pl = oracle.expected_pool(shards, recs, mode, flags, n_parts, g)
+            got, mask = helpers.emulate_part(plan, g, len(exp))
+            assert (mask == helpers.expected_mask(pl, len(exp))).all()
+            assert (got == exp).all()
+    else:
+        exp, pl = oracle.expected_pool(shards, recs, mode, flags)
+        acc = np.zeros(len(exp), np.uint8)
+        cover = np.zeros(len(exp), np.int32)
+        for g in range(n_parts):
+            got, mask = helpers.emulate_part(plan, g, len(exp))
+            acc[mask] = got[mask]
+            cover += mask
+        assert (cover == helpers.expected_mask(pl, len(exp)).astype(np.int32)).all(), "parts must partition the pool exactly"
+        assert (acc == exp).all()
+        assert sum(p["src_bytes"] for p in plan["parts"]) == plan["file_bytes"]
+    for p in plan["parts"]:
+        for ch in p["chunks"]:
+            assert ch["buf_bytes"] <= chunk
+    return plan
+
+
+def test_mixed_safetensors_single(native, tmp_path):
+    p = str(tmp_path / "m.safetensors")
+    helpers.mixed_safetensors(p)
+    plan = run_case(p)
+    assert len(plan["parts"][0]["chunks"]) >= 1
+
+
+def test_mixed_unpadded_header_single(native, tmp_path):
+    p = str(tmp_path / "m.safetensors")
+    helpers.mixed_safetensors(p, pad_header=False)
+    run_case(p)
+
+
+def test_keep_f32_flag(native, tmp_path):
+    p = str(tmp_path / "m.safetensors")
+    helpers.mixed_safetensors(p)
+    run_case(p, flags=gpupool.LOAD_KEEP_F32)
+
+
+def test_golden_files_plan(native):
+    run_case(os.path.join(G, "st_mixed.safetensors"))
+    run_case(os.path.join(G, "q4k.gguf"))
+    run_case(os.path.join(G, "sharded"))
+
+
+def test_llama_split_across_chunks_and_broadcast_parts(native, tmp_path):
+    d = str(tmp_path / "llama")
+    synth.make_llama(d, dict(hidden=256, ffn=704, layers=3, kv_dim=64, vocab=3000), max_shard_bytes=3_000_000)
+    plan = run_case(d, chunk=1 * MB)
+    assert any(len(ch["segs"]) > 1 for ch in plan["parts"][0]["chunks"])
+    for n in (2, 3, 8):
+        pb = run_case(d, mode=gpupool.MODE_BROADCAST, n_parts=n, chunk=1 * MB)
+        srcs = [p["src_bytes"] for p in pb["parts"]]
+        assert sum(srcs) == pb["file_bytes"]
+        assert max(srcs) - min(srcs) <= 2 * MB, "parts should be balanced to within ~a chunk"
+
+
+def test_scatter_slices(native, tmp_path):
+    d = str(tmp_path / "llama")
+    synth.make_llama(d, dict(hidden=256, ffn=704, layers=2, kv_dim=64, vocab=1024), max_shard_bytes=2_500_000)
+    for n in (2, 4, 8):
+        plan = run_case(d, mode=gpupool.MODE_SCATTER, n_parts=n, chunk=1 * MB)
+        lay = {t["name"]: t for t in plan["layouts"][1]["tensors"]}
+        assert lay["model.layers.0.self_attn.q_proj.weight"]["slice_dim"] == 0
+        assert lay["model.layers.0.self_attn.o_proj.weight"]["slice_dim"] == 1
+        assert lay["model.layers.0.mlp.down_proj.weight"]["shape"] == [256, 704 // n]
+        assert lay["model.layers.0.input_layernorm.weight"]["slice_dim"] is None
+        assert lay["model.embed_tokens.weight"]["slice_begin"] == 1024 // n
+        # each rank reads ~1/n of the sliceable bytes (norms are replicated)
+        assert plan["parts"][0]["src_bytes"] < plan["file_bytes"] / n * 1.05 + 64 * 1024
+
+
+def test_scatter_indivisible_dims_are_replicated(native, tmp_path):
+    d = str(tmp_path / "llama")
+    synth.make_llama(d, dict(hidden=96, ffn=100, layers=1, kv_dim=32, vocab=77), max_shard_bytes=10_000_000)
+    plan = run_case(d, mode=gpupool.MODE_SCATTER, n_parts=8, chunk=1 * MB)
+    lay = {t["name"]: t for t in plan["layouts"][3]["tensors"]}
+    assert lay["model.embed_tokens.weight"]["slice_dim"] is None  # 77 % 8 != 0
+    assert lay["model.layers.0.self_attn.q_proj.weight"]["slice_dim"] == 0  # 96 % 8 == 0
+
+
+def test_gpt2_conv1d_transpose(native, tmp_path):
+    p = str(tmp_path / "gpt2.safetensors")
+    synth.make_gpt2(p, n_layer=2, d=96, vocab=301, n_pos=40)
+    plan = run_case(p, flags=gpupool.LOAD_GPT2_CONV1D_T, chunk=1 * MB)
+    lay = {t["name"]: t for t in plan["layouts"][0]["tensors"]}
+    assert lay["h.0.attn.c_attn.weight"]["shape"] == [288, 96]
+    assert lay["h.1.mlp.c_proj.weight"]["shape"] == [96, 384]
+    assert lay["wte.weight"]["shape"] == [301, 96]
+    run_case(p, flags=gpupool.LOAD_GPT2_CONV1D_T | gpupool.LOAD_KEEP_F32, chunk=1 * MB)
+    run_case(p, flags=gpupool.LOAD_GPT2_CONV1D_T, mode=gpupool.MODE_BROADCAST, n_parts=2, chunk=1 * MB)
+
+
+def test_gpt2_f16_and_bf16_transpose(native, tmp_path):
+    for dt in ("F16", "BF16"):
+        p = str(tmp_path / f"gpt2_{dt}.safetensors")
+        synth.write_safetensors(p, synth.gpt2_tensors(n_layer=1, d=40, vocab=50, n_pos=8, dtype=dt), 3)
+        run_case(p, flags=gpupool.LOAD_GPT2_CONV1D_T, chunk=1 * MB)
+
+
+def test_mixtral_gguf_plan(native, tmp_path):
+    p = str(tmp_path / "mix.gguf")
+    synth.write_gguf(p, synth.mixtral_gguf_tensors(hidden=256, ffn=768, layers=2, experts=2, vocab=512, kv_dim=256), 7)
+    run_case(p, chunk=1 * MB)
+    run_case(p, mode=gpupool.MODE_BROADCAST, n_parts=4, chunk=1 * MB)
+    run_case(p, mode=gpupool.MODE_SCATTER, n_parts=2, chunk=1 * MB)
+
+
+def test_unsupported_quant_is_refused_at_plan_time(native, tmp_path):
+    import struct
+    p = str(tmp_path / "q8.gguf")
+    head = struct.pack("<IIQQ", 0x46554747, 3, 1, 0) + struct.pack("<Q", 1) + b"w" + struct.pack("<I", 1) + struct.pack("<Q", 32) + struct.pack("<IQ", 8, 0)
+    head += b"\0" * ((-len(head)) % 32)
+    open(p, "wb").write(head + b"\0" * 64)
+    assert gpupool.index(p)[0]["dtype"] == "Q8_0"  # indexing works ...
+    with pytest.raises(gpupool.ErrUnsupported, match="Q8_0"):  # ... loading is refused, never approximated
+        gpupool.plan_describe(p)
+
+
+def test_bad_arguments(native, tmp_path):
+    p = str(tmp_path / "m.safetensors")
+    helpers.mixed_safetensors(p)
+    with pytest.raises(gpupool.ErrInvalid):
+        gpupool.plan_describe(p, mode=gpupool.MODE_SINGLE, n_parts=2)
+    with pytest.raises(gpupool.ErrInvalid):
+        gpupool.plan_describe(p, mode=7)
+    with pytest.raises(gpupool.ErrInvalid):
+        gpupool.plan_describe(p, mode=gpupool.MODE_BROADCAST, n_parts=9)

@@ -1,0 +1,101 @@
+/*
+ * synth_fill.c — fast seeded content generator for tools/synth.py (synthetic checkpoints for tests and
+ * bench.py).  Not part of the product and not part of the oracle.  Content of byte range
+ * [off, off+n) of tensor `idx` depends only on (seed, idx, position), so any piece can be regenerated.
+ * Built by tools/Makefile into tools/_build/libkk_synth.so.
+ */
+#define _GNU_SOURCE
+#include <errno.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+enum { K_BYTES = 0, K_BF16 = 1, K_F16 = 2, K_F32 = 3, K_Q4K = 4 };
+
+static inline uint64_t mix64(uint64_t x) {
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27; x *= 0x94d049bb133111ebull;
+  x ^= x >> 31;
+  return x;
+}
+static inline uint64_t rnd(uint64_t seed, uint64_t idx, uint64_t i) {
+  return mix64((seed + 0x1234567ull) * 0xD1B54A32D192ED03ull + idx * 0xA0761D6478BD642Full + i * 0x9E3779B97F4A7C15ull);
+}
+
+/* fill words [w0, w0+nw) (8-byte words of the tensor) into dst */
+static void fill_words(uint8_t* dst, uint64_t w0, uint64_t nw, int kind, uint64_t seed, uint64_t idx) {
+  for (uint64_t k = 0; k < nw; ++k) {
+    uint64_t r = rnd(seed, idx, w0 + k);
+    if (kind == K_BF16) { /* clear exponent 0xFF -> 0xFE in each 16-bit lane: all finite */
+      uint64_t e = r & 0x7F807F807F807F80ull;
+      uint64_t full = (e + 0x0080008000800080ull) & 0x8000800080008000ull; /* lane exponent == 0xFF <=> carry into bit 15 */
+      r &= ~(full >> 8);                                                    /* clear bit 7 of those lanes */
+    } else if (kind == K_F16) {
+      uint64_t e = r & 0x7C007C007C007C00ull;
+      uint64_t full = (e + 0x0400040004000400ull) & 0x8000800080008000ull;
+      r &= ~(full >> 5);                                                    /* clear bit 10 */
+    } else if (kind == K_F32) {
+      for (int h = 0; h < 2; ++h) { /* two floats ~ U(-0.04, 0.04) */
+        uint32_t u = (uint32_t)(r >> (32 * h));
+        float f = ((float)(u >> 8) * (1.0f / 16777216.0f) - 0.5f) * 0.08f;
+        memcpy(dst + 8 * k + 4 * h, &f, 4);
+      }
+      continue;
+    }
+    memcpy(dst + 8 * k, &r, 8);
+  }
+}
+
+static void fix_q4k(uint8_t* buf, uint64_t first_block, uint64_t nblocks, uint64_t seed, uint64_t idx) {
+  for (uint64_t b = 0; b < nblocks; ++b) {
+    uint64_t r = rnd(seed ^ 0xABCDEFull, idx, first_block + b);
+    uint16_t d = (uint16_t)((((r & 0xFF) % 7 + 5) << 10) | ((r >> 8) & 0x3FF));          /* 2^-10 .. 2^-4 */
+    uint16_t m = (uint16_t)(((((r >> 20) & 0xFF) % 7 + 5) << 10) | ((r >> 28) & 0x3FF));
+    memcpy(buf + 144 * b, &d, 2);
+    memcpy(buf + 144 * b + 2, &m, 2);
+  }
+}
+
+/* Generate bytes [0, nbytes) of tensor idx and pwrite them at file_off. nbytes % 8 may be non-zero.
+ * Q4_K: nbytes must be a multiple of 144.  Returns 0 or -errno. */
+int synth_write(int fd, uint64_t file_off, uint64_t nbytes, int kind, uint64_t seed, uint64_t idx) {
+  const uint64_t CH = (kind == K_Q4K) ? (144ull * 8 * 7168) : (8ull << 20); /* multiple of 8 and of 144*8 */
+  const uint64_t nch = (nbytes + CH - 1) / CH;
+  int err = 0;
+#pragma omp parallel
+  {
+    uint8_t* buf = (uint8_t*)malloc(CH + 8);
+#pragma omp for schedule(dynamic, 1)
+    for (uint64_t c = 0; c < nch; ++c) {
+      const uint64_t b0 = c * CH;
+      const uint64_t n = nbytes - b0 < CH ? nbytes - b0 : CH;
+      fill_words(buf, b0 / 8, (n + 7) / 8, kind == K_Q4K ? K_BYTES : kind, seed, idx);
+      if (kind == K_Q4K) fix_q4k(buf, b0 / 144, n / 144, seed, idx);
+      uint64_t done = 0;
+      while (done < n) {
+        ssize_t w = pwrite(fd, buf + done, n - done, (off_t)(file_off + b0 + done));
+        if (w < 0) {
+          if (errno == EINTR) continue;
+          err = -errno;
+          break;
+        }
+        done += (uint64_t)w;
+      }
+    }
+    free(buf);
+  }
+  return err;
+}
+
+/* Same content into memory (tests regenerate pieces without a file). */
+void synth_fill(uint8_t* dst, uint64_t nbytes, int kind, uint64_t seed, uint64_t idx) {
+  uint64_t nw = nbytes / 8;
+  fill_words(dst, 0, nw, kind == K_Q4K ? K_BYTES : kind, seed, idx);
+  if (nbytes & 7) {
+    uint8_t tmp[8];
+    fill_words(tmp, nw, 1, kind == K_Q4K ? K_BYTES : kind, seed, idx);
+    memcpy(dst + 8 * nw, tmp, nbytes & 7);
+  }
+  if (kind == K_Q4K) fix_q4k(dst, 0, nbytes / 144, seed, idx);
+}
