@@ -59,6 +59,9 @@ def parse():
     ap.add_argument("--zerocopy", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nccl-compare", action="store_true", help="also time an NCCL all-gather of the pools (comparison collective)")
+    ap.add_argument("--kernel-only", action="store_true", help="profiling aid: skip the streaming load / e2e legs (every kk_convert launch is a resident one)")
+    ap.add_argument("--e2e-only", action="store_true", help="tuning aid: skip the resident kernel leg")
+    ap.add_argument("--no-numa-pin", action="store_true")
     return ap.parse_args()
 
 
@@ -271,7 +274,7 @@ def main():
     t_gen = time.time() - t_gen
 
     mode = gpupool.MODE_SINGLE if world == 1 else (gpupool.MODE_SCATTER if spec["mode"] == "scatter" else gpupool.MODE_BROADCAST)
-    flags = gpupool.CFG_ZEROCOPY if args.zerocopy else 0
+    flags = (gpupool.CFG_ZEROCOPY if args.zerocopy else 0) | (gpupool.CFG_NO_NUMA_PIN if args.no_numa_pin else 0)
     t0 = time.time()
     pool = gpupool.Pool([local], n_staging_buffers=args.slots, staging_buffer_bytes=args.slot_mb << 20, n_reader_threads=args.readers, flags=flags)
     t_open = time.time() - t0
@@ -290,11 +293,34 @@ def main():
             if r != rank:
                 m.peer_attach(r, hh)
     barrier()
-    m.load_part()
+    if args.kernel_only:
+        m.stage_resident()
+        barrier()
+        m.convert_resident()
+    else:
+        m.load_part()
     handle, manifest = m.export(local)
     barrier()
-    t_ready = allmax(time.time() - t_ready0)
+    t_ready = None if args.kernel_only else allmax(time.time() - t_ready0)
     st0 = m.stats()
+
+    # pinned H2D probe (plumbing; tells what the PCIe link of this box can do for the e2e leg)
+    h2d_probe = None
+    try:
+        hb = torch.empty(1 << 30, dtype=torch.uint8).pin_memory()
+        db = torch.empty(1 << 30, dtype=torch.uint8, device=f"cuda:{local}")
+        db.copy_(hb, non_blocking=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            db.copy_(hb, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        h2d_probe = 3 * (1 << 30) / (e0.elapsed_time(e1) / 1e3) / 1e9
+        del hb, db
+    except Exception:  # noqa: BLE001
+        pass
 
     # ---- verification against the files (product-only: bf16 passthrough == file bytes) -------------------
     verified = None
@@ -327,9 +353,12 @@ def main():
         barrier()
         return dt
 
-    for _ in range(args.warmup):
-        e2e_step()
-    e2e_ts = [allmax(e2e_step()) for _ in range(args.steps)]
+    if args.kernel_only:
+        e2e_ts = [float("nan")]
+    else:
+        for _ in range(args.warmup):
+            e2e_step()
+        e2e_ts = [allmax(e2e_step()) for _ in range(args.steps)]
     e2e_time = sum(e2e_ts)
     delivered = (pool_bytes if mode == gpupool.MODE_SCATTER else file_bytes) * (1 if mode == gpupool.MODE_SCATTER else world)
     if mode == gpupool.MODE_SCATTER:
@@ -338,7 +367,23 @@ def main():
     chunks_per_load = part["chunks"]
 
     # ---- value: kernel stage from the HBM-resident image ---------------------------------------------------
-    m.stage_resident()
+    if args.e2e_only:
+        line = {"metric": METRIC, "e2e_only": True, "n_gpus": N, "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_time / args.steps * 1e3},
+                "time_to_agent_ready_s": t_ready, "h2d_probe_GBps": h2d_probe,
+                "config": {"readers": args.readers, "slots": args.slots, "slot_mb": args.slot_mb, "zerocopy": args.zerocopy, "numa_pin": not args.no_numa_pin,
+                           "chunks_per_load": chunks_per_load, "kk_open_s": t_open}}
+        m.release()
+        pool.close()
+        barrier()
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+            if not args.keep_data:
+                shutil.rmtree(d, ignore_errors=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    if not args.kernel_only:
+        m.stage_resident()
     barrier()
     for _ in range(max(args.warmup, 3)):
         barrier()
@@ -429,7 +474,7 @@ def main():
         "time_to_agent_ready_s": t_ready,
         "wall_ms_per_step": wall / args.steps * 1e3,
         "setup": {"synth_s": t_gen, "kk_open_s": t_open, "index_s": st0["index_s"], "plan_s": st0["plan_s"], "alloc_s": st0["alloc_s"],
-                  "first_load_s": st0["load_s"], "chunks_per_load": chunks_per_load},
+                  "first_load_s": st0["load_s"], "chunks_per_load": chunks_per_load, "h2d_probe_GBps": h2d_probe},
     }
     if nvlink:
         line["nvlink"] = nvlink

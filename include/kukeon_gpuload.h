@@ -90,6 +90,7 @@ typedef enum kk_fanout {
 /* kk_config.flags */
 #define KK_CFG_ZEROCOPY 0x1u     /* convert kernels read the pinned host ring directly (no H2D copy engine hop) */
 #define KK_CFG_NO_PEER_ACCESS 0x2u /* do not enable peer access between devices (forces replicas) */
+#define KK_CFG_NO_NUMA_PIN 0x4u    /* do not bind reader threads / pinned slots to the device's NUMA node */
 
 /* kk_load_opts.flags */
 #define KK_LOAD_GPT2_CONV1D_T 0x1u /* transpose HF GPT-2 Conv1D weights ([in,out] -> [out,in]) while loading */
@@ -103,9 +104,9 @@ typedef struct kk_config {
   int32_t n_devices;                /* 1..KK_MAX_DEVICES */
   int32_t devices[KK_MAX_DEVICES];  /* CUDA ordinals */
   uint64_t pool_bytes_per_device;   /* budget across all resident models; 0 = no limit */
-  uint32_t n_staging_buffers;       /* pinned ring slots per device; 0 = default (8) */
-  uint64_t staging_buffer_bytes;    /* bytes per slot; 0 = default (64 MiB); rounded up to 2 MiB */
-  uint32_t n_reader_threads;        /* host reader threads per device; 0 = default (4) */
+  uint32_t n_staging_buffers;       /* pinned ring slots per device; 0 = default (2 per reader thread) */
+  uint64_t staging_buffer_bytes;    /* bytes per slot; 0 = default (32 MiB); rounded up to 2 MiB */
+  uint32_t n_reader_threads;        /* host reader threads per device; 0 = default (8) */
   uint32_t flags;                   /* KK_CFG_* */
 } kk_config;
 

@@ -10,6 +10,8 @@
 #include "kk_loader.hpp"
 
 #include <fcntl.h>
+#include <pthread.h>
+#include <sched.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -59,6 +61,44 @@ void pread_full(int fd, uint8_t* dst, uint64_t len, uint64_t off, const std::str
     off += (uint64_t)r;
     len -= (uint64_t)r;
   }
+}
+
+// CPUs of the NUMA node the device hangs off (empty when sysfs does not say).
+std::vector<int> numa_cpus_of_device(int ordinal) {
+  std::vector<int> cpus;
+  char bdf[32] = {0};
+  if (cudaDeviceGetPCIBusId(bdf, sizeof bdf, ordinal) != cudaSuccess) { cudaGetLastError(); return cpus; }
+  for (char* c = bdf; *c; ++c) *c = (char)tolower(*c);
+  char path[256];
+  snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bdf);
+  FILE* f = fopen(path, "r");
+  if (!f) return cpus;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  if (node < 0) return cpus;
+  snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+  f = fopen(path, "r");
+  if (!f) return cpus;
+  char buf[4096] = {0};
+  if (fgets(buf, sizeof buf, f)) {
+    for (char* tok = strtok(buf, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+      int a, b;
+      if (sscanf(tok, "%d-%d", &a, &b) == 2) { for (int i = a; i <= b; ++i) cpus.push_back(i); }
+      else if (sscanf(tok, "%d", &a) == 1) cpus.push_back(a);
+    }
+  }
+  fclose(f);
+  return cpus;
+}
+
+void pin_this_thread(const std::vector<int>& cpus) {
+  if (cpus.empty()) return;
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  for (int c : cpus)
+    if (c >= 0 && c < CPU_SETSIZE) CPU_SET(c, &set);
+  pthread_setaffinity_np(pthread_self(), sizeof set, &set);  // best effort
 }
 
 struct ErrorSink {
@@ -117,6 +157,7 @@ void run_part(kk_model* m, int li, int part, const FdSet& fds) {
   ErrorSink sink;
   auto worker = [&](Reader* rd) {
     try {
+      if (!(c->cfg.flags & KK_CFG_NO_NUMA_PIN)) pin_this_thread(dev.numa_cpus);
       KK_CUDA(cudaSetDevice(dev.ordinal));
       size_t k = 0;
       for (;;) {
@@ -146,8 +187,8 @@ void run_part(kk_model* m, int li, int part, const FdSet& fds) {
     }
   };
   std::vector<std::thread> th;
-  for (size_t r = 1; r < dev.readers.size(); ++r) th.emplace_back(worker, &dev.readers[r]);
-  worker(&dev.readers[0]);
+  // every reader runs on its own (NUMA-pinned) thread; the caller's thread affinity is left alone
+  for (size_t r = 0; r < dev.readers.size(); ++r) th.emplace_back(worker, &dev.readers[r]);
   for (auto& t : th) t.join();
   if (sink.first) {
     // leave the streams quiet before reporting
@@ -213,11 +254,11 @@ kk_ctx* ctx_open(const kk_config& cfg_in) {
     fail(KK_ECUDA, "no usable CUDA device (%s); this library has no CPU path", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
   for (int i = 0; i < cfg.n_devices; ++i)
     if (cfg.devices[i] < 0 || cfg.devices[i] >= count) fail(KK_EINVAL, "device ordinal %d not present (%d devices)", cfg.devices[i], count);
-  if (cfg.n_staging_buffers == 0) cfg.n_staging_buffers = 8;
-  if (cfg.n_reader_threads == 0) cfg.n_reader_threads = 4;
+  if (cfg.n_reader_threads == 0) cfg.n_reader_threads = 8;
+  if (cfg.n_staging_buffers == 0) cfg.n_staging_buffers = 2 * cfg.n_reader_threads;
   if (cfg.n_reader_threads > 64) fail(KK_EINVAL, "n_reader_threads %u too large", cfg.n_reader_threads);
   if (cfg.n_staging_buffers < cfg.n_reader_threads) cfg.n_staging_buffers = cfg.n_reader_threads;
-  if (cfg.staging_buffer_bytes == 0) cfg.staging_buffer_bytes = 64ull << 20;
+  if (cfg.staging_buffer_bytes == 0) cfg.staging_buffer_bytes = 32ull << 20;
   if (cfg.staging_buffer_bytes < (1ull << 20)) fail(KK_EINVAL, "staging_buffer_bytes must be at least 1 MiB");
 
   std::unique_ptr<kk_ctx> c(new kk_ctx);
@@ -236,7 +277,13 @@ kk_ctx* ctx_open(const kk_config& cfg_in) {
       KK_CUDA(kernels_init_device());
       d.kernels_ready = true;
       KK_CUDA(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+      d.numa_cpus = numa_cpus_of_device(d.ordinal);
       d.readers.resize(cfg.n_reader_threads);
+      // allocate (and thereby first-touch / pin) the slots from a thread bound to the device's NUMA node
+      std::exception_ptr alloc_err;
+      std::thread alloc([&] { try {
+      if (!(cfg.flags & KK_CFG_NO_NUMA_PIN)) pin_this_thread(d.numa_cpus);
+      KK_CUDA(cudaSetDevice(d.ordinal));
       for (uint32_t r = 0; r < cfg.n_reader_threads; ++r) {
         Reader& rd = d.readers[r];
         KK_CUDA(cudaStreamCreateWithFlags(&rd.stream, cudaStreamNonBlocking));
@@ -248,6 +295,9 @@ kk_ctx* ctx_open(const kk_config& cfg_in) {
           KK_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         }
       }
+      } catch (...) { alloc_err = std::current_exception(); } });
+      alloc.join();
+      if (alloc_err) std::rethrow_exception(alloc_err);
     }
     c->peer_ok = cfg.n_devices > 1 && !(cfg.flags & KK_CFG_NO_PEER_ACCESS);
     if (c->peer_ok) {

@@ -40,6 +40,7 @@ struct Device {
   cudaStream_t stream = nullptr;  // resident launches, checksum, misc
   uint64_t pool_in_use = 0;
   bool kernels_ready = false;
+  std::vector<int> numa_cpus;  // CPUs local to the device's PCIe root (reader threads are pinned there)
 };
 
 struct Model;

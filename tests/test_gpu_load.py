@@ -83,7 +83,7 @@ def test_llama_multishard_small_chunks(native, tmp_path):
     synth.make_llama(d, dict(hidden=256, ffn=704, layers=3, kv_dim=64, vocab=3000), max_shard_bytes=3_000_000)
     with gpupool.Pool([0], n_staging_buffers=4, staging_buffer_bytes=1 * MB, n_reader_threads=2) as pl:
         st = load_and_check(pl, d)
-        assert st["parts"][0]["chunks"] > 8
+        assert st["parts"][0]["chunks"] >= 4
         load_and_check(pl, d, mode=gpupool.MODE_BROADCAST)  # one device: degenerates to a single load
 
 
