@@ -283,7 +283,8 @@ def main():
     barrier()
     t_ready0 = time.time()
     ref = modelhub.Pull(path)
-    m = modelhub.Load(pool, ref, mode=mode, fanout=gpupool.FANOUT_P2P, flags=gpupool.LOAD_DEFER,
+    lflags = gpupool.LOAD_DEFER | (gpupool.LOAD_GPT2_CONV1D_T if spec["kind"] == "gpt2" else 0)
+    m = modelhub.Load(pool, ref, mode=mode, fanout=gpupool.FANOUT_P2P, flags=lflags,
                       part_index=rank if world > 1 else 0, part_count=world if world > 1 else 0)
     if world > 1 and mode == gpupool.MODE_BROADCAST:
         h, _ = m.export(local)

@@ -105,8 +105,8 @@ typedef struct kk_config {
   int32_t devices[KK_MAX_DEVICES];  /* CUDA ordinals */
   uint64_t pool_bytes_per_device;   /* budget across all resident models; 0 = no limit */
   uint32_t n_staging_buffers;       /* pinned ring slots per device; 0 = default (2 per reader thread) */
-  uint64_t staging_buffer_bytes;    /* bytes per slot; 0 = default (32 MiB); rounded up to 2 MiB */
-  uint32_t n_reader_threads;        /* host reader threads per device; 0 = default (8) */
+  uint64_t staging_buffer_bytes;    /* bytes per slot; 0 = default (16 MiB); rounded up to 2 MiB */
+  uint32_t n_reader_threads;        /* host reader threads per device; 0 = default (16) */
   uint32_t flags;                   /* KK_CFG_* */
 } kk_config;
 

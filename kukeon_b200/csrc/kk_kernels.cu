@@ -25,7 +25,10 @@ namespace kk {
 namespace {
 
 constexpr int kStages = 4;
-constexpr int kConsumerWarps = 8;
+#ifndef KK_CONSUMER_WARPS
+#define KK_CONSUMER_WARPS 8
+#endif
+constexpr int kConsumerWarps = KK_CONSUMER_WARPS;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kThreads = 32 + kConsumerThreads;  // 288
 constexpr uint32_t kStageBytes = KK_TILE_SRC_BYTES + KK_STAGE_PAD;
@@ -128,10 +131,15 @@ struct Dsts {
   uint8_t* p[KK_MAX_DST];
   uint32_t n;
   bool multimem;
+  bool single;  // n == 1 and not multimem
 };
 
 // 16-byte store of one output vector to every destination pool.
 __device__ __forceinline__ void store16_all(const Dsts& D, uint64_t off, const uint4& v) {
+  if (D.single) {  // the common N = 1 case: no per-store predicate ladder
+    stg128(D.p[0] + off, v);
+    return;
+  }
   if (D.multimem) {
     stmm128(D.p[0] + off, v);
     return;
@@ -256,55 +264,74 @@ __device__ __forceinline__ void consume_f16(const Dsts& D, uint32_t pay, uint32_
 // Q4_K super-block (144 B): d f16 | dmin f16 | scales[12] | qs[128]  ->  256 bf16.
 // y = (d*sc_j)*q - (dmin*m_j), every product and the difference rounded to fp32 separately (no FMA
 // contraction) so the result is bit-identical to the oracle's gguf-py restatement, then RNE to bf16.
+//
+// One warp handles FOUR super-blocks per iteration: lane l decodes the 6-bit (scale, min) pair of
+// sub-block (l & 7) of block (l >> 3) — so the unpack runs once per four blocks instead of once per block —
+// and __shfl_sync hands every lane the pair of the sub-block its 8 outputs belong to.  The four blocks'
+// dependency chains are independent and fully unrolled (ILP hides the ALU latency with only 2 warps/SMSP).
+__device__ __forceinline__ uint32_t lds32_bytes(uint32_t a) {
+  return lds8(a) | (lds8(a + 1) << 8) | (lds8(a + 2) << 16) | (lds8(a + 3) << 24);
+}
+
+template <bool ALIGNED>
+__device__ __forceinline__ void q4k_quad(const Dsts& D, uint32_t pay, uint32_t b0, uint32_t nb, uint64_t dst_off, int lane) {
+  // --- decode: lane -> (block b0 + min(lane>>3, nb-1), sub-block lane&7)
+  const uint32_t hb = min((uint32_t)(lane >> 3), nb - 1);
+  const uint32_t hblk = pay + (b0 + hb) * KK_Q4K_BLOCK_BYTES;
+  uint32_t h0, s0, s1, s2;
+  if (ALIGNED) {
+    const uint4 h = lds128(hblk);
+    h0 = h.x; s0 = h.y; s1 = h.z; s2 = h.w;
+  } else {
+    h0 = lds32_bytes(hblk); s0 = lds32_bytes(hblk + 4); s1 = lds32_bytes(hblk + 8); s2 = lds32_bytes(hblk + 12);
+  }
+  const float d = __half2float(__ushort_as_half((unsigned short)(h0 & 0xFFFFu)));
+  const float dmin = __half2float(__ushort_as_half((unsigned short)(h0 >> 16)));
+  const int j = lane & 7, sh = (j & 3) * 8;
+  const uint32_t b_lo = (s0 >> sh) & 0xFFu, b_mid = (s1 >> sh) & 0xFFu, b_hi = (s2 >> sh) & 0xFFu;
+  const uint32_t sc = (j < 4) ? (b_lo & 63u) : ((b_hi & 0xFu) | ((b_lo >> 6) << 4));
+  const uint32_t mn = (j < 4) ? (b_mid & 63u) : ((b_hi >> 4) | ((b_mid >> 6) << 4));
+  const float dsc_j = __fmul_rn(d, (float)sc);
+  const float dmn_j = __fmul_rn(dmin, (float)mn);
+  // --- expand: this lane's 8 outputs of every block live in sub-block myj = lane >> 2
+  const int myj = lane >> 2;
+  const uint32_t qoff = 16u + 32u * (uint32_t)(myj >> 1) + 8u * (uint32_t)(lane & 3);
+  const int nsh = (myj & 1) * 4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float dsc = __shfl_sync(0xffffffffu, dsc_j, 8 * k + myj);
+    const float dmn = __shfl_sync(0xffffffffu, dmn_j, 8 * k + myj);
+    if ((uint32_t)k < nb) {
+      const uint32_t qa = pay + (b0 + k) * KK_Q4K_BLOCK_BYTES + qoff;
+      uint32_t q0, q1;
+      if (ALIGNED) {
+        const uint2 q = lds64(qa);
+        q0 = q.x; q1 = q.y;
+      } else {
+        q0 = lds32_bytes(qa); q1 = lds32_bytes(qa + 4);
+      }
+      q0 = (q0 >> nsh) & 0x0F0F0F0Fu;
+      q1 = (q1 >> nsh) & 0x0F0F0F0Fu;
+      float y[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        // 0x4B0000qq is the float 2^23 + q; subtracting 2^23 gives q exactly (PRMT + FADD, no I2F).
+        const uint32_t bits = __byte_perm(e < 4 ? q0 : q1, 0x4B000000u, 0x7440u | (uint32_t)(e & 3));
+        const float q = __fsub_rn(__uint_as_float(bits), 8388608.0f);
+        y[e] = __fsub_rn(__fmul_rn(dsc, q), dmn);
+      }
+      store16_all(D, dst_off + (uint64_t)(b0 + k) * 512u + (uint32_t)lane * 16u,
+                  make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7])));
+    }
+  }
+}
+
 __device__ __forceinline__ void consume_q4k(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
-  const bool al = (pay & 15u) == 0;
-  for (uint32_t b = cwarp; b < nblk; b += kConsumerWarps) {
-    const uint32_t blk = pay + b * KK_Q4K_BLOCK_BYTES;
-    uint32_t h0, s0, s1, s2;
-    if (al) {
-      uint4 h = lds128(blk);
-      h0 = h.x; s0 = h.y; s1 = h.z; s2 = h.w;
-    } else {
-      uint32_t w[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) w[k] = lds8(blk + 4 * k) | (lds8(blk + 4 * k + 1) << 8) | (lds8(blk + 4 * k + 2) << 16) | (lds8(blk + 4 * k + 3) << 24);
-      h0 = w[0]; s0 = w[1]; s1 = w[2]; s2 = w[3];
-    }
-    const float d = __half2float(__ushort_as_half((unsigned short)(h0 & 0xFFFFu)));
-    const float dmin = __half2float(__ushort_as_half((unsigned short)(h0 >> 16)));
-    // (scale, min) of sub-block j = lane & 7, decoded by every lane (no divergence), then distributed.
-    const int j = lane & 7, sh = (j & 3) * 8;
-    const uint32_t b_lo = (s0 >> sh) & 0xFFu, b_mid = (s1 >> sh) & 0xFFu, b_hi = (s2 >> sh) & 0xFFu;
-    const uint32_t sc = (j < 4) ? (b_lo & 63u) : ((b_hi & 0xFu) | ((b_lo >> 6) << 4));
-    const uint32_t mn = (j < 4) ? (b_mid & 63u) : ((b_hi >> 4) | ((b_mid >> 6) << 4));
-    const float dsc_j = __fmul_rn(d, (float)sc);
-    const float dmn_j = __fmul_rn(dmin, (float)mn);
-    const int myj = lane >> 2;  // this lane's 8 outputs live in sub-block myj
-    const float dsc = __shfl_sync(0xffffffffu, dsc_j, myj);
-    const float dmn = __shfl_sync(0xffffffffu, dmn_j, myj);
-    // 8 quant bytes: chunk c = myj/2 (32 bytes hold sub-blocks 2c (low nibbles) and 2c+1 (high nibbles)).
-    const uint32_t qa = blk + 16 + 32 * (myj >> 1) + 8 * (lane & 3);
-    uint32_t q0, q1;
-    if (al) {
-      uint2 q = lds64(qa);
-      q0 = q.x; q1 = q.y;
-    } else {
-      q0 = lds8(qa) | (lds8(qa + 1) << 8) | (lds8(qa + 2) << 16) | (lds8(qa + 3) << 24);
-      q1 = lds8(qa + 4) | (lds8(qa + 5) << 8) | (lds8(qa + 6) << 16) | (lds8(qa + 7) << 24);
-    }
-    const int nsh = (myj & 1) * 4;
-    q0 = (q0 >> nsh) & 0x0F0F0F0Fu;
-    q1 = (q1 >> nsh) & 0x0F0F0F0Fu;
-    float y[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      // 0x4B0000qq is the float 2^23 + q; subtracting 2^23 gives q exactly (PRMT + FADD, no I2F).
-      const uint32_t bits = __byte_perm(k < 4 ? q0 : q1, 0x4B000000u, 0x7440u | (uint32_t)(k & 3));
-      const float q = __fsub_rn(__uint_as_float(bits), 8388608.0f);
-      y[k] = __fsub_rn(__fmul_rn(dsc, q), dmn);
-    }
-    store16_all(D, dst_off + (uint64_t)b * 512u + (uint32_t)lane * 16u,
-                make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7])));
+  const bool al = (pay & 15u) == 0;  // 144-byte blocks keep the tile's alignment class
+  for (uint32_t b0 = (uint32_t)cwarp * 4u; b0 < nblk; b0 += kConsumerWarps * 4u) {
+    const uint32_t nb = min(4u, nblk - b0);
+    if (al) q4k_quad<true>(D, pay, b0, nb, dst_off, lane);
+    else q4k_quad<false>(D, pay, b0, nb, dst_off, lane);
   }
 }
 
@@ -469,6 +496,7 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
     for (int i = 0; i < KK_MAX_DST; ++i) D.p[i] = L.dst[i];
     D.n = L.n_dst;
     D.multimem = (L.flags & KK_LAUNCH_MULTIMEM) != 0;
+    D.single = (L.n_dst == 1) && !D.multimem;
     int pending = -1;  // stage whose bulk stores may still be reading shared memory (warp 1 lane 0 only)
     uint32_t it = 0;
     for (uint32_t tile = blockIdx.x; tile < L.n_tiles; tile += gridDim.x, ++it) {

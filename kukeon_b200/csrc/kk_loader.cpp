@@ -254,11 +254,11 @@ kk_ctx* ctx_open(const kk_config& cfg_in) {
     fail(KK_ECUDA, "no usable CUDA device (%s); this library has no CPU path", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
   for (int i = 0; i < cfg.n_devices; ++i)
     if (cfg.devices[i] < 0 || cfg.devices[i] >= count) fail(KK_EINVAL, "device ordinal %d not present (%d devices)", cfg.devices[i], count);
-  if (cfg.n_reader_threads == 0) cfg.n_reader_threads = 8;
+  if (cfg.n_reader_threads == 0) cfg.n_reader_threads = 16;  // 16 x ~4 GB/s of page-cache pread saturates a Gen5 x16 link (profiles/r01)
   if (cfg.n_staging_buffers == 0) cfg.n_staging_buffers = 2 * cfg.n_reader_threads;
   if (cfg.n_reader_threads > 64) fail(KK_EINVAL, "n_reader_threads %u too large", cfg.n_reader_threads);
   if (cfg.n_staging_buffers < cfg.n_reader_threads) cfg.n_staging_buffers = cfg.n_reader_threads;
-  if (cfg.staging_buffer_bytes == 0) cfg.staging_buffer_bytes = 32ull << 20;
+  if (cfg.staging_buffer_bytes == 0) cfg.staging_buffer_bytes = 16ull << 20;
   if (cfg.staging_buffer_bytes < (1ull << 20)) fail(KK_EINVAL, "staging_buffer_bytes must be at least 1 MiB");
 
   std::unique_ptr<kk_ctx> c(new kk_ctx);

@@ -104,7 +104,8 @@ ABI_SYMBOLS = [
 
 
 def lib_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+    """In-tree library next to this file; KUKEON_GPULOAD_LIB overrides it (experiments / packaged installs)."""
+    return os.environ.get("KUKEON_GPULOAD_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 
 def lib():
