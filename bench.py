@@ -178,7 +178,7 @@ def cpu_port_setup(path: str, sample_bytes: int):
 def cpu_port_step(ctx) -> float:
     coracle, shards, jobs, src, pool = ctx
     t = time.perf_counter()
-    coracle.cpu_load(shards, jobs, pool, threads=0)
+    coracle.cpu_load(shards, jobs, pool, threads=os.cpu_count() or 1)  # explicit: torchrun exports OMP_NUM_THREADS=1
     return time.perf_counter() - t
 
 
@@ -190,7 +190,7 @@ def run_reference(args, spec, path, file_bytes):
         return
     sample = min(file_bytes, 4 << 30)
     ctx = cpu_port_setup(path, sample)
-    cores = ctx[0].max_threads()
+    cores = os.cpu_count() or 1
     for _ in range(max(args.warmup, 1)):
         cpu_port_step(ctx)
     ts = [cpu_port_step(ctx) for _ in range(args.steps)]
@@ -205,14 +205,32 @@ def run_reference(args, spec, path, file_bytes):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line goes to the real stdout; fd 1 itself is pointed at stderr while the benchmark runs so that
+    native libraries (NCCL's version banner, ...) cannot interleave with it."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     spec = workload_spec(args)
     from tools import synth
     file_bytes = synth.total_bytes(spec["tensors"])
@@ -325,12 +343,16 @@ def main():
 
     # ---- verification against the files (product-only: bf16 passthrough == file bytes) -------------------
     verified = None
-    if spec["kind"] == "llama" and mode != gpupool.MODE_SCATTER:
+    if spec["kind"] == "llama":
         verified = True
-        for r in (ref.tensors[0], ref.tensors[len(ref.tensors) // 2], ref.tensors[-1]):
+        for r in (ref.tensors[0], ref.tensors[1], ref.tensors[len(ref.tensors) // 2], ref.tensors[-1]):
             pl = m.placements(r["name"])[0]
+            if pl.slice_dim == 1:
+                continue  # column slices are strided in the file; covered by tests/test_gpu_multi.py
+            row_bytes = r["nbytes"] // r["shape"][0] if r["shape"] else r["nbytes"]
+            base = r["file_offset"] + (pl.slice_begin * row_bytes if pl.slice_dim == 0 else 0)
             n = min(pl.nbytes, 8 << 20)
-            raw = np.fromfile(ref.shards[r["shard"]], np.uint8, count=n, offset=r["file_offset"] + pl.nbytes - n)
+            raw = np.fromfile(ref.shards[r["shard"]], np.uint8, count=n, offset=base + pl.nbytes - n)
             got = m.read(local, pl.pool_offset + pl.nbytes - n, n)
             verified = verified and bool(np.array_equal(raw, got))
         if not verified:
@@ -377,7 +399,7 @@ def main():
         pool.close()
         barrier()
         if rank == 0:
-            print(json.dumps(line), flush=True)
+            emit(line)
             if not args.keep_data:
                 shutil.rmtree(d, ignore_errors=True)
         if world > 1:
@@ -453,7 +475,7 @@ def main():
             ctx = cpu_port_setup(path, min(file_bytes, 4 << 30))
             cpu_port_step(ctx)
             ts = [cpu_port_step(ctx) for _ in range(3)]
-            cpu = {"value": ctx[3] * len(ts) / sum(ts) / 1e9, "unit": UNIT, "cores": ctx[0].max_threads(), "kind": "port",
+            cpu = {"value": ctx[3] * len(ts) / sum(ts) / 1e9, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                    "sample": f"first {ctx[3] / 1e9:.2f} GB of the checkpoint x{len(ts)}, pread + convert into host memory, all OpenMP threads"}
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
@@ -485,7 +507,7 @@ def main():
     pool.close()
     barrier()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
         if not args.keep_data:
             shutil.rmtree(d, ignore_errors=True)
     if world > 1:

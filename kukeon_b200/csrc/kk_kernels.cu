@@ -5,7 +5,7 @@
 //   warp 0 (one elected lane) = TMA producer. It walks this CTA's tiles, resolves tile -> segment,
 //     publishes a TileDesc and pulls the tile's source bytes into a 4-stage shared-memory ring with
 //     cp.async.bulk (UBLKCP) completing on an mbarrier.
-//   warps 1..8 = consumers. Depending on the segment op they
+//   warps 1..16 = consumers. Depending on the segment op they
 //       COPY, aligned     : one lane fires cp.async.bulk shared->global stores, one per destination pool
 //                           (local pool + peer-mapped pools: the fused fan-out), no register traffic;
 //       F32/F16 -> BF16   : ld.shared.v4, cvt.rn.bf16x2.f32, st.global.v4 (16 B per lane, coalesced);
@@ -26,7 +26,7 @@ namespace {
 
 constexpr int kStages = 4;
 #ifndef KK_CONSUMER_WARPS
-#define KK_CONSUMER_WARPS 8
+#define KK_CONSUMER_WARPS 16
 #endif
 constexpr int kConsumerWarps = KK_CONSUMER_WARPS;
 constexpr int kConsumerThreads = kConsumerWarps * 32;

@@ -38,6 +38,8 @@ def _c():
         L.synth_write.restype = C.c_int
         L.synth_fill.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_uint64]
         L.synth_fill.restype = None
+        L.synth_set_threads.argtypes = [C.c_int]
+        L.synth_set_threads(int(os.environ.get("KK_SYNTH_THREADS", "0")) or (os.cpu_count() or 1))
         _lib = L
     return _lib
 

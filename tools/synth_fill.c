@@ -10,6 +10,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 enum { K_BYTES = 0, K_BF16 = 1, K_F16 = 2, K_F32 = 3, K_Q4K = 4 };
 
@@ -98,4 +101,13 @@ void synth_fill(uint8_t* dst, uint64_t nbytes, int kind, uint64_t seed, uint64_t
     memcpy(dst + 8 * nw, tmp, nbytes & 7);
   }
   if (kind == K_Q4K) fix_q4k(dst, 0, nbytes / 144, seed, idx);
+}
+
+/* torchrun exports OMP_NUM_THREADS=1; callers that want all cores say so explicitly. */
+void synth_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
 }
