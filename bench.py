@@ -300,25 +300,39 @@ def main():
     # ---- cold path once: index + plan + pool allocation (+ peer exchange), then time-to-agent-ready ----------
     barrier()
     t_ready0 = time.time()
+    brk = {}
     ref = modelhub.Pull(path)
+    brk["pull_s"] = time.time() - t_ready0
     lflags = gpupool.LOAD_DEFER | (gpupool.LOAD_GPT2_CONV1D_T if spec["kind"] == "gpt2" else 0)
+    t1 = time.time()
     m = modelhub.Load(pool, ref, mode=mode, fanout=gpupool.FANOUT_P2P, flags=lflags,
                       part_index=rank if world > 1 else 0, part_count=world if world > 1 else 0)
+    brk["plan_alloc_s"] = time.time() - t1
+    t1 = time.time()
     if world > 1 and mode == gpupool.MODE_BROADCAST:
         h, _ = m.export(local)
         hs = [None] * world
         dist.all_gather_object(hs, h, group=gloo)
+        brk["handle_exchange_s"] = time.time() - t1
+        t1 = time.time()
         for r, hh in enumerate(hs):
             if r != rank:
                 m.peer_attach(r, hh)
+        brk["peer_attach_s"] = time.time() - t1
+    t1 = time.time()
     barrier()
     if args.kernel_only:
         m.stage_resident()
         barrier()
         m.convert_resident()
     else:
+        brk["barrier_s"] = time.time() - t1
+        t1 = time.time()
         m.load_part()
+        brk["load_part_s"] = time.time() - t1
+    t1 = time.time()
     handle, manifest = m.export(local)
+    brk["export_s"] = time.time() - t1
     barrier()
     t_ready = None if args.kernel_only else allmax(time.time() - t_ready0)
     st0 = m.stats()
@@ -495,6 +509,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
         "time_to_agent_ready_s": t_ready,
+        "time_to_agent_ready_breakdown_rank0": brk,
         "wall_ms_per_step": wall / args.steps * 1e3,
         "setup": {"synth_s": t_gen, "kk_open_s": t_open, "index_s": st0["index_s"], "plan_s": st0["plan_s"], "alloc_s": st0["alloc_s"],
                   "first_load_s": st0["load_s"], "chunks_per_load": chunks_per_load, "h2d_probe_GBps": h2d_probe},

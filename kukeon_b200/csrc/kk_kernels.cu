@@ -335,37 +335,70 @@ __device__ __forceinline__ void consume_q4k(const Dsts& D, uint32_t pay, uint32_
   }
 }
 
-// 2-D transpose tile read straight from global memory (source rows may be arbitrarily aligned).
+// 2-D transpose tile.  Source elements come either from the TMA-staged tile (t.bulk == 2: the producer pulled
+// the tile's rows into the stage with one cp.async.bulk per row, KK_T_COLS*ES + 16 bytes apart) or, when a row
+// is not 16-byte aligned, straight from global memory through a [col][row] scratch in the stage buffer.
 template <int ES, int OES, int CONV>  // CONV: 0 verbatim, 1 f32->bf16, 2 f16->bf16
-__device__ __forceinline__ void consume_transpose(const Dsts& D, const uint8_t* src, const TileDesc& t, uint32_t scratch, int ctid) {
+__device__ __forceinline__ void consume_transpose(const Dsts& D, const uint8_t* src, const TileDesc& t, uint32_t sbase, int ctid) {
   const uint32_t nr = t.n_units & 0xFFFFu, nc = t.n_units >> 16;
-  const uint8_t* s0 = src + t.src_off;
-  for (uint32_t i = ctid; i < KK_T_ROWS * KK_T_COLS; i += kConsumerThreads) {
-    const uint32_t r = i / KK_T_COLS, c = i % KK_T_COLS;
-    if (r < nr && c < nc) {
-      const uint8_t* p = s0 + ((uint64_t)r * t.C + c) * ES;
-      uint32_t w = 0;
-      if (((uintptr_t)p & (ES - 1)) == 0) {
-        if (ES == 4) w = *reinterpret_cast<const uint32_t*>(p);
-        else w = *reinterpret_cast<const uint16_t*>(p);
-      } else {
+  const bool staged = t.bulk == 2;
+  constexpr uint32_t kPitch = KK_T_COLS * ES + KK_T_PITCH_PAD;
+  if (!staged) {
+    const uint8_t* s0 = src + t.src_off;
+    for (uint32_t i = ctid; i < KK_T_ROWS * KK_T_COLS; i += kConsumerThreads) {
+      const uint32_t r = i / KK_T_COLS, c = i % KK_T_COLS;
+      if (r < nr && c < nc) {
+        const uint8_t* p = s0 + ((uint64_t)r * t.C + c) * ES;
+        uint32_t w = 0;
+        if (((uintptr_t)p & (ES - 1)) == 0) {
+          if (ES == 4) w = *reinterpret_cast<const uint32_t*>(p);
+          else w = *reinterpret_cast<const uint16_t*>(p);
+        } else {
 #pragma unroll
-        for (int k = 0; k < ES; ++k) w |= (uint32_t)p[k] << (8 * k);
+          for (int k = 0; k < ES; ++k) w |= (uint32_t)p[k] << (8 * k);
+        }
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(sbase + 4 * (c * (KK_T_ROWS + 1) + r)), "r"(w) : "memory");
       }
-      asm volatile("st.shared.u32 [%0], %1;" ::"r"(scratch + 4 * (c * (KK_T_ROWS + 1) + r)), "r"(w) : "memory");
     }
+    named_bar_consumers();
   }
-  named_bar_consumers();
-  for (uint32_t i = ctid; i < KK_T_ROWS * KK_T_COLS; i += kConsumerThreads) {
-    const uint32_t c = i / KK_T_ROWS, r = i % KK_T_ROWS;
-    if (r < nr && c < nc) {
-      uint32_t w;
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(scratch + 4 * (c * (KK_T_ROWS + 1) + r)));
-      const uint64_t off = t.dst_off + ((uint64_t)(t.col0 + c) * t.R + t.row0 + r) * OES;
-      if (CONV == 1) store2_all(D, off, to_bf16(__uint_as_float(w)));
-      else if (CONV == 2) store2_all(D, off, to_bf16(__half2float(__ushort_as_half((unsigned short)w))));
-      else if (OES == 2) store2_all(D, off, (uint16_t)w);
-      else store4_all(D, off, w);
+  auto elem = [&](uint32_t r, uint32_t c) -> uint32_t {
+    uint32_t w;
+    if (staged) {
+      if (ES == 4) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(sbase + r * kPitch + c * ES));
+      else asm volatile("ld.shared.u16 %0, [%1];" : "=r"(w) : "r"(sbase + r * kPitch + c * ES));
+    } else {
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(sbase + 4 * (c * (KK_T_ROWS + 1) + r)));
+    }
+    return w;
+  };
+  auto conv16 = [&](uint32_t w) -> uint32_t {
+    if (CONV == 1) return to_bf16(__uint_as_float(w));
+    if (CONV == 2) return to_bf16(__half2float(__ushort_as_half((unsigned short)w)));
+    return w & 0xFFFFu;
+  };
+  if (OES == 2 && (t.R & 1u) == 0 && (t.dst_off & 3u) == 0 && (t.row0 & 1u) == 0) {
+    // two adjacent destination elements (source rows 2k, 2k+1) per 4-byte store
+    const uint32_t npair = (nr + 1) / 2;
+    for (uint32_t i = ctid; i < (KK_T_ROWS / 2) * KK_T_COLS; i += kConsumerThreads) {
+      const uint32_t c = i / (KK_T_ROWS / 2), rp = i % (KK_T_ROWS / 2);
+      if (rp < npair && c < nc) {
+        const uint32_t r = 2 * rp;
+        const uint64_t off = t.dst_off + ((uint64_t)(t.col0 + c) * t.R + t.row0 + r) * 2;
+        const uint32_t lo = conv16(elem(r, c));
+        if (r + 1 < nr) store4_all(D, off, lo | (conv16(elem(r + 1, c)) << 16));
+        else store2_all(D, off, (uint16_t)lo);
+      }
+    }
+  } else {
+    for (uint32_t i = ctid; i < KK_T_ROWS * KK_T_COLS; i += kConsumerThreads) {
+      const uint32_t c = i / KK_T_ROWS, r = i % KK_T_ROWS;
+      if (r < nr && c < nc) {
+        const uint32_t w = elem(r, c);
+        const uint64_t off = t.dst_off + ((uint64_t)(t.col0 + c) * t.R + t.row0 + r) * OES;
+        if (OES == 2) store2_all(D, off, (uint16_t)conv16(w));
+        else store4_all(D, off, w);
+      }
     }
   }
 }
@@ -450,7 +483,7 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
             d.dst_off = seg.dst_off + b * 512u;
             break;
           }
-          default: {  // transposes: no TMA, consumers read global memory directly
+          default: {  // transposes
             const uint32_t C = seg.p0;
             const uint32_t ct = (C + KK_T_COLS - 1) / KK_T_COLS;
             const uint32_t tr = t / ct, tc = t % ct;
@@ -464,6 +497,19 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
             d.C = C; d.R = seg.p1; d.col0 = c0; d.row0 = seg.p2 + (uint32_t)r0;
             d.src_off = seg.src_off + (r0 * C + c0) * es;
             d.dst_off = seg.dst_off;
+            // rows 16-byte aligned and a whole number of 16-byte units wide: stage the tile with one bulk copy per row
+            const uint64_t row_pitch = (uint64_t)C * es;
+            if ((((uintptr_t)(L.src + d.src_off)) & 15u) == 0 && (row_pitch & 15u) == 0 && ((nc * es) & 15u) == 0) {
+              d.bulk = 2;
+              d.pay_off = 0;
+              descs[s] = d;
+              const uint32_t rb = nc * es, spitch = KK_T_COLS * es + KK_T_PITCH_PAD;
+              mbar_arrive_expect_tx(full0 + 8 * s, nr * rb);
+              const uint8_t* gp = L.src + d.src_off;
+              const uint32_t sb = smem_u32(stage_buf + s * kStageBytes);
+              for (uint32_t r = 0; r < nr; ++r) bulk_g2s(sb + r * spitch, gp + r * row_pitch, rb, full0 + 8 * s);
+              continue;
+            }
             break;
           }
         }

@@ -12,6 +12,7 @@
 #include <fcntl.h>
 #include <pthread.h>
 #include <sched.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -33,20 +34,40 @@ double now_s() {
 
 struct FdSet {
   std::vector<int> fds;
-  explicit FdSet(const std::vector<std::string>& paths) {
+  std::vector<const uint8_t*> maps;  // read-only mappings, used for short strided reads (no syscall per row)
+  std::vector<uint64_t> sizes;
+  explicit FdSet(const std::vector<std::string>& paths, bool want_maps = false) {
     for (auto& p : paths) {
       int fd = ::open(p.c_str(), O_RDONLY | O_CLOEXEC);
       if (fd < 0) {
         int e = errno;
-        for (int f : fds) ::close(f);
+        cleanup();
         fail(e == ENOENT ? KK_ENOENT : KK_EIO, "open %s: %s", p.c_str(), strerror(e));
       }
       fds.push_back(fd);
+      const uint8_t* mp = nullptr;
+      uint64_t sz = 0;
+      if (want_maps) {
+        struct stat st;
+        if (fstat(fd, &st) == 0 && st.st_size > 0) {
+          void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_SHARED, fd, 0);
+          if (m != MAP_FAILED) { mp = (const uint8_t*)m; sz = (uint64_t)st.st_size; }
+        }
+      }
+      maps.push_back(mp);
+      sizes.push_back(sz);
     }
   }
-  ~FdSet() {
+  void cleanup() {
+    for (size_t i = 0; i < maps.size(); ++i)
+      if (maps[i]) munmap((void*)maps[i], sizes[i]);
     for (int f : fds) ::close(f);
+    maps.clear();
+    fds.clear();
   }
+  ~FdSet() { cleanup(); }
+  FdSet(const FdSet&) = delete;
+  FdSet& operator=(const FdSet&) = delete;
 };
 
 void pread_full(int fd, uint8_t* dst, uint64_t len, uint64_t off, const std::string& name) {
@@ -117,7 +138,14 @@ struct ErrorSink {
 
 // Fill the slot with the chunk's file bytes.
 void read_chunk(const Chunk& c, const FdSet& fds, const Index& ix, uint8_t* pinned) {
-  for (auto& r : c.reads) pread_full(fds.fds[c.shard], pinned + r.buf_off, r.len, r.file_off, ix.shards[c.shard]);
+  const uint8_t* mp = fds.maps.empty() ? nullptr : fds.maps[c.shard];
+  const uint64_t msz = mp ? fds.sizes[c.shard] : 0;
+  for (auto& r : c.reads) {
+    // column-slice rows (SCATTER) are thousands of 2-7 KB runs per chunk: copy them out of the mapping instead
+    // of paying one pread syscall each; long contiguous ranges go through pread (no page-fault / TLB cost)
+    if (mp && r.len <= (256u << 10) && r.file_off <= msz && r.len <= msz - r.file_off) memcpy(pinned + r.buf_off, mp + r.file_off, r.len);
+    else pread_full(fds.fds[c.shard], pinned + r.buf_off, r.len, r.file_off, ix.shards[c.shard]);
+  }
 }
 
 uint64_t seg_base_of(const Plan& P, int part) {
@@ -126,14 +154,29 @@ uint64_t seg_base_of(const Plan& P, int part) {
   return b;
 }
 
+// Test hook: KUKEON_GPULOAD_TEST_NDST=<n> pads the destination list to n entries by repeating the ones it has,
+// so that the kernel's n-destination store paths (the 8-GPU fan-out ladder) can be exercised on a box with fewer
+// GPUs.  Writing the same bytes to the same pool several times is harmless.
+void pad_dsts_for_test(ConvertLaunch& L) {
+  static const int want = [] {
+    const char* e = getenv("KUKEON_GPULOAD_TEST_NDST");
+    return e ? atoi(e) : 0;
+  }();
+  if (want <= 0) return;
+  const uint32_t have = L.n_dst;
+  while (L.n_dst < (uint32_t)want && L.n_dst < KK_MAX_DST) { L.dst[L.n_dst] = L.dst[L.n_dst % have]; L.n_dst++; }
+}
+
 // Destination pools a convert launch on local device `li` writes to.
 void fill_dsts(kk_model* m, int li, ConvertLaunch& L) {
   L.n_dst = 0;
   L.flags = 0;
   for (auto& d : L.dst) d = nullptr;
   L.dst[L.n_dst++] = m->pools[(size_t)li];
-  if (m->plan.mode != KK_MODE_BROADCAST) return;
-  if (m->opts.fanout == KK_FANOUT_NONE) return;
+  if (m->plan.mode != KK_MODE_BROADCAST || m->opts.fanout == KK_FANOUT_NONE) {
+    pad_dsts_for_test(L);
+    return;
+  }
   if (m->opts.part_count > 1) {
     for (int r = 0; r < KK_MAX_DEVICES; ++r)
       if (m->peer_ptr[r]) L.dst[L.n_dst++] = (uint8_t*)m->peer_ptr[r];
@@ -141,6 +184,7 @@ void fill_dsts(kk_model* m, int li, ConvertLaunch& L) {
     for (size_t j = 0; j < m->pools.size(); ++j)
       if ((int)j != li) L.dst[L.n_dst++] = m->pools[j];
   }
+  pad_dsts_for_test(L);
 }
 
 // Ingest plan part `part` on local device `li`.
@@ -347,7 +391,7 @@ void ctx_close(kk_ctx* c) {
 // ---------------------------------------------------------------------------------------------
 static void do_load(kk_model* m) {
   const double t0 = now_s();
-  FdSet fds(m->plan.index.shards);
+  FdSet fds(m->plan.index.shards, m->plan.mode == KK_MODE_SCATTER);
   const size_t nl = m->dev_idx.size();
   m->t_part.assign(nl, 0.0);
   const bool multi_proc = m->opts.part_count > 1;
@@ -598,7 +642,7 @@ std::string model_stats(kk_model* m) {
 void model_stage_resident(kk_model* m) {
   free_resident(m);
   kk_ctx* c = m->ctx;
-  FdSet fds(m->plan.index.shards);
+  FdSet fds(m->plan.index.shards, m->plan.mode == KK_MODE_SCATTER);
   m->resident.resize(m->dev_idx.size());
   for (size_t li = 0; li < m->dev_idx.size(); ++li) {
     Device& dev = c->devs[(size_t)m->dev_idx[li]];

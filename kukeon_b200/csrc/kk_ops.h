@@ -10,7 +10,8 @@
 #define KK_Q4K_BLOCK_ELEMS 256u
 #define KK_Q4K_TILE_BLOCKS 224u  /* 224*144 = 32256 B in, 224*512 = 114688 B out */
 #define KK_T_ROWS 32u            /* transpose tile: 32 source rows ... */
-#define KK_T_COLS 64u            /* ... x 64 source columns (elements) */
+#define KK_T_COLS 128u           /* ... x 128 source columns (elements) */
+#define KK_T_PITCH_PAD 16u       /* TMA-staged transpose rows sit KK_T_COLS*es + 16 bytes apart (bank spread) */
 #define KK_MAX_DST 8
 
 enum KKOp : uint32_t {

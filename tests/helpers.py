@@ -59,7 +59,7 @@ def emulate_part(plan: dict, part: int, pool_bytes: int) -> Tuple[np.ndarray, np
                     dst = pool[do:do + C * R * oes].reshape(C, R, oes)
                     dst[:, r0:r0 + u, :] = v.transpose(1, 0, 2)
                     mask[do:do + C * R * oes].reshape(C, R, oes)[:, r0:r0 + u, :] = True
-                    tiles += -(-u // 32) * -(-C // 64)
+                    tiles += -(-u // 32) * -(-C // 128)
                     continue
                 assert not mask[do:do + out.size].any(), "segment overlaps an earlier one"
                 pool[do:do + out.size] = out

@@ -311,3 +311,124 @@ def test_medium_checkpoint_checksum_of_checksums(native, tmp_path, coracle):
     finally:
         import shutil
         shutil.rmtree(d, ignore_errors=True)
+
+
+def _shm_free() -> int:
+    try:
+        st = os.statvfs("/dev/shm")
+        return st.f_bavail * st.f_frsize
+    except OSError:
+        return 0
+
+
+@pytest.mark.skipif(_shm_free() < 40 << 30, reason="needs ~20 GB of /dev/shm for the full-size checkpoint")
+def test_full_size_llama3_8b_round_trip_properties(native, coracle):
+    """BASELINE config 2 at its full size (291 tensors, 16,060,522,496 B): index == oracle, every tensor's
+    device-side checksum == oracle checksum of the file bytes (bf16 passthrough is the identity), a checksum
+    of checksums ties it together, and a second load (idempotence) leaves the pool bit-identical."""
+    import shutil
+    d = f"/dev/shm/kk_full8b_{os.getpid()}"
+    try:
+        synth.make_llama(d, synth.LLAMA3_8B)
+        shards, recs = oracle.index_path(d)
+        assert len(recs) == 291 and len(shards) == 4 and sum(r["nbytes"] for r in recs) == 16_060_522_496
+        assert gpupool.index(d) == recs
+        with gpupool.Pool([0]) as pl:
+            m = pl.load(d)
+            try:
+                assert m.info()["pool_bytes"] == 16_060_522_496  # every slot already 256-aligned: no padding
+                gpu_sums = [m.checksum(0, p.pool_offset, p.nbytes) for p in (m.placements(r["name"])[0] for r in recs)]
+                cpu_sums = []
+                for r in recs:
+                    mm = np.memmap(shards[r["shard"]], np.uint8, "r", offset=r["file_offset"], shape=(r["nbytes"],))
+                    cpu_sums.append(coracle.checksum(mm))
+                    del mm
+                assert gpu_sums == cpu_sums
+                whole = m.checksum(0, 0, 16_060_522_496)
+                m.load_part()  # idempotence: loading again must not change a byte
+                assert m.checksum(0, 0, 16_060_522_496) == whole
+                assert oracle.checksum(np.array(gpu_sums, np.uint64)) == oracle.checksum(np.array(cpu_sums, np.uint64))
+            finally:
+                m.release()
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+@pytest.mark.skipif(_shm_free() < 40 << 30, reason="needs /dev/shm for the checkpoint")
+def test_large_q4k_linearity_and_checksum(native, coracle):
+    """Mixtral-shaped GGUF (2 layers, ~1.7 GB of Q4_K blocks -> ~6 GB bf16): device checksum of every dequantised
+    tensor == checksum of the C oracle's output for it."""
+    import shutil
+    p = f"/dev/shm/kk_q4k_{os.getpid()}.gguf"
+    try:
+        synth.write_gguf(p, synth.mixtral_gguf_tensors(layers=2), 8007)
+        shards, recs = oracle.index_path(p)
+        with gpupool.Pool([0]) as pl:
+            m = pl.load(p)
+            try:
+                checked = 0
+                for r in recs:
+                    if r["dtype"] != "Q4_K" or r["nbytes"] > 600 << 20:
+                        continue
+                    raw = np.fromfile(p, np.uint8, count=r["nbytes"], offset=r["file_offset"])
+                    want = coracle.checksum(coracle.q4k_to_bf16(raw))
+                    q = m.placements(r["name"])[0]
+                    assert m.checksum(0, q.pool_offset, q.nbytes) == want, r["name"]
+                    checked += 1
+                assert checked >= 10
+            finally:
+                m.release()
+    finally:
+        if os.path.exists(p):
+            os.remove(p)
+
+
+_NDST_CHILD = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np
+from kukeon_b200 import gpupool
+from oracle import oracle
+paths = sys.argv[2:]
+with gpupool.Pool([0], n_staging_buffers=2, staging_buffer_bytes=1 << 20, n_reader_threads=1) as pl:
+    for spec in paths:
+        path, flags = spec.rsplit(":", 1)
+        flags = int(flags)
+        shards, recs = oracle.index_path(path)
+        m = pl.load(path, flags=flags)
+        try:
+            exp, plan = oracle.expected_pool(shards, recs, 0, flags)
+            got = m.read(0, 0, len(exp))
+            for p in plan:
+                a, b = p["pool_offset"], p["pool_offset"] + p["nbytes"]
+                assert np.array_equal(got[a:b], exp[a:b]), f"n_dst={os.environ['KUKEON_GPULOAD_TEST_NDST']}: {p['name']} differs"
+            m.stage_resident(); m.convert_resident()
+            got = m.read(0, 0, len(exp))
+            for p in plan:
+                a, b = p["pool_offset"], p["pool_offset"] + p["nbytes"]
+                assert np.array_equal(got[a:b], exp[a:b]), f"resident n_dst={os.environ['KUKEON_GPULOAD_TEST_NDST']}: {p['name']} differs"
+        finally:
+            m.release()
+print("ok")
+'''
+
+
+@pytest.mark.parametrize("ndst", [3, 8])
+def test_multi_destination_store_paths_on_one_gpu(native, tmp_path, ndst):
+    """The fused fan-out stores every output vector to n_dst pools.  KUKEON_GPULOAD_TEST_NDST aliases the extra
+    destinations onto the local pool so every op's n-destination path (incl. 8 = a full HGX box) runs on one GPU."""
+    d = str(tmp_path / "llama")
+    synth.make_llama(d, dict(hidden=256, ffn=704, layers=2, kv_dim=64, vocab=3000), max_shard_bytes=3_000_000)
+    mixed = str(tmp_path / "m.safetensors")
+    helpers.mixed_safetensors(mixed, pad_header=False)
+    g = str(tmp_path / "mix.gguf")
+    synth.write_gguf(g, synth.mixtral_gguf_tensors(hidden=256, ffn=768, layers=1, experts=2, vocab=512, kv_dim=256), 7)
+    f = str(tmp_path / "gpt2.safetensors")
+    synth.make_gpt2(f, n_layer=2, d=96, vocab=301, n_pos=40)
+    f2 = str(tmp_path / "gpt2_odd.safetensors")
+    synth.write_safetensors(f2, synth.gpt2_tensors(n_layer=1, d=40, vocab=50, n_pos=8, dtype="F16"), 3)
+    env = dict(os.environ, KUKEON_GPULOAD_TEST_NDST=str(ndst))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", _NDST_CHILD, root, f"{d}:0", f"{mixed}:0", f"{g}:0", f"{f}:1", f"{f}:3", f"{f2}:1"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-3000:]
