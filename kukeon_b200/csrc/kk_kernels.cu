@@ -37,7 +37,7 @@ struct __align__(16) TileDesc {
   uint32_t op;
   uint32_t pay_off;  // payload offset inside the stage buffer (0..15 for TMA tiles)
   uint32_t n_units;  // units in this tile (bytes / elements / blocks); transposes: rows | cols<<16
-  uint32_t bulk;     // 1: aligned copy, bulk-store from shared memory
+  uint32_t bulk;     // 1: aligned copy, bulk-store from shared memory; 2: transpose tile staged row by row with TMA
   uint64_t dst_off;  // pool byte offset of the tile's first output (transposes: dst tensor origin)
   uint64_t src_off;  // transposes: byte offset of source element (r0, c0) from L.src
   uint32_t C;        // transposes: source columns
@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
       const TileDesc t = descs[s];
       const uint32_t sbase = smem_u32(stage_buf + s * kStageBytes);
       const uint32_t pay = sbase + t.pay_off;
-      if (t.bulk) {
+      if (t.bulk == 1) {
         if (cwarp == 0) {
           if (lane == 0) {
             fence_proxy_async();

@@ -119,6 +119,10 @@ def test_gpt2_conv1d_transpose(pool, tmp_path):
         q = str(tmp_path / f"gpt2_{dt}.safetensors")
         synth.write_safetensors(q, synth.gpt2_tensors(n_layer=1, d=40, vocab=50, n_pos=8, dtype=dt), 3)
         load_and_check(pool, q, flags=gpupool.LOAD_GPT2_CONV1D_T)
+    for dt, d in (("F32", 41), ("F16", 43), ("BF16", 37)):  # rows that are not 16-byte multiples: direct-global path
+        q = str(tmp_path / f"gpt2_{dt}_{d}.safetensors")
+        synth.write_safetensors(q, synth.gpt2_tensors(n_layer=2, d=d, vocab=50, n_pos=8, dtype=dt), 3)
+        load_and_check(pool, q, flags=gpupool.LOAD_GPT2_CONV1D_T)
 
 
 def test_special_values_nan_inf_subnormal(pool, tmp_path):
@@ -427,8 +431,10 @@ def test_multi_destination_store_paths_on_one_gpu(native, tmp_path, ndst):
     synth.make_gpt2(f, n_layer=2, d=96, vocab=301, n_pos=40)
     f2 = str(tmp_path / "gpt2_odd.safetensors")
     synth.write_safetensors(f2, synth.gpt2_tensors(n_layer=1, d=40, vocab=50, n_pos=8, dtype="F16"), 3)
+    f3 = str(tmp_path / "gpt2_d41.safetensors")  # rows of 41/123/164 elements: not 16-byte multiples -> direct-global transpose path
+    synth.write_safetensors(f3, synth.gpt2_tensors(n_layer=2, d=41, vocab=50, n_pos=8), 4)
     env = dict(os.environ, KUKEON_GPULOAD_TEST_NDST=str(ndst))
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-c", _NDST_CHILD, root, f"{d}:0", f"{mixed}:0", f"{g}:0", f"{f}:1", f"{f}:3", f"{f2}:1"],
+    r = subprocess.run([sys.executable, "-c", _NDST_CHILD, root, f"{d}:0", f"{mixed}:0", f"{g}:0", f"{f}:1", f"{f}:3", f"{f2}:1", f"{f3}:1", f"{f3}:3"],
                        capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-3000:]

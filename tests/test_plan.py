@@ -131,9 +131,9 @@ def test_gpt2_conv1d_transpose(native, tmp_path):
 
 
 def test_gpt2_f16_and_bf16_transpose(native, tmp_path):
-    for dt in ("F16", "BF16"):
-        p = str(tmp_path / f"gpt2_{dt}.safetensors")
-        synth.write_safetensors(p, synth.gpt2_tensors(n_layer=1, d=40, vocab=50, n_pos=8, dtype=dt), 3)
+    for dt, d in (("F16", 40), ("BF16", 40), ("F32", 41), ("F16", 43)):
+        p = str(tmp_path / f"gpt2_{dt}_{d}.safetensors")
+        synth.write_safetensors(p, synth.gpt2_tensors(n_layer=1, d=d, vocab=50, n_pos=8, dtype=dt), 3)
         run_case(p, flags=gpupool.LOAD_GPT2_CONV1D_T, chunk=1 * MB)
 
 
