@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--kernel-only", action="store_true", help="profiling aid: skip the streaming load / e2e legs (every kk_convert launch is a resident one)")
     ap.add_argument("--e2e-only", action="store_true", help="tuning aid: skip the resident kernel leg")
     ap.add_argument("--no-numa-pin", action="store_true")
+    ap.add_argument("--fanout", default="p2p", choices=["p2p", "raw"], help="broadcast order: fused convert+fan-out (p2p) or all-gather the file bytes then convert locally (raw)")
     return ap.parse_args()
 
 
@@ -305,19 +306,21 @@ def main():
     brk["pull_s"] = time.time() - t_ready0
     lflags = gpupool.LOAD_DEFER | (gpupool.LOAD_GPT2_CONV1D_T if spec["kind"] == "gpt2" else 0)
     t1 = time.time()
-    m = modelhub.Load(pool, ref, mode=mode, fanout=gpupool.FANOUT_P2P, flags=lflags,
+    raw = args.fanout == "raw" and world > 1 and mode == gpupool.MODE_BROADCAST
+    m = modelhub.Load(pool, ref, mode=mode, fanout=gpupool.FANOUT_RAW if raw else gpupool.FANOUT_P2P, flags=lflags,
                       part_index=rank if world > 1 else 0, part_count=world if world > 1 else 0)
     brk["plan_alloc_s"] = time.time() - t1
     t1 = time.time()
     if world > 1 and mode == gpupool.MODE_BROADCAST:
-        h, _ = m.export(local)
+        which = gpupool.BUF_RAW if raw else gpupool.BUF_POOL
+        h = m.export_buffer(local, which)
         hs = [None] * world
         dist.all_gather_object(hs, h, group=gloo)
         brk["handle_exchange_s"] = time.time() - t1
         t1 = time.time()
         for r, hh in enumerate(hs):
             if r != rank:
-                m.peer_attach(r, hh)
+                m.peer_attach_buffer(r, which, hh)
         brk["peer_attach_s"] = time.time() - t1
     t1 = time.time()
     barrier()
@@ -329,6 +332,9 @@ def main():
         brk["barrier_s"] = time.time() - t1
         t1 = time.time()
         m.load_part()
+        if raw:
+            barrier()
+            m.convert_local()
         brk["load_part_s"] = time.time() - t1
     t1 = time.time()
     handle, manifest = m.export(local)
@@ -384,6 +390,9 @@ def main():
         barrier()
         t = time.perf_counter()
         m.load_part()
+        if raw:
+            barrier()
+            m.convert_local()
         m.export(local)
         m.checksum(local, first.pool_offset, min(first.nbytes, 1 << 20))  # 8-byte D2H result read
         dt = time.perf_counter() - t
@@ -425,6 +434,9 @@ def main():
     for _ in range(max(args.warmup, 3)):
         barrier()
         m.convert_resident()
+        if raw:
+            barrier()
+            m.convert_local()
     clocks = ClockSampler(local)
     clocks.start()
     time.sleep(0.25)
@@ -433,9 +445,15 @@ def main():
     tc0 = time.time()
     step_ms, launch_ms = [], []
     wall0 = time.perf_counter()
+    raw_ms = []
     for _ in range(args.steps):
         barrier()
         tot, per = m.convert_resident()
+        if raw:  # stage 1 (fan-out of the file bytes) was just timed; stage 2 after every rank's stage 1 has landed
+            barrier()
+            t2 = m.convert_local()
+            raw_ms.append((tot, t2))
+            tot, per = tot + t2, [tot, t2]
         step_ms.append(tot)
         launch_ms.append(per)
     torch.cuda.synchronize()
@@ -456,6 +474,8 @@ def main():
     avg_launch_ms = sum(sum(p) for p in launch_ms) / (len(launch_ms) * max(n_launch, 1))
     # algorithmic HBM bytes of this rank per launch: source read once + pool writes landing in THIS GPU's HBM
     alg_per_step = local_src + part["out_bytes"] * (1 if mode == gpupool.MODE_SCATTER else world) if mode != gpupool.MODE_SINGLE else local_src + part["out_bytes"]
+    if raw:  # stage 1: read own part + incoming peers' parts written; stage 2: read the whole image + write the whole pool
+        alg_per_step = local_src + (file_bytes - local_src) + file_bytes + pool_bytes
     alg_per_launch = alg_per_step / max(n_launch, 1)
     achieved = alg_per_launch / (avg_launch_ms / 1e3) / 1e9 if avg_launch_ms > 0 else 0.0
     traffic = None
@@ -514,6 +534,16 @@ def main():
         "setup": {"synth_s": t_gen, "kk_open_s": t_open, "index_s": st0["index_s"], "plan_s": st0["plan_s"], "alloc_s": st0["alloc_s"],
                   "first_load_s": st0["load_s"], "chunks_per_load": chunks_per_load, "h2d_probe_GBps": h2d_probe},
     }
+    if raw:
+        line["config"]["mode"] = "broadcast, RAW order: all-gather file bytes over NVLink (stage 1) + local convert (stage 2)"
+        line["raw_stages_ms_rank0"] = {"fanout_ms": sum(a for a, _ in raw_ms) / len(raw_ms), "convert_ms": sum(b for _, b in raw_ms) / len(raw_ms)}
+        if nvlink:
+            eg = local_src * (world - 1)
+            fm = line["raw_stages_ms_rank0"]["fanout_ms"]
+            nvlink.update(egress_bytes_per_step_per_gpu=eg, achieved_GBps_per_gpu=eg / (fm / 1e3) / 1e9 if fm > 0 else 0.0,
+                          form="all-gather of the file bytes by P2P bulk stores (stage 1 only)")
+            nvlink["frac_of_measured"] = nvlink["achieved_GBps_per_gpu"] / 770.0
+            nvlink["frac_of_nominal"] = nvlink["achieved_GBps_per_gpu"] / 900.0
     if nvlink:
         line["nvlink"] = nvlink
     if nccl:

@@ -84,7 +84,8 @@ typedef enum kk_fanout {
   KK_FANOUT_P2P = 0,  /* convert kernel stores every output vector to all peer-mapped pools (NVLink/NVSwitch) */
   KK_FANOUT_NVLS = 1, /* multimem.st on an NVLS multicast mapping of the pools (when the host exposes it) */
   KK_FANOUT_NONE = 2, /* local pool only; the caller runs its own collective (e.g. the NCCL comparison) */
-  KK_FANOUT_RAW = 3   /* fan out the *file* bytes (e.g. q4_K blocks) to peers, every device converts locally */
+  KK_FANOUT_RAW = 3   /* BROADCAST only: all-gather the *file* bytes (e.g. q4_K blocks, 3.56x smaller than their bf16)
+                         into a per-device raw image over NVLink, then every device converts everything locally */
 } kk_fanout;
 
 /* kk_config.flags */
@@ -192,6 +193,15 @@ int kk_load_part(kk_model* m);
  * ipc_handle is the 64-byte handle that process got from kk_export.  rank must differ from part_index. */
 int kk_peer_attach(kk_model* m, int rank, const void* ipc_handle_64B);
 int kk_peer_detach_all(kk_model* m);
+/* KK_FANOUT_RAW in multi-process operation: the fan-out destinations are the other ranks' raw images, exported and
+ * attached like pools (which = KK_BUF_RAW).  After every rank's kk_load_part (stage 1) and a caller-side barrier,
+ * kk_convert_local (stage 2) dequantises/casts the gathered bytes into the local pool; ms_total (may be NULL)
+ * receives its CUDA-event time.  Single-process kk_load runs both stages itself. */
+#define KK_BUF_POOL 0
+#define KK_BUF_RAW 1
+int kk_export_buffer(kk_model* m, int device, int which, void* ipc_handle_64B);
+int kk_peer_attach_buffer(kk_model* m, int rank, int which, const void* ipc_handle_64B);
+int kk_convert_local(kk_model* m, float* ms_total);
 
 int kk_model_get_info(kk_model* m, kk_model_info* out);
 int kk_placements(kk_model* m, const char* tensor, kk_placement* out, size_t cap, size_t* n);

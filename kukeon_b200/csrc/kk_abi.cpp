@@ -179,6 +179,39 @@ int kk_peer_detach_all(kk_model* m) {
   });
 }
 
+int kk_export_buffer(kk_model* m, int device, int which, void* h) {
+  return guard([&] {
+    need(m, "model");
+    need(h, "ipc_handle");
+    int li = kk::model_local_device(m, device);
+    if (which == KK_BUF_POOL) {
+      KK_CUDA(cudaSetDevice(device));
+      cudaIpcMemHandle_t ih;
+      KK_CUDA(cudaIpcGetMemHandle(&ih, m->pools[(size_t)li]));
+      memcpy(h, &ih, sizeof ih);
+    } else if (which == KK_BUF_RAW) {
+      kk::model_export_raw(m, li, h);
+    } else kk::fail(KK_EINVAL, "unknown buffer kind %d", which);
+  });
+}
+
+int kk_peer_attach_buffer(kk_model* m, int rank, int which, const void* h) {
+  return guard([&] {
+    need(m, "model");
+    need(h, "ipc_handle");
+    if (which == KK_BUF_POOL) kk::model_peer_attach(m, rank, h);
+    else if (which == KK_BUF_RAW) kk::model_peer_attach_raw(m, rank, h);
+    else kk::fail(KK_EINVAL, "unknown buffer kind %d", which);
+  });
+}
+
+int kk_convert_local(kk_model* m, float* ms_total) {
+  return guard([&] {
+    need(m, "model");
+    kk::model_convert_local(m, ms_total);
+  });
+}
+
 int kk_model_get_info(kk_model* m, kk_model_info* o) {
   return guard([&] {
     need(m, "model");

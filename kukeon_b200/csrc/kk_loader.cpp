@@ -242,6 +242,189 @@ void run_part(kk_model* m, int li, int part, const FdSet& fds) {
   sink.rethrow();
 }
 
+// ---- KK_FANOUT_RAW ------------------------------------------------------------------------------
+bool is_raw(const kk_model* m) { return m->opts.fanout == KK_FANOUT_RAW && m->plan.mode == KK_MODE_BROADCAST; }
+
+// Peer raw images a stage-1 copy launch on local device li writes to (never the local image: it is the source).
+void fill_raw_dsts(kk_model* m, int li, ConvertLaunch& L) {
+  L.n_dst = 0;
+  L.flags = 0;
+  for (auto& d : L.dst) d = nullptr;
+  if (m->opts.part_count > 1) {
+    for (int r = 0; r < KK_MAX_DEVICES; ++r)
+      if (m->peer_raw_ptr[r]) L.dst[L.n_dst++] = (uint8_t*)m->peer_raw_ptr[r];
+  } else {
+    for (size_t j = 0; j < m->raw.size(); ++j)
+      if ((int)j != li) L.dst[L.n_dst++] = m->raw[j].image;
+  }
+}
+
+// Stage 1 of a RAW load on local device li: file bytes of plan part `part` -> local raw image (H2D straight into
+// place) -> peers' raw images (COPY launch per chunk, bulk TMA stores over NVLink).  fan_out=false: H2D only.
+void run_part_raw(kk_model* m, int li, int part, const FdSet& fds, bool fan_out) {
+  kk_ctx* c = m->ctx;
+  Device& dev = c->devs[(size_t)m->dev_idx[(size_t)li]];
+  const PartPlan& pp = m->plan.parts[(size_t)part];
+  if (pp.chunks.empty()) return;
+  kk_model::Raw& R = m->raw[(size_t)li];
+  ConvertLaunch base{};
+  fill_raw_dsts(m, li, base);
+  const bool do_fan = fan_out && base.n_dst > 0;
+  if (do_fan && !c->peer_ok && m->opts.part_count <= 1) fail(KK_EUNSUPPORTED, "KK_FANOUT_RAW needs peer access between the context's devices");
+  std::atomic<size_t> next{0};
+  ErrorSink sink;
+  auto worker = [&](Reader* rd) {
+    try {
+      if (!(c->cfg.flags & KK_CFG_NO_NUMA_PIN)) pin_this_thread(dev.numa_cpus);
+      KK_CUDA(cudaSetDevice(dev.ordinal));
+      size_t k = 0;
+      for (;;) {
+        if (sink.stop) break;
+        size_t ci = next.fetch_add(1);
+        if (ci >= pp.chunks.size()) break;
+        const Chunk& ch = pp.chunks[ci];
+        Slot& s = rd->slots[k++ % rd->slots.size()];
+        KK_CUDA(cudaEventSynchronize(s.done));
+        read_chunk(ch, fds, m->plan.index, s.pinned);
+        KK_CUDA(cudaMemcpyAsync(R.image + m->img_off[(size_t)part][ci], s.pinned, ch.buf_bytes, cudaMemcpyHostToDevice, rd->stream));
+        if (do_fan) {
+          ConvertLaunch L = base;
+          L.src = R.image;
+          L.segs = R.d_copy_segs + m->chunk_base[(size_t)part] + ci;
+          L.n_segs = 1;
+          L.n_tiles = (uint32_t)kk_seg_tiles(KK_OP_COPY, align_up(ch.buf_bytes, 16), 0);
+          KK_CUDA(launch_convert(L, dev.sm_count, rd->stream));
+        }
+        KK_CUDA(cudaEventRecord(s.done, rd->stream));
+      }
+      KK_CUDA(cudaStreamSynchronize(rd->stream));
+    } catch (...) {
+      sink.capture();
+    }
+  };
+  std::vector<std::thread> th;
+  for (size_t r = 0; r < dev.readers.size(); ++r) th.emplace_back(worker, &dev.readers[r]);
+  for (auto& t : th) t.join();
+  if (sink.first) {
+    cudaSetDevice(dev.ordinal);
+    for (auto& r : dev.readers) cudaStreamSynchronize(r.stream);
+  }
+  sink.rethrow();
+}
+
+// Allocate the raw images and build the stage-1 (copy) and stage-2 (convert) segment tables.
+void setup_raw(kk_model* m) {
+  const Plan& P = m->plan;
+  m->img_off.assign(P.parts.size(), {});
+  m->chunk_base.assign(P.parts.size(), 0);
+  uint64_t tot = 0;
+  uint32_t nchunks = 0;
+  for (size_t p = 0; p < P.parts.size(); ++p) {
+    m->chunk_base[p] = nchunks;
+    for (auto& ch : P.parts[p].chunks) {
+      m->img_off[p].push_back(tot);
+      tot += align_up(ch.buf_bytes + 64, 256);
+      nchunks++;
+    }
+  }
+  std::vector<KKSeg> copy_segs, conv_segs;
+  std::vector<kk_model::Resident::Launch> launches;
+  int last_shard = -1;
+  for (size_t p = 0; p < P.parts.size(); ++p) {
+    const PartPlan& pp = P.parts[p];
+    for (size_t ci = 0; ci < pp.chunks.size(); ++ci) {
+      const Chunk& ch = pp.chunks[ci];
+      KKSeg cs{};
+      cs.src_off = cs.dst_off = m->img_off[p][ci];
+      cs.units = align_up(ch.buf_bytes, 16);
+      cs.op = KK_OP_COPY;
+      copy_segs.push_back(cs);
+      bool fresh = launches.empty() || last_shard != (int)ch.shard || launches.back().n_segs + ch.seg_count > kMaxSegsPerLaunch ||
+                   (uint64_t)launches.back().n_tiles + ch.n_tiles > 0xFFFFFFF0ull;
+      if (fresh) launches.push_back({(uint32_t)conv_segs.size(), 0, 0, 0, 0});
+      last_shard = (int)ch.shard;
+      auto& L = launches.back();
+      for (uint32_t j = 0; j < ch.seg_count; ++j) {
+        KKSeg sg = pp.segs[ch.seg_begin + j];
+        sg.src_off += m->img_off[p][ci];
+        sg.tile_begin += L.n_tiles;
+        conv_segs.push_back(sg);
+      }
+      L.n_segs += ch.seg_count;
+      L.n_tiles += ch.n_tiles;
+      L.src_bytes += ch.src_bytes;
+      L.out_bytes += ch.out_bytes;
+    }
+  }
+  m->raw.resize(m->dev_idx.size());
+  for (size_t li = 0; li < m->dev_idx.size(); ++li) {
+    Device& d = m->ctx->devs[(size_t)m->dev_idx[li]];
+    KK_CUDA(cudaSetDevice(d.ordinal));
+    auto& R = m->raw[li];
+    R.bytes = tot ? tot : 256;
+    cudaError_t e = cudaMalloc((void**)&R.image, R.bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); R.image = nullptr; fail(KK_ENOMEM, "device %d: cudaMalloc(%llu) for the raw image failed", d.ordinal, (unsigned long long)R.bytes); }
+    if (!copy_segs.empty()) {
+      KK_CUDA(cudaMalloc((void**)&R.d_copy_segs, copy_segs.size() * sizeof(KKSeg)));
+      KK_CUDA(cudaMemcpy(R.d_copy_segs, copy_segs.data(), copy_segs.size() * sizeof(KKSeg), cudaMemcpyHostToDevice));
+    }
+    if (!conv_segs.empty()) {
+      KK_CUDA(cudaMalloc((void**)&R.d_conv_segs, conv_segs.size() * sizeof(KKSeg)));
+      KK_CUDA(cudaMemcpy(R.d_conv_segs, conv_segs.data(), conv_segs.size() * sizeof(KKSeg), cudaMemcpyHostToDevice));
+    }
+    R.conv_launches = launches;
+  }
+}
+
+void free_raw(kk_model* m) {
+  for (size_t li = 0; li < m->raw.size(); ++li) {
+    auto& R = m->raw[li];
+    cudaSetDevice(m->ctx->devs[(size_t)m->dev_idx[li]].ordinal);
+    if (R.image) cudaFree(R.image);
+    if (R.d_copy_segs) cudaFree(R.d_copy_segs);
+    if (R.d_conv_segs) cudaFree(R.d_conv_segs);
+  }
+  m->raw.clear();
+}
+
+// Stage 2: every local device converts the whole gathered image into its own pool.
+void convert_local_all(kk_model* m, float* ms_total) {
+  kk_ctx* c = m->ctx;
+  const size_t nl = m->dev_idx.size();
+  std::vector<cudaEvent_t> e0(nl), e1(nl);
+  for (size_t li = 0; li < nl; ++li) {
+    Device& dev = c->devs[(size_t)m->dev_idx[li]];
+    auto& R = m->raw[li];
+    KK_CUDA(cudaSetDevice(dev.ordinal));
+    KK_CUDA(cudaEventCreate(&e0[li]));
+    KK_CUDA(cudaEventCreate(&e1[li]));
+    KK_CUDA(cudaEventRecord(e0[li], dev.stream));
+    for (auto& La : R.conv_launches) {
+      ConvertLaunch L{};
+      L.src = R.image;
+      L.segs = R.d_conv_segs + La.seg_begin;
+      L.n_segs = La.n_segs;
+      L.n_tiles = La.n_tiles;
+      L.n_dst = 1;
+      L.dst[0] = m->pools[li];
+      KK_CUDA(launch_convert(L, dev.sm_count, dev.stream));
+    }
+    KK_CUDA(cudaEventRecord(e1[li], dev.stream));
+  }
+  float worst = 0.f;
+  for (size_t li = 0; li < nl; ++li) {
+    Device& dev = c->devs[(size_t)m->dev_idx[li]];
+    KK_CUDA(cudaSetDevice(dev.ordinal));
+    KK_CUDA(cudaStreamSynchronize(dev.stream));
+    float ms = 0.f;
+    KK_CUDA(cudaEventElapsedTime(&ms, e0[li], e1[li]));
+    if (ms > worst) worst = ms;
+    cudaEventDestroy(e0[li]);
+    cudaEventDestroy(e1[li]);
+  }
+  if (ms_total) *ms_total = worst;
+}
+
 void free_resident(kk_model* m) {
   for (size_t li = 0; li < m->resident.size(); ++li) {
     auto& R = m->resident[li];
@@ -257,6 +440,13 @@ void free_resident(kk_model* m) {
 void destroy_model(kk_model* m) {
   kk_ctx* c = m->ctx;
   free_resident(m);
+  for (int r = 0; r < KK_MAX_DEVICES; ++r)
+    if (m->peer_raw_ptr[r]) {
+      cudaSetDevice(c->devs[(size_t)m->dev_idx[0]].ordinal);
+      cudaIpcCloseMemHandle(m->peer_raw_ptr[r]);
+      m->peer_raw_ptr[r] = nullptr;
+    }
+  free_raw(m);
   for (int r = 0; r < KK_MAX_DEVICES; ++r)
     if (m->peer_ptr[r]) {
       cudaSetDevice(c->devs[(size_t)m->dev_idx[0]].ordinal);
@@ -401,7 +591,9 @@ static void do_load(kk_model* m) {
   auto per_dev = [&](int li) {
     try {
       const double a = now_s();
-      if (replicas) {
+      if (is_raw(m)) {
+        run_part_raw(m, li, m->local_parts[(size_t)li], fds, true);
+      } else if (replicas) {
         for (int p = 0; p < m->plan.n_parts; ++p) run_part(m, li, p, fds);
       } else {
         run_part(m, li, m->local_parts[(size_t)li], fds);
@@ -416,6 +608,13 @@ static void do_load(kk_model* m) {
   per_dev(0);
   for (auto& t : th) t.join();
   sink.rethrow();
+  if (is_raw(m)) {
+    m->raw_staged = true;
+    if (!multi_proc) {  // one process owns every device: all stage-1 work is done, convert now
+      convert_local_all(m, nullptr);
+      m->raw_staged = false;
+    }
+  }
   m->t_load = now_s() - t0;
   m->n_loads++;
 }
@@ -427,8 +626,9 @@ kk_model* model_load(kk_ctx* c, const std::string& path, const kk_load_opts& opt
     fail(KK_EINVAL, "part %d of %d out of range", opts.part_index, opts.part_count);
   if (opts.mode < KK_MODE_SINGLE || opts.mode > KK_MODE_SCATTER) fail(KK_EINVAL, "unknown mode %d", opts.mode);
   if (opts.fanout < KK_FANOUT_P2P || opts.fanout > KK_FANOUT_RAW) fail(KK_EINVAL, "unknown fanout %d", opts.fanout);
-  if (opts.fanout == KK_FANOUT_NVLS || opts.fanout == KK_FANOUT_RAW)
-    fail(KK_EUNSUPPORTED, "fan-out %s is not available in this build", opts.fanout == KK_FANOUT_NVLS ? "NVLS" : "RAW");
+  if (opts.fanout == KK_FANOUT_NVLS)
+    fail(KK_EUNSUPPORTED, "fan-out NVLS is not available in this build (an all-gather is ingress-bound either way; see DESIGN.md)");
+  if (opts.fanout == KK_FANOUT_RAW && opts.mode != KK_MODE_BROADCAST) fail(KK_EINVAL, "KK_FANOUT_RAW only applies to KK_MODE_BROADCAST");
   const bool multi_proc = opts.part_count > 1;
   if (multi_proc && c->cfg.n_devices != 1) fail(KK_EINVAL, "multi-process parts need a one-device context (got %d devices)", c->cfg.n_devices);
   if (multi_proc && opts.mode == KK_MODE_SINGLE) fail(KK_EINVAL, "KK_MODE_SINGLE cannot be split into parts");
@@ -504,10 +704,12 @@ kk_model* model_load(kk_ctx* c, const std::string& path, const kk_load_opts& opt
         KK_CUDA(cudaMemcpy(m->d_segs[li], all.data(), all.size() * sizeof(KKSeg), cudaMemcpyHostToDevice));
       }
     }
+    if (is_raw(m)) setup_raw(m);
     m->t_alloc = now_s() - t0;
     if (!(opts.flags & KK_LOAD_DEFER)) {
       do_load(m);
-      m->loaded = true;
+      m->loaded = !(is_raw(m) && multi_proc);
+      if (is_raw(m) && !multi_proc) free_raw(m);  // the gathered file bytes are not needed once the pools are built
     }
   } catch (...) {
     {
@@ -527,9 +729,40 @@ kk_model* model_load(kk_ctx* c, const std::string& path, const kk_load_opts& opt
 }
 
 void model_load_part(kk_model* m) {
+  if (is_raw(m) && m->raw.empty()) fail(KK_ESTATE, "the raw image of this model has been released");
   do_load(m);
   std::lock_guard<std::mutex> g(m->ctx->mu);
+  if (!(is_raw(m) && m->opts.part_count > 1)) m->loaded = true;  // multi-process RAW: loaded after kk_convert_local
+}
+
+void model_convert_local(kk_model* m, float* ms_total) {
+  if (!is_raw(m) || m->raw.empty()) fail(KK_ESTATE, "kk_convert_local only applies to KK_FANOUT_RAW models with a live raw image");
+  convert_local_all(m, ms_total);
+  std::lock_guard<std::mutex> g(m->ctx->mu);
   m->loaded = true;
+  m->raw_staged = false;
+}
+
+void model_export_raw(kk_model* m, int li, void* handle_out) {
+  if (!is_raw(m) || m->raw.empty()) fail(KK_ESTATE, "this model has no raw image");
+  KK_CUDA(cudaSetDevice(m->ctx->devs[(size_t)m->dev_idx[(size_t)li]].ordinal));
+  cudaIpcMemHandle_t h;
+  KK_CUDA(cudaIpcGetMemHandle(&h, m->raw[(size_t)li].image));
+  memcpy(handle_out, &h, sizeof h);
+}
+
+void model_peer_attach_raw(kk_model* m, int rank, const void* handle) {
+  if (!is_raw(m)) fail(KK_ESTATE, "raw peer attach needs a KK_FANOUT_RAW model");
+  if (m->opts.part_count <= 1) fail(KK_ESTATE, "peer attach needs a multi-process (part_count > 1) model");
+  if (rank < 0 || rank >= m->opts.part_count || rank == m->opts.part_index) fail(KK_EINVAL, "bad peer rank %d", rank);
+  if (m->peer_raw_ptr[rank]) fail(KK_ESTATE, "peer rank %d already attached", rank);
+  Device& d = m->ctx->devs[(size_t)m->dev_idx[0]];
+  KK_CUDA(cudaSetDevice(d.ordinal));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  void* p = nullptr;
+  KK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  m->peer_raw_ptr[rank] = p;
 }
 
 void model_release(kk_model* m) {
@@ -560,11 +793,16 @@ void model_peer_attach(kk_model* m, int rank, const void* handle) {
 void model_peer_detach_all(kk_model* m) {
   Device& d = m->ctx->devs[(size_t)m->dev_idx[0]];
   cudaSetDevice(d.ordinal);
-  for (int r = 0; r < KK_MAX_DEVICES; ++r)
+  for (int r = 0; r < KK_MAX_DEVICES; ++r) {
     if (m->peer_ptr[r]) {
       cudaIpcCloseMemHandle(m->peer_ptr[r]);
       m->peer_ptr[r] = nullptr;
     }
+    if (m->peer_raw_ptr[r]) {
+      cudaIpcCloseMemHandle(m->peer_raw_ptr[r]);
+      m->peer_raw_ptr[r] = nullptr;
+    }
+  }
 }
 
 int model_local_device(kk_model* m, int ordinal) {
@@ -640,6 +878,12 @@ std::string model_stats(kk_model* m) {
 // resident image: kernel-stage measurement with the source bytes already in HBM
 // ---------------------------------------------------------------------------------------------
 void model_stage_resident(kk_model* m) {
+  if (is_raw(m)) {  // RAW: the resident image IS the raw image; stage this process's own part(s), no fan-out
+    if (m->raw.empty()) fail(KK_ESTATE, "the raw image of this model has been released");
+    FdSet fds(m->plan.index.shards);
+    for (size_t li = 0; li < m->dev_idx.size(); ++li) run_part_raw(m, (int)li, m->local_parts[li], fds, false);
+    return;
+  }
   free_resident(m);
   kk_ctx* c = m->ctx;
   FdSet fds(m->plan.index.shards, m->plan.mode == KK_MODE_SCATTER);
@@ -698,9 +942,80 @@ void model_stage_resident(kk_model* m) {
   }
 }
 
-void model_unstage_resident(kk_model* m) { free_resident(m); }
+void model_unstage_resident(kk_model* m) {
+  if (is_raw(m)) return;  // the raw image lives as long as a deferred RAW model does
+  free_resident(m);
+}
+
+// RAW: time the stage-1 fan-out only (own part of the image -> every peer image), one launch per local device.
+static void raw_fanout_resident(kk_model* m, float* ms_total, float* ms_per_launch, size_t cap, size_t* n_launches) {
+  kk_ctx* c = m->ctx;
+  const size_t nl = m->dev_idx.size();
+  std::vector<cudaEvent_t> e0(nl), e1(nl);
+  size_t launched = 0;
+  for (size_t li = 0; li < nl; ++li) {
+    Device& dev = c->devs[(size_t)m->dev_idx[li]];
+    KK_CUDA(cudaSetDevice(dev.ordinal));
+    KK_CUDA(cudaEventCreate(&e0[li]));
+    KK_CUDA(cudaEventCreate(&e1[li]));
+    ConvertLaunch L{};
+    fill_raw_dsts(m, (int)li, L);
+    const int part = m->local_parts[li];
+    const PartPlan& pp = m->plan.parts[(size_t)part];
+    KK_CUDA(cudaEventRecord(e0[li], dev.stream));
+    if (L.n_dst > 0 && !pp.chunks.empty()) {
+      // one launch over all of this part's chunks (their COPY segments are consecutive in d_copy_segs)
+      std::vector<KKSeg> segs(pp.chunks.size());
+      uint32_t tiles = 0;
+      for (size_t ci = 0; ci < pp.chunks.size(); ++ci) {
+        KKSeg sg{};
+        sg.src_off = sg.dst_off = m->img_off[(size_t)part][ci];
+        sg.units = align_up(pp.chunks[ci].buf_bytes, 16);
+        sg.op = KK_OP_COPY;
+        sg.tile_begin = tiles;
+        tiles += (uint32_t)kk_seg_tiles(KK_OP_COPY, sg.units, 0);
+        segs[ci] = sg;
+      }
+      if (segs.size() > kMaxSegsPerLaunch) fail(KK_EUNSUPPORTED, "too many chunks for one raw fan-out launch");
+      KKSeg* d_tmp = nullptr;
+      KK_CUDA(cudaMalloc((void**)&d_tmp, segs.size() * sizeof(KKSeg)));
+      KK_CUDA(cudaMemcpyAsync(d_tmp, segs.data(), segs.size() * sizeof(KKSeg), cudaMemcpyHostToDevice, dev.stream));
+      KK_CUDA(cudaEventRecord(e0[li], dev.stream));
+      L.src = m->raw[li].image;
+      L.segs = d_tmp;
+      L.n_segs = (uint32_t)segs.size();
+      L.n_tiles = tiles;
+      KK_CUDA(launch_convert(L, dev.sm_count, dev.stream));
+      KK_CUDA(cudaEventRecord(e1[li], dev.stream));
+      KK_CUDA(cudaStreamSynchronize(dev.stream));
+      cudaFree(d_tmp);
+      launched = 1;
+    } else {
+      KK_CUDA(cudaEventRecord(e1[li], dev.stream));
+    }
+  }
+  float worst = 0.f;
+  for (size_t li = 0; li < nl; ++li) {
+    Device& dev = c->devs[(size_t)m->dev_idx[li]];
+    KK_CUDA(cudaSetDevice(dev.ordinal));
+    KK_CUDA(cudaStreamSynchronize(dev.stream));
+    float ms = 0.f;
+    KK_CUDA(cudaEventElapsedTime(&ms, e0[li], e1[li]));
+    if (ms > worst) worst = ms;
+    cudaEventDestroy(e0[li]);
+    cudaEventDestroy(e1[li]);
+  }
+  if (ms_total) *ms_total = worst;
+  if (n_launches) *n_launches = launched;
+  if (ms_per_launch && cap && launched) ms_per_launch[0] = worst;
+}
 
 void model_convert_resident(kk_model* m, float* ms_total, float* ms_per_launch, size_t cap, size_t* n_launches) {
+  if (is_raw(m)) {
+    if (m->raw.empty()) fail(KK_ESTATE, "the raw image of this model has been released");
+    raw_fanout_resident(m, ms_total, ms_per_launch, cap, n_launches);
+    return;
+  }
   if (m->resident.size() != m->dev_idx.size()) fail(KK_ESTATE, "kk_stage_resident has not been called");
   kk_ctx* c = m->ctx;
   const size_t nl = m->dev_idx.size();

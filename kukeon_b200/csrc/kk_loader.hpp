@@ -79,6 +79,20 @@ struct kk_model {
     std::vector<Launch> launches;
   };
   std::vector<Resident> resident;  // per local device
+  // KK_FANOUT_RAW: the file bytes of every part are all-gathered into a per-device raw image (stage 1, fan-out of
+  // the *quantised* bytes), then every device converts the whole image into its own pool (stage 2).
+  struct Raw {
+    uint8_t* image = nullptr;
+    uint64_t bytes = 0;
+    KKSeg* d_copy_segs = nullptr;  // one COPY segment per chunk of every part: [chunk_base[part] + ci]
+    KKSeg* d_conv_segs = nullptr;  // every part's segments rebased onto the image
+    std::vector<Resident::Launch> conv_launches;
+  };
+  std::vector<Raw> raw;                         // per local device (empty unless fanout == RAW)
+  std::vector<std::vector<uint64_t>> img_off;   // [part][chunk] offset of the chunk buffer inside the raw image
+  std::vector<uint32_t> chunk_base;             // prefix sum of chunk counts per part
+  void* peer_raw_ptr[KK_MAX_DEVICES] = {};      // IPC-opened raw images of the other ranks
+  bool raw_staged = false;                      // stage 1 complete on this process since the last conversion
   // state
   int refcount = 0;
   bool loading = true;
@@ -100,6 +114,9 @@ kk_model* model_load(kk_ctx* c, const std::string& path, const kk_load_opts& opt
 void model_load_part(kk_model* m);
 void model_release(kk_model* m);
 void model_peer_attach(kk_model* m, int rank, const void* handle);
+void model_peer_attach_raw(kk_model* m, int rank, const void* handle);
+void model_export_raw(kk_model* m, int local, void* handle_out);
+void model_convert_local(kk_model* m, float* ms_total);
 void model_peer_detach_all(kk_model* m);
 int model_local_device(kk_model* m, int ordinal);  // index into m->dev_idx or throws
 std::string model_manifest(kk_model* m, int local);

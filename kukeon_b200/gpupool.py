@@ -24,6 +24,7 @@ MODE_SINGLE, MODE_BROADCAST, MODE_SCATTER = 0, 1, 2
 FANOUT_P2P, FANOUT_NVLS, FANOUT_NONE, FANOUT_RAW = 0, 1, 2, 3
 CFG_ZEROCOPY, CFG_NO_PEER_ACCESS, CFG_NO_NUMA_PIN = 0x1, 0x2, 0x4
 LOAD_GPT2_CONV1D_T, LOAD_KEEP_F32, LOAD_DEFER = 0x1, 0x2, 0x4
+BUF_POOL, BUF_RAW = 0, 1
 
 DTYPE_NAMES = {
     0: "BOOL", 1: "F4", 2: "F6_E2M3", 3: "F6_E3M2", 4: "U8", 5: "I8", 6: "F8_E5M2", 7: "F8_E4M3", 8: "F8_E8M0",
@@ -97,6 +98,7 @@ _lib = None
 ABI_SYMBOLS = [
     "kk_abi_version", "kk_last_error", "kk_status_name", "kk_open", "kk_close", "kk_index", "kk_free_index",
     "kk_index_shard", "kk_plan_describe", "kk_load", "kk_load_ex", "kk_load_part", "kk_peer_attach", "kk_peer_detach_all",
+    "kk_export_buffer", "kk_peer_attach_buffer", "kk_convert_local",
     "kk_model_get_info", "kk_placements", "kk_model_tensor", "kk_export", "kk_export_size", "kk_pool_ptr",
     "kk_acquire", "kk_release", "kk_stats", "kk_read", "kk_checksum", "kk_stage_resident", "kk_convert_resident",
     "kk_unstage_resident",
@@ -134,6 +136,9 @@ def lib():
     L.kk_load_part.argtypes = [vp]
     L.kk_peer_attach.argtypes = [vp, C.c_int, C.c_void_p]
     L.kk_peer_detach_all.argtypes = [vp]
+    L.kk_export_buffer.argtypes = [vp, C.c_int, C.c_int, C.c_void_p]
+    L.kk_peer_attach_buffer.argtypes = [vp, C.c_int, C.c_int, C.c_void_p]
+    L.kk_convert_local.argtypes = [vp, C.POINTER(C.c_float)]
     L.kk_model_get_info.argtypes = [vp, C.POINTER(KKModelInfo)]
     L.kk_placements.argtypes = [vp, C.c_char_p, C.POINTER(KKPlacement), C.c_size_t, C.POINTER(C.c_size_t)]
     L.kk_model_tensor.argtypes = [vp, C.c_size_t, C.POINTER(KKTensorMeta)]
@@ -284,6 +289,22 @@ class Model:
     def peer_attach(self, rank: int, ipc_handle: bytes) -> None:
         assert len(ipc_handle) == KK_IPC_HANDLE_BYTES
         _check(lib().kk_peer_attach(self._h, rank, C.c_char_p(ipc_handle)))
+
+    def export_buffer(self, device: int, which: int) -> bytes:
+        """IPC handle of the pool (BUF_POOL) or of the raw image of a KK_FANOUT_RAW model (BUF_RAW)."""
+        h = C.create_string_buffer(KK_IPC_HANDLE_BYTES)
+        _check(lib().kk_export_buffer(self._h, device, which, h))
+        return h.raw
+
+    def peer_attach_buffer(self, rank: int, which: int, ipc_handle: bytes) -> None:
+        assert len(ipc_handle) == KK_IPC_HANDLE_BYTES
+        _check(lib().kk_peer_attach_buffer(self._h, rank, which, C.c_char_p(ipc_handle)))
+
+    def convert_local(self) -> float:
+        """Stage 2 of a multi-process KK_FANOUT_RAW load; returns its CUDA-event milliseconds."""
+        ms = C.c_float()
+        _check(lib().kk_convert_local(self._h, C.byref(ms)))
+        return float(ms.value)
 
     def peer_detach_all(self) -> None:
         _check(lib().kk_peer_detach_all(self._h))

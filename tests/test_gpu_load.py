@@ -438,3 +438,29 @@ def test_multi_destination_store_paths_on_one_gpu(native, tmp_path, ndst):
     r = subprocess.run([sys.executable, "-c", _NDST_CHILD, root, f"{d}:0", f"{mixed}:0", f"{g}:0", f"{f}:1", f"{f}:3", f"{f2}:1", f"{f3}:1", f"{f3}:3"],
                        capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-3000:]
+
+
+def test_raw_fanout_degenerates_on_one_gpu(pool, tmp_path):
+    """KK_FANOUT_RAW = gather the file bytes into a raw image, then convert locally.  On one GPU there is nobody to
+    gather from, but both stages (H2D into the image, convert from the image) still run and must match the oracle."""
+    g = str(tmp_path / "mix.gguf")
+    synth.write_gguf(g, synth.mixtral_gguf_tensors(hidden=256, ffn=768, layers=2, experts=2, vocab=512, kv_dim=256), 7)
+    load_and_check(pool, g, mode=gpupool.MODE_BROADCAST, fanout=gpupool.FANOUT_RAW)
+    p = str(tmp_path / "m.safetensors")
+    helpers.mixed_safetensors(p)
+    load_and_check(pool, p, mode=gpupool.MODE_BROADCAST, fanout=gpupool.FANOUT_RAW)
+    with pytest.raises(gpupool.ErrInvalid):
+        pool.load(p, mode=gpupool.MODE_SINGLE, fanout=gpupool.FANOUT_RAW)
+    # deferred flavour (what bench.py drives): stage 1, then kk_convert_local
+    shards, recs = oracle.index_path(g)
+    m = pool.load(g, mode=gpupool.MODE_BROADCAST, fanout=gpupool.FANOUT_RAW, flags=gpupool.LOAD_DEFER)
+    try:
+        m.load_part()
+        m.convert_local()
+        assert_pool_matches(m, 0, shards, recs)
+        m.stage_resident()
+        tot, per = m.convert_resident()  # no peers: nothing to fan out
+        assert per == [] and m.convert_local() > 0
+        assert_pool_matches(m, 0, shards, recs)
+    finally:
+        m.release()

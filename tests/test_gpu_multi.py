@@ -63,6 +63,22 @@ def test_single_process_broadcast_fused_p2p(native, tmp_path):
 
 
 @needs2
+def test_single_process_raw_fanout(native, tmp_path):
+    """Variant (ii) of SURVEY.md §8(d) config 4: all-gather the quantised file bytes, dequantise on every GPU."""
+    n = min(_ngpu(), 8)
+    d, g, f = make_mixed(tmp_path)
+    with gpupool.Pool(list(range(n)), n_staging_buffers=4, staging_buffer_bytes=1 * MB, n_reader_threads=2) as pl:
+        for path in (g, d):
+            shards, recs = oracle.index_path(path)
+            m = pl.load(path, mode=gpupool.MODE_BROADCAST, fanout=gpupool.FANOUT_RAW)
+            try:
+                for dev in range(n):
+                    check_pool(m, dev, shards, recs)
+            finally:
+                m.release()
+
+
+@needs2
 def test_single_process_broadcast_without_fanout_is_replicas(native, tmp_path):
     d, _, _ = make_mixed(tmp_path)
     shards, recs = oracle.index_path(d)
@@ -140,6 +156,31 @@ def _rank_main(rank, world, port, paths, out_dir):
                     m.peer_detach_all()
                 finally:
                     m.release()
+            # RAW fan-out across processes: exchange the raw-image handles, stage 1, barrier, stage 2
+            path = paths[1][0]
+            shards, recs = orc.index_path(path)
+            m = pl.load(path, mode=gp.MODE_BROADCAST, fanout=gp.FANOUT_RAW, flags=gp.LOAD_DEFER, part_index=rank, part_count=world)
+            try:
+                hs = [None] * world
+                dist.all_gather_object(hs, m.export_buffer(rank, gp.BUF_RAW))
+                for r, hh in enumerate(hs):
+                    if r != rank:
+                        m.peer_attach_buffer(r, gp.BUF_RAW, hh)
+                dist.barrier()
+                m.load_part()
+                assert not m.info()["loaded"]
+                dist.barrier()
+                m.convert_local()
+                assert m.info()["loaded"]
+                exp, plan = orc.expected_pool(shards, recs, 1, 0)
+                got = m.read(rank, 0, len(exp))
+                for p in plan:
+                    a, b = p["pool_offset"], p["pool_offset"] + p["nbytes"]
+                    assert np.array_equal(got[a:b], exp[a:b]), f"rank {rank} RAW: {p['name']} differs"
+                dist.barrier()
+                m.peer_detach_all()
+            finally:
+                m.release()
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
