@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--kernel-only", action="store_true", help="profiling aid: skip the streaming load / e2e legs (every kk_convert launch is a resident one)")
     ap.add_argument("--e2e-only", action="store_true", help="tuning aid: skip the resident kernel leg")
     ap.add_argument("--no-numa-pin", action="store_true")
+    ap.add_argument("--lazy-peers", action="store_true", help="leave peer-access setup to the first kk_peer_attach (A/B for time-to-ready)")
     ap.add_argument("--fanout", default="p2p", choices=["p2p", "raw"], help="broadcast order: fused convert+fan-out (p2p) or all-gather the file bytes then convert locally (raw)")
     return ap.parse_args()
 
@@ -169,7 +170,7 @@ def cpu_port_setup(path: str, sample_bytes: int):
     plan, total = oracle.plan_pool(recs)
     jobs, src = coracle.make_jobs(recs, plan, job_bytes=8 << 20, max_src_bytes=sample_bytes)
     out_of = {coracle.OP_COPY: lambda n: n, coracle.OP_F32_BF16: lambda n: n // 2, coracle.OP_F16_BF16: lambda n: n,
-              coracle.OP_Q4K_BF16: lambda n: n // 144 * 512}
+              coracle.OP_Q4K_BF16: lambda n: n // 144 * 512, coracle.OP_Q8_0_BF16: lambda n: n // 34 * 64, coracle.OP_Q6K_BF16: lambda n: n // 210 * 512}
     hi = max((j.dst_off + out_of[j.op](j.nbytes) for j in jobs), default=0)
     pool = np.empty(min(total, hi) + 4096, np.uint8)
     pool[::4096] = 0  # first touch outside the timed region
@@ -294,6 +295,8 @@ def main():
 
     mode = gpupool.MODE_SINGLE if world == 1 else (gpupool.MODE_SCATTER if spec["mode"] == "scatter" else gpupool.MODE_BROADCAST)
     flags = (gpupool.CFG_ZEROCOPY if args.zerocopy else 0) | (gpupool.CFG_NO_NUMA_PIN if args.no_numa_pin else 0)
+    if world > 1 and not args.lazy_peers:
+        flags |= gpupool.CFG_PEER_ALL  # daemon-lifetime work (kk_open), not part of a model's time-to-ready
     t0 = time.time()
     pool = gpupool.Pool([local], n_staging_buffers=args.slots, staging_buffer_bytes=args.slot_mb << 20, n_reader_threads=args.readers, flags=flags)
     t_open = time.time() - t0
@@ -306,13 +309,13 @@ def main():
     brk["pull_s"] = time.time() - t_ready0
     lflags = gpupool.LOAD_DEFER | (gpupool.LOAD_GPT2_CONV1D_T if spec["kind"] == "gpt2" else 0)
     t1 = time.time()
-    raw = args.fanout == "raw" and world > 1 and mode == gpupool.MODE_BROADCAST
-    m = modelhub.Load(pool, ref, mode=mode, fanout=gpupool.FANOUT_RAW if raw else gpupool.FANOUT_P2P, flags=lflags,
+    raw_order = args.fanout == "raw" and world > 1 and mode == gpupool.MODE_BROADCAST
+    m = modelhub.Load(pool, ref, mode=mode, fanout=gpupool.FANOUT_RAW if raw_order else gpupool.FANOUT_P2P, flags=lflags,
                       part_index=rank if world > 1 else 0, part_count=world if world > 1 else 0)
     brk["plan_alloc_s"] = time.time() - t1
     t1 = time.time()
     if world > 1 and mode == gpupool.MODE_BROADCAST:
-        which = gpupool.BUF_RAW if raw else gpupool.BUF_POOL
+        which = gpupool.BUF_RAW if raw_order else gpupool.BUF_POOL
         h = m.export_buffer(local, which)
         hs = [None] * world
         dist.all_gather_object(hs, h, group=gloo)
@@ -332,7 +335,7 @@ def main():
         brk["barrier_s"] = time.time() - t1
         t1 = time.time()
         m.load_part()
-        if raw:
+        if raw_order:
             barrier()
             m.convert_local()
         brk["load_part_s"] = time.time() - t1
@@ -390,7 +393,7 @@ def main():
         barrier()
         t = time.perf_counter()
         m.load_part()
-        if raw:
+        if raw_order:
             barrier()
             m.convert_local()
         m.export(local)
@@ -434,7 +437,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         barrier()
         m.convert_resident()
-        if raw:
+        if raw_order:
             barrier()
             m.convert_local()
     clocks = ClockSampler(local)
@@ -449,7 +452,7 @@ def main():
     for _ in range(args.steps):
         barrier()
         tot, per = m.convert_resident()
-        if raw:  # stage 1 (fan-out of the file bytes) was just timed; stage 2 after every rank's stage 1 has landed
+        if raw_order:  # stage 1 (fan-out of the file bytes) was just timed; stage 2 after every rank's stage 1 has landed
             barrier()
             t2 = m.convert_local()
             raw_ms.append((tot, t2))
@@ -474,7 +477,7 @@ def main():
     avg_launch_ms = sum(sum(p) for p in launch_ms) / (len(launch_ms) * max(n_launch, 1))
     # algorithmic HBM bytes of this rank per launch: source read once + pool writes landing in THIS GPU's HBM
     alg_per_step = local_src + part["out_bytes"] * (1 if mode == gpupool.MODE_SCATTER else world) if mode != gpupool.MODE_SINGLE else local_src + part["out_bytes"]
-    if raw:  # stage 1: read own part + incoming peers' parts written; stage 2: read the whole image + write the whole pool
+    if raw_order:  # stage 1: read own part + incoming peers' parts written; stage 2: read the whole image + write the whole pool
         alg_per_step = local_src + (file_bytes - local_src) + file_bytes + pool_bytes
     alg_per_launch = alg_per_step / max(n_launch, 1)
     achieved = alg_per_launch / (avg_launch_ms / 1e3) / 1e9 if avg_launch_ms > 0 else 0.0
@@ -534,7 +537,7 @@ def main():
         "setup": {"synth_s": t_gen, "kk_open_s": t_open, "index_s": st0["index_s"], "plan_s": st0["plan_s"], "alloc_s": st0["alloc_s"],
                   "first_load_s": st0["load_s"], "chunks_per_load": chunks_per_load, "h2d_probe_GBps": h2d_probe},
     }
-    if raw:
+    if raw_order:
         line["config"]["mode"] = "broadcast, RAW order: all-gather file bytes over NVLink (stage 1) + local convert (stage 2)"
         line["raw_stages_ms_rank0"] = {"fanout_ms": sum(a for a, _ in raw_ms) / len(raw_ms), "convert_ms": sum(b for _, b in raw_ms) / len(raw_ms)}
         if nvlink:

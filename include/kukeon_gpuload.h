@@ -91,6 +91,8 @@ typedef enum kk_fanout {
 /* kk_config.flags */
 #define KK_CFG_ZEROCOPY 0x1u     /* convert kernels read the pinned host ring directly (no H2D copy engine hop) */
 #define KK_CFG_NO_PEER_ACCESS 0x2u /* do not enable peer access between devices (forces replicas) */
+#define KK_CFG_PEER_ALL 0x8u       /* kk_open enables peer access from the context's devices to EVERY visible GPU (one-rank-
+                                      per-GPU deployments: moves the one-time peer setup out of the first kk_peer_attach) */
 #define KK_CFG_NO_NUMA_PIN 0x4u    /* do not bind reader threads / pinned slots to the device's NUMA node */
 
 /* kk_load_opts.flags */

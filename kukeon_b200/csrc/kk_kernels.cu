@@ -335,6 +335,70 @@ __device__ __forceinline__ void consume_q4k(const Dsts& D, uint32_t pay, uint32_
   }
 }
 
+// Blocks of 34 and 210 bytes are only 2-byte aligned inside a tile: assemble words from 16-bit shared loads.
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32_h(uint32_t a) {  // a is 2-byte aligned (falls back to bytes otherwise)
+  if (a & 1u) return lds32_bytes(a);
+  return lds16(a) | (lds16(a + 2) << 16);
+}
+__device__ __forceinline__ uint32_t lds16_any(uint32_t a) { return (a & 1u) ? (lds8(a) | (lds8(a + 1) << 8)) : lds16(a); }
+
+// Q8_0 block (34 B): d f16 | qs[32] int8 -> 32 bf16, y = q * d in fp32 (gguf/quants.py Q8_0.dequantize_blocks).
+// Lane l of a warp handles elements 8*(l&3)..+8 of block (l>>2): 8 blocks and 512 contiguous output bytes per iteration.
+__device__ __forceinline__ void consume_q8_0(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
+  for (uint32_t b0 = (uint32_t)cwarp * 8u; b0 < nblk; b0 += kConsumerWarps * 8u) {
+    const uint32_t b = b0 + (uint32_t)(lane >> 2);
+    if (b < nblk) {
+      const uint32_t blk = pay + b * KK_Q8_0_BLOCK_BYTES;
+      const float d = __half2float(__ushort_as_half((unsigned short)lds16_any(blk)));
+      const uint32_t qa = blk + 2u + 8u * (uint32_t)(lane & 3);
+      const uint32_t q0 = lds32_h(qa), q1 = lds32_h(qa + 4);
+      float y[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int q = (int)(signed char)(((e < 4 ? q0 : q1) >> (8 * (e & 3))) & 0xFFu);
+        y[e] = __fmul_rn((float)q, d);
+      }
+      store16_all(D, dst_off + (uint64_t)b * 64u + (uint32_t)(lane & 3) * 16u,
+                  make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7])));
+    }
+  }
+}
+
+// Q6_K super-block (210 B): ql[128] | qh[64] | scales[16] int8 | d f16 -> 256 bf16 (gguf/quants.py:552-572):
+// element e = 32*g + i (g = 0..7): low nibble source ql[64*(g/4) + 32*(g%2) + i] >> 4*((g%4)/2), high 2 bits
+// qh[32*(g/4) + i] >> 2*(g%4); q = (lo | hi<<4) - 32; y = (d * scales[e/16]) * q, both products rounded to fp32.
+// Lane l handles the 8 elements e = 8l..8l+7 (g = l>>2, i = 8*(l&3)..+8): one block, 512 output bytes per warp iteration.
+__device__ __forceinline__ void consume_q6k(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
+  const int g = lane >> 2, i0 = 8 * (lane & 3);
+  const uint32_t ql_off = 64u * (uint32_t)(g >> 2) + 32u * (uint32_t)(g & 1) + (uint32_t)i0;
+  const uint32_t qh_off = 128u + 32u * (uint32_t)(g >> 2) + (uint32_t)i0;
+  const int lsh = 4 * ((g & 3) >> 1), hsh = 2 * (g & 3);
+  for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
+    const uint32_t blk = pay + b * KK_Q6K_BLOCK_BYTES;
+    const float d = __half2float(__ushort_as_half((unsigned short)lds16_any(blk + 208u)));
+    const int sc = (int)(signed char)lds8(blk + 192u + (uint32_t)(lane >> 1));
+    const float dsc = __fmul_rn(d, (float)sc);
+    const uint32_t l0 = lds32_h(blk + ql_off), l1 = lds32_h(blk + ql_off + 4);
+    const uint32_t h0 = lds32_h(blk + qh_off), h1 = lds32_h(blk + qh_off + 4);
+    float y[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const uint32_t lw = e < 4 ? l0 : l1, hw = e < 4 ? h0 : h1;
+      const uint32_t lo = (lw >> (8 * (e & 3) + lsh)) & 0xFu;
+      const uint32_t hi = (hw >> (8 * (e & 3) + hsh)) & 0x3u;
+      const int q = (int)(lo | (hi << 4)) - 32;
+      y[e] = __fmul_rn(dsc, (float)q);
+    }
+    store16_all(D, dst_off + (uint64_t)b * 512u + (uint32_t)lane * 16u,
+                make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7])));
+  }
+}
+
 // 2-D transpose tile.  Source elements come either from the TMA-staged tile (t.bulk == 2: the producer pulled
 // the tile's rows into the stage with one cp.async.bulk per row, KK_T_COLS*ES + 16 bytes apart) or, when a row
 // is not 16-byte aligned, straight from global memory through a [col][row] scratch in the stage buffer.
@@ -483,6 +547,22 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
             d.dst_off = seg.dst_off + b * 512u;
             break;
           }
+          case KK_OP_Q8_0_BF16: {
+            const uint64_t b = (uint64_t)t * KK_Q8_0_TILE_BLOCKS;
+            const uint64_t rem = seg.units - b;
+            d.n_units = rem < KK_Q8_0_TILE_BLOCKS ? (uint32_t)rem : KK_Q8_0_TILE_BLOCKS;
+            in_bytes = d.n_units * KK_Q8_0_BLOCK_BYTES; in_off = seg.src_off + b * KK_Q8_0_BLOCK_BYTES;
+            d.dst_off = seg.dst_off + b * 64u;
+            break;
+          }
+          case KK_OP_Q6K_BF16: {
+            const uint64_t b = (uint64_t)t * KK_Q6K_TILE_BLOCKS;
+            const uint64_t rem = seg.units - b;
+            d.n_units = rem < KK_Q6K_TILE_BLOCKS ? (uint32_t)rem : KK_Q6K_TILE_BLOCKS;
+            in_bytes = d.n_units * KK_Q6K_BLOCK_BYTES; in_off = seg.src_off + b * KK_Q6K_BLOCK_BYTES;
+            d.dst_off = seg.dst_off + b * 512u;
+            break;
+          }
           default: {  // transposes
             const uint32_t C = seg.p0;
             const uint32_t ct = (C + KK_T_COLS - 1) / KK_T_COLS;
@@ -580,6 +660,8 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
         case KK_OP_F32_BF16: consume_f32(D, pay, t.n_units, t.dst_off, ctid); break;
         case KK_OP_F16_BF16: consume_f16(D, pay, t.n_units, t.dst_off, ctid); break;
         case KK_OP_Q4K_BF16: consume_q4k(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
+        case KK_OP_Q8_0_BF16: consume_q8_0(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
+        case KK_OP_Q6K_BF16: consume_q6k(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
         case KK_OP_T_F32_BF16: consume_transpose<4, 2, 1>(D, L.src, t, sbase, ctid); break;
         case KK_OP_T_F16_BF16: consume_transpose<2, 2, 2>(D, L.src, t, sbase, ctid); break;
         case KK_OP_T_B16: consume_transpose<2, 2, 0>(D, L.src, t, sbase, ctid); break;

@@ -533,6 +533,18 @@ kk_ctx* ctx_open(const kk_config& cfg_in) {
       alloc.join();
       if (alloc_err) std::rethrow_exception(alloc_err);
     }
+    if (cfg.flags & KK_CFG_PEER_ALL) {
+      for (int i = 0; i < cfg.n_devices; ++i) {
+        KK_CUDA(cudaSetDevice(cfg.devices[i]));
+        for (int j = 0; j < count; ++j) {
+          if (j == cfg.devices[i]) continue;
+          int can = 0;
+          if (cudaDeviceCanAccessPeer(&can, cfg.devices[i], j) != cudaSuccess || !can) { cudaGetLastError(); continue; }
+          cudaError_t pe = cudaDeviceEnablePeerAccess(j, 0);
+          if (pe != cudaSuccess) cudaGetLastError();  // already enabled or refused: kk_peer_attach will report a real failure
+        }
+      }
+    }
     c->peer_ok = cfg.n_devices > 1 && !(cfg.flags & KK_CFG_NO_PEER_ACCESS);
     if (c->peer_ok) {
       for (int i = 0; i < cfg.n_devices && c->peer_ok; ++i)
@@ -855,7 +867,8 @@ std::string model_stats(kk_model* m) {
       switch (s.op) {
         case KK_OP_COPY: e = b + s.units; break;
         case KK_OP_F32_BF16: case KK_OP_F16_BF16: e = b + s.units * 2; break;
-        case KK_OP_Q4K_BF16: e = b + s.units * 512; break;
+        case KK_OP_Q4K_BF16: case KK_OP_Q6K_BF16: e = b + s.units * 512; break;
+        case KK_OP_Q8_0_BF16: e = b + s.units * 64; break;
         case KK_OP_T_B32: e = b + (uint64_t)s.p0 * s.p1 * 4; break;
         default: e = b + (uint64_t)s.p0 * s.p1 * 2; break;
       }

@@ -9,6 +9,11 @@
 #define KK_Q4K_BLOCK_BYTES 144u
 #define KK_Q4K_BLOCK_ELEMS 256u
 #define KK_Q4K_TILE_BLOCKS 224u  /* 224*144 = 32256 B in, 224*512 = 114688 B out */
+#define KK_Q8_0_BLOCK_BYTES 34u
+#define KK_Q8_0_BLOCK_ELEMS 32u
+#define KK_Q8_0_TILE_BLOCKS 960u /* 960*34 = 32640 B in (a multiple of 16), 960*64 = 61440 B out */
+#define KK_Q6K_BLOCK_BYTES 210u
+#define KK_Q6K_TILE_BLOCKS 152u  /* 152*210 = 31920 B in (a multiple of 16), 152*512 = 77824 B out */
 #define KK_T_ROWS 32u            /* transpose tile: 32 source rows ... */
 #define KK_T_COLS 128u           /* ... x 128 source columns (elements) */
 #define KK_T_PITCH_PAD 16u       /* TMA-staged transpose rows sit KK_T_COLS*es + 16 bytes apart (bank spread) */
@@ -26,7 +31,9 @@ enum KKOp : uint32_t {
   KK_OP_T_F16_BF16 = 5,
   KK_OP_T_B16 = 6,     // 2-byte elements moved verbatim (bf16, i16, ...)
   KK_OP_T_B32 = 7,     // 4-byte elements moved verbatim
-  KK_OP_COUNT = 8
+  KK_OP_Q8_0_BF16 = 8, // units = 32-weight blocks (34 B: d f16 | 32 x int8)
+  KK_OP_Q6K_BF16 = 9,  // units = 256-weight super-blocks (210 B: ql[128] | qh[64] | scales[16] int8 | d f16)
+  KK_OP_COUNT = 10
 };
 
 struct KKSeg {
@@ -52,6 +59,8 @@ uint64_t kk_seg_tiles(uint32_t op, uint64_t units, uint32_t p0) {
     case KK_OP_F32_BF16: return (units + KK_TILE_SRC_BYTES / 4 - 1) / (KK_TILE_SRC_BYTES / 4);
     case KK_OP_F16_BF16: return (units + KK_TILE_SRC_BYTES / 2 - 1) / (KK_TILE_SRC_BYTES / 2);
     case KK_OP_Q4K_BF16: return (units + KK_Q4K_TILE_BLOCKS - 1) / KK_Q4K_TILE_BLOCKS;
+    case KK_OP_Q8_0_BF16: return (units + KK_Q8_0_TILE_BLOCKS - 1) / KK_Q8_0_TILE_BLOCKS;
+    case KK_OP_Q6K_BF16: return (units + KK_Q6K_TILE_BLOCKS - 1) / KK_Q6K_TILE_BLOCKS;
     case KK_OP_T_F32_BF16:
     case KK_OP_T_B32:
     case KK_OP_T_F16_BF16:

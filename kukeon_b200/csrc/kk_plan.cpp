@@ -35,12 +35,14 @@ OpInfo op_for(uint32_t dt, uint32_t flags, const std::string& name) {
       return {KK_OP_F32_BF16, KK_BF16, 4, 2, KK_TILE_SRC_BYTES / 4};
     case KK_F16: return {KK_OP_F16_BF16, KK_BF16, 2, 2, KK_TILE_SRC_BYTES / 2};
     case KK_Q4_K: return {KK_OP_Q4K_BF16, KK_BF16, KK_Q4K_BLOCK_BYTES, 512, KK_Q4K_TILE_BLOCKS};
+    case KK_Q8_0: return {KK_OP_Q8_0_BF16, KK_BF16, KK_Q8_0_BLOCK_BYTES, 64, KK_Q8_0_TILE_BLOCKS};
+    case KK_Q6_K: return {KK_OP_Q6K_BF16, KK_BF16, KK_Q6K_BLOCK_BYTES, 512, KK_Q6K_TILE_BLOCKS};
     default: break;
   }
   const DtypeInfo* di = dtype_info(dt);
   if (!di) fail(KK_EINVAL, "tensor %s: unknown dtype %u", name.c_str(), dt);
   if (di->block_elems > 1 && dt >= 32)
-    fail(KK_EUNSUPPORTED, "tensor %s: %s -> bf16 dequantisation is not implemented (only Q4_K)", name.c_str(), di->name);
+    fail(KK_EUNSUPPORTED, "tensor %s: %s -> bf16 dequantisation is not implemented (Q4_K, Q6_K and Q8_0 are)", name.c_str(), di->name);
   return {KK_OP_COPY, dt, 1, 1, KK_TILE_SRC_BYTES};  // integers, bool, fp8, f64, sub-byte: verbatim bytes
 }
 

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libkk_oracle.so")
 _lib = None
 
-OP_COPY, OP_F32_BF16, OP_F16_BF16, OP_Q4K_BF16 = 0, 1, 2, 3
+OP_COPY, OP_F32_BF16, OP_F16_BF16, OP_Q4K_BF16, OP_Q8_0_BF16, OP_Q6K_BF16 = 0, 1, 2, 3, 4, 5
 
 
 class OrcJob(C.Structure):
@@ -36,6 +36,8 @@ def lib():
         L.orc_f32_to_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.orc_f16_to_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.orc_q4k_to_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.orc_q8_0_to_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.orc_q6k_to_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.orc_checksum.argtypes = [C.c_void_p, C.c_uint64]
         L.orc_checksum.restype = C.c_uint64
         for fn in ("orc_fill_bytes", "orc_fill_bf16_finite", "orc_fill_f32", "orc_fill_q4k"):
@@ -76,6 +78,24 @@ def q4k_to_bf16(blocks: np.ndarray) -> np.ndarray:
     return out.reshape(n, 256)
 
 
+def q8_0_to_bf16(blocks: np.ndarray) -> np.ndarray:
+    src = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1)
+    assert src.size % 34 == 0
+    n = src.size // 34
+    out = np.empty(n * 32, np.uint16)
+    lib().orc_q8_0_to_bf16(_ptr(src), _ptr(out), n)
+    return out.reshape(n, 32)
+
+
+def q6k_to_bf16(blocks: np.ndarray) -> np.ndarray:
+    src = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1)
+    assert src.size % 210 == 0
+    n = src.size // 210
+    out = np.empty(n * 256, np.uint16)
+    lib().orc_q6k_to_bf16(_ptr(src), _ptr(out), n)
+    return out.reshape(n, 256)
+
+
 def checksum(a: np.ndarray) -> int:
     src = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
     return int(lib().orc_checksum(_ptr(src), src.size))
@@ -112,7 +132,7 @@ def fill_into(kind: str, dst: np.ndarray, seed: int) -> None:
         raise ValueError(kind)
 
 
-_OPS = {"BF16": OP_COPY, "F32": OP_F32_BF16, "F16": OP_F16_BF16, "Q4_K": OP_Q4K_BF16}
+_OPS = {"BF16": OP_COPY, "F32": OP_F32_BF16, "F16": OP_F16_BF16, "Q4_K": OP_Q4K_BF16, "Q8_0": OP_Q8_0_BF16, "Q6_K": OP_Q6K_BF16}
 
 
 def make_jobs(recs: Sequence[dict], plan: Sequence[dict], job_bytes: int = 8 << 20, max_src_bytes: int | None = None):
@@ -121,7 +141,8 @@ def make_jobs(recs: Sequence[dict], plan: Sequence[dict], job_bytes: int = 8 << 
     total = 0
     for r, p in zip(recs, plan):
         op = _OPS.get(r["dtype"], OP_COPY)
-        unit, out_unit = {OP_COPY: (256, 256), OP_F32_BF16: (4, 2), OP_F16_BF16: (2, 2), OP_Q4K_BF16: (144, 512)}[op]
+        unit, out_unit = {OP_COPY: (256, 256), OP_F32_BF16: (4, 2), OP_F16_BF16: (2, 2), OP_Q4K_BF16: (144, 512), OP_Q8_0_BF16: (34, 64),
+                          OP_Q6K_BF16: (210, 512)}[op]
         step = max(unit, job_bytes // unit * unit)
         off = 0
         while off < r["nbytes"]:

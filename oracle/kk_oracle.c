@@ -81,6 +81,41 @@ void orc_q4k_to_bf16(const uint8_t* blocks, uint16_t* dst, uint64_t nblocks) {
   for (uint64_t i = 0; i < nblocks; ++i) q4k_block(blocks + 144 * i, dst + 256 * i);
 }
 
+/* Q8_0 block (34 B): d f16 | 32 x int8; y = q * d (gguf/quants.py:395-401). */
+static void q8_0_block(const uint8_t* b, uint16_t* out) {
+  uint16_t hd;
+  memcpy(&hd, b, 2);
+  const float d = f16bits_to_f32(hd);
+  for (int i = 0; i < 32; ++i) out[i] = f32_to_bf16((float)(int8_t)b[2 + i] * d);
+}
+void orc_q8_0_to_bf16(const uint8_t* blocks, uint16_t* dst, uint64_t nblocks) {
+#pragma omp parallel for schedule(static)
+  for (uint64_t i = 0; i < nblocks; ++i) q8_0_block(blocks + 34 * i, dst + 32 * i);
+}
+
+/* Q6_K super-block (210 B): ql[128] | qh[64] | scales[16] int8 | d f16 (gguf/quants.py:552-572). */
+static void q6k_block(const uint8_t* b, uint16_t* out) {
+  const uint8_t* ql = b;
+  const uint8_t* qh = b + 128;
+  const int8_t* sc = (const int8_t*)(b + 192);
+  uint16_t hd;
+  memcpy(&hd, b + 208, 2);
+  const float d = f16bits_to_f32(hd);
+  for (int g = 0; g < 8; ++g)
+    for (int i = 0; i < 32; ++i) {
+      const int e = 32 * g + i;
+      const int lo = (ql[64 * (g / 4) + 32 * (g % 2) + i] >> (4 * ((g % 4) / 2))) & 0x0F;
+      const int hi = (qh[32 * (g / 4) + i] >> (2 * (g % 4))) & 0x03;
+      const int q = (lo | (hi << 4)) - 32;
+      volatile float dsc = d * (float)sc[e / 16];
+      out[e] = f32_to_bf16(dsc * (float)q);
+    }
+}
+void orc_q6k_to_bf16(const uint8_t* blocks, uint16_t* dst, uint64_t nblocks) {
+#pragma omp parallel for schedule(static)
+  for (uint64_t i = 0; i < nblocks; ++i) q6k_block(blocks + 210 * i, dst + 256 * i);
+}
+
 static inline uint64_t mix64(uint64_t x) {
   x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
   x ^= x >> 27; x *= 0x94d049bb133111ebull;
@@ -169,7 +204,7 @@ void orc_fill_q4k(uint8_t* dst, uint64_t nblocks, uint64_t seed) {
 }
 
 /* ---- CPU loader ("port" of the hot path for the cpu_baseline legs) ---------------------------- */
-enum { ORC_COPY = 0, ORC_F32_BF16 = 1, ORC_F16_BF16 = 2, ORC_Q4K_BF16 = 3 };
+enum { ORC_COPY = 0, ORC_F32_BF16 = 1, ORC_F16_BF16 = 2, ORC_Q4K_BF16 = 3, ORC_Q8_0_BF16 = 4, ORC_Q6K_BF16 = 5 };
 
 typedef struct {
   uint32_t shard;
@@ -226,6 +261,10 @@ int orc_cpu_load(const char* const* shard_paths, uint32_t n_shards, const orc_jo
           for (uint64_t i = 0; i < J->nbytes / 2; ++i) { uint16_t h; memcpy(&h, scratch + 2 * i, 2); out[i] = f32_to_bf16(f16bits_to_f32(h)); }
         } else if (J->op == ORC_Q4K_BF16) {
           for (uint64_t i = 0; i < J->nbytes / 144; ++i) q4k_block(scratch + 144 * i, out + 256 * i);
+        } else if (J->op == ORC_Q8_0_BF16) {
+          for (uint64_t i = 0; i < J->nbytes / 34; ++i) q8_0_block(scratch + 34 * i, out + 32 * i);
+        } else if (J->op == ORC_Q6K_BF16) {
+          for (uint64_t i = 0; i < J->nbytes / 210; ++i) q6k_block(scratch + 210 * i, out + 256 * i);
         } else err = -1;
       }
       free(scratch);

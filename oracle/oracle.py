@@ -12,7 +12,7 @@ the *published file formats*, pinned instead against the format owners' own libr
 image:
 
 * safetensors 0.7.0  — header layout, validation rules  (``tests/test_oracle_index.py``)
-* gguf 0.19.0        — GGUF v3 header, ``quants.Q4_K.dequantize_blocks`` (gguf/quants.py:475-521)
+* gguf 0.19.0        — GGUF v3 header, ``quants.Q4_K/Q6_K/Q8_0.dequantize_blocks`` (gguf/quants.py:475-521, 552-572, 395-401)
 * torch 2.11         — fp32/fp16 -> bf16 round-to-nearest-even
 
 Everything here is plain Python/numpy so that it can be read next to those sources.  Heavy loops have a
@@ -332,6 +332,43 @@ def dequant_q4k_bf16(blocks: np.ndarray) -> np.ndarray:
     return f32_to_bf16(dequant_q4k_f32(blocks)).reshape(-1, 256)
 
 
+def dequant_q8_0_f32(blocks: np.ndarray) -> np.ndarray:
+    """[n,34] uint8 (d f16 | 32 x int8) -> [n,32] float32, y = q * d in fp32 (gguf/quants.py:395-401)."""
+    b = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, 34)
+    d = b[:, 0:2].copy().view(np.float16).astype(np.float32)
+    q = b[:, 2:].view(np.int8).astype(np.float32)
+    with np.errstate(all="ignore"):
+        return (q * d).astype(np.float32)
+
+
+def dequant_q8_0_bf16(blocks: np.ndarray) -> np.ndarray:
+    return f32_to_bf16(dequant_q8_0_f32(blocks)).reshape(-1, 32)
+
+
+def dequant_q6k_f32(blocks: np.ndarray) -> np.ndarray:
+    """[n,210] uint8 (ql[128] | qh[64] | scales[16] int8 | d f16) -> [n,256] float32.  Explicit-index restatement of
+    gguf/quants.py:552-572: element e = 32g+i takes its low nibble from ql[64*(g//4) + 32*(g%2) + i] >> 4*((g%4)//2),
+    its high two bits from qh[32*(g//4) + i] >> 2*(g%4); q = (lo | hi<<4) - 32; y = (d*scales[e//16]) * q."""
+    b = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, 210)
+    n = b.shape[0]
+    ql, qh = b[:, 0:128], b[:, 128:192]
+    sc = b[:, 192:208].view(np.int8).astype(np.float32)
+    d = b[:, 208:210].copy().view(np.float16).astype(np.float32)
+    q = np.empty((n, 8, 32), np.int16)
+    for g in range(8):
+        lo = (ql[:, 64 * (g // 4) + 32 * (g % 2): 64 * (g // 4) + 32 * (g % 2) + 32] >> (4 * ((g % 4) // 2))) & 0x0F
+        hi = (qh[:, 32 * (g // 4): 32 * (g // 4) + 32] >> (2 * (g % 4))) & 0x03
+        q[:, g, :] = (lo | (hi << 4)).astype(np.int16) - 32
+    with np.errstate(all="ignore"):
+        dsc = (d * sc).astype(np.float32)  # [n,16]
+        y = (dsc[:, :, None] * q.reshape(n, 16, 16).astype(np.float32)).astype(np.float32)
+    return y.reshape(n, 256)
+
+
+def dequant_q6k_bf16(blocks: np.ndarray) -> np.ndarray:
+    return f32_to_bf16(dequant_q6k_f32(blocks)).reshape(-1, 256)
+
+
 _MASK = (1 << 64) - 1
 
 
@@ -369,7 +406,7 @@ _ELEM_BYTES.update({"F32": 4, "F16": 2, "BF16": 2, "I8": 1, "I16": 2, "I32": 4, 
 
 
 def pool_dtype(dt: str, flags: int = 0) -> str:
-    if dt in ("F16", "BF16", "Q4_K"):
+    if dt in ("F16", "BF16", "Q4_K", "Q6_K", "Q8_0"):
         return "BF16"
     if dt == "F32":
         return "F32" if flags & LOAD_KEEP_F32 else "BF16"
@@ -438,6 +475,10 @@ def convert_tensor(rec: dict, raw: bytes, flags: int = 0) -> np.ndarray:
         return f16_bits_to_bf16(a.view("<u2")).view(np.uint8)
     if dt == "Q4_K":
         return dequant_q4k_bf16(a.reshape(-1, 144)).reshape(-1).view(np.uint8)
+    if dt == "Q8_0":
+        return dequant_q8_0_bf16(a.reshape(-1, 34)).reshape(-1).view(np.uint8)
+    if dt == "Q6_K":
+        return dequant_q6k_bf16(a.reshape(-1, 210)).reshape(-1).view(np.uint8)
     if dt.startswith("Q"):
         raise OracleError(f"{dt} dequantisation not defined by this oracle")
     return a.copy()

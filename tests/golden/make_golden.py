@@ -94,6 +94,40 @@ def make_gguf():
     np.savez_compressed(p + ".bf16.npz", **outs)
 
 
+def make_gguf_mixed_quants():
+    """A Q4_K_M-style file: Q4_K + Q6_K + Q8_0 + F32 tensors (real llama.cpp Q4_K_M checkpoints mix Q4_K and Q6_K)."""
+    import gguf
+    from gguf import GGMLQuantizationType as Q
+    rng = np.random.Generator(np.random.Philox(key=78))
+
+    def blocks(nblk, bsz, doffs):
+        b = rng.integers(0, 256, size=(nblk, bsz), dtype=np.uint8)
+        for off in doffs:
+            e = rng.integers(5, 12, size=nblk, dtype=np.uint16)
+            m = rng.integers(0, 1024, size=nblk, dtype=np.uint16)
+            sgn = rng.integers(0, 2, size=nblk, dtype=np.uint16) << 15
+            b[:, off:off + 2] = ((e << 10) | m | sgn).astype("<u2").view(np.uint8).reshape(nblk, 2)
+        return b
+
+    p = os.path.join(HERE, "q4km_mix.gguf")
+    w = gguf.GGUFWriter(p, "llama")
+    w.add_tensor("blk.0.ffn_down.weight", blocks(3 * 2, 210, [208]).reshape(3, 2 * 210), raw_dtype=Q.Q6_K)   # [3, 512]
+    w.add_tensor("blk.0.attn_v.weight", blocks(5 * 3, 34, [0]).reshape(5, 3 * 34), raw_dtype=Q.Q8_0)          # [5, 96]
+    w.add_tensor("blk.0.attn_q.weight", blocks(2 * 1, 144, [0, 2]).reshape(2, 144), raw_dtype=Q.Q4_K)          # [2, 256]
+    w.add_tensor("output.weight", blocks(4 * 1, 210, [208]).reshape(4, 210), raw_dtype=Q.Q6_K)                  # [4, 256]
+    w.add_tensor("blk.0.attn_norm.weight", rng.standard_normal(16).astype(np.float32))
+    w.write_header_to_file(); w.write_kv_data_to_file(); w.write_tensors_to_file(); w.close()
+    r = gguf.GGUFReader(p)
+    exp, outs = [], {}
+    for t in r.tensors:
+        shape = [int(x) for x in reversed(t.shape.tolist())]
+        exp.append(dict(name=t.name, dtype=t.tensor_type.name, shape=shape, file_offset=int(t.data_offset), nbytes=int(t.n_bytes)))
+        f32 = gguf.quants.dequantize(np.array(t.data), t.tensor_type)
+        outs[t.name] = bits16(torch.from_numpy(np.ascontiguousarray(f32, dtype=np.float32)).to(torch.bfloat16)).reshape(-1)
+    json.dump(dict(tensors=exp, alignment=int(r.alignment), data_offset=int(r.data_offset)), open(p + ".expected.json", "w"), indent=1)
+    np.savez_compressed(p + ".bf16.npz", **outs)
+
+
 def make_sharded():
     from huggingface_hub import save_torch_state_dict
     d = os.path.join(HERE, "sharded")
@@ -124,7 +158,7 @@ def make_cast_vectors():
 
 
 if __name__ == "__main__":
-    make_safetensors(); make_gguf(); make_sharded(); make_cast_vectors()
+    make_safetensors(); make_gguf(); make_gguf_mixed_quants(); make_sharded(); make_cast_vectors()
     for r, _, fs in os.walk(HERE):
         for f in sorted(fs):
             p = os.path.join(r, f)

@@ -10,7 +10,7 @@ import numpy as np
 
 from oracle import oracle
 
-OP_COPY, OP_F32, OP_F16, OP_Q4K, OP_T_F32_BF16, OP_T_F16_BF16, OP_T_B16, OP_T_B32 = range(8)
+OP_COPY, OP_F32, OP_F16, OP_Q4K, OP_T_F32_BF16, OP_T_F16_BF16, OP_T_B16, OP_T_B32, OP_Q8_0, OP_Q6K = range(10)
 
 
 def emulate_part(plan: dict, part: int, pool_bytes: int) -> Tuple[np.ndarray, np.ndarray]:
@@ -45,6 +45,12 @@ def emulate_part(plan: dict, part: int, pool_bytes: int) -> Tuple[np.ndarray, np
                 elif op == OP_Q4K:
                     out = oracle.dequant_q4k_bf16(buf[so:so + 144 * u].reshape(-1, 144)).reshape(-1).view(np.uint8)
                     tiles += -(-u // 224)
+                elif op == OP_Q8_0:
+                    out = oracle.dequant_q8_0_bf16(buf[so:so + 34 * u].reshape(-1, 34)).reshape(-1).view(np.uint8)
+                    tiles += -(-u // 960)
+                elif op == OP_Q6K:
+                    out = oracle.dequant_q6k_bf16(buf[so:so + 210 * u].reshape(-1, 210)).reshape(-1).view(np.uint8)
+                    tiles += -(-u // 152)
                 else:
                     C, R, r0 = sg["p0"], sg["p1"], sg["p2"]
                     es = 4 if op in (OP_T_F32_BF16, OP_T_B32) else 2

@@ -59,6 +59,25 @@ def test_unpadded_header_exercises_the_misaligned_path(pool, tmp_path):
         load_and_check(pool, p)
 
 
+def test_q4_k_m_style_mixed_quants_q6k_q8_0(pool, tmp_path):
+    """Real Q4_K_M GGUFs mix Q4_K with Q6_K (and Q8_0 appears in other presets): bit-exact vs the oracle and vs the
+    committed gguf-py fixture."""
+    from tests.test_plan import q4km_tensors
+    p = str(tmp_path / "q4km.gguf")
+    synth.write_gguf(p, q4km_tensors(hidden=512, ffn=1536, layers=2, vocab=1024), 9)
+    load_and_check(pool, p)
+    g = os.path.join(G, "q4km_mix.gguf")
+    load_and_check(pool, g)
+    outs = np.load(g + ".bf16.npz")
+    m = pool.load(g)
+    try:
+        for name in outs.files:
+            pl = m.placements(name)[0]
+            assert np.array_equal(m.read(0, pl.pool_offset, pl.nbytes).view(np.uint16), outs[name]), name
+    finally:
+        m.release()
+
+
 def test_golden_files(pool):
     load_and_check(pool, os.path.join(G, "st_mixed.safetensors"))
     load_and_check(pool, os.path.join(G, "sharded"))
@@ -431,11 +450,14 @@ def test_multi_destination_store_paths_on_one_gpu(native, tmp_path, ndst):
     synth.make_gpt2(f, n_layer=2, d=96, vocab=301, n_pos=40)
     f2 = str(tmp_path / "gpt2_odd.safetensors")
     synth.write_safetensors(f2, synth.gpt2_tensors(n_layer=1, d=40, vocab=50, n_pos=8, dtype="F16"), 3)
+    from tests.test_plan import q4km_tensors
+    g2 = str(tmp_path / "q4km.gguf")
+    synth.write_gguf(g2, q4km_tensors(), 9)
     f3 = str(tmp_path / "gpt2_d41.safetensors")  # rows of 41/123/164 elements: not 16-byte multiples -> direct-global transpose path
     synth.write_safetensors(f3, synth.gpt2_tensors(n_layer=2, d=41, vocab=50, n_pos=8), 4)
     env = dict(os.environ, KUKEON_GPULOAD_TEST_NDST=str(ndst))
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-c", _NDST_CHILD, root, f"{d}:0", f"{mixed}:0", f"{g}:0", f"{f}:1", f"{f}:3", f"{f2}:1", f"{f3}:1", f"{f3}:3"],
+    r = subprocess.run([sys.executable, "-c", _NDST_CHILD, root, f"{d}:0", f"{mixed}:0", f"{g}:0", f"{g2}:0", f"{f}:1", f"{f}:3", f"{f2}:1", f"{f3}:1", f"{f3}:3"],
                        capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-3000:]
 

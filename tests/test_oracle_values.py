@@ -107,3 +107,36 @@ def test_fill_generators_are_finite_and_reproducible(coracle):
     q = coracle.fill("q4k", 100, 1).reshape(-1, 144)
     d = q[:, 0:4].copy().view(np.float16).astype(np.float32)
     assert np.isfinite(d).all() and (d >= 2.0 ** -10).all() and (d < 2.0 ** -3).all()
+
+
+def test_q6k_q8_0_random_blocks_vs_gguf_py_live_bit_exact(coracle):
+    from gguf import GGMLQuantizationType, quants
+    from tools import synth
+    q8 = synth.gen_bytes("Q8_0", 34 * 6000, 3, 1).reshape(-1, 34)
+    ref = bits16(torch.from_numpy(quants.dequantize(q8, GGMLQuantizationType.Q8_0)).to(torch.bfloat16))
+    assert (oracle.dequant_q8_0_bf16(q8) == ref).all() and (coracle.q8_0_to_bf16(q8) == ref).all()
+    q6 = synth.gen_bytes("Q6_K", 210 * 3000, 3, 2).reshape(-1, 210)
+    ref = bits16(torch.from_numpy(quants.dequantize(q6, GGMLQuantizationType.Q6_K)).to(torch.bfloat16))
+    assert (oracle.dequant_q6k_bf16(q6) == ref).all() and (coracle.q6k_to_bf16(q6) == ref).all()
+    # extremes: all-ones payload (q = 31, scales = -1), zero payload (q = -32), d = largest finite half
+    b = np.zeros((3, 210), np.uint8)
+    b[0, :208] = 0xFF; b[0, 208:] = np.array([0x3C00], "<u2").view(np.uint8)
+    b[1, 208:] = np.array([0x7BFF], "<u2").view(np.uint8); b[1, 192:208] = 0x7F
+    b[2, :192] = 0xA5; b[2, 192:208] = 0x80; b[2, 208:] = np.array([0x8001], "<u2").view(np.uint8)
+    ref = bits16(torch.from_numpy(quants.dequantize(b, GGMLQuantizationType.Q6_K)).to(torch.bfloat16))
+    assert (oracle.dequant_q6k_bf16(b) == ref).all() and (coracle.q6k_to_bf16(b) == ref).all()
+
+
+def test_mixed_quant_golden_file_vs_gguf_py():
+    import json
+    p = os.path.join(G, "q4km_mix.gguf")
+    exp = json.load(open(p + ".expected.json"))
+    outs = np.load(p + ".bf16.npz")
+    raw = open(p, "rb").read()
+    seen = set()
+    for t in exp["tensors"]:
+        rec = dict(name=t["name"], dtype=t["dtype"], shape=t["shape"], nbytes=t["nbytes"])
+        got = oracle.convert_tensor(rec, raw[t["file_offset"]:t["file_offset"] + t["nbytes"]]).view(np.uint16)
+        assert (got == outs[t["name"]]).all(), t["name"]
+        seen.add(t["dtype"])
+    assert {"Q4_K", "Q6_K", "Q8_0", "F32"} <= seen

@@ -147,13 +147,34 @@ def test_mixtral_gguf_plan(native, tmp_path):
 
 def test_unsupported_quant_is_refused_at_plan_time(native, tmp_path):
     import struct
-    p = str(tmp_path / "q8.gguf")
-    head = struct.pack("<IIQQ", 0x46554747, 3, 1, 0) + struct.pack("<Q", 1) + b"w" + struct.pack("<I", 1) + struct.pack("<Q", 32) + struct.pack("<IQ", 8, 0)
+    p = str(tmp_path / "q5k.gguf")
+    head = struct.pack("<IIQQ", 0x46554747, 3, 1, 0) + struct.pack("<Q", 1) + b"w" + struct.pack("<I", 1) + struct.pack("<Q", 256) + struct.pack("<IQ", 13, 0)
     head += b"\0" * ((-len(head)) % 32)
-    open(p, "wb").write(head + b"\0" * 64)
-    assert gpupool.index(p)[0]["dtype"] == "Q8_0"  # indexing works ...
-    with pytest.raises(gpupool.ErrUnsupported, match="Q8_0"):  # ... loading is refused, never approximated
+    open(p, "wb").write(head + b"\0" * 192)
+    assert gpupool.index(p)[0]["dtype"] == "Q5_K"  # indexing works ...
+    with pytest.raises(gpupool.ErrUnsupported, match="Q5_K"):  # ... loading is refused, never approximated
         gpupool.plan_describe(p)
+
+
+def q4km_tensors(hidden=256, ffn=768, layers=2, vocab=512):
+    """llama.cpp Q4_K_M-style mix: attention/ffn in Q4_K, ffn_down and output in Q6_K, one Q8_0 tensor, norms F32."""
+    t = [("token_embd.weight", "Q4_K", [vocab, hidden])]
+    for i in range(layers):
+        p = f"blk.{i}."
+        t += [(p + "attn_norm.weight", "F32", [hidden]), (p + "attn_q.weight", "Q4_K", [hidden, hidden]),
+              (p + "attn_v.weight", "Q8_0", [hidden // 4, hidden]), (p + "ffn_up.weight", "Q4_K", [ffn, hidden]),
+              (p + "ffn_down.weight", "Q6_K", [hidden, ffn])]
+    t += [("output_norm.weight", "F32", [hidden]), ("output.weight", "Q6_K", [vocab, hidden])]
+    return t
+
+
+def test_q4_k_m_style_mixed_quant_plan(native, tmp_path):
+    p = str(tmp_path / "q4km.gguf")
+    synth.write_gguf(p, q4km_tensors(), 9)
+    run_case(p, chunk=1 * MB)
+    run_case(p, mode=gpupool.MODE_BROADCAST, n_parts=3, chunk=1 * MB)
+    run_case(p, mode=gpupool.MODE_SCATTER, n_parts=2, chunk=1 * MB)
+    run_case(os.path.join(G, "q4km_mix.gguf"))
 
 
 def test_bad_arguments(native, tmp_path):

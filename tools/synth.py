@@ -20,8 +20,8 @@ from typing import Dict, List, Sequence, Tuple
 import numpy as np
 
 ST_ITEMSIZE = {"F32": 4, "F16": 2, "BF16": 2, "I64": 8, "I32": 4, "U8": 1, "I8": 1, "BOOL": 1, "F64": 8, "I16": 2, "U16": 2}
-GGML = {"F32": (0, 1, 4), "F16": (1, 1, 2), "Q4_K": (12, 256, 144), "BF16": (30, 1, 2)}
-_KIND = {"BF16": 1, "F16": 2, "F32": 3, "Q4_K": 4}
+GGML = {"F32": (0, 1, 4), "F16": (1, 1, 2), "Q4_K": (12, 256, 144), "BF16": (30, 1, 2), "Q8_0": (8, 32, 34), "Q6_K": (14, 256, 210)}
+_KIND = {"BF16": 1, "F16": 2, "F32": 3, "Q4_K": 4, "Q8_0": 5, "Q6_K": 6}
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libkk_synth.so")
 _lib = None

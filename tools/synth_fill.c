@@ -14,7 +14,7 @@
 #include <omp.h>
 #endif
 
-enum { K_BYTES = 0, K_BF16 = 1, K_F16 = 2, K_F32 = 3, K_Q4K = 4 };
+enum { K_BYTES = 0, K_BF16 = 1, K_F16 = 2, K_F32 = 3, K_Q4K = 4, K_Q8_0 = 5, K_Q6K = 6 };
 
 static inline uint64_t mix64(uint64_t x) {
   x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
@@ -60,10 +60,23 @@ static void fix_q4k(uint8_t* buf, uint64_t first_block, uint64_t nblocks, uint64
   }
 }
 
+/* Block-quantised kinds other than Q4_K: random payload, the fp16 scale `d` (at byte `doff` of every `bsz`-byte block)
+ * overwritten with a finite value in [2^-10, 2^-4]. */
+static void fix_scale(uint8_t* buf, uint64_t first_block, uint64_t nblocks, uint64_t bsz, uint64_t doff, uint64_t seed, uint64_t idx) {
+  for (uint64_t b = 0; b < nblocks; ++b) {
+    uint64_t r = rnd(seed ^ 0x5CA1Eull, idx, first_block + b);
+    uint16_t d = (uint16_t)((((r & 0xFF) % 7 + 5) << 10) | ((r >> 8) & 0x3FF) | ((r >> 40) & 1 ? 0x8000 : 0));
+    memcpy(buf + bsz * b + doff, &d, 2);
+  }
+}
+static uint64_t block_bytes(int kind) { return kind == K_Q4K ? 144 : kind == K_Q8_0 ? 34 : kind == K_Q6K ? 210 : 0; }
+
 /* Generate bytes [0, nbytes) of tensor idx and pwrite them at file_off. nbytes % 8 may be non-zero.
  * Q4_K: nbytes must be a multiple of 144.  Returns 0 or -errno. */
 int synth_write(int fd, uint64_t file_off, uint64_t nbytes, int kind, uint64_t seed, uint64_t idx) {
-  const uint64_t CH = (kind == K_Q4K) ? (144ull * 8 * 7168) : (8ull << 20); /* multiple of 8 and of 144*8 */
+  const uint64_t CH = kind == K_Q4K ? (144ull * 8 * 7168) : kind == K_Q8_0 ? (136ull * 61440) : kind == K_Q6K ? (840ull * 9984)
+                                    : (8ull << 20); /* multiple of 8 and of the block size */
+  const uint64_t bsz = block_bytes(kind);
   const uint64_t nch = (nbytes + CH - 1) / CH;
   int err = 0;
 #pragma omp parallel
@@ -73,8 +86,10 @@ int synth_write(int fd, uint64_t file_off, uint64_t nbytes, int kind, uint64_t s
     for (uint64_t c = 0; c < nch; ++c) {
       const uint64_t b0 = c * CH;
       const uint64_t n = nbytes - b0 < CH ? nbytes - b0 : CH;
-      fill_words(buf, b0 / 8, (n + 7) / 8, kind == K_Q4K ? K_BYTES : kind, seed, idx);
+      fill_words(buf, b0 / 8, (n + 7) / 8, bsz ? K_BYTES : kind, seed, idx);
       if (kind == K_Q4K) fix_q4k(buf, b0 / 144, n / 144, seed, idx);
+      else if (kind == K_Q8_0) fix_scale(buf, b0 / 34, n / 34, 34, 0, seed, idx);
+      else if (kind == K_Q6K) fix_scale(buf, b0 / 210, n / 210, 210, 208, seed, idx);
       uint64_t done = 0;
       while (done < n) {
         ssize_t w = pwrite(fd, buf + done, n - done, (off_t)(file_off + b0 + done));
@@ -94,13 +109,16 @@ int synth_write(int fd, uint64_t file_off, uint64_t nbytes, int kind, uint64_t s
 /* Same content into memory (tests regenerate pieces without a file). */
 void synth_fill(uint8_t* dst, uint64_t nbytes, int kind, uint64_t seed, uint64_t idx) {
   uint64_t nw = nbytes / 8;
-  fill_words(dst, 0, nw, kind == K_Q4K ? K_BYTES : kind, seed, idx);
+  const int wk = block_bytes(kind) ? K_BYTES : kind;
+  fill_words(dst, 0, nw, wk, seed, idx);
   if (nbytes & 7) {
     uint8_t tmp[8];
-    fill_words(tmp, nw, 1, kind == K_Q4K ? K_BYTES : kind, seed, idx);
+    fill_words(tmp, nw, 1, wk, seed, idx);
     memcpy(dst + 8 * nw, tmp, nbytes & 7);
   }
   if (kind == K_Q4K) fix_q4k(dst, 0, nbytes / 144, seed, idx);
+  else if (kind == K_Q8_0) fix_scale(dst, 0, nbytes / 34, 34, 0, seed, idx);
+  else if (kind == K_Q6K) fix_scale(dst, 0, nbytes / 210, 210, 208, seed, idx);
 }
 
 /* torchrun exports OMP_NUM_THREADS=1; callers that want all cores say so explicitly. */
