@@ -5,7 +5,8 @@ the named architectures' exact tensor inventories with seeded counter-based rand
 (counter-based splitmix64 keyed by (seed, tensor index, position) in tools/synth_fill.c, so any
 piece of any tensor can be regenerated without keeping a copy).
 The writers emit the container formats directly (safetensors: u64 header length | JSON | data;
-GGUF v3) and are themselves checked against the format owners' readers in tests/test_synth.py.
+GGUF v3) and are themselves checked against the format owners' readers (safetensors.safe_open,
+gguf.GGUFReader) in tests/test_index.py.
 Neither the product nor the oracle is used here.
 """
 from __future__ import annotations
