@@ -62,7 +62,9 @@ def parse():
     ap.add_argument("--kernel-only", action="store_true", help="profiling aid: skip the streaming load / e2e legs (every kk_convert launch is a resident one)")
     ap.add_argument("--e2e-only", action="store_true", help="tuning aid: skip the resident kernel leg")
     ap.add_argument("--no-numa-pin", action="store_true")
-    ap.add_argument("--lazy-peers", action="store_true", help="leave peer-access setup to the first kk_peer_attach (A/B for time-to-ready)")
+    ap.add_argument("--eager-peers", action="store_true", help="enable peer access to every GPU in kk_open (A/B for time-to-ready)")
+    ap.add_argument("--no-exchange", action="store_true", help="scatter: every rank gathers its own column runs from the file (no NVLink row exchange)")
+    ap.add_argument("--no-single-process", action="store_true", help="skip the one-process-all-GPUs time-to-ready measurement at N > 1")
     ap.add_argument("--fanout", default="p2p", choices=["p2p", "raw"], help="broadcast order: fused convert+fan-out (p2p) or all-gather the file bytes then convert locally (raw)")
     return ap.parse_args()
 
@@ -295,8 +297,8 @@ def main():
 
     mode = gpupool.MODE_SINGLE if world == 1 else (gpupool.MODE_SCATTER if spec["mode"] == "scatter" else gpupool.MODE_BROADCAST)
     flags = (gpupool.CFG_ZEROCOPY if args.zerocopy else 0) | (gpupool.CFG_NO_NUMA_PIN if args.no_numa_pin else 0)
-    if world > 1 and not args.lazy_peers:
-        flags |= gpupool.CFG_PEER_ALL  # daemon-lifetime work (kk_open), not part of a model's time-to-ready
+    if world > 1 and args.eager_peers:
+        flags |= gpupool.CFG_PEER_ALL  # measured: does not shorten cudaIpcOpenMemHandle (the mapping itself is the cost)
     t0 = time.time()
     pool = gpupool.Pool([local], n_staging_buffers=args.slots, staging_buffer_bytes=args.slot_mb << 20, n_reader_threads=args.readers, flags=flags)
     t_open = time.time() - t0
@@ -308,13 +310,16 @@ def main():
     ref = modelhub.Pull(path)
     brk["pull_s"] = time.time() - t_ready0
     lflags = gpupool.LOAD_DEFER | (gpupool.LOAD_GPT2_CONV1D_T if spec["kind"] == "gpt2" else 0)
+    exchange = world > 1 and mode == gpupool.MODE_SCATTER and not args.no_exchange
+    if exchange:
+        lflags |= gpupool.LOAD_SCATTER_EXCHANGE
     t1 = time.time()
     raw_order = args.fanout == "raw" and world > 1 and mode == gpupool.MODE_BROADCAST
     m = modelhub.Load(pool, ref, mode=mode, fanout=gpupool.FANOUT_RAW if raw_order else gpupool.FANOUT_P2P, flags=lflags,
                       part_index=rank if world > 1 else 0, part_count=world if world > 1 else 0)
     brk["plan_alloc_s"] = time.time() - t1
     t1 = time.time()
-    if world > 1 and mode == gpupool.MODE_BROADCAST:
+    if world > 1 and (mode == gpupool.MODE_BROADCAST or exchange):
         which = gpupool.BUF_RAW if raw_order else gpupool.BUF_POOL
         h = m.export_buffer(local, which)
         hs = [None] * world
@@ -524,7 +529,8 @@ def main():
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if spec["kind"] != "gpt2" else "f32->bf16",
         "data": "synthetic",
         "config": {"workload": spec["name"], "file_bytes": file_bytes, "tensors": len(ref.tensors), "shards": len(ref.shards),
-                   "mode": {0: "single", 1: "broadcast (sharded ingest + fused P2P fan-out)", 2: "scatter"}[mode], "pool_bytes_per_gpu": pool_bytes,
+                   "mode": {0: "single", 1: "broadcast (sharded ingest + fused P2P fan-out)",
+                            2: "scatter" + (" (row-parallel tensors exchanged over NVLink: KK_LOAD_SCATTER_EXCHANGE)" if exchange else "")}[mode], "pool_bytes_per_gpu": pool_bytes,
                    "l2": "inputs (>= 2 GB per GPU) far larger than the 126 MB L2; no flush needed", "files": f"warm in {os.path.dirname(d) or d}",
                    "staging": "zero-copy pinned reads" if args.zerocopy else "pinned ring + H2D copy engine", "verified_vs_files": verified},
         "clocks": ck,
@@ -556,6 +562,35 @@ def main():
     m.release()
     pool.close()
     barrier()
+    # ---- time-to-agent-ready in kukeond's real shape: ONE process owning all N GPUs (no CUDA IPC between ranks) ------
+    if world > 1 and not args.no_single_process:
+        if rank == 0:
+            try:
+                t0 = time.time()
+                sp = gpupool.Pool(list(range(world)), n_staging_buffers=args.slots, staging_buffer_bytes=args.slot_mb << 20, n_reader_threads=args.readers)
+                sp_open = time.time() - t0
+                t0 = time.time()
+                ref2 = modelhub.Pull(path)
+                spf = (gpupool.LOAD_GPT2_CONV1D_T if spec["kind"] == "gpt2" else 0) | (gpupool.LOAD_SCATTER_EXCHANGE if exchange else 0)
+                m2 = modelhub.Load(sp, ref2, mode=mode, fanout=gpupool.FANOUT_RAW if raw_order else gpupool.FANOUT_P2P, flags=spf)
+                for dev in range(world):
+                    m2.export(dev)
+                sp_ready = time.time() - t0
+                t0 = time.time()
+                m2.release()
+                m3 = modelhub.Load(sp, ref2, mode=mode, fanout=gpupool.FANOUT_RAW if raw_order else gpupool.FANOUT_P2P, flags=spf)
+                for dev in range(world):
+                    m3.export(dev)
+                sp_ready2 = time.time() - t0
+                st2 = m3.stats()
+                m3.release()
+                sp.close()
+                line["time_to_agent_ready_single_process_s"] = min(sp_ready, sp_ready2)
+                line["single_process"] = {"what": "one process, one kk_ctx over all N GPUs (kukeond's shape): Pull + kk_load(mode) + kk_export x N; pinned ring and peer access set up in kk_open",
+                                          "kk_open_s": sp_open, "first_s": sp_ready, "second_s": sp_ready2, "load_s": st2["load_s"], "alloc_s": st2["alloc_s"]}
+            except Exception as e:  # noqa: BLE001
+                line["single_process"] = {"error": str(e)}
+        barrier()
     if rank == 0:
         emit(line)
         if not args.keep_data:

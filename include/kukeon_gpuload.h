@@ -99,6 +99,10 @@ typedef enum kk_fanout {
 #define KK_LOAD_GPT2_CONV1D_T 0x1u /* transpose HF GPT-2 Conv1D weights ([in,out] -> [out,in]) while loading */
 #define KK_LOAD_KEEP_F32 0x2u      /* keep F32 tensors as F32 in the pool (default: convert to bf16) */
 #define KK_LOAD_DEFER 0x4u         /* index + plan + allocate pools only; data moves on kk_load_part */
+#define KK_LOAD_SCATTER_EXCHANGE 0x8u /* KK_MODE_SCATTER: row-parallel (dim-1 sliced) tensors are ingested as whole rows by
+                                      the rank owning 1/N of the rows and split across the N pools by the kernel over NVLink
+                                      (an all-to-all through NVSwitch) instead of every rank gathering 2-7 KB column runs
+                                      from the file; needs peer access (one process) or attached peers (kk_peer_attach) */
 
 typedef struct kk_ctx kk_ctx;     /* one per process (kukeond lifetime) */
 typedef struct kk_model kk_model; /* refcounted; one per (checkpoint identity, mode, flags) */
@@ -201,6 +205,8 @@ int kk_peer_detach_all(kk_model* m);
  * receives its CUDA-event time.  Single-process kk_load runs both stages itself. */
 #define KK_BUF_POOL 0
 #define KK_BUF_RAW 1
+#define KK_BUF_POOL_PTR 2 /* kk_peer_attach_buffer only: `ipc_handle_64B` points at a `void*` holding a device pointer that is
+                             already valid in THIS process (several ranks hosted by one process, e.g. the single-GPU tests) */
 int kk_export_buffer(kk_model* m, int device, int which, void* ipc_handle_64B);
 int kk_peer_attach_buffer(kk_model* m, int rank, int which, const void* ipc_handle_64B);
 int kk_convert_local(kk_model* m, float* ms_total);

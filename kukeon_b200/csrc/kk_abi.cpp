@@ -199,7 +199,8 @@ int kk_peer_attach_buffer(kk_model* m, int rank, int which, const void* h) {
   return guard([&] {
     need(m, "model");
     need(h, "ipc_handle");
-    if (which == KK_BUF_POOL) kk::model_peer_attach(m, rank, h);
+    if (which == KK_BUF_POOL) kk::model_peer_attach(m, rank, h, true);
+    else if (which == KK_BUF_POOL_PTR) kk::model_peer_attach(m, rank, h, false);
     else if (which == KK_BUF_RAW) kk::model_peer_attach_raw(m, rank, h);
     else kk::fail(KK_EINVAL, "unknown buffer kind %d", which);
   });

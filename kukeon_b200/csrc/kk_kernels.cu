@@ -525,6 +525,17 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
             in_bytes = d.n_units; in_off = seg.src_off + o; d.dst_off = seg.dst_off + o;
             break;
           }
+          case KK_OP_ROWSPLIT: {
+            const uint64_t o = (uint64_t)t * KK_TILE_SRC_BYTES;
+            const uint64_t rem = seg.units - o;
+            d.n_units = rem < KK_TILE_SRC_BYTES ? (uint32_t)rem : KK_TILE_SRC_BYTES;
+            in_bytes = d.n_units; in_off = seg.src_off + o; d.dst_off = seg.dst_off;
+            d.C = seg.p0;                      // row bytes
+            d.R = seg.p1;                      // slice bytes
+            d.row0 = seg.p2;                   // first row of this rank's piece
+            d.col0 = seg.p3 + (uint32_t)o;     // byte position of the tile inside the piece
+            break;
+          }
           case KK_OP_F32_BF16: {
             const uint64_t e = (uint64_t)t * (KK_TILE_SRC_BYTES / 4);
             const uint64_t rem = seg.units - e;
@@ -601,6 +612,10 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
           tx = (mis + in_bytes + 15u) & ~15u;
           if (seg.op == KK_OP_COPY && mis == 0 && (in_bytes & 15u) == 0 && !(L.flags & (KK_LAUNCH_NO_BULK_STORE | KK_LAUNCH_MULTIMEM)))
             d.bulk = 1;
+          // row-split exchange: every (row, destination) piece must be a whole number of 16-byte units on both sides
+          if (seg.op == KK_OP_ROWSPLIT && mis == 0 && (seg.p0 & 15u) == 0 && (seg.p1 & 15u) == 0 && (in_bytes & 15u) == 0 &&
+              (seg.dst_off & 15u) == 0 && !(L.flags & KK_LAUNCH_NO_BULK_STORE))
+            d.bulk = 3;
           g -= mis;
         } else {
           d.pay_off = 0;
@@ -650,12 +665,48 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
         }
         continue;
       }
+      if (t.bulk == 3) {  // row-split exchange, aligned: one bulk store per (row, destination pool) piece of the tile
+        if (cwarp == 0) {
+          if (lane == 0) {
+            fence_proxy_async();
+            uint32_t pos = t.col0;
+            const uint32_t end = t.col0 + t.n_units;
+            uint32_t row = pos / t.C, col = pos - row * t.C;
+            while (pos < end) {
+              const uint32_t j = col / t.R, within = col - j * t.R;
+              uint32_t len = t.R - within;
+              if (len > end - pos) len = end - pos;
+              bulk_s2g(L.xdst[j] + t.dst_off + (uint64_t)(t.row0 + row) * t.R + within, pay + (pos - t.col0), len);
+              pos += len; col += len;
+              if (col >= t.C) { col = 0; ++row; }
+            }
+            bulk_commit();
+            if (pending >= 0) {
+              bulk_wait_read<1>();
+              mbar_arrive(empty0 + 8 * pending);
+            }
+            pending = (int)s;
+          }
+        } else {
+          if (lane == 0) mbar_arrive(empty0 + 8 * s);
+        }
+        continue;
+      }
       if (cwarp == 0 && lane == 0 && pending >= 0) {
         bulk_wait_read<0>();
         mbar_arrive(empty0 + 8 * pending);
         pending = -1;
       }
       switch (t.op) {
+        case KK_OP_ROWSPLIT: {  // unaligned fallback: byte-granular all-to-all copy
+          for (uint32_t k = ctid; k < t.n_units; k += kConsumerThreads) {
+            const uint32_t pos = t.col0 + k;
+            const uint32_t row = pos / t.C, col = pos - row * t.C;
+            const uint32_t j = col / t.R, within = col - j * t.R;
+            L.xdst[j][t.dst_off + (uint64_t)(t.row0 + row) * t.R + within] = (uint8_t)lds8(pay + k);
+          }
+          break;
+        }
         case KK_OP_COPY: consume_copy(D, pay, t.n_units, t.dst_off, ctid); break;
         case KK_OP_F32_BF16: consume_f32(D, pay, t.n_units, t.dst_off, ctid); break;
         case KK_OP_F16_BF16: consume_f16(D, pay, t.n_units, t.dst_off, ctid); break;

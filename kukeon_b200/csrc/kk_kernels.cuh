@@ -15,6 +15,9 @@ struct ConvertLaunch {
   uint32_t n_dst;            // 1 = local pool only; >1 = fused fan-out to peer pools
   uint32_t flags;            // KK_LAUNCH_*
   uint8_t* dst[KK_MAX_DST];  // pool bases (dst[0] is the local pool); multimem VA when NVLS
+  uint8_t* xdst[KK_MAX_DST]; // KK_OP_ROWSPLIT only: pool of every rank, indexed by rank (all-to-all destinations)
+  uint32_t n_xdst;
+  uint32_t pad_;
 };
 
 #define KK_LAUNCH_NO_BULK_STORE 0x1u  // force the register path for aligned copies (A/B measurement)

@@ -136,6 +136,14 @@ struct ErrorSink {
   }
 };
 
+// Column-slice rows can be copied out of a read-only mapping instead of one pread each.  Measured on the 8xB200 box
+// (Llama-3-70B scatter, tmpfs): 1.99 s per load with the mapping vs 1.51 s with pread — first-touch page faults of the
+// mapping cost more than the syscalls — so pread stays the default; KUKEON_GPULOAD_ROW_MMAP=1 switches.
+bool want_row_maps(const kk_model* m) {
+  static const bool on = [] { const char* e = getenv("KUKEON_GPULOAD_ROW_MMAP"); return e && *e == '1'; }();
+  return on && m->plan.mode == KK_MODE_SCATTER;
+}
+
 // Fill the slot with the chunk's file bytes.
 void read_chunk(const Chunk& c, const FdSet& fds, const Index& ix, uint8_t* pinned) {
   const uint8_t* mp = fds.maps.empty() ? nullptr : fds.maps[c.shard];
@@ -173,6 +181,20 @@ void fill_dsts(kk_model* m, int li, ConvertLaunch& L) {
   L.flags = 0;
   for (auto& d : L.dst) d = nullptr;
   L.dst[L.n_dst++] = m->pools[(size_t)li];
+  L.n_xdst = 0;
+  for (auto& d : L.xdst) d = nullptr;
+  if (m->plan.mode == KK_MODE_SCATTER && (m->plan.flags & KK_LOAD_SCATTER_EXCHANGE) && m->plan.n_parts > 1) {
+    // all-to-all destinations of KK_OP_ROWSPLIT segments: the pool of every rank, indexed by rank
+    const int n = m->plan.n_parts;
+    for (int j = 0; j < n; ++j) {
+      uint8_t* p = nullptr;
+      if (m->opts.part_count > 1) p = (j == m->opts.part_index) ? m->pools[0] : (uint8_t*)m->peer_ptr[j];
+      else if (m->ctx->peer_ok) p = m->pools[(size_t)j];
+      if (!p) fail(KK_ESTATE, "KK_LOAD_SCATTER_EXCHANGE: the pool of rank %d is not reachable (attach it with kk_peer_attach, or enable peer access)", j);
+      L.xdst[j] = p;
+    }
+    L.n_xdst = (uint32_t)n;
+  }
   if (m->plan.mode != KK_MODE_BROADCAST || m->opts.fanout == KK_FANOUT_NONE) {
     pad_dsts_for_test(L);
     return;
@@ -450,7 +472,7 @@ void destroy_model(kk_model* m) {
   for (int r = 0; r < KK_MAX_DEVICES; ++r)
     if (m->peer_ptr[r]) {
       cudaSetDevice(c->devs[(size_t)m->dev_idx[0]].ordinal);
-      cudaIpcCloseMemHandle(m->peer_ptr[r]);
+      if (m->peer_is_ipc[r]) cudaIpcCloseMemHandle(m->peer_ptr[r]);
       m->peer_ptr[r] = nullptr;
     }
   for (size_t i = 0; i < m->pools.size(); ++i) {
@@ -593,7 +615,7 @@ void ctx_close(kk_ctx* c) {
 // ---------------------------------------------------------------------------------------------
 static void do_load(kk_model* m) {
   const double t0 = now_s();
-  FdSet fds(m->plan.index.shards, m->plan.mode == KK_MODE_SCATTER);
+  FdSet fds(m->plan.index.shards, want_row_maps(m));
   const size_t nl = m->dev_idx.size();
   m->t_part.assign(nl, 0.0);
   const bool multi_proc = m->opts.part_count > 1;
@@ -788,18 +810,25 @@ void model_release(kk_model* m) {
   destroy_model(m);
 }
 
-void model_peer_attach(kk_model* m, int rank, const void* handle) {
+void model_peer_attach(kk_model* m, int rank, const void* handle, bool is_ipc) {
   if (m->opts.part_count <= 1) fail(KK_ESTATE, "peer attach needs a multi-process (part_count > 1) model");
   if (rank < 0 || rank >= m->opts.part_count || rank == m->opts.part_index) fail(KK_EINVAL, "bad peer rank %d", rank);
-  if (m->plan.mode != KK_MODE_BROADCAST) fail(KK_ESTATE, "peer attach only applies to BROADCAST models");
+  if (m->plan.mode != KK_MODE_BROADCAST && !(m->plan.mode == KK_MODE_SCATTER && (m->plan.flags & KK_LOAD_SCATTER_EXCHANGE)))
+    fail(KK_ESTATE, "peer attach only applies to BROADCAST models and to SCATTER models loaded with KK_LOAD_SCATTER_EXCHANGE");
   if (m->peer_ptr[rank]) fail(KK_ESTATE, "peer rank %d already attached", rank);
   Device& d = m->ctx->devs[(size_t)m->dev_idx[0]];
   KK_CUDA(cudaSetDevice(d.ordinal));
-  cudaIpcMemHandle_t h;
-  memcpy(&h, handle, sizeof h);
   void* p = nullptr;
-  KK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  if (is_ipc) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    KK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  } else {
+    memcpy(&p, handle, sizeof p);
+    if (!p) fail(KK_EINVAL, "null device pointer");
+  }
   m->peer_ptr[rank] = p;
+  m->peer_is_ipc[rank] = is_ipc;
 }
 
 void model_peer_detach_all(kk_model* m) {
@@ -807,7 +836,7 @@ void model_peer_detach_all(kk_model* m) {
   cudaSetDevice(d.ordinal);
   for (int r = 0; r < KK_MAX_DEVICES; ++r) {
     if (m->peer_ptr[r]) {
-      cudaIpcCloseMemHandle(m->peer_ptr[r]);
+      if (m->peer_is_ipc[r]) cudaIpcCloseMemHandle(m->peer_ptr[r]);
       m->peer_ptr[r] = nullptr;
     }
     if (m->peer_raw_ptr[r]) {
@@ -865,6 +894,7 @@ std::string model_stats(kk_model* m) {
     for (auto& s : pp.segs) {
       uint64_t b = s.dst_off, e;
       switch (s.op) {
+        case KK_OP_ROWSPLIT: continue;  // lands in every pool; not part of this rank's contiguous range
         case KK_OP_COPY: e = b + s.units; break;
         case KK_OP_F32_BF16: case KK_OP_F16_BF16: e = b + s.units * 2; break;
         case KK_OP_Q4K_BF16: case KK_OP_Q6K_BF16: e = b + s.units * 512; break;
@@ -899,7 +929,7 @@ void model_stage_resident(kk_model* m) {
   }
   free_resident(m);
   kk_ctx* c = m->ctx;
-  FdSet fds(m->plan.index.shards, m->plan.mode == KK_MODE_SCATTER);
+  FdSet fds(m->plan.index.shards, want_row_maps(m));
   m->resident.resize(m->dev_idx.size());
   for (size_t li = 0; li < m->dev_idx.size(); ++li) {
     Device& dev = c->devs[(size_t)m->dev_idx[li]];

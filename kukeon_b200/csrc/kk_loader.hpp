@@ -70,6 +70,7 @@ struct kk_model {
   std::vector<KKSeg*> d_segs;        // per local device: device copy of its part's segment table
   // multi-process fan-out destinations (BROADCAST): IPC-opened peer pools by rank
   void* peer_ptr[KK_MAX_DEVICES] = {};
+  bool peer_is_ipc[KK_MAX_DEVICES] = {};  // false: caller-owned pointer (KK_BUF_POOL_PTR), never closed by us
   // resident image (kernel-stage measurement)
   struct Resident {
     uint8_t* image = nullptr;
@@ -113,7 +114,7 @@ void ctx_close(kk_ctx* c);
 kk_model* model_load(kk_ctx* c, const std::string& path, const kk_load_opts& opts);
 void model_load_part(kk_model* m);
 void model_release(kk_model* m);
-void model_peer_attach(kk_model* m, int rank, const void* handle);
+void model_peer_attach(kk_model* m, int rank, const void* handle, bool is_ipc = true);
 void model_peer_attach_raw(kk_model* m, int rank, const void* handle);
 void model_export_raw(kk_model* m, int local, void* handle_out);
 void model_convert_local(kk_model* m, float* ms_total);

@@ -33,7 +33,11 @@ enum KKOp : uint32_t {
   KK_OP_T_B32 = 7,     // 4-byte elements moved verbatim
   KK_OP_Q8_0_BF16 = 8, // units = 32-weight blocks (34 B: d f16 | 32 x int8)
   KK_OP_Q6K_BF16 = 9,  // units = 256-weight super-blocks (210 B: ql[128] | qh[64] | scales[16] int8 | d f16)
-  KK_OP_COUNT = 10
+  // SCATTER exchange: units = bytes of whole source rows; every row is cut into N column slices of p1 bytes and slice j
+  // goes to pool j (ConvertLaunch::xdst[j]) at dst_off + row * p1.  p0 = row bytes, p1 = slice bytes, p2 = index of the
+  // first row of this rank's piece, p3 = bytes of the piece that precede this segment.
+  KK_OP_ROWSPLIT = 10,
+  KK_OP_COUNT = 11
 };
 
 struct KKSeg {
@@ -55,7 +59,8 @@ __host__ __device__
 #endif
 uint64_t kk_seg_tiles(uint32_t op, uint64_t units, uint32_t p0) {
   switch (op) {
-    case KK_OP_COPY: return (units + KK_TILE_SRC_BYTES - 1) / KK_TILE_SRC_BYTES;
+    case KK_OP_COPY:
+    case KK_OP_ROWSPLIT: return (units + KK_TILE_SRC_BYTES - 1) / KK_TILE_SRC_BYTES;
     case KK_OP_F32_BF16: return (units + KK_TILE_SRC_BYTES / 4 - 1) / (KK_TILE_SRC_BYTES / 4);
     case KK_OP_F16_BF16: return (units + KK_TILE_SRC_BYTES / 2 - 1) / (KK_TILE_SRC_BYTES / 2);
     case KK_OP_Q4K_BF16: return (units + KK_Q4K_TILE_BLOCKS - 1) / KK_Q4K_TILE_BLOCKS;

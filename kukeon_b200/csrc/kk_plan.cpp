@@ -58,6 +58,8 @@ struct Piece {
   uint32_t p0 = 0, p1 = 0;  // transposes: C, R
   bool transpose = false;
   uint64_t row_src_bytes = 0;  // transposes: C * es
+  bool rowsplit = false;       // SCATTER exchange: whole rows in, column slices out to every pool
+  uint32_t rs_row_bytes = 0, rs_slice_bytes = 0, rs_first_row = 0;
 };
 
 struct ChunkBuilder {
@@ -116,6 +118,13 @@ struct ChunkBuilder {
       s.p1 = pc.p1;
       s.p2 = (uint32_t)units_done;
       cur.out_bytes += units * pc.p0 * pc.oi.out_unit_bytes;
+    } else if (pc.rowsplit) {
+      s.dst_off = pc.dst_off;
+      s.p0 = pc.rs_row_bytes;
+      s.p1 = pc.rs_slice_bytes;
+      s.p2 = pc.rs_first_row;
+      s.p3 = (uint32_t)units_done;
+      cur.out_bytes += units;
     } else {
       s.dst_off = pc.dst_off + units_done * pc.oi.out_unit_bytes;
       cur.out_bytes += units * pc.oi.out_unit_bytes;
@@ -305,14 +314,31 @@ Plan build_plan(Index index, int mode, uint32_t flags, int n_parts, uint64_t chu
             const uint64_t es = di->block_bytes;
             p.slice_begin = cols * (uint64_t)L;
             p.shape[1] = cols;
-            pc.file_off = t.file_offset + p.slice_begin * es;
-            pc.run_bytes = cols * es;
-            pc.n_runs = R;
-            pc.stride = C * es;
-            pc.units = R * (pc.run_bytes / oi.src_unit_bytes);
-            if (cols == C) { pc.n_runs = 1; pc.run_bytes = t.nbytes; }
+            const uint64_t row_bytes = C * es, slice_bytes = cols * es;
+            const bool exchange = (flags & KK_LOAD_SCATTER_EXCHANGE) && oi.op == KK_OP_COPY && row_bytes <= 0xFFFFFFFFull &&
+                                  R <= 0xFFFFFFFFull && (R / (uint64_t)n_parts + (uint64_t)n_parts) * row_bytes < 0xFFFFFFFFull;
+            if (exchange) {
+              // this rank ingests whole rows [r0, r1) and the kernel deals column slice j of every row to pool j
+              const uint64_t per = R / (uint64_t)n_parts;
+              const uint64_t r0 = per * (uint64_t)L, r1 = (L == n_parts - 1) ? R : per * (uint64_t)(L + 1);
+              pc.rowsplit = true;
+              pc.rs_row_bytes = (uint32_t)row_bytes;
+              pc.rs_slice_bytes = (uint32_t)slice_bytes;
+              pc.rs_first_row = (uint32_t)r0;
+              pc.file_off = t.file_offset + r0 * row_bytes;
+              pc.run_bytes = (r1 - r0) * row_bytes;
+              pc.units = pc.run_bytes;
+              pc.oi.op = KK_OP_ROWSPLIT;
+              p.nbytes = R * slice_bytes;
+            } else {
+              pc.file_off = t.file_offset + p.slice_begin * es;
+              pc.run_bytes = cols * es;
+              pc.n_runs = R;
+              pc.stride = C * es;
+              pc.units = R * (pc.run_bytes / oi.src_unit_bytes);
+            }
           }
-          p.nbytes = pc.units * oi.out_unit_bytes;
+          if (!pc.rowsplit) p.nbytes = pc.units * oi.out_unit_bytes;
         }
       }
       p.pool_offset = off;
@@ -404,7 +430,7 @@ std::string plan_to_json(const Plan& P) {
         const KKSeg& sg = pp.segs[ch.seg_begin + s];
         o << (s ? "," : "") << "{\"src_off\":" << sg.src_off << ",\"dst_off\":" << sg.dst_off << ",\"units\":" << sg.units
           << ",\"op\":" << sg.op << ",\"tile_begin\":" << sg.tile_begin << ",\"p0\":" << sg.p0 << ",\"p1\":" << sg.p1
-          << ",\"p2\":" << sg.p2 << "}";
+          << ",\"p2\":" << sg.p2 << ",\"p3\":" << sg.p3 << "}";
       }
       o << "]}";
     }

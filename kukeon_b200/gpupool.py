@@ -23,8 +23,8 @@ KK_POOL_ALIGN = 256
 MODE_SINGLE, MODE_BROADCAST, MODE_SCATTER = 0, 1, 2
 FANOUT_P2P, FANOUT_NVLS, FANOUT_NONE, FANOUT_RAW = 0, 1, 2, 3
 CFG_ZEROCOPY, CFG_NO_PEER_ACCESS, CFG_NO_NUMA_PIN, CFG_PEER_ALL = 0x1, 0x2, 0x4, 0x8
-LOAD_GPT2_CONV1D_T, LOAD_KEEP_F32, LOAD_DEFER = 0x1, 0x2, 0x4
-BUF_POOL, BUF_RAW = 0, 1
+LOAD_GPT2_CONV1D_T, LOAD_KEEP_F32, LOAD_DEFER, LOAD_SCATTER_EXCHANGE = 0x1, 0x2, 0x4, 0x8
+BUF_POOL, BUF_RAW, BUF_POOL_PTR = 0, 1, 2
 
 DTYPE_NAMES = {
     0: "BOOL", 1: "F4", 2: "F6_E2M3", 3: "F6_E3M2", 4: "U8", 5: "I8", 6: "F8_E5M2", 7: "F8_E4M3", 8: "F8_E8M0",
@@ -299,6 +299,11 @@ class Model:
     def peer_attach_buffer(self, rank: int, which: int, ipc_handle: bytes) -> None:
         assert len(ipc_handle) == KK_IPC_HANDLE_BYTES
         _check(lib().kk_peer_attach_buffer(self._h, rank, which, C.c_char_p(ipc_handle)))
+
+    def peer_attach_local_pointer(self, rank: int, dev_ptr: int) -> None:
+        """Several ranks hosted by one process (tests): attach another model's pool by raw device pointer."""
+        p = C.c_void_p(dev_ptr)
+        _check(lib().kk_peer_attach_buffer(self._h, rank, BUF_POOL_PTR, C.byref(p)))
 
     def convert_local(self) -> float:
         """Stage 2 of a multi-process KK_FANOUT_RAW load; returns its CUDA-event milliseconds."""

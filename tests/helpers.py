@@ -10,12 +10,13 @@ import numpy as np
 
 from oracle import oracle
 
-OP_COPY, OP_F32, OP_F16, OP_Q4K, OP_T_F32_BF16, OP_T_F16_BF16, OP_T_B16, OP_T_B32, OP_Q8_0, OP_Q6K = range(10)
+OP_COPY, OP_F32, OP_F16, OP_Q4K, OP_T_F32_BF16, OP_T_F16_BF16, OP_T_B16, OP_T_B32, OP_Q8_0, OP_Q6K, OP_ROWSPLIT = range(11)
 
 
-def emulate_part(plan: dict, part: int, pool_bytes: int) -> Tuple[np.ndarray, np.ndarray]:
+def emulate_part(plan: dict, part: int, pool_bytes: int, exchange: dict | None = None) -> Tuple[np.ndarray, np.ndarray]:
     """Execute one part of a kk_plan_describe plan on the CPU with the oracle's arithmetic.
-    Returns (pool, written-mask).  This checks the planner (reads, segments, offsets), not the kernels."""
+    Returns (pool, written-mask).  This checks the planner (reads, segments, offsets), not the kernels.
+    `exchange` (rank -> (pool, mask)) receives what KK_OP_ROWSPLIT segments deal to the other ranks' pools."""
     pool = np.zeros(pool_bytes, np.uint8)
     mask = np.zeros(pool_bytes, bool)
     fhs = [open(s, "rb") for s in plan["shards"]]
@@ -33,6 +34,22 @@ def emulate_part(plan: dict, part: int, pool_bytes: int) -> Tuple[np.ndarray, np
                 assert sg["tile_begin"] == tiles, "tile_begin must be the running tile count of the chunk"
                 op, so, do, u = sg["op"], sg["src_off"], sg["dst_off"], sg["units"]
                 assert do % 16 == 0
+                if op == OP_ROWSPLIT:
+                    row_bytes, w, r0, done = sg["p0"], sg["p1"], sg["p2"], sg["p3"]
+                    assert exchange is not None and row_bytes % w == 0
+                    pos = done + np.arange(u, dtype=np.int64)
+                    row, col = pos // row_bytes, pos % row_bytes
+                    j, within = col // w, col % w
+                    dsto = do + (r0 + row) * w + within
+                    src = buf[so:so + u]
+                    for rk in np.unique(j):
+                        sel = j == rk
+                        pj, mj = exchange[int(rk)]
+                        assert not mj[dsto[sel]].any(), "exchange pieces overlap"
+                        pj[dsto[sel]] = src[sel]
+                        mj[dsto[sel]] = True
+                    tiles += -(-u // 32768)
+                    continue
                 if op == OP_COPY:
                     out = buf[so:so + u]
                     tiles += -(-u // 32768)

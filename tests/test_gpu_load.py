@@ -486,3 +486,81 @@ def test_raw_fanout_degenerates_on_one_gpu(pool, tmp_path):
         assert_pool_matches(m, 0, shards, recs)
     finally:
         m.release()
+
+
+def _virtual_ranks(pool, path, mode, n, flags=0):
+    """N ranks hosted by ONE process on ONE GPU: rank i = model (part i of n); pools attached to each other by raw
+    device pointer (KK_BUF_POOL_PTR).  Runs the real multi-rank kernels (fused fan-out, row-split exchange)."""
+    ms = [pool.load(path, mode=mode, fanout=gpupool.FANOUT_P2P, flags=flags | gpupool.LOAD_DEFER, part_index=i, part_count=n) for i in range(n)]
+    assert len({m.handle for m in ms}) == n
+    ptrs = [m.pool_ptr(0)[0] for m in ms]
+    need_peers = mode == gpupool.MODE_BROADCAST or (flags & gpupool.LOAD_SCATTER_EXCHANGE)
+    if need_peers:
+        for i, m in enumerate(ms):
+            for j in range(n):
+                if j != i:
+                    m.peer_attach_local_pointer(j, ptrs[j])
+    return ms
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_virtual_ranks_broadcast_on_one_gpu(pool, tmp_path, n):
+    from tests.test_plan import q4km_tensors
+    d = str(tmp_path / "llama")
+    synth.make_llama(d, dict(hidden=256, ffn=704, layers=2, kv_dim=64, vocab=3000), max_shard_bytes=3_000_000)
+    g = str(tmp_path / "q4km.gguf")
+    synth.write_gguf(g, q4km_tensors(), 9)
+    f = str(tmp_path / "gpt2.safetensors")
+    synth.make_gpt2(f, n_layer=2, d=96, vocab=301, n_pos=40)
+    for path, flags in ((d, 0), (g, 0), (f, gpupool.LOAD_GPT2_CONV1D_T)):
+        shards, recs = oracle.index_path(path)
+        ms = _virtual_ranks(pool, path, gpupool.MODE_BROADCAST, n, flags)
+        try:
+            for m in ms:
+                m.load_part()  # rank i converts its 1/n and stores it into all n pools
+            for m in ms:
+                assert_pool_matches(m, 0, shards, recs, flags=flags)
+            for m in ms:       # and again from the resident image (what bench.py times)
+                m.stage_resident()
+            for m in ms:
+                m.convert_resident()
+            for m in ms:
+                assert_pool_matches(m, 0, shards, recs, flags=flags)
+        finally:
+            for m in ms:
+                m.release()
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_virtual_ranks_scatter_exchange_on_one_gpu(pool, tmp_path, n):
+    """KK_LOAD_SCATTER_EXCHANGE: rank i ingests whole rows of the row-parallel tensors and the KK_OP_ROWSPLIT tiles deal
+    every row's column slices to the n pools; every rank's pool must equal its oracle slice pool."""
+    d = str(tmp_path / "llama")
+    synth.make_llama(d, dict(hidden=512, ffn=1408, layers=2, kv_dim=128, vocab=2048), max_shard_bytes=6_000_000)
+    shards, recs = oracle.index_path(d)
+    for flags in (gpupool.LOAD_SCATTER_EXCHANGE, 0):
+        ms = _virtual_ranks(pool, d, gpupool.MODE_SCATTER, n, flags)
+        try:
+            for m in ms:
+                m.load_part()
+            for i, m in enumerate(ms):
+                assert_pool_matches(m, 0, shards, recs, mode=gpupool.MODE_SCATTER, n_parts=n, part=i)
+            if flags:
+                for m in ms:
+                    m.stage_resident()
+                for m in ms:
+                    m.convert_resident()
+                for i, m in enumerate(ms):
+                    assert_pool_matches(m, 0, shards, recs, mode=gpupool.MODE_SCATTER, n_parts=n, part=i)
+                st = ms[0].stats()
+                assert st["local_src_bytes"] < st["file_bytes"] / n * 1.1 + (1 << 20)
+        finally:
+            for m in ms:
+                m.release()
+    # without the peers attached an exchange load must refuse, not silently drop the slices of other ranks
+    m = pool.load(d, mode=gpupool.MODE_SCATTER, flags=gpupool.LOAD_SCATTER_EXCHANGE | gpupool.LOAD_DEFER, part_index=0, part_count=n)
+    try:
+        with pytest.raises(gpupool.ErrState, match="not reachable"):
+            m.load_part()
+    finally:
+        m.release()

@@ -108,6 +108,21 @@ def test_single_process_scatter(native, tmp_path):
             m.release()
 
 
+@needs2
+def test_single_process_scatter_exchange(native, tmp_path):
+    n = min(_ngpu(), 8)
+    d = str(tmp_path / "llama")
+    synth.make_llama(d, dict(hidden=512, ffn=1408, layers=2, kv_dim=128, vocab=2048), max_shard_bytes=6_000_000)
+    shards, recs = oracle.index_path(d)
+    with gpupool.Pool(list(range(n)), n_staging_buffers=2, staging_buffer_bytes=1 * MB, n_reader_threads=1) as pl:
+        m = pl.load(d, mode=gpupool.MODE_SCATTER, flags=gpupool.LOAD_SCATTER_EXCHANGE)
+        try:
+            for dev in range(n):
+                check_pool(m, dev, shards, recs, mode=gpupool.MODE_SCATTER, n_parts=n, part=dev)
+        finally:
+            m.release()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

@@ -109,6 +109,39 @@ def test_scatter_slices(native, tmp_path):
         assert plan["parts"][0]["src_bytes"] < plan["file_bytes"] / n * 1.05 + 64 * 1024
 
 
+def test_scatter_exchange_rows_dealt_to_every_pool(native, tmp_path):
+    """KK_LOAD_SCATTER_EXCHANGE: row-parallel tensors are ingested as whole rows by the rank owning 1/N of the rows and
+    dealt column-slice by column-slice to all N pools; emulating every rank must reproduce every rank's oracle pool."""
+    d = str(tmp_path / "llama")
+    synth.make_llama(d, dict(hidden=256, ffn=704, layers=2, kv_dim=64, vocab=1024), max_shard_bytes=2_500_000)
+    shards, recs = oracle.index_path(d)
+    X = 0x8
+    for n in (2, 4, 8):
+        plan = gpupool.plan_describe(d, mode=gpupool.MODE_SCATTER, flags=X, n_parts=n, chunk_bytes=1 * MB)
+        check_layout(plan, recs, gpupool.MODE_SCATTER, 0, n)
+        exps = [oracle.expected_pool(shards, recs, gpupool.MODE_SCATTER, 0, n, g) for g in range(n)]
+        ex = {g: (np.zeros(len(exps[g][0]), np.uint8), np.zeros(len(exps[g][0]), bool)) for g in range(n)}
+        ops = set()
+        for g in range(n):
+            got, mask = helpers.emulate_part(plan, g, len(exps[g][0]), exchange=ex)
+            assert not (mask & ex[g][1]).any()
+            ex[g][0][mask] = got[mask]
+            ex[g][1][mask] = True
+            ops |= {sg["op"] for ch in plan["parts"][g]["chunks"] for sg in ch["segs"]}
+            # whole-row ingest: every read of this rank is one long contiguous range, no 2-7 KB row runs
+            n_reads = sum(len(ch["reads"]) for ch in plan["parts"][g]["chunks"])
+            assert n_reads <= 2 * len(recs), "exchange plans must not gather rows one pread at a time"
+        assert helpers.OP_ROWSPLIT in ops
+        for g in range(n):
+            exp, pl = exps[g]
+            assert (ex[g][1] == helpers.expected_mask(pl, len(exp))).all()
+            assert (ex[g][0] == exp).all()
+        # every byte of the row-parallel tensors is read exactly once across ranks
+        total = sum(p["src_bytes"] for p in plan["parts"])
+        repl = sum(r["nbytes"] for r in recs if oracle.slice_dim(r, n) is None)
+        assert total == plan["file_bytes"] + (n - 1) * repl
+
+
 def test_scatter_indivisible_dims_are_replicated(native, tmp_path):
     d = str(tmp_path / "llama")
     synth.make_llama(d, dict(hidden=96, ffn=100, layers=1, kv_dim=32, vocab=77), max_shard_bytes=10_000_000)
