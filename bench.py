@@ -373,10 +373,20 @@ def main():
     verified = None
     if spec["kind"] == "llama":
         verified = True
-        for r in (ref.tensors[0], ref.tensors[1], ref.tensors[len(ref.tensors) // 2], ref.tensors[-1]):
+        picks = [ref.tensors[0], ref.tensors[1], ref.tensors[len(ref.tensors) // 2], ref.tensors[-1]]
+        picks += [t for t in ref.tensors if t["name"].endswith(("o_proj.weight", "down_proj.weight"))][-2:]
+        for r in picks:
             pl = m.placements(r["name"])[0]
-            if pl.slice_dim == 1:
-                continue  # column slices are strided in the file; covered by tests/test_gpu_multi.py
+            if pl.slice_dim == 1:  # column slice: compare the last 64 rows run by run
+                R = r["shape"][0]
+                row_bytes, w = r["nbytes"] // R, pl.nbytes // R
+                es = row_bytes // r["shape"][1]
+                mm = np.memmap(ref.shards[r["shard"]], np.uint8, "r", offset=r["file_offset"], shape=(R, row_bytes))
+                want = np.ascontiguousarray(mm[R - 64:, pl.slice_begin * es: pl.slice_begin * es + w]).reshape(-1)
+                got = m.read(local, pl.pool_offset + (R - 64) * w, 64 * w)
+                verified = verified and bool(np.array_equal(want, got))
+                del mm
+                continue
             row_bytes = r["nbytes"] // r["shape"][0] if r["shape"] else r["nbytes"]
             base = r["file_offset"] + (pl.slice_begin * row_bytes if pl.slice_dim == 0 else 0)
             n = min(pl.nbytes, 8 << 20)
