@@ -215,6 +215,7 @@ void run_part(kk_model* m, int li, int part, const FdSet& fds) {
   Device& dev = c->devs[(size_t)m->dev_idx[(size_t)li]];
   const PartPlan& pp = m->plan.parts[(size_t)part];
   if (pp.chunks.empty()) return;
+  std::lock_guard<std::mutex> pipeline(*dev.load_mu);
   const KKSeg* d_segs = m->d_segs[(size_t)li] + seg_base_of(m->plan, part);
   ConvertLaunch base{};
   fill_dsts(m, li, base);
@@ -288,6 +289,7 @@ void run_part_raw(kk_model* m, int li, int part, const FdSet& fds, bool fan_out)
   Device& dev = c->devs[(size_t)m->dev_idx[(size_t)li]];
   const PartPlan& pp = m->plan.parts[(size_t)part];
   if (pp.chunks.empty()) return;
+  std::lock_guard<std::mutex> pipeline(*dev.load_mu);
   kk_model::Raw& R = m->raw[(size_t)li];
   ConvertLaunch base{};
   fill_raw_dsts(m, li, base);
@@ -946,6 +948,7 @@ void model_stage_resident(kk_model* m) {
     cudaError_t e = cudaMalloc((void**)&R.image, R.image_bytes);
     if (e != cudaSuccess) { cudaGetLastError(); R.image = nullptr; fail(KK_ENOMEM, "device %d: cudaMalloc(%llu) for the resident image failed", dev.ordinal, (unsigned long long)R.image_bytes); }
     // copy the chunk bytes exactly as the streaming path stages them
+    std::lock_guard<std::mutex> pipeline(*dev.load_mu);
     Reader& rd = dev.readers[0];
     size_t k = 0;
     for (size_t i = 0; i < pp.chunks.size(); ++i) {

@@ -34,6 +34,9 @@ struct Reader {
 };
 
 struct Device {
+  // One staging pipeline at a time per device: the reader slots and streams below belong to whichever load holds this.
+  // (Concurrent loads of different checkpoints on one GPU serialise here; its PCIe link is the bottleneck anyway.)
+  std::unique_ptr<std::mutex> load_mu{new std::mutex};
   int ordinal = -1;
   int sm_count = 0;
   std::vector<Reader> readers;

@@ -564,3 +564,37 @@ def test_virtual_ranks_scatter_exchange_on_one_gpu(pool, tmp_path, n):
             m.load_part()
     finally:
         m.release()
+
+
+def test_concurrent_loads_of_different_checkpoints_share_the_staging_ring_safely(pool, tmp_path):
+    """Several cells starting at once with DIFFERENT models: the loads share one device's pinned ring and must not
+    trample each other's slots (they serialise on the device's pipeline lock)."""
+    paths = []
+    for i in range(4):
+        d = str(tmp_path / f"llama{i}")
+        synth.make_llama(d, dict(hidden=256, ffn=704, layers=2, kv_dim=64, vocab=1500 + 100 * i), seed=100 + i, max_shard_bytes=3_000_000)
+        paths.append(d)
+    g = str(tmp_path / "mix.gguf")
+    synth.write_gguf(g, synth.mixtral_gguf_tensors(hidden=256, ffn=768, layers=1, experts=2, vocab=512, kv_dim=256), 7)
+    paths.append(g)
+    out, errs = [None] * len(paths), []
+
+    def session(i):
+        try:
+            out[i] = pool.load(paths[i])
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=session, args=(i,)) for i in range(len(paths))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    try:
+        assert not errs, errs
+        assert len({m.handle for m in out}) == len(paths)
+        for p, m in zip(paths, out):
+            shards, recs = oracle.index_path(p)
+            assert_pool_matches(m, 0, shards, recs)
+    finally:
+        for m in out:
+            if m is not None:
+                m.release()
