@@ -63,6 +63,29 @@ class MountSpec:
     mounts: List[dict] = field(default_factory=list)
     env: List[str] = field(default_factory=list)
     host_dir: str = ""
+    devices: List[dict] = field(default_factory=list)        # OCI linux.devices
+    device_cgroup: List[dict] = field(default_factory=list)  # OCI linux.resources.devices allow rules
+
+
+def device_nodes(devices, stat=os.stat) -> tuple:
+    """"next" row f2: the NVIDIA character devices an agent container needs to open a CUDA-IPC
+    handle — /dev/nvidiactl, /dev/nvidia-uvm, /dev/nvidia-uvm-tools and /dev/nvidia<N> for each exported device — as
+    OCI `linux.devices` entries plus the matching device-cgroup allow rules (the reference's spec builder emits
+    neither today: internal/ctr/spec.go:218-380).  Nodes that do not exist on the host are skipped."""
+    import stat as st_mod
+    paths = ["/dev/nvidiactl", "/dev/nvidia-uvm", "/dev/nvidia-uvm-tools"] + [f"/dev/nvidia{d}" for d in sorted(set(devices))]
+    devs, rules = [], []
+    for p in paths:
+        try:
+            s = stat(p)
+        except OSError:
+            continue
+        if not st_mod.S_ISCHR(s.st_mode):
+            continue
+        major, minor = os.major(s.st_rdev), os.minor(s.st_rdev)
+        devs.append({"path": p, "type": "c", "major": major, "minor": minor, "fileMode": 0o666, "uid": 0, "gid": 0})
+        rules.append({"allow": True, "type": "c", "major": major, "minor": minor, "access": "rw"})
+    return devs, rules
 
 
 def _atomic_write(path: str, data: bytes, mode: int = 0o644) -> None:
@@ -83,7 +106,7 @@ def _atomic_write(path: str, data: bytes, mode: int = 0o644) -> None:
         pass
 
 
-def Mount(model: gpupool.Model, device: int, container_dir: str) -> MountSpec:
+def Mount(model: gpupool.Model, device: int, container_dir: str, with_devices: bool = False, stat=os.stat) -> MountSpec:
     """Export `device`'s pool for one agent container: write the manifest + IPC handle under
     `<container_dir>/gpupool/` and describe the read-only bind mount and env that expose them."""
     handle, manifest = model.export(device)
@@ -91,11 +114,12 @@ def Mount(model: gpupool.Model, device: int, container_dir: str) -> MountSpec:
     os.makedirs(host_dir, mode=0o750, exist_ok=True)
     _atomic_write(os.path.join(host_dir, "manifest.json"), json.dumps(manifest, separators=(",", ":")).encode())
     _atomic_write(os.path.join(host_dir, "ipc.handle"), handle, 0o640)
+    devs, rules = device_nodes([device], stat) if with_devices else ([], [])
     return MountSpec(
         mounts=[{"destination": CONTAINER_GPUPOOL_DIR, "type": "bind", "source": host_dir, "options": ["rbind", "ro"]}],
         env=[f"{ENV_MANIFEST}={CONTAINER_GPUPOOL_DIR}/manifest.json", f"{ENV_IPC_HANDLE}={CONTAINER_GPUPOOL_DIR}/ipc.handle",
              f"{ENV_DEVICE}={device}"],
-        host_dir=host_dir,
+        host_dir=host_dir, devices=devs, device_cgroup=rules,
     )
 
 

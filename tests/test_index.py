@@ -222,3 +222,64 @@ def test_weight_map_inconsistency_rejected(native, tmp_path):
     json.dump(doc, open(idx, "w"))
     with pytest.raises(gpupool.ErrFormat, match="weight_map"):
         gpupool.index(str(d))
+
+
+def test_unicode_and_escaped_tensor_names(native, tmp_path):
+    """The header is JSON: names may carry escapes and non-ASCII text; product, oracle and safetensors must agree."""
+    from safetensors import safe_open
+    names = ["plain", "with space", "quote\"d", "back\\slash", "tab\there", "unicode-é-漢字-😀", "slash/inside", "escé"]
+    hdr, off = {}, 0
+    for i, n in enumerate(names):
+        hdr[n] = {"dtype": "U8", "shape": [i + 1], "data_offsets": [off, off + i + 1]}
+        off += i + 1
+    p = str(tmp_path / "names.safetensors")
+    # ensure_ascii=True makes json emit \\uXXXX escapes (incl. a surrogate pair for the emoji): exercises the parser
+    raw = json.dumps(hdr, ensure_ascii=True).encode()
+    helpers.write_raw_safetensors(p, raw, bytes(off))
+    recs, _ = both(p)
+    assert sorted(r["name"] for r in recs) == sorted(names)
+    with safe_open(p, "np") as f:
+        assert sorted(f.keys()) == sorted(names)
+    q = str(tmp_path / "names_utf8.safetensors")
+    helpers.write_raw_safetensors(q, json.dumps(hdr, ensure_ascii=False).encode("utf-8"), bytes(off))
+    assert [r["name"] for r in gpupool.index(q)] == [r["name"] for r in recs]
+
+
+def test_limits_name_length_and_rank(native, tmp_path):
+    p = str(tmp_path / "long.safetensors")
+    helpers.write_raw_safetensors(p, {"n" * 255: {"dtype": "U8", "shape": [1], "data_offsets": [0, 1]}}, b"\0")
+    assert len(gpupool.index(p)[0]["name"]) == 255
+    helpers.write_raw_safetensors(p, {"n" * 256: {"dtype": "U8", "shape": [1], "data_offsets": [0, 1]}}, b"\0")
+    with pytest.raises(gpupool.ErrUnsupported, match="name longer"):
+        gpupool.index(p)
+    helpers.write_raw_safetensors(p, {"t": {"dtype": "U8", "shape": [1] * 8, "data_offsets": [0, 1]}}, b"\0")
+    assert gpupool.index(p)[0]["shape"] == [1] * 8
+    helpers.write_raw_safetensors(p, {"t": {"dtype": "U8", "shape": [1] * 9, "data_offsets": [0, 1]}}, b"\0")
+    with pytest.raises(gpupool.ErrUnsupported, match="dims"):
+        gpupool.index(p)
+
+
+def test_shape_overflow_and_negative_numbers_rejected(native, tmp_path):
+    p = str(tmp_path / "ovf.safetensors")
+    helpers.write_raw_safetensors(p, {"t": {"dtype": "F32", "shape": [2 ** 40, 2 ** 40], "data_offsets": [0, 4]}}, b"\0" * 4)
+    with pytest.raises(gpupool.ErrFormat):
+        gpupool.index(p)
+    helpers.write_raw_safetensors(p, b'{"t":{"dtype":"F32","shape":[-1],"data_offsets":[0,4]}}', b"\0" * 4)
+    with pytest.raises(gpupool.ErrFormat):
+        gpupool.index(p)
+    helpers.write_raw_safetensors(p, b'{"t":{"dtype":"F32","shape":[1.5],"data_offsets":[0,4]}}', b"\0" * 4)
+    with pytest.raises(gpupool.ErrFormat):
+        gpupool.index(p)
+
+
+def test_split_gguf_directory(native, tmp_path):
+    d = tmp_path / "split"
+    os.makedirs(d)
+    synth.write_gguf(str(d / "m-00001-of-00002.gguf"), [("a.weight", "Q4_K", [4, 256]), ("b.weight", "F32", [7])], 1)
+    synth.write_gguf(str(d / "m-00002-of-00002.gguf"), [("c.weight", "Q6_K", [2, 256]), ("d.weight", "Q8_0", [3, 64])], 2)
+    recs, shards = both(str(d))
+    assert len(shards) == 2 and [r["shard"] for r in recs] == [0, 0, 1, 1]
+    assert {r["name"]: r["dtype"] for r in recs} == {"a.weight": "Q4_K", "b.weight": "F32", "c.weight": "Q6_K", "d.weight": "Q8_0"}
+    synth.write_gguf(str(d / "m-00003-of-00003.gguf"), [("a.weight", "F32", [1])], 3)  # duplicate name across shards
+    with pytest.raises(gpupool.ErrFormat, match="more than one shard"):
+        gpupool.index(str(d))
