@@ -979,8 +979,6 @@ void model_stage_resident(kk_model* m) {
       L.src_bytes += ch.src_bytes;
       L.out_bytes += ch.out_bytes;
     }
-    // tile_begin above was offset by the launch's tile count *before* adding this chunk: fix ordering
-    // (n_tiles is bumped after the chunk's segments are rebased, so the rebasing is already correct).
     if (!segs.empty()) {
       KK_CUDA(cudaMalloc((void**)&R.d_segs, segs.size() * sizeof(KKSeg)));
       KK_CUDA(cudaMemcpy(R.d_segs, segs.data(), segs.size() * sizeof(KKSeg), cudaMemcpyHostToDevice));

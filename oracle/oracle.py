@@ -11,7 +11,7 @@ reference code, call site, test or golden vector for this path.  The oracle is t
 the *published file formats*, pinned instead against the format owners' own libraries installed in the
 image:
 
-* safetensors 0.7.0  — header layout, validation rules  (``tests/test_oracle_index.py``)
+* safetensors 0.7.0  — header layout, validation rules  (``tests/test_index.py``)
 * gguf 0.19.0        — GGUF v3 header, ``quants.Q4_K/Q6_K/Q8_0.dequantize_blocks`` (gguf/quants.py:475-521, 552-572, 395-401)
 * torch 2.11         — fp32/fp16 -> bf16 round-to-nearest-even
 

@@ -55,6 +55,26 @@ def _worker(rank, world, port, ckpt, mode, out_dir):
             sizes = [None] * world
             dist.all_gather_object(sizes, layout["pool_bytes"])
             assert len(set(sizes)) == 1, "equal slices -> equal pool sizes on every rank"
+            # same load with the NVLink row exchange: this rank ingests whole rows of the row-parallel tensors and deals
+            # column slices to every rank; summing what all ranks dealt to pool r must give rank r's oracle pool
+            xplan = gpupool.plan_describe(ckpt, mode=mode, flags=gpupool.LOAD_SCATTER_EXCHANGE, n_parts=world, chunk_bytes=1 << 20)
+            n = layout["pool_bytes"]
+            ex = {r: (np.zeros(n, np.uint8), np.zeros(n, bool)) for r in range(world)}
+            own, own_mask = helpers.emulate_part(xplan, rank, n, exchange=ex)
+            ex[rank][0][own_mask] = own[own_mask]
+            ex[rank][1][own_mask] = True
+            for r in range(world):
+                data = torch.from_numpy(np.where(ex[r][1], ex[r][0], 0).astype(np.int32))
+                cover = torch.from_numpy(ex[r][1].astype(np.int32))
+                dist.all_reduce(data)
+                dist.all_reduce(cover)
+                if r == rank:
+                    assert (cover.numpy() == helpers.expected_mask(pl, len(exp)).astype(np.int32)).all(), "every pool byte dealt exactly once"
+                    assert (data.numpy().astype(np.uint8) == exp).all()
+            src = torch.tensor([xplan["parts"][rank]["src_bytes"]], dtype=torch.int64)
+            dist.all_reduce(src)
+            repl = sum(r_["nbytes"] for r_ in recs if oracle.slice_dim(r_, world) is None)
+            assert int(src.item()) == xplan["file_bytes"] + (world - 1) * repl, "row-parallel bytes are read by exactly one rank"
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
