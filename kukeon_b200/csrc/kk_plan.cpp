@@ -225,6 +225,7 @@ uint32_t scatter_slice_dim(const TensorRec& t, int n_parts) {
     for (auto s : kDim0)
       if (ends_with(n, s) && !contains(n, "norm")) dim = 0;
   if (dim == kNoSlice) return kNoSlice;
+  if (t.shape[0] == 0 || t.shape[1] == 0) return kNoSlice;  // empty tensors are "replicated" (nothing to slice)
   if (t.shape[dim] % (uint64_t)n_parts != 0) return kNoSlice;
   const DtypeInfo* di = dtype_info(t.dtype);
   if (di->block_elems > 1) {

@@ -424,7 +424,7 @@ def slice_dim(rec: dict, n_parts: int):
         dim = 1
     elif any(n.endswith(s) for s in SCATTER_DIM0) and "norm" not in n:
         dim = 0
-    if dim is None or rec["shape"][dim] % n_parts:
+    if dim is None or 0 in rec["shape"] or rec["shape"][dim] % n_parts:
         return None
     if rec["dtype"] in ("F4", "F6_E2M3", "F6_E3M2"):
         return None

@@ -598,3 +598,48 @@ def test_concurrent_loads_of_different_checkpoints_share_the_staging_ring_safely
         for m in out:
             if m is not None:
                 m.release()
+
+
+def test_gguf_alignment_8_puts_quant_blocks_off_16_byte_boundaries(pool, tmp_path):
+    """general.alignment = 8: block-quantised tensors start 8 bytes off a 16-byte boundary, so the kernel's byte-assembled
+    shared-memory reads (not the vector ones) feed the dequantisers."""
+    from tests.test_plan import q4km_tensors
+    p = str(tmp_path / "a8.gguf")
+    tensors = [("pad.weight", "F32", [2])] + q4km_tensors(hidden=256, ffn=512, layers=1, vocab=256) + [("tail.weight", "F16", [3])]
+    synth.write_gguf(p, tensors, 21, alignment=8)
+    recs = gpupool.index(p)
+    assert any(r["dtype"] == "Q4_K" and r["file_offset"] % 16 == 8 for r in recs)
+    assert any(r["dtype"] == "Q6_K" and r["file_offset"] % 16 == 8 for r in recs)
+    load_and_check(pool, p)
+
+
+def test_error_paths_through_the_abi(pool, tmp_path):
+    import ctypes as C
+    p = str(tmp_path / "m.safetensors")
+    helpers.mixed_safetensors(p)
+    m = pool.load(p, flags=gpupool.LOAD_KEEP_F32)
+    try:
+        L = gpupool.lib()
+        assert m.placements("b.f32")[0].dtype == "F32" and m.placements("c.f16")[0].dtype == "BF16"
+        shards, recs = oracle.index_path(p)
+        assert_pool_matches(m, 0, shards, recs, flags=gpupool.LOAD_KEEP_F32)
+        with pytest.raises(gpupool.ErrNotFound):
+            m.placements("no.such.tensor")
+        with pytest.raises(gpupool.ErrInvalid):
+            m.read(0, m.info()["pool_bytes"], 16)
+        with pytest.raises(gpupool.ErrInvalid):
+            m.checksum(0, 4, 16)  # offset must be a multiple of 8
+        with pytest.raises(gpupool.ErrInvalid):
+            m.export(3)           # device without a pool of this model
+        small = C.create_string_buffer(8)
+        assert L.kk_export(m._h, 0, None, small, 8) == -9 and b"manifest needs" in L.kk_last_error()   # KK_ERANGE
+        assert L.kk_stats(m._h, small, 8) == -9
+        with pytest.raises(gpupool.ErrState):
+            m.peer_attach(1, b"\0" * 64)  # not a multi-process model
+        with pytest.raises(gpupool.ErrState):
+            m.convert_local()             # not a RAW model
+        m.acquire()
+        m.release()
+        assert m.info()["refcount"] == 1
+    finally:
+        m.release()

@@ -219,3 +219,18 @@ def test_bad_arguments(native, tmp_path):
         gpupool.plan_describe(p, mode=7)
     with pytest.raises(gpupool.ErrInvalid):
         gpupool.plan_describe(p, mode=gpupool.MODE_BROADCAST, n_parts=9)
+
+
+def test_scatter_of_empty_2d_tensors_does_not_divide_by_zero(native, tmp_path):
+    """Found by tools/fuzz (UBSan): a [0, C] tensor with a column-parallel name used to divide by its row count."""
+    p = str(tmp_path / "empty.safetensors")
+    hdr = {"model.layers.0.self_attn.q_proj.weight": {"dtype": "BF16", "shape": [0, 64], "data_offsets": [0, 0]},
+           "model.layers.0.self_attn.o_proj.weight": {"dtype": "BF16", "shape": [8, 0], "data_offsets": [0, 0]},
+           "model.layers.0.mlp.down_proj.weight": {"dtype": "BF16", "shape": [8, 16], "data_offsets": [0, 256]}}
+    helpers.write_raw_safetensors(p, hdr, bytes(range(256)))
+    for flags in (0, 0x8):
+        plan = gpupool.plan_describe(p, mode=gpupool.MODE_SCATTER, flags=flags, n_parts=4, chunk_bytes=1 * MB)
+        lay = {t["name"]: t for t in plan["layouts"][2]["tensors"]}
+        assert lay["model.layers.0.self_attn.q_proj.weight"]["slice_dim"] is None and lay["model.layers.0.self_attn.q_proj.weight"]["nbytes"] == 0
+        assert lay["model.layers.0.mlp.down_proj.weight"]["slice_dim"] == 1
+    run_case(p, mode=gpupool.MODE_SCATTER, n_parts=4, chunk=1 * MB)
