@@ -279,7 +279,7 @@ Plan build_plan(Index index, int mode, uint32_t flags, int n_parts, uint64_t chu
         pc.oi = {op, pdt, es, oes, KK_T_ROWS};
         pc.transpose = true;
         pc.row_src_bytes = C * es;
-        pc.units = R;
+        pc.units = C ? R : 0;  // [R, 0]: nothing to move (found by the hypothesis test)
         pc.p0 = (uint32_t)C;
         pc.p1 = (uint32_t)R;
         pc.file_off = t.file_offset;

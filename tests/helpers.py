@@ -24,16 +24,24 @@ def emulate_part(plan: dict, part: int, pool_bytes: int, exchange: dict | None =
         for ch in plan["parts"][part]["chunks"]:
             buf = np.zeros(ch["buf_bytes"] + 64, np.uint8)
             fh = fhs[ch["shard"]]
+            covered = np.zeros(ch["buf_bytes"], bool)
             for fo, ln, bo in ch["reads"]:
+                assert bo + ln <= ch["buf_bytes"], "read lands outside the chunk buffer"
+                assert not covered[bo:bo + ln].any(), "two reads overlap in the chunk buffer"
+                covered[bo:bo + ln] = True
                 fh.seek(fo)
                 raw = fh.read(ln)
-                assert len(raw) == ln
+                assert len(raw) == ln, "read runs past the end of the shard"
                 buf[bo:bo + ln] = np.frombuffer(raw, np.uint8)
             tiles = 0
             for sg in ch["segs"]:
                 assert sg["tile_begin"] == tiles, "tile_begin must be the running tile count of the chunk"
                 op, so, do, u = sg["op"], sg["src_off"], sg["dst_off"], sg["units"]
                 assert do % 16 == 0
+                src_bytes = {OP_COPY: u, OP_F32: 4 * u, OP_F16: 2 * u, OP_Q4K: 144 * u, OP_Q8_0: 34 * u, OP_Q6K: 210 * u, OP_ROWSPLIT: u,
+                             OP_T_F32_BF16: 4 * u * sg["p0"], OP_T_B32: 4 * u * sg["p0"], OP_T_F16_BF16: 2 * u * sg["p0"], OP_T_B16: 2 * u * sg["p0"]}[op]
+                assert so + src_bytes <= ch["buf_bytes"], "segment reads past the bytes staged for its chunk"
+                assert covered[so:so + src_bytes].all(), "segment consumes bytes no read put there"
                 if op == OP_ROWSPLIT:
                     row_bytes, w, r0, done = sg["p0"], sg["p1"], sg["p2"], sg["p3"]
                     assert exchange is not None and row_bytes % w == 0
@@ -84,6 +92,7 @@ def emulate_part(plan: dict, part: int, pool_bytes: int, exchange: dict | None =
                     mask[do:do + C * R * oes].reshape(C, R, oes)[:, r0:r0 + u, :] = True
                     tiles += -(-u // 32) * -(-C // 128)
                     continue
+                assert do + out.size <= pool_bytes, "segment writes past the end of the pool"
                 assert not mask[do:do + out.size].any(), "segment overlaps an earlier one"
                 pool[do:do + out.size] = out
                 mask[do:do + out.size] = True
