@@ -171,9 +171,7 @@ def cpu_port_setup(path: str, sample_bytes: int):
     shards, recs = oracle.index_path(path)
     plan, total = oracle.plan_pool(recs)
     jobs, src = coracle.make_jobs(recs, plan, job_bytes=8 << 20, max_src_bytes=sample_bytes)
-    out_of = {coracle.OP_COPY: lambda n: n, coracle.OP_F32_BF16: lambda n: n // 2, coracle.OP_F16_BF16: lambda n: n,
-              coracle.OP_Q4K_BF16: lambda n: n // 144 * 512, coracle.OP_Q8_0_BF16: lambda n: n // 34 * 64, coracle.OP_Q6K_BF16: lambda n: n // 210 * 512}
-    hi = max((j.dst_off + out_of[j.op](j.nbytes) for j in jobs), default=0)
+    hi = max((j.dst_off + j.nbytes // coracle._UNITS[j.op][0] * coracle._UNITS[j.op][1] for j in jobs), default=0)
     pool = np.empty(min(total, hi) + 4096, np.uint8)
     pool[::4096] = 0  # first touch outside the timed region
     return coracle, shards, jobs, src, pool

@@ -1,0 +1,219 @@
+// Block dequantisers of kk_convert_kernel's consumer warps (every GGUF block type except Q4_K, whose four-blocks-per-
+// warp variant trades lanes through __shfl_sync and lives in kk_kernels.cu).
+//
+// Each function is written from the point of view of ONE lane and touches nothing but the primitives below, which the
+// including translation unit provides:
+//     uint32_t lds8(a) / lds16(a) / lds32(a)     loads from the staged tile (shared-memory byte address; 16- and 32-bit
+//                                                forms need natural alignment)
+//     float    kk_h2f(h16)                       fp16 bit pattern -> float (exact)
+//     float    __fmul_rn / __fadd_rn / __fsub_rn one IEEE fp32 operation each — never contracted into an FMA, so results are
+//                                                bit-identical to gguf-py's numpy arithmetic (oracle/oracle.py)
+//     uint32_t pack_bf16x2(a, b)                 two floats -> bf16x2, RNE, NaN -> 0x7FFF
+//     void     store16_all(D, off, uint4)        16 output bytes to every destination pool
+//     Dsts, uint4, make_uint4, kConsumerWarps, KK_DQ_DEV (function attributes)
+// kk_kernels.cu binds them to PTX; tests/emul/kk_dequant_emul.cpp binds them to plain C++ (with alignment and
+// write-once checks) and runs all 16 x 32 lanes in a loop, so the lane -> element index arithmetic of exactly this source
+// is checked against the oracle on the CPU test tier.  That harness is test infrastructure: the product has no CPU path.
+//
+// Lane mapping, same for every type: a lane produces 8 consecutive weights = one 16-byte bf16 store; a warp iteration
+// produces 512 contiguous output bytes (256-weight super-blocks: one block; 32-weight blocks: eight blocks).
+#pragma once
+#include "kk_ops.h"
+
+// ---- loads of any alignment (blocks of 18..210 bytes are only 2-byte aligned inside a tile, or not at all) -----------
+KK_DQ_DEV uint32_t lds32_bytes(uint32_t a) { return lds8(a) | (lds8(a + 1) << 8) | (lds8(a + 2) << 16) | (lds8(a + 3) << 24); }
+KK_DQ_DEV uint32_t lds32_h(uint32_t a) {  // a is 2-byte aligned (falls back to bytes otherwise)
+  if (a & 1u) return lds32_bytes(a);
+  return lds16(a) | (lds16(a + 2) << 16);
+}
+KK_DQ_DEV uint32_t lds16_any(uint32_t a) { return (a & 1u) ? (lds8(a) | (lds8(a + 1) << 8)) : lds16(a); }
+KK_DQ_DEV uint32_t lds32_any(uint32_t a) {
+  if ((a & 3u) == 0) return lds32(a);
+  return lds32_h(a);
+}
+KK_DQ_DEV float lds_f16(uint32_t a) { return kk_h2f(lds16_any(a)); }
+KK_DQ_DEV void store_bf16x8(const Dsts& D, uint64_t off, const float (&y)[8]) {
+  store16_all(D, off, make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7])));
+}
+
+// Q8_0 block (34 B): d f16 | qs[32] int8 -> 32 bf16, y = q * d in fp32 (gguf/quants.py Q8_0.dequantize_blocks).
+// Lane l of a warp handles elements 8*(l&3)..+8 of block (l>>2): 8 blocks and 512 contiguous output bytes per iteration.
+KK_DQ_DEV void consume_q8_0(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
+  for (uint32_t b0 = (uint32_t)cwarp * 8u; b0 < nblk; b0 += kConsumerWarps * 8u) {
+    const uint32_t b = b0 + (uint32_t)(lane >> 2);
+    if (b < nblk) {
+      const uint32_t blk = pay + b * KK_Q8_0_BLOCK_BYTES;
+      const float d = kk_h2f(lds16_any(blk));
+      const uint32_t qa = blk + 2u + 8u * (uint32_t)(lane & 3);
+      const uint32_t q0 = lds32_h(qa), q1 = lds32_h(qa + 4);
+      float y[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int q = (int)(signed char)(((e < 4 ? q0 : q1) >> (8 * (e & 3))) & 0xFFu);
+        y[e] = __fmul_rn((float)q, d);
+      }
+      store16_all(D, dst_off + (uint64_t)b * 64u + (uint32_t)(lane & 3) * 16u,
+                  make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7])));
+    }
+  }
+}
+
+// Q6_K super-block (210 B): ql[128] | qh[64] | scales[16] int8 | d f16 -> 256 bf16 (gguf/quants.py:552-572):
+// element e = 32*g + i (g = 0..7): low nibble source ql[64*(g/4) + 32*(g%2) + i] >> 4*((g%4)/2), high 2 bits
+// qh[32*(g/4) + i] >> 2*(g%4); q = (lo | hi<<4) - 32; y = (d * scales[e/16]) * q, both products rounded to fp32.
+// Lane l handles the 8 elements e = 8l..8l+7 (g = l>>2, i = 8*(l&3)..+8): one block, 512 output bytes per warp iteration.
+KK_DQ_DEV void consume_q6k(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
+  const int g = lane >> 2, i0 = 8 * (lane & 3);
+  const uint32_t ql_off = 64u * (uint32_t)(g >> 2) + 32u * (uint32_t)(g & 1) + (uint32_t)i0;
+  const uint32_t qh_off = 128u + 32u * (uint32_t)(g >> 2) + (uint32_t)i0;
+  const int lsh = 4 * ((g & 3) >> 1), hsh = 2 * (g & 3);
+  for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
+    const uint32_t blk = pay + b * KK_Q6K_BLOCK_BYTES;
+    const float d = kk_h2f(lds16_any(blk + 208u));
+    const int sc = (int)(signed char)lds8(blk + 192u + (uint32_t)(lane >> 1));
+    const float dsc = __fmul_rn(d, (float)sc);
+    const uint32_t l0 = lds32_h(blk + ql_off), l1 = lds32_h(blk + ql_off + 4);
+    const uint32_t h0 = lds32_h(blk + qh_off), h1 = lds32_h(blk + qh_off + 4);
+    float y[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const uint32_t lw = e < 4 ? l0 : l1, hw = e < 4 ? h0 : h1;
+      const uint32_t lo = (lw >> (8 * (e & 3) + lsh)) & 0xFu;
+      const uint32_t hi = (hw >> (8 * (e & 3) + hsh)) & 0x3u;
+      const int q = (int)(lo | (hi << 4)) - 32;
+      y[e] = __fmul_rn(dsc, (float)q);
+    }
+    store16_all(D, dst_off + (uint64_t)b * 512u + (uint32_t)lane * 16u,
+                make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7])));
+  }
+}
+
+// ---- §8(f4): the 32-weight legacy blocks ------------------------------------------------------------------------------
+// Q4_0 (18 B): d f16 | qs[16]                      y = d * (q4 - 8)            (gguf/quants.py:220-231)
+// Q4_1 (20 B): d f16 | m f16 | qs[16]              y = (d * q4) + m            (gguf/quants.py:254-267)
+// Q5_0 (22 B): d f16 | qh u32 | qs[16]             y = d * (q5 - 16)           (gguf/quants.py:291-308)
+// Q5_1 (24 B): d f16 | m f16 | qh u32 | qs[16]     y = (d * q5) + m            (gguf/quants.py:333-352)
+// Element e < 16 is the LOW nibble of qs[e], element e >= 16 the HIGH nibble of qs[e-16]; bit 4 of element e is bit e of qh.
+// Lane l handles elements e0 = 8*(l&3) .. e0+7 of block (l>>2): they come from qs[e0 % 16 .. +8] (one nibble each) and
+// the byte (qh >> e0) & 0xFF.  Eight blocks and 512 contiguous output bytes per warp iteration.
+template <uint32_t BYTES, bool HAS_M, bool HAS_QH>
+KK_DQ_DEV void consume_legacy32(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
+  constexpr uint32_t kQhOff = HAS_M ? 4u : 2u;
+  constexpr uint32_t kQsOff = kQhOff + (HAS_QH ? 4u : 0u);
+  static_assert(kQsOff + 16u == BYTES, "legacy block layout");
+  const uint32_t e0 = 8u * (uint32_t)(lane & 3);
+  const uint32_t q_off = kQsOff + (e0 & 15u);
+  const uint32_t nsh = (e0 >> 4) * 4u;  // 0: low nibbles (elements 0..15), 4: high nibbles (elements 16..31)
+  for (uint32_t b0 = (uint32_t)cwarp * 8u; b0 < nblk; b0 += kConsumerWarps * 8u) {
+    const uint32_t b = b0 + (uint32_t)(lane >> 2);
+    if (b < nblk) {
+      const uint32_t blk = pay + b * BYTES;
+      const float d = lds_f16(blk);
+      const float m = HAS_M ? lds_f16(blk + 2u) : 0.f;
+      const uint32_t q0 = (lds32_any(blk + q_off) >> nsh) & 0x0F0F0F0Fu;
+      const uint32_t q1 = (lds32_any(blk + q_off + 4u) >> nsh) & 0x0F0F0F0Fu;
+      const uint32_t hbits = HAS_QH ? ((lds32_any(blk + kQhOff) >> e0) & 0xFFu) : 0u;
+      float y[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        int q = (int)(((e < 4 ? q0 : q1) >> (8 * (e & 3))) & 0xFu);
+        if (HAS_QH) q |= (int)((hbits >> e) & 1u) << 4;
+        if (HAS_M) y[e] = __fadd_rn(__fmul_rn(d, (float)q), m);
+        else y[e] = __fmul_rn(d, (float)(q - (HAS_QH ? 16 : 8)));
+      }
+      store_bf16x8(D, dst_off + (uint64_t)b * 64u + (uint32_t)(lane & 3) * 16u, y);
+    }
+  }
+}
+
+// ---- §8(f4): the remaining 256-weight K super-blocks; lane l handles elements 8l..8l+7, one block per warp iteration --
+// Q2_K (84 B): scales[16] | qs[64] | d f16 | dmin f16  (gguf/quants.py:404-428).  Element e = 128h + 32s + i (h<2, s<4, i<32):
+// q = (qs[32h+i] >> 2s) & 3; 16-weight sub-block j = e/16: y = (d*(scales[j]&15))*q - dmin*(scales[j]>>4).
+// Lane l: h = l>>4, s = (l>>2)&3, i = 8*(l&3)..+8, j = l>>1.
+KK_DQ_DEV void consume_q2k(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
+  const uint32_t q_off = 16u + 32u * (uint32_t)(lane >> 4) + 8u * (uint32_t)(lane & 3);
+  const uint32_t sh = 2u * (uint32_t)((lane >> 2) & 3);
+  for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
+    const uint32_t blk = pay + b * KK_Q2K_BLOCK_BYTES;
+    const float d = lds_f16(blk + 80u), dmin = lds_f16(blk + 82u);
+    const uint32_t sc = lds8(blk + (uint32_t)(lane >> 1));
+    const float dl = __fmul_rn(d, (float)(sc & 0xFu));
+    const float ml = __fmul_rn(dmin, (float)(sc >> 4));
+    const uint32_t q0 = (lds32_any(blk + q_off) >> sh) & 0x03030303u;
+    const uint32_t q1 = (lds32_any(blk + q_off + 4u) >> sh) & 0x03030303u;
+    float y[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const uint32_t q = ((e < 4 ? q0 : q1) >> (8 * (e & 3))) & 0x3u;
+      y[e] = __fsub_rn(__fmul_rn(dl, (float)q), ml);
+    }
+    store_bf16x8(D, dst_off + (uint64_t)b * 512u + (uint32_t)lane * 16u, y);
+  }
+}
+
+// Q3_K (110 B): hmask[32] | qs[64] | scales[12] | d f16  (gguf/quants.py:431-472).  Element e = 32g + i (g<8, i<32):
+// low bits (qs[32*(g/4) + i] >> 2*(g%4)) & 3; q = low - 4 when bit g of hmask[i] is CLEAR, else low.  Scale k = e/16 is 6 bits:
+// low 4 = scales[k] & 15 (k<8) or scales[k-8] >> 4 (k>=8), high 2 = (scales[8 + k%4] >> 2*(k/4)) & 3, value - 32.
+// y = (d*scale_k)*q.  Lane l: g = l>>2, i = 8*(l&3)..+8, k = l>>1.
+KK_DQ_DEV void consume_q3k(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
+  const uint32_t g = (uint32_t)(lane >> 2), i0 = 8u * (uint32_t)(lane & 3), k = (uint32_t)(lane >> 1);
+  const uint32_t q_off = 32u + 32u * (g >> 2) + i0;
+  const uint32_t sh = 2u * (g & 3u);
+  const uint32_t lo_off = 96u + (k & 7u), lo_sh = (k >> 3) * 4u;
+  const uint32_t hi_off = 104u + (k & 3u), hi_sh = 2u * (k >> 2);
+  for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
+    const uint32_t blk = pay + b * KK_Q3K_BLOCK_BYTES;
+    const float d = lds_f16(blk + 108u);
+    const uint32_t lo4 = (lds8(blk + lo_off) >> lo_sh) & 0xFu;
+    const uint32_t hi2 = (lds8(blk + hi_off) >> hi_sh) & 0x3u;
+    const float dl = __fmul_rn(d, (float)((int)(lo4 | (hi2 << 4)) - 32));
+    const uint32_t q0 = (lds32_any(blk + q_off) >> sh) & 0x03030303u;
+    const uint32_t q1 = (lds32_any(blk + q_off + 4u) >> sh) & 0x03030303u;
+    const uint32_t h0 = (lds32_any(blk + i0) >> g) & 0x01010101u;
+    const uint32_t h1 = (lds32_any(blk + i0 + 4u) >> g) & 0x01010101u;
+    float y[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int lo = (int)(((e < 4 ? q0 : q1) >> (8 * (e & 3))) & 0x3u);
+      const int set = (int)(((e < 4 ? h0 : h1) >> (8 * (e & 3))) & 0x1u);
+      y[e] = __fmul_rn(dl, (float)(lo - ((set ^ 1) << 2)));
+    }
+    store_bf16x8(D, dst_off + (uint64_t)b * 512u + (uint32_t)lane * 16u, y);
+  }
+}
+
+// Q5_K (176 B): d f16 | dmin f16 | scales[12] | qh[32] | qs[128]  (gguf/quants.py:525-548).  Sub-block j (32 weights), element i:
+// q = ((qs[32*(j/2) + i] >> 4*(j%2)) & 15) | (((qh[i] >> j) & 1) << 4); (scale, min) of sub-block j packed as in Q4_K;
+// y = (d*sc_j)*q - dmin*m_j.  Lane l: j = l>>2, i = 8*(l&3)..+8.
+KK_DQ_DEV void consume_q5k(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
+  const uint32_t j = (uint32_t)(lane >> 2), i0 = 8u * (uint32_t)(lane & 3);
+  const uint32_t q_off = 48u + 32u * (j >> 1) + i0;
+  const uint32_t nsh = 4u * (j & 1u);
+  for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
+    const uint32_t blk = pay + b * KK_Q5K_BLOCK_BYTES;
+    const float d = lds_f16(blk), dmin = lds_f16(blk + 2u);
+    const uint32_t s = blk + 4u;
+    uint32_t sc, mn;
+    if (j < 4u) {
+      sc = lds8(s + j) & 63u;
+      mn = lds8(s + j + 4u) & 63u;
+    } else {
+      const uint32_t hi = lds8(s + j + 4u);
+      sc = (hi & 0xFu) | ((lds8(s + j - 4u) >> 6) << 4);
+      mn = (hi >> 4) | ((lds8(s + j) >> 6) << 4);
+    }
+    const float dsc = __fmul_rn(d, (float)sc);
+    const float dmn = __fmul_rn(dmin, (float)mn);
+    const uint32_t q0 = (lds32_any(blk + q_off) >> nsh) & 0x0F0F0F0Fu;
+    const uint32_t q1 = (lds32_any(blk + q_off + 4u) >> nsh) & 0x0F0F0F0Fu;
+    const uint32_t h0 = (lds32_any(blk + 16u + i0) >> j) & 0x01010101u;
+    const uint32_t h1 = (lds32_any(blk + 16u + i0 + 4u) >> j) & 0x01010101u;
+    float y[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const uint32_t q = (((e < 4 ? q0 : q1) >> (8 * (e & 3))) & 0xFu) | ((((e < 4 ? h0 : h1) >> (8 * (e & 3))) & 0x1u) << 4);
+      y[e] = __fsub_rn(__fmul_rn(dsc, (float)q), dmn);
+    }
+    store_bf16x8(D, dst_off + (uint64_t)b * 512u + (uint32_t)lane * 16u, y);
+  }
+}

@@ -12,6 +12,7 @@
 //       Q4_K -> BF16      : one warp per 256-weight super-block; the 8 (scale,min) pairs are decoded once
 //                           and handed to the lanes with __shfl_sync; nibbles become floats with a PRMT
 //                           + FADD magic-number trick; every lane stores 16 B of bf16;
+//       other GGUF quants : Q4_0/Q4_1/Q5_0/Q5_1/Q8_0/Q2_K/Q3_K/Q5_K/Q6_K, one lane per 8 weights (kk_dequant.cuh);
 //       2-D transposes    : shared-memory tile transpose (GPT-2 Conv1D weights).
 //   Every output vector is stored to n_dst pools; dst[1..] are NVLink peer mappings, so conversion and
 //   broadcast are ONE kernel and the source bytes are read from HBM exactly once.
@@ -261,6 +262,21 @@ __device__ __forceinline__ void consume_f16(const Dsts& D, uint32_t pay, uint32_
   if (ctid < (int)tail) store2_all(D, dst_off + 2ull * (base + ctid), to_bf16(lds_f16_any(pay + 2 * (base + ctid))));
 }
 
+// Q8_0, Q6_K and the §8(f4) legacy / K quants: per-lane device functions shared with the host emulation harness.
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float kk_h2f(uint32_t h) { return __half2float(__ushort_as_half((unsigned short)h)); }
+#define KK_DQ_DEV __device__ __forceinline__
+#include "kk_dequant.cuh"
+
 // Q4_K super-block (144 B): d f16 | dmin f16 | scales[12] | qs[128]  ->  256 bf16.
 // y = (d*sc_j)*q - (dmin*m_j), every product and the difference rounded to fp32 separately (no FMA
 // contraction) so the result is bit-identical to the oracle's gguf-py restatement, then RNE to bf16.
@@ -269,10 +285,6 @@ __device__ __forceinline__ void consume_f16(const Dsts& D, uint32_t pay, uint32_
 // sub-block (l & 7) of block (l >> 3) — so the unpack runs once per four blocks instead of once per block —
 // and __shfl_sync hands every lane the pair of the sub-block its 8 outputs belong to.  The four blocks'
 // dependency chains are independent and fully unrolled (ILP hides the ALU latency with only 2 warps/SMSP).
-__device__ __forceinline__ uint32_t lds32_bytes(uint32_t a) {
-  return lds8(a) | (lds8(a + 1) << 8) | (lds8(a + 2) << 16) | (lds8(a + 3) << 24);
-}
-
 template <bool ALIGNED>
 __device__ __forceinline__ void q4k_quad(const Dsts& D, uint32_t pay, uint32_t b0, uint32_t nb, uint64_t dst_off, int lane) {
   // --- decode: lane -> (block b0 + min(lane>>3, nb-1), sub-block lane&7)
@@ -332,70 +344,6 @@ __device__ __forceinline__ void consume_q4k(const Dsts& D, uint32_t pay, uint32_
     const uint32_t nb = min(4u, nblk - b0);
     if (al) q4k_quad<true>(D, pay, b0, nb, dst_off, lane);
     else q4k_quad<false>(D, pay, b0, nb, dst_off, lane);
-  }
-}
-
-// Blocks of 34 and 210 bytes are only 2-byte aligned inside a tile: assemble words from 16-bit shared loads.
-__device__ __forceinline__ uint32_t lds16(uint32_t a) {
-  uint32_t v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ uint32_t lds32_h(uint32_t a) {  // a is 2-byte aligned (falls back to bytes otherwise)
-  if (a & 1u) return lds32_bytes(a);
-  return lds16(a) | (lds16(a + 2) << 16);
-}
-__device__ __forceinline__ uint32_t lds16_any(uint32_t a) { return (a & 1u) ? (lds8(a) | (lds8(a + 1) << 8)) : lds16(a); }
-
-// Q8_0 block (34 B): d f16 | qs[32] int8 -> 32 bf16, y = q * d in fp32 (gguf/quants.py Q8_0.dequantize_blocks).
-// Lane l of a warp handles elements 8*(l&3)..+8 of block (l>>2): 8 blocks and 512 contiguous output bytes per iteration.
-__device__ __forceinline__ void consume_q8_0(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
-  for (uint32_t b0 = (uint32_t)cwarp * 8u; b0 < nblk; b0 += kConsumerWarps * 8u) {
-    const uint32_t b = b0 + (uint32_t)(lane >> 2);
-    if (b < nblk) {
-      const uint32_t blk = pay + b * KK_Q8_0_BLOCK_BYTES;
-      const float d = __half2float(__ushort_as_half((unsigned short)lds16_any(blk)));
-      const uint32_t qa = blk + 2u + 8u * (uint32_t)(lane & 3);
-      const uint32_t q0 = lds32_h(qa), q1 = lds32_h(qa + 4);
-      float y[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int q = (int)(signed char)(((e < 4 ? q0 : q1) >> (8 * (e & 3))) & 0xFFu);
-        y[e] = __fmul_rn((float)q, d);
-      }
-      store16_all(D, dst_off + (uint64_t)b * 64u + (uint32_t)(lane & 3) * 16u,
-                  make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7])));
-    }
-  }
-}
-
-// Q6_K super-block (210 B): ql[128] | qh[64] | scales[16] int8 | d f16 -> 256 bf16 (gguf/quants.py:552-572):
-// element e = 32*g + i (g = 0..7): low nibble source ql[64*(g/4) + 32*(g%2) + i] >> 4*((g%4)/2), high 2 bits
-// qh[32*(g/4) + i] >> 2*(g%4); q = (lo | hi<<4) - 32; y = (d * scales[e/16]) * q, both products rounded to fp32.
-// Lane l handles the 8 elements e = 8l..8l+7 (g = l>>2, i = 8*(l&3)..+8): one block, 512 output bytes per warp iteration.
-__device__ __forceinline__ void consume_q6k(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
-  const int g = lane >> 2, i0 = 8 * (lane & 3);
-  const uint32_t ql_off = 64u * (uint32_t)(g >> 2) + 32u * (uint32_t)(g & 1) + (uint32_t)i0;
-  const uint32_t qh_off = 128u + 32u * (uint32_t)(g >> 2) + (uint32_t)i0;
-  const int lsh = 4 * ((g & 3) >> 1), hsh = 2 * (g & 3);
-  for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
-    const uint32_t blk = pay + b * KK_Q6K_BLOCK_BYTES;
-    const float d = __half2float(__ushort_as_half((unsigned short)lds16_any(blk + 208u)));
-    const int sc = (int)(signed char)lds8(blk + 192u + (uint32_t)(lane >> 1));
-    const float dsc = __fmul_rn(d, (float)sc);
-    const uint32_t l0 = lds32_h(blk + ql_off), l1 = lds32_h(blk + ql_off + 4);
-    const uint32_t h0 = lds32_h(blk + qh_off), h1 = lds32_h(blk + qh_off + 4);
-    float y[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const uint32_t lw = e < 4 ? l0 : l1, hw = e < 4 ? h0 : h1;
-      const uint32_t lo = (lw >> (8 * (e & 3) + lsh)) & 0xFu;
-      const uint32_t hi = (hw >> (8 * (e & 3) + hsh)) & 0x3u;
-      const int q = (int)(lo | (hi << 4)) - 32;
-      y[e] = __fmul_rn(dsc, (float)q);
-    }
-    store16_all(D, dst_off + (uint64_t)b * 512u + (uint32_t)lane * 16u,
-                make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7])));
   }
 }
 
@@ -574,6 +522,19 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
             d.dst_off = seg.dst_off + b * 512u;
             break;
           }
+          case KK_OP_Q4_0_BF16:
+          case KK_OP_Q4_1_BF16:
+          case KK_OP_Q5_0_BF16:
+          case KK_OP_Q5_1_BF16:
+          case KK_OP_Q2K_BF16:
+          case KK_OP_Q3K_BF16:
+          case KK_OP_Q5K_BF16: {  // the other block quants: same tiling, geometry from kk_ops.h
+            const KKBlockTile bt = kk_block_tile(seg, t);
+            d.n_units = bt.n_blocks;
+            in_bytes = bt.in_bytes; in_off = bt.in_off;
+            d.dst_off = bt.dst_off;
+            break;
+          }
           default: {  // transposes
             const uint32_t C = seg.p0;
             const uint32_t ct = (C + KK_T_COLS - 1) / KK_T_COLS;
@@ -713,6 +674,13 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
         case KK_OP_Q4K_BF16: consume_q4k(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
         case KK_OP_Q8_0_BF16: consume_q8_0(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
         case KK_OP_Q6K_BF16: consume_q6k(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
+        case KK_OP_Q4_0_BF16: consume_legacy32<KK_Q4_0_BLOCK_BYTES, false, false>(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
+        case KK_OP_Q4_1_BF16: consume_legacy32<KK_Q4_1_BLOCK_BYTES, true, false>(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
+        case KK_OP_Q5_0_BF16: consume_legacy32<KK_Q5_0_BLOCK_BYTES, false, true>(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
+        case KK_OP_Q5_1_BF16: consume_legacy32<KK_Q5_1_BLOCK_BYTES, true, true>(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
+        case KK_OP_Q2K_BF16: consume_q2k(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
+        case KK_OP_Q3K_BF16: consume_q3k(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
+        case KK_OP_Q5K_BF16: consume_q5k(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
         case KK_OP_T_F32_BF16: consume_transpose<4, 2, 1>(D, L.src, t, sbase, ctid); break;
         case KK_OP_T_F16_BF16: consume_transpose<2, 2, 2>(D, L.src, t, sbase, ctid); break;
         case KK_OP_T_B16: consume_transpose<2, 2, 0>(D, L.src, t, sbase, ctid); break;

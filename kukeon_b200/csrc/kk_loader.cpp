@@ -899,10 +899,9 @@ std::string model_stats(kk_model* m) {
         case KK_OP_ROWSPLIT: continue;  // lands in every pool; not part of this rank's contiguous range
         case KK_OP_COPY: e = b + s.units; break;
         case KK_OP_F32_BF16: case KK_OP_F16_BF16: e = b + s.units * 2; break;
-        case KK_OP_Q4K_BF16: case KK_OP_Q6K_BF16: e = b + s.units * 512; break;
-        case KK_OP_Q8_0_BF16: e = b + s.units * 64; break;
         case KK_OP_T_B32: e = b + (uint64_t)s.p0 * s.p1 * 4; break;
-        default: e = b + (uint64_t)s.p0 * s.p1 * 2; break;
+        case KK_OP_T_F32_BF16: case KK_OP_T_F16_BF16: case KK_OP_T_B16: e = b + (uint64_t)s.p0 * s.p1 * 2; break;
+        default: e = b + s.units * kk_block_geom(s.op).out_bytes; break;  // block-dequantising ops
       }
       if (b < lo) lo = b;
       if (e > hi) hi = e;

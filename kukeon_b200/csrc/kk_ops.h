@@ -14,6 +14,22 @@
 #define KK_Q8_0_TILE_BLOCKS 960u /* 960*34 = 32640 B in (a multiple of 16), 960*64 = 61440 B out */
 #define KK_Q6K_BLOCK_BYTES 210u
 #define KK_Q6K_TILE_BLOCKS 152u  /* 152*210 = 31920 B in (a multiple of 16), 152*512 = 77824 B out */
+/* §8(f4) legacy and K quants: blocks per tile chosen so that a full tile's source bytes are a multiple of 16 (every tile
+ * of a 16-byte aligned tensor then starts 16-byte aligned in its stage) and at most KK_TILE_SRC_BYTES. */
+#define KK_Q4_0_BLOCK_BYTES 18u
+#define KK_Q4_0_TILE_BLOCKS 1816u /* 32688 B in, 116224 B out */
+#define KK_Q4_1_BLOCK_BYTES 20u
+#define KK_Q4_1_TILE_BLOCKS 1632u /* 32640 B in */
+#define KK_Q5_0_BLOCK_BYTES 22u
+#define KK_Q5_0_TILE_BLOCKS 1488u /* 32736 B in */
+#define KK_Q5_1_BLOCK_BYTES 24u
+#define KK_Q5_1_TILE_BLOCKS 1360u /* 32640 B in */
+#define KK_Q2K_BLOCK_BYTES 84u
+#define KK_Q2K_TILE_BLOCKS 388u   /* 32592 B in, 198656 B out */
+#define KK_Q3K_BLOCK_BYTES 110u
+#define KK_Q3K_TILE_BLOCKS 296u   /* 32560 B in */
+#define KK_Q5K_BLOCK_BYTES 176u
+#define KK_Q5K_TILE_BLOCKS 186u   /* 32736 B in */
 #define KK_T_ROWS 32u            /* transpose tile: 32 source rows ... */
 #define KK_T_COLS 128u           /* ... x 128 source columns (elements) */
 #define KK_T_PITCH_PAD 16u       /* TMA-staged transpose rows sit KK_T_COLS*es + 16 bytes apart (bank spread) */
@@ -37,7 +53,17 @@ enum KKOp : uint32_t {
   // goes to pool j (ConvertLaunch::xdst[j]) at dst_off + row * p1.  p0 = row bytes, p1 = slice bytes, p2 = index of the
   // first row of this rank's piece, p3 = bytes of the piece that precede this segment.
   KK_OP_ROWSPLIT = 10,
-  KK_OP_COUNT = 11
+  // units = 32-weight blocks: Q4_0 (18 B: d f16 | qs[16]), Q4_1 (20 B: d | m | qs), Q5_0 (22 B: d | qh u32 | qs), Q5_1 (24 B: d | m | qh | qs)
+  KK_OP_Q4_0_BF16 = 11,
+  KK_OP_Q4_1_BF16 = 12,
+  KK_OP_Q5_0_BF16 = 13,
+  KK_OP_Q5_1_BF16 = 14,
+  // units = 256-weight super-blocks: Q2_K (84 B: scales[16] | qs[64] | d | dmin), Q3_K (110 B: hmask[32] | qs[64] | scales[12] | d),
+  // Q5_K (176 B: d | dmin | scales[12] | qh[32] | qs[128])
+  KK_OP_Q2K_BF16 = 15,
+  KK_OP_Q3K_BF16 = 16,
+  KK_OP_Q5K_BF16 = 17,
+  KK_OP_COUNT = 18
 };
 
 struct KKSeg {
@@ -52,12 +78,59 @@ struct KKSeg {
 #ifdef __cplusplus
 static_assert(sizeof(KKSeg) == 48, "KKSeg layout is shared with the device");
 
-// Units one tile covers, and the number of tiles of a segment (host + device).
-static inline
 #ifdef __CUDACC__
-__host__ __device__
+#define KK_HD __host__ __device__
+#else
+#define KK_HD
 #endif
-uint64_t kk_seg_tiles(uint32_t op, uint64_t units, uint32_t p0) {
+
+// Geometry of the block-dequantising ops: source bytes and bf16 output bytes per block, blocks per tile.
+// block_bytes == 0: `op` is not a block op.
+struct KKBlockGeom {
+  uint32_t block_bytes, out_bytes, tile_blocks;
+};
+static inline KK_HD KKBlockGeom kk_block_geom(uint32_t op) {
+  switch (op) {
+    case KK_OP_Q4K_BF16: return {KK_Q4K_BLOCK_BYTES, 512u, KK_Q4K_TILE_BLOCKS};
+    case KK_OP_Q8_0_BF16: return {KK_Q8_0_BLOCK_BYTES, 64u, KK_Q8_0_TILE_BLOCKS};
+    case KK_OP_Q6K_BF16: return {KK_Q6K_BLOCK_BYTES, 512u, KK_Q6K_TILE_BLOCKS};
+    case KK_OP_Q4_0_BF16: return {KK_Q4_0_BLOCK_BYTES, 64u, KK_Q4_0_TILE_BLOCKS};
+    case KK_OP_Q4_1_BF16: return {KK_Q4_1_BLOCK_BYTES, 64u, KK_Q4_1_TILE_BLOCKS};
+    case KK_OP_Q5_0_BF16: return {KK_Q5_0_BLOCK_BYTES, 64u, KK_Q5_0_TILE_BLOCKS};
+    case KK_OP_Q5_1_BF16: return {KK_Q5_1_BLOCK_BYTES, 64u, KK_Q5_1_TILE_BLOCKS};
+    case KK_OP_Q2K_BF16: return {KK_Q2K_BLOCK_BYTES, 512u, KK_Q2K_TILE_BLOCKS};
+    case KK_OP_Q3K_BF16: return {KK_Q3K_BLOCK_BYTES, 512u, KK_Q3K_TILE_BLOCKS};
+    case KK_OP_Q5K_BF16: return {KK_Q5K_BLOCK_BYTES, 512u, KK_Q5K_TILE_BLOCKS};
+    default: return {0u, 0u, 0u};
+  }
+}
+// Tile t of a block-op segment: the blocks it covers, where their bytes start (relative to the launch's src base) and
+// where their bf16 output starts in the pool.  Used by the kernel's producer warp and by tests/emul.
+struct KKBlockTile {
+  uint32_t n_blocks, in_bytes;
+  uint64_t in_off, dst_off;
+};
+static inline KK_HD KKBlockTile kk_block_tile(const KKSeg& seg, uint32_t t) {
+  const KKBlockGeom g = kk_block_geom(seg.op);
+  const uint64_t b = (uint64_t)t * g.tile_blocks;
+  const uint64_t rem = seg.units - b;
+  KKBlockTile r;
+  r.n_blocks = rem < g.tile_blocks ? (uint32_t)rem : g.tile_blocks;
+  r.in_bytes = r.n_blocks * g.block_bytes;
+  r.in_off = seg.src_off + b * g.block_bytes;
+  r.dst_off = seg.dst_off + b * g.out_bytes;
+  return r;
+}
+#define KK_TILE_OK(bytes, blocks) ((bytes) * (blocks) <= KK_TILE_SRC_BYTES && ((bytes) * (blocks)) % 16u == 0)
+static_assert(KK_TILE_OK(KK_Q4K_BLOCK_BYTES, KK_Q4K_TILE_BLOCKS) && KK_TILE_OK(KK_Q8_0_BLOCK_BYTES, KK_Q8_0_TILE_BLOCKS) &&
+                  KK_TILE_OK(KK_Q6K_BLOCK_BYTES, KK_Q6K_TILE_BLOCKS) && KK_TILE_OK(KK_Q4_0_BLOCK_BYTES, KK_Q4_0_TILE_BLOCKS) &&
+                  KK_TILE_OK(KK_Q4_1_BLOCK_BYTES, KK_Q4_1_TILE_BLOCKS) && KK_TILE_OK(KK_Q5_0_BLOCK_BYTES, KK_Q5_0_TILE_BLOCKS) &&
+                  KK_TILE_OK(KK_Q5_1_BLOCK_BYTES, KK_Q5_1_TILE_BLOCKS) && KK_TILE_OK(KK_Q2K_BLOCK_BYTES, KK_Q2K_TILE_BLOCKS) &&
+                  KK_TILE_OK(KK_Q3K_BLOCK_BYTES, KK_Q3K_TILE_BLOCKS) && KK_TILE_OK(KK_Q5K_BLOCK_BYTES, KK_Q5K_TILE_BLOCKS),
+              "a full tile of every block op fits one stage and keeps the next tile 16-byte aligned");
+
+// Units one tile covers, and the number of tiles of a segment (host + device).
+static inline KK_HD uint64_t kk_seg_tiles(uint32_t op, uint64_t units, uint32_t p0) {
   switch (op) {
     case KK_OP_COPY:
     case KK_OP_ROWSPLIT: return (units + KK_TILE_SRC_BYTES - 1) / KK_TILE_SRC_BYTES;
@@ -66,6 +139,16 @@ uint64_t kk_seg_tiles(uint32_t op, uint64_t units, uint32_t p0) {
     case KK_OP_Q4K_BF16: return (units + KK_Q4K_TILE_BLOCKS - 1) / KK_Q4K_TILE_BLOCKS;
     case KK_OP_Q8_0_BF16: return (units + KK_Q8_0_TILE_BLOCKS - 1) / KK_Q8_0_TILE_BLOCKS;
     case KK_OP_Q6K_BF16: return (units + KK_Q6K_TILE_BLOCKS - 1) / KK_Q6K_TILE_BLOCKS;
+    case KK_OP_Q4_0_BF16:
+    case KK_OP_Q4_1_BF16:
+    case KK_OP_Q5_0_BF16:
+    case KK_OP_Q5_1_BF16:
+    case KK_OP_Q2K_BF16:
+    case KK_OP_Q3K_BF16:
+    case KK_OP_Q5K_BF16: {
+      const uint32_t tb = kk_block_geom(op).tile_blocks;
+      return (units + tb - 1) / tb;
+    }
     case KK_OP_T_F32_BF16:
     case KK_OP_T_B32:
     case KK_OP_T_F16_BF16:

@@ -34,15 +34,31 @@ OpInfo op_for(uint32_t dt, uint32_t flags, const std::string& name) {
       if (flags & KK_LOAD_KEEP_F32) return {KK_OP_COPY, KK_F32, 1, 1, KK_TILE_SRC_BYTES};
       return {KK_OP_F32_BF16, KK_BF16, 4, 2, KK_TILE_SRC_BYTES / 4};
     case KK_F16: return {KK_OP_F16_BF16, KK_BF16, 2, 2, KK_TILE_SRC_BYTES / 2};
-    case KK_Q4_K: return {KK_OP_Q4K_BF16, KK_BF16, KK_Q4K_BLOCK_BYTES, 512, KK_Q4K_TILE_BLOCKS};
-    case KK_Q8_0: return {KK_OP_Q8_0_BF16, KK_BF16, KK_Q8_0_BLOCK_BYTES, 64, KK_Q8_0_TILE_BLOCKS};
-    case KK_Q6_K: return {KK_OP_Q6K_BF16, KK_BF16, KK_Q6K_BLOCK_BYTES, 512, KK_Q6K_TILE_BLOCKS};
     default: break;
+  }
+  // block-quantised GGUF types -> bf16 (geometry shared with the kernel: kk_ops.h)
+  uint32_t qop = KK_OP_COUNT;
+  switch (dt) {
+    case KK_Q4_0: qop = KK_OP_Q4_0_BF16; break;
+    case KK_Q4_1: qop = KK_OP_Q4_1_BF16; break;
+    case KK_Q5_0: qop = KK_OP_Q5_0_BF16; break;
+    case KK_Q5_1: qop = KK_OP_Q5_1_BF16; break;
+    case KK_Q8_0: qop = KK_OP_Q8_0_BF16; break;
+    case KK_Q2_K: qop = KK_OP_Q2K_BF16; break;
+    case KK_Q3_K: qop = KK_OP_Q3K_BF16; break;
+    case KK_Q4_K: qop = KK_OP_Q4K_BF16; break;
+    case KK_Q5_K: qop = KK_OP_Q5K_BF16; break;
+    case KK_Q6_K: qop = KK_OP_Q6K_BF16; break;
+    default: break;
+  }
+  if (qop != KK_OP_COUNT) {
+    const KKBlockGeom g = kk_block_geom(qop);
+    return {qop, KK_BF16, g.block_bytes, g.out_bytes, g.tile_blocks};
   }
   const DtypeInfo* di = dtype_info(dt);
   if (!di) fail(KK_EINVAL, "tensor %s: unknown dtype %u", name.c_str(), dt);
   if (di->block_elems > 1 && dt >= 32)
-    fail(KK_EUNSUPPORTED, "tensor %s: %s -> bf16 dequantisation is not implemented (Q4_K, Q6_K and Q8_0 are)", name.c_str(), di->name);
+    fail(KK_EUNSUPPORTED, "tensor %s: %s -> bf16 dequantisation is not implemented (Q4_0, Q4_1, Q5_0, Q5_1, Q8_0, Q2_K, Q3_K, Q4_K, Q5_K and Q6_K are)", name.c_str(), di->name);
   return {KK_OP_COPY, dt, 1, 1, KK_TILE_SRC_BYTES};  // integers, bool, fp8, f64, sub-byte: verbatim bytes
 }
 

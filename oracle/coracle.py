@@ -13,6 +13,10 @@ _SO = os.path.join(_HERE, "_build", "libkk_oracle.so")
 _lib = None
 
 OP_COPY, OP_F32_BF16, OP_F16_BF16, OP_Q4K_BF16, OP_Q8_0_BF16, OP_Q6K_BF16 = 0, 1, 2, 3, 4, 5
+OP_DEQUANT = 0x100  # | ggml type id
+# file dtype -> (ggml type id, weights per block, bytes per block)   (gguf/constants.py GGML_QUANT_SIZES)
+GGML_BLOCK = {"Q4_0": (2, 32, 18), "Q4_1": (3, 32, 20), "Q5_0": (6, 32, 22), "Q5_1": (7, 32, 24), "Q8_0": (8, 32, 34),
+              "Q2_K": (10, 256, 84), "Q3_K": (11, 256, 110), "Q4_K": (12, 256, 144), "Q5_K": (13, 256, 176), "Q6_K": (14, 256, 210)}
 
 
 class OrcJob(C.Structure):
@@ -38,6 +42,8 @@ def lib():
         L.orc_q4k_to_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.orc_q8_0_to_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.orc_q6k_to_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.orc_dequant_to_bf16.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.orc_dequant_to_bf16.restype = C.c_int
         L.orc_checksum.argtypes = [C.c_void_p, C.c_uint64]
         L.orc_checksum.restype = C.c_uint64
         for fn in ("orc_fill_bytes", "orc_fill_bf16_finite", "orc_fill_f32", "orc_fill_q4k"):
@@ -96,6 +102,18 @@ def q6k_to_bf16(blocks: np.ndarray) -> np.ndarray:
     return out.reshape(n, 256)
 
 
+def dequant_to_bf16(dtype: str, blocks: np.ndarray) -> np.ndarray:
+    """Any block-quantised GGUF type the oracle defines -> bf16 bit patterns [n_blocks, weights per block]."""
+    tid, nel, nb = GGML_BLOCK[dtype]
+    src = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1)
+    assert src.size % nb == 0
+    n = src.size // nb
+    out = np.empty(n * nel, np.uint16)
+    if lib().orc_dequant_to_bf16(tid, _ptr(src), _ptr(out), n) != 0:
+        raise ValueError(dtype)
+    return out.reshape(n, nel)
+
+
 def checksum(a: np.ndarray) -> int:
     src = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
     return int(lib().orc_checksum(_ptr(src), src.size))
@@ -133,6 +151,9 @@ def fill_into(kind: str, dst: np.ndarray, seed: int) -> None:
 
 
 _OPS = {"BF16": OP_COPY, "F32": OP_F32_BF16, "F16": OP_F16_BF16, "Q4_K": OP_Q4K_BF16, "Q8_0": OP_Q8_0_BF16, "Q6_K": OP_Q6K_BF16}
+_OPS.update({dt: OP_DEQUANT | tid for dt, (tid, _, _) in GGML_BLOCK.items() if dt not in _OPS})
+_UNITS = {OP_COPY: (1, 1), OP_F32_BF16: (4, 2), OP_F16_BF16: (2, 2)}  # op -> (source bytes, pool bytes) per unit
+_UNITS.update({_OPS[dt]: (nb, 2 * nel) for dt, (_, nel, nb) in GGML_BLOCK.items()})
 
 
 def make_jobs(recs: Sequence[dict], plan: Sequence[dict], job_bytes: int = 8 << 20, max_src_bytes: int | None = None):
@@ -141,8 +162,7 @@ def make_jobs(recs: Sequence[dict], plan: Sequence[dict], job_bytes: int = 8 << 
     total = 0
     for r, p in zip(recs, plan):
         op = _OPS.get(r["dtype"], OP_COPY)
-        unit, out_unit = {OP_COPY: (256, 256), OP_F32_BF16: (4, 2), OP_F16_BF16: (2, 2), OP_Q4K_BF16: (144, 512), OP_Q8_0_BF16: (34, 64),
-                          OP_Q6K_BF16: (210, 512)}[op]
+        unit, out_unit = _UNITS[op]
         step = max(unit, job_bytes // unit * unit)
         off = 0
         while off < r["nbytes"]:

@@ -4,7 +4,7 @@
  * cpu_baseline / --impl reference legs; never by the product.
  *
  * PARITY UNPINNED AGAINST THE REFERENCE (eminwux/kukeon has no weight loader — SURVEY.md §0); pinned
- * against safetensors 0.7.0 / gguf 0.19.0 (gguf/quants.py:475-521) / torch RNE through oracle.py, which
+ * against safetensors 0.7.0 / gguf 0.19.0 (gguf/quants.py:220-572) / torch RNE through oracle.py, which
  * tests/test_oracle_values.py checks this file against bit for bit.
  *
  * Build: see oracle/Makefile (gcc -O3 -fopenmp -ffp-contract=off).
@@ -116,6 +116,133 @@ void orc_q6k_to_bf16(const uint8_t* blocks, uint16_t* dst, uint64_t nblocks) {
   for (uint64_t i = 0; i < nblocks; ++i) q6k_block(blocks + 210 * i, dst + 256 * i);
 }
 
+/* ---- the remaining legacy and K quants; element formulas as in oracle/oracle.py ---------- */
+static inline float ld_f16(const uint8_t* p) {
+  uint16_t h;
+  memcpy(&h, p, 2);
+  return f16bits_to_f32(h);
+}
+/* 32-weight legacy blocks: element e < 16 is the low nibble of qs[e], e >= 16 the high nibble of qs[e-16]. */
+static inline int legacy_nibble(const uint8_t* qs, int e) { return e < 16 ? (qs[e] & 0x0F) : (qs[e - 16] >> 4); }
+
+/* Q4_0 (18 B): d f16 | qs[16]; y = d * (q - 8)  (gguf/quants.py:220-231). */
+static void q4_0_block(const uint8_t* b, uint16_t* out) {
+  const float d = ld_f16(b);
+  for (int e = 0; e < 32; ++e) out[e] = f32_to_bf16(d * (float)(legacy_nibble(b + 2, e) - 8));
+}
+/* Q4_1 (20 B): d f16 | m f16 | qs[16]; y = (d*q) + m  (gguf/quants.py:254-267). */
+static void q4_1_block(const uint8_t* b, uint16_t* out) {
+  const float d = ld_f16(b), m = ld_f16(b + 2);
+  for (int e = 0; e < 32; ++e) {
+    volatile float p = d * (float)legacy_nibble(b + 4, e);
+    out[e] = f32_to_bf16(p + m);
+  }
+}
+/* Q5_0 (22 B): d f16 | qh u32 | qs[16]; bit 4 of element e is bit e of qh; y = d * (q - 16)  (gguf/quants.py:291-308). */
+static void q5_0_block(const uint8_t* b, uint16_t* out) {
+  const float d = ld_f16(b);
+  uint32_t qh;
+  memcpy(&qh, b + 2, 4);
+  for (int e = 0; e < 32; ++e) {
+    const int q = (legacy_nibble(b + 6, e) | (int)(((qh >> e) & 1u) << 4)) - 16;
+    out[e] = f32_to_bf16(d * (float)q);
+  }
+}
+/* Q5_1 (24 B): d f16 | m f16 | qh u32 | qs[16]; y = (d*q) + m  (gguf/quants.py:333-352). */
+static void q5_1_block(const uint8_t* b, uint16_t* out) {
+  const float d = ld_f16(b), m = ld_f16(b + 2);
+  uint32_t qh;
+  memcpy(&qh, b + 4, 4);
+  for (int e = 0; e < 32; ++e) {
+    const int q = legacy_nibble(b + 8, e) | (int)(((qh >> e) & 1u) << 4);
+    volatile float p = d * (float)q;
+    out[e] = f32_to_bf16(p + m);
+  }
+}
+/* Q2_K (84 B): scales[16] | qs[64] | d f16 | dmin f16; e = 128h + 32s + i: q = (qs[32h+i] >> 2s) & 3;
+ * y = (d*(scales[e/16]&15))*q - dmin*(scales[e/16]>>4)  (gguf/quants.py:404-428). */
+static void q2k_block(const uint8_t* b, uint16_t* out) {
+  const uint8_t* sc = b;
+  const uint8_t* qs = b + 16;
+  const float d = ld_f16(b + 80), dmin = ld_f16(b + 82);
+  for (int e = 0; e < 256; ++e) {
+    const int h = e >> 7, s = (e >> 5) & 3, i = e & 31;
+    const int q = (qs[32 * h + i] >> (2 * s)) & 3;
+    volatile float dl = d * (float)(sc[e >> 4] & 0x0F);
+    volatile float ml = dmin * (float)(sc[e >> 4] >> 4);
+    volatile float p = dl * (float)q;
+    out[e] = f32_to_bf16(p - ml);
+  }
+}
+/* Q3_K (110 B): hmask[32] | qs[64] | scales[12] | d f16  (gguf/quants.py:431-472). */
+static void q3k_block(const uint8_t* b, uint16_t* out) {
+  const uint8_t* hm = b;
+  const uint8_t* qs = b + 32;
+  const uint8_t* s = b + 96;
+  const float d = ld_f16(b + 108);
+  for (int e = 0; e < 256; ++e) {
+    const int k = e >> 4, g = e >> 5, i = e & 31;
+    const int lo4 = k < 8 ? (s[k] & 0x0F) : (s[k - 8] >> 4);
+    const int hi2 = (s[8 + (k & 3)] >> (2 * (k >> 2))) & 3;
+    const int scale = (lo4 | (hi2 << 4)) - 32;
+    const int lo = (qs[32 * (g >> 2) + i] >> (2 * (g & 3))) & 3;
+    const int q = lo - ((((hm[i] >> g) & 1) ^ 1) << 2);
+    volatile float dl = d * (float)scale;
+    out[e] = f32_to_bf16(dl * (float)q);
+  }
+}
+/* Q5_K (176 B): d f16 | dmin f16 | scales[12] | qh[32] | qs[128]; scales packed as in Q4_K  (gguf/quants.py:525-548). */
+static void q5k_block(const uint8_t* b, uint16_t* out) {
+  const float d = ld_f16(b), dmin = ld_f16(b + 2);
+  const uint8_t* s = b + 4;
+  const uint8_t* qh = b + 16;
+  const uint8_t* qs = b + 48;
+  for (int j = 0; j < 8; ++j) {
+    uint8_t sc, m;
+    if (j < 4) {
+      sc = s[j] & 63;
+      m = s[j + 4] & 63;
+    } else {
+      sc = (uint8_t)((s[j + 4] & 0x0F) | ((s[j - 4] >> 6) << 4));
+      m = (uint8_t)((s[j + 4] >> 4) | ((s[j] >> 6) << 4));
+    }
+    volatile float dsc = d * (float)sc;
+    volatile float dmn = dmin * (float)m;
+    for (int i = 0; i < 32; ++i) {
+      const int q = ((qs[32 * (j >> 1) + i] >> (4 * (j & 1))) & 0x0F) | (((qh[i] >> j) & 1) << 4);
+      volatile float p = dsc * (float)q;
+      out[32 * j + i] = f32_to_bf16(p - dmn);
+    }
+  }
+}
+
+/* Dispatch by ggml type id (gguf/constants.py GGMLQuantizationType): block bytes / weights per block / function. */
+typedef void (*orc_block_fn)(const uint8_t*, uint16_t*);
+static orc_block_fn block_fn(uint32_t ggml_type, uint32_t* bytes, uint32_t* elems) {
+  switch (ggml_type) {
+    case 2: *bytes = 18; *elems = 32; return q4_0_block;
+    case 3: *bytes = 20; *elems = 32; return q4_1_block;
+    case 6: *bytes = 22; *elems = 32; return q5_0_block;
+    case 7: *bytes = 24; *elems = 32; return q5_1_block;
+    case 8: *bytes = 34; *elems = 32; return q8_0_block;
+    case 10: *bytes = 84; *elems = 256; return q2k_block;
+    case 11: *bytes = 110; *elems = 256; return q3k_block;
+    case 12: *bytes = 144; *elems = 256; return q4k_block;
+    case 13: *bytes = 176; *elems = 256; return q5k_block;
+    case 14: *bytes = 210; *elems = 256; return q6k_block;
+    default: return 0;
+  }
+}
+/* Returns 0, or -1 for a type this oracle does not define. */
+int orc_dequant_to_bf16(uint32_t ggml_type, const uint8_t* blocks, uint16_t* dst, uint64_t nblocks) {
+  uint32_t nb = 0, ne = 0;
+  const orc_block_fn fn = block_fn(ggml_type, &nb, &ne);
+  if (!fn) return -1;
+#pragma omp parallel for schedule(static)
+  for (uint64_t i = 0; i < nblocks; ++i) fn(blocks + (uint64_t)nb * i, dst + (uint64_t)ne * i);
+  return 0;
+}
+
 static inline uint64_t mix64(uint64_t x) {
   x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
   x ^= x >> 27; x *= 0x94d049bb133111ebull;
@@ -204,7 +331,8 @@ void orc_fill_q4k(uint8_t* dst, uint64_t nblocks, uint64_t seed) {
 }
 
 /* ---- CPU loader ("port" of the hot path for the cpu_baseline legs) ---------------------------- */
-enum { ORC_COPY = 0, ORC_F32_BF16 = 1, ORC_F16_BF16 = 2, ORC_Q4K_BF16 = 3, ORC_Q8_0_BF16 = 4, ORC_Q6K_BF16 = 5 };
+enum { ORC_COPY = 0, ORC_F32_BF16 = 1, ORC_F16_BF16 = 2, ORC_Q4K_BF16 = 3, ORC_Q8_0_BF16 = 4, ORC_Q6K_BF16 = 5,
+       ORC_DEQUANT = 0x100 /* | ggml type id: any block-quantised type block_fn() knows */ };
 
 typedef struct {
   uint32_t shard;
@@ -265,6 +393,11 @@ int orc_cpu_load(const char* const* shard_paths, uint32_t n_shards, const orc_jo
           for (uint64_t i = 0; i < J->nbytes / 34; ++i) q8_0_block(scratch + 34 * i, out + 32 * i);
         } else if (J->op == ORC_Q6K_BF16) {
           for (uint64_t i = 0; i < J->nbytes / 210; ++i) q6k_block(scratch + 210 * i, out + 256 * i);
+        } else if (J->op & ORC_DEQUANT) {
+          uint32_t nb = 0, ne = 0;
+          const orc_block_fn fn = block_fn(J->op & 0xFFu, &nb, &ne);
+          if (!fn) { err = -1; continue; }
+          for (uint64_t i = 0; i < J->nbytes / nb; ++i) fn(scratch + (uint64_t)nb * i, out + (uint64_t)ne * i);
         } else err = -1;
       }
       free(scratch);

@@ -12,7 +12,7 @@ the *published file formats*, pinned instead against the format owners' own libr
 image:
 
 * safetensors 0.7.0  — header layout, validation rules  (``tests/test_index.py``)
-* gguf 0.19.0        — GGUF v3 header, ``quants.Q4_K/Q6_K/Q8_0.dequantize_blocks`` (gguf/quants.py:475-521, 552-572, 395-401)
+* gguf 0.19.0        — GGUF v3 header, ``quants.{Q4_0,Q4_1,Q5_0,Q5_1,Q8_0,Q2_K,Q3_K,Q4_K,Q5_K,Q6_K}.dequantize_blocks`` (gguf/quants.py:220-572)
 * torch 2.11         — fp32/fp16 -> bf16 round-to-nearest-even
 
 Everything here is plain Python/numpy so that it can be read next to those sources.  Heavy loops have a
@@ -369,6 +369,143 @@ def dequant_q6k_bf16(blocks: np.ndarray) -> np.ndarray:
     return f32_to_bf16(dequant_q6k_f32(blocks)).reshape(-1, 256)
 
 
+
+def _f16(b: np.ndarray) -> np.ndarray:
+    """[n,2] uint8 -> [n,1] float32 (exact widening of the little-endian fp16)."""
+    return np.ascontiguousarray(b).view(np.float16).astype(np.float32).reshape(-1, 1)
+
+
+def _nibbles_lo_then_hi(qs: np.ndarray) -> np.ndarray:
+    """[n,16] packed bytes -> [n,32]: elements 0..15 are the low nibbles of qs[0..15], 16..31 the high nibbles
+    (the 32-weight legacy blocks Q4_0/Q4_1/Q5_0/Q5_1; gguf/quants.py:227-228)."""
+    return np.concatenate([qs & 0x0F, qs >> 4], axis=1)
+
+
+def dequant_q4_0_f32(blocks: np.ndarray) -> np.ndarray:
+    """[n,18] (d f16 | qs[16]) -> [n,32]: y = d * (q - 8)  (gguf/quants.py:220-231)."""
+    b = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, 18)
+    q = _nibbles_lo_then_hi(b[:, 2:18]).astype(np.int8) - np.int8(8)
+    with np.errstate(all="ignore"):
+        return (_f16(b[:, 0:2]) * q.astype(np.float32)).astype(np.float32)
+
+
+def dequant_q4_1_f32(blocks: np.ndarray) -> np.ndarray:
+    """[n,20] (d f16 | m f16 | qs[16]) -> [n,32]: y = (d*q) + m, product and sum rounded separately (gguf/quants.py:254-267)."""
+    b = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, 20)
+    q = _nibbles_lo_then_hi(b[:, 4:20]).astype(np.float32)
+    with np.errstate(all="ignore"):
+        return ((_f16(b[:, 0:2]) * q).astype(np.float32) + _f16(b[:, 2:4])).astype(np.float32)
+
+
+def _q5_legacy_q(qh4: np.ndarray, qs: np.ndarray) -> np.ndarray:
+    """5-bit values of a 32-weight block: low 4 bits as in Q4_0, bit 4 of element e is bit e of the LE u32 qh."""
+    qh = np.ascontiguousarray(qh4).view("<u4").reshape(-1, 1)
+    hi = ((qh >> np.arange(32, dtype=np.uint32).reshape(1, 32)) & np.uint32(1)).astype(np.uint8)
+    return _nibbles_lo_then_hi(qs) | (hi << 4)
+
+
+def dequant_q5_0_f32(blocks: np.ndarray) -> np.ndarray:
+    """[n,22] (d f16 | qh u32 | qs[16]) -> [n,32]: y = d * (q5 - 16)  (gguf/quants.py:291-308)."""
+    b = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, 22)
+    q = _q5_legacy_q(b[:, 2:6], b[:, 6:22]).astype(np.int8) - np.int8(16)
+    with np.errstate(all="ignore"):
+        return (_f16(b[:, 0:2]) * q.astype(np.float32)).astype(np.float32)
+
+
+def dequant_q5_1_f32(blocks: np.ndarray) -> np.ndarray:
+    """[n,24] (d f16 | m f16 | qh u32 | qs[16]) -> [n,32]: y = (d*q5) + m  (gguf/quants.py:333-352)."""
+    b = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, 24)
+    q = _q5_legacy_q(b[:, 4:8], b[:, 8:24]).astype(np.float32)
+    with np.errstate(all="ignore"):
+        return ((_f16(b[:, 0:2]) * q).astype(np.float32) + _f16(b[:, 2:4])).astype(np.float32)
+
+
+def dequant_q2k_f32(blocks: np.ndarray) -> np.ndarray:
+    """[n,84] (scales[16] | qs[64] | d f16 | dmin f16) -> [n,256].  Element e = 128h + 32s + i (h<2, s<4, i<32) takes
+    q = (qs[32h+i] >> 2s) & 3; its 16-weight sub-block j = e//16 has dl = d*(scales[j]&15), ml = dmin*(scales[j]>>4);
+    y = dl*q - ml, every operation rounded to fp32 (gguf/quants.py:404-428)."""
+    b = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, 84)
+    n = b.shape[0]
+    sc, qs = b[:, 0:16], b[:, 16:80]
+    d, dmin = _f16(b[:, 80:82]), _f16(b[:, 82:84])
+    q = np.empty((n, 2, 4, 32), np.uint8)
+    for h in range(2):
+        for s in range(4):
+            q[:, h, s, :] = (qs[:, 32 * h: 32 * h + 32] >> (2 * s)) & 3
+    with np.errstate(all="ignore"):
+        dl = (d * (sc & 0x0F).astype(np.float32)).astype(np.float32)
+        ml = (dmin * (sc >> 4).astype(np.float32)).astype(np.float32)
+        y = ((dl[:, :, None] * q.reshape(n, 16, 16).astype(np.float32)).astype(np.float32) - ml[:, :, None]).astype(np.float32)
+    return y.reshape(n, 256)
+
+
+def q3k_scales(s12: np.ndarray) -> np.ndarray:
+    """12 packed bytes -> 16 signed 6-bit scales (gguf/quants.py:441-462): low 4 bits of scale k are s[k]&15 (k<8) or
+    s[k-8]>>4 (k>=8); its high 2 bits are (s[8 + k%4] >> 2*(k//4)) & 3; value = (lo | hi<<4) - 32."""
+    s = s12.astype(np.uint8)
+    out = np.empty(s.shape[:-1] + (16,), np.int8)
+    for k in range(16):
+        lo = (s[..., k] & 0x0F) if k < 8 else (s[..., k - 8] >> 4)
+        hi = (s[..., 8 + (k % 4)] >> (2 * (k // 4))) & 3
+        out[..., k] = (lo | (hi << 4)).astype(np.int8) - np.int8(32)
+    return out
+
+
+def dequant_q3k_f32(blocks: np.ndarray) -> np.ndarray:
+    """[n,110] (hmask[32] | qs[64] | scales[12] | d f16) -> [n,256].  Element e = 128h + 32s + i has low bits
+    (qs[32h+i] >> 2s) & 3; written as e = 32b + i (b<8) its high bit is (hmask[i] >> b) & 1 and q = low - (4 if that
+    bit is CLEAR else 0); y = (d*scale[e//16]) * q (gguf/quants.py:431-472)."""
+    b = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, 110)
+    n = b.shape[0]
+    hm, qs = b[:, 0:32], b[:, 32:96]
+    sc = q3k_scales(b[:, 96:108]).astype(np.float32)
+    d = _f16(b[:, 108:110])
+    q = np.empty((n, 8, 32), np.int8)
+    for g in range(8):  # g = 4h + s = e // 32
+        lo = (qs[:, 32 * (g // 4): 32 * (g // 4) + 32] >> (2 * (g % 4))) & 3
+        clear = ((hm >> g) & 1) ^ 1
+        q[:, g, :] = lo.astype(np.int8) - (clear << 2).astype(np.int8)
+    with np.errstate(all="ignore"):
+        dl = (d * sc).astype(np.float32)
+        y = (dl[:, :, None] * q.reshape(n, 16, 16).astype(np.float32)).astype(np.float32)
+    return y.reshape(n, 256)
+
+
+def dequant_q5k_f32(blocks: np.ndarray) -> np.ndarray:
+    """[n,176] (d f16 | dmin f16 | scales[12] | qh[32] | qs[128]) -> [n,256].  Sub-block j (32 weights), element i:
+    q = ((qs[32*(j//2)+i] >> 4*(j%2)) & 15) | (((qh[i] >> j) & 1) << 4); (scale, min) packed as in Q4_K;
+    y = (d*sc_j)*q - (dmin*m_j) (gguf/quants.py:525-548)."""
+    b = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, 176)
+    n = b.shape[0]
+    d, dmin = _f16(b[:, 0:2]), _f16(b[:, 2:4])
+    sc, mn = q4k_scale_min(b[:, 4:16])
+    qh, qs = b[:, 16:48], b[:, 48:176]
+    q = np.empty((n, 8, 32), np.uint8)
+    for j in range(8):
+        lo = (qs[:, 32 * (j // 2): 32 * (j // 2) + 32] >> (4 * (j % 2))) & 0x0F
+        q[:, j, :] = lo | (((qh >> j) & 1) << 4)
+    with np.errstate(all="ignore"):
+        dsc = (d * sc.astype(np.float32)).astype(np.float32)
+        dmn = (dmin * mn.astype(np.float32)).astype(np.float32)
+        y = ((dsc[:, :, None] * q.astype(np.float32)).astype(np.float32) - dmn[:, :, None]).astype(np.float32)
+    return y.reshape(n, 256)
+
+
+# file dtype -> (weights per block, bytes per block, fp32 dequantiser).  Everything the product dequantises to bf16.
+BLOCK_QUANTS = {
+    "Q4_0": (32, 18, dequant_q4_0_f32), "Q4_1": (32, 20, dequant_q4_1_f32), "Q5_0": (32, 22, dequant_q5_0_f32),
+    "Q5_1": (32, 24, dequant_q5_1_f32), "Q8_0": (32, 34, dequant_q8_0_f32), "Q2_K": (256, 84, dequant_q2k_f32),
+    "Q3_K": (256, 110, dequant_q3k_f32), "Q4_K": (256, 144, dequant_q4k_f32), "Q5_K": (256, 176, dequant_q5k_f32),
+    "Q6_K": (256, 210, dequant_q6k_f32),
+}
+
+
+def dequant_bf16(dtype: str, blocks: np.ndarray) -> np.ndarray:
+    """Block-quantised bytes of `dtype` -> bf16 bit patterns [n_blocks, weights per block]."""
+    nel, nb, fn = BLOCK_QUANTS[dtype]
+    return f32_to_bf16(fn(np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, nb))).reshape(-1, nel)
+
+
 _MASK = (1 << 64) - 1
 
 
@@ -406,7 +543,7 @@ _ELEM_BYTES.update({"F32": 4, "F16": 2, "BF16": 2, "I8": 1, "I16": 2, "I32": 4, 
 
 
 def pool_dtype(dt: str, flags: int = 0) -> str:
-    if dt in ("F16", "BF16", "Q4_K", "Q6_K", "Q8_0"):
+    if dt in ("F16", "BF16") or dt in BLOCK_QUANTS:
         return "BF16"
     if dt == "F32":
         return "F32" if flags & LOAD_KEEP_F32 else "BF16"
@@ -473,12 +610,8 @@ def convert_tensor(rec: dict, raw: bytes, flags: int = 0) -> np.ndarray:
         return f32_bits_to_bf16(a.view("<u4")).view(np.uint8)
     if dt == "F16":
         return f16_bits_to_bf16(a.view("<u2")).view(np.uint8)
-    if dt == "Q4_K":
-        return dequant_q4k_bf16(a.reshape(-1, 144)).reshape(-1).view(np.uint8)
-    if dt == "Q8_0":
-        return dequant_q8_0_bf16(a.reshape(-1, 34)).reshape(-1).view(np.uint8)
-    if dt == "Q6_K":
-        return dequant_q6k_bf16(a.reshape(-1, 210)).reshape(-1).view(np.uint8)
+    if dt in BLOCK_QUANTS:
+        return dequant_bf16(dt, a).reshape(-1).view(np.uint8)
     if dt.startswith("Q"):
         raise OracleError(f"{dt} dequantisation not defined by this oracle")
     return a.copy()

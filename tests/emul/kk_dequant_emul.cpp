@@ -1,0 +1,152 @@
+// Host emulation of kk_convert_kernel's block dequantisers.  TEST INFRASTRUCTURE ONLY.
+//
+// Compiles kukeon_b200/csrc/kk_dequant.cuh — the exact device source — with g++ by binding the handful of primitives it
+// uses (shared-memory loads, single-rounding fp32 arithmetic, bf16 packing, the 16-byte store) to plain C++, then plays
+// all 16 consumer warps x 32 lanes of one tile in a loop.  What this checks, on the CPU test tier, is the part of a
+// dequantiser that is easy to get wrong and cannot be seen by reading a formula: which lane reads which bytes of which
+// block and where its 16 output bytes land.  The bindings are stricter than the hardware: a misaligned 16/32-bit
+// shared load, a read outside the staged tile, a store outside the tile's output window or two stores to the same 16 bytes
+// all fail the run.  It does not check PTX spelling, memory ordering or anything about the producer warp; the -m gpu
+// parity tests do.  The product never links this file and has no CPU path.
+#include <cstdint>
+#include <cstring>
+
+namespace {
+
+struct uint4 { uint32_t x, y, z, w; };
+inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+
+struct Emu {
+  const uint8_t* tile = nullptr;  // the stage buffer; shared-memory address a <-> tile[a]
+  uint32_t tile_bytes = 0;
+  uint8_t* out = nullptr;
+  uint64_t out_bytes = 0;
+  uint8_t* hits = nullptr;  // one counter per 16 output bytes
+  int err = 0;              // first failure: 1 load out of range, 2 misaligned load, 3 store out of range/misaligned, 4 double store
+};
+thread_local Emu g;
+
+inline void flag(int e) { if (!g.err) g.err = e; }
+inline uint32_t lds8(uint32_t a) {
+  if (a >= g.tile_bytes) { flag(1); return 0; }
+  return g.tile[a];
+}
+inline uint32_t lds16(uint32_t a) {
+  if (a & 1u) { flag(2); return 0; }
+  if (a + 2 > g.tile_bytes) { flag(1); return 0; }
+  uint16_t v; memcpy(&v, g.tile + a, 2); return v;
+}
+inline uint32_t lds32(uint32_t a) {
+  if (a & 3u) { flag(2); return 0; }
+  if (a + 4 > g.tile_bytes) { flag(1); return 0; }
+  uint32_t v; memcpy(&v, g.tile + a, 4); return v;
+}
+inline float kk_h2f(uint32_t h) {
+  uint16_t b = (uint16_t)h;
+  _Float16 x; memcpy(&x, &b, 2);
+  return (float)x;
+}
+// one IEEE operation each; -ffp-contract=off in the build line, volatile as a second guard
+inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+inline uint32_t bf16_rne(float f) {
+  uint32_t u; memcpy(&u, &f, 4);
+  if ((u & 0x7FFFFFFFu) > 0x7F800000u) return 0x7FFFu;  // cvt.rn.bf16x2.f32: canonical NaN
+  return (u + 0x7FFFu + ((u >> 16) & 1u)) >> 16;
+}
+inline uint32_t pack_bf16x2(float a, float b) { return bf16_rne(a) | (bf16_rne(b) << 16); }
+
+struct Dsts { int unused; };
+inline void store16_all(const Dsts&, uint64_t off, const uint4& v) {
+  if ((off & 15u) || off + 16 > g.out_bytes) { flag(3); return; }
+  if (g.hits[off >> 4]++) flag(4);
+  memcpy(g.out + off, &v, 16);
+}
+
+constexpr int kConsumerWarps = 16;  // must equal KK_CONSUMER_WARPS of the kernel build
+#define KK_DQ_DEV static inline
+#define min(a, b) ((a) < (b) ? (a) : (b))
+#include "../../kukeon_b200/csrc/kk_dequant.cuh"
+#undef min
+
+}  // namespace
+
+// Run the consumer side of one tile of block op `op` (KKOp): `nblk` blocks whose first byte sits at tile[pay_off].
+// out receives nblk * out_bytes_per_block bytes; hits (out_bytes/16 counters, zeroed here) how often each 16-byte unit
+// was stored.  Returns 0, a positive Emu::err code, or -1 for an op this harness does not cover.
+extern "C" int kk_emul_dequant_tile(uint32_t op, const uint8_t* tile, uint32_t tile_bytes, uint32_t pay_off, uint32_t nblk, uint8_t* out,
+                                    uint64_t out_bytes, uint8_t* hits) {
+  g = Emu{};
+  g.tile = tile; g.tile_bytes = tile_bytes; g.out = out; g.out_bytes = out_bytes; g.hits = hits;
+  memset(hits, 0, out_bytes / 16);
+  const Dsts D{0};
+  for (int cwarp = 0; cwarp < kConsumerWarps; ++cwarp)
+    for (int lane = 0; lane < 32; ++lane) {
+      switch (op) {
+        case KK_OP_Q8_0_BF16: consume_q8_0(D, pay_off, nblk, 0, cwarp, lane); break;
+        case KK_OP_Q6K_BF16: consume_q6k(D, pay_off, nblk, 0, cwarp, lane); break;
+        case KK_OP_Q4_0_BF16: consume_legacy32<KK_Q4_0_BLOCK_BYTES, false, false>(D, pay_off, nblk, 0, cwarp, lane); break;
+        case KK_OP_Q4_1_BF16: consume_legacy32<KK_Q4_1_BLOCK_BYTES, true, false>(D, pay_off, nblk, 0, cwarp, lane); break;
+        case KK_OP_Q5_0_BF16: consume_legacy32<KK_Q5_0_BLOCK_BYTES, false, true>(D, pay_off, nblk, 0, cwarp, lane); break;
+        case KK_OP_Q5_1_BF16: consume_legacy32<KK_Q5_1_BLOCK_BYTES, true, true>(D, pay_off, nblk, 0, cwarp, lane); break;
+        case KK_OP_Q2K_BF16: consume_q2k(D, pay_off, nblk, 0, cwarp, lane); break;
+        case KK_OP_Q3K_BF16: consume_q3k(D, pay_off, nblk, 0, cwarp, lane); break;
+        case KK_OP_Q5K_BF16: consume_q5k(D, pay_off, nblk, 0, cwarp, lane); break;
+        default: return -1;
+      }
+    }
+  return g.err;
+}
+
+// A whole segment the way the kernel walks it: the producer's per-tile arithmetic (kk_block_tile, the same function the
+// kernel calls), the 16-byte aligned superset its bulk copy brings into the stage (pay_off = source address & 15), then the
+// consumers.  `src` holds the segment's blocks; src_misalign (0..15) is the alignment class of its first byte in the staged
+// chunk.  out/hits cover units * out_bytes_per_block bytes.  Returns like kk_emul_dequant_tile.
+extern "C" int kk_emul_dequant_segment(uint32_t op, const uint8_t* src, uint64_t units, uint32_t src_misalign, uint8_t* out, uint64_t out_bytes,
+                                       uint8_t* hits) {
+  const KKBlockGeom gm = kk_block_geom(op);
+  if (!gm.block_bytes) return -1;
+  KKSeg seg{};
+  seg.op = op;
+  seg.units = units;
+  seg.src_off = src_misalign;  // pretend the launch's src base is 16-byte aligned and the segment starts here
+  memset(hits, 0, out_bytes / 16);
+  static thread_local uint8_t stage[KK_TILE_SRC_BYTES + KK_STAGE_PAD];
+  const uint64_t n_tiles = kk_seg_tiles(op, units, 0);
+  for (uint64_t t = 0; t < n_tiles; ++t) {
+    const KKBlockTile bt = kk_block_tile(seg, (uint32_t)t);
+    const uint32_t mis = (uint32_t)(bt.in_off & 15u);
+    const uint32_t tx = (mis + bt.in_bytes + 15u) & ~15u;  // what the producer asks TMA for
+    if (tx > sizeof stage) return 5;
+    memset(stage, 0xEE, sizeof stage);
+    // bytes before the payload / after it come from the neighbouring source bytes on the GPU; the consumers must not depend on them
+    memcpy(stage + mis, src + (bt.in_off - src_misalign), bt.in_bytes);
+    g = Emu{};
+    g.tile = stage; g.tile_bytes = mis + bt.in_bytes; g.out = out; g.out_bytes = out_bytes; g.hits = hits;
+    const Dsts D{0};
+    for (int cwarp = 0; cwarp < kConsumerWarps; ++cwarp)
+      for (int lane = 0; lane < 32; ++lane) {
+        switch (op) {
+          case KK_OP_Q8_0_BF16: consume_q8_0(D, mis, bt.n_blocks, bt.dst_off, cwarp, lane); break;
+          case KK_OP_Q6K_BF16: consume_q6k(D, mis, bt.n_blocks, bt.dst_off, cwarp, lane); break;
+          case KK_OP_Q4_0_BF16: consume_legacy32<KK_Q4_0_BLOCK_BYTES, false, false>(D, mis, bt.n_blocks, bt.dst_off, cwarp, lane); break;
+          case KK_OP_Q4_1_BF16: consume_legacy32<KK_Q4_1_BLOCK_BYTES, true, false>(D, mis, bt.n_blocks, bt.dst_off, cwarp, lane); break;
+          case KK_OP_Q5_0_BF16: consume_legacy32<KK_Q5_0_BLOCK_BYTES, false, true>(D, mis, bt.n_blocks, bt.dst_off, cwarp, lane); break;
+          case KK_OP_Q5_1_BF16: consume_legacy32<KK_Q5_1_BLOCK_BYTES, true, true>(D, mis, bt.n_blocks, bt.dst_off, cwarp, lane); break;
+          case KK_OP_Q2K_BF16: consume_q2k(D, mis, bt.n_blocks, bt.dst_off, cwarp, lane); break;
+          case KK_OP_Q3K_BF16: consume_q3k(D, mis, bt.n_blocks, bt.dst_off, cwarp, lane); break;
+          case KK_OP_Q5K_BF16: consume_q5k(D, mis, bt.n_blocks, bt.dst_off, cwarp, lane); break;
+          default: return -1;
+        }
+      }
+    if (g.err) return g.err;
+  }
+  return 0;
+}
+
+// Geometry the kernel and the planner share (kk_ops.h), exported so the test can cross-check the Python-side tables.
+extern "C" void kk_emul_block_geom(uint32_t op, uint32_t* block_bytes, uint32_t* out_bytes, uint32_t* tile_blocks) {
+  const KKBlockGeom gm = kk_block_geom(op);
+  *block_bytes = gm.block_bytes; *out_bytes = gm.out_bytes; *tile_blocks = gm.tile_blocks;
+}

@@ -128,6 +128,44 @@ def make_gguf_mixed_quants():
     np.savez_compressed(p + ".bf16.npz", **outs)
 
 
+def make_gguf_legacy_and_k_quants():
+    """One tensor of each remaining legacy / K quant type (Q4_0, Q4_1, Q5_0, Q5_1, Q2_K, Q3_K, Q5_K), sizes chosen so that
+    tensor starts fall on different 16-byte phases; expected values from gguf.quants.dequantize."""
+    import gguf
+    from gguf import GGMLQuantizationType as Q
+    rng = np.random.Generator(np.random.Philox(key=79))
+
+    def blocks(nblk, bsz, doffs):
+        b = rng.integers(0, 256, size=(nblk, bsz), dtype=np.uint8)
+        for off in doffs:
+            e = rng.integers(5, 12, size=nblk, dtype=np.uint16)
+            m = rng.integers(0, 1024, size=nblk, dtype=np.uint16)
+            sgn = rng.integers(0, 2, size=nblk, dtype=np.uint16) << 15
+            b[:, off:off + 2] = ((e << 10) | m | sgn).astype("<u2").view(np.uint8).reshape(nblk, 2)
+        return b
+
+    p = os.path.join(HERE, "quants_f4.gguf")
+    w = gguf.GGUFWriter(p, "llama")
+    w.add_tensor("blk.0.attn_q.weight", blocks(3 * 3, 18, [0]).reshape(3, 3 * 18), raw_dtype=Q.Q4_0)            # [3, 96]
+    w.add_tensor("blk.0.attn_k.weight", blocks(2 * 5, 20, [0, 2]).reshape(2, 5 * 20), raw_dtype=Q.Q4_1)         # [2, 160]
+    w.add_tensor("blk.0.attn_v.weight", blocks(5 * 1, 22, [0]).reshape(5, 22), raw_dtype=Q.Q5_0)                # [5, 32]
+    w.add_tensor("blk.0.attn_output.weight", blocks(3 * 2, 24, [0, 2]).reshape(3, 2 * 24), raw_dtype=Q.Q5_1)    # [3, 64]
+    w.add_tensor("blk.0.ffn_gate.weight", blocks(3 * 1, 84, [80, 82]).reshape(3, 84), raw_dtype=Q.Q2_K)         # [3, 256]
+    w.add_tensor("blk.0.ffn_up.weight", blocks(2 * 2, 110, [108]).reshape(2, 2 * 110), raw_dtype=Q.Q3_K)        # [2, 512]
+    w.add_tensor("blk.0.ffn_down.weight", blocks(3 * 1, 176, [0, 2]).reshape(3, 176), raw_dtype=Q.Q5_K)         # [3, 256]
+    w.add_tensor("blk.0.attn_norm.weight", rng.standard_normal(12).astype(np.float32))
+    w.write_header_to_file(); w.write_kv_data_to_file(); w.write_tensors_to_file(); w.close()
+    r = gguf.GGUFReader(p)
+    exp, outs = [], {}
+    for t in r.tensors:
+        shape = [int(x) for x in reversed(t.shape.tolist())]
+        exp.append(dict(name=t.name, dtype=t.tensor_type.name, shape=shape, file_offset=int(t.data_offset), nbytes=int(t.n_bytes)))
+        f32 = gguf.quants.dequantize(np.array(t.data), t.tensor_type)
+        outs[t.name] = bits16(torch.from_numpy(np.ascontiguousarray(f32, dtype=np.float32)).to(torch.bfloat16)).reshape(-1)
+    json.dump(dict(tensors=exp, alignment=int(r.alignment), data_offset=int(r.data_offset)), open(p + ".expected.json", "w"), indent=1)
+    np.savez_compressed(p + ".bf16.npz", **outs)
+
+
 def make_sharded():
     from huggingface_hub import save_torch_state_dict
     d = os.path.join(HERE, "sharded")
@@ -158,7 +196,7 @@ def make_cast_vectors():
 
 
 if __name__ == "__main__":
-    make_safetensors(); make_gguf(); make_gguf_mixed_quants(); make_sharded(); make_cast_vectors()
+    make_safetensors(); make_gguf(); make_gguf_mixed_quants(); make_gguf_legacy_and_k_quants(); make_sharded(); make_cast_vectors()
     for r, _, fs in os.walk(HERE):
         for f in sorted(fs):
             p = os.path.join(r, f)

@@ -11,6 +11,12 @@ import numpy as np
 from oracle import oracle
 
 OP_COPY, OP_F32, OP_F16, OP_Q4K, OP_T_F32_BF16, OP_T_F16_BF16, OP_T_B16, OP_T_B32, OP_Q8_0, OP_Q6K, OP_ROWSPLIT = range(11)
+OP_Q4_0, OP_Q4_1, OP_Q5_0, OP_Q5_1, OP_Q2K, OP_Q3K, OP_Q5K = range(11, 18)
+# block-dequantising ops: op -> (source bytes per block, bf16 bytes per block, blocks per tile)   (csrc/kk_ops.h kk_block_geom)
+BLOCK_GEOM = {OP_Q4K: (144, 512, 224), OP_Q8_0: (34, 64, 960), OP_Q6K: (210, 512, 152), OP_Q4_0: (18, 64, 1816), OP_Q4_1: (20, 64, 1632),
+              OP_Q5_0: (22, 64, 1488), OP_Q5_1: (24, 64, 1360), OP_Q2K: (84, 512, 388), OP_Q3K: (110, 512, 296), OP_Q5K: (176, 512, 186)}
+BLOCK_DTYPE = {OP_Q4K: "Q4_K", OP_Q8_0: "Q8_0", OP_Q6K: "Q6_K", OP_Q4_0: "Q4_0", OP_Q4_1: "Q4_1", OP_Q5_0: "Q5_0", OP_Q5_1: "Q5_1",
+               OP_Q2K: "Q2_K", OP_Q3K: "Q3_K", OP_Q5K: "Q5_K"}
 
 
 def emulate_part(plan: dict, part: int, pool_bytes: int, exchange: dict | None = None) -> Tuple[np.ndarray, np.ndarray]:
@@ -38,8 +44,11 @@ def emulate_part(plan: dict, part: int, pool_bytes: int, exchange: dict | None =
                 assert sg["tile_begin"] == tiles, "tile_begin must be the running tile count of the chunk"
                 op, so, do, u = sg["op"], sg["src_off"], sg["dst_off"], sg["units"]
                 assert do % 16 == 0
-                src_bytes = {OP_COPY: u, OP_F32: 4 * u, OP_F16: 2 * u, OP_Q4K: 144 * u, OP_Q8_0: 34 * u, OP_Q6K: 210 * u, OP_ROWSPLIT: u,
-                             OP_T_F32_BF16: 4 * u * sg["p0"], OP_T_B32: 4 * u * sg["p0"], OP_T_F16_BF16: 2 * u * sg["p0"], OP_T_B16: 2 * u * sg["p0"]}[op]
+                if op in BLOCK_GEOM:
+                    src_bytes = BLOCK_GEOM[op][0] * u
+                else:
+                    src_bytes = {OP_COPY: u, OP_F32: 4 * u, OP_F16: 2 * u, OP_ROWSPLIT: u, OP_T_F32_BF16: 4 * u * sg["p0"], OP_T_B32: 4 * u * sg["p0"],
+                                 OP_T_F16_BF16: 2 * u * sg["p0"], OP_T_B16: 2 * u * sg["p0"]}[op]
                 assert so + src_bytes <= ch["buf_bytes"], "segment reads past the bytes staged for its chunk"
                 assert covered[so:so + src_bytes].all(), "segment consumes bytes no read put there"
                 if op == OP_ROWSPLIT:
@@ -67,15 +76,10 @@ def emulate_part(plan: dict, part: int, pool_bytes: int, exchange: dict | None =
                 elif op == OP_F16:
                     out = oracle.f16_bits_to_bf16(buf[so:so + 2 * u].copy().view("<u2")).view(np.uint8)
                     tiles += -(-u // 16384)
-                elif op == OP_Q4K:
-                    out = oracle.dequant_q4k_bf16(buf[so:so + 144 * u].reshape(-1, 144)).reshape(-1).view(np.uint8)
-                    tiles += -(-u // 224)
-                elif op == OP_Q8_0:
-                    out = oracle.dequant_q8_0_bf16(buf[so:so + 34 * u].reshape(-1, 34)).reshape(-1).view(np.uint8)
-                    tiles += -(-u // 960)
-                elif op == OP_Q6K:
-                    out = oracle.dequant_q6k_bf16(buf[so:so + 210 * u].reshape(-1, 210)).reshape(-1).view(np.uint8)
-                    tiles += -(-u // 152)
+                elif op in BLOCK_GEOM:
+                    bb, _, tb = BLOCK_GEOM[op]
+                    out = oracle.dequant_bf16(BLOCK_DTYPE[op], buf[so:so + bb * u].reshape(-1, bb)).reshape(-1).view(np.uint8)
+                    tiles += -(-u // tb)
                 else:
                     C, R, r0 = sg["p0"], sg["p1"], sg["p2"]
                     es = 4 if op in (OP_T_F32_BF16, OP_T_B32) else 2

@@ -1,0 +1,116 @@
+"""CPU tier: the device dequantisers (kukeon_b200/csrc/kk_dequant.cuh), compiled for the host by tests/emul and played lane
+by lane, against the oracle (which tests/test_oracle_values.py pins to gguf-py bit for bit).
+
+Covers every block op that lives in that header: Q8_0 and Q6_K (proven on the GPU in round 1 — they validate the
+harness) and the §8(f4) additions Q4_0, Q4_1, Q5_0, Q5_1, Q2_K, Q3_K, Q5_K.  Cases: a full tile (KK_*_TILE_BLOCKS), ragged
+block counts around the warp-iteration sizes, and every source alignment class a tile can start at (pay_off 0..15)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests import helpers
+from tools import synth
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+OPS = {"Q8_0": helpers.OP_Q8_0, "Q6_K": helpers.OP_Q6K, "Q4_0": helpers.OP_Q4_0, "Q4_1": helpers.OP_Q4_1, "Q5_0": helpers.OP_Q5_0,
+       "Q5_1": helpers.OP_Q5_1, "Q2_K": helpers.OP_Q2K, "Q3_K": helpers.OP_Q3K, "Q5_K": helpers.OP_Q5K}
+ERR = {1: "shared-memory load outside the staged tile", 2: "misaligned 16/32-bit shared-memory load", 3: "store outside the output window or not 16-byte aligned",
+       4: "two lanes stored the same 16 bytes"}
+
+
+@pytest.fixture(scope="module")
+def emul():
+    subprocess.run(["make", "-C", os.path.join(_HERE, "emul"), "-s"], check=True)
+    L = C.CDLL(os.path.join(_HERE, "emul", "_build", "libkk_dequant_emul.so"))
+    L.kk_emul_dequant_tile.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
+    L.kk_emul_dequant_tile.restype = C.c_int
+    L.kk_emul_dequant_segment.argtypes = [C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
+    L.kk_emul_dequant_segment.restype = C.c_int
+    L.kk_emul_block_geom.argtypes = [C.c_uint32] + [C.POINTER(C.c_uint32)] * 3
+    L.kk_emul_block_geom.restype = None
+    return L
+
+
+def geom(L, op):
+    a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    L.kk_emul_block_geom(op, C.byref(a), C.byref(b), C.byref(c))
+    return a.value, b.value, c.value
+
+
+def run_tile(L, dtype, blocks, pay_off):
+    op = OPS[dtype]
+    nel, nb, _ = oracle.BLOCK_QUANTS[dtype]
+    n = blocks.shape[0]
+    tile = np.full(pay_off + n * nb, 0xA5, np.uint8)  # exactly as many bytes as the producer's bulk copy brings in
+    tile[pay_off:] = blocks.reshape(-1)
+    out = np.zeros(n * nel * 2, np.uint8)
+    hits = np.zeros(out.size // 16, np.uint8)
+    rc = L.kk_emul_dequant_tile(op, tile.ctypes.data, tile.size, pay_off, n, out.ctypes.data, out.size, hits.ctypes.data)
+    assert rc == 0, f"{dtype}: {ERR.get(rc, rc)}"
+    assert (hits == 1).all(), f"{dtype}: {int((hits != 1).sum())} output vectors not stored exactly once"
+    return out.view(np.uint16).reshape(n, nel)
+
+
+@pytest.mark.parametrize("dtype", sorted(OPS))
+def test_geometry_tables_agree(emul, dtype):
+    nel, nb, _ = oracle.BLOCK_QUANTS[dtype]
+    bb, ob, tb = geom(emul, OPS[dtype])
+    assert (bb, ob) == (nb, 2 * nel)
+    assert helpers.BLOCK_GEOM[OPS[dtype]] == (bb, ob, tb)
+    assert bb * tb <= 32768 and (bb * tb) % 16 == 0
+
+
+@pytest.mark.parametrize("dtype", sorted(OPS))
+def test_full_tile_finite_scales(emul, dtype):
+    nel, nb, _ = oracle.BLOCK_QUANTS[dtype]
+    tb = geom(emul, OPS[dtype])[2]
+    blocks = synth.gen_bytes(dtype, nb * tb, 11, 3).reshape(tb, nb)
+    assert (run_tile(emul, dtype, blocks, 0) == oracle.dequant_bf16(dtype, blocks)).all()
+
+
+@pytest.mark.parametrize("dtype", sorted(OPS))
+def test_ragged_counts_and_every_alignment_random_bytes(emul, dtype):
+    """Fully random bytes (Inf/NaN scales included: NaN -> 0x7FFF on both sides) at every start alignment a tile can have."""
+    nel, nb, _ = oracle.BLOCK_QUANTS[dtype]
+    per_iter = 8 if nel == 32 else 1  # blocks one warp iteration covers
+    rng = np.random.default_rng(5)
+    counts = [1, 2, per_iter - 1 or 1, per_iter, per_iter + 1, 16 * per_iter - 1, 16 * per_iter, 16 * per_iter + 1, 16 * per_iter + 5, 37 * per_iter + 3]
+    for k, n in enumerate(counts):
+        blocks = rng.integers(0, 256, (n, nb), dtype=np.uint8)
+        for pay_off in ([0, 2, 4, 8, 10] if k else range(16)):
+            got = run_tile(emul, dtype, blocks, pay_off)
+            assert (got == oracle.dequant_bf16(dtype, blocks)).all(), (dtype, n, pay_off)
+
+
+@pytest.mark.parametrize("dtype", sorted(OPS))
+def test_multi_tile_segments_walked_like_the_producer(emul, dtype):
+    """2.4 tiles of every type, starting 16-byte aligned and not: the per-tile split (kk_block_tile, shared with the kernel)
+    hands every block to exactly one tile and every output vector is stored exactly once at the right pool offset."""
+    nel, nb, _ = oracle.BLOCK_QUANTS[dtype]
+    tb = geom(emul, OPS[dtype])[2]
+    n = 2 * tb + tb * 2 // 5 + 3
+    blocks = synth.gen_bytes(dtype, nb * n, 13, 5).reshape(n, nb)
+    want = oracle.dequant_bf16(dtype, blocks)
+    for mis in (0, 8, 6):
+        out = np.zeros(n * nel * 2, np.uint8)
+        hits = np.zeros(out.size // 16, np.uint8)
+        rc = emul.kk_emul_dequant_segment(OPS[dtype], blocks.ctypes.data, n, mis, out.ctypes.data, out.size, hits.ctypes.data)
+        assert rc == 0, f"{dtype}: {ERR.get(rc, rc)}"
+        assert (hits == 1).all() and (out.view(np.uint16).reshape(n, nel) == want).all(), (dtype, mis)
+
+
+def test_harness_sees_wrong_answers(emul):
+    """The checker is live: feeding Q5_0 blocks to the Q4_0 function must not reproduce the Q5_0 oracle."""
+    blocks = synth.gen_bytes("Q5_0", 22 * 9 * 8, 2, 1).reshape(-1, 22)
+    tile = blocks.reshape(-1)
+    n = tile.size // 18
+    out = np.zeros(n * 64, np.uint8)
+    hits = np.zeros(out.size // 16, np.uint8)
+    assert emul.kk_emul_dequant_tile(helpers.OP_Q4_0, tile.ctypes.data, n * 18, 0, n, out.ctypes.data, out.size, hits.ctypes.data) == 0
+    assert not (out.view(np.uint16)[: 32 * 8] == oracle.dequant_bf16("Q5_0", blocks)[:8].reshape(-1)).all()
+    # and a tile shorter than the blocks it is said to hold is reported, not read past
+    assert emul.kk_emul_dequant_tile(helpers.OP_Q4_0, tile.ctypes.data, n * 18 - 1, 0, n, out.ctypes.data, out.size, hits.ctypes.data) == 1

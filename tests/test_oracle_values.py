@@ -140,3 +140,54 @@ def test_mixed_quant_golden_file_vs_gguf_py():
         assert (got == outs[t["name"]]).all(), t["name"]
         seen.add(t["dtype"])
     assert {"Q4_K", "Q6_K", "Q8_0", "F32"} <= seen
+
+
+F4_TYPES = ["Q4_0", "Q4_1", "Q5_0", "Q5_1", "Q2_K", "Q3_K", "Q5_K"]
+
+
+@pytest.mark.parametrize("dtype", F4_TYPES + ["Q4_K", "Q6_K", "Q8_0"])
+def test_every_block_quant_vs_gguf_py_live_bit_exact(coracle, dtype):
+    """§8(f4): numpy restatement and C twin against gguf.quants.dequantize on (a) fully random bytes — Inf/NaN scales
+    included, compared as fp32 bit patterns with NaN == NaN — and (b) finite-scale synthetic blocks after RNE to bf16."""
+    from gguf import GGMLQuantizationType, quants
+    from tools import synth
+    nel, nb, fn = oracle.BLOCK_QUANTS[dtype]
+    qt = getattr(GGMLQuantizationType, dtype)
+    rng = np.random.Generator(np.random.Philox(key=1234))
+    b = rng.integers(0, 256, size=(4096, nb), dtype=np.uint8)
+    with np.errstate(all="ignore"):
+        ref, got = quants.dequantize(b, qt), fn(b)
+    assert ((ref.view(np.uint32) == got.view(np.uint32)) | (np.isnan(ref) & np.isnan(got))).all()
+    b = synth.gen_bytes(dtype, nb * 5000, 9, 4).reshape(-1, nb)
+    ref = bits16(torch.from_numpy(quants.dequantize(b, qt)).to(torch.bfloat16))
+    assert (oracle.dequant_bf16(dtype, b) == ref).all() and (coracle.dequant_to_bf16(dtype, b) == ref).all()
+    # extremes: all-zero and all-ones payloads with d = dmin = 1.0 and the largest finite half
+    for fill in (0x00, 0xFF):
+        for h in (0x3C00, 0x7BFF, 0xBC00):
+            e = np.full((2, nb), fill, np.uint8)
+            for off in {"Q4_0": [0], "Q4_1": [0, 2], "Q5_0": [0], "Q5_1": [0, 2], "Q2_K": [80, 82], "Q3_K": [108], "Q5_K": [0, 2], "Q4_K": [0, 2],
+                        "Q6_K": [208], "Q8_0": [0]}[dtype]:
+                e[:, off:off + 2] = np.array([h], "<u2").view(np.uint8)
+            with np.errstate(all="ignore"):
+                ref = bits16(torch.from_numpy(quants.dequantize(e, qt)).to(torch.bfloat16))
+            nan = (ref & 0x7FFF) > 0x7F80
+            got, cgot = oracle.dequant_bf16(dtype, e), coracle.dequant_to_bf16(dtype, e)
+            assert ((got == ref) | (nan & (got == 0x7FFF))).all() and (got == cgot).all()
+
+
+def test_legacy_and_k_quant_golden_file_vs_gguf_py():
+    import json
+    p = os.path.join(G, "quants_f4.gguf")
+    exp = json.load(open(p + ".expected.json"))
+    outs = np.load(p + ".bf16.npz")
+    raw = open(p, "rb").read()
+    shards, recs = oracle.index_path(p)
+    assert [(r["name"], r["dtype"], r["shape"], r["file_offset"], r["nbytes"]) for r in recs] == \
+        [(t["name"], t["dtype"], t["shape"], t["file_offset"], t["nbytes"]) for t in exp["tensors"]]
+    seen = set()
+    for t in exp["tensors"]:
+        rec = dict(name=t["name"], dtype=t["dtype"], shape=t["shape"], nbytes=t["nbytes"])
+        got = oracle.convert_tensor(rec, raw[t["file_offset"]:t["file_offset"] + t["nbytes"]]).view(np.uint16)
+        assert (got == outs[t["name"]]).all(), t["name"]
+        seen.add(t["dtype"])
+    assert set(F4_TYPES) <= seen

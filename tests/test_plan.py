@@ -179,14 +179,50 @@ def test_mixtral_gguf_plan(native, tmp_path):
 
 
 def test_unsupported_quant_is_refused_at_plan_time(native, tmp_path):
+    """Q8_K is llama.cpp's intermediate activation format (never a weight type in released files) and the one ggml block
+    type the index knows but the kernel does not dequantise."""
     import struct
-    p = str(tmp_path / "q5k.gguf")
-    head = struct.pack("<IIQQ", 0x46554747, 3, 1, 0) + struct.pack("<Q", 1) + b"w" + struct.pack("<I", 1) + struct.pack("<Q", 256) + struct.pack("<IQ", 13, 0)
+    p = str(tmp_path / "q8k.gguf")
+    head = struct.pack("<IIQQ", 0x46554747, 3, 1, 0) + struct.pack("<Q", 1) + b"w" + struct.pack("<I", 1) + struct.pack("<Q", 256) + struct.pack("<IQ", 15, 0)
     head += b"\0" * ((-len(head)) % 32)
-    open(p, "wb").write(head + b"\0" * 192)
-    assert gpupool.index(p)[0]["dtype"] == "Q5_K"  # indexing works ...
-    with pytest.raises(gpupool.ErrUnsupported, match="Q5_K"):  # ... loading is refused, never approximated
+    open(p, "wb").write(head + b"\0" * 320)
+    assert gpupool.index(p)[0]["dtype"] == "Q8_K"  # indexing works ...
+    with pytest.raises(gpupool.ErrUnsupported, match="Q8_K"):  # ... loading is refused, never approximated
         gpupool.plan_describe(p)
+
+
+F4_MIX = ["Q4_0", "Q4_1", "Q5_0", "Q5_1", "Q2_K", "Q3_K", "Q5_K"]
+
+
+def f4_tensors(hidden=256, ffn=768, layers=2, vocab=512):
+    """Every §8(f4) type in one llama-shaped inventory (column-parallel names so that SCATTER slices whole rows of blocks)."""
+    t = [("token_embd.weight", "Q2_K", [vocab, hidden])]
+    for i in range(layers):
+        p = f"blk.{i}."
+        t += [(p + "attn_norm.weight", "F32", [hidden]), (p + "attn_q.weight", "Q4_0", [hidden, hidden]), (p + "attn_k.weight", "Q4_1", [hidden // 4, hidden]),
+              (p + "attn_v.weight", "Q5_0", [hidden // 4, hidden]), (p + "attn_output.weight", "Q5_1", [hidden, hidden]),
+              (p + "ffn_gate.weight", "Q3_K", [ffn, hidden]), (p + "ffn_up.weight", "Q5_K", [ffn, hidden]), (p + "ffn_down.weight", "Q2_K", [hidden, ffn])]
+    t += [("output_norm.weight", "F32", [hidden]), ("output.weight", "Q5_K", [vocab, hidden])]
+    return t
+
+
+def test_legacy_and_k_quant_plan(native, tmp_path):
+    p = str(tmp_path / "f4.gguf")
+    synth.write_gguf(p, f4_tensors(), 11)
+    plan = run_case(p, chunk=1 * MB)
+    ops = {sg["op"] for ch in plan["parts"][0]["chunks"] for sg in ch["segs"]}
+    assert {helpers.OP_Q4_0, helpers.OP_Q4_1, helpers.OP_Q5_0, helpers.OP_Q5_1, helpers.OP_Q2K, helpers.OP_Q3K, helpers.OP_Q5K} <= ops
+    run_case(p, mode=gpupool.MODE_BROADCAST, n_parts=3, chunk=1 * MB)
+    plan = run_case(p, mode=gpupool.MODE_SCATTER, n_parts=4, chunk=1 * MB)
+    lay = {t["name"]: t for t in plan["layouts"][1]["tensors"]}
+    assert lay["blk.0.ffn_up.weight"]["slice_dim"] == 0 and lay["blk.0.ffn_up.weight"]["shape"] == [192, 256]
+    assert lay["blk.0.ffn_down.weight"]["slice_dim"] is None  # dim-1 slices would cut quantised blocks
+    run_case(os.path.join(G, "quants_f4.gguf"))
+    # tensors bigger than one tile of every type, so that tile boundaries inside a tensor are exercised (Q4_0: 1816 blocks/tile)
+    big = [(f"blk.{i}.ffn_up.weight", dt, [96, 2048]) for i, dt in enumerate(F4_MIX)]
+    p2 = str(tmp_path / "f4big.gguf")
+    synth.write_gguf(p2, big, 12)
+    run_case(p2, chunk=1 * MB)
 
 
 def q4km_tensors(hidden=256, ffn=768, layers=2, vocab=512):

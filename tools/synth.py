@@ -21,8 +21,11 @@ from typing import Dict, List, Sequence, Tuple
 import numpy as np
 
 ST_ITEMSIZE = {"F32": 4, "F16": 2, "BF16": 2, "I64": 8, "I32": 4, "U8": 1, "I8": 1, "BOOL": 1, "F64": 8, "I16": 2, "U16": 2}
-GGML = {"F32": (0, 1, 4), "F16": (1, 1, 2), "Q4_K": (12, 256, 144), "BF16": (30, 1, 2), "Q8_0": (8, 32, 34), "Q6_K": (14, 256, 210)}
-_KIND = {"BF16": 1, "F16": 2, "F32": 3, "Q4_K": 4, "Q8_0": 5, "Q6_K": 6}
+GGML = {"F32": (0, 1, 4), "F16": (1, 1, 2), "Q4_K": (12, 256, 144), "BF16": (30, 1, 2), "Q8_0": (8, 32, 34), "Q6_K": (14, 256, 210),
+        "Q4_0": (2, 32, 18), "Q4_1": (3, 32, 20), "Q5_0": (6, 32, 22), "Q5_1": (7, 32, 24), "Q2_K": (10, 256, 84), "Q3_K": (11, 256, 110),
+        "Q5_K": (13, 256, 176)}
+_KIND = {"BF16": 1, "F16": 2, "F32": 3, "Q4_K": 4, "Q8_0": 5, "Q6_K": 6, "Q4_0": 7, "Q4_1": 8, "Q5_0": 9, "Q5_1": 10, "Q2_K": 11, "Q3_K": 12,
+         "Q5_K": 13}
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libkk_synth.so")
 _lib = None
@@ -47,7 +50,7 @@ def _c():
 
 def gen_bytes(dtype: str, nbytes: int, seed: int, idx: int) -> np.ndarray:
     """Content of a whole tensor of file dtype `dtype` (BF16/F16: finite patterns; F32: U(-0.04,0.04);
-    Q4_K: random blocks with finite d/dmin in [2^-10, 2^-4]; anything else: random bytes)."""
+    block-quantised types: random blocks whose fp16 scales are finite, magnitude in [2^-10, 2^-4]; anything else: random bytes)."""
     a = np.empty(nbytes, np.uint8)
     _c().synth_fill(a.ctypes.data_as(C.c_void_p), nbytes, _KIND.get(dtype, 0), seed, idx)
     return a

@@ -14,7 +14,8 @@
 #include <omp.h>
 #endif
 
-enum { K_BYTES = 0, K_BF16 = 1, K_F16 = 2, K_F32 = 3, K_Q4K = 4, K_Q8_0 = 5, K_Q6K = 6 };
+enum { K_BYTES = 0, K_BF16 = 1, K_F16 = 2, K_F32 = 3, K_Q4K = 4, K_Q8_0 = 5, K_Q6K = 6,
+       K_Q4_0 = 7, K_Q4_1 = 8, K_Q5_0 = 9, K_Q5_1 = 10, K_Q2K = 11, K_Q3K = 12, K_Q5K = 13 };
 
 static inline uint64_t mix64(uint64_t x) {
   x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
@@ -69,14 +70,43 @@ static void fix_scale(uint8_t* buf, uint64_t first_block, uint64_t nblocks, uint
     memcpy(buf + bsz * b + doff, &d, 2);
   }
 }
-static uint64_t block_bytes(int kind) { return kind == K_Q4K ? 144 : kind == K_Q8_0 ? 34 : kind == K_Q6K ? 210 : 0; }
+/* The later kinds: block size, offset of the fp16 scale d and of the second fp16 (min / dmin; -1 when the type has none). */
+typedef struct { uint64_t bsz; int d_off, m_off; } blk_geom;
+static blk_geom geom_of(int kind) {
+  switch (kind) {
+    case K_Q4_0: return (blk_geom){18, 0, -1};
+    case K_Q4_1: return (blk_geom){20, 0, 2};
+    case K_Q5_0: return (blk_geom){22, 0, -1};
+    case K_Q5_1: return (blk_geom){24, 0, 2};
+    case K_Q2K: return (blk_geom){84, 80, 82};
+    case K_Q3K: return (blk_geom){110, 108, -1};
+    case K_Q5K: return (blk_geom){176, 0, 2};
+    default: return (blk_geom){0, 0, -1};
+  }
+}
+static uint64_t block_bytes(int kind) {
+  return kind == K_Q4K ? 144 : kind == K_Q8_0 ? 34 : kind == K_Q6K ? 210 : geom_of(kind).bsz;
+}
+/* Overwrite the fp16 scale(s) of a run of blocks so that every block dequantises to finite values. */
+static void fix_blocks(uint8_t* buf, uint64_t first_block, uint64_t nblocks, int kind, uint64_t seed, uint64_t idx) {
+  if (kind == K_Q4K) fix_q4k(buf, first_block, nblocks, seed, idx);
+  else if (kind == K_Q8_0) fix_scale(buf, first_block, nblocks, 34, 0, seed, idx);
+  else if (kind == K_Q6K) fix_scale(buf, first_block, nblocks, 210, 208, seed, idx);
+  else {
+    const blk_geom g = geom_of(kind);
+    if (!g.bsz) return;
+    fix_scale(buf, first_block, nblocks, g.bsz, (uint64_t)g.d_off, seed, idx);
+    if (g.m_off >= 0) fix_scale(buf, first_block, nblocks, g.bsz, (uint64_t)g.m_off, seed ^ 0x3117ull, idx);
+  }
+}
 
 /* Generate bytes [0, nbytes) of tensor idx and pwrite them at file_off. nbytes % 8 may be non-zero.
  * Q4_K: nbytes must be a multiple of 144.  Returns 0 or -errno. */
 int synth_write(int fd, uint64_t file_off, uint64_t nbytes, int kind, uint64_t seed, uint64_t idx) {
-  const uint64_t CH = kind == K_Q4K ? (144ull * 8 * 7168) : kind == K_Q8_0 ? (136ull * 61440) : kind == K_Q6K ? (840ull * 9984)
-                                    : (8ull << 20); /* multiple of 8 and of the block size */
   const uint64_t bsz = block_bytes(kind);
+  const uint64_t CH = kind == K_Q4K ? (144ull * 8 * 7168) : kind == K_Q8_0 ? (136ull * 61440) : kind == K_Q6K ? (840ull * 9984)
+                      : bsz ? (bsz * 8) * ((8ull << 20) / (bsz * 8))
+                            : (8ull << 20); /* multiple of 8 and of the block size */
   const uint64_t nch = (nbytes + CH - 1) / CH;
   int err = 0;
 #pragma omp parallel
@@ -87,9 +117,7 @@ int synth_write(int fd, uint64_t file_off, uint64_t nbytes, int kind, uint64_t s
       const uint64_t b0 = c * CH;
       const uint64_t n = nbytes - b0 < CH ? nbytes - b0 : CH;
       fill_words(buf, b0 / 8, (n + 7) / 8, bsz ? K_BYTES : kind, seed, idx);
-      if (kind == K_Q4K) fix_q4k(buf, b0 / 144, n / 144, seed, idx);
-      else if (kind == K_Q8_0) fix_scale(buf, b0 / 34, n / 34, 34, 0, seed, idx);
-      else if (kind == K_Q6K) fix_scale(buf, b0 / 210, n / 210, 210, 208, seed, idx);
+      if (bsz) fix_blocks(buf, b0 / bsz, n / bsz, kind, seed, idx);
       uint64_t done = 0;
       while (done < n) {
         ssize_t w = pwrite(fd, buf + done, n - done, (off_t)(file_off + b0 + done));
@@ -116,9 +144,7 @@ void synth_fill(uint8_t* dst, uint64_t nbytes, int kind, uint64_t seed, uint64_t
     fill_words(tmp, nw, 1, wk, seed, idx);
     memcpy(dst + 8 * nw, tmp, nbytes & 7);
   }
-  if (kind == K_Q4K) fix_q4k(dst, 0, nbytes / 144, seed, idx);
-  else if (kind == K_Q8_0) fix_scale(dst, 0, nbytes / 34, 34, 0, seed, idx);
-  else if (kind == K_Q6K) fix_scale(dst, 0, nbytes / 210, 210, 208, seed, idx);
+  if (block_bytes(kind)) fix_blocks(dst, 0, nbytes / block_bytes(kind), kind, seed, idx);
 }
 
 /* torchrun exports OMP_NUM_THREADS=1; callers that want all cores say so explicitly. */
