@@ -103,7 +103,8 @@ std::vector<int> numa_cpus_of_device(int ordinal) {
   if (!f) return cpus;
   char buf[4096] = {0};
   if (fgets(buf, sizeof buf, f)) {
-    for (char* tok = strtok(buf, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+    char* save = nullptr;  // strtok_r: kk_open may run on several threads at once
+    for (char* tok = strtok_r(buf, ",\n", &save); tok; tok = strtok_r(nullptr, ",\n", &save)) {
       int a, b;
       if (sscanf(tok, "%d-%d", &a, &b) == 2) { for (int i = a; i <= b; ++i) cpus.push_back(i); }
       else if (sscanf(tok, "%d", &a) == 1) cpus.push_back(a);
@@ -133,6 +134,30 @@ struct ErrorSink {
   }
   void rethrow() {
     if (first) std::rethrow_exception(first);
+  }
+};
+
+// CUDA events / scratch device memory that must not leak when a KK_CUDA check throws half way through a function.
+struct EventSet {
+  std::vector<cudaEvent_t> ev;
+  explicit EventSet(size_t n = 0) : ev(n, nullptr) {}
+  cudaEvent_t& operator[](size_t i) { return ev[i]; }
+  size_t size() const { return ev.size(); }
+  void create_all() {
+    for (auto& e : ev) KK_CUDA(cudaEventCreate(&e));
+  }
+  ~EventSet() {
+    for (auto e : ev)
+      if (e) cudaEventDestroy(e);
+  }
+  EventSet(const EventSet&) = delete;
+  EventSet& operator=(const EventSet&) = delete;
+  EventSet(EventSet&& o) noexcept : ev(std::move(o.ev)) { o.ev.clear(); }
+};
+struct DevScratch {
+  void* p = nullptr;
+  ~DevScratch() {
+    if (p) cudaFree(p);
   }
 };
 
@@ -415,7 +440,7 @@ void free_raw(kk_model* m) {
 void convert_local_all(kk_model* m, float* ms_total) {
   kk_ctx* c = m->ctx;
   const size_t nl = m->dev_idx.size();
-  std::vector<cudaEvent_t> e0(nl), e1(nl);
+  EventSet e0(nl), e1(nl);
   for (size_t li = 0; li < nl; ++li) {
     Device& dev = c->devs[(size_t)m->dev_idx[li]];
     auto& R = m->raw[li];
@@ -443,8 +468,6 @@ void convert_local_all(kk_model* m, float* ms_total) {
     float ms = 0.f;
     KK_CUDA(cudaEventElapsedTime(&ms, e0[li], e1[li]));
     if (ms > worst) worst = ms;
-    cudaEventDestroy(e0[li]);
-    cudaEventDestroy(e1[li]);
   }
   if (ms_total) *ms_total = worst;
 }
@@ -482,6 +505,7 @@ void destroy_model(kk_model* m) {
     cudaSetDevice(d.ordinal);
     if (m->pools[i]) {
       cudaFree(m->pools[i]);
+      std::lock_guard<std::mutex> g(c->mu);  // model_load checks the budget under the same lock
       d.pool_in_use -= m->pool_bytes[i];
     }
     if (i < m->d_segs.size() && m->d_segs[i]) cudaFree(m->d_segs[i]);
@@ -765,6 +789,7 @@ kk_model* model_load(kk_ctx* c, const std::string& path, const kk_load_opts& opt
 }
 
 void model_load_part(kk_model* m) {
+  std::lock_guard<std::mutex> op(m->op_mu);
   if (is_raw(m) && m->raw.empty()) fail(KK_ESTATE, "the raw image of this model has been released");
   do_load(m);
   std::lock_guard<std::mutex> g(m->ctx->mu);
@@ -772,6 +797,7 @@ void model_load_part(kk_model* m) {
 }
 
 void model_convert_local(kk_model* m, float* ms_total) {
+  std::lock_guard<std::mutex> op(m->op_mu);
   if (!is_raw(m) || m->raw.empty()) fail(KK_ESTATE, "kk_convert_local only applies to KK_FANOUT_RAW models with a live raw image");
   convert_local_all(m, ms_total);
   std::lock_guard<std::mutex> g(m->ctx->mu);
@@ -788,6 +814,7 @@ void model_export_raw(kk_model* m, int li, void* handle_out) {
 }
 
 void model_peer_attach_raw(kk_model* m, int rank, const void* handle) {
+  std::lock_guard<std::mutex> op(m->op_mu);  // the destination tables are read by a running load
   if (!is_raw(m)) fail(KK_ESTATE, "raw peer attach needs a KK_FANOUT_RAW model");
   if (m->opts.part_count <= 1) fail(KK_ESTATE, "peer attach needs a multi-process (part_count > 1) model");
   if (rank < 0 || rank >= m->opts.part_count || rank == m->opts.part_index) fail(KK_EINVAL, "bad peer rank %d", rank);
@@ -813,6 +840,7 @@ void model_release(kk_model* m) {
 }
 
 void model_peer_attach(kk_model* m, int rank, const void* handle, bool is_ipc) {
+  std::lock_guard<std::mutex> op(m->op_mu);  // the destination tables are read by a running load
   if (m->opts.part_count <= 1) fail(KK_ESTATE, "peer attach needs a multi-process (part_count > 1) model");
   if (rank < 0 || rank >= m->opts.part_count || rank == m->opts.part_index) fail(KK_EINVAL, "bad peer rank %d", rank);
   if (m->plan.mode != KK_MODE_BROADCAST && !(m->plan.mode == KK_MODE_SCATTER && (m->plan.flags & KK_LOAD_SCATTER_EXCHANGE)))
@@ -834,6 +862,7 @@ void model_peer_attach(kk_model* m, int rank, const void* handle, bool is_ipc) {
 }
 
 void model_peer_detach_all(kk_model* m) {
+  std::lock_guard<std::mutex> op(m->op_mu);  // the destination tables are read by a running load
   Device& d = m->ctx->devs[(size_t)m->dev_idx[0]];
   cudaSetDevice(d.ordinal);
   for (int r = 0; r < KK_MAX_DEVICES; ++r) {
@@ -922,6 +951,7 @@ std::string model_stats(kk_model* m) {
 // resident image: kernel-stage measurement with the source bytes already in HBM
 // ---------------------------------------------------------------------------------------------
 void model_stage_resident(kk_model* m) {
+  std::lock_guard<std::mutex> op(m->op_mu);
   if (is_raw(m)) {  // RAW: the resident image IS the raw image; stage this process's own part(s), no fan-out
     if (m->raw.empty()) fail(KK_ESTATE, "the raw image of this model has been released");
     FdSet fds(m->plan.index.shards);
@@ -986,6 +1016,7 @@ void model_stage_resident(kk_model* m) {
 }
 
 void model_unstage_resident(kk_model* m) {
+  std::lock_guard<std::mutex> op(m->op_mu);
   if (is_raw(m)) return;  // the raw image lives as long as a deferred RAW model does
   free_resident(m);
 }
@@ -994,7 +1025,7 @@ void model_unstage_resident(kk_model* m) {
 static void raw_fanout_resident(kk_model* m, float* ms_total, float* ms_per_launch, size_t cap, size_t* n_launches) {
   kk_ctx* c = m->ctx;
   const size_t nl = m->dev_idx.size();
-  std::vector<cudaEvent_t> e0(nl), e1(nl);
+  EventSet e0(nl), e1(nl);
   size_t launched = 0;
   for (size_t li = 0; li < nl; ++li) {
     Device& dev = c->devs[(size_t)m->dev_idx[li]];
@@ -1020,8 +1051,9 @@ static void raw_fanout_resident(kk_model* m, float* ms_total, float* ms_per_laun
         segs[ci] = sg;
       }
       if (segs.size() > kMaxSegsPerLaunch) fail(KK_EUNSUPPORTED, "too many chunks for one raw fan-out launch");
-      KKSeg* d_tmp = nullptr;
-      KK_CUDA(cudaMalloc((void**)&d_tmp, segs.size() * sizeof(KKSeg)));
+      DevScratch tmp;
+      KK_CUDA(cudaMalloc(&tmp.p, segs.size() * sizeof(KKSeg)));
+      KKSeg* d_tmp = (KKSeg*)tmp.p;
       KK_CUDA(cudaMemcpyAsync(d_tmp, segs.data(), segs.size() * sizeof(KKSeg), cudaMemcpyHostToDevice, dev.stream));
       KK_CUDA(cudaEventRecord(e0[li], dev.stream));
       L.src = m->raw[li].image;
@@ -1030,8 +1062,7 @@ static void raw_fanout_resident(kk_model* m, float* ms_total, float* ms_per_laun
       L.n_tiles = tiles;
       KK_CUDA(launch_convert(L, dev.sm_count, dev.stream));
       KK_CUDA(cudaEventRecord(e1[li], dev.stream));
-      KK_CUDA(cudaStreamSynchronize(dev.stream));
-      cudaFree(d_tmp);
+      KK_CUDA(cudaStreamSynchronize(dev.stream));  // tmp is freed on scope exit, after the launch that reads it has finished
       launched = 1;
     } else {
       KK_CUDA(cudaEventRecord(e1[li], dev.stream));
@@ -1045,8 +1076,6 @@ static void raw_fanout_resident(kk_model* m, float* ms_total, float* ms_per_laun
     float ms = 0.f;
     KK_CUDA(cudaEventElapsedTime(&ms, e0[li], e1[li]));
     if (ms > worst) worst = ms;
-    cudaEventDestroy(e0[li]);
-    cudaEventDestroy(e1[li]);
   }
   if (ms_total) *ms_total = worst;
   if (n_launches) *n_launches = launched;
@@ -1054,6 +1083,7 @@ static void raw_fanout_resident(kk_model* m, float* ms_total, float* ms_per_laun
 }
 
 void model_convert_resident(kk_model* m, float* ms_total, float* ms_per_launch, size_t cap, size_t* n_launches) {
+  std::lock_guard<std::mutex> op(m->op_mu);
   if (is_raw(m)) {
     if (m->raw.empty()) fail(KK_ESTATE, "the raw image of this model has been released");
     raw_fanout_resident(m, ms_total, ms_per_launch, cap, n_launches);
@@ -1062,15 +1092,16 @@ void model_convert_resident(kk_model* m, float* ms_total, float* ms_per_launch, 
   if (m->resident.size() != m->dev_idx.size()) fail(KK_ESTATE, "kk_stage_resident has not been called");
   kk_ctx* c = m->ctx;
   const size_t nl = m->dev_idx.size();
-  std::vector<std::vector<cudaEvent_t>> evs(nl);
+  std::vector<EventSet> evs;
+  evs.reserve(nl);
   size_t max_launches = 0;
   // enqueue on every local device first (they run concurrently), then collect
   for (size_t li = 0; li < nl; ++li) {
     Device& dev = c->devs[(size_t)m->dev_idx[li]];
     auto& R = m->resident[li];
     KK_CUDA(cudaSetDevice(dev.ordinal));
-    evs[li].resize(R.launches.size() + 1);
-    for (auto& e : evs[li]) KK_CUDA(cudaEventCreate(&e));
+    evs.emplace_back(R.launches.size() + 1);
+    evs[li].create_all();
     ConvertLaunch base{};
     fill_dsts(m, (int)li, base);
     for (size_t k = 0; k < R.launches.size(); ++k) {
@@ -1100,7 +1131,6 @@ void model_convert_resident(kk_model* m, float* ms_total, float* ms_per_launch, 
       KK_CUDA(cudaEventElapsedTime(&ms, evs[li][k], evs[li][k + 1]));
       if (ms > per[k]) per[k] = ms;
     }
-    for (auto& e : evs[li]) cudaEventDestroy(e);
   }
   if (ms_total) *ms_total = worst;
   if (n_launches) *n_launches = max_launches;

@@ -98,6 +98,7 @@ struct kk_model {
   void* peer_raw_ptr[KK_MAX_DEVICES] = {};      // IPC-opened raw images of the other ranks
   bool raw_staged = false;                      // stage 1 complete on this process since the last conversion
   // state
+  std::mutex op_mu;  // serialises the data-moving calls on ONE model (kk_load_part, kk_convert_local, kk_*_resident) against each other
   int refcount = 0;
   bool loading = true;
   bool loaded = false;

@@ -59,3 +59,43 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
 def test_no_gpu_means_error_not_fallback(native):
     with pytest.raises(gpupool.ErrCUDA):
         gpupool.Pool([0])
+
+
+def test_cpu_entry_points_are_thread_safe_and_errors_are_per_thread(native, tmp_path):
+    """kukeond serves one goroutine per connection (internal/daemon/server.go:236), so calls arrive on arbitrary OS threads
+    at once: 16 threads index and plan good and malformed checkpoints concurrently; every thread must see its own
+    kk_last_error (thread-local) and the same records as a single-threaded run."""
+    import threading
+
+    from tests import helpers
+    from tools import synth
+    good = str(tmp_path / "g.safetensors")
+    helpers.mixed_safetensors(good)
+    gg = str(tmp_path / "g.gguf")
+    synth.write_gguf(gg, [("blk.0.attn_q.weight", "Q4_K", [8, 256]), ("blk.0.ffn_up.weight", "Q5_K", [4, 512]), ("blk.0.attn_norm.weight", "F32", [16])], 3)
+    bad = str(tmp_path / "bad.safetensors")
+    open(bad, "wb").write(b"\xff" * 64)
+    want = {good: gpupool.index(good), gg: gpupool.index(gg)}
+    want_plan = {p: gpupool.plan_describe(p, mode=gpupool.MODE_BROADCAST, n_parts=3) for p in want}
+    errs = []
+
+    def worker(k):
+        try:
+            for it in range(40):
+                p = (good, gg)[(k + it) % 2]
+                assert gpupool.index(p) == want[p]
+                if it % 4 == 0:
+                    assert gpupool.plan_describe(p, mode=gpupool.MODE_BROADCAST, n_parts=3) == want_plan[p]
+                if k % 2:  # odd threads interleave failing calls; their message must be theirs
+                    missing = str(tmp_path / f"missing-{k}.safetensors")
+                    with pytest.raises(gpupool.ErrNotFound, match=f"missing-{k}"):
+                        gpupool.index(missing)
+                    with pytest.raises(gpupool.ErrFormat):
+                        gpupool.index(bad)
+        except BaseException as e:  # noqa: BLE001
+            errs.append((k, repr(e)))
+
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(16)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
