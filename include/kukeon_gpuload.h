@@ -104,6 +104,10 @@ typedef enum kk_fanout {
                                       (an all-to-all through NVSwitch) instead of every rank gathering 2-7 KB column runs
                                       from the file; needs peer access (one process) or attached peers (kk_peer_attach) */
 
+#define KK_LOAD_F8_TO_BF16 0x10u    /* widen safetensors F8_E4M3 / F8_E5M2 tensors to bf16 (exact; NaN -> 0x7FFF).  Default: FP8 stays
+                                      verbatim in the pool — FP8 engines want the bytes, and the per-block scale tensors that FP8
+                                      checkpoints carry are model-specific and are not applied here */
+
 typedef struct kk_ctx kk_ctx;     /* one per process (kukeond lifetime) */
 typedef struct kk_model kk_model; /* refcounted; one per (checkpoint identity, mode, flags) */
 

@@ -10,6 +10,9 @@
 //                                                bit-identical to gguf-py's numpy arithmetic (oracle/oracle.py)
 //     uint32_t pack_bf16x2(a, b)                 two floats -> bf16x2, RNE, NaN -> 0x7FFF
 //     void     store16_all(D, off, uint4)        16 output bytes to every destination pool
+//     void     store2_all(D, off, u16)           one bf16 (ragged tails)
+//     uint4    lds128(a)                         16-byte aligned vector load
+//     uint32_t kk_f8x2_to_f16x2<E5M2>(u16)       two FP8 -> two fp16 (exact; cvt.rn.f16x2.e4m3x2 / .e5m2x2 on the device)
 //     Dsts, uint4, make_uint4, kConsumerWarps, KK_DQ_DEV (function attributes)
 // kk_kernels.cu binds them to PTX; tests/emul/kk_dequant_emul.cpp binds them to plain C++ (with alignment and
 // write-once checks) and runs all 16 x 32 lanes in a loop, so the lane -> element index arithmetic of exactly this source
@@ -215,5 +218,40 @@ KK_DQ_DEV void consume_q5k(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t 
       y[e] = __fsub_rn(__fmul_rn(dsc, (float)q), dmn);
     }
     store_bf16x8(D, dst_off + (uint64_t)b * 512u + (uint32_t)lane * 16u, y);
+  }
+}
+
+// ---- §8(f4): FP8 (safetensors F8_E4M3 / F8_E5M2) widened to bf16, opt-in through KK_LOAD_F8_TO_BF16 -----------------------------
+// Elementwise and exact: FP8 -> fp16 with the hardware pair conversion, fp16 -> fp32 -> bf16 (RNE never rounds: every FP8 value
+// has at most 3 mantissa bits).  A thread turns 16 source bytes into two 16-byte stores; n = elements of the tile.
+template <bool E5M2>
+KK_DQ_DEV void f8x4_to_bf16x4(uint32_t w, uint32_t& o0, uint32_t& o1) {  // 4 FP8 in a word -> 2 + 2 bf16
+  const uint32_t h0 = kk_f8x2_to_f16x2<E5M2>(w & 0xFFFFu), h1 = kk_f8x2_to_f16x2<E5M2>(w >> 16);
+  o0 = pack_bf16x2(kk_h2f(h0 & 0xFFFFu), kk_h2f(h0 >> 16));
+  o1 = pack_bf16x2(kk_h2f(h1 & 0xFFFFu), kk_h2f(h1 >> 16));
+}
+template <bool E5M2>
+KK_DQ_DEV void consume_f8(const Dsts& D, uint32_t pay, uint32_t n, uint64_t dst_off, int ctid) {
+  const uint32_t ngrp = n >> 4;  // 16 elements -> 32 B out
+  const bool al = (pay & 15u) == 0;
+  for (uint32_t g = (uint32_t)ctid; g < ngrp; g += kConsumerWarps * 32u) {
+    uint32_t w[4];
+    if (al) {
+      const uint4 v = lds128(pay + (g << 4));
+      w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) w[k] = lds32_any(pay + (g << 4) + 4u * (uint32_t)k);
+    }
+    uint32_t o[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) f8x4_to_bf16x4<E5M2>(w[k], o[2 * k], o[2 * k + 1]);
+    store16_all(D, dst_off + ((uint64_t)g << 5), make_uint4(o[0], o[1], o[2], o[3]));
+    store16_all(D, dst_off + ((uint64_t)g << 5) + 16u, make_uint4(o[4], o[5], o[6], o[7]));
+  }
+  const uint32_t tail = n & 15u, base = ngrp << 4;
+  if ((uint32_t)ctid < tail) {
+    const uint32_t h = kk_f8x2_to_f16x2<E5M2>(lds8(pay + base + (uint32_t)ctid));
+    store2_all(D, dst_off + 2ull * (base + (uint32_t)ctid), (uint16_t)(pack_bf16x2(kk_h2f(h & 0xFFFFu), 0.f) & 0xFFFFu));
   }
 }

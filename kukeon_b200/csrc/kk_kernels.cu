@@ -274,6 +274,15 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a) {
   return v;
 }
 __device__ __forceinline__ float kk_h2f(uint32_t h) { return __half2float(__ushort_as_half((unsigned short)h)); }
+// two FP8 (low 16 bits of v) -> two fp16, exact (sm_89+ pair conversion)
+template <bool E5M2>
+__device__ __forceinline__ uint32_t kk_f8x2_to_f16x2(uint32_t v) {
+  uint32_t r;
+  const unsigned short s = (unsigned short)v;
+  if (E5M2) asm("cvt.rn.f16x2.e5m2x2 %0, %1;" : "=r"(r) : "h"(s));
+  else asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(r) : "h"(s));
+  return r;
+}
 #define KK_DQ_DEV __device__ __forceinline__
 #include "kk_dequant.cuh"
 
@@ -484,6 +493,14 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
             d.col0 = seg.p3 + (uint32_t)o;     // byte position of the tile inside the piece
             break;
           }
+          case KK_OP_F8E4M3_BF16:
+          case KK_OP_F8E5M2_BF16: {
+            const uint64_t e = (uint64_t)t * KK_TILE_SRC_BYTES;
+            const uint64_t rem = seg.units - e;
+            d.n_units = rem < KK_TILE_SRC_BYTES ? (uint32_t)rem : KK_TILE_SRC_BYTES;
+            in_bytes = d.n_units; in_off = seg.src_off + e; d.dst_off = seg.dst_off + e * 2;
+            break;
+          }
           case KK_OP_F32_BF16: {
             const uint64_t e = (uint64_t)t * (KK_TILE_SRC_BYTES / 4);
             const uint64_t rem = seg.units - e;
@@ -681,6 +698,8 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
         case KK_OP_Q2K_BF16: consume_q2k(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
         case KK_OP_Q3K_BF16: consume_q3k(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
         case KK_OP_Q5K_BF16: consume_q5k(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
+        case KK_OP_F8E4M3_BF16: consume_f8<false>(D, pay, t.n_units, t.dst_off, ctid); break;
+        case KK_OP_F8E5M2_BF16: consume_f8<true>(D, pay, t.n_units, t.dst_off, ctid); break;
         case KK_OP_T_F32_BF16: consume_transpose<4, 2, 1>(D, L.src, t, sbase, ctid); break;
         case KK_OP_T_F16_BF16: consume_transpose<2, 2, 2>(D, L.src, t, sbase, ctid); break;
         case KK_OP_T_B16: consume_transpose<2, 2, 0>(D, L.src, t, sbase, ctid); break;

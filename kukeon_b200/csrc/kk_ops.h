@@ -63,7 +63,10 @@ enum KKOp : uint32_t {
   KK_OP_Q2K_BF16 = 15,
   KK_OP_Q3K_BF16 = 16,
   KK_OP_Q5K_BF16 = 17,
-  KK_OP_COUNT = 18
+  // units = elements (1 byte each): FP8 widened to bf16 (KK_LOAD_F8_TO_BF16)
+  KK_OP_F8E4M3_BF16 = 18,
+  KK_OP_F8E5M2_BF16 = 19,
+  KK_OP_COUNT = 20
 };
 
 struct KKSeg {
@@ -133,6 +136,8 @@ static_assert(KK_TILE_OK(KK_Q4K_BLOCK_BYTES, KK_Q4K_TILE_BLOCKS) && KK_TILE_OK(K
 static inline KK_HD uint64_t kk_seg_tiles(uint32_t op, uint64_t units, uint32_t p0) {
   switch (op) {
     case KK_OP_COPY:
+    case KK_OP_F8E4M3_BF16:
+    case KK_OP_F8E5M2_BF16:
     case KK_OP_ROWSPLIT: return (units + KK_TILE_SRC_BYTES - 1) / KK_TILE_SRC_BYTES;
     case KK_OP_F32_BF16: return (units + KK_TILE_SRC_BYTES / 4 - 1) / (KK_TILE_SRC_BYTES / 4);
     case KK_OP_F16_BF16: return (units + KK_TILE_SRC_BYTES / 2 - 1) / (KK_TILE_SRC_BYTES / 2);

@@ -34,6 +34,12 @@ OpInfo op_for(uint32_t dt, uint32_t flags, const std::string& name) {
       if (flags & KK_LOAD_KEEP_F32) return {KK_OP_COPY, KK_F32, 1, 1, KK_TILE_SRC_BYTES};
       return {KK_OP_F32_BF16, KK_BF16, 4, 2, KK_TILE_SRC_BYTES / 4};
     case KK_F16: return {KK_OP_F16_BF16, KK_BF16, 2, 2, KK_TILE_SRC_BYTES / 2};
+    case KK_F8_E4M3:
+      if (flags & KK_LOAD_F8_TO_BF16) return {KK_OP_F8E4M3_BF16, KK_BF16, 1, 2, KK_TILE_SRC_BYTES};
+      break;
+    case KK_F8_E5M2:
+      if (flags & KK_LOAD_F8_TO_BF16) return {KK_OP_F8E5M2_BF16, KK_BF16, 1, 2, KK_TILE_SRC_BYTES};
+      break;
     default: break;
   }
   // block-quantised GGUF types -> bf16 (geometry shared with the kernel: kk_ops.h)

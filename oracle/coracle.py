@@ -13,6 +13,7 @@ _SO = os.path.join(_HERE, "_build", "libkk_oracle.so")
 _lib = None
 
 OP_COPY, OP_F32_BF16, OP_F16_BF16, OP_Q4K_BF16, OP_Q8_0_BF16, OP_Q6K_BF16 = 0, 1, 2, 3, 4, 5
+OP_F8E4M3_BF16, OP_F8E5M2_BF16 = 6, 7
 OP_DEQUANT = 0x100  # | ggml type id
 # file dtype -> (ggml type id, weights per block, bytes per block)   (gguf/constants.py GGML_QUANT_SIZES)
 GGML_BLOCK = {"Q4_0": (2, 32, 18), "Q4_1": (3, 32, 20), "Q5_0": (6, 32, 22), "Q5_1": (7, 32, 24), "Q8_0": (8, 32, 34),
@@ -42,6 +43,7 @@ def lib():
         L.orc_q4k_to_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.orc_q8_0_to_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.orc_q6k_to_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.orc_f8_to_bf16.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64]
         L.orc_dequant_to_bf16.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64]
         L.orc_dequant_to_bf16.restype = C.c_int
         L.orc_checksum.argtypes = [C.c_void_p, C.c_uint64]
@@ -102,6 +104,13 @@ def q6k_to_bf16(blocks: np.ndarray) -> np.ndarray:
     return out.reshape(n, 256)
 
 
+def f8_to_bf16(dtype: str, u8: np.ndarray) -> np.ndarray:
+    src = np.ascontiguousarray(u8, dtype=np.uint8).reshape(-1)
+    out = np.empty(src.size, np.uint16)
+    lib().orc_f8_to_bf16({"F8_E4M3": 0, "F8_E5M2": 1}[dtype], _ptr(src), _ptr(out), src.size)
+    return out
+
+
 def dequant_to_bf16(dtype: str, blocks: np.ndarray) -> np.ndarray:
     """Any block-quantised GGUF type the oracle defines -> bf16 bit patterns [n_blocks, weights per block]."""
     tid, nel, nb = GGML_BLOCK[dtype]
@@ -153,6 +162,7 @@ def fill_into(kind: str, dst: np.ndarray, seed: int) -> None:
 _OPS = {"BF16": OP_COPY, "F32": OP_F32_BF16, "F16": OP_F16_BF16, "Q4_K": OP_Q4K_BF16, "Q8_0": OP_Q8_0_BF16, "Q6_K": OP_Q6K_BF16}
 _OPS.update({dt: OP_DEQUANT | tid for dt, (tid, _, _) in GGML_BLOCK.items() if dt not in _OPS})
 _UNITS = {OP_COPY: (1, 1), OP_F32_BF16: (4, 2), OP_F16_BF16: (2, 2)}  # op -> (source bytes, pool bytes) per unit
+_UNITS.update({OP_F8E4M3_BF16: (1, 2), OP_F8E5M2_BF16: (1, 2)})
 _UNITS.update({_OPS[dt]: (nb, 2 * nel) for dt, (_, nel, nb) in GGML_BLOCK.items()})
 
 
@@ -161,7 +171,12 @@ def make_jobs(recs: Sequence[dict], plan: Sequence[dict], job_bytes: int = 8 << 
     jobs: List[OrcJob] = []
     total = 0
     for r, p in zip(recs, plan):
-        op = _OPS.get(r["dtype"], OP_COPY)
+        if p["dtype"] == r["dtype"]:  # kept verbatim (BF16, integers, F32 under KEEP_F32, FP8 without F8_TO_BF16)
+            op = OP_COPY
+        elif r["dtype"] in ("F8_E4M3", "F8_E5M2"):
+            op = OP_F8E4M3_BF16 if r["dtype"] == "F8_E4M3" else OP_F8E5M2_BF16
+        else:
+            op = _OPS.get(r["dtype"], OP_COPY)
         unit, out_unit = _UNITS[op]
         step = max(unit, job_bytes // unit * unit)
         off = 0

@@ -46,6 +46,22 @@ void orc_f16_to_bf16(const uint16_t* src, uint16_t* dst, uint64_t n) {
   for (uint64_t i = 0; i < n; ++i) dst[i] = f32_to_bf16(f16bits_to_f32(src[i]));
 }
 
+/* FP8 -> bf16 (exact widenings; opt-in KK_LOAD_F8_TO_BF16).  E4M3 "fn": bias 7, no infinities, S.1111.111 = NaN. */
+static inline uint16_t f8e4m3_to_bf16(uint8_t b) {
+  const uint16_t s = (uint16_t)((b >> 7) << 15);
+  const unsigned e = (b >> 3) & 15u, m = b & 7u;
+  if (e == 15 && m == 7) return 0x7FFF;
+  if (e == 0) return (uint16_t)(s | f32_to_bf16((float)m * 0.001953125f)); /* subnormal: m * 2^-9 */
+  return (uint16_t)(s | ((e + 120u) << 7) | (m << 4));
+}
+static inline uint16_t f8e5m2_to_bf16(uint8_t b) { return f32_to_bf16(f16bits_to_f32((uint16_t)((uint16_t)b << 8))); }
+
+/* kind: 0 = E4M3, 1 = E5M2 */
+void orc_f8_to_bf16(int kind, const uint8_t* src, uint16_t* dst, uint64_t n) {
+#pragma omp parallel for schedule(static)
+  for (uint64_t i = 0; i < n; ++i) dst[i] = kind ? f8e5m2_to_bf16(src[i]) : f8e4m3_to_bf16(src[i]);
+}
+
 /* One Q4_K super-block: d f16 | dmin f16 | scales[12] | qs[128] -> 256 bf16.
  * y = (d*sc_j)*q - (dmin*m_j); every operation rounds to fp32 (no FMA: -ffp-contract=off). */
 static void q4k_block(const uint8_t* b, uint16_t* out) {
@@ -331,7 +347,7 @@ void orc_fill_q4k(uint8_t* dst, uint64_t nblocks, uint64_t seed) {
 }
 
 /* ---- CPU loader ("port" of the hot path for the cpu_baseline legs) ---------------------------- */
-enum { ORC_COPY = 0, ORC_F32_BF16 = 1, ORC_F16_BF16 = 2, ORC_Q4K_BF16 = 3, ORC_Q8_0_BF16 = 4, ORC_Q6K_BF16 = 5,
+enum { ORC_COPY = 0, ORC_F32_BF16 = 1, ORC_F16_BF16 = 2, ORC_Q4K_BF16 = 3, ORC_Q8_0_BF16 = 4, ORC_Q6K_BF16 = 5, ORC_F8E4M3_BF16 = 6, ORC_F8E5M2_BF16 = 7,
        ORC_DEQUANT = 0x100 /* | ggml type id: any block-quantised type block_fn() knows */ };
 
 typedef struct {
@@ -393,6 +409,10 @@ int orc_cpu_load(const char* const* shard_paths, uint32_t n_shards, const orc_jo
           for (uint64_t i = 0; i < J->nbytes / 34; ++i) q8_0_block(scratch + 34 * i, out + 32 * i);
         } else if (J->op == ORC_Q6K_BF16) {
           for (uint64_t i = 0; i < J->nbytes / 210; ++i) q6k_block(scratch + 210 * i, out + 256 * i);
+        } else if (J->op == ORC_F8E4M3_BF16) {
+          for (uint64_t i = 0; i < J->nbytes; ++i) out[i] = f8e4m3_to_bf16(scratch[i]);
+        } else if (J->op == ORC_F8E5M2_BF16) {
+          for (uint64_t i = 0; i < J->nbytes; ++i) out[i] = f8e5m2_to_bf16(scratch[i]);
         } else if (J->op & ORC_DEQUANT) {
           uint32_t nb = 0, ne = 0;
           const orc_block_fn fn = block_fn(J->op & 0xFFu, &nb, &ne);

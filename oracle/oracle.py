@@ -292,6 +292,23 @@ def f16_bits_to_bf16(u16: np.ndarray) -> np.ndarray:
     return f32_to_bf16(np.ascontiguousarray(u16, dtype=np.uint16).view(np.float16).astype(np.float32))
 
 
+def f8e4m3_bits_to_bf16(u8: np.ndarray) -> np.ndarray:
+    """OCP FP8 E4M3 ("fn": no infinities, S.1111.111 is NaN) -> bf16.  Exact: 3 mantissa bits and exponents 2^-9..2^8 all fit.
+    Normal: sign | (e + 120) << 7 | m << 4 (bias 7 -> 127); subnormal (e = 0): m * 2^-9; NaN -> 0x7FFF like every cast here."""
+    u = np.ascontiguousarray(u8, dtype=np.uint8).astype(np.uint16)
+    sgn, e, m = (u >> 7) << 15, (u >> 3) & 15, u & 7
+    out = sgn | ((e + 120) << 7) | (m << 4)
+    sub = e == 0
+    out[sub] = sgn[sub] | f32_to_bf16(m[sub].astype(np.float32) * np.float32(2.0 ** -9))
+    out[(e == 15) & (m == 7)] = 0x7FFF
+    return out.astype(np.uint16)
+
+
+def f8e5m2_bits_to_bf16(u8: np.ndarray) -> np.ndarray:
+    """FP8 E5M2 is the top byte of an IEEE half: widen through fp16 (exact; +-inf kept, NaN -> 0x7FFF)."""
+    return f16_bits_to_bf16(np.ascontiguousarray(u8, dtype=np.uint8).astype(np.uint16) << 8)
+
+
 def q4k_scale_min(scales: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
     """6-bit packed (scale, min) of the 8 sub-blocks; gguf/quants.py:479-501 restated with explicit
     indices (j<4: sc=s[j]&63, m=s[j+4]&63; j>=4: sc=(s[j+4]&15)|((s[j-4]>>6)<<4), m=(s[j+4]>>4)|((s[j]>>6)<<4))."""
@@ -537,7 +554,7 @@ SCATTER_DIM0 = ("q_proj.weight", "k_proj.weight", "v_proj.weight", "gate_proj.we
                 "ffn_gate.weight", "ffn_up.weight", "token_embd.weight", "output.weight")
 SCATTER_DIM1 = ("o_proj.weight", "down_proj.weight", "attn_output.weight", "ffn_down.weight")
 MODE_SINGLE, MODE_BROADCAST, MODE_SCATTER = 0, 1, 2
-LOAD_GPT2_CONV1D_T, LOAD_KEEP_F32 = 0x1, 0x2
+LOAD_GPT2_CONV1D_T, LOAD_KEEP_F32, LOAD_F8_TO_BF16 = 0x1, 0x2, 0x10
 _ELEM_BYTES = {k: v // 8 for k, v in ST_BITS.items() if v % 8 == 0}
 _ELEM_BYTES.update({"F32": 4, "F16": 2, "BF16": 2, "I8": 1, "I16": 2, "I32": 4, "I64": 8, "F64": 8})
 
@@ -547,6 +564,8 @@ def pool_dtype(dt: str, flags: int = 0) -> str:
         return "BF16"
     if dt == "F32":
         return "F32" if flags & LOAD_KEEP_F32 else "BF16"
+    if dt in ("F8_E4M3", "F8_E5M2") and flags & LOAD_F8_TO_BF16:
+        return "BF16"
     return dt
 
 
@@ -610,6 +629,10 @@ def convert_tensor(rec: dict, raw: bytes, flags: int = 0) -> np.ndarray:
         return f32_bits_to_bf16(a.view("<u4")).view(np.uint8)
     if dt == "F16":
         return f16_bits_to_bf16(a.view("<u2")).view(np.uint8)
+    if dt == "F8_E4M3" and flags & LOAD_F8_TO_BF16:
+        return f8e4m3_bits_to_bf16(a).view(np.uint8)
+    if dt == "F8_E5M2" and flags & LOAD_F8_TO_BF16:
+        return f8e5m2_bits_to_bf16(a).view(np.uint8)
     if dt in BLOCK_QUANTS:
         return dequant_bf16(dt, a).reshape(-1).view(np.uint8)
     if dt.startswith("Q"):

@@ -10,6 +10,7 @@
 // parity tests do.  The product never links this file and has no CPU path.
 #include <cstdint>
 #include <cstring>
+#include <vector>
 
 namespace {
 
@@ -22,6 +23,7 @@ struct Emu {
   uint8_t* out = nullptr;
   uint64_t out_bytes = 0;
   uint8_t* hits = nullptr;  // one counter per 16 output bytes
+  uint8_t* out_mask = nullptr;  // per 2 output bytes: written by a scalar (tail) store
   int err = 0;              // first failure: 1 load out of range, 2 misaligned load, 3 store out of range/misaligned, 4 double store
 };
 thread_local Emu g;
@@ -58,11 +60,42 @@ inline uint32_t bf16_rne(float f) {
 inline uint32_t pack_bf16x2(float a, float b) { return bf16_rne(a) | (bf16_rne(b) << 16); }
 
 struct Dsts { int unused; };
+// hits[u] counts the BYTES stored into 16-byte unit u: 16 after exactly one vector store (or eight 2-byte tail stores)
 inline void store16_all(const Dsts&, uint64_t off, const uint4& v) {
   if ((off & 15u) || off + 16 > g.out_bytes) { flag(3); return; }
-  if (g.hits[off >> 4]++) flag(4);
+  if (g.hits[off >> 4]) flag(4);
+  g.hits[off >> 4] += 16;
   memcpy(g.out + off, &v, 16);
 }
+inline void store2_all(const Dsts&, uint64_t off, uint16_t v) {
+  if ((off & 1u) || off + 2 > g.out_bytes) { flag(3); return; }
+  if (g.out_mask[off >> 1]) flag(4);
+  g.out_mask[off >> 1] = 1;
+  g.hits[off >> 4] += 2;
+  memcpy(g.out + off, &v, 2);
+}
+inline uint4 lds128(uint32_t a) {
+  uint4 v{0, 0, 0, 0};
+  if (a & 15u) { flag(2); return v; }
+  if (a + 16 > g.tile_bytes) { flag(1); return v; }
+  memcpy(&v, g.tile + a, 16);
+  return v;
+}
+// FP8 -> fp16 bit patterns (what cvt.rn.f16x2.e4m3x2 / .e5m2x2 produce; exact)
+inline uint32_t f8_to_f16_bits(uint32_t b, bool e5m2) {
+  b &= 0xFFu;
+  if (e5m2) return b << 8;
+  const uint32_t s = (b >> 7) << 15, e = (b >> 3) & 15u, m = b & 7u;
+  if (e == 15 && m == 7) return s | 0x7FFFu;                  // NaN
+  if (e == 0) {                                              // subnormal m * 2^-9 -> normal fp16
+    if (!m) return s;
+    int sh = m >= 4 ? 0 : m >= 2 ? 1 : 2;                    // leading one at bit 2 - sh
+    return s | (uint32_t)((8 - sh) << 10) | (((m << (sh + 1)) & 7u) << 7);
+  }
+  return s | ((e + 8u) << 10) | (m << 7);                    // bias 7 -> 15
+}
+template <bool E5M2>
+inline uint32_t kk_f8x2_to_f16x2(uint32_t v) { return f8_to_f16_bits(v, E5M2) | (f8_to_f16_bits(v >> 8, E5M2) << 16); }
 
 constexpr int kConsumerWarps = 16;  // must equal KK_CONSUMER_WARPS of the kernel build
 #define KK_DQ_DEV static inline
@@ -79,11 +112,16 @@ extern "C" int kk_emul_dequant_tile(uint32_t op, const uint8_t* tile, uint32_t t
                                     uint64_t out_bytes, uint8_t* hits) {
   g = Emu{};
   g.tile = tile; g.tile_bytes = tile_bytes; g.out = out; g.out_bytes = out_bytes; g.hits = hits;
-  memset(hits, 0, out_bytes / 16);
+  memset(hits, 0, (out_bytes + 15) / 16);
+  std::vector<uint8_t> mask(out_bytes / 2 + 1, 0);
+  g.out_mask = mask.data();
   const Dsts D{0};
   for (int cwarp = 0; cwarp < kConsumerWarps; ++cwarp)
     for (int lane = 0; lane < 32; ++lane) {
       switch (op) {
+        // elementwise ops: nblk = elements of the tile, threads indexed 0..511 across the consumer warps
+        case KK_OP_F8E4M3_BF16: consume_f8<false>(D, pay_off, nblk, 0, cwarp * 32 + lane); break;
+        case KK_OP_F8E5M2_BF16: consume_f8<true>(D, pay_off, nblk, 0, cwarp * 32 + lane); break;
         case KK_OP_Q8_0_BF16: consume_q8_0(D, pay_off, nblk, 0, cwarp, lane); break;
         case KK_OP_Q6K_BF16: consume_q6k(D, pay_off, nblk, 0, cwarp, lane); break;
         case KK_OP_Q4_0_BF16: consume_legacy32<KK_Q4_0_BLOCK_BYTES, false, false>(D, pay_off, nblk, 0, cwarp, lane); break;
@@ -113,6 +151,7 @@ extern "C" int kk_emul_dequant_segment(uint32_t op, const uint8_t* src, uint64_t
   seg.src_off = src_misalign;  // pretend the launch's src base is 16-byte aligned and the segment starts here
   memset(hits, 0, out_bytes / 16);
   static thread_local uint8_t stage[KK_TILE_SRC_BYTES + KK_STAGE_PAD];
+  std::vector<uint8_t> mask(out_bytes / 2 + 1, 0);
   const uint64_t n_tiles = kk_seg_tiles(op, units, 0);
   for (uint64_t t = 0; t < n_tiles; ++t) {
     const KKBlockTile bt = kk_block_tile(seg, (uint32_t)t);
@@ -124,6 +163,7 @@ extern "C" int kk_emul_dequant_segment(uint32_t op, const uint8_t* src, uint64_t
     memcpy(stage + mis, src + (bt.in_off - src_misalign), bt.in_bytes);
     g = Emu{};
     g.tile = stage; g.tile_bytes = mis + bt.in_bytes; g.out = out; g.out_bytes = out_bytes; g.hits = hits;
+    g.out_mask = mask.data();
     const Dsts D{0};
     for (int cwarp = 0; cwarp < kConsumerWarps; ++cwarp)
       for (int lane = 0; lane < 32; ++lane) {

@@ -11,7 +11,7 @@ import numpy as np
 from oracle import oracle
 
 OP_COPY, OP_F32, OP_F16, OP_Q4K, OP_T_F32_BF16, OP_T_F16_BF16, OP_T_B16, OP_T_B32, OP_Q8_0, OP_Q6K, OP_ROWSPLIT = range(11)
-OP_Q4_0, OP_Q4_1, OP_Q5_0, OP_Q5_1, OP_Q2K, OP_Q3K, OP_Q5K = range(11, 18)
+OP_Q4_0, OP_Q4_1, OP_Q5_0, OP_Q5_1, OP_Q2K, OP_Q3K, OP_Q5K, OP_F8E4M3, OP_F8E5M2 = range(11, 20)
 # block-dequantising ops: op -> (source bytes per block, bf16 bytes per block, blocks per tile)   (csrc/kk_ops.h kk_block_geom)
 BLOCK_GEOM = {OP_Q4K: (144, 512, 224), OP_Q8_0: (34, 64, 960), OP_Q6K: (210, 512, 152), OP_Q4_0: (18, 64, 1816), OP_Q4_1: (20, 64, 1632),
               OP_Q5_0: (22, 64, 1488), OP_Q5_1: (24, 64, 1360), OP_Q2K: (84, 512, 388), OP_Q3K: (110, 512, 296), OP_Q5K: (176, 512, 186)}
@@ -47,7 +47,7 @@ def emulate_part(plan: dict, part: int, pool_bytes: int, exchange: dict | None =
                 if op in BLOCK_GEOM:
                     src_bytes = BLOCK_GEOM[op][0] * u
                 else:
-                    src_bytes = {OP_COPY: u, OP_F32: 4 * u, OP_F16: 2 * u, OP_ROWSPLIT: u, OP_T_F32_BF16: 4 * u * sg["p0"], OP_T_B32: 4 * u * sg["p0"],
+                    src_bytes = {OP_COPY: u, OP_F32: 4 * u, OP_F16: 2 * u, OP_ROWSPLIT: u, OP_F8E4M3: u, OP_F8E5M2: u, OP_T_F32_BF16: 4 * u * sg["p0"], OP_T_B32: 4 * u * sg["p0"],
                                  OP_T_F16_BF16: 2 * u * sg["p0"], OP_T_B16: 2 * u * sg["p0"]}[op]
                 assert so + src_bytes <= ch["buf_bytes"], "segment reads past the bytes staged for its chunk"
                 assert covered[so:so + src_bytes].all(), "segment consumes bytes no read put there"
@@ -76,6 +76,10 @@ def emulate_part(plan: dict, part: int, pool_bytes: int, exchange: dict | None =
                 elif op == OP_F16:
                     out = oracle.f16_bits_to_bf16(buf[so:so + 2 * u].copy().view("<u2")).view(np.uint8)
                     tiles += -(-u // 16384)
+                elif op in (OP_F8E4M3, OP_F8E5M2):
+                    fn = oracle.f8e4m3_bits_to_bf16 if op == OP_F8E4M3 else oracle.f8e5m2_bits_to_bf16
+                    out = fn(buf[so:so + u]).view(np.uint8)
+                    tiles += -(-u // 32768)
                 elif op in BLOCK_GEOM:
                     bb, _, tb = BLOCK_GEOM[op]
                     out = oracle.dequant_bf16(BLOCK_DTYPE[op], buf[so:so + bb * u].reshape(-1, bb)).reshape(-1).view(np.uint8)

@@ -51,7 +51,7 @@ def run_tile(L, dtype, blocks, pay_off):
     hits = np.zeros(out.size // 16, np.uint8)
     rc = L.kk_emul_dequant_tile(op, tile.ctypes.data, tile.size, pay_off, n, out.ctypes.data, out.size, hits.ctypes.data)
     assert rc == 0, f"{dtype}: {ERR.get(rc, rc)}"
-    assert (hits == 1).all(), f"{dtype}: {int((hits != 1).sum())} output vectors not stored exactly once"
+    assert (hits == 16).all(), f"{dtype}: {int((hits != 16).sum())} output vectors not stored exactly once"
     return out.view(np.uint16).reshape(n, nel)
 
 
@@ -100,7 +100,27 @@ def test_multi_tile_segments_walked_like_the_producer(emul, dtype):
         hits = np.zeros(out.size // 16, np.uint8)
         rc = emul.kk_emul_dequant_segment(OPS[dtype], blocks.ctypes.data, n, mis, out.ctypes.data, out.size, hits.ctypes.data)
         assert rc == 0, f"{dtype}: {ERR.get(rc, rc)}"
-        assert (hits == 1).all() and (out.view(np.uint16).reshape(n, nel) == want).all(), (dtype, mis)
+        assert (hits == 16).all() and (out.view(np.uint16).reshape(n, nel) == want).all(), (dtype, mis)
+
+
+@pytest.mark.parametrize("dtype,op,fn", [("F8_E4M3", helpers.OP_F8E4M3, oracle.f8e4m3_bits_to_bf16), ("F8_E5M2", helpers.OP_F8E5M2, oracle.f8e5m2_bits_to_bf16)])
+def test_fp8_widening_every_byte_value_every_alignment_and_tail(emul, dtype, op, fn):
+    """Elementwise FP8 -> bf16: all 256 byte values, counts that end inside a 16-element group, aligned and byte-assembled loads."""
+    rng = np.random.default_rng(8)
+    for n in (1, 15, 16, 17, 256, 511 * 16 + 3, 512 * 16, 512 * 16 + 9, 32768):
+        src = np.concatenate([np.arange(256, dtype=np.uint8), rng.integers(0, 256, max(0, n - 256), dtype=np.uint8)])[:n]
+        for pay_off in (0, 1, 2, 4, 8, 13):
+            tile = np.full(pay_off + n, 0x5A, np.uint8)
+            tile[pay_off:] = src
+            out = np.zeros(2 * n, np.uint8)
+            hits = np.zeros((2 * n + 15) // 16, np.uint8)
+            rc = emul.kk_emul_dequant_tile(op, tile.ctypes.data, tile.size, pay_off, n, out.ctypes.data, out.size, hits.ctypes.data)
+            assert rc == 0, f"{dtype} n={n} pay_off={pay_off}: {ERR.get(rc, rc)}"
+            want_hits = np.full(hits.size, 16, np.uint8)
+            if (2 * n) % 16:
+                want_hits[-1] = (2 * n) % 16
+            assert (hits == want_hits).all()
+            assert (out.view(np.uint16) == fn(src)).all(), (dtype, n, pay_off)
 
 
 def test_harness_sees_wrong_answers(emul):

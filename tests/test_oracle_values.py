@@ -191,3 +191,18 @@ def test_legacy_and_k_quant_golden_file_vs_gguf_py():
         assert (got == outs[t["name"]]).all(), t["name"]
         seen.add(t["dtype"])
     assert set(F4_TYPES) <= seen
+
+
+def test_fp8_widening_vs_torch_every_bit_pattern(coracle):
+    """KK_LOAD_F8_TO_BF16: all 256 E4M3 ("fn") and E5M2 patterns against torch's float8 -> bfloat16 cast; NaNs -> 0x7FFF."""
+    b = np.arange(256, dtype=np.uint8)
+    for tdt, name, fn in ((torch.float8_e4m3fn, "F8_E4M3", oracle.f8e4m3_bits_to_bf16), (torch.float8_e5m2, "F8_E5M2", oracle.f8e5m2_bits_to_bf16)):
+        ref = bits16(torch.from_numpy(b.copy()).view(tdt).to(torch.bfloat16))
+        nan = (ref & 0x7FFF) > 0x7F80
+        got = fn(b)
+        assert int(nan.sum()) == (2 if name == "F8_E4M3" else 6)
+        assert (got[~nan] == ref[~nan]).all() and (got[nan] == 0x7FFF).all()
+        assert (coracle.f8_to_bf16(name, b) == got).all()
+        # widening is exact: going back to float8 reproduces the byte
+        back = torch.from_numpy(got[~nan].view(np.int16)).view(torch.bfloat16).to(tdt).view(torch.uint8).numpy()
+        assert (back == b[~nan]).all()

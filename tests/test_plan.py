@@ -109,6 +109,28 @@ def test_scatter_slices(native, tmp_path):
         assert plan["parts"][0]["src_bytes"] < plan["file_bytes"] / n * 1.05 + 64 * 1024
 
 
+def run_case_scatter_exchange(path, flags, n, chunk=1 * MB):
+    """SCATTER with KK_LOAD_SCATTER_EXCHANGE set in `flags`: replay every rank (its ROWSPLIT tiles write into the other ranks' pools)
+    and compare every rank's pool with the oracle's slice pool.  The oracle does not know the exchange flag: it changes the
+    route, not the result."""
+    shards, recs = oracle.index_path(path)
+    oflags = flags & ~gpupool.LOAD_SCATTER_EXCHANGE
+    plan = gpupool.plan_describe(path, mode=gpupool.MODE_SCATTER, flags=flags, n_parts=n, chunk_bytes=chunk)
+    check_layout(plan, recs, gpupool.MODE_SCATTER, oflags, n)
+    exps = [oracle.expected_pool(shards, recs, gpupool.MODE_SCATTER, oflags, n, g) for g in range(n)]
+    ex = {g: (np.zeros(len(exps[g][0]), np.uint8), np.zeros(len(exps[g][0]), bool)) for g in range(n)}
+    for g in range(n):
+        got, mask = helpers.emulate_part(plan, g, len(exps[g][0]), exchange=ex)
+        assert not (mask & ex[g][1]).any()
+        ex[g][0][mask] = got[mask]
+        ex[g][1][mask] = True
+    for g in range(n):
+        exp, pl = exps[g]
+        assert (ex[g][1] == helpers.expected_mask(pl, len(exp))).all()
+        assert (ex[g][0] == exp).all()
+    return plan
+
+
 def test_scatter_exchange_rows_dealt_to_every_pool(native, tmp_path):
     """KK_LOAD_SCATTER_EXCHANGE: row-parallel tensors are ingested as whole rows by the rank owning 1/N of the rows and
     dealt column-slice by column-slice to all N pools; emulating every rank must reproduce every rank's oracle pool."""
@@ -244,6 +266,30 @@ def test_q4_k_m_style_mixed_quant_plan(native, tmp_path):
     run_case(p, mode=gpupool.MODE_BROADCAST, n_parts=3, chunk=1 * MB)
     run_case(p, mode=gpupool.MODE_SCATTER, n_parts=2, chunk=1 * MB)
     run_case(os.path.join(G, "q4km_mix.gguf"))
+
+
+def test_fp8_checkpoint_verbatim_by_default_widened_on_request(native, tmp_path):
+    """FP8 safetensors (DeepSeek-V3 / Llama-3.1-FP8 style: F8_E4M3 weights + F32 per-block scale tensors): verbatim bytes by
+    default, bf16 with KK_LOAD_F8_TO_BF16; dim-1 scatter slices stay element-granular."""
+    p = str(tmp_path / "fp8.safetensors")
+    t = [("model.embed_tokens.weight", "BF16", [512, 128])]
+    for i in range(2):
+        q = f"model.layers.{i}."
+        t += [(q + "self_attn.q_proj.weight", "F8_E4M3", [128, 128]), (q + "self_attn.q_proj.weight_scale_inv", "F32", [1, 1]),
+              (q + "self_attn.o_proj.weight", "F8_E4M3", [128, 128]), (q + "mlp.down_proj.weight", "F8_E5M2", [128, 352]),
+              (q + "mlp.up_proj.weight", "F8_E4M3", [352, 128]), (q + "input_layernorm.weight", "BF16", [128]), (q + "odd.weight", "F8_E4M3", [3, 37])]
+    synth.write_safetensors(p, t, 17)
+    plan = run_case(p, chunk=1 * MB)
+    assert {x["dtype"] for x in plan["layouts"][0]["tensors"]} >= {"F8_E4M3", "F8_E5M2"}
+    plan = run_case(p, flags=gpupool.LOAD_F8_TO_BF16, chunk=1 * MB)
+    assert not any(x["dtype"].startswith("F8") for x in plan["layouts"][0]["tensors"])
+    ops = {sg["op"] for ch in plan["parts"][0]["chunks"] for sg in ch["segs"]}
+    assert {helpers.OP_F8E4M3, helpers.OP_F8E5M2} <= ops
+    run_case(p, flags=gpupool.LOAD_F8_TO_BF16, mode=gpupool.MODE_BROADCAST, n_parts=3, chunk=1 * MB)
+    for flags in (0, gpupool.LOAD_F8_TO_BF16, gpupool.LOAD_F8_TO_BF16 | gpupool.LOAD_SCATTER_EXCHANGE):
+        plan = run_case_scatter_exchange(p, flags, 4) if flags & gpupool.LOAD_SCATTER_EXCHANGE else run_case(p, mode=gpupool.MODE_SCATTER, flags=flags, n_parts=4, chunk=1 * MB)
+        lay = {x["name"]: x for x in plan["layouts"][1]["tensors"]}
+        assert lay["model.layers.0.mlp.down_proj.weight"]["slice_dim"] == 1 and lay["model.layers.0.mlp.down_proj.weight"]["shape"] == [128, 88]
 
 
 def test_bad_arguments(native, tmp_path):

@@ -89,3 +89,22 @@ def test_scatter_keeps_whole_rows_of_blocks(native, tmp_path):
                 assert_pool_matches(m, 0, shards, recs, mode=gpupool.MODE_SCATTER, n_parts=4, part=part)
             finally:
                 m.release()
+
+
+def test_fp8_safetensors_verbatim_by_default_and_widened_on_request(pool, tmp_path):
+    """F8_E4M3 / F8_E5M2: bytes kept by default; KK_LOAD_F8_TO_BF16 widens exactly (cvt.rn.f16x2.e4m3x2 path), all 256 patterns present,
+    sizes that end inside a 16-element group, a header that leaves the data off 16-byte alignment."""
+    for pad in (True, False):
+        p = str(tmp_path / f"fp8_{int(pad)}.safetensors")
+        t = [("a.weight", "F8_E4M3", [300, 512]), ("a.weight_scale_inv", "F32", [3, 4]), ("b.weight", "F8_E5M2", [129, 65]), ("c.weight", "F8_E4M3", [7]),
+             ("d.weight", "BF16", [33, 77]), ("e.weight", "F8_E4M3", [40000]), ("f.weight", "F8_E5M2", [3, 5, 7])]
+        synth.write_safetensors(p, t, 23, pad_header=pad)
+        raw = synth.gen_bytes("F8_E4M3", 300 * 512, 23, 0)
+        assert len(set(raw.tolist())) == 256
+        load_and_check(pool, p)
+        load_and_check(pool, p, flags=gpupool.LOAD_F8_TO_BF16)
+        m = pool.load(p, flags=gpupool.LOAD_F8_TO_BF16)
+        try:
+            assert m.placements("a.weight")[0].dtype == "BF16" and m.placements("a.weight")[0].nbytes == 300 * 512 * 2
+        finally:
+            m.release()

@@ -20,7 +20,8 @@ from typing import Dict, List, Sequence, Tuple
 
 import numpy as np
 
-ST_ITEMSIZE = {"F32": 4, "F16": 2, "BF16": 2, "I64": 8, "I32": 4, "U8": 1, "I8": 1, "BOOL": 1, "F64": 8, "I16": 2, "U16": 2}
+ST_ITEMSIZE = {"F32": 4, "F16": 2, "BF16": 2, "I64": 8, "I32": 4, "U8": 1, "I8": 1, "BOOL": 1, "F64": 8, "I16": 2, "U16": 2, "U32": 4,
+               "F8_E4M3": 1, "F8_E5M2": 1}
 GGML = {"F32": (0, 1, 4), "F16": (1, 1, 2), "Q4_K": (12, 256, 144), "BF16": (30, 1, 2), "Q8_0": (8, 32, 34), "Q6_K": (14, 256, 210),
         "Q4_0": (2, 32, 18), "Q4_1": (3, 32, 20), "Q5_0": (6, 32, 22), "Q5_1": (7, 32, 24), "Q2_K": (10, 256, 84), "Q3_K": (11, 256, 110),
         "Q5_K": (13, 256, 176)}
