@@ -107,6 +107,9 @@ typedef enum kk_fanout {
 #define KK_LOAD_F8_TO_BF16 0x10u    /* widen safetensors F8_E4M3 / F8_E5M2 tensors to bf16 (exact; NaN -> 0x7FFF).  Default: FP8 stays
                                       verbatim in the pool — FP8 engines want the bytes, and the per-block scale tensors that FP8
                                       checkpoints carry are model-specific and are not applied here */
+#define KK_LOAD_T8_TILES 0x20u      /* KK_LOAD_GPT2_CONV1D_T: transpose on 8-row x 4 KiB tiles (8x fewer bulk copies per byte, bank-conflict-free
+                                      reads, 16-byte stores).  Candidate geometry, bit-identical results; opt-in until it has been
+                                      measured against the 32x128 tiles on hardware, then it becomes the default */
 
 typedef struct kk_ctx kk_ctx;     /* one per process (kukeond lifetime) */
 typedef struct kk_model kk_model; /* refcounted; one per (checkpoint identity, mode, flags) */

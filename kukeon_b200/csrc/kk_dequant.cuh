@@ -13,6 +13,9 @@
 //     void     store2_all(D, off, u16)           one bf16 (ragged tails)
 //     uint4    lds128(a)                         16-byte aligned vector load
 //     uint32_t kk_f8x2_to_f16x2<E5M2>(u16)       two FP8 -> two fp16 (exact; cvt.rn.f16x2.e4m3x2 / .e5m2x2 on the device)
+//     float    kk_bits2f(u32)                    bit cast
+//     void     sts16(a, v) / sts32(a, v)         stores into the stage (gather fallback of the 8-row transposes)
+//     uint32_t kk_ldg8(p)                        one byte from global memory (same fallback)
 //     Dsts, uint4, make_uint4, kConsumerWarps, KK_DQ_DEV (function attributes)
 // kk_kernels.cu binds them to PTX; tests/emul/kk_dequant_emul.cpp binds them to plain C++ (with alignment and
 // write-once checks) and runs all 16 x 32 lanes in a loop, so the lane -> element index arithmetic of exactly this source
@@ -253,5 +256,54 @@ KK_DQ_DEV void consume_f8(const Dsts& D, uint32_t pay, uint32_t n, uint64_t dst_
   if ((uint32_t)ctid < tail) {
     const uint32_t h = kk_f8x2_to_f16x2<E5M2>(lds8(pay + base + (uint32_t)ctid));
     store2_all(D, dst_off + 2ull * (base + (uint32_t)ctid), (uint16_t)(pack_bf16x2(kk_h2f(h & 0xFFFFu), 0.f) & 0xFFFFu));
+  }
+}
+
+// ---- 8-row transpose tiles (KK_LOAD_T8_TILES; KK_OP_T8_*) ---------------------------------------------------------------------------
+// The stage holds nr <= 8 source rows of nc columns, row r at sbase + r * pitch (staged by the producer's bulk copies, or gathered
+// by t8_gather when the source rows are not 16-byte aligned).  Thread t takes columns t, t + 512, ...: its 8 loads walk DOWN one
+// column while the lanes of its warp sit side by side ALONG the row — consecutive shared-memory words, conflict-free whatever
+// the pitch — and the 8 converted values are the 16 contiguous destination bytes dst[(col0 + c) * R + row0 .. + 8).
+template <int ES, int CONV>  // CONV: 0 verbatim 16-bit, 1 f32 -> bf16, 2 f16 -> bf16
+KK_DQ_DEV uint32_t t8_pack2(uint32_t a, uint32_t b) {
+  if (CONV == 1) return pack_bf16x2(kk_bits2f(a), kk_bits2f(b));
+  if (CONV == 2) return pack_bf16x2(kk_h2f(a), kk_h2f(b));
+  return (a & 0xFFFFu) | (b << 16);
+}
+template <int ES, int CONV>
+KK_DQ_DEV void consume_t8(const Dsts& D, uint32_t sbase, uint32_t pitch, uint32_t nr, uint32_t nc, uint32_t R, uint32_t col0, uint32_t row0,
+                          uint64_t dst_off, int ctid) {
+  const bool vec = nr == KK_T8_ROWS && (R & 7u) == 0 && (row0 & 7u) == 0 && (dst_off & 15u) == 0;
+  for (uint32_t c = (uint32_t)ctid; c < nc; c += kConsumerWarps * 32u) {
+    uint32_t v[KK_T8_ROWS];
+#pragma unroll
+    for (uint32_t k = 0; k < KK_T8_ROWS; ++k) {
+      const uint32_t a = sbase + k * pitch + c * (uint32_t)ES;
+      v[k] = k < nr ? (ES == 4 ? lds32(a) : lds16(a)) : 0u;
+    }
+    const uint64_t off = dst_off + ((uint64_t)(col0 + c) * R + row0) * 2u;
+    if (vec) {
+      store16_all(D, off, make_uint4(t8_pack2<ES, CONV>(v[0], v[1]), t8_pack2<ES, CONV>(v[2], v[3]), t8_pack2<ES, CONV>(v[4], v[5]),
+                                     t8_pack2<ES, CONV>(v[6], v[7])));
+    } else {
+#pragma unroll
+      for (uint32_t k = 0; k < KK_T8_ROWS; ++k)
+        if (k < nr) store2_all(D, off + 2u * k, (uint16_t)(t8_pack2<ES, CONV>(v[k], 0u) & 0xFFFFu));
+    }
+  }
+}
+// Fallback when the producer could not stage the tile with bulk copies (rows not 16-byte aligned / not a whole number of 16-byte
+// units): every consumer thread copies elements from global memory into the same [row][col] layout; the caller puts a barrier
+// between this and consume_t8.  src points at source element (r0, c0); C = source columns of the tensor.
+template <int ES>
+KK_DQ_DEV void t8_gather(const uint8_t* src, uint32_t sbase, uint32_t pitch, uint32_t nr, uint32_t nc, uint32_t C, int ctid) {
+  for (uint32_t i = (uint32_t)ctid; i < nr * nc; i += kConsumerWarps * 32u) {
+    const uint32_t r = i / nc, c = i - r * nc;
+    const uint8_t* p = src + ((uint64_t)r * C + c) * (uint32_t)ES;
+    uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < ES; ++k) w |= kk_ldg8(p + k) << (8 * k);
+    if (ES == 4) sts32(sbase + r * pitch + c * 4u, w);
+    else sts16(sbase + r * pitch + c * 2u, w);
   }
 }

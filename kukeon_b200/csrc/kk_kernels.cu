@@ -38,7 +38,8 @@ struct __align__(16) TileDesc {
   uint32_t op;
   uint32_t pay_off;  // payload offset inside the stage buffer (0..15 for TMA tiles)
   uint32_t n_units;  // units in this tile (bytes / elements / blocks); transposes: rows | cols<<16
-  uint32_t bulk;     // 1: aligned copy, bulk-store from shared memory; 2: transpose tile staged row by row with TMA
+  uint32_t bulk;     // 1: aligned copy, bulk-store from shared memory; 2: transpose tile staged row by row with TMA; 3: row-split exchange;
+                     // 4: 8-row transpose tile staged with TMA, rows nc*es bytes apart
   uint64_t dst_off;  // pool byte offset of the tile's first output (transposes: dst tensor origin)
   uint64_t src_off;  // transposes: byte offset of source element (r0, c0) from L.src
   uint32_t C;        // transposes: source columns
@@ -283,6 +284,10 @@ __device__ __forceinline__ uint32_t kk_f8x2_to_f16x2(uint32_t v) {
   else asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(r) : "h"(s));
   return r;
 }
+__device__ __forceinline__ float kk_bits2f(uint32_t u) { return __uint_as_float(u); }
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t kk_ldg8(const uint8_t* p) { return (uint32_t)__ldg(p); }
 #define KK_DQ_DEV __device__ __forceinline__
 #include "kk_dequant.cuh"
 
@@ -424,6 +429,19 @@ __device__ __forceinline__ void consume_transpose(const Dsts& D, const uint8_t* 
   }
 }
 
+// 8-row transpose tile (KK_OP_T8_*): staged by the producer (t.bulk == 4) or gathered here.
+template <int ES, int CONV>
+__device__ __forceinline__ void run_t8(const Dsts& D, const uint8_t* src, const TileDesc& t, uint32_t sbase, int ctid) {
+  const uint32_t nr = t.n_units & 0xFFFFu, nc = t.n_units >> 16;
+  uint32_t pitch = nc * ES;
+  if (t.bulk != 4) {
+    pitch = (pitch + 3u) & ~3u;
+    t8_gather<ES>(src + t.src_off, sbase, pitch, nr, nc, t.C, ctid);
+    named_bar_consumers();
+  }
+  consume_t8<ES, CONV>(D, sbase, pitch, nr, nc, t.R, t.col0, t.row0, t.dst_off, ctid);
+}
+
 __device__ __forceinline__ KKSeg load_seg(const KKSeg* p) {
   const uint4* q = reinterpret_cast<const uint4*>(p);
   uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
@@ -551,6 +569,40 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
             in_bytes = bt.in_bytes; in_off = bt.in_off;
             d.dst_off = bt.dst_off;
             break;
+          }
+          case KK_OP_T8_F32_BF16:
+          case KK_OP_T8_F16_BF16:
+          case KK_OP_T8_B16: {  // 8 source rows x up to KK_T8_ROW_BYTES per row
+            const uint32_t es = seg.op == KK_OP_T8_F32_BF16 ? 4u : 2u;
+            const uint32_t C = seg.p0, W = KK_T8_ROW_BYTES / es;
+            const uint32_t ct = (C + W - 1) / W;
+            const uint32_t tr = t / ct, tc = t % ct;
+            const uint64_t r0 = (uint64_t)tr * KK_T8_ROWS;
+            const uint32_t c0 = tc * W;
+            const uint64_t rrem = seg.units - r0;
+            const uint32_t nr = rrem < KK_T8_ROWS ? (uint32_t)rrem : KK_T8_ROWS;
+            const uint32_t nc = (C - c0) < W ? (C - c0) : W;
+            d.n_units = nr | (nc << 16);
+            d.C = C; d.R = seg.p1; d.col0 = c0; d.row0 = seg.p2 + (uint32_t)r0;
+            d.src_off = seg.src_off + (r0 * C + c0) * es;
+            d.dst_off = seg.dst_off;
+            const uint64_t row_pitch = (uint64_t)C * es;
+            const uint32_t rb = nc * es;
+            if ((((uintptr_t)(L.src + d.src_off)) & 15u) == 0 && (row_pitch & 15u) == 0 && (rb & 15u) == 0) {
+              d.bulk = 4;
+              d.pay_off = 0;
+              descs[s] = d;
+              mbar_arrive_expect_tx(full0 + 8 * s, nr * rb);
+              const uint8_t* gp = L.src + d.src_off;
+              const uint32_t sb = smem_u32(stage_buf + s * kStageBytes);
+              if (nc == C) {  // the tile spans whole rows: they are contiguous in the source, one bulk copy brings all of them
+                bulk_g2s(sb, gp, nr * rb, full0 + 8 * s);
+              } else {
+                for (uint32_t r = 0; r < nr; ++r) bulk_g2s(sb + r * rb, gp + r * row_pitch, rb, full0 + 8 * s);
+              }
+              continue;
+            }
+            break;  // unaligned rows: publish the descriptor only, the consumers gather the tile themselves
           }
           default: {  // transposes
             const uint32_t C = seg.p0;
@@ -698,6 +750,9 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
         case KK_OP_Q2K_BF16: consume_q2k(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
         case KK_OP_Q3K_BF16: consume_q3k(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
         case KK_OP_Q5K_BF16: consume_q5k(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
+        case KK_OP_T8_F32_BF16: run_t8<4, 1>(D, L.src, t, sbase, ctid); break;
+        case KK_OP_T8_F16_BF16: run_t8<2, 2>(D, L.src, t, sbase, ctid); break;
+        case KK_OP_T8_B16: run_t8<2, 0>(D, L.src, t, sbase, ctid); break;
         case KK_OP_F8E4M3_BF16: consume_f8<false>(D, pay, t.n_units, t.dst_off, ctid); break;
         case KK_OP_F8E5M2_BF16: consume_f8<true>(D, pay, t.n_units, t.dst_off, ctid); break;
         case KK_OP_T_F32_BF16: consume_transpose<4, 2, 1>(D, L.src, t, sbase, ctid); break;

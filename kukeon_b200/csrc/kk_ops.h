@@ -33,6 +33,11 @@
 #define KK_T_ROWS 32u            /* transpose tile: 32 source rows ... */
 #define KK_T_COLS 128u           /* ... x 128 source columns (elements) */
 #define KK_T_PITCH_PAD 16u       /* TMA-staged transpose rows sit KK_T_COLS*es + 16 bytes apart (bank spread) */
+/* Candidate transpose geometry (KK_LOAD_T8_TILES): 8 source rows x (KK_T8_ROW_BYTES / es) columns.  Eight bulk copies bring in a full
+ * 32 KiB stage (ONE when the tile spans whole rows, which are then contiguous in the source); consumers read along rows — conflict-free
+ * at any pitch — and every thread packs the 8 rows of one column into a single 16-byte store. */
+#define KK_T8_ROWS 8u
+#define KK_T8_ROW_BYTES 4096u    /* per staged row: 1024 f32 or 2048 16-bit columns */
 #define KK_MAX_DST 8
 
 enum KKOp : uint32_t {
@@ -66,7 +71,12 @@ enum KKOp : uint32_t {
   // units = elements (1 byte each): FP8 widened to bf16 (KK_LOAD_F8_TO_BF16)
   KK_OP_F8E4M3_BF16 = 18,
   KK_OP_F8E5M2_BF16 = 19,
-  KK_OP_COUNT = 20
+  // 2-D transposes on 8-row tiles (same units / p0 / p1 / p2 as KK_OP_T_*); chosen by the planner under KK_LOAD_T8_TILES when the
+  // destination row length (p1) is a multiple of 8, so that every 8-row group of a column is one aligned 16-byte store
+  KK_OP_T8_F32_BF16 = 20,
+  KK_OP_T8_F16_BF16 = 21,
+  KK_OP_T8_B16 = 22,
+  KK_OP_COUNT = 23
 };
 
 struct KKSeg {
@@ -160,6 +170,12 @@ static inline KK_HD uint64_t kk_seg_tiles(uint32_t op, uint64_t units, uint32_t 
     case KK_OP_T_B16: {
       uint64_t ct = ((uint64_t)p0 + KK_T_COLS - 1) / KK_T_COLS;
       return ((units + KK_T_ROWS - 1) / KK_T_ROWS) * ct;
+    }
+    case KK_OP_T8_F32_BF16:
+    case KK_OP_T8_F16_BF16:
+    case KK_OP_T8_B16: {
+      const uint64_t w = KK_T8_ROW_BYTES / (op == KK_OP_T8_F32_BF16 ? 4u : 2u);
+      return ((units + KK_T8_ROWS - 1) / KK_T8_ROWS) * (((uint64_t)p0 + w - 1) / w);
     }
     default: return 0;
   }

@@ -9,6 +9,7 @@
 // all fail the run.  It does not check PTX spelling, memory ordering or anything about the producer warp; the -m gpu
 // parity tests do.  The product never links this file and has no CPU path.
 #include <cstdint>
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -19,6 +20,8 @@ inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return
 
 struct Emu {
   const uint8_t* tile = nullptr;  // the stage buffer; shared-memory address a <-> tile[a]
+  uint8_t* wtile = nullptr;       // same buffer when the code under test may store into it (sts16 / sts32)
+  std::vector<uint32_t>* trace = nullptr;  // when set: every 16/32-bit shared load appends its address (bank-conflict accounting)
   uint32_t tile_bytes = 0;
   uint8_t* out = nullptr;
   uint64_t out_bytes = 0;
@@ -36,13 +39,25 @@ inline uint32_t lds8(uint32_t a) {
 inline uint32_t lds16(uint32_t a) {
   if (a & 1u) { flag(2); return 0; }
   if (a + 2 > g.tile_bytes) { flag(1); return 0; }
+  if (g.trace) g.trace->push_back(a);
   uint16_t v; memcpy(&v, g.tile + a, 2); return v;
 }
 inline uint32_t lds32(uint32_t a) {
   if (a & 3u) { flag(2); return 0; }
   if (a + 4 > g.tile_bytes) { flag(1); return 0; }
+  if (g.trace) g.trace->push_back(a);
   uint32_t v; memcpy(&v, g.tile + a, 4); return v;
 }
+inline void sts16(uint32_t a, uint32_t v) {
+  if ((a & 1u) || a + 2 > g.tile_bytes || !g.wtile) { flag(6); return; }
+  uint16_t h = (uint16_t)v; memcpy(g.wtile + a, &h, 2);
+}
+inline void sts32(uint32_t a, uint32_t v) {
+  if ((a & 3u) || a + 4 > g.tile_bytes || !g.wtile) { flag(6); return; }
+  memcpy(g.wtile + a, &v, 4);
+}
+inline uint32_t kk_ldg8(const uint8_t* p) { return *p; }
+inline float kk_bits2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 inline float kk_h2f(uint32_t h) {
   uint16_t b = (uint16_t)h;
   _Float16 x; memcpy(&x, &b, 2);
@@ -183,6 +198,69 @@ extern "C" int kk_emul_dequant_segment(uint32_t op, const uint8_t* src, uint64_t
     if (g.err) return g.err;
   }
   return 0;
+}
+
+// One 8-row transpose tile (KK_OP_T8_*) the way the kernel runs it.  `src` points at source element (r0, c0) of a row-major
+// [*, C] tensor of ES-byte elements; staged != 0 lays the tile out as the producer's bulk copies do (rows nc*ES apart), staged == 0
+// runs the consumers' gather fallback first.  `dst` is the destination tensor's origin ([C_total, R] row-major, 2-byte elements),
+// dst_bytes its size; hits as in kk_emul_dequant_tile over dst.  stats[0] receives the shared-memory wavefronts the consumers'
+// loads need (one per distinct 4-byte word per bank per warp instruction), stats[1] the ideal (one per warp instruction).
+extern "C" int kk_emul_t8_tile(uint32_t op, const uint8_t* src, uint32_t C, uint32_t nr, uint32_t nc, uint32_t R, uint32_t col0, uint32_t row0,
+                               int staged, uint8_t* dst, uint64_t dst_bytes, uint8_t* hits, uint64_t* stats) {
+  const uint32_t es = op == KK_OP_T8_F32_BF16 ? 4u : 2u;
+  if (op != KK_OP_T8_F32_BF16 && op != KK_OP_T8_F16_BF16 && op != KK_OP_T8_B16) return -1;
+  if (nr > KK_T8_ROWS || nc * es > KK_T8_ROW_BYTES) return 5;
+  static thread_local uint8_t stage[KK_TILE_SRC_BYTES + KK_STAGE_PAD];
+  memset(stage, 0xEE, sizeof stage);
+  uint32_t pitch = nc * es;
+  std::vector<uint8_t> mask(dst_bytes / 2 + 1, 0);
+  memset(hits, 0, (dst_bytes + 15) / 16);
+  g = Emu{};
+  g.tile = stage; g.wtile = stage; g.tile_bytes = sizeof stage; g.out = dst; g.out_bytes = dst_bytes; g.hits = hits; g.out_mask = mask.data();
+  const Dsts D{0};
+  const int nthreads = kConsumerWarps * 32;
+  if (staged) {
+    for (uint32_t r = 0; r < nr; ++r) memcpy(stage + r * pitch, src + (uint64_t)r * C * es, (size_t)nc * es);
+  } else {
+    pitch = (pitch + 3u) & ~3u;
+    for (int t = 0; t < nthreads; ++t) {
+      if (es == 4) t8_gather<4>(src, 0, pitch, nr, nc, C, t);
+      else t8_gather<2>(src, 0, pitch, nr, nc, C, t);
+    }
+    // (the kernel has a named barrier here)
+  }
+  std::vector<std::vector<uint32_t>> traces((size_t)nthreads);
+  for (int t = 0; t < nthreads; ++t) {
+    g.trace = &traces[(size_t)t];
+    if (op == KK_OP_T8_F32_BF16) consume_t8<4, 1>(D, 0, pitch, nr, nc, R, col0, row0, 0, t);
+    else if (op == KK_OP_T8_F16_BF16) consume_t8<2, 2>(D, 0, pitch, nr, nc, R, col0, row0, 0, t);
+    else consume_t8<2, 0>(D, 0, pitch, nr, nc, R, col0, row0, 0, t);
+  }
+  g.trace = nullptr;
+  uint64_t wavefronts = 0, ideal = 0;
+  for (int w = 0; w < kConsumerWarps; ++w) {
+    size_t longest = 0;
+    for (int l = 0; l < 32; ++l) longest = std::max(longest, traces[(size_t)(32 * w + l)].size());
+    for (size_t k = 0; k < longest; ++k) {  // the k-th shared load of every lane of the warp is one warp instruction
+      std::vector<uint32_t> words[32];
+      bool any = false;
+      for (int l = 0; l < 32; ++l) {
+        const auto& tr = traces[(size_t)(32 * w + l)];
+        if (k >= tr.size()) continue;
+        any = true;
+        const uint32_t word = tr[k] >> 2;
+        auto& v = words[word & 31u];
+        if (std::find(v.begin(), v.end(), word) == v.end()) v.push_back(word);
+      }
+      if (!any) continue;
+      size_t worst = 1;
+      for (auto& v : words) worst = std::max(worst, v.size());
+      wavefronts += worst;
+      ideal += 1;
+    }
+  }
+  if (stats) { stats[0] = wavefronts; stats[1] = ideal; }
+  return g.err;
 }
 
 // Geometry the kernel and the planner share (kk_ops.h), exported so the test can cross-check the Python-side tables.

@@ -30,6 +30,8 @@ def emul():
     L.kk_emul_dequant_tile.restype = C.c_int
     L.kk_emul_dequant_segment.argtypes = [C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
     L.kk_emul_dequant_segment.restype = C.c_int
+    L.kk_emul_t8_tile.argtypes = [C.c_uint32, C.c_void_p] + [C.c_uint32] * 6 + [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]
+    L.kk_emul_t8_tile.restype = C.c_int
     L.kk_emul_block_geom.argtypes = [C.c_uint32] + [C.POINTER(C.c_uint32)] * 3
     L.kk_emul_block_geom.restype = None
     return L
@@ -121,6 +123,60 @@ def test_fp8_widening_every_byte_value_every_alignment_and_tail(emul, dtype, op,
                 want_hits[-1] = (2 * n) % 16
             assert (hits == want_hits).all()
             assert (out.view(np.uint16) == fn(src)).all(), (dtype, n, pay_off)
+
+
+T8 = {"F32": (helpers.OP_T8_F32_BF16, 4), "F16": (helpers.OP_T8_F16_BF16, 2), "BF16": (helpers.OP_T8_B16, 2)}
+
+
+def t8_expected(dtype, src_rc):
+    """[nr, nc] source elements (as raw uint of the element width) -> bf16 bits [nc, nr] (the transposed, converted tile)."""
+    if dtype == "F32":
+        v = oracle.f32_bits_to_bf16(src_rc.reshape(-1)).reshape(src_rc.shape)
+    elif dtype == "F16":
+        v = oracle.f16_bits_to_bf16(src_rc.reshape(-1)).reshape(src_rc.shape)
+    else:
+        v = src_rc
+    return np.ascontiguousarray(v.T)
+
+
+@pytest.mark.parametrize("dtype", sorted(T8))
+@pytest.mark.parametrize("staged", [1, 0])
+def test_t8_transpose_tiles_values_write_once_and_bank_conflicts(emul, dtype, staged):
+    """8-row transpose tiles: a tile placed inside a bigger tensor (C_total x R destination), full width, ragged width, fewer
+    than 8 rows, destination rows that defeat the 16-byte store (R % 8 != 0) — values vs the oracle, every destination element
+    of the tile written exactly once and nothing else touched.  Staged full tiles must read shared memory conflict-free."""
+    op, es = T8[dtype]
+    W = 4096 // es
+    rng = np.random.default_rng(21)
+    udt = np.uint32 if es == 4 else np.uint16
+    cases = [(8, W, 768, 0), (8, W, 768, 16), (8, 768, 3072, 8), (8, 40, 24, 0), (5, 72, 64, 8), (8, 129 if not staged else 136, 20, 0), (8, 16, 36, 4), (1, 8, 8, 0)]
+    for nr, nc, R, row0 in cases:
+        if staged and (nc * es) % 16:
+            continue
+        Cs = nc + 24  # the tile is a window of a wider source tensor
+        col0 = 8
+        if dtype == "BF16":
+            src = rng.integers(0, 1 << 16, (nr, Cs), dtype=np.uint64).astype(udt)
+        else:
+            src = synth.gen_bytes(dtype, nr * Cs * es, 3, nr + nc).view(udt).reshape(nr, Cs)
+        c_total = col0 + nc + 3
+        dst = np.full(c_total * R, 0xCDCD, np.uint16)
+        hits = np.zeros((dst.nbytes + 15) // 16, np.uint8)
+        stats = (C.c_uint64 * 2)()
+        win = np.ascontiguousarray(src)  # element (0, 0) of the window is src[0, 0]; only the first nc columns belong to the tile
+        rc = emul.kk_emul_t8_tile(op, win.ctypes.data, Cs, nr, nc, R, col0, row0, staged, dst.ctypes.data, dst.nbytes, hits.ctypes.data, stats)
+        assert rc == 0, f"{dtype} {nr}x{nc}: {ERR.get(rc, rc)}"
+        want = np.full((c_total, R), 0xCDCD, np.uint16)
+        want[col0:col0 + nc, row0:row0 + nr] = t8_expected(dtype, win[:, :nc])
+        assert (dst.reshape(c_total, R) == want).all(), (dtype, nr, nc, R, row0)
+        touched = np.zeros(dst.nbytes, np.uint8)
+        m = np.zeros((c_total, R), bool)
+        m[col0:col0 + nc, row0:row0 + nr] = True
+        per16 = np.add.reduceat(np.repeat(m.reshape(-1), 2).astype(np.uint8), np.arange(0, dst.nbytes, 16))
+        assert (hits == per16).all(), "bytes stored per 16-byte unit differ from the tile's footprint"
+        if staged and nr == 8 and nc % 32 == 0:
+            assert stats[0] == stats[1], f"{dtype} {nr}x{nc}: {stats[0]} shared-memory wavefronts for {stats[1]} warp loads"
+        del touched
 
 
 def test_harness_sees_wrong_answers(emul):

@@ -108,3 +108,65 @@ def test_fp8_safetensors_verbatim_by_default_and_widened_on_request(pool, tmp_pa
             assert m.placements("a.weight")[0].dtype == "BF16" and m.placements("a.weight")[0].nbytes == 300 * 512 * 2
         finally:
             m.release()
+
+
+# ---- KK_LOAD_T8_TILES: the candidate 8-row transpose geometry (first hardware run, like the quant types above) ----------------------
+T8 = gpupool.LOAD_GPT2_CONV1D_T | gpupool.LOAD_T8_TILES
+
+
+def test_t8_gpt2_every_dtype_and_odd_shapes(pool, tmp_path):
+    """Same pools as the 32x128 tiles, bit for bit vs the oracle: GPT-2 shaped (R = 96..384: staged path, whole-row tiles of one bulk
+    copy), rows wider than one tile (d = 1032: 4128-byte f32 rows -> two tiles per row group), 16-bit sources, shapes whose R is
+    not a multiple of 8 (planner keeps the 32x128 ops), and an unpadded header (rows off 16-byte alignment -> gather fallback)."""
+    p = str(tmp_path / "gpt2.safetensors")
+    synth.make_gpt2(p, n_layer=2, d=96, vocab=301, n_pos=40)
+    load_and_check(pool, p, flags=T8)
+    for dt, d in (("F16", 40), ("BF16", 40), ("F32", 41), ("F16", 43), ("F32", 1032), ("BF16", 1032)):
+        q = str(tmp_path / f"gpt2_{dt}_{d}.safetensors")
+        synth.write_safetensors(q, synth.gpt2_tensors(n_layer=1, d=d, vocab=50, n_pos=8, dtype=dt), 3)
+        load_and_check(pool, q, flags=T8)
+    for pad in (False, True):
+        q = str(tmp_path / f"unpadded_{int(pad)}.safetensors")
+        synth.write_safetensors(q, [("x", "U8", [3])] + synth.gpt2_tensors(n_layer=1, d=72, vocab=20, n_pos=8, dtype="F32"), 4, pad_header=pad)
+        load_and_check(pool, q, flags=T8)
+
+
+def test_t8_full_size_gpt2_matches_the_32x128_tiles(pool, tmp_path):
+    """GPT-2-small at full size (0.5 GB): checksum of every tensor equal between the two tile geometries and equal to the oracle."""
+    p = str(tmp_path / "gpt2_full.safetensors")
+    synth.make_gpt2(p)
+    a = pool.load(p, flags=gpupool.LOAD_GPT2_CONV1D_T)
+    try:
+        sums = {t["name"]: a.checksum(0, a.placements(t["name"])[0].pool_offset, a.placements(t["name"])[0].nbytes) for t in a.tensors()}
+    finally:
+        a.release()
+    b = pool.load(p, flags=T8)
+    try:
+        for t in b.tensors():
+            pl = b.placements(t["name"])[0]
+            assert b.checksum(0, pl.pool_offset, pl.nbytes) == sums[t["name"]], t["name"]
+        shards, recs = oracle.index_path(p)
+        r = next(x for x in recs if x["name"] == "h.0.attn.c_attn.weight")
+        raw = np.fromfile(shards[0], np.uint8, r["nbytes"], offset=r["file_offset"]).view("<u4").reshape(768, 2304)
+        want = np.ascontiguousarray(oracle.f32_bits_to_bf16(raw.reshape(-1)).reshape(768, 2304).T)
+        pl = b.placements(r["name"])[0]
+        assert pl.shape == [2304, 768] and np.array_equal(b.read(0, pl.pool_offset, pl.nbytes).view(np.uint16).reshape(2304, 768), want)
+    finally:
+        b.release()
+
+
+def test_t8_virtual_rank_fan_out(pool, tmp_path):
+    """The 8-row tiles through the n-destination store ladder (broadcast to 4 virtual ranks on one GPU)."""
+    from tests.test_gpu_load import _virtual_ranks
+    f = str(tmp_path / "gpt2.safetensors")
+    synth.make_gpt2(f, n_layer=2, d=96, vocab=301, n_pos=40)
+    shards, recs = oracle.index_path(f)
+    ms = _virtual_ranks(pool, f, gpupool.MODE_BROADCAST, 4, T8)
+    try:
+        for m in ms:
+            m.load_part()
+        for m in ms:
+            assert_pool_matches(m, 0, shards, recs, flags=gpupool.LOAD_GPT2_CONV1D_T)
+    finally:
+        for m in ms:
+            m.release()
