@@ -66,7 +66,9 @@ def parse():
     ap.add_argument("--no-exchange", action="store_true", help="scatter: every rank gathers its own column runs from the file (no NVLink row exchange)")
     ap.add_argument("--no-single-process", action="store_true", help="skip the one-process-all-GPUs time-to-ready measurement at N > 1")
     ap.add_argument("--t8", action="store_true", help="gpt2: transpose on 8-row tiles (KK_LOAD_T8_TILES), A/B against the 32x128 tiles")
-    ap.add_argument("--fanout", default="p2p", choices=["p2p", "raw"], help="broadcast order: fused convert+fan-out (p2p) or all-gather the file bytes then convert locally (raw)")
+    ap.add_argument("--fanout", default="p2p", choices=["p2p", "raw", "pull"],
+                    help="broadcast order: fused convert+fan-out (p2p), all-gather the file bytes then convert locally (raw), or convert into own pool + "
+                         "slice buffer and pull the peers' slices (pull: peers map 1/N of the bytes, for one-process-per-GPU time-to-ready)")
     return ap.parse_args()
 
 
@@ -314,12 +316,14 @@ def main():
         lflags |= gpupool.LOAD_SCATTER_EXCHANGE
     t1 = time.time()
     raw_order = args.fanout == "raw" and world > 1 and mode == gpupool.MODE_BROADCAST
-    m = modelhub.Load(pool, ref, mode=mode, fanout=gpupool.FANOUT_RAW if raw_order else gpupool.FANOUT_P2P, flags=lflags,
+    pull_order = args.fanout == "pull" and world > 1 and mode == gpupool.MODE_BROADCAST
+    two_stage = raw_order or pull_order  # kk_load_part / kk_convert_resident = stage 1, barrier, kk_convert_local = stage 2
+    m = modelhub.Load(pool, ref, mode=mode, fanout=gpupool.FANOUT_RAW if raw_order else gpupool.FANOUT_PULL if pull_order else gpupool.FANOUT_P2P, flags=lflags,
                       part_index=rank if world > 1 else 0, part_count=world if world > 1 else 0)
     brk["plan_alloc_s"] = time.time() - t1
     t1 = time.time()
     if world > 1 and (mode == gpupool.MODE_BROADCAST or exchange):
-        which = gpupool.BUF_RAW if raw_order else gpupool.BUF_POOL
+        which = gpupool.BUF_RAW if raw_order else gpupool.BUF_SLICE if pull_order else gpupool.BUF_POOL
         h = m.export_buffer(local, which)
         hs = [None] * world
         dist.all_gather_object(hs, h, group=gloo)
@@ -339,7 +343,7 @@ def main():
         brk["barrier_s"] = time.time() - t1
         t1 = time.time()
         m.load_part()
-        if raw_order:
+        if two_stage:
             barrier()
             m.convert_local()
         brk["load_part_s"] = time.time() - t1
@@ -407,7 +411,7 @@ def main():
         barrier()
         t = time.perf_counter()
         m.load_part()
-        if raw_order:
+        if two_stage:
             barrier()
             m.convert_local()
         m.export(local)
@@ -451,7 +455,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         barrier()
         m.convert_resident()
-        if raw_order:
+        if two_stage:
             barrier()
             m.convert_local()
     clocks = ClockSampler(local)
@@ -466,7 +470,7 @@ def main():
     for _ in range(args.steps):
         barrier()
         tot, per = m.convert_resident()
-        if raw_order:  # stage 1 (fan-out of the file bytes) was just timed; stage 2 after every rank's stage 1 has landed
+        if two_stage:  # stage 1 was just timed; stage 2 after every rank's stage 1 has landed
             barrier()
             t2 = m.convert_local()
             raw_ms.append((tot, t2))
@@ -493,6 +497,8 @@ def main():
     alg_per_step = local_src + part["out_bytes"] * (1 if mode == gpupool.MODE_SCATTER else world) if mode != gpupool.MODE_SINGLE else local_src + part["out_bytes"]
     if raw_order:  # stage 1: read own part + incoming peers' parts written; stage 2: read the whole image + write the whole pool
         alg_per_step = local_src + (file_bytes - local_src) + file_bytes + pool_bytes
+    if pull_order:  # stage 1: read own part, write it twice (pool + slice buffer); stage 2: the other ranks' slices written into the pool
+        alg_per_step = local_src + 2 * part["out_bytes"] + (pool_bytes - part["out_bytes"])
     alg_per_launch = alg_per_step / max(n_launch, 1)
     achieved = alg_per_launch / (avg_launch_ms / 1e3) / 1e9 if avg_launch_ms > 0 else 0.0
     traffic = None
@@ -555,6 +561,16 @@ def main():
         "setup": {"synth_s": t_gen, "kk_open_s": t_open, "index_s": st0["index_s"], "plan_s": st0["plan_s"], "alloc_s": st0["alloc_s"],
                   "first_load_s": st0["load_s"], "chunks_per_load": chunks_per_load, "h2d_probe_GBps": h2d_probe},
     }
+    if pull_order:
+        line["config"]["mode"] = "broadcast, PULL order: convert into own pool + slice buffer (stage 1), pull the peers' slices over NVLink (stage 2)"
+        line["pull_stages_ms_rank0"] = {"convert_ms": sum(a for a, _ in raw_ms) / len(raw_ms), "pull_ms": sum(b for _, b in raw_ms) / len(raw_ms)}
+        if nvlink:
+            ing = pool_bytes - part["out_bytes"]
+            pm = line["pull_stages_ms_rank0"]["pull_ms"]
+            nvlink.update(egress_bytes_per_step_per_gpu=ing, achieved_GBps_per_gpu=ing / (pm / 1e3) / 1e9 if pm > 0 else 0.0,
+                          form="all-gather by P2P bulk LOADS from the peers' slice buffers (stage 2 only; bytes are ingress per GPU)")
+            nvlink["frac_of_measured"] = nvlink["achieved_GBps_per_gpu"] / 770.0
+            nvlink["frac_of_nominal"] = nvlink["achieved_GBps_per_gpu"] / 900.0
     if raw_order:
         line["config"]["mode"] = "broadcast, RAW order: all-gather file bytes over NVLink (stage 1) + local convert (stage 2)"
         line["raw_stages_ms_rank0"] = {"fanout_ms": sum(a for a, _ in raw_ms) / len(raw_ms), "convert_ms": sum(b for _, b in raw_ms) / len(raw_ms)}

@@ -84,8 +84,12 @@ typedef enum kk_fanout {
   KK_FANOUT_P2P = 0,  /* convert kernel stores every output vector to all peer-mapped pools (NVLink/NVSwitch) */
   KK_FANOUT_NVLS = 1, /* multimem.st on an NVLS multicast mapping of the pools (when the host exposes it) */
   KK_FANOUT_NONE = 2, /* local pool only; the caller runs its own collective (e.g. the NCCL comparison) */
-  KK_FANOUT_RAW = 3   /* BROADCAST only: all-gather the *file* bytes (e.g. q4_K blocks, 3.56x smaller than their bf16)
+  KK_FANOUT_RAW = 3,  /* BROADCAST only: all-gather the *file* bytes (e.g. q4_K blocks, 3.56x smaller than their bf16)
                          into a per-device raw image over NVLink, then every device converts everything locally */
+  KK_FANOUT_PULL = 4  /* BROADCAST, one process per GPU only: every rank converts its part into its own pool AND into a slice buffer
+                         (its 1/N of the pool, a separate allocation); peers map only the slice buffers — 1/N of the bytes a pool
+                         mapping costs, which is what dominates time-to-ready in that deployment — and kk_convert_local pulls them
+                         into the local pool with bulk loads over NVLink.  Same NVLink bytes as the push order. */
 } kk_fanout;
 
 /* kk_config.flags */
@@ -214,8 +218,13 @@ int kk_peer_detach_all(kk_model* m);
 #define KK_BUF_RAW 1
 #define KK_BUF_POOL_PTR 2 /* kk_peer_attach_buffer only: `ipc_handle_64B` points at a `void*` holding a device pointer that is
                              already valid in THIS process (several ranks hosted by one process, e.g. the single-GPU tests) */
+#define KK_BUF_SLICE 3     /* KK_FANOUT_PULL: the slice buffer (export: its IPC handle; attach: the peer's) */
+#define KK_BUF_SLICE_PTR 4 /* same, by raw device pointer valid in this process: export writes a `void*` into the first 8 bytes of
+                             ipc_handle_64B, attach reads one from it */
 int kk_export_buffer(kk_model* m, int device, int which, void* ipc_handle_64B);
 int kk_peer_attach_buffer(kk_model* m, int rank, int which, const void* ipc_handle_64B);
+/* KK_FANOUT_PULL uses the same two-stage protocol: kk_load_part (stage 1: own part -> own pool + slice buffer), caller-side barrier,
+ * kk_convert_local (stage 2: pull every attached peer's slice into the local pool). */
 int kk_convert_local(kk_model* m, float* ms_total);
 
 int kk_model_get_info(kk_model* m, kk_model_info* out);

@@ -191,6 +191,8 @@ int kk_export_buffer(kk_model* m, int device, int which, void* h) {
       memcpy(h, &ih, sizeof ih);
     } else if (which == KK_BUF_RAW) {
       kk::model_export_raw(m, li, h);
+    } else if (which == KK_BUF_SLICE || which == KK_BUF_SLICE_PTR) {
+      kk::model_export_slice(m, h, which == KK_BUF_SLICE_PTR);
     } else kk::fail(KK_EINVAL, "unknown buffer kind %d", which);
   });
 }
@@ -202,6 +204,8 @@ int kk_peer_attach_buffer(kk_model* m, int rank, int which, const void* h) {
     if (which == KK_BUF_POOL) kk::model_peer_attach(m, rank, h, true);
     else if (which == KK_BUF_POOL_PTR) kk::model_peer_attach(m, rank, h, false);
     else if (which == KK_BUF_RAW) kk::model_peer_attach_raw(m, rank, h);
+    else if (which == KK_BUF_SLICE) kk::model_peer_attach_slice(m, rank, h, true);
+    else if (which == KK_BUF_SLICE_PTR) kk::model_peer_attach_slice(m, rank, h, false);
     else kk::fail(KK_EINVAL, "unknown buffer kind %d", which);
   });
 }

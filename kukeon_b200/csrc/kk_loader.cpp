@@ -16,6 +16,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstring>
 #include <exception>
@@ -200,6 +201,32 @@ void pad_dsts_for_test(ConvertLaunch& L) {
   while (L.n_dst < (uint32_t)want && L.n_dst < KK_MAX_DST) { L.dst[L.n_dst] = L.dst[L.n_dst % have]; L.n_dst++; }
 }
 
+bool is_pull(const kk_model* m) { return m->opts.fanout == KK_FANOUT_PULL && m->plan.mode == KK_MODE_BROADCAST; }
+
+// Pool bytes [lo, hi) that plan part `part` produces.  Pool order equals file order, so for every op that writes its output
+// linearly this is one contiguous range and the ranges of different parts are disjoint.  Returns false when the part carries ops
+// whose output is not linear in the pool (transposes, the scatter row exchange): such plans cannot be pulled slice by slice.
+bool part_pool_range(const Plan& P, int part, uint64_t& lo, uint64_t& hi) {
+  lo = UINT64_MAX;
+  hi = 0;
+  for (auto& s : P.parts[(size_t)part].segs) {
+    uint64_t e;
+    switch (s.op) {
+      case KK_OP_COPY: e = s.dst_off + s.units; break;
+      case KK_OP_F32_BF16: case KK_OP_F16_BF16: case KK_OP_F8E4M3_BF16: case KK_OP_F8E5M2_BF16: e = s.dst_off + s.units * 2; break;
+      default: {
+        const KKBlockGeom g = kk_block_geom(s.op);
+        if (!g.block_bytes) return false;
+        e = s.dst_off + s.units * g.out_bytes;
+      }
+    }
+    if (s.dst_off < lo) lo = s.dst_off;
+    if (e > hi) hi = e;
+  }
+  if (lo == UINT64_MAX) lo = hi = 0;
+  return true;
+}
+
 // Destination pools a convert launch on local device `li` writes to.
 void fill_dsts(kk_model* m, int li, ConvertLaunch& L) {
   L.n_dst = 0;
@@ -219,6 +246,10 @@ void fill_dsts(kk_model* m, int li, ConvertLaunch& L) {
       L.xdst[j] = p;
     }
     L.n_xdst = (uint32_t)n;
+  }
+  if (is_pull(m)) {  // stage 1 of a pull load: the same bytes into the slice buffer the peers will read (pool offset -> slice_buf - slice_base)
+    if (m->slice_buf) L.dst[L.n_dst++] = (uint8_t*)((uintptr_t)m->slice_buf - (uintptr_t)m->slice_base);
+    return;
   }
   if (m->plan.mode != KK_MODE_BROADCAST || m->opts.fanout == KK_FANOUT_NONE) {
     pad_dsts_for_test(L);
@@ -472,6 +503,66 @@ void convert_local_all(kk_model* m, float* ms_total) {
   if (ms_total) *ms_total = worst;
 }
 
+// Stage 2 of a KK_FANOUT_PULL load: one COPY launch whose segments read every attached peer's slice buffer over NVLink (bulk loads)
+// and write the local pool.  Segments start with the peer after this rank so that the N ranks do not all read GPU 0 first.
+void pull_slices(kk_model* m, float* ms_total) {
+  kk_ctx* c = m->ctx;
+  Device& dev = c->devs[(size_t)m->dev_idx[0]];
+  const int n = m->opts.part_count, me = m->opts.part_index;
+  std::vector<int> peers;
+  for (int k = 1; k < n; ++k) {
+    const int r = (me + k) % n;
+    if (m->part_range[(size_t)r].second > m->part_range[(size_t)r].first) {
+      if (!m->peer_slice_ptr[r]) fail(KK_ESTATE, "KK_FANOUT_PULL: the slice buffer of rank %d is not attached (kk_peer_attach_buffer, KK_BUF_SLICE)", r);
+      peers.push_back(r);
+    }
+  }
+  KK_CUDA(cudaSetDevice(dev.ordinal));
+  EventSet ev(2);
+  ev.create_all();
+  if (peers.empty()) {
+    KK_CUDA(cudaEventRecord(ev[0], dev.stream));
+    KK_CUDA(cudaEventRecord(ev[1], dev.stream));
+  } else {
+    // one src base for the launch: the numerically lowest peer mapping; every segment's src_off is its distance from it
+    uintptr_t base = UINTPTR_MAX;
+    for (int r : peers) base = std::min(base, (uintptr_t)m->peer_slice_ptr[r]);
+    base &= ~(uintptr_t)15;
+    std::vector<KKSeg> segs;
+    uint64_t tiles = 0;
+    for (int r : peers) {
+      const uint64_t lo = m->part_range[(size_t)r].first, hi = m->part_range[(size_t)r].second;
+      KKSeg sg{};
+      sg.src_off = (uint64_t)((uintptr_t)m->peer_slice_ptr[r] - base) + (lo - (lo & ~(uint64_t)255));  // peers allocate from slice_base = lo & ~255
+      sg.dst_off = lo;
+      sg.units = hi - lo;
+      sg.op = KK_OP_COPY;
+      sg.tile_begin = (uint32_t)tiles;
+      tiles += kk_seg_tiles(KK_OP_COPY, sg.units, 0);
+      segs.push_back(sg);
+    }
+    if (tiles > 0xFFFFFFF0ull) fail(KK_EUNSUPPORTED, "too many tiles for one pull launch");
+    DevScratch tmp;
+    KK_CUDA(cudaMalloc(&tmp.p, segs.size() * sizeof(KKSeg)));
+    KK_CUDA(cudaMemcpyAsync(tmp.p, segs.data(), segs.size() * sizeof(KKSeg), cudaMemcpyHostToDevice, dev.stream));
+    ConvertLaunch L{};
+    L.src = (const uint8_t*)base;
+    L.segs = (const KKSeg*)tmp.p;
+    L.n_segs = (uint32_t)segs.size();
+    L.n_tiles = (uint32_t)tiles;
+    L.n_dst = 1;
+    L.dst[0] = m->pools[0];
+    KK_CUDA(cudaEventRecord(ev[0], dev.stream));
+    KK_CUDA(launch_convert(L, dev.sm_count, dev.stream));
+    KK_CUDA(cudaEventRecord(ev[1], dev.stream));
+    KK_CUDA(cudaStreamSynchronize(dev.stream));  // tmp outlives the launch
+  }
+  KK_CUDA(cudaStreamSynchronize(dev.stream));
+  float ms = 0.f;
+  KK_CUDA(cudaEventElapsedTime(&ms, ev[0], ev[1]));
+  if (ms_total) *ms_total = ms;
+}
+
 void free_resident(kk_model* m) {
   for (size_t li = 0; li < m->resident.size(); ++li) {
     auto& R = m->resident[li];
@@ -494,6 +585,17 @@ void destroy_model(kk_model* m) {
       m->peer_raw_ptr[r] = nullptr;
     }
   free_raw(m);
+  for (int r = 0; r < KK_MAX_DEVICES; ++r)
+    if (m->peer_slice_ptr[r]) {
+      cudaSetDevice(c->devs[(size_t)m->dev_idx[0]].ordinal);
+      if (m->peer_slice_is_ipc[r]) cudaIpcCloseMemHandle(m->peer_slice_ptr[r]);
+      m->peer_slice_ptr[r] = nullptr;
+    }
+  if (m->slice_buf) {
+    cudaSetDevice(c->devs[(size_t)m->dev_idx[0]].ordinal);
+    cudaFree(m->slice_buf);
+    m->slice_buf = nullptr;
+  }
   for (int r = 0; r < KK_MAX_DEVICES; ++r)
     if (m->peer_ptr[r]) {
       cudaSetDevice(c->devs[(size_t)m->dev_idx[0]].ordinal);
@@ -685,11 +787,14 @@ kk_model* model_load(kk_ctx* c, const std::string& path, const kk_load_opts& opt
   if (opts.part_index < 0 || opts.part_index >= opts.part_count || opts.part_count > KK_MAX_DEVICES)
     fail(KK_EINVAL, "part %d of %d out of range", opts.part_index, opts.part_count);
   if (opts.mode < KK_MODE_SINGLE || opts.mode > KK_MODE_SCATTER) fail(KK_EINVAL, "unknown mode %d", opts.mode);
-  if (opts.fanout < KK_FANOUT_P2P || opts.fanout > KK_FANOUT_RAW) fail(KK_EINVAL, "unknown fanout %d", opts.fanout);
+  if (opts.fanout < KK_FANOUT_P2P || opts.fanout > KK_FANOUT_PULL) fail(KK_EINVAL, "unknown fanout %d", opts.fanout);
   if (opts.fanout == KK_FANOUT_NVLS)
     fail(KK_EUNSUPPORTED, "fan-out NVLS is not available in this build (an all-gather is ingress-bound either way; see DESIGN.md)");
   if (opts.fanout == KK_FANOUT_RAW && opts.mode != KK_MODE_BROADCAST) fail(KK_EINVAL, "KK_FANOUT_RAW only applies to KK_MODE_BROADCAST");
   const bool multi_proc = opts.part_count > 1;
+  if (opts.fanout == KK_FANOUT_PULL && opts.mode != KK_MODE_BROADCAST) fail(KK_EINVAL, "KK_FANOUT_PULL only applies to KK_MODE_BROADCAST");
+  if (opts.fanout == KK_FANOUT_PULL && !multi_proc)
+    fail(KK_EINVAL, "KK_FANOUT_PULL is for one-process-per-GPU operation (part_count > 1); one process owning the GPUs fans out with P2P stores");
   if (multi_proc && c->cfg.n_devices != 1) fail(KK_EINVAL, "multi-process parts need a one-device context (got %d devices)", c->cfg.n_devices);
   if (multi_proc && opts.mode == KK_MODE_SINGLE) fail(KK_EINVAL, "KK_MODE_SINGLE cannot be split into parts");
 
@@ -765,10 +870,22 @@ kk_model* model_load(kk_ctx* c, const std::string& path, const kk_load_opts& opt
       }
     }
     if (is_raw(m)) setup_raw(m);
+    if (is_pull(m)) {
+      m->part_range.assign((size_t)m->plan.n_parts, {0, 0});
+      for (int p = 0; p < m->plan.n_parts; ++p)
+        if (!part_pool_range(m->plan, p, m->part_range[(size_t)p].first, m->part_range[(size_t)p].second))
+          fail(KK_EUNSUPPORTED, "KK_FANOUT_PULL cannot be combined with transposing loads (their output is not one contiguous pool range per rank)");
+      const auto& mine = m->part_range[(size_t)opts.part_index];
+      m->slice_base = mine.first & ~(uint64_t)255;
+      const uint64_t sb = mine.second > m->slice_base ? mine.second - m->slice_base : 0;
+      KK_CUDA(cudaSetDevice(c->devs[(size_t)m->dev_idx[0]].ordinal));
+      cudaError_t se = cudaMalloc((void**)&m->slice_buf, align_up(sb ? sb : 256, 256));
+      if (se != cudaSuccess) { cudaGetLastError(); m->slice_buf = nullptr; fail(KK_ENOMEM, "cudaMalloc(%llu) for the slice buffer failed", (unsigned long long)sb); }
+    }
     m->t_alloc = now_s() - t0;
     if (!(opts.flags & KK_LOAD_DEFER)) {
       do_load(m);
-      m->loaded = !(is_raw(m) && multi_proc);
+      m->loaded = !((is_raw(m) || is_pull(m)) && multi_proc);
       if (is_raw(m) && !multi_proc) free_raw(m);  // the gathered file bytes are not needed once the pools are built
     }
   } catch (...) {
@@ -793,12 +910,18 @@ void model_load_part(kk_model* m) {
   if (is_raw(m) && m->raw.empty()) fail(KK_ESTATE, "the raw image of this model has been released");
   do_load(m);
   std::lock_guard<std::mutex> g(m->ctx->mu);
-  if (!(is_raw(m) && m->opts.part_count > 1)) m->loaded = true;  // multi-process RAW: loaded after kk_convert_local
+  if (!((is_raw(m) || is_pull(m)) && m->opts.part_count > 1)) m->loaded = true;  // multi-process RAW / PULL: loaded after kk_convert_local
 }
 
 void model_convert_local(kk_model* m, float* ms_total) {
   std::lock_guard<std::mutex> op(m->op_mu);
-  if (!is_raw(m) || m->raw.empty()) fail(KK_ESTATE, "kk_convert_local only applies to KK_FANOUT_RAW models with a live raw image");
+  if (is_pull(m)) {
+    pull_slices(m, ms_total);
+    std::lock_guard<std::mutex> g(m->ctx->mu);
+    m->loaded = true;
+    return;
+  }
+  if (!is_raw(m) || m->raw.empty()) fail(KK_ESTATE, "kk_convert_local only applies to KK_FANOUT_RAW models with a live raw image and to KK_FANOUT_PULL models");
   convert_local_all(m, ms_total);
   std::lock_guard<std::mutex> g(m->ctx->mu);
   m->loaded = true;
@@ -826,6 +949,38 @@ void model_peer_attach_raw(kk_model* m, int rank, const void* handle) {
   void* p = nullptr;
   KK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
   m->peer_raw_ptr[rank] = p;
+}
+
+void model_export_slice(kk_model* m, void* handle_out, bool as_pointer) {
+  if (!is_pull(m) || !m->slice_buf) fail(KK_ESTATE, "this model has no slice buffer (KK_FANOUT_PULL only)");
+  if (as_pointer) {
+    void* p = m->slice_buf;
+    memcpy(handle_out, &p, sizeof p);
+    return;
+  }
+  KK_CUDA(cudaSetDevice(m->ctx->devs[(size_t)m->dev_idx[0]].ordinal));
+  cudaIpcMemHandle_t h;
+  KK_CUDA(cudaIpcGetMemHandle(&h, m->slice_buf));
+  memcpy(handle_out, &h, sizeof h);
+}
+
+void model_peer_attach_slice(kk_model* m, int rank, const void* handle, bool is_ipc) {
+  std::lock_guard<std::mutex> op(m->op_mu);
+  if (!is_pull(m)) fail(KK_ESTATE, "slice attach needs a KK_FANOUT_PULL model");
+  if (rank < 0 || rank >= m->opts.part_count || rank == m->opts.part_index) fail(KK_EINVAL, "bad peer rank %d", rank);
+  if (m->peer_slice_ptr[rank]) fail(KK_ESTATE, "peer rank %d already attached", rank);
+  KK_CUDA(cudaSetDevice(m->ctx->devs[(size_t)m->dev_idx[0]].ordinal));
+  void* p = nullptr;
+  if (is_ipc) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    KK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  } else {
+    memcpy(&p, handle, sizeof p);
+    if (!p) fail(KK_EINVAL, "null device pointer");
+  }
+  m->peer_slice_ptr[rank] = p;
+  m->peer_slice_is_ipc[rank] = is_ipc;
 }
 
 void model_release(kk_model* m) {
@@ -873,6 +1028,10 @@ void model_peer_detach_all(kk_model* m) {
     if (m->peer_raw_ptr[r]) {
       cudaIpcCloseMemHandle(m->peer_raw_ptr[r]);
       m->peer_raw_ptr[r] = nullptr;
+    }
+    if (m->peer_slice_ptr[r]) {
+      if (m->peer_slice_is_ipc[r]) cudaIpcCloseMemHandle(m->peer_slice_ptr[r]);
+      m->peer_slice_ptr[r] = nullptr;
     }
   }
 }

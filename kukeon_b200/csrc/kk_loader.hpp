@@ -96,6 +96,13 @@ struct kk_model {
   std::vector<std::vector<uint64_t>> img_off;   // [part][chunk] offset of the chunk buffer inside the raw image
   std::vector<uint32_t> chunk_base;             // prefix sum of chunk counts per part
   void* peer_raw_ptr[KK_MAX_DEVICES] = {};      // IPC-opened raw images of the other ranks
+  // KK_FANOUT_PULL (one process per GPU): this rank's part of the pool, [slice_lo, slice_hi), also lives in slice_buf (a separate,
+  // small allocation — the only thing peers have to map); slice_buf[0] corresponds to pool offset slice_base
+  uint8_t* slice_buf = nullptr;
+  uint64_t slice_base = 0;
+  std::vector<std::pair<uint64_t, uint64_t>> part_range;  // [lo, hi) pool bytes every part produces
+  void* peer_slice_ptr[KK_MAX_DEVICES] = {};
+  bool peer_slice_is_ipc[KK_MAX_DEVICES] = {};
   bool raw_staged = false;                      // stage 1 complete on this process since the last conversion
   // state
   std::mutex op_mu;  // serialises the data-moving calls on ONE model (kk_load_part, kk_convert_local, kk_*_resident) against each other
@@ -121,6 +128,8 @@ void model_release(kk_model* m);
 void model_peer_attach(kk_model* m, int rank, const void* handle, bool is_ipc = true);
 void model_peer_attach_raw(kk_model* m, int rank, const void* handle);
 void model_export_raw(kk_model* m, int local, void* handle_out);
+void model_export_slice(kk_model* m, void* handle_out, bool as_pointer);
+void model_peer_attach_slice(kk_model* m, int rank, const void* handle, bool is_ipc);
 void model_convert_local(kk_model* m, float* ms_total);
 void model_peer_detach_all(kk_model* m);
 int model_local_device(kk_model* m, int ordinal);  // index into m->dev_idx or throws

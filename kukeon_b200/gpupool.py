@@ -21,10 +21,10 @@ KK_IPC_HANDLE_BYTES = 64
 KK_POOL_ALIGN = 256
 
 MODE_SINGLE, MODE_BROADCAST, MODE_SCATTER = 0, 1, 2
-FANOUT_P2P, FANOUT_NVLS, FANOUT_NONE, FANOUT_RAW = 0, 1, 2, 3
+FANOUT_P2P, FANOUT_NVLS, FANOUT_NONE, FANOUT_RAW, FANOUT_PULL = 0, 1, 2, 3, 4
 CFG_ZEROCOPY, CFG_NO_PEER_ACCESS, CFG_NO_NUMA_PIN, CFG_PEER_ALL = 0x1, 0x2, 0x4, 0x8
 LOAD_GPT2_CONV1D_T, LOAD_KEEP_F32, LOAD_DEFER, LOAD_SCATTER_EXCHANGE, LOAD_F8_TO_BF16, LOAD_T8_TILES = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
-BUF_POOL, BUF_RAW, BUF_POOL_PTR = 0, 1, 2
+BUF_POOL, BUF_RAW, BUF_POOL_PTR, BUF_SLICE, BUF_SLICE_PTR = 0, 1, 2, 3, 4
 
 DTYPE_NAMES = {
     0: "BOOL", 1: "F4", 2: "F6_E2M3", 3: "F6_E3M2", 4: "U8", 5: "I8", 6: "F8_E5M2", 7: "F8_E4M3", 8: "F8_E8M0",
@@ -291,7 +291,8 @@ class Model:
         _check(lib().kk_peer_attach(self._h, rank, C.c_char_p(ipc_handle)))
 
     def export_buffer(self, device: int, which: int) -> bytes:
-        """IPC handle of the pool (BUF_POOL) or of the raw image of a KK_FANOUT_RAW model (BUF_RAW)."""
+        """IPC handle of the pool (BUF_POOL), of the raw image of a KK_FANOUT_RAW model (BUF_RAW) or of the slice buffer of a
+        KK_FANOUT_PULL model (BUF_SLICE; BUF_SLICE_PTR: its raw device pointer in the first 8 bytes, for ranks sharing a process)."""
         h = C.create_string_buffer(KK_IPC_HANDLE_BYTES)
         _check(lib().kk_export_buffer(self._h, device, which, h))
         return h.raw
@@ -306,7 +307,8 @@ class Model:
         _check(lib().kk_peer_attach_buffer(self._h, rank, BUF_POOL_PTR, C.byref(p)))
 
     def convert_local(self) -> float:
-        """Stage 2 of a multi-process KK_FANOUT_RAW load; returns its CUDA-event milliseconds."""
+        """Stage 2 of a multi-process KK_FANOUT_RAW load (dequantise the gathered bytes) or of a KK_FANOUT_PULL load (pull the peers'
+        slices over NVLink); returns its CUDA-event milliseconds."""
         ms = C.c_float()
         _check(lib().kk_convert_local(self._h, C.byref(ms)))
         return float(ms.value)

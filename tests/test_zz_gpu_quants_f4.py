@@ -170,3 +170,126 @@ def test_t8_virtual_rank_fan_out(pool, tmp_path):
     finally:
         for m in ms:
             m.release()
+
+
+# ---- KK_FANOUT_PULL: one-process-per-GPU broadcast where peers map only 1/N slice buffers (first hardware run) --------------------------
+def _pull_ranks(pool, path, n, flags=0):
+    import ctypes as C
+    ms = [pool.load(path, mode=gpupool.MODE_BROADCAST, fanout=gpupool.FANOUT_PULL, flags=flags | gpupool.LOAD_DEFER, part_index=i, part_count=n) for i in range(n)]
+    ptrs = [m.export_buffer(0, gpupool.BUF_SLICE_PTR) for m in ms]  # raw device pointer in the first 8 bytes
+    assert all(int.from_bytes(p[:8], "little") for p in ptrs)
+    for i, m in enumerate(ms):
+        for j in range(n):
+            if j != i:
+                m.peer_attach_buffer(j, gpupool.BUF_SLICE_PTR, ptrs[j])
+    return ms
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_pull_fan_out_virtual_ranks_on_one_gpu(pool, tmp_path, n):
+    """n ranks hosted by one process on one GPU (slice buffers attached by raw pointer): stage 1 on every rank, then stage 2 — every
+    pool must equal the oracle's; stage 1 alone leaves a rank with only its own part and `loaded` false."""
+    from tests.test_plan import q4km_tensors
+    d = str(tmp_path / "llama")
+    synth.make_llama(d, dict(hidden=256, ffn=704, layers=2, kv_dim=64, vocab=3000), max_shard_bytes=3_000_000)
+    g = str(tmp_path / "q4km.gguf")
+    synth.write_gguf(g, q4km_tensors(), 9)
+    for path in (d, g):
+        shards, recs = oracle.index_path(path)
+        ms = _pull_ranks(pool, path, n)
+        try:
+            for m in ms:
+                m.load_part()
+                assert not m.info()["loaded"]
+            for m in ms:
+                assert m.convert_local() >= 0.0
+                assert m.info()["loaded"]
+            for m in ms:
+                assert_pool_matches(m, 0, shards, recs)
+            for m in ms:  # again through the resident image (what bench.py times)
+                m.stage_resident()
+            for m in ms:
+                m.convert_resident()
+            for m in ms:
+                m.convert_local()
+            for m in ms:
+                assert_pool_matches(m, 0, shards, recs)
+        finally:
+            for m in ms:
+                m.release()
+
+
+def test_pull_argument_and_state_errors(pool, tmp_path):
+    d = str(tmp_path / "llama")
+    synth.make_llama(d, dict(hidden=128, ffn=352, layers=1, kv_dim=32, vocab=500), max_shard_bytes=3_000_000)
+    with pytest.raises(gpupool.ErrInvalid, match="one-process-per-GPU"):
+        pool.load(d, mode=gpupool.MODE_BROADCAST, fanout=gpupool.FANOUT_PULL)
+    with pytest.raises(gpupool.ErrInvalid):
+        pool.load(d, mode=gpupool.MODE_SCATTER, fanout=gpupool.FANOUT_PULL, part_index=0, part_count=2)
+    f = str(tmp_path / "gpt2.safetensors")
+    synth.make_gpt2(f, n_layer=1, d=96, vocab=301, n_pos=40)
+    with pytest.raises(gpupool.ErrUnsupported, match="transposing"):
+        pool.load(f, mode=gpupool.MODE_BROADCAST, fanout=gpupool.FANOUT_PULL, flags=gpupool.LOAD_GPT2_CONV1D_T | gpupool.LOAD_DEFER, part_index=0, part_count=2)
+    m = pool.load(d, mode=gpupool.MODE_BROADCAST, fanout=gpupool.FANOUT_PULL, flags=gpupool.LOAD_DEFER, part_index=0, part_count=2)
+    try:
+        m.load_part()
+        with pytest.raises(gpupool.ErrState, match="not attached"):
+            m.convert_local()  # the other rank's slice was never attached: refuse, do not leave half a pool marked loaded
+        assert not m.info()["loaded"]
+        with pytest.raises(gpupool.ErrState):
+            m.peer_attach_buffer(1, gpupool.BUF_RAW, b"\0" * 64)
+    finally:
+        m.release()
+
+
+def _pull_rank_main(rank, world, port, path, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.cuda.set_device(rank)
+        from kukeon_b200 import gpupool as gp
+        from oracle import oracle as orc
+        shards, recs = orc.index_path(path)
+        with gp.Pool([rank], n_staging_buffers=2, staging_buffer_bytes=1 << 20, n_reader_threads=1) as pl:
+            m = pl.load(path, mode=gp.MODE_BROADCAST, fanout=gp.FANOUT_PULL, flags=gp.LOAD_DEFER, part_index=rank, part_count=world)
+            try:
+                hs = [None] * world
+                dist.all_gather_object(hs, m.export_buffer(rank, gp.BUF_SLICE))
+                for r, hh in enumerate(hs):
+                    if r != rank:
+                        m.peer_attach_buffer(r, gp.BUF_SLICE, hh)
+                dist.barrier()
+                m.load_part()
+                dist.barrier()
+                m.convert_local()
+                exp, plan = orc.expected_pool(shards, recs, 1, 0)
+                got = m.read(rank, 0, len(exp))
+                for p in plan:
+                    a, b = p["pool_offset"], p["pool_offset"] + p["nbytes"]
+                    assert np.array_equal(got[a:b], exp[a:b]), f"rank {rank} PULL: {p['name']} differs"
+                dist.barrier()
+                m.peer_detach_all()
+            finally:
+                m.release()
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.multigpu
+def test_pull_one_process_per_gpu_over_ipc(native, tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+    from tests.test_gpu_multi import _free_port
+    ngpu = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if ngpu < 4 else 4
+    d = str(tmp_path / "llama")
+    synth.make_llama(d, dict(hidden=256, ffn=704, layers=3, kv_dim=64, vocab=3000), max_shard_bytes=3_000_000)
+    out = str(tmp_path / "out")
+    os.makedirs(out)
+    mp.spawn(_pull_rank_main, args=(world, _free_port(), d, out), nprocs=world, join=True)
+    assert sorted(os.listdir(out)) == [f"ok{r}" for r in range(world)]
