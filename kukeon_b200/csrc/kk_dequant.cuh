@@ -14,6 +14,7 @@
 //     uint4    lds128(a)                         16-byte aligned vector load
 //     uint32_t kk_f8x2_to_f16x2<E5M2>(u16)       two FP8 -> two fp16 (exact; cvt.rn.f16x2.e4m3x2 / .e5m2x2 on the device)
 //     float    kk_bits2f(u32)                    bit cast
+//     uint32_t kk_byte_perm(a, b, sel)           PRMT: byte (sel & 7) of the 8 bytes {b:a} in the low byte of the result
 //     void     sts16(a, v) / sts32(a, v)         stores into the stage (gather fallback of the 8-row transposes)
 //     uint32_t kk_ldg8(p)                        one byte from global memory (same fallback)
 //     Dsts, uint4, make_uint4, kConsumerWarps, KK_DQ_DEV (function attributes)
@@ -305,5 +306,68 @@ KK_DQ_DEV void t8_gather(const uint8_t* src, uint32_t sbase, uint32_t pitch, uin
     for (int k = 0; k < ES; ++k) w |= kk_ldg8(p + k) << (8 * k);
     if (ES == 4) sts32(sbase + r * pitch + c * 4u, w);
     else sts16(sbase + r * pitch + c * 2u, w);
+  }
+}
+
+// ---- §8(f4): 4-bit codebook types ---------------------------------------------------------------------------------------------------
+// IQ4_NL (18 B): d f16 | qs[16] — Q4_0's nibble layout, value = kIQ4NL[q4]                       (gguf/quants.py:1330-1348)
+// IQ4_XS (136 B): d f16 | scales_h u16 | scales_l[4] | qs[128]; sub-block j (32 weights): 6-bit scale
+//                 ls = ((scales_l[j/2] >> 4(j%2)) & 15) | (((scales_h >> 2j) & 3) << 4), y = (d*(ls-32)) * kIQ4NL[q4]; its elements
+//                 i < 16 are the low nibbles of qs[16j + i], i >= 16 the high nibbles of qs[16j + i - 16]   (gguf/quants.py:1351-1380)
+// MXFP4 (17 B):   e u8 (E8M0) | qs[16]; y = 2^(e-128) * kMXFP4[q4] (the table holds DOUBLED e2m1 values)   (gguf/quants.py:656-708)
+// The 16-entry tables live in four registers each; a lookup is one PRMT over a register pair picked by bit 3 of the index.
+template <int TABLE>  // 0: IQ4_NL values, 1: MXFP4 (e2m1 x 2)
+KK_DQ_DEV float lut16(uint32_t idx) {
+  // little-endian packing of {-127,-104,-83,-65, -49,-35,-22,-10, 1,13,25,38, 53,69,89,113} and {0,1,2,3, 4,6,8,12, 0,-1,-2,-3, -4,-6,-8,-12}
+  constexpr uint32_t K0 = TABLE ? 0x03020100u : 0xBFAD9881u, K1 = TABLE ? 0x0C080604u : 0xF6EADDCFu;
+  constexpr uint32_t K2 = TABLE ? 0xFDFEFF00u : 0x26190D01u, K3 = TABLE ? 0xF4F8FAFCu : 0x71594535u;
+  const uint32_t b = (idx & 8u) ? kk_byte_perm(K2, K3, idx & 7u) : kk_byte_perm(K0, K1, idx & 7u);
+  return (float)(int)(signed char)(b & 0xFFu);
+}
+// 32-weight codebook blocks: lane l takes elements 8(l&3)..+8 of block (l>>2), eight blocks per warp iteration (as consume_legacy32).
+template <uint32_t BYTES, int TABLE>
+KK_DQ_DEV void consume_codebook32(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
+  constexpr uint32_t kQsOff = BYTES - 16u;  // 2 (fp16 d) or 1 (E8M0 byte)
+  const uint32_t e0 = 8u * (uint32_t)(lane & 3);
+  const uint32_t q_off = kQsOff + (e0 & 15u);
+  const uint32_t nsh = (e0 >> 4) * 4u;
+  for (uint32_t b0 = (uint32_t)cwarp * 8u; b0 < nblk; b0 += kConsumerWarps * 8u) {
+    const uint32_t b = b0 + (uint32_t)(lane >> 2);
+    if (b < nblk) {
+      const uint32_t blk = pay + b * BYTES;
+      float d;
+      if (TABLE == 1) {
+        const uint32_t e = lds8(blk);
+        d = kk_bits2f(e < 2u ? (0x00200000u << e) : ((e - 1u) << 23));  // half of 2^(e-127): the table values are doubled
+      } else {
+        d = lds_f16(blk);
+      }
+      const uint32_t q0 = (lds32_any(blk + q_off) >> nsh) & 0x0F0F0F0Fu;
+      const uint32_t q1 = (lds32_any(blk + q_off + 4u) >> nsh) & 0x0F0F0F0Fu;
+      float y[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = __fmul_rn(d, lut16<TABLE>(((e < 4 ? q0 : q1) >> (8 * (e & 3))) & 0xFu));
+      store_bf16x8(D, dst_off + (uint64_t)b * 64u + (uint32_t)(lane & 3) * 16u, y);
+    }
+  }
+}
+// IQ4_XS: lane l handles elements 8l..8l+7 = sub-block j = l>>2, i = 8(l&3)..+8; one super-block per warp iteration.
+KK_DQ_DEV void consume_iq4xs(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
+  const uint32_t j = (uint32_t)(lane >> 2), i0 = 8u * (uint32_t)(lane & 3);
+  const uint32_t q_off = 8u + 16u * j + (i0 & 15u);
+  const uint32_t nsh = (i0 >> 4) * 4u;
+  for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
+    const uint32_t blk = pay + b * KK_IQ4XS_BLOCK_BYTES;
+    const float d = lds_f16(blk);
+    const uint32_t sh = lds16_any(blk + 2u);
+    const uint32_t sl = lds8(blk + 4u + (j >> 1));
+    const uint32_t ls = ((sl >> (4u * (j & 1u))) & 0xFu) | (((sh >> (2u * j)) & 3u) << 4);
+    const float dl = __fmul_rn(d, (float)((int)ls - 32));
+    const uint32_t q0 = (lds32_any(blk + q_off) >> nsh) & 0x0F0F0F0Fu;
+    const uint32_t q1 = (lds32_any(blk + q_off + 4u) >> nsh) & 0x0F0F0F0Fu;
+    float y[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) y[e] = __fmul_rn(dl, lut16<0>(((e < 4 ? q0 : q1) >> (8 * (e & 3))) & 0xFu));
+    store_bf16x8(D, dst_off + (uint64_t)b * 512u + (uint32_t)lane * 16u, y);
   }
 }

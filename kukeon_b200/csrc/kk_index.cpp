@@ -45,7 +45,8 @@ const DtRow kDt[] = {
     {KK_Q8_0, {"Q8_0", 32, 34, true}, 0},      {KK_Q2_K, {"Q2_K", 256, 84, true}, 0},
     {KK_Q3_K, {"Q3_K", 256, 110, true}, 0},    {KK_Q4_K, {"Q4_K", 256, 144, true}, 0},
     {KK_Q5_K, {"Q5_K", 256, 176, true}, 0},    {KK_Q6_K, {"Q6_K", 256, 210, true}, 0},
-    {KK_Q8_K, {"Q8_K", 256, 292, true}, 0},
+    {KK_Q8_K, {"Q8_K", 256, 292, true}, 0},    {KK_IQ4_NL, {"IQ4_NL", 32, 18, true}, 0},
+    {KK_IQ4_XS, {"IQ4_XS", 256, 136, true}, 0}, {KK_MXFP4, {"MXFP4", 32, 17, true}, 0},
 };
 const DtRow* dt_row(uint32_t dt) {
   for (auto& r : kDt)
@@ -70,6 +71,7 @@ int dtype_from_ggml(uint32_t t) {
     case 0: return KK_F32;   case 1: return KK_F16;   case 2: return KK_Q4_0;  case 3: return KK_Q4_1;
     case 6: return KK_Q5_0;  case 7: return KK_Q5_1;  case 8: return KK_Q8_0;  case 10: return KK_Q2_K;
     case 11: return KK_Q3_K; case 12: return KK_Q4_K; case 13: return KK_Q5_K; case 14: return KK_Q6_K;
+    case 20: return KK_IQ4_NL; case 23: return KK_IQ4_XS; case 39: return KK_MXFP4;
     case 15: return KK_Q8_K; case 24: return KK_I8;   case 25: return KK_I16;  case 26: return KK_I32;
     case 27: return KK_I64;  case 28: return KK_F64;  case 30: return KK_BF16;
     default: return -1;

@@ -285,6 +285,7 @@ __device__ __forceinline__ uint32_t kk_f8x2_to_f16x2(uint32_t v) {
   return r;
 }
 __device__ __forceinline__ float kk_bits2f(uint32_t u) { return __uint_as_float(u); }
+__device__ __forceinline__ uint32_t kk_byte_perm(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
 __device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t kk_ldg8(const uint8_t* p) { return (uint32_t)__ldg(p); }
@@ -563,7 +564,10 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
           case KK_OP_Q5_1_BF16:
           case KK_OP_Q2K_BF16:
           case KK_OP_Q3K_BF16:
-          case KK_OP_Q5K_BF16: {  // the other block quants: same tiling, geometry from kk_ops.h
+          case KK_OP_Q5K_BF16:
+          case KK_OP_IQ4NL_BF16:
+          case KK_OP_IQ4XS_BF16:
+          case KK_OP_MXFP4_BF16: {  // the other block quants: same tiling, geometry from kk_ops.h
             const KKBlockTile bt = kk_block_tile(seg, t);
             d.n_units = bt.n_blocks;
             in_bytes = bt.in_bytes; in_off = bt.in_off;
@@ -750,6 +754,9 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
         case KK_OP_Q2K_BF16: consume_q2k(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
         case KK_OP_Q3K_BF16: consume_q3k(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
         case KK_OP_Q5K_BF16: consume_q5k(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
+        case KK_OP_IQ4NL_BF16: consume_codebook32<KK_IQ4NL_BLOCK_BYTES, 0>(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
+        case KK_OP_MXFP4_BF16: consume_codebook32<KK_MXFP4_BLOCK_BYTES, 1>(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
+        case KK_OP_IQ4XS_BF16: consume_iq4xs(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
         case KK_OP_T8_F32_BF16: run_t8<4, 1>(D, L.src, t, sbase, ctid); break;
         case KK_OP_T8_F16_BF16: run_t8<2, 2>(D, L.src, t, sbase, ctid); break;
         case KK_OP_T8_B16: run_t8<2, 0>(D, L.src, t, sbase, ctid); break;

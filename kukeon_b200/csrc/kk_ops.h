@@ -30,6 +30,12 @@
 #define KK_Q3K_TILE_BLOCKS 296u   /* 32560 B in */
 #define KK_Q5K_BLOCK_BYTES 176u
 #define KK_Q5K_TILE_BLOCKS 186u   /* 32736 B in */
+#define KK_IQ4NL_BLOCK_BYTES 18u
+#define KK_IQ4NL_TILE_BLOCKS 1816u /* as Q4_0 */
+#define KK_IQ4XS_BLOCK_BYTES 136u
+#define KK_IQ4XS_TILE_BLOCKS 240u  /* 32640 B in */
+#define KK_MXFP4_BLOCK_BYTES 17u
+#define KK_MXFP4_TILE_BLOCKS 1920u /* 32640 B in */
 #define KK_T_ROWS 32u            /* transpose tile: 32 source rows ... */
 #define KK_T_COLS 128u           /* ... x 128 source columns (elements) */
 #define KK_T_PITCH_PAD 16u       /* TMA-staged transpose rows sit KK_T_COLS*es + 16 bytes apart (bank spread) */
@@ -76,7 +82,11 @@ enum KKOp : uint32_t {
   KK_OP_T8_F32_BF16 = 20,
   KK_OP_T8_F16_BF16 = 21,
   KK_OP_T8_B16 = 22,
-  KK_OP_COUNT = 23
+  // codebook 4-bit types: IQ4_NL (18 B: d f16 | qs[16]), IQ4_XS (136 B: d | scales_h u16 | scales_l[4] | qs[128]), MXFP4 (17 B: E8M0 | qs[16])
+  KK_OP_IQ4NL_BF16 = 23,
+  KK_OP_IQ4XS_BF16 = 24,
+  KK_OP_MXFP4_BF16 = 25,
+  KK_OP_COUNT = 26
 };
 
 struct KKSeg {
@@ -114,6 +124,9 @@ static inline KK_HD KKBlockGeom kk_block_geom(uint32_t op) {
     case KK_OP_Q2K_BF16: return {KK_Q2K_BLOCK_BYTES, 512u, KK_Q2K_TILE_BLOCKS};
     case KK_OP_Q3K_BF16: return {KK_Q3K_BLOCK_BYTES, 512u, KK_Q3K_TILE_BLOCKS};
     case KK_OP_Q5K_BF16: return {KK_Q5K_BLOCK_BYTES, 512u, KK_Q5K_TILE_BLOCKS};
+    case KK_OP_IQ4NL_BF16: return {KK_IQ4NL_BLOCK_BYTES, 64u, KK_IQ4NL_TILE_BLOCKS};
+    case KK_OP_IQ4XS_BF16: return {KK_IQ4XS_BLOCK_BYTES, 512u, KK_IQ4XS_TILE_BLOCKS};
+    case KK_OP_MXFP4_BF16: return {KK_MXFP4_BLOCK_BYTES, 64u, KK_MXFP4_TILE_BLOCKS};
     default: return {0u, 0u, 0u};
   }
 }
@@ -139,7 +152,9 @@ static_assert(KK_TILE_OK(KK_Q4K_BLOCK_BYTES, KK_Q4K_TILE_BLOCKS) && KK_TILE_OK(K
                   KK_TILE_OK(KK_Q6K_BLOCK_BYTES, KK_Q6K_TILE_BLOCKS) && KK_TILE_OK(KK_Q4_0_BLOCK_BYTES, KK_Q4_0_TILE_BLOCKS) &&
                   KK_TILE_OK(KK_Q4_1_BLOCK_BYTES, KK_Q4_1_TILE_BLOCKS) && KK_TILE_OK(KK_Q5_0_BLOCK_BYTES, KK_Q5_0_TILE_BLOCKS) &&
                   KK_TILE_OK(KK_Q5_1_BLOCK_BYTES, KK_Q5_1_TILE_BLOCKS) && KK_TILE_OK(KK_Q2K_BLOCK_BYTES, KK_Q2K_TILE_BLOCKS) &&
-                  KK_TILE_OK(KK_Q3K_BLOCK_BYTES, KK_Q3K_TILE_BLOCKS) && KK_TILE_OK(KK_Q5K_BLOCK_BYTES, KK_Q5K_TILE_BLOCKS),
+                  KK_TILE_OK(KK_Q3K_BLOCK_BYTES, KK_Q3K_TILE_BLOCKS) && KK_TILE_OK(KK_Q5K_BLOCK_BYTES, KK_Q5K_TILE_BLOCKS) &&
+                  KK_TILE_OK(KK_IQ4NL_BLOCK_BYTES, KK_IQ4NL_TILE_BLOCKS) && KK_TILE_OK(KK_IQ4XS_BLOCK_BYTES, KK_IQ4XS_TILE_BLOCKS) &&
+                  KK_TILE_OK(KK_MXFP4_BLOCK_BYTES, KK_MXFP4_TILE_BLOCKS),
               "a full tile of every block op fits one stage and keeps the next tile 16-byte aligned");
 
 // Units one tile covers, and the number of tiles of a segment (host + device).
@@ -160,7 +175,10 @@ static inline KK_HD uint64_t kk_seg_tiles(uint32_t op, uint64_t units, uint32_t 
     case KK_OP_Q5_1_BF16:
     case KK_OP_Q2K_BF16:
     case KK_OP_Q3K_BF16:
-    case KK_OP_Q5K_BF16: {
+    case KK_OP_Q5K_BF16:
+    case KK_OP_IQ4NL_BF16:
+    case KK_OP_IQ4XS_BF16:
+    case KK_OP_MXFP4_BF16: {
       const uint32_t tb = kk_block_geom(op).tile_blocks;
       return (units + tb - 1) / tb;
     }

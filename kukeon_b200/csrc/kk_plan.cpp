@@ -55,6 +55,9 @@ OpInfo op_for(uint32_t dt, uint32_t flags, const std::string& name) {
     case KK_Q4_K: qop = KK_OP_Q4K_BF16; break;
     case KK_Q5_K: qop = KK_OP_Q5K_BF16; break;
     case KK_Q6_K: qop = KK_OP_Q6K_BF16; break;
+    case KK_IQ4_NL: qop = KK_OP_IQ4NL_BF16; break;
+    case KK_IQ4_XS: qop = KK_OP_IQ4XS_BF16; break;
+    case KK_MXFP4: qop = KK_OP_MXFP4_BF16; break;
     default: break;
   }
   if (qop != KK_OP_COUNT) {
@@ -64,7 +67,7 @@ OpInfo op_for(uint32_t dt, uint32_t flags, const std::string& name) {
   const DtypeInfo* di = dtype_info(dt);
   if (!di) fail(KK_EINVAL, "tensor %s: unknown dtype %u", name.c_str(), dt);
   if (di->block_elems > 1 && dt >= 32)
-    fail(KK_EUNSUPPORTED, "tensor %s: %s -> bf16 dequantisation is not implemented (Q4_0, Q4_1, Q5_0, Q5_1, Q8_0, Q2_K, Q3_K, Q4_K, Q5_K and Q6_K are)", name.c_str(), di->name);
+    fail(KK_EUNSUPPORTED, "tensor %s: %s -> bf16 dequantisation is not implemented (Q4_0, Q4_1, Q5_0, Q5_1, Q8_0, Q2_K .. Q6_K, IQ4_NL, IQ4_XS and MXFP4 are)", name.c_str(), di->name);
   return {KK_OP_COPY, dt, 1, 1, KK_TILE_SRC_BYTES};  // integers, bool, fp8, f64, sub-byte: verbatim bytes
 }
 

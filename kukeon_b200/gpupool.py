@@ -30,7 +30,7 @@ DTYPE_NAMES = {
     0: "BOOL", 1: "F4", 2: "F6_E2M3", 3: "F6_E3M2", 4: "U8", 5: "I8", 6: "F8_E5M2", 7: "F8_E4M3", 8: "F8_E8M0",
     9: "I16", 10: "U16", 11: "F16", 12: "BF16", 13: "I32", 14: "U32", 15: "F32", 16: "C64", 17: "F64", 18: "I64",
     19: "U64", 32: "Q4_0", 33: "Q4_1", 34: "Q5_0", 35: "Q5_1", 36: "Q8_0", 37: "Q2_K", 38: "Q3_K", 39: "Q4_K",
-    40: "Q5_K", 41: "Q6_K", 42: "Q8_K",
+    40: "Q5_K", 41: "Q6_K", 42: "Q8_K", 43: "IQ4_NL", 44: "IQ4_XS", 45: "MXFP4",
 }
 
 

@@ -17,7 +17,8 @@ OP_F8E4M3_BF16, OP_F8E5M2_BF16 = 6, 7
 OP_DEQUANT = 0x100  # | ggml type id
 # file dtype -> (ggml type id, weights per block, bytes per block)   (gguf/constants.py GGML_QUANT_SIZES)
 GGML_BLOCK = {"Q4_0": (2, 32, 18), "Q4_1": (3, 32, 20), "Q5_0": (6, 32, 22), "Q5_1": (7, 32, 24), "Q8_0": (8, 32, 34),
-              "Q2_K": (10, 256, 84), "Q3_K": (11, 256, 110), "Q4_K": (12, 256, 144), "Q5_K": (13, 256, 176), "Q6_K": (14, 256, 210)}
+              "Q2_K": (10, 256, 84), "Q3_K": (11, 256, 110), "Q4_K": (12, 256, 144), "Q5_K": (13, 256, 176), "Q6_K": (14, 256, 210),
+              "IQ4_NL": (20, 32, 18), "IQ4_XS": (23, 256, 136), "MXFP4": (39, 32, 17)}
 
 
 class OrcJob(C.Structure):

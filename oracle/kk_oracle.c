@@ -232,6 +232,34 @@ static void q5k_block(const uint8_t* b, uint16_t* out) {
   }
 }
 
+/* IQ4_NL (18 B): Q4_0's layout with a 16-entry codebook; IQ4_XS (136 B): d f16 | scales_h u16 | scales_l[4] | qs[128], eight
+ * 32-weight sub-blocks with 6-bit scales; MXFP4 (17 B): E8M0 scale byte | qs[16] (gguf/quants.py:1330-1380, 656-708). */
+static const int8_t kIQ4NL[16] = {-127, -104, -83, -65, -49, -35, -22, -10, 1, 13, 25, 38, 53, 69, 89, 113};
+static const int8_t kMXFP4[16] = {0, 1, 2, 3, 4, 6, 8, 12, 0, -1, -2, -3, -4, -6, -8, -12};
+static void iq4nl_block(const uint8_t* b, uint16_t* out) {
+  const float d = ld_f16(b);
+  for (int e = 0; e < 32; ++e) out[e] = f32_to_bf16(d * (float)kIQ4NL[legacy_nibble(b + 2, e)]);
+}
+static void iq4xs_block(const uint8_t* b, uint16_t* out) {
+  const float d = ld_f16(b);
+  uint16_t sh;
+  memcpy(&sh, b + 2, 2);
+  const uint8_t* sl = b + 4;
+  const uint8_t* qs = b + 8;
+  for (int j = 0; j < 8; ++j) {
+    const int ls = ((sl[j >> 1] >> (4 * (j & 1))) & 0x0F) | (((sh >> (2 * j)) & 3) << 4);
+    volatile float dl = d * (float)(ls - 32);
+    for (int i = 0; i < 32; ++i) out[32 * j + i] = f32_to_bf16(dl * (float)kIQ4NL[legacy_nibble(qs + 16 * j, i)]);
+  }
+}
+static void mxfp4_block(const uint8_t* b, uint16_t* out) {
+  const uint32_t e = b[0];
+  const uint32_t bits = e < 2 ? (0x00200000u << e) : ((e - 1u) << 23); /* half the E8M0 scale */
+  float d;
+  memcpy(&d, &bits, 4);
+  for (int i = 0; i < 32; ++i) out[i] = f32_to_bf16(d * (float)kMXFP4[legacy_nibble(b + 1, i)]);
+}
+
 /* Dispatch by ggml type id (gguf/constants.py GGMLQuantizationType): block bytes / weights per block / function. */
 typedef void (*orc_block_fn)(const uint8_t*, uint16_t*);
 static orc_block_fn block_fn(uint32_t ggml_type, uint32_t* bytes, uint32_t* elems) {
@@ -246,6 +274,9 @@ static orc_block_fn block_fn(uint32_t ggml_type, uint32_t* bytes, uint32_t* elem
     case 12: *bytes = 144; *elems = 256; return q4k_block;
     case 13: *bytes = 176; *elems = 256; return q5k_block;
     case 14: *bytes = 210; *elems = 256; return q6k_block;
+    case 20: *bytes = 18; *elems = 32; return iq4nl_block;
+    case 23: *bytes = 136; *elems = 256; return iq4xs_block;
+    case 39: *bytes = 17; *elems = 32; return mxfp4_block;
     default: return 0;
   }
 }

@@ -41,6 +41,7 @@ GGML_TYPES = {
     0: ("F32", 1, 4), 1: ("F16", 1, 2), 2: ("Q4_0", 32, 18), 3: ("Q4_1", 32, 20), 6: ("Q5_0", 32, 22),
     7: ("Q5_1", 32, 24), 8: ("Q8_0", 32, 34), 10: ("Q2_K", 256, 84), 11: ("Q3_K", 256, 110),
     12: ("Q4_K", 256, 144), 13: ("Q5_K", 256, 176), 14: ("Q6_K", 256, 210), 15: ("Q8_K", 256, 292),
+    20: ("IQ4_NL", 32, 18), 23: ("IQ4_XS", 256, 136), 39: ("MXFP4", 32, 17),
     24: ("I8", 1, 1), 25: ("I16", 1, 2), 26: ("I32", 1, 4), 27: ("I64", 1, 8), 28: ("F64", 1, 8),
     30: ("BF16", 1, 2),
 }
@@ -508,12 +509,60 @@ def dequant_q5k_f32(blocks: np.ndarray) -> np.ndarray:
     return y.reshape(n, 256)
 
 
+IQ4NL_VALUES = np.array([-127, -104, -83, -65, -49, -35, -22, -10, 1, 13, 25, 38, 53, 69, 89, 113], np.int8)  # gguf/quants.py:1331
+MXFP4_VALUES = np.array([0, 1, 2, 3, 4, 6, 8, 12, 0, -1, -2, -3, -4, -6, -8, -12], np.int8)  # e2m1 values, doubled (gguf/quants.py:659)
+
+
+def dequant_iq4nl_f32(blocks: np.ndarray) -> np.ndarray:
+    """[n,18] (d f16 | qs[16]) -> [n,32]: Q4_0's layout with a non-linear codebook, y = d * IQ4NL_VALUES[q4] (gguf/quants.py:1330-1348)."""
+    b = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, 18)
+    kv = IQ4NL_VALUES[_nibbles_lo_then_hi(b[:, 2:18])].astype(np.float32)
+    with np.errstate(all="ignore"):
+        return (_f16(b[:, 0:2]) * kv).astype(np.float32)
+
+
+def dequant_iq4xs_f32(blocks: np.ndarray) -> np.ndarray:
+    """[n,136] (d f16 | scales_h u16 | scales_l[4] | qs[128]) -> [n,256].  Sub-block j (32 weights): 6-bit scale
+    ls = ((scales_l[j//2] >> 4*(j%2)) & 15) | (((scales_h >> 2j) & 3) << 4), dl = d * (ls - 32); its elements i < 16 are the low
+    nibbles of qs[16j + i], i >= 16 the high nibbles of qs[16j + i - 16]; y = dl * IQ4NL_VALUES[q4] (gguf/quants.py:1351-1380)."""
+    b = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, 136)
+    n = b.shape[0]
+    d = _f16(b[:, 0:2])
+    sh = np.ascontiguousarray(b[:, 2:4]).view("<u2").reshape(n).astype(np.uint32)
+    sl, qs = b[:, 4:8], b[:, 8:136]
+    ls = np.empty((n, 8), np.uint8)
+    q = np.empty((n, 8, 32), np.uint8)
+    for j in range(8):
+        ls[:, j] = ((sl[:, j // 2] >> (4 * (j % 2))) & 0x0F) | ((((sh >> (2 * j)) & 3) << 4).astype(np.uint8))
+        q[:, j, :] = _nibbles_lo_then_hi(qs[:, 16 * j: 16 * j + 16])
+    with np.errstate(all="ignore"):
+        dl = (d * (ls.astype(np.int8) - np.int8(32)).astype(np.float32)).astype(np.float32)
+        y = (dl[:, :, None] * IQ4NL_VALUES[q].astype(np.float32)).astype(np.float32)
+    return y.reshape(n, 256)
+
+
+def e8m0_to_f32_half(e: np.ndarray) -> np.ndarray:
+    """E8M0 scale byte -> HALF the power of two it encodes, as fp32 (the codebook holds doubled e2m1 values):
+    2^(e-128) — a subnormal for e < 2 (bits 0x00200000 << e), else exponent field e - 1 (ggml-impl.h ggml_e8m0_to_fp32_half)."""
+    e = e.astype(np.uint32)
+    return np.where(e < 2, np.uint32(0x00200000) << e, (e - np.uint32(1)) << np.uint32(23)).astype(np.uint32).view(np.float32)
+
+
+def dequant_mxfp4_f32(blocks: np.ndarray) -> np.ndarray:
+    """[n,17] (e u8 (E8M0) | qs[16]) -> [n,32]: y = e8m0_half(e) * MXFP4_VALUES[q4]; nibble order as in Q4_0 (gguf/quants.py:656-708)."""
+    b = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, 17)
+    kv = MXFP4_VALUES[_nibbles_lo_then_hi(b[:, 1:17])].astype(np.float32)
+    with np.errstate(all="ignore"):
+        return (e8m0_to_f32_half(b[:, 0:1]) * kv).astype(np.float32)
+
+
 # file dtype -> (weights per block, bytes per block, fp32 dequantiser).  Everything the product dequantises to bf16.
 BLOCK_QUANTS = {
     "Q4_0": (32, 18, dequant_q4_0_f32), "Q4_1": (32, 20, dequant_q4_1_f32), "Q5_0": (32, 22, dequant_q5_0_f32),
     "Q5_1": (32, 24, dequant_q5_1_f32), "Q8_0": (32, 34, dequant_q8_0_f32), "Q2_K": (256, 84, dequant_q2k_f32),
     "Q3_K": (256, 110, dequant_q3k_f32), "Q4_K": (256, 144, dequant_q4k_f32), "Q5_K": (256, 176, dequant_q5k_f32),
-    "Q6_K": (256, 210, dequant_q6k_f32),
+    "Q6_K": (256, 210, dequant_q6k_f32), "IQ4_NL": (32, 18, dequant_iq4nl_f32), "IQ4_XS": (256, 136, dequant_iq4xs_f32),
+    "MXFP4": (32, 17, dequant_mxfp4_f32),
 }
 
 
@@ -584,7 +633,7 @@ def slice_dim(rec: dict, n_parts: int):
         return None
     if rec["dtype"] in ("F4", "F6_E2M3", "F6_E3M2"):
         return None
-    if rec["dtype"].startswith("Q") and dim == 1:
+    if rec["dtype"] in BLOCK_QUANTS and dim == 1:
         return None
     return dim
 
@@ -609,7 +658,7 @@ def plan_pool(recs: List[dict], mode: int = MODE_SINGLE, flags: int = 0, n_parts
         nel = 1
         for s in shape:
             nel *= s
-        if r["dtype"].startswith("Q"):
+        if r["dtype"] in BLOCK_QUANTS:
             nbytes = nel * 2
         elif pdt in _ELEM_BYTES:
             nbytes = nel * _ELEM_BYTES[pdt]
@@ -635,7 +684,7 @@ def convert_tensor(rec: dict, raw: bytes, flags: int = 0) -> np.ndarray:
         return f8e5m2_bits_to_bf16(a).view(np.uint8)
     if dt in BLOCK_QUANTS:
         return dequant_bf16(dt, a).reshape(-1).view(np.uint8)
-    if dt.startswith("Q"):
+    if dt in ("Q8_K", "Q8_1"):
         raise OracleError(f"{dt} dequantisation not defined by this oracle")
     return a.copy()
 

@@ -57,6 +57,13 @@ inline void sts32(uint32_t a, uint32_t v) {
   memcpy(g.wtile + a, &v, 4);
 }
 inline uint32_t kk_ldg8(const uint8_t* p) { return *p; }
+// PRMT (default mode) as the code under test uses it: selector nibble 0 picks byte (sel & 7) of {b:a}; the msb-replicate bit is never set
+inline uint32_t kk_byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
+  const uint64_t v = ((uint64_t)b << 32) | a;
+  uint32_t r = 0;
+  for (int k = 0; k < 4; ++k) r |= (uint32_t)((v >> (8 * ((sel >> (4 * k)) & 7u))) & 0xFFu) << (8 * k);
+  return r;
+}
 inline float kk_bits2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 inline float kk_h2f(uint32_t h) {
   uint16_t b = (uint16_t)h;
@@ -118,6 +125,28 @@ constexpr int kConsumerWarps = 16;  // must equal KK_CONSUMER_WARPS of the kerne
 #include "../../kukeon_b200/csrc/kk_dequant.cuh"
 #undef min
 
+// One lane of the consumer side of a block / elementwise op — the same switch the kernel has.  false: op not covered here.
+inline bool run_op(uint32_t op, const Dsts& D, uint32_t pay, uint32_t n, uint64_t dst_off, int cwarp, int lane) {
+  switch (op) {
+    case KK_OP_Q8_0_BF16: consume_q8_0(D, pay, n, dst_off, cwarp, lane); return true;
+    case KK_OP_Q6K_BF16: consume_q6k(D, pay, n, dst_off, cwarp, lane); return true;
+    case KK_OP_Q4_0_BF16: consume_legacy32<KK_Q4_0_BLOCK_BYTES, false, false>(D, pay, n, dst_off, cwarp, lane); return true;
+    case KK_OP_Q4_1_BF16: consume_legacy32<KK_Q4_1_BLOCK_BYTES, true, false>(D, pay, n, dst_off, cwarp, lane); return true;
+    case KK_OP_Q5_0_BF16: consume_legacy32<KK_Q5_0_BLOCK_BYTES, false, true>(D, pay, n, dst_off, cwarp, lane); return true;
+    case KK_OP_Q5_1_BF16: consume_legacy32<KK_Q5_1_BLOCK_BYTES, true, true>(D, pay, n, dst_off, cwarp, lane); return true;
+    case KK_OP_Q2K_BF16: consume_q2k(D, pay, n, dst_off, cwarp, lane); return true;
+    case KK_OP_Q3K_BF16: consume_q3k(D, pay, n, dst_off, cwarp, lane); return true;
+    case KK_OP_Q5K_BF16: consume_q5k(D, pay, n, dst_off, cwarp, lane); return true;
+    case KK_OP_IQ4NL_BF16: consume_codebook32<KK_IQ4NL_BLOCK_BYTES, 0>(D, pay, n, dst_off, cwarp, lane); return true;
+    case KK_OP_MXFP4_BF16: consume_codebook32<KK_MXFP4_BLOCK_BYTES, 1>(D, pay, n, dst_off, cwarp, lane); return true;
+    case KK_OP_IQ4XS_BF16: consume_iq4xs(D, pay, n, dst_off, cwarp, lane); return true;
+    // elementwise ops: n = elements of the tile, threads indexed 0..511 across the consumer warps
+    case KK_OP_F8E4M3_BF16: consume_f8<false>(D, pay, n, dst_off, cwarp * 32 + lane); return true;
+    case KK_OP_F8E5M2_BF16: consume_f8<true>(D, pay, n, dst_off, cwarp * 32 + lane); return true;
+    default: return false;
+  }
+}
+
 }  // namespace
 
 // Run the consumer side of one tile of block op `op` (KKOp): `nblk` blocks whose first byte sits at tile[pay_off].
@@ -132,23 +161,8 @@ extern "C" int kk_emul_dequant_tile(uint32_t op, const uint8_t* tile, uint32_t t
   g.out_mask = mask.data();
   const Dsts D{0};
   for (int cwarp = 0; cwarp < kConsumerWarps; ++cwarp)
-    for (int lane = 0; lane < 32; ++lane) {
-      switch (op) {
-        // elementwise ops: nblk = elements of the tile, threads indexed 0..511 across the consumer warps
-        case KK_OP_F8E4M3_BF16: consume_f8<false>(D, pay_off, nblk, 0, cwarp * 32 + lane); break;
-        case KK_OP_F8E5M2_BF16: consume_f8<true>(D, pay_off, nblk, 0, cwarp * 32 + lane); break;
-        case KK_OP_Q8_0_BF16: consume_q8_0(D, pay_off, nblk, 0, cwarp, lane); break;
-        case KK_OP_Q6K_BF16: consume_q6k(D, pay_off, nblk, 0, cwarp, lane); break;
-        case KK_OP_Q4_0_BF16: consume_legacy32<KK_Q4_0_BLOCK_BYTES, false, false>(D, pay_off, nblk, 0, cwarp, lane); break;
-        case KK_OP_Q4_1_BF16: consume_legacy32<KK_Q4_1_BLOCK_BYTES, true, false>(D, pay_off, nblk, 0, cwarp, lane); break;
-        case KK_OP_Q5_0_BF16: consume_legacy32<KK_Q5_0_BLOCK_BYTES, false, true>(D, pay_off, nblk, 0, cwarp, lane); break;
-        case KK_OP_Q5_1_BF16: consume_legacy32<KK_Q5_1_BLOCK_BYTES, true, true>(D, pay_off, nblk, 0, cwarp, lane); break;
-        case KK_OP_Q2K_BF16: consume_q2k(D, pay_off, nblk, 0, cwarp, lane); break;
-        case KK_OP_Q3K_BF16: consume_q3k(D, pay_off, nblk, 0, cwarp, lane); break;
-        case KK_OP_Q5K_BF16: consume_q5k(D, pay_off, nblk, 0, cwarp, lane); break;
-        default: return -1;
-      }
-    }
+    for (int lane = 0; lane < 32; ++lane)
+      if (!run_op(op, D, pay_off, nblk, 0, cwarp, lane)) return -1;
   return g.err;
 }
 
@@ -181,20 +195,8 @@ extern "C" int kk_emul_dequant_segment(uint32_t op, const uint8_t* src, uint64_t
     g.out_mask = mask.data();
     const Dsts D{0};
     for (int cwarp = 0; cwarp < kConsumerWarps; ++cwarp)
-      for (int lane = 0; lane < 32; ++lane) {
-        switch (op) {
-          case KK_OP_Q8_0_BF16: consume_q8_0(D, mis, bt.n_blocks, bt.dst_off, cwarp, lane); break;
-          case KK_OP_Q6K_BF16: consume_q6k(D, mis, bt.n_blocks, bt.dst_off, cwarp, lane); break;
-          case KK_OP_Q4_0_BF16: consume_legacy32<KK_Q4_0_BLOCK_BYTES, false, false>(D, mis, bt.n_blocks, bt.dst_off, cwarp, lane); break;
-          case KK_OP_Q4_1_BF16: consume_legacy32<KK_Q4_1_BLOCK_BYTES, true, false>(D, mis, bt.n_blocks, bt.dst_off, cwarp, lane); break;
-          case KK_OP_Q5_0_BF16: consume_legacy32<KK_Q5_0_BLOCK_BYTES, false, true>(D, mis, bt.n_blocks, bt.dst_off, cwarp, lane); break;
-          case KK_OP_Q5_1_BF16: consume_legacy32<KK_Q5_1_BLOCK_BYTES, true, true>(D, mis, bt.n_blocks, bt.dst_off, cwarp, lane); break;
-          case KK_OP_Q2K_BF16: consume_q2k(D, mis, bt.n_blocks, bt.dst_off, cwarp, lane); break;
-          case KK_OP_Q3K_BF16: consume_q3k(D, mis, bt.n_blocks, bt.dst_off, cwarp, lane); break;
-          case KK_OP_Q5K_BF16: consume_q5k(D, mis, bt.n_blocks, bt.dst_off, cwarp, lane); break;
-          default: return -1;
-        }
-      }
+      for (int lane = 0; lane < 32; ++lane)
+        if (!run_op(op, D, mis, bt.n_blocks, bt.dst_off, cwarp, lane)) return -1;
     if (g.err) return g.err;
   }
   return 0;

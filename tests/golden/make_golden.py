@@ -166,6 +166,42 @@ def make_gguf_legacy_and_k_quants():
     np.savez_compressed(p + ".bf16.npz", **outs)
 
 
+def make_gguf_codebook_quants():
+    """IQ4_NL, IQ4_XS and MXFP4 (the 4-bit codebook types) written by gguf-py's GGUFWriter; expected values from quants.dequantize."""
+    import gguf
+    from gguf import GGMLQuantizationType as Q
+    rng = np.random.Generator(np.random.Philox(key=80))
+
+    def blocks(nblk, bsz, d_off=None, e8m0_off=None):
+        b = rng.integers(0, 256, size=(nblk, bsz), dtype=np.uint8)
+        if d_off is not None:
+            e = rng.integers(5, 12, size=nblk, dtype=np.uint16)
+            m = rng.integers(0, 1024, size=nblk, dtype=np.uint16)
+            sgn = rng.integers(0, 2, size=nblk, dtype=np.uint16) << 15
+            b[:, d_off:d_off + 2] = ((e << 10) | m | sgn).astype("<u2").view(np.uint8).reshape(nblk, 2)
+        if e8m0_off is not None:
+            b[:, e8m0_off] = rng.integers(100, 140, size=nblk, dtype=np.uint8)
+            b[0, e8m0_off], b[1 % nblk, e8m0_off] = 0, 1  # the two subnormal encodings of the shared exponent
+        return b
+
+    p = os.path.join(HERE, "quants_cb.gguf")
+    w = gguf.GGUFWriter(p, "llama")
+    w.add_tensor("blk.0.attn_q.weight", blocks(3 * 3, 18, d_off=0).reshape(3, 3 * 18), raw_dtype=Q.IQ4_NL)   # [3, 96]
+    w.add_tensor("blk.0.ffn_up.weight", blocks(2 * 2, 136, d_off=0).reshape(2, 2 * 136), raw_dtype=Q.IQ4_XS)  # [2, 512]
+    w.add_tensor("blk.0.ffn_gate.weight", blocks(5 * 3, 17, e8m0_off=0).reshape(5, 3 * 17), raw_dtype=Q.MXFP4)  # [5, 96]
+    w.add_tensor("blk.0.attn_norm.weight", rng.standard_normal(12).astype(np.float32))
+    w.write_header_to_file(); w.write_kv_data_to_file(); w.write_tensors_to_file(); w.close()
+    r = gguf.GGUFReader(p)
+    exp, outs = [], {}
+    for t in r.tensors:
+        shape = [int(x) for x in reversed(t.shape.tolist())]
+        exp.append(dict(name=t.name, dtype=t.tensor_type.name, shape=shape, file_offset=int(t.data_offset), nbytes=int(t.n_bytes)))
+        f32 = gguf.quants.dequantize(np.array(t.data), t.tensor_type)
+        outs[t.name] = bits16(torch.from_numpy(np.ascontiguousarray(f32, dtype=np.float32)).to(torch.bfloat16)).reshape(-1)
+    json.dump(dict(tensors=exp, alignment=int(r.alignment), data_offset=int(r.data_offset)), open(p + ".expected.json", "w"), indent=1)
+    np.savez_compressed(p + ".bf16.npz", **outs)
+
+
 def make_sharded():
     from huggingface_hub import save_torch_state_dict
     d = os.path.join(HERE, "sharded")
@@ -196,7 +232,7 @@ def make_cast_vectors():
 
 
 if __name__ == "__main__":
-    make_safetensors(); make_gguf(); make_gguf_mixed_quants(); make_gguf_legacy_and_k_quants(); make_sharded(); make_cast_vectors()
+    make_safetensors(); make_gguf(); make_gguf_mixed_quants(); make_gguf_legacy_and_k_quants(); make_gguf_codebook_quants(); make_sharded(); make_cast_vectors()
     for r, _, fs in os.walk(HERE):
         for f in sorted(fs):
             p = os.path.join(r, f)

@@ -17,7 +17,8 @@ from tools import synth
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 OPS = {"Q8_0": helpers.OP_Q8_0, "Q6_K": helpers.OP_Q6K, "Q4_0": helpers.OP_Q4_0, "Q4_1": helpers.OP_Q4_1, "Q5_0": helpers.OP_Q5_0,
-       "Q5_1": helpers.OP_Q5_1, "Q2_K": helpers.OP_Q2K, "Q3_K": helpers.OP_Q3K, "Q5_K": helpers.OP_Q5K}
+       "Q5_1": helpers.OP_Q5_1, "Q2_K": helpers.OP_Q2K, "Q3_K": helpers.OP_Q3K, "Q5_K": helpers.OP_Q5K, "IQ4_NL": helpers.OP_IQ4NL,
+       "IQ4_XS": helpers.OP_IQ4XS, "MXFP4": helpers.OP_MXFP4}
 ERR = {1: "shared-memory load outside the staged tile", 2: "misaligned 16/32-bit shared-memory load", 3: "store outside the output window or not 16-byte aligned",
        4: "two lanes stored the same 16 bytes"}
 

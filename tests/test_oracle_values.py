@@ -145,7 +145,10 @@ def test_mixed_quant_golden_file_vs_gguf_py():
 F4_TYPES = ["Q4_0", "Q4_1", "Q5_0", "Q5_1", "Q2_K", "Q3_K", "Q5_K"]
 
 
-@pytest.mark.parametrize("dtype", F4_TYPES + ["Q4_K", "Q6_K", "Q8_0"])
+CB_TYPES = ["IQ4_NL", "IQ4_XS", "MXFP4"]
+
+
+@pytest.mark.parametrize("dtype", F4_TYPES + CB_TYPES + ["Q4_K", "Q6_K", "Q8_0"])
 def test_every_block_quant_vs_gguf_py_live_bit_exact(coracle, dtype):
     """§8(f4): numpy restatement and C twin against gguf.quants.dequantize on (a) fully random bytes — Inf/NaN scales
     included, compared as fp32 bit patterns with NaN == NaN — and (b) finite-scale synthetic blocks after RNE to bf16."""
@@ -166,7 +169,7 @@ def test_every_block_quant_vs_gguf_py_live_bit_exact(coracle, dtype):
         for h in (0x3C00, 0x7BFF, 0xBC00):
             e = np.full((2, nb), fill, np.uint8)
             for off in {"Q4_0": [0], "Q4_1": [0, 2], "Q5_0": [0], "Q5_1": [0, 2], "Q2_K": [80, 82], "Q3_K": [108], "Q5_K": [0, 2], "Q4_K": [0, 2],
-                        "Q6_K": [208], "Q8_0": [0]}[dtype]:
+                        "Q6_K": [208], "Q8_0": [0], "IQ4_NL": [0], "IQ4_XS": [0], "MXFP4": []}[dtype]:
                 e[:, off:off + 2] = np.array([h], "<u2").view(np.uint8)
             with np.errstate(all="ignore"):
                 ref = bits16(torch.from_numpy(quants.dequantize(e, qt)).to(torch.bfloat16))
@@ -175,9 +178,22 @@ def test_every_block_quant_vs_gguf_py_live_bit_exact(coracle, dtype):
             assert ((got == ref) | (nan & (got == 0x7FFF))).all() and (got == cgot).all()
 
 
-def test_legacy_and_k_quant_golden_file_vs_gguf_py():
+def test_mxfp4_every_shared_exponent_vs_gguf_py(coracle):
+    """All 256 E8M0 bytes (0 and 1 are fp32 subnormals, 255 = 2^127) x all 16 code points."""
+    from gguf import GGMLQuantizationType, quants
+    b = np.zeros((256, 17), np.uint8)
+    b[:, 0] = np.arange(256)
+    b[:, 1:9] = (np.arange(8, dtype=np.uint8) * 2) | ((np.arange(8, dtype=np.uint8) * 2 + 1) << 4)  # nibbles 0..15 in the low/high halves
+    b[:, 9:17] = b[:, 1:9][:, ::-1]
+    with np.errstate(all="ignore"):
+        ref = bits16(torch.from_numpy(quants.dequantize(b, GGMLQuantizationType.MXFP4)).to(torch.bfloat16))
+    assert (oracle.dequant_bf16("MXFP4", b) == ref).all() and (coracle.dequant_to_bf16("MXFP4", b) == ref).all()
+
+
+@pytest.mark.parametrize("fixture,types", [("quants_f4.gguf", F4_TYPES), ("quants_cb.gguf", CB_TYPES)])
+def test_legacy_k_and_codebook_quant_golden_files_vs_gguf_py(fixture, types):
     import json
-    p = os.path.join(G, "quants_f4.gguf")
+    p = os.path.join(G, fixture)
     exp = json.load(open(p + ".expected.json"))
     outs = np.load(p + ".bf16.npz")
     raw = open(p, "rb").read()
@@ -190,7 +206,7 @@ def test_legacy_and_k_quant_golden_file_vs_gguf_py():
         got = oracle.convert_tensor(rec, raw[t["file_offset"]:t["file_offset"] + t["nbytes"]]).view(np.uint16)
         assert (got == outs[t["name"]]).all(), t["name"]
         seen.add(t["dtype"])
-    assert set(F4_TYPES) <= seen
+    assert set(types) <= seen
 
 
 def test_fp8_widening_vs_torch_every_bit_pattern(coracle):

@@ -1,5 +1,6 @@
-"""GPU parity for the §8(f4) quant types (Q4_0, Q4_1, Q5_0, Q5_1, Q2_K, Q3_K, Q5_K), through the C ABI, bit for bit
-against the oracle and against the committed gguf-py fixture.
+"""GPU parity for the §8(f4) quant types (Q4_0, Q4_1, Q5_0, Q5_1, Q2_K, Q3_K, Q5_K, IQ4_NL, IQ4_XS, MXFP4, FP8 widening) and for the
+other paths written after round 1's GPU budget was spent (8-row transpose tiles, KK_FANOUT_PULL), through the C ABI, bit for bit
+against the oracle and against the committed gguf-py fixtures.
 
 STATUS: these kernels were written after round 1's GPU budget was spent.  Their lane/index arithmetic is verified on the CPU
 tier by tests/test_dequant_emul.py (the same device source compiled for the host); this file is their first run on
@@ -21,8 +22,9 @@ G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 MB = 1 << 20
 
 
-def test_golden_fixture_values_vs_gguf_py(pool):
-    g = os.path.join(G, "quants_f4.gguf")
+@pytest.mark.parametrize("fixture", ["quants_f4.gguf", "quants_cb.gguf"])
+def test_golden_fixture_values_vs_gguf_py(pool, fixture):
+    g = os.path.join(G, fixture)
     load_and_check(pool, g)
     outs = np.load(g + ".bf16.npz")
     m = pool.load(g)
@@ -48,7 +50,7 @@ def test_llama_shaped_mix_of_every_type(pool, tmp_path):
     p = str(tmp_path / "f4.gguf")
     synth.write_gguf(p, f4_tensors(hidden=512, ffn=1536, layers=2, vocab=1024), 11)
     st = load_and_check(pool, p)
-    assert st["n_tensors"] == 2 * 8 + 3
+    assert st["n_tensors"] == 2 * 11 + 3
 
 
 def a8_file(path):

@@ -15,7 +15,8 @@
 #endif
 
 enum { K_BYTES = 0, K_BF16 = 1, K_F16 = 2, K_F32 = 3, K_Q4K = 4, K_Q8_0 = 5, K_Q6K = 6,
-       K_Q4_0 = 7, K_Q4_1 = 8, K_Q5_0 = 9, K_Q5_1 = 10, K_Q2K = 11, K_Q3K = 12, K_Q5K = 13 };
+       K_Q4_0 = 7, K_Q4_1 = 8, K_Q5_0 = 9, K_Q5_1 = 10, K_Q2K = 11, K_Q3K = 12, K_Q5K = 13,
+       K_IQ4NL = 14, K_IQ4XS = 15, K_MXFP4 = 16 };
 
 static inline uint64_t mix64(uint64_t x) {
   x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
@@ -81,6 +82,9 @@ static blk_geom geom_of(int kind) {
     case K_Q2K: return (blk_geom){84, 80, 82};
     case K_Q3K: return (blk_geom){110, 108, -1};
     case K_Q5K: return (blk_geom){176, 0, 2};
+    case K_IQ4NL: return (blk_geom){18, 0, -1};
+    case K_IQ4XS: return (blk_geom){136, 0, -1};
+    case K_MXFP4: return (blk_geom){17, -1, -1}; /* no fp16 scale: byte 0 is an E8M0 exponent, fixed up below */
     default: return (blk_geom){0, 0, -1};
   }
 }
@@ -95,6 +99,10 @@ static void fix_blocks(uint8_t* buf, uint64_t first_block, uint64_t nblocks, int
   else {
     const blk_geom g = geom_of(kind);
     if (!g.bsz) return;
+    if (kind == K_MXFP4) { /* keep the shared exponent in 2^-20 .. 2^+9 so that every product is a finite, normal fp32 */
+      for (uint64_t b = 0; b < nblocks; ++b) buf[g.bsz * b] = (uint8_t)(108 + rnd(seed ^ 0xE8E8ull, idx, first_block + b) % 30);
+      return;
+    }
     fix_scale(buf, first_block, nblocks, g.bsz, (uint64_t)g.d_off, seed, idx);
     if (g.m_off >= 0) fix_scale(buf, first_block, nblocks, g.bsz, (uint64_t)g.m_off, seed ^ 0x3117ull, idx);
   }
