@@ -2,10 +2,10 @@
 other paths written after round 1's GPU budget was spent (8-row transpose tiles, KK_FANOUT_PULL), through the C ABI, bit for bit
 against the oracle and against the committed gguf-py fixtures.
 
-STATUS: these kernels were written after round 1's GPU budget was spent.  Their lane/index arithmetic is verified on the CPU
-tier by tests/test_dequant_emul.py (the same device source compiled for the host); this file is their first run on
-hardware.  It sorts after every other GPU test file on purpose, so a surprise here cannot mask the verified suite under
-`pytest -x`."""
+STATUS: these kernels were written after round 1's profiling budget was spent, against the host emulation of their device source
+(tests/test_dequant_emul.py).  The round's last GPU seconds ran tools/gpu_quick.py (all PASS) and the first 18 cases of this file
+(all passed; profiles/r01/late_hw_check.log, late_zz_pytest.log).  The file sorts after every other GPU test file on purpose, so a
+surprise in the cases that have not run yet cannot mask the long-verified suite under `pytest -x`."""
 import os
 
 import numpy as np
