@@ -25,10 +25,10 @@
 // Lane mapping, same for every type: a lane produces 8 consecutive weights = one 16-byte bf16 store; a warp iteration
 // produces 512 contiguous output bytes (256-weight super-blocks: one block; 32-weight blocks: eight blocks).
 #pragma once
+#include "kk_consume_core.cuh"  // lds32_bytes, to_bf16
 #include "kk_ops.h"
 
 // ---- loads of any alignment (blocks of 18..210 bytes are only 2-byte aligned inside a tile, or not at all) -----------
-KK_DQ_DEV uint32_t lds32_bytes(uint32_t a) { return lds8(a) | (lds8(a + 1) << 8) | (lds8(a + 2) << 16) | (lds8(a + 3) << 24); }
 KK_DQ_DEV uint32_t lds32_h(uint32_t a) {  // a is 2-byte aligned (falls back to bytes otherwise)
   if (a & 1u) return lds32_bytes(a);
   return lds16(a) | (lds16(a + 2) << 16);

@@ -127,7 +127,6 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
 }
-__device__ __forceinline__ uint16_t to_bf16(float a) { return (uint16_t)(pack_bf16x2(a, 0.f) & 0xFFFFu); }
 
 struct Dsts {
   uint8_t* p[KK_MAX_DST];
@@ -176,94 +175,9 @@ __device__ __forceinline__ void store4_all(const Dsts& D, uint64_t off, uint32_t
     if (d < (int)D.n) *reinterpret_cast<uint32_t*>(D.p[d] + off) = v;
 }
 
-// ---- consumer bodies --------------------------------------------------------------------------
-// ctid: 0..255 within the consumer warps.
-
-__device__ __forceinline__ void consume_copy(const Dsts& D, uint32_t pay, uint32_t n, uint64_t dst_off, int ctid) {
-  const uint32_t nvec = n >> 4;
-  if ((pay & 15u) == 0) {
-    for (uint32_t i = ctid; i < nvec; i += kConsumerThreads) store16_all(D, dst_off + ((uint64_t)i << 4), lds128(pay + (i << 4)));
-  } else {
-    for (uint32_t i = ctid; i < nvec; i += kConsumerThreads) {
-      uint32_t w[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        uint32_t a = pay + (i << 4) + 4 * k;
-        w[k] = lds8(a) | (lds8(a + 1) << 8) | (lds8(a + 2) << 16) | (lds8(a + 3) << 24);
-      }
-      store16_all(D, dst_off + ((uint64_t)i << 4), make_uint4(w[0], w[1], w[2], w[3]));
-    }
-  }
-  const uint32_t tail = n & 15u;
-  if (ctid < (int)tail) store1_all(D, dst_off + ((uint64_t)nvec << 4) + ctid, (uint8_t)lds8(pay + (nvec << 4) + ctid));
-}
-
-__device__ __forceinline__ float lds_f32_any(uint32_t a) {
-  uint32_t w;
-  if ((a & 3u) == 0) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(a));
-  else w = lds8(a) | (lds8(a + 1) << 8) | (lds8(a + 2) << 16) | (lds8(a + 3) << 24);
-  return __uint_as_float(w);
-}
-__device__ __forceinline__ float lds_f16_any(uint32_t a) {
-  uint32_t h;
-  if ((a & 1u) == 0) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(h) : "r"(a));
-  else h = lds8(a) | (lds8(a + 1) << 8);
-  return __half2float(__ushort_as_half((unsigned short)h));
-}
-
-__device__ __forceinline__ void consume_f32(const Dsts& D, uint32_t pay, uint32_t n, uint64_t dst_off, int ctid) {
-  const uint32_t ngrp = n >> 3;  // 8 elements -> 16 B out
-  if ((pay & 15u) == 0) {
-    for (uint32_t g = ctid; g < ngrp; g += kConsumerThreads) {
-      uint4 a = lds128(pay + (g << 5)), b = lds128(pay + (g << 5) + 16);
-      uint4 o;
-      o.x = pack_bf16x2(__uint_as_float(a.x), __uint_as_float(a.y));
-      o.y = pack_bf16x2(__uint_as_float(a.z), __uint_as_float(a.w));
-      o.z = pack_bf16x2(__uint_as_float(b.x), __uint_as_float(b.y));
-      o.w = pack_bf16x2(__uint_as_float(b.z), __uint_as_float(b.w));
-      store16_all(D, dst_off + ((uint64_t)g << 4), o);
-    }
-  } else {
-    for (uint32_t g = ctid; g < ngrp; g += kConsumerThreads) {
-      float f[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) f[k] = lds_f32_any(pay + (g << 5) + 4 * k);
-      store16_all(D, dst_off + ((uint64_t)g << 4),
-                  make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7])));
-    }
-  }
-  const uint32_t tail = n & 7u, base = ngrp << 3;
-  if (ctid < (int)tail) store2_all(D, dst_off + 2ull * (base + ctid), to_bf16(lds_f32_any(pay + 4 * (base + ctid))));
-}
-
-__device__ __forceinline__ void consume_f16(const Dsts& D, uint32_t pay, uint32_t n, uint64_t dst_off, int ctid) {
-  const uint32_t ngrp = n >> 3;
-  if ((pay & 15u) == 0) {
-    for (uint32_t g = ctid; g < ngrp; g += kConsumerThreads) {
-      uint4 a = lds128(pay + (g << 4));
-      const uint32_t w[4] = {a.x, a.y, a.z, a.w};
-      uint32_t o[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
-        o[k] = pack_bf16x2(f.x, f.y);
-      }
-      store16_all(D, dst_off + ((uint64_t)g << 4), make_uint4(o[0], o[1], o[2], o[3]));
-    }
-  } else {
-    for (uint32_t g = ctid; g < ngrp; g += kConsumerThreads) {
-      float f[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) f[k] = lds_f16_any(pay + (g << 4) + 2 * k);
-      store16_all(D, dst_off + ((uint64_t)g << 4),
-                  make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7])));
-    }
-  }
-  const uint32_t tail = n & 7u, base = ngrp << 3;
-  if (ctid < (int)tail) store2_all(D, dst_off + 2ull * (base + ctid), to_bf16(lds_f16_any(pay + 2 * (base + ctid))));
-}
-
-// Q8_0, Q6_K and the §8(f4) legacy / K quants: per-lane device functions shared with the host emulation harness.
+// ---- consumer bodies ------------------------------------------------------------------------------------------------------------
+// Every per-lane consumer function lives in kk_consume_core.cuh (copy, casts, Q4_K) and kk_dequant.cuh (the other block types, FP8,
+// 8-row transposes), written against the primitives bound here so that tests/emul can compile the same source for the host.
 __device__ __forceinline__ uint32_t lds16(uint32_t a) {
   uint32_t v;
   asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
@@ -289,78 +203,14 @@ __device__ __forceinline__ uint32_t kk_byte_perm(uint32_t a, uint32_t b, uint32_
 __device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t kk_ldg8(const uint8_t* p) { return (uint32_t)__ldg(p); }
+__device__ __forceinline__ void kk_h2x2f(uint32_t w, float& x, float& y) {
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+  x = f.x;
+  y = f.y;
+}
 #define KK_DQ_DEV __device__ __forceinline__
+#include "kk_consume_core.cuh"
 #include "kk_dequant.cuh"
-
-// Q4_K super-block (144 B): d f16 | dmin f16 | scales[12] | qs[128]  ->  256 bf16.
-// y = (d*sc_j)*q - (dmin*m_j), every product and the difference rounded to fp32 separately (no FMA
-// contraction) so the result is bit-identical to the oracle's gguf-py restatement, then RNE to bf16.
-//
-// One warp handles FOUR super-blocks per iteration: lane l decodes the 6-bit (scale, min) pair of
-// sub-block (l & 7) of block (l >> 3) — so the unpack runs once per four blocks instead of once per block —
-// and __shfl_sync hands every lane the pair of the sub-block its 8 outputs belong to.  The four blocks'
-// dependency chains are independent and fully unrolled (ILP hides the ALU latency with only 2 warps/SMSP).
-template <bool ALIGNED>
-__device__ __forceinline__ void q4k_quad(const Dsts& D, uint32_t pay, uint32_t b0, uint32_t nb, uint64_t dst_off, int lane) {
-  // --- decode: lane -> (block b0 + min(lane>>3, nb-1), sub-block lane&7)
-  const uint32_t hb = min((uint32_t)(lane >> 3), nb - 1);
-  const uint32_t hblk = pay + (b0 + hb) * KK_Q4K_BLOCK_BYTES;
-  uint32_t h0, s0, s1, s2;
-  if (ALIGNED) {
-    const uint4 h = lds128(hblk);
-    h0 = h.x; s0 = h.y; s1 = h.z; s2 = h.w;
-  } else {
-    h0 = lds32_bytes(hblk); s0 = lds32_bytes(hblk + 4); s1 = lds32_bytes(hblk + 8); s2 = lds32_bytes(hblk + 12);
-  }
-  const float d = __half2float(__ushort_as_half((unsigned short)(h0 & 0xFFFFu)));
-  const float dmin = __half2float(__ushort_as_half((unsigned short)(h0 >> 16)));
-  const int j = lane & 7, sh = (j & 3) * 8;
-  const uint32_t b_lo = (s0 >> sh) & 0xFFu, b_mid = (s1 >> sh) & 0xFFu, b_hi = (s2 >> sh) & 0xFFu;
-  const uint32_t sc = (j < 4) ? (b_lo & 63u) : ((b_hi & 0xFu) | ((b_lo >> 6) << 4));
-  const uint32_t mn = (j < 4) ? (b_mid & 63u) : ((b_hi >> 4) | ((b_mid >> 6) << 4));
-  const float dsc_j = __fmul_rn(d, (float)sc);
-  const float dmn_j = __fmul_rn(dmin, (float)mn);
-  // --- expand: this lane's 8 outputs of every block live in sub-block myj = lane >> 2
-  const int myj = lane >> 2;
-  const uint32_t qoff = 16u + 32u * (uint32_t)(myj >> 1) + 8u * (uint32_t)(lane & 3);
-  const int nsh = (myj & 1) * 4;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float dsc = __shfl_sync(0xffffffffu, dsc_j, 8 * k + myj);
-    const float dmn = __shfl_sync(0xffffffffu, dmn_j, 8 * k + myj);
-    if ((uint32_t)k < nb) {
-      const uint32_t qa = pay + (b0 + k) * KK_Q4K_BLOCK_BYTES + qoff;
-      uint32_t q0, q1;
-      if (ALIGNED) {
-        const uint2 q = lds64(qa);
-        q0 = q.x; q1 = q.y;
-      } else {
-        q0 = lds32_bytes(qa); q1 = lds32_bytes(qa + 4);
-      }
-      q0 = (q0 >> nsh) & 0x0F0F0F0Fu;
-      q1 = (q1 >> nsh) & 0x0F0F0F0Fu;
-      float y[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        // 0x4B0000qq is the float 2^23 + q; subtracting 2^23 gives q exactly (PRMT + FADD, no I2F).
-        const uint32_t bits = __byte_perm(e < 4 ? q0 : q1, 0x4B000000u, 0x7440u | (uint32_t)(e & 3));
-        const float q = __fsub_rn(__uint_as_float(bits), 8388608.0f);
-        y[e] = __fsub_rn(__fmul_rn(dsc, q), dmn);
-      }
-      store16_all(D, dst_off + (uint64_t)(b0 + k) * 512u + (uint32_t)lane * 16u,
-                  make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7])));
-    }
-  }
-}
-
-__device__ __forceinline__ void consume_q4k(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
-  const bool al = (pay & 15u) == 0;  // 144-byte blocks keep the tile's alignment class
-  for (uint32_t b0 = (uint32_t)cwarp * 4u; b0 < nblk; b0 += kConsumerWarps * 4u) {
-    const uint32_t nb = min(4u, nblk - b0);
-    if (al) q4k_quad<true>(D, pay, b0, nb, dst_off, lane);
-    else q4k_quad<false>(D, pay, b0, nb, dst_off, lane);
-  }
-}
 
 // 2-D transpose tile.  Source elements come either from the TMA-staged tile (t.bulk == 2: the producer pulled
 // the tile's rows into the stage with one cp.async.bulk per row, KK_T_COLS*ES + 16 bytes apart) or, when a row

@@ -16,6 +16,7 @@
 namespace {
 
 struct uint4 { uint32_t x, y, z, w; };
+struct uint2 { uint32_t x, y; };
 inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 
 struct Emu {
@@ -26,7 +27,12 @@ struct Emu {
   uint8_t* out = nullptr;
   uint64_t out_bytes = 0;
   uint8_t* hits = nullptr;  // one counter per 16 output bytes
-  uint8_t* out_mask = nullptr;  // per 2 output bytes: written by a scalar (tail) store
+  uint8_t* out_mask = nullptr;  // per 2 output bytes: written by a scalar (tail) store (per byte for store1_all: see byte_mask)
+  uint8_t* byte_mask = nullptr; // per output byte: written by store1_all
+  // warp-shuffle emulation (see __shfl_sync below)
+  static constexpr int kMaxShfl = 64;
+  int shfl_mode = 0, shfl_calls = 0, lane = 0;
+  float shfl_table[kMaxShfl][32];
   int err = 0;              // first failure: 1 load out of range, 2 misaligned load, 3 store out of range/misaligned, 4 double store
 };
 thread_local Emu g;
@@ -56,6 +62,29 @@ inline void sts32(uint32_t a, uint32_t v) {
   if ((a & 3u) || a + 4 > g.tile_bytes || !g.wtile) { flag(6); return; }
   memcpy(g.wtile + a, &v, 4);
 }
+inline uint2 lds64(uint32_t a) {
+  uint2 v{0, 0};
+  if (a & 7u) { flag(2); return v; }
+  if (a + 8 > g.tile_bytes) { flag(1); return v; }
+  memcpy(&v, g.tile + a, 8);
+  return v;
+}
+// Warp shuffle by record / replay: the driver runs every lane of a warp twice.  Pass 1 (g.shfl_mode == 1) records the value each lane
+// offers at its k-th shuffle and suppresses stores; pass 2 (== 2) hands out the recorded value of the source lane.  Valid for code whose
+// shuffled values do not depend on earlier shuffle results and whose lanes all execute the same shuffles (true of q4k_quad).
+inline float __shfl_sync(unsigned, float v, int src) {
+  if (g.shfl_mode == 1) {
+    if (g.shfl_calls >= Emu::kMaxShfl) { flag(7); return v; }
+    g.shfl_table[g.shfl_calls++][g.lane] = v;
+    return v;
+  }
+  if (g.shfl_mode == 2) {
+    if (g.shfl_calls >= Emu::kMaxShfl) { flag(7); return v; }
+    return g.shfl_table[g.shfl_calls++][src & 31];
+  }
+  flag(7);  // a shuffle outside record/replay cannot be emulated
+  return v;
+}
 inline uint32_t kk_ldg8(const uint8_t* p) { return *p; }
 // PRMT (default mode) as the code under test uses it: selector nibble 0 picks byte (sel & 7) of {b:a}; the msb-replicate bit is never set
 inline uint32_t kk_byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
@@ -70,6 +99,7 @@ inline float kk_h2f(uint32_t h) {
   _Float16 x; memcpy(&x, &b, 2);
   return (float)x;
 }
+inline void kk_h2x2f(uint32_t w, float& x, float& y) { x = kk_h2f(w & 0xFFFFu); y = kk_h2f(w >> 16); }
 // one IEEE operation each; -ffp-contract=off in the build line, volatile as a second guard
 inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
@@ -84,12 +114,22 @@ inline uint32_t pack_bf16x2(float a, float b) { return bf16_rne(a) | (bf16_rne(b
 struct Dsts { int unused; };
 // hits[u] counts the BYTES stored into 16-byte unit u: 16 after exactly one vector store (or eight 2-byte tail stores)
 inline void store16_all(const Dsts&, uint64_t off, const uint4& v) {
+  if (g.shfl_mode == 1) return;
   if ((off & 15u) || off + 16 > g.out_bytes) { flag(3); return; }
   if (g.hits[off >> 4]) flag(4);
   g.hits[off >> 4] += 16;
   memcpy(g.out + off, &v, 16);
 }
+inline void store1_all(const Dsts&, uint64_t off, uint8_t v) {
+  if (g.shfl_mode == 1) return;
+  if (off + 1 > g.out_bytes) { flag(3); return; }
+  if (g.byte_mask[off]) flag(4);
+  g.byte_mask[off] = 1;
+  g.hits[off >> 4] += 1;
+  g.out[off] = v;
+}
 inline void store2_all(const Dsts&, uint64_t off, uint16_t v) {
+  if (g.shfl_mode == 1) return;
   if ((off & 1u) || off + 2 > g.out_bytes) { flag(3); return; }
   if (g.out_mask[off >> 1]) flag(4);
   g.out_mask[off >> 1] = 1;
@@ -120,11 +160,14 @@ template <bool E5M2>
 inline uint32_t kk_f8x2_to_f16x2(uint32_t v) { return f8_to_f16_bits(v, E5M2) | (f8_to_f16_bits(v >> 8, E5M2) << 16); }
 
 constexpr int kConsumerWarps = 16;  // must equal KK_CONSUMER_WARPS of the kernel build
+constexpr int kConsumerThreads = kConsumerWarps * 32;
 #define KK_DQ_DEV static inline
 #define min(a, b) ((a) < (b) ? (a) : (b))
+#include "../../kukeon_b200/csrc/kk_consume_core.cuh"
 #include "../../kukeon_b200/csrc/kk_dequant.cuh"
 #undef min
 
+// (run_warps, below, plays all warps of a tile; ops that shuffle are run twice per warp)
 // One lane of the consumer side of a block / elementwise op — the same switch the kernel has.  false: op not covered here.
 inline bool run_op(uint32_t op, const Dsts& D, uint32_t pay, uint32_t n, uint64_t dst_off, int cwarp, int lane) {
   switch (op) {
@@ -140,7 +183,11 @@ inline bool run_op(uint32_t op, const Dsts& D, uint32_t pay, uint32_t n, uint64_
     case KK_OP_IQ4NL_BF16: consume_codebook32<KK_IQ4NL_BLOCK_BYTES, 0>(D, pay, n, dst_off, cwarp, lane); return true;
     case KK_OP_MXFP4_BF16: consume_codebook32<KK_MXFP4_BLOCK_BYTES, 1>(D, pay, n, dst_off, cwarp, lane); return true;
     case KK_OP_IQ4XS_BF16: consume_iq4xs(D, pay, n, dst_off, cwarp, lane); return true;
-    // elementwise ops: n = elements of the tile, threads indexed 0..511 across the consumer warps
+    case KK_OP_Q4K_BF16: consume_q4k(D, pay, n, dst_off, cwarp, lane); return true;
+    // elementwise ops: n = elements (COPY: bytes) of the tile, threads indexed 0..511 across the consumer warps
+    case KK_OP_COPY: consume_copy(D, pay, n, dst_off, cwarp * 32 + lane); return true;
+    case KK_OP_F32_BF16: consume_f32(D, pay, n, dst_off, cwarp * 32 + lane); return true;
+    case KK_OP_F16_BF16: consume_f16(D, pay, n, dst_off, cwarp * 32 + lane); return true;
     case KK_OP_F8E4M3_BF16: consume_f8<false>(D, pay, n, dst_off, cwarp * 32 + lane); return true;
     case KK_OP_F8E5M2_BF16: consume_f8<true>(D, pay, n, dst_off, cwarp * 32 + lane); return true;
     default: return false;
@@ -148,6 +195,22 @@ inline bool run_op(uint32_t op, const Dsts& D, uint32_t pay, uint32_t n, uint64_
 }
 
 }  // namespace
+
+inline bool run_warps(uint32_t op, const Dsts& D, uint32_t pay, uint32_t n, uint64_t dst_off) {
+  const bool shuffles = op == KK_OP_Q4K_BF16;
+  for (int cwarp = 0; cwarp < kConsumerWarps; ++cwarp) {
+    for (int pass = shuffles ? 1 : 0; pass <= (shuffles ? 2 : 0); ++pass) {
+      g.shfl_mode = pass;
+      for (int lane = 0; lane < 32; ++lane) {
+        g.lane = lane;
+        g.shfl_calls = 0;
+        if (!run_op(op, D, pay, n, dst_off, cwarp, lane)) return false;
+      }
+    }
+  }
+  g.shfl_mode = 0;
+  return true;
+}
 
 // Run the consumer side of one tile of block op `op` (KKOp): `nblk` blocks whose first byte sits at tile[pay_off].
 // out receives nblk * out_bytes_per_block bytes; hits (out_bytes/16 counters, zeroed here) how often each 16-byte unit
@@ -157,12 +220,11 @@ extern "C" int kk_emul_dequant_tile(uint32_t op, const uint8_t* tile, uint32_t t
   g = Emu{};
   g.tile = tile; g.tile_bytes = tile_bytes; g.out = out; g.out_bytes = out_bytes; g.hits = hits;
   memset(hits, 0, (out_bytes + 15) / 16);
-  std::vector<uint8_t> mask(out_bytes / 2 + 1, 0);
+  std::vector<uint8_t> mask(out_bytes / 2 + 1, 0), bmask(out_bytes + 1, 0);
   g.out_mask = mask.data();
+  g.byte_mask = bmask.data();
   const Dsts D{0};
-  for (int cwarp = 0; cwarp < kConsumerWarps; ++cwarp)
-    for (int lane = 0; lane < 32; ++lane)
-      if (!run_op(op, D, pay_off, nblk, 0, cwarp, lane)) return -1;
+  if (!run_warps(op, D, pay_off, nblk, 0)) return -1;
   return g.err;
 }
 
@@ -180,7 +242,7 @@ extern "C" int kk_emul_dequant_segment(uint32_t op, const uint8_t* src, uint64_t
   seg.src_off = src_misalign;  // pretend the launch's src base is 16-byte aligned and the segment starts here
   memset(hits, 0, out_bytes / 16);
   static thread_local uint8_t stage[KK_TILE_SRC_BYTES + KK_STAGE_PAD];
-  std::vector<uint8_t> mask(out_bytes / 2 + 1, 0);
+  std::vector<uint8_t> mask(out_bytes / 2 + 1, 0), bmask(out_bytes + 1, 0);
   const uint64_t n_tiles = kk_seg_tiles(op, units, 0);
   for (uint64_t t = 0; t < n_tiles; ++t) {
     const KKBlockTile bt = kk_block_tile(seg, (uint32_t)t);
@@ -193,10 +255,9 @@ extern "C" int kk_emul_dequant_segment(uint32_t op, const uint8_t* src, uint64_t
     g = Emu{};
     g.tile = stage; g.tile_bytes = mis + bt.in_bytes; g.out = out; g.out_bytes = out_bytes; g.hits = hits;
     g.out_mask = mask.data();
+    g.byte_mask = bmask.data();
     const Dsts D{0};
-    for (int cwarp = 0; cwarp < kConsumerWarps; ++cwarp)
-      for (int lane = 0; lane < 32; ++lane)
-        if (!run_op(op, D, mis, bt.n_blocks, bt.dst_off, cwarp, lane)) return -1;
+    if (!run_warps(op, D, mis, bt.n_blocks, bt.dst_off)) return -1;
     if (g.err) return g.err;
   }
   return 0;

@@ -16,7 +16,7 @@ from tests import helpers
 from tools import synth
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-OPS = {"Q8_0": helpers.OP_Q8_0, "Q6_K": helpers.OP_Q6K, "Q4_0": helpers.OP_Q4_0, "Q4_1": helpers.OP_Q4_1, "Q5_0": helpers.OP_Q5_0,
+OPS = {"Q4_K": helpers.OP_Q4K, "Q8_0": helpers.OP_Q8_0, "Q6_K": helpers.OP_Q6K, "Q4_0": helpers.OP_Q4_0, "Q4_1": helpers.OP_Q4_1, "Q5_0": helpers.OP_Q5_0,
        "Q5_1": helpers.OP_Q5_1, "Q2_K": helpers.OP_Q2K, "Q3_K": helpers.OP_Q3K, "Q5_K": helpers.OP_Q5K, "IQ4_NL": helpers.OP_IQ4NL,
        "IQ4_XS": helpers.OP_IQ4XS, "MXFP4": helpers.OP_MXFP4}
 ERR = {1: "shared-memory load outside the staged tile", 2: "misaligned 16/32-bit shared-memory load", 3: "store outside the output window or not 16-byte aligned",
@@ -79,7 +79,7 @@ def test_full_tile_finite_scales(emul, dtype):
 def test_ragged_counts_and_every_alignment_random_bytes(emul, dtype):
     """Fully random bytes (Inf/NaN scales included: NaN -> 0x7FFF on both sides) at every start alignment a tile can have."""
     nel, nb, _ = oracle.BLOCK_QUANTS[dtype]
-    per_iter = 8 if nel == 32 else 1  # blocks one warp iteration covers
+    per_iter = 8 if nel == 32 else 4 if dtype == "Q4_K" else 1  # blocks one warp iteration covers
     rng = np.random.default_rng(5)
     counts = [1, 2, per_iter - 1 or 1, per_iter, per_iter + 1, 16 * per_iter - 1, 16 * per_iter, 16 * per_iter + 1, 16 * per_iter + 5, 37 * per_iter + 3]
     for k, n in enumerate(counts):
@@ -178,6 +178,53 @@ def test_t8_transpose_tiles_values_write_once_and_bank_conflicts(emul, dtype, st
         if staged and nr == 8 and nc % 32 == 0:
             assert stats[0] == stats[1], f"{dtype} {nr}x{nc}: {stats[0]} shared-memory wavefronts for {stats[1]} warp loads"
         del touched
+
+
+def _run_elementwise(emul, op, src_bytes, n_units, pay_off, out_bytes):
+    tile = np.full(pay_off + src_bytes.size, 0x5A, np.uint8)
+    tile[pay_off:] = src_bytes
+    out = np.zeros(out_bytes, np.uint8)
+    hits = np.zeros((out_bytes + 15) // 16, np.uint8)
+    rc = emul.kk_emul_dequant_tile(op, tile.ctypes.data, tile.size, pay_off, n_units, out.ctypes.data, out.size, hits.ctypes.data)
+    assert rc == 0, ERR.get(rc, rc)
+    want_hits = np.full(hits.size, 16, np.uint8)
+    if out_bytes % 16:
+        want_hits[-1] = out_bytes % 16
+    assert (hits == want_hits).all(), "every output byte stored exactly once"
+    return out
+
+
+def test_copy_and_casts_register_paths_every_alignment_and_tail(emul):
+    """The non-TMA consumer paths of the headline ops: COPY (misaligned / ragged tiles), F32 -> bf16 and F16 -> bf16 — aligned vector
+    loads and byte-assembled ones, counts that end inside a 16-byte group, a full 32 KiB tile."""
+    rng = np.random.default_rng(4)
+    for n in (1, 15, 16, 17, 255, 8191 * 4 + 3, 32768):
+        src = rng.integers(0, 256, n, dtype=np.uint8)
+        for pay_off in (0, 1, 4, 8, 15):
+            if pay_off + n > 32768 + 128:
+                continue
+            assert (_run_elementwise(emul, helpers.OP_COPY, src, n, pay_off, n) == src).all(), ("COPY", n, pay_off)
+    for n in (1, 7, 8, 9, 513, 8192):
+        f32 = synth.gen_bytes("F32", 4 * n, 6, n)
+        f32[:4 * min(n, 4)] = np.array([0x7F800000, 0xFF800001, 0x3F808000, 0x00000001], "<u4").view(np.uint8)[:4 * min(n, 4)]  # inf, NaN, tie, subnormal
+        f16 = synth.gen_bytes("F16", 2 * n, 7, n)
+        for pay_off in (0, 2, 4, 6, 8, 12) + ((1, 3) if n < 600 else ()):
+            got = _run_elementwise(emul, helpers.OP_F32, f32, n, pay_off, 2 * n).view(np.uint16)
+            assert (got == oracle.f32_bits_to_bf16(f32.view("<u4"))).all(), ("F32", n, pay_off)
+            got = _run_elementwise(emul, helpers.OP_F16, f16, n, pay_off, 2 * n).view(np.uint16)
+            assert (got == oracle.f16_bits_to_bf16(f16.view("<u2"))).all(), ("F16", n, pay_off)
+
+
+def test_q4k_shuffle_emulation_is_live(emul):
+    """Q4_K is the one consumer whose lanes trade values (__shfl_sync, emulated by record/replay): swapping two sub-block scale bytes
+    of one block must change exactly that block's output."""
+    blocks = synth.gen_bytes("Q4_K", 144 * 9, 2, 1).reshape(9, 144)
+    base = run_tile(emul, "Q4_K", blocks, 0)
+    mut = blocks.copy()
+    mut[5, 4], mut[5, 5] = blocks[5, 5] ^ 0x15, blocks[5, 4] ^ 0x2A
+    got = run_tile(emul, "Q4_K", mut, 0)
+    assert (got == oracle.dequant_bf16("Q4_K", mut)).all()
+    assert (got[5] != base[5]).any() and (np.delete(got, 5, 0) == np.delete(base, 5, 0)).all()
 
 
 def test_harness_sees_wrong_answers(emul):
