@@ -5,6 +5,6 @@ The product is `libkukeon_gpuload.so` (C ABI in include/kukeon_gpuload.h, source
 `modelhub.Pull/Load/Mount` Go surface.  Importing this package does not load the native library; the
 first call does, and fails loudly if it is missing — there is no CPU fallback.
 """
-from . import gpupool, modelhub, registry  # noqa: F401
+from . import gpupool, modelhub, registry, schema  # noqa: F401
 
-__all__ = ["gpupool", "modelhub", "registry"]
+__all__ = ["gpupool", "modelhub", "registry", "schema"]
