@@ -66,6 +66,7 @@ def parse():
     ap.add_argument("--no-exchange", action="store_true", help="scatter: every rank gathers its own column runs from the file (no NVLink row exchange)")
     ap.add_argument("--no-single-process", action="store_true", help="skip the one-process-all-GPUs time-to-ready measurement at N > 1")
     ap.add_argument("--t8", action="store_true", help="gpt2: transpose on 8-row tiles (KK_LOAD_T8_TILES), A/B against the 32x128 tiles")
+    ap.add_argument("--tw", action="store_true", help="gpt2: transpose on 32-row wide-store tiles (KK_LOAD_TW_TILES), A/B against the other two")
     ap.add_argument("--fanout", default="p2p", choices=["p2p", "raw", "pull"],
                     help="broadcast order: fused convert+fan-out (p2p), all-gather the file bytes then convert locally (raw), or convert into own pool + "
                          "slice buffer and pull the peers' slices (pull: peers map 1/N of the bytes, for one-process-per-GPU time-to-ready)")
@@ -310,7 +311,7 @@ def main():
     brk = {}
     ref = modelhub.Pull(path)
     brk["pull_s"] = time.time() - t_ready0
-    lflags = gpupool.LOAD_DEFER | (gpupool.LOAD_GPT2_CONV1D_T if spec["kind"] == "gpt2" else 0) | (gpupool.LOAD_T8_TILES if args.t8 else 0)
+    lflags = gpupool.LOAD_DEFER | (gpupool.LOAD_GPT2_CONV1D_T if spec["kind"] == "gpt2" else 0) | (gpupool.LOAD_T8_TILES if args.t8 else 0) | (gpupool.LOAD_TW_TILES if args.tw else 0)
     exchange = world > 1 and mode == gpupool.MODE_SCATTER and not args.no_exchange
     if exchange:
         lflags |= gpupool.LOAD_SCATTER_EXCHANGE
@@ -548,7 +549,7 @@ def main():
                             2: "scatter" + (" (row-parallel tensors exchanged over NVLink: KK_LOAD_SCATTER_EXCHANGE)" if exchange else "")}[mode], "pool_bytes_per_gpu": pool_bytes,
                    "l2": "inputs (>= 2 GB per GPU) far larger than the 126 MB L2; no flush needed", "files": f"warm in {os.path.dirname(d) or d}",
                    "staging": "zero-copy pinned reads" if args.zerocopy else "pinned ring + H2D copy engine", "verified_vs_files": verified,
-                   **({"transpose_tiles": "8 rows x 4 KiB (KK_LOAD_T8_TILES)" if args.t8 else "32 x 128"} if spec["kind"] == "gpt2" else {})},
+                   **({"transpose_tiles": "32 rows x 960 B, 64-byte stores (KK_LOAD_TW_TILES)" if args.tw else "8 rows x 4 KiB (KK_LOAD_T8_TILES)" if args.t8 else "32 x 128"} if spec["kind"] == "gpt2" else {})},
         "clocks": ck,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(allsum(float(local_src))), "d2h_bytes_per_step": 8 * world,
                 "ms_per_step": e2e_time / args.steps * 1e3, "what": "kk_load_part (pread->pinned->H2D->kernels) + kk_export + checksum word D2H"},
@@ -597,7 +598,7 @@ def main():
                 sp_open = time.time() - t0
                 t0 = time.time()
                 ref2 = modelhub.Pull(path)
-                spf = (gpupool.LOAD_GPT2_CONV1D_T if spec["kind"] == "gpt2" else 0) | (gpupool.LOAD_SCATTER_EXCHANGE if exchange else 0) | (gpupool.LOAD_T8_TILES if args.t8 else 0)
+                spf = (gpupool.LOAD_GPT2_CONV1D_T if spec["kind"] == "gpt2" else 0) | (gpupool.LOAD_SCATTER_EXCHANGE if exchange else 0) | (gpupool.LOAD_T8_TILES if args.t8 else 0) | (gpupool.LOAD_TW_TILES if args.tw else 0)
                 m2 = modelhub.Load(sp, ref2, mode=mode, fanout=gpupool.FANOUT_RAW if raw_order else gpupool.FANOUT_P2P, flags=spf)
                 for dev in range(world):
                     m2.export(dev)

@@ -114,6 +114,8 @@ typedef enum kk_fanout {
 #define KK_LOAD_T8_TILES 0x20u      /* KK_LOAD_GPT2_CONV1D_T: transpose on 8-row x 4 KiB tiles (8x fewer bulk copies per byte, bank-conflict-free
                                       reads, 16-byte stores).  Candidate geometry, bit-identical results; opt-in until it has been
                                       measured against the 32x128 tiles on hardware, then it becomes the default */
+#define KK_LOAD_TW_TILES 0x40u      /* second candidate: 32-row x 960-byte tiles whose lane mapping stores full 64-byte segments (fewer, wider
+                                      store transactions than the 8-row tiles, more bulk copies).  Takes precedence over KK_LOAD_T8_TILES */
 
 typedef struct kk_ctx kk_ctx;     /* one per process (kukeond lifetime) */
 typedef struct kk_model kk_model; /* refcounted; one per (checkpoint identity, mode, flags) */

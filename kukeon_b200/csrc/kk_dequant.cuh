@@ -371,3 +371,42 @@ KK_DQ_DEV void consume_iq4xs(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_
     store_bf16x8(D, dst_off + (uint64_t)b * 512u + (uint32_t)lane * 16u, y);
   }
 }
+
+// ---- 32-row wide-store transpose tiles (KK_LOAD_TW_TILES; KK_OP_TW_*) --------------------------------------------------------------------
+// Stage: nr <= 32 source rows of nc columns, row r at sbase + r * pitch (pitch = KK_TW_PITCH when staged by bulk copies).  A warp
+// takes 8 columns at a time; lane = (cc = lane & 7, rg = lane >> 3) produces rows 8rg .. 8rg+7 of column cb + cc, i.e. 16 of the 64
+// contiguous destination bytes that column has in this tile, so the four rg-lanes of a column write one full 64-byte segment per store
+// instruction.  Reading row 8rg + ((k + 2rg) & 7) at step k spreads the four row groups over different banks (see kk_ops.h).
+template <int ES, int CONV>
+KK_DQ_DEV void consume_tw(const Dsts& D, uint32_t sbase, uint32_t pitch, uint32_t nr, uint32_t nc, uint32_t R, uint32_t col0, uint32_t row0,
+                          uint64_t dst_off, int cwarp, int lane) {
+  const uint32_t cc = (uint32_t)(lane & 7), rg = (uint32_t)(lane >> 3);
+  const uint32_t rbase = 8u * rg;
+  const bool vec = rbase + 8u <= nr && (R & 7u) == 0 && (row0 & 7u) == 0 && (dst_off & 15u) == 0;
+  for (uint32_t cb = (uint32_t)cwarp * 8u; cb < nc; cb += kConsumerWarps * 8u) {
+    const uint32_t c = cb + cc;
+    if (c >= nc || rbase >= nr) continue;
+    uint32_t u[8];  // u[k] = source row rbase + ((k + 2rg) & 7): the rotated order keeps the four row groups on different banks
+#pragma unroll
+    for (uint32_t k = 0; k < 8; ++k) {
+      const uint32_t row = rbase + ((k + 2u * rg) & 7u);
+      const uint32_t a = sbase + row * pitch + c * (uint32_t)ES;
+      u[k] = row < nr ? (ES == 4 ? lds32(a) : lds16(a)) : 0u;
+    }
+    const uint64_t off = dst_off + ((uint64_t)(col0 + c) * R + row0 + rbase) * 2u;
+    if (vec) {
+      // an even rotation keeps row pairs together: word i holds rows (2i + 2rg) & 7 and the next one; undo the rotation on the packed words
+      uint32_t p0 = t8_pack2<ES, CONV>(u[0], u[1]), p1 = t8_pack2<ES, CONV>(u[2], u[3]), p2 = t8_pack2<ES, CONV>(u[4], u[5]),
+               p3 = t8_pack2<ES, CONV>(u[6], u[7]);
+      if (rg & 1u) { const uint32_t t = p3; p3 = p2; p2 = p1; p1 = p0; p0 = t; }            // output word j = packed word (j - 1) & 3
+      if (rg & 2u) { uint32_t t = p0; p0 = p2; p2 = t; t = p1; p1 = p3; p3 = t; }          // output word j = packed word (j - 2) & 3
+      store16_all(D, off, make_uint4(p0, p1, p2, p3));
+    } else {
+#pragma unroll
+      for (uint32_t k = 0; k < 8; ++k) {
+        const uint32_t kr = (k + 2u * rg) & 7u;
+        if (rbase + kr < nr) store2_all(D, off + 2u * kr, (uint16_t)(t8_pack2<ES, CONV>(u[k], 0u) & 0xFFFFu));
+      }
+    }
+  }
+}

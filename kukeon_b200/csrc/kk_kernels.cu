@@ -39,7 +39,7 @@ struct __align__(16) TileDesc {
   uint32_t pay_off;  // payload offset inside the stage buffer (0..15 for TMA tiles)
   uint32_t n_units;  // units in this tile (bytes / elements / blocks); transposes: rows | cols<<16
   uint32_t bulk;     // 1: aligned copy, bulk-store from shared memory; 2: transpose tile staged row by row with TMA; 3: row-split exchange;
-                     // 4: 8-row transpose tile staged with TMA, rows nc*es bytes apart
+                     // 4: 8-row transpose tile staged with TMA, rows nc*es bytes apart; 5: 32-row wide-store tile, rows KK_TW_PITCH apart
   uint64_t dst_off;  // pool byte offset of the tile's first output (transposes: dst tensor origin)
   uint64_t src_off;  // transposes: byte offset of source element (r0, c0) from L.src
   uint32_t C;        // transposes: source columns
@@ -293,6 +293,17 @@ __device__ __forceinline__ void run_t8(const Dsts& D, const uint8_t* src, const 
   consume_t8<ES, CONV>(D, sbase, pitch, nr, nc, t.R, t.col0, t.row0, t.dst_off, ctid);
 }
 
+// 32-row wide-store transpose tile (KK_OP_TW_*): staged by the producer (t.bulk == 5, rows KK_TW_PITCH apart) or gathered here.
+template <int ES, int CONV>
+__device__ __forceinline__ void run_tw(const Dsts& D, const uint8_t* src, const TileDesc& t, uint32_t sbase, int cwarp, int lane, int ctid) {
+  const uint32_t nr = t.n_units & 0xFFFFu, nc = t.n_units >> 16;
+  if (t.bulk != 5) {
+    t8_gather<ES>(src + t.src_off, sbase, KK_TW_PITCH, nr, nc, t.C, ctid);
+    named_bar_consumers();
+  }
+  consume_tw<ES, CONV>(D, sbase, KK_TW_PITCH, nr, nc, t.R, t.col0, t.row0, t.dst_off, cwarp, lane);
+}
+
 __device__ __forceinline__ KKSeg load_seg(const KKSeg* p) {
   const uint4* q = reinterpret_cast<const uint4*>(p);
   uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
@@ -458,6 +469,36 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
             }
             break;  // unaligned rows: publish the descriptor only, the consumers gather the tile themselves
           }
+          case KK_OP_TW_F32_BF16:
+          case KK_OP_TW_F16_BF16:
+          case KK_OP_TW_B16: {  // 32 source rows x up to KK_TW_ROW_BYTES per row, KK_TW_PITCH apart in the stage
+            const uint32_t es = seg.op == KK_OP_TW_F32_BF16 ? 4u : 2u;
+            const uint32_t C = seg.p0, W = KK_TW_ROW_BYTES / es;
+            const uint32_t ct = (C + W - 1) / W;
+            const uint32_t tr = t / ct, tc = t % ct;
+            const uint64_t r0 = (uint64_t)tr * KK_TW_ROWS;
+            const uint32_t c0 = tc * W;
+            const uint64_t rrem = seg.units - r0;
+            const uint32_t nr = rrem < KK_TW_ROWS ? (uint32_t)rrem : KK_TW_ROWS;
+            const uint32_t nc = (C - c0) < W ? (C - c0) : W;
+            d.n_units = nr | (nc << 16);
+            d.C = C; d.R = seg.p1; d.col0 = c0; d.row0 = seg.p2 + (uint32_t)r0;
+            d.src_off = seg.src_off + (r0 * C + c0) * es;
+            d.dst_off = seg.dst_off;
+            const uint64_t row_pitch = (uint64_t)C * es;
+            const uint32_t rb = nc * es;
+            if ((((uintptr_t)(L.src + d.src_off)) & 15u) == 0 && (row_pitch & 15u) == 0 && (rb & 15u) == 0) {
+              d.bulk = 5;
+              d.pay_off = 0;
+              descs[s] = d;
+              mbar_arrive_expect_tx(full0 + 8 * s, nr * rb);
+              const uint8_t* gp = L.src + d.src_off;
+              const uint32_t sb = smem_u32(stage_buf + s * kStageBytes);
+              for (uint32_t r = 0; r < nr; ++r) bulk_g2s(sb + r * KK_TW_PITCH, gp + r * row_pitch, rb, full0 + 8 * s);
+              continue;
+            }
+            break;
+          }
           default: {  // transposes
             const uint32_t C = seg.p0;
             const uint32_t ct = (C + KK_T_COLS - 1) / KK_T_COLS;
@@ -610,6 +651,9 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
         case KK_OP_T8_F32_BF16: run_t8<4, 1>(D, L.src, t, sbase, ctid); break;
         case KK_OP_T8_F16_BF16: run_t8<2, 2>(D, L.src, t, sbase, ctid); break;
         case KK_OP_T8_B16: run_t8<2, 0>(D, L.src, t, sbase, ctid); break;
+        case KK_OP_TW_F32_BF16: run_tw<4, 1>(D, L.src, t, sbase, cwarp, lane, ctid); break;
+        case KK_OP_TW_F16_BF16: run_tw<2, 2>(D, L.src, t, sbase, cwarp, lane, ctid); break;
+        case KK_OP_TW_B16: run_tw<2, 0>(D, L.src, t, sbase, cwarp, lane, ctid); break;
         case KK_OP_F8E4M3_BF16: consume_f8<false>(D, pay, t.n_units, t.dst_off, ctid); break;
         case KK_OP_F8E5M2_BF16: consume_f8<true>(D, pay, t.n_units, t.dst_off, ctid); break;
         case KK_OP_T_F32_BF16: consume_transpose<4, 2, 1>(D, L.src, t, sbase, ctid); break;

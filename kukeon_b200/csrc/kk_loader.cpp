@@ -1089,7 +1089,8 @@ std::string model_stats(kk_model* m) {
         case KK_OP_F32_BF16: case KK_OP_F16_BF16: case KK_OP_F8E4M3_BF16: case KK_OP_F8E5M2_BF16: e = b + s.units * 2; break;
         case KK_OP_T_B32: e = b + (uint64_t)s.p0 * s.p1 * 4; break;
         case KK_OP_T_F32_BF16: case KK_OP_T_F16_BF16: case KK_OP_T_B16:
-        case KK_OP_T8_F32_BF16: case KK_OP_T8_F16_BF16: case KK_OP_T8_B16: e = b + (uint64_t)s.p0 * s.p1 * 2; break;
+        case KK_OP_T8_F32_BF16: case KK_OP_T8_F16_BF16: case KK_OP_T8_B16:
+        case KK_OP_TW_F32_BF16: case KK_OP_TW_F16_BF16: case KK_OP_TW_B16: e = b + (uint64_t)s.p0 * s.p1 * 2; break;
         default: e = b + s.units * kk_block_geom(s.op).out_bytes; break;  // block-dequantising ops
       }
       if (b < lo) lo = b;

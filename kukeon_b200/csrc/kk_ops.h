@@ -44,6 +44,14 @@
  * at any pitch — and every thread packs the 8 rows of one column into a single 16-byte store. */
 #define KK_T8_ROWS 8u
 #define KK_T8_ROW_BYTES 4096u    /* per staged row: 1024 f32 or 2048 16-bit columns */
+/* Second candidate (KK_LOAD_TW_TILES): 32 source rows x (KK_TW_ROW_BYTES / es) columns, rows KK_TW_PITCH bytes apart in the stage.
+ * Costs 32 bulk copies per 30 KiB (half of what the 32x128 tiles need per byte, 4x what the 8-row tiles need) but every column of a
+ * tile is 64 contiguous destination bytes: a warp = 8 columns x 4 row groups stores 8 full 64-byte segments per instruction instead of
+ * 32 scattered 16-byte ones.  Pitch 976 B = 244 words: with lane (cc, rg) reading row 8*rg + ((k + 2*rg) & 7) at step k the bank is
+ * (20*k + 8*rg + cc) mod 32 — all 32 lanes distinct. */
+#define KK_TW_ROWS 32u
+#define KK_TW_ROW_BYTES 960u
+#define KK_TW_PITCH 976u
 #define KK_MAX_DST 8
 
 enum KKOp : uint32_t {
@@ -86,7 +94,11 @@ enum KKOp : uint32_t {
   KK_OP_IQ4NL_BF16 = 23,
   KK_OP_IQ4XS_BF16 = 24,
   KK_OP_MXFP4_BF16 = 25,
-  KK_OP_COUNT = 26
+  // 2-D transposes on 32-row wide-store tiles (KK_LOAD_TW_TILES); units / p0 / p1 / p2 as KK_OP_T_*
+  KK_OP_TW_F32_BF16 = 26,
+  KK_OP_TW_F16_BF16 = 27,
+  KK_OP_TW_B16 = 28,
+  KK_OP_COUNT = 29
 };
 
 struct KKSeg {
@@ -195,7 +207,14 @@ static inline KK_HD uint64_t kk_seg_tiles(uint32_t op, uint64_t units, uint32_t 
       const uint64_t w = KK_T8_ROW_BYTES / (op == KK_OP_T8_F32_BF16 ? 4u : 2u);
       return ((units + KK_T8_ROWS - 1) / KK_T8_ROWS) * (((uint64_t)p0 + w - 1) / w);
     }
+    case KK_OP_TW_F32_BF16:
+    case KK_OP_TW_F16_BF16:
+    case KK_OP_TW_B16: {
+      const uint64_t w = KK_TW_ROW_BYTES / (op == KK_OP_TW_F32_BF16 ? 4u : 2u);
+      return ((units + KK_TW_ROWS - 1) / KK_TW_ROWS) * (((uint64_t)p0 + w - 1) / w);
+    }
     default: return 0;
   }
 }
+static_assert(KK_TW_ROWS * KK_TW_PITCH <= KK_TILE_SRC_BYTES + KK_STAGE_PAD && KK_TW_PITCH % 16u == 0 && KK_TW_ROW_BYTES <= KK_TW_PITCH, "TW tile fits a stage");
 #endif

@@ -23,7 +23,7 @@ KK_POOL_ALIGN = 256
 MODE_SINGLE, MODE_BROADCAST, MODE_SCATTER = 0, 1, 2
 FANOUT_P2P, FANOUT_NVLS, FANOUT_NONE, FANOUT_RAW, FANOUT_PULL = 0, 1, 2, 3, 4
 CFG_ZEROCOPY, CFG_NO_PEER_ACCESS, CFG_NO_NUMA_PIN, CFG_PEER_ALL = 0x1, 0x2, 0x4, 0x8
-LOAD_GPT2_CONV1D_T, LOAD_KEEP_F32, LOAD_DEFER, LOAD_SCATTER_EXCHANGE, LOAD_F8_TO_BF16, LOAD_T8_TILES = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
+LOAD_GPT2_CONV1D_T, LOAD_KEEP_F32, LOAD_DEFER, LOAD_SCATTER_EXCHANGE, LOAD_F8_TO_BF16, LOAD_T8_TILES, LOAD_TW_TILES = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20, 0x40
 BUF_POOL, BUF_RAW, BUF_POOL_PTR, BUF_SLICE, BUF_SLICE_PTR = 0, 1, 2, 3, 4
 
 DTYPE_NAMES = {

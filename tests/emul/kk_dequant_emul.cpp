@@ -23,6 +23,7 @@ struct Emu {
   const uint8_t* tile = nullptr;  // the stage buffer; shared-memory address a <-> tile[a]
   uint8_t* wtile = nullptr;       // same buffer when the code under test may store into it (sts16 / sts32)
   std::vector<uint32_t>* trace = nullptr;  // when set: every 16/32-bit shared load appends its address (bank-conflict accounting)
+  std::vector<uint64_t>* strace = nullptr; // when set: every 16-byte store appends its destination offset (store-transaction accounting)
   uint32_t tile_bytes = 0;
   uint8_t* out = nullptr;
   uint64_t out_bytes = 0;
@@ -118,6 +119,7 @@ inline void store16_all(const Dsts&, uint64_t off, const uint4& v) {
   if ((off & 15u) || off + 16 > g.out_bytes) { flag(3); return; }
   if (g.hits[off >> 4]) flag(4);
   g.hits[off >> 4] += 16;
+  if (g.strace) g.strace->push_back(off);
   memcpy(g.out + off, &v, 16);
 }
 inline void store1_all(const Dsts&, uint64_t off, uint8_t v) {
@@ -263,29 +265,35 @@ extern "C" int kk_emul_dequant_segment(uint32_t op, const uint8_t* src, uint64_t
   return 0;
 }
 
-// One 8-row transpose tile (KK_OP_T8_*) the way the kernel runs it.  `src` points at source element (r0, c0) of a row-major
-// [*, C] tensor of ES-byte elements; staged != 0 lays the tile out as the producer's bulk copies do (rows nc*ES apart), staged == 0
-// runs the consumers' gather fallback first.  `dst` is the destination tensor's origin ([C_total, R] row-major, 2-byte elements),
-// dst_bytes its size; hits as in kk_emul_dequant_tile over dst.  stats[0] receives the shared-memory wavefronts the consumers'
-// loads need (one per distinct 4-byte word per bank per warp instruction), stats[1] the ideal (one per warp instruction).
+// One transpose tile of the candidate geometries (KK_OP_T8_*: 8 rows, compact rows; KK_OP_TW_*: 32 rows, KK_TW_PITCH apart) the way the
+// kernel runs it.  `src` points at source element (r0, c0) of a row-major [*, C] tensor of ES-byte elements; staged != 0 lays the tile out
+// as the producer's bulk copies do, staged == 0 runs the consumers' gather fallback first.  `dst` is the destination tensor's origin
+// ([C_total, R] row-major, 2-byte elements), dst_bytes its size; hits as in kk_emul_dequant_tile over dst.
+// stats: [0] shared-memory wavefronts the consumers' loads need (one per distinct 4-byte word per bank per warp instruction), [1] the
+// ideal (one per warp load), [2] warp-level 16-byte store instructions, [3] distinct 128-byte lines and [4] distinct 32-byte sectors those
+// touch, summed over instructions (what the LSU / L2 see as transactions).
 extern "C" int kk_emul_t8_tile(uint32_t op, const uint8_t* src, uint32_t C, uint32_t nr, uint32_t nc, uint32_t R, uint32_t col0, uint32_t row0,
                                int staged, uint8_t* dst, uint64_t dst_bytes, uint8_t* hits, uint64_t* stats) {
-  const uint32_t es = op == KK_OP_T8_F32_BF16 ? 4u : 2u;
-  if (op != KK_OP_T8_F32_BF16 && op != KK_OP_T8_F16_BF16 && op != KK_OP_T8_B16) return -1;
-  if (nr > KK_T8_ROWS || nc * es > KK_T8_ROW_BYTES) return 5;
+  const bool t8 = op == KK_OP_T8_F32_BF16 || op == KK_OP_T8_F16_BF16 || op == KK_OP_T8_B16;
+  const bool tw = op == KK_OP_TW_F32_BF16 || op == KK_OP_TW_F16_BF16 || op == KK_OP_TW_B16;
+  if (!t8 && !tw) return -1;
+  const uint32_t es = (op == KK_OP_T8_F32_BF16 || op == KK_OP_TW_F32_BF16) ? 4u : 2u;
+  if (t8 && (nr > KK_T8_ROWS || nc * es > KK_T8_ROW_BYTES)) return 5;
+  if (tw && (nr > KK_TW_ROWS || nc * es > KK_TW_ROW_BYTES)) return 5;
   static thread_local uint8_t stage[KK_TILE_SRC_BYTES + KK_STAGE_PAD];
   memset(stage, 0xEE, sizeof stage);
-  uint32_t pitch = nc * es;
-  std::vector<uint8_t> mask(dst_bytes / 2 + 1, 0);
+  uint32_t pitch = tw ? KK_TW_PITCH : nc * es;
+  std::vector<uint8_t> mask(dst_bytes / 2 + 1, 0), bmask(dst_bytes + 1, 0);
   memset(hits, 0, (dst_bytes + 15) / 16);
   g = Emu{};
   g.tile = stage; g.wtile = stage; g.tile_bytes = sizeof stage; g.out = dst; g.out_bytes = dst_bytes; g.hits = hits; g.out_mask = mask.data();
+  g.byte_mask = bmask.data();
   const Dsts D{0};
   const int nthreads = kConsumerWarps * 32;
   if (staged) {
     for (uint32_t r = 0; r < nr; ++r) memcpy(stage + r * pitch, src + (uint64_t)r * C * es, (size_t)nc * es);
   } else {
-    pitch = (pitch + 3u) & ~3u;
+    if (t8) pitch = (pitch + 3u) & ~3u;
     for (int t = 0; t < nthreads; ++t) {
       if (es == 4) t8_gather<4>(src, 0, pitch, nr, nc, C, t);
       else t8_gather<2>(src, 0, pitch, nr, nc, C, t);
@@ -293,14 +301,23 @@ extern "C" int kk_emul_t8_tile(uint32_t op, const uint8_t* src, uint32_t C, uint
     // (the kernel has a named barrier here)
   }
   std::vector<std::vector<uint32_t>> traces((size_t)nthreads);
+  std::vector<std::vector<uint64_t>> straces((size_t)nthreads);
   for (int t = 0; t < nthreads; ++t) {
     g.trace = &traces[(size_t)t];
-    if (op == KK_OP_T8_F32_BF16) consume_t8<4, 1>(D, 0, pitch, nr, nc, R, col0, row0, 0, t);
-    else if (op == KK_OP_T8_F16_BF16) consume_t8<2, 2>(D, 0, pitch, nr, nc, R, col0, row0, 0, t);
-    else consume_t8<2, 0>(D, 0, pitch, nr, nc, R, col0, row0, 0, t);
+    g.strace = &straces[(size_t)t];
+    const int cwarp = t >> 5, lane = t & 31;
+    switch (op) {
+      case KK_OP_T8_F32_BF16: consume_t8<4, 1>(D, 0, pitch, nr, nc, R, col0, row0, 0, t); break;
+      case KK_OP_T8_F16_BF16: consume_t8<2, 2>(D, 0, pitch, nr, nc, R, col0, row0, 0, t); break;
+      case KK_OP_T8_B16: consume_t8<2, 0>(D, 0, pitch, nr, nc, R, col0, row0, 0, t); break;
+      case KK_OP_TW_F32_BF16: consume_tw<4, 1>(D, 0, pitch, nr, nc, R, col0, row0, 0, cwarp, lane); break;
+      case KK_OP_TW_F16_BF16: consume_tw<2, 2>(D, 0, pitch, nr, nc, R, col0, row0, 0, cwarp, lane); break;
+      default: consume_tw<2, 0>(D, 0, pitch, nr, nc, R, col0, row0, 0, cwarp, lane); break;
+    }
   }
   g.trace = nullptr;
-  uint64_t wavefronts = 0, ideal = 0;
+  g.strace = nullptr;
+  uint64_t wavefronts = 0, ideal = 0, st_instr = 0, st_lines = 0, st_sectors = 0;
   for (int w = 0; w < kConsumerWarps; ++w) {
     size_t longest = 0;
     for (int l = 0; l < 32; ++l) longest = std::max(longest, traces[(size_t)(32 * w + l)].size());
@@ -321,8 +338,24 @@ extern "C" int kk_emul_t8_tile(uint32_t op, const uint8_t* src, uint32_t C, uint
       wavefronts += worst;
       ideal += 1;
     }
+    longest = 0;
+    for (int l = 0; l < 32; ++l) longest = std::max(longest, straces[(size_t)(32 * w + l)].size());
+    for (size_t k = 0; k < longest; ++k) {  // likewise the k-th 16-byte store
+      std::vector<uint64_t> lines, sectors;
+      for (int l = 0; l < 32; ++l) {
+        const auto& tr = straces[(size_t)(32 * w + l)];
+        if (k >= tr.size()) continue;
+        const uint64_t ln = tr[k] >> 7, sc = tr[k] >> 5;
+        if (std::find(lines.begin(), lines.end(), ln) == lines.end()) lines.push_back(ln);
+        if (std::find(sectors.begin(), sectors.end(), sc) == sectors.end()) sectors.push_back(sc);
+      }
+      if (lines.empty()) continue;
+      st_instr += 1;
+      st_lines += lines.size();
+      st_sectors += sectors.size();
+    }
   }
-  if (stats) { stats[0] = wavefronts; stats[1] = ideal; }
+  if (stats) { stats[0] = wavefronts; stats[1] = ideal; stats[2] = st_instr; stats[3] = st_lines; stats[4] = st_sectors; }
   return g.err;
 }
 

@@ -11,7 +11,7 @@ import numpy as np
 from oracle import oracle
 
 OP_COPY, OP_F32, OP_F16, OP_Q4K, OP_T_F32_BF16, OP_T_F16_BF16, OP_T_B16, OP_T_B32, OP_Q8_0, OP_Q6K, OP_ROWSPLIT = range(11)
-OP_Q4_0, OP_Q4_1, OP_Q5_0, OP_Q5_1, OP_Q2K, OP_Q3K, OP_Q5K, OP_F8E4M3, OP_F8E5M2, OP_T8_F32_BF16, OP_T8_F16_BF16, OP_T8_B16, OP_IQ4NL, OP_IQ4XS, OP_MXFP4 = range(11, 26)
+OP_Q4_0, OP_Q4_1, OP_Q5_0, OP_Q5_1, OP_Q2K, OP_Q3K, OP_Q5K, OP_F8E4M3, OP_F8E5M2, OP_T8_F32_BF16, OP_T8_F16_BF16, OP_T8_B16, OP_IQ4NL, OP_IQ4XS, OP_MXFP4, OP_TW_F32_BF16, OP_TW_F16_BF16, OP_TW_B16 = range(11, 29)
 # block-dequantising ops: op -> (source bytes per block, bf16 bytes per block, blocks per tile)   (csrc/kk_ops.h kk_block_geom)
 BLOCK_GEOM = {OP_Q4K: (144, 512, 224), OP_Q8_0: (34, 64, 960), OP_Q6K: (210, 512, 152), OP_Q4_0: (18, 64, 1816), OP_Q4_1: (20, 64, 1632),
               OP_Q5_0: (22, 64, 1488), OP_Q5_1: (24, 64, 1360), OP_Q2K: (84, 512, 388), OP_Q3K: (110, 512, 296), OP_Q5K: (176, 512, 186),
@@ -49,7 +49,8 @@ def emulate_part(plan: dict, part: int, pool_bytes: int, exchange: dict | None =
                     src_bytes = BLOCK_GEOM[op][0] * u
                 else:
                     src_bytes = {OP_COPY: u, OP_F32: 4 * u, OP_F16: 2 * u, OP_ROWSPLIT: u, OP_F8E4M3: u, OP_F8E5M2: u,
-                                 OP_T8_F32_BF16: 4 * u * sg["p0"], OP_T8_F16_BF16: 2 * u * sg["p0"], OP_T8_B16: 2 * u * sg["p0"], OP_T_F32_BF16: 4 * u * sg["p0"], OP_T_B32: 4 * u * sg["p0"],
+                                 OP_T8_F32_BF16: 4 * u * sg["p0"], OP_T8_F16_BF16: 2 * u * sg["p0"], OP_T8_B16: 2 * u * sg["p0"],
+                                 OP_TW_F32_BF16: 4 * u * sg["p0"], OP_TW_F16_BF16: 2 * u * sg["p0"], OP_TW_B16: 2 * u * sg["p0"], OP_T_F32_BF16: 4 * u * sg["p0"], OP_T_B32: 4 * u * sg["p0"],
                                  OP_T_F16_BF16: 2 * u * sg["p0"], OP_T_B16: 2 * u * sg["p0"]}[op]
                 assert so + src_bytes <= ch["buf_bytes"], "segment reads past the bytes staged for its chunk"
                 assert covered[so:so + src_bytes].all(), "segment consumes bytes no read put there"
@@ -88,11 +89,11 @@ def emulate_part(plan: dict, part: int, pool_bytes: int, exchange: dict | None =
                     tiles += -(-u // tb)
                 else:
                     C, R, r0 = sg["p0"], sg["p1"], sg["p2"]
-                    es = 4 if op in (OP_T_F32_BF16, OP_T_B32, OP_T8_F32_BF16) else 2
+                    es = 4 if op in (OP_T_F32_BF16, OP_T_B32, OP_T8_F32_BF16, OP_TW_F32_BF16) else 2
                     src = buf[so:so + u * C * es].reshape(u, C, es)
-                    if op in (OP_T_F32_BF16, OP_T8_F32_BF16):
+                    if op in (OP_T_F32_BF16, OP_T8_F32_BF16, OP_TW_F32_BF16):
                         v = oracle.f32_bits_to_bf16(src.reshape(-1).copy().view("<u4")).view(np.uint8).reshape(u, C, 2)
-                    elif op in (OP_T_F16_BF16, OP_T8_F16_BF16):
+                    elif op in (OP_T_F16_BF16, OP_T8_F16_BF16, OP_TW_F16_BF16):
                         v = oracle.f16_bits_to_bf16(src.reshape(-1).copy().view("<u2")).view(np.uint8).reshape(u, C, 2)
                     else:
                         v = src
@@ -103,6 +104,9 @@ def emulate_part(plan: dict, part: int, pool_bytes: int, exchange: dict | None =
                     if op in (OP_T8_F32_BF16, OP_T8_F16_BF16, OP_T8_B16):
                         assert R % 8 == 0 and r0 % 8 == 0, "8-row tiles need 16-byte aligned destination groups"
                         tiles += -(-u // 8) * -(-C // (4096 // es))
+                    elif op in (OP_TW_F32_BF16, OP_TW_F16_BF16, OP_TW_B16):
+                        assert R % 8 == 0 and r0 % 8 == 0, "wide-store tiles need 16-byte aligned destination groups"
+                        tiles += -(-u // 32) * -(-C // (960 // es))
                     else:
                         tiles += -(-u // 32) * -(-C // 128)
                     continue

@@ -31,7 +31,7 @@ def emul():
     L.kk_emul_dequant_tile.restype = C.c_int
     L.kk_emul_dequant_segment.argtypes = [C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
     L.kk_emul_dequant_segment.restype = C.c_int
-    L.kk_emul_t8_tile.argtypes = [C.c_uint32, C.c_void_p] + [C.c_uint32] * 6 + [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]
+    L.kk_emul_t8_tile.argtypes = [C.c_uint32, C.c_void_p] + [C.c_uint32] * 6 + [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]  # T8 and TW ops
     L.kk_emul_t8_tile.restype = C.c_int
     L.kk_emul_block_geom.argtypes = [C.c_uint32] + [C.POINTER(C.c_uint32)] * 3
     L.kk_emul_block_geom.restype = None
@@ -127,6 +127,7 @@ def test_fp8_widening_every_byte_value_every_alignment_and_tail(emul, dtype, op,
 
 
 T8 = {"F32": (helpers.OP_T8_F32_BF16, 4), "F16": (helpers.OP_T8_F16_BF16, 2), "BF16": (helpers.OP_T8_B16, 2)}
+TW = {"F32": (helpers.OP_TW_F32_BF16, 4), "F16": (helpers.OP_TW_F16_BF16, 2), "BF16": (helpers.OP_TW_B16, 2)}
 
 
 def t8_expected(dtype, src_rc):
@@ -140,91 +141,72 @@ def t8_expected(dtype, src_rc):
     return np.ascontiguousarray(v.T)
 
 
+def run_transpose_tile(emul, op, es, dtype, nr, nc, R, row0, staged, seed=21):
+    """One tile placed inside a bigger tensor (C_total x R destination): values vs the oracle, every destination element of the tile
+    written exactly once and nothing else touched.  Returns the emulator's statistics."""
+    rng = np.random.default_rng(seed)
+    udt = np.uint32 if es == 4 else np.uint16
+    Cs = nc + 24  # the tile is a window of a wider source tensor
+    col0 = 8
+    if dtype == "BF16":
+        src = rng.integers(0, 1 << 16, (nr, Cs), dtype=np.uint64).astype(udt)
+    else:
+        src = synth.gen_bytes(dtype, nr * Cs * es, 3, nr + nc).view(udt).reshape(nr, Cs)
+    c_total = col0 + nc + 3
+    dst = np.full(c_total * R, 0xCDCD, np.uint16)
+    hits = np.zeros((dst.nbytes + 15) // 16, np.uint8)
+    stats = (C.c_uint64 * 5)()
+    win = np.ascontiguousarray(src)  # element (0, 0) of the window is src[0, 0]; only the first nc columns belong to the tile
+    rc = emul.kk_emul_t8_tile(op, win.ctypes.data, Cs, nr, nc, R, col0, row0, staged, dst.ctypes.data, dst.nbytes, hits.ctypes.data, stats)
+    assert rc == 0, f"{dtype} {nr}x{nc}: {ERR.get(rc, rc)}"
+    want = np.full((c_total, R), 0xCDCD, np.uint16)
+    want[col0:col0 + nc, row0:row0 + nr] = t8_expected(dtype, win[:, :nc])
+    assert (dst.reshape(c_total, R) == want).all(), (dtype, nr, nc, R, row0)
+    m = np.zeros((c_total, R), bool)
+    m[col0:col0 + nc, row0:row0 + nr] = True
+    per16 = np.add.reduceat(np.repeat(m.reshape(-1), 2).astype(np.uint8), np.arange(0, dst.nbytes, 16))
+    assert (hits == per16).all(), "bytes stored per 16-byte unit differ from the tile's footprint"
+    return list(stats)
+
+
 @pytest.mark.parametrize("dtype", sorted(T8))
 @pytest.mark.parametrize("staged", [1, 0])
 def test_t8_transpose_tiles_values_write_once_and_bank_conflicts(emul, dtype, staged):
-    """8-row transpose tiles: a tile placed inside a bigger tensor (C_total x R destination), full width, ragged width, fewer
-    than 8 rows, destination rows that defeat the 16-byte store (R % 8 != 0) — values vs the oracle, every destination element
-    of the tile written exactly once and nothing else touched.  Staged full tiles must read shared memory conflict-free."""
+    """8-row transpose tiles: full width, ragged width, fewer than 8 rows, destination rows that defeat the 16-byte store
+    (R % 8 != 0).  Staged full tiles must read shared memory conflict-free."""
     op, es = T8[dtype]
     W = 4096 // es
-    rng = np.random.default_rng(21)
-    udt = np.uint32 if es == 4 else np.uint16
     cases = [(8, W, 768, 0), (8, W, 768, 16), (8, 768, 3072, 8), (8, 40, 24, 0), (5, 72, 64, 8), (8, 129 if not staged else 136, 20, 0), (8, 16, 36, 4), (1, 8, 8, 0)]
     for nr, nc, R, row0 in cases:
         if staged and (nc * es) % 16:
             continue
-        Cs = nc + 24  # the tile is a window of a wider source tensor
-        col0 = 8
-        if dtype == "BF16":
-            src = rng.integers(0, 1 << 16, (nr, Cs), dtype=np.uint64).astype(udt)
-        else:
-            src = synth.gen_bytes(dtype, nr * Cs * es, 3, nr + nc).view(udt).reshape(nr, Cs)
-        c_total = col0 + nc + 3
-        dst = np.full(c_total * R, 0xCDCD, np.uint16)
-        hits = np.zeros((dst.nbytes + 15) // 16, np.uint8)
-        stats = (C.c_uint64 * 2)()
-        win = np.ascontiguousarray(src)  # element (0, 0) of the window is src[0, 0]; only the first nc columns belong to the tile
-        rc = emul.kk_emul_t8_tile(op, win.ctypes.data, Cs, nr, nc, R, col0, row0, staged, dst.ctypes.data, dst.nbytes, hits.ctypes.data, stats)
-        assert rc == 0, f"{dtype} {nr}x{nc}: {ERR.get(rc, rc)}"
-        want = np.full((c_total, R), 0xCDCD, np.uint16)
-        want[col0:col0 + nc, row0:row0 + nr] = t8_expected(dtype, win[:, :nc])
-        assert (dst.reshape(c_total, R) == want).all(), (dtype, nr, nc, R, row0)
-        touched = np.zeros(dst.nbytes, np.uint8)
-        m = np.zeros((c_total, R), bool)
-        m[col0:col0 + nc, row0:row0 + nr] = True
-        per16 = np.add.reduceat(np.repeat(m.reshape(-1), 2).astype(np.uint8), np.arange(0, dst.nbytes, 16))
-        assert (hits == per16).all(), "bytes stored per 16-byte unit differ from the tile's footprint"
+        st = run_transpose_tile(emul, op, es, dtype, nr, nc, R, row0, staged)
         if staged and nr == 8 and nc % 32 == 0:
-            assert stats[0] == stats[1], f"{dtype} {nr}x{nc}: {stats[0]} shared-memory wavefronts for {stats[1]} warp loads"
-        del touched
+            assert st[0] == st[1], f"{dtype} {nr}x{nc}: {st[0]} shared-memory wavefronts for {st[1]} warp loads"
 
 
-def _run_elementwise(emul, op, src_bytes, n_units, pay_off, out_bytes):
-    tile = np.full(pay_off + src_bytes.size, 0x5A, np.uint8)
-    tile[pay_off:] = src_bytes
-    out = np.zeros(out_bytes, np.uint8)
-    hits = np.zeros((out_bytes + 15) // 16, np.uint8)
-    rc = emul.kk_emul_dequant_tile(op, tile.ctypes.data, tile.size, pay_off, n_units, out.ctypes.data, out.size, hits.ctypes.data)
-    assert rc == 0, ERR.get(rc, rc)
-    want_hits = np.full(hits.size, 16, np.uint8)
-    if out_bytes % 16:
-        want_hits[-1] = out_bytes % 16
-    assert (hits == want_hits).all(), "every output byte stored exactly once"
-    return out
-
-
-def test_copy_and_casts_register_paths_every_alignment_and_tail(emul):
-    """The non-TMA consumer paths of the headline ops: COPY (misaligned / ragged tiles), F32 -> bf16 and F16 -> bf16 — aligned vector
-    loads and byte-assembled ones, counts that end inside a 16-byte group, a full 32 KiB tile."""
-    rng = np.random.default_rng(4)
-    for n in (1, 15, 16, 17, 255, 8191 * 4 + 3, 32768):
-        src = rng.integers(0, 256, n, dtype=np.uint8)
-        for pay_off in (0, 1, 4, 8, 15):
-            if pay_off + n > 32768 + 128:
-                continue
-            assert (_run_elementwise(emul, helpers.OP_COPY, src, n, pay_off, n) == src).all(), ("COPY", n, pay_off)
-    for n in (1, 7, 8, 9, 513, 8192):
-        f32 = synth.gen_bytes("F32", 4 * n, 6, n)
-        f32[:4 * min(n, 4)] = np.array([0x7F800000, 0xFF800001, 0x3F808000, 0x00000001], "<u4").view(np.uint8)[:4 * min(n, 4)]  # inf, NaN, tie, subnormal
-        f16 = synth.gen_bytes("F16", 2 * n, 7, n)
-        for pay_off in (0, 2, 4, 6, 8, 12) + ((1, 3) if n < 600 else ()):
-            got = _run_elementwise(emul, helpers.OP_F32, f32, n, pay_off, 2 * n).view(np.uint16)
-            assert (got == oracle.f32_bits_to_bf16(f32.view("<u4"))).all(), ("F32", n, pay_off)
-            got = _run_elementwise(emul, helpers.OP_F16, f16, n, pay_off, 2 * n).view(np.uint16)
-            assert (got == oracle.f16_bits_to_bf16(f16.view("<u2"))).all(), ("F16", n, pay_off)
-
-
-def test_q4k_shuffle_emulation_is_live(emul):
-    """Q4_K is the one consumer whose lanes trade values (__shfl_sync, emulated by record/replay): swapping two sub-block scale bytes
-    of one block must change exactly that block's output."""
-    blocks = synth.gen_bytes("Q4_K", 144 * 9, 2, 1).reshape(9, 144)
-    base = run_tile(emul, "Q4_K", blocks, 0)
-    mut = blocks.copy()
-    mut[5, 4], mut[5, 5] = blocks[5, 5] ^ 0x15, blocks[5, 4] ^ 0x2A
-    got = run_tile(emul, "Q4_K", mut, 0)
-    assert (got == oracle.dequant_bf16("Q4_K", mut)).all()
-    assert (got[5] != base[5]).any() and (np.delete(got, 5, 0) == np.delete(base, 5, 0)).all()
+@pytest.mark.parametrize("dtype", sorted(TW))
+@pytest.mark.parametrize("staged", [1, 0])
+def test_tw_wide_store_tiles_values_write_once_conflicts_and_store_width(emul, dtype, staged):
+    """32-row wide-store tiles: same checks, plus what the geometry is for — on a full tile every warp store instruction writes whole
+    64-byte segments (8 lines, 16 sectors for its 32 lanes) where the 8-row tiles touch 32 lines with 32 half-filled sectors."""
+    op, es = TW[dtype]
+    W = 960 // es
+    cases = [(32, W, 768, 0), (32, W, 768, 32), (32, 128, 3072, 64), (32, 40, 40, 0), (13, 72, 64, 8), (24, 16, 48, 8), (32, 16, 36, 4), (1, 8, 8, 0), (32, 8, 32, 0)]
+    for nr, nc, R, row0 in cases:
+        if staged and (nc * es) % 16:
+            continue
+        st = run_transpose_tile(emul, op, es, dtype, nr, nc, R, row0, staged)
+        if nr == 32 and nc % 8 == 0 and R % 8 == 0 and row0 % 8 == 0:
+            assert st[0] == st[1], f"{dtype} {nr}x{nc}: {st[0]} shared-memory wavefronts for {st[1]} warp loads"
+            if R % 64 == 0 and row0 % 64 == 0:
+                assert st[3] == 8 * st[2] and st[4] == 16 * st[2], st
+    # the comparison the two candidates are about, on a GPT-2 sized destination row (R = 768): store transactions per output byte
+    t8 = run_transpose_tile(emul, T8[dtype][0], es, dtype, 8, 4096 // es, 768, 0, 1)
+    tw = run_transpose_tile(emul, op, es, dtype, 32, W, 768, 0, 1)
+    t8_lines_per_kb = t8[3] / (8 * (4096 // es) * 2 / 1024)
+    tw_lines_per_kb = tw[3] / (32 * W * 2 / 1024)
+    assert tw_lines_per_kb * 3.9 < t8_lines_per_kb, (t8, tw)
 
 
 def test_harness_sees_wrong_answers(emul):

@@ -185,17 +185,18 @@ def test_gpt2_conv1d_transpose(native, tmp_path):
     run_case(p, flags=gpupool.LOAD_GPT2_CONV1D_T, mode=gpupool.MODE_BROADCAST, n_parts=2, chunk=1 * MB)
 
 
-def test_gpt2_conv1d_transpose_on_8_row_tiles(native, tmp_path):
-    """KK_LOAD_T8_TILES: same pools, different tiling — 8-row ops wherever the destination row length is a multiple of 8, the 32x128
-    ops elsewhere (d = 43: R = 43, 129, 172 are not)."""
-    T = gpupool.LOAD_GPT2_CONV1D_T | gpupool.LOAD_T8_TILES
-    t8 = {helpers.OP_T8_F32_BF16, helpers.OP_T8_F16_BF16, helpers.OP_T8_B16}
+@pytest.mark.parametrize("geom", ["t8", "tw"])
+def test_gpt2_conv1d_transpose_on_candidate_tiles(native, tmp_path, geom):
+    """KK_LOAD_T8_TILES / KK_LOAD_TW_TILES: same pools, different tiling — the candidate ops wherever the destination row length is a
+    multiple of 8, the 32x128 ops elsewhere (d = 43: R = 43, 129, 172 are not)."""
+    T = gpupool.LOAD_GPT2_CONV1D_T | (gpupool.LOAD_T8_TILES if geom == "t8" else gpupool.LOAD_TW_TILES)
+    cand = {"t8": {helpers.OP_T8_F32_BF16, helpers.OP_T8_F16_BF16, helpers.OP_T8_B16}, "tw": {helpers.OP_TW_F32_BF16, helpers.OP_TW_F16_BF16, helpers.OP_TW_B16}}[geom]
     old = {helpers.OP_T_F32_BF16, helpers.OP_T_F16_BF16, helpers.OP_T_B16, helpers.OP_T_B32}
     p = str(tmp_path / "gpt2.safetensors")
     synth.make_gpt2(p, n_layer=2, d=96, vocab=301, n_pos=40)
     plan = run_case(p, flags=T, chunk=1 * MB)
     ops = {sg["op"] for ch in plan["parts"][0]["chunks"] for sg in ch["segs"]}
-    assert ops & t8 and not ops & old
+    assert ops & cand and not ops & old
     base = gpupool.plan_describe(p, flags=gpupool.LOAD_GPT2_CONV1D_T, chunk_bytes=1 * MB)
     assert plan["layouts"] == base["layouts"], "the tile geometry must not move anything in the pool"
     run_case(p, flags=T, mode=gpupool.MODE_BROADCAST, n_parts=3, chunk=1 * MB)
@@ -206,7 +207,10 @@ def test_gpt2_conv1d_transpose_on_8_row_tiles(native, tmp_path):
         synth.write_safetensors(q, synth.gpt2_tensors(n_layer=1, d=d, vocab=50, n_pos=8, dtype=dt), 3)
         plan = run_case(q, flags=T, chunk=1 * MB)
         ops = {sg["op"] for ch in plan["parts"][0]["chunks"] for sg in ch["segs"]}
-        assert (ops & t8) if d % 8 == 0 else (ops & old and not ops & t8), (dt, d, ops)
+        assert (ops & cand) if d % 8 == 0 else (ops & old and not ops & cand), (dt, d, ops)
+    # both flags: the wide-store tiles take precedence
+    plan = gpupool.plan_describe(p, flags=gpupool.LOAD_GPT2_CONV1D_T | gpupool.LOAD_T8_TILES | gpupool.LOAD_TW_TILES, chunk_bytes=1 * MB)
+    assert {sg["op"] for ch in plan["parts"][0]["chunks"] for sg in ch["segs"]} & {helpers.OP_TW_F32_BF16}
 
 
 def test_gpt2_f16_and_bf16_transpose(native, tmp_path):

@@ -31,7 +31,7 @@ def inventories(draw):
 
 
 @settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
-@given(inv=inventories(), mode=st.sampled_from([0, 1, 2]), n_parts=st.integers(1, 8), flags=st.sampled_from([0, 1, 2, 3, 8, 9, 16, 19, 24, 33, 35, 49]),
+@given(inv=inventories(), mode=st.sampled_from([0, 1, 2]), n_parts=st.integers(1, 8), flags=st.sampled_from([0, 1, 2, 3, 8, 9, 16, 19, 24, 33, 35, 49, 65, 67]),
        pad=st.booleans(), chunk_mb=st.sampled_from([1, 2]))
 def test_random_inventories_plan_to_the_oracle_pool(native, inv, mode, n_parts, flags, pad, chunk_mb):
     if mode == 0:
@@ -42,7 +42,7 @@ def test_random_inventories_plan_to_the_oracle_pool(native, inv, mode, n_parts, 
         shards, recs = oracle.index_path(p)
         assert gpupool.index(p) == recs
         plan = gpupool.plan_describe(p, mode=mode, flags=flags, n_parts=n_parts, chunk_bytes=chunk_mb << 20)
-        oflags = flags & (3 | 16)  # the oracle knows GPT2_CONV1D_T, KEEP_F32 and F8_TO_BF16; SCATTER_EXCHANGE and T8_TILES change the route, not the result
+        oflags = flags & (3 | 16)  # the oracle knows GPT2_CONV1D_T, KEEP_F32 and F8_TO_BF16; SCATTER_EXCHANGE, T8_TILES and TW_TILES change the route, not the result
         if mode == 2:
             exps = [oracle.expected_pool(shards, recs, 2, oflags, n_parts, g) for g in range(n_parts)]
             ex = {g: (np.zeros(len(exps[g][0]), np.uint8), np.zeros(len(exps[g][0]), bool)) for g in range(n_parts)}

@@ -114,9 +114,11 @@ def test_fp8_safetensors_verbatim_by_default_and_widened_on_request(pool, tmp_pa
 
 # ---- KK_LOAD_T8_TILES: the candidate 8-row transpose geometry (first hardware run, like the quant types above) ----------------------
 T8 = gpupool.LOAD_GPT2_CONV1D_T | gpupool.LOAD_T8_TILES
+TW = gpupool.LOAD_GPT2_CONV1D_T | gpupool.LOAD_TW_TILES
 
 
-def test_t8_gpt2_every_dtype_and_odd_shapes(pool, tmp_path):
+@pytest.mark.parametrize("T8", [T8, TW], ids=["t8", "tw"])
+def test_t8_gpt2_every_dtype_and_odd_shapes(pool, tmp_path, T8):
     """Same pools as the 32x128 tiles, bit for bit vs the oracle: GPT-2 shaped (R = 96..384: staged path, whole-row tiles of one bulk
     copy), rows wider than one tile (d = 1032: 4128-byte f32 rows -> two tiles per row group), 16-bit sources, shapes whose R is
     not a multiple of 8 (planner keeps the 32x128 ops), and an unpadded header (rows off 16-byte alignment -> gather fallback)."""
@@ -133,7 +135,8 @@ def test_t8_gpt2_every_dtype_and_odd_shapes(pool, tmp_path):
         load_and_check(pool, q, flags=T8)
 
 
-def test_t8_full_size_gpt2_matches_the_32x128_tiles(pool, tmp_path):
+@pytest.mark.parametrize("T8", [T8, TW], ids=["t8", "tw"])
+def test_t8_full_size_gpt2_matches_the_32x128_tiles(pool, tmp_path, T8):
     """GPT-2-small at full size (0.5 GB): checksum of every tensor equal between the two tile geometries and equal to the oracle."""
     p = str(tmp_path / "gpt2_full.safetensors")
     synth.make_gpt2(p)
@@ -157,7 +160,8 @@ def test_t8_full_size_gpt2_matches_the_32x128_tiles(pool, tmp_path):
         b.release()
 
 
-def test_t8_virtual_rank_fan_out(pool, tmp_path):
+@pytest.mark.parametrize("T8", [T8, TW], ids=["t8", "tw"])
+def test_t8_virtual_rank_fan_out(pool, tmp_path, T8):
     """The 8-row tiles through the n-destination store ladder (broadcast to 4 virtual ranks on one GPU)."""
     from tests.test_gpu_load import _virtual_ranks
     f = str(tmp_path / "gpt2.safetensors")

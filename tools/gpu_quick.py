@@ -66,6 +66,8 @@ def main():
         q = os.path.join(d, "gpt2w.safetensors")
         synth.write_safetensors(q, synth.gpt2_tensors(n_layer=1, d=1032, vocab=50, n_pos=8, dtype="F32"), 3)
         check("8-row tiles, rows wider than one tile (d=1032)", q, flags=gpupool.LOAD_GPT2_CONV1D_T | gpupool.LOAD_T8_TILES)
+        check("GPT-2 transposes, 32-row wide-store tiles", p, flags=gpupool.LOAD_GPT2_CONV1D_T | gpupool.LOAD_TW_TILES)
+        check("32-row wide-store tiles, d=1032", q, flags=gpupool.LOAD_GPT2_CONV1D_T | gpupool.LOAD_TW_TILES)
         # KK_FANOUT_PULL with 4 virtual ranks on this GPU
         try:
             ld = os.path.join(d, "llama")

@@ -1,4 +1,4 @@
-"""Torch-free A/B of the two transpose tile geometries on GPT-2-small (resident image, CUDA-event timed inside the library)."""
+"""Torch-free A/B of the transpose tile geometries on GPT-2-small (resident image, CUDA-event timed inside the library)."""
 import json
 import os
 import sys
@@ -17,7 +17,8 @@ with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") els
     nbytes = synth.make_gpt2(p)
     out["synth_s"] = time.time() - t0
     pool = gpupool.Pool([0])
-    for name, flags in (("tiles_32x128", gpupool.LOAD_GPT2_CONV1D_T), ("tiles_8row", gpupool.LOAD_GPT2_CONV1D_T | gpupool.LOAD_T8_TILES)):
+    for name, flags in (("tiles_32x128", gpupool.LOAD_GPT2_CONV1D_T), ("tiles_8row", gpupool.LOAD_GPT2_CONV1D_T | gpupool.LOAD_T8_TILES),
+                        ("tiles_32row_wide_store", gpupool.LOAD_GPT2_CONV1D_T | gpupool.LOAD_TW_TILES)):
         m = pool.load(p, flags=flags | gpupool.LOAD_DEFER)
         try:
             m.stage_resident()
@@ -33,6 +34,7 @@ with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") els
             m.release()
     pool.close()
 out["speedup"] = out["tiles_32x128"]["ms_median"] / out["tiles_8row"]["ms_median"]
+out["speedup_wide_store"] = out["tiles_32x128"]["ms_median"] / out["tiles_32row_wide_store"]["ms_median"]
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "t8_ab.json"), "w"), indent=1)
 print(json.dumps(out))
