@@ -1,5 +1,7 @@
-// Block dequantisers of kk_convert_kernel's consumer warps (every GGUF block type except Q4_K, whose four-blocks-per-
-// warp variant trades lanes through __shfl_sync and lives in kk_kernels.cu).
+// Consumer bodies of kk_convert_kernel, part 2 (part 1 — copy, casts, Q4_K — is kk_consume_core.cuh):
+//   * block dequantisers of every other GGUF type: Q8_0, Q6_K, Q4_0, Q4_1, Q5_0, Q5_1, Q2_K, Q3_K, Q5_K, IQ4_NL, IQ4_XS, MXFP4;
+//   * the FP8 -> bf16 widening (safetensors F8_E4M3 / F8_E5M2, opt-in);
+//   * the two candidate transpose geometries (8-row tiles, 32-row wide-store tiles) and their gather fallback.
 //
 // Each function is written from the point of view of ONE lane and touches nothing but the primitives below, which the
 // including translation unit provides:
@@ -22,8 +24,8 @@
 // write-once checks) and runs all 16 x 32 lanes in a loop, so the lane -> element index arithmetic of exactly this source
 // is checked against the oracle on the CPU test tier.  That harness is test infrastructure: the product has no CPU path.
 //
-// Lane mapping, same for every type: a lane produces 8 consecutive weights = one 16-byte bf16 store; a warp iteration
-// produces 512 contiguous output bytes (256-weight super-blocks: one block; 32-weight blocks: eight blocks).
+// Lane mapping of the dequantisers, same for every type: a lane produces 8 consecutive weights = one 16-byte bf16 store; a warp
+// iteration produces 512 contiguous output bytes (256-weight super-blocks: one block; 32-weight blocks: eight blocks).
 #pragma once
 #include "kk_consume_core.cuh"  // lds32_bytes, to_bf16
 #include "kk_ops.h"
