@@ -45,6 +45,15 @@ KK_DQ_DEV void store_bf16x8(const Dsts& D, uint64_t off, const float (&y)[8]) {
   store16_all(D, off, make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7])));
 }
 
+// Byte k (0..3) of w minus BIAS as an exact float, without I2F: PRMT builds 0x4B0000bb = 2^23 + b, one FADD takes off 2^23 + BIAS.
+// Every dequantiser below first assembles four small UNSIGNED values per 32-bit word (SIMD-in-word), then calls this per element.
+template <int BIAS>
+KK_DQ_DEV float byte_to_float(uint32_t w, int k) {
+  return __fsub_rn(kk_bits2f(kk_byte_perm(w, 0x4B000000u, 0x7440u | (uint32_t)k)), 8388608.0f + (float)BIAS);
+}
+// bits 0..3 of x -> bit 0 of bytes 0..3 (the multiplier's four set bits are 7 apart, so no partial products overlap)
+KK_DQ_DEV uint32_t spread4(uint32_t x) { return ((x & 0xFu) * 0x00204081u) & 0x01010101u; }
+
 // Q8_0 block (34 B): d f16 | qs[32] int8 -> 32 bf16, y = q * d in fp32 (gguf/quants.py Q8_0.dequantize_blocks).
 // Lane l of a warp handles elements 8*(l&3)..+8 of block (l>>2): 8 blocks and 512 contiguous output bytes per iteration.
 KK_DQ_DEV void consume_q8_0(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
@@ -54,13 +63,10 @@ KK_DQ_DEV void consume_q8_0(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t
       const uint32_t blk = pay + b * KK_Q8_0_BLOCK_BYTES;
       const float d = kk_h2f(lds16_any(blk));
       const uint32_t qa = blk + 2u + 8u * (uint32_t)(lane & 3);
-      const uint32_t q0 = lds32_h(qa), q1 = lds32_h(qa + 4);
+      const uint32_t q0 = lds32_h(qa) ^ 0x80808080u, q1 = lds32_h(qa + 4) ^ 0x80808080u;  // int8 -> value + 128, unsigned
       float y[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int q = (int)(signed char)(((e < 4 ? q0 : q1) >> (8 * (e & 3))) & 0xFFu);
-        y[e] = __fmul_rn((float)q, d);
-      }
+      for (int e = 0; e < 8; ++e) y[e] = __fmul_rn(byte_to_float<128>(e < 4 ? q0 : q1, e & 3), d);
       store16_all(D, dst_off + (uint64_t)b * 64u + (uint32_t)(lane & 3) * 16u,
                   make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7])));
     }
@@ -83,15 +89,12 @@ KK_DQ_DEV void consume_q6k(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t 
     const float dsc = __fmul_rn(d, (float)sc);
     const uint32_t l0 = lds32_h(blk + ql_off), l1 = lds32_h(blk + ql_off + 4);
     const uint32_t h0 = lds32_h(blk + qh_off), h1 = lds32_h(blk + qh_off + 4);
+    // four 6-bit values per word: low nibble | high two bits << 4 (q + 32, unsigned)
+    const uint32_t w0 = ((l0 >> lsh) & 0x0F0F0F0Fu) | (((h0 >> hsh) & 0x03030303u) << 4);
+    const uint32_t w1 = ((l1 >> lsh) & 0x0F0F0F0Fu) | (((h1 >> hsh) & 0x03030303u) << 4);
     float y[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const uint32_t lw = e < 4 ? l0 : l1, hw = e < 4 ? h0 : h1;
-      const uint32_t lo = (lw >> (8 * (e & 3) + lsh)) & 0xFu;
-      const uint32_t hi = (hw >> (8 * (e & 3) + hsh)) & 0x3u;
-      const int q = (int)(lo | (hi << 4)) - 32;
-      y[e] = __fmul_rn(dsc, (float)q);
-    }
+    for (int e = 0; e < 8; ++e) y[e] = __fmul_rn(dsc, byte_to_float<32>(e < 4 ? w0 : w1, e & 3));
     store16_all(D, dst_off + (uint64_t)b * 512u + (uint32_t)lane * 16u,
                 make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7])));
   }
@@ -119,16 +122,18 @@ KK_DQ_DEV void consume_legacy32(const Dsts& D, uint32_t pay, uint32_t nblk, uint
       const uint32_t blk = pay + b * BYTES;
       const float d = lds_f16(blk);
       const float m = HAS_M ? lds_f16(blk + 2u) : 0.f;
-      const uint32_t q0 = (lds32_any(blk + q_off) >> nsh) & 0x0F0F0F0Fu;
-      const uint32_t q1 = (lds32_any(blk + q_off + 4u) >> nsh) & 0x0F0F0F0Fu;
-      const uint32_t hbits = HAS_QH ? ((lds32_any(blk + kQhOff) >> e0) & 0xFFu) : 0u;
+      uint32_t q0 = (lds32_any(blk + q_off) >> nsh) & 0x0F0F0F0Fu;
+      uint32_t q1 = (lds32_any(blk + q_off + 4u) >> nsh) & 0x0F0F0F0Fu;
+      if (HAS_QH) {  // bit 4 of element e0 + k is bit k of this byte of qh
+        const uint32_t hbits = (lds32_any(blk + kQhOff) >> e0) & 0xFFu;
+        q0 |= spread4(hbits) << 4;
+        q1 |= spread4(hbits >> 4) << 4;
+      }
       float y[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        int q = (int)(((e < 4 ? q0 : q1) >> (8 * (e & 3))) & 0xFu);
-        if (HAS_QH) q |= (int)((hbits >> e) & 1u) << 4;
-        if (HAS_M) y[e] = __fadd_rn(__fmul_rn(d, (float)q), m);
-        else y[e] = __fmul_rn(d, (float)(q - (HAS_QH ? 16 : 8)));
+        if (HAS_M) y[e] = __fadd_rn(__fmul_rn(d, byte_to_float<0>(e < 4 ? q0 : q1, e & 3)), m);
+        else y[e] = __fmul_rn(d, byte_to_float<(HAS_QH ? 16 : 8)>(e < 4 ? q0 : q1, e & 3));
       }
       store_bf16x8(D, dst_off + (uint64_t)b * 64u + (uint32_t)(lane & 3) * 16u, y);
     }
@@ -152,10 +157,7 @@ KK_DQ_DEV void consume_q2k(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t 
     const uint32_t q1 = (lds32_any(blk + q_off + 4u) >> sh) & 0x03030303u;
     float y[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const uint32_t q = ((e < 4 ? q0 : q1) >> (8 * (e & 3))) & 0x3u;
-      y[e] = __fsub_rn(__fmul_rn(dl, (float)q), ml);
-    }
+    for (int e = 0; e < 8; ++e) y[e] = __fsub_rn(__fmul_rn(dl, byte_to_float<0>(e < 4 ? q0 : q1, e & 3)), ml);
     store_bf16x8(D, dst_off + (uint64_t)b * 512u + (uint32_t)lane * 16u, y);
   }
 }
@@ -176,17 +178,12 @@ KK_DQ_DEV void consume_q3k(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t 
     const uint32_t lo4 = (lds8(blk + lo_off) >> lo_sh) & 0xFu;
     const uint32_t hi2 = (lds8(blk + hi_off) >> hi_sh) & 0x3u;
     const float dl = __fmul_rn(d, (float)((int)(lo4 | (hi2 << 4)) - 32));
-    const uint32_t q0 = (lds32_any(blk + q_off) >> sh) & 0x03030303u;
-    const uint32_t q1 = (lds32_any(blk + q_off + 4u) >> sh) & 0x03030303u;
-    const uint32_t h0 = (lds32_any(blk + i0) >> g) & 0x01010101u;
-    const uint32_t h1 = (lds32_any(blk + i0 + 4u) >> g) & 0x01010101u;
+    // q = low - 4 when the mask bit is clear = (low | maskbit << 2) - 4: four 3-bit values per word, bias 4
+    const uint32_t w0 = ((lds32_any(blk + q_off) >> sh) & 0x03030303u) | (((lds32_any(blk + i0) >> g) & 0x01010101u) << 2);
+    const uint32_t w1 = ((lds32_any(blk + q_off + 4u) >> sh) & 0x03030303u) | (((lds32_any(blk + i0 + 4u) >> g) & 0x01010101u) << 2);
     float y[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int lo = (int)(((e < 4 ? q0 : q1) >> (8 * (e & 3))) & 0x3u);
-      const int set = (int)(((e < 4 ? h0 : h1) >> (8 * (e & 3))) & 0x1u);
-      y[e] = __fmul_rn(dl, (float)(lo - ((set ^ 1) << 2)));
-    }
+    for (int e = 0; e < 8; ++e) y[e] = __fmul_rn(dl, byte_to_float<4>(e < 4 ? w0 : w1, e & 3));
     store_bf16x8(D, dst_off + (uint64_t)b * 512u + (uint32_t)lane * 16u, y);
   }
 }
@@ -213,16 +210,11 @@ KK_DQ_DEV void consume_q5k(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t 
     }
     const float dsc = __fmul_rn(d, (float)sc);
     const float dmn = __fmul_rn(dmin, (float)mn);
-    const uint32_t q0 = (lds32_any(blk + q_off) >> nsh) & 0x0F0F0F0Fu;
-    const uint32_t q1 = (lds32_any(blk + q_off + 4u) >> nsh) & 0x0F0F0F0Fu;
-    const uint32_t h0 = (lds32_any(blk + 16u + i0) >> j) & 0x01010101u;
-    const uint32_t h1 = (lds32_any(blk + 16u + i0 + 4u) >> j) & 0x01010101u;
+    const uint32_t w0 = ((lds32_any(blk + q_off) >> nsh) & 0x0F0F0F0Fu) | (((lds32_any(blk + 16u + i0) >> j) & 0x01010101u) << 4);
+    const uint32_t w1 = ((lds32_any(blk + q_off + 4u) >> nsh) & 0x0F0F0F0Fu) | (((lds32_any(blk + 16u + i0 + 4u) >> j) & 0x01010101u) << 4);
     float y[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const uint32_t q = (((e < 4 ? q0 : q1) >> (8 * (e & 3))) & 0xFu) | ((((e < 4 ? h0 : h1) >> (8 * (e & 3))) & 0x1u) << 4);
-      y[e] = __fsub_rn(__fmul_rn(dsc, (float)q), dmn);
-    }
+    for (int e = 0; e < 8; ++e) y[e] = __fsub_rn(__fmul_rn(dsc, byte_to_float<0>(e < 4 ? w0 : w1, e & 3)), dmn);
     store_bf16x8(D, dst_off + (uint64_t)b * 512u + (uint32_t)lane * 16u, y);
   }
 }
@@ -320,11 +312,12 @@ KK_DQ_DEV void t8_gather(const uint8_t* src, uint32_t sbase, uint32_t pitch, uin
 // The 16-entry tables live in four registers each; a lookup is one PRMT over a register pair picked by bit 3 of the index.
 template <int TABLE>  // 0: IQ4_NL values, 1: MXFP4 (e2m1 x 2)
 KK_DQ_DEV float lut16(uint32_t idx) {
-  // little-endian packing of {-127,-104,-83,-65, -49,-35,-22,-10, 1,13,25,38, 53,69,89,113} and {0,1,2,3, 4,6,8,12, 0,-1,-2,-3, -4,-6,-8,-12}
-  constexpr uint32_t K0 = TABLE ? 0x03020100u : 0xBFAD9881u, K1 = TABLE ? 0x0C080604u : 0xF6EADDCFu;
-  constexpr uint32_t K2 = TABLE ? 0xFDFEFF00u : 0x26190D01u, K3 = TABLE ? 0xF4F8FAFCu : 0x71594535u;
+  // little-endian packing of {-127,-104,-83,-65, -49,-35,-22,-10, 1,13,25,38, 53,69,89,113} and {0,1,2,3, 4,6,8,12, 0,-1,-2,-3, -4,-6,-8,-12},
+  // every entry + 128 so that the bytes are unsigned and the second PRMT + FADD (byte_to_float<128>) yields the signed value
+  constexpr uint32_t K0 = (TABLE ? 0x03020100u : 0xBFAD9881u) ^ 0x80808080u, K1 = (TABLE ? 0x0C080604u : 0xF6EADDCFu) ^ 0x80808080u;
+  constexpr uint32_t K2 = (TABLE ? 0xFDFEFF00u : 0x26190D01u) ^ 0x80808080u, K3 = (TABLE ? 0xF4F8FAFCu : 0x71594535u) ^ 0x80808080u;
   const uint32_t b = (idx & 8u) ? kk_byte_perm(K2, K3, idx & 7u) : kk_byte_perm(K0, K1, idx & 7u);
-  return (float)(int)(signed char)(b & 0xFFu);
+  return byte_to_float<128>(b, 0);
 }
 // 32-weight codebook blocks: lane l takes elements 8(l&3)..+8 of block (l>>2), eight blocks per warp iteration (as consume_legacy32).
 template <uint32_t BYTES, int TABLE>
