@@ -8,7 +8,10 @@
 #define KK_STAGE_PAD 128u        /* slack so a 16-B-aligned superset of a misaligned tile still fits */
 #define KK_Q4K_BLOCK_BYTES 144u
 #define KK_Q4K_BLOCK_ELEMS 256u
+#ifndef KK_Q4K_TILE_BLOCKS        /* overridable for A/B builds: 16 consumer warps x 4 blocks = 64 blocks per sweep, so 224 = 3.5 sweeps (half the
+                                     warps idle in the last one) against 192 = 3 full sweeps of a smaller tile */
 #define KK_Q4K_TILE_BLOCKS 224u  /* 224*144 = 32256 B in, 224*512 = 114688 B out */
+#endif
 #define KK_Q8_0_BLOCK_BYTES 34u
 #define KK_Q8_0_BLOCK_ELEMS 32u
 #define KK_Q8_0_TILE_BLOCKS 960u /* 960*34 = 32640 B in (a multiple of 16), 960*64 = 61440 B out */
