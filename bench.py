@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="llama3-8b", choices=["llama3-8b", "mixtral-q4k", "gpt2", "llama3-70b-scatter"])
+    ap.add_argument("--qtype", default="Q4_K", help="mixtral-q4k: block type of the weights (Q4_K = the BASELINE config; Q4_0, Q5_K, IQ4_XS, ... "
+                    "measure the other dequantisers at the same shapes)")
     ap.add_argument("--layers", type=int, default=0, help="override the layer count (reported in config; 0 = full size)")
     ap.add_argument("--data-dir", default="")
     ap.add_argument("--keep-data", action="store_true")
@@ -94,8 +96,10 @@ def workload_spec(args):
         return dict(kind="llama", cfg=cfg, tensors=t, name=name, mode="scatter")
     if args.workload == "mixtral-q4k":
         kw = dict(layers=args.layers) if args.layers else {}
-        t = synth.mixtral_gguf_tensors(**kw)
-        name = "Mixtral-8x7B GGUF q4_K -> bf16" + (f" (REDUCED to {args.layers} layers)" if args.layers else "")
+        if args.qtype not in synth.GGML or synth.GGML[args.qtype][1] == 1:
+            raise SystemExit(f"--qtype {args.qtype}: not a block-quantised GGUF type this tool can write")
+        t = synth.mixtral_gguf_tensors(qtype=args.qtype, **kw)
+        name = f"Mixtral-8x7B GGUF {args.qtype.lower()} -> bf16" + (f" (REDUCED to {args.layers} layers)" if args.layers else "")
         return dict(kind="gguf", tensors=t, name=name, mode="broadcast")
     t = synth.gpt2_tensors()
     return dict(kind="gpt2", tensors=t, name="GPT-2-small f32 safetensors", mode="broadcast")
@@ -506,7 +510,8 @@ def main():
     tf = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tf):
         try:
-            ratio = json.load(open(tf)).get(args.workload, {}).get("ratio")
+            key = args.workload if (args.workload != "mixtral-q4k" or args.qtype == "Q4_K") else None  # the capture is of the Q4_K kernel only
+            ratio = json.load(open(tf)).get(key, {}).get("ratio") if key else None
             traffic = ratio * alg_per_launch if ratio and world == 1 else None
         except Exception:  # noqa: BLE001
             traffic = None

@@ -163,18 +163,20 @@ def gpt2_tensors(n_layer: int = 12, d: int = 768, vocab: int = 50257, n_pos: int
     return t
 
 
-def mixtral_gguf_tensors(hidden: int = 4096, ffn: int = 14336, layers: int = 32, experts: int = 8, vocab: int = 32000, kv_dim: int = 1024):
-    """llama.cpp naming, merged experts: 10*layers + 3 tensors. Shapes outermost-first."""
-    t = [("token_embd.weight", "Q4_K", [vocab, hidden])]
+def mixtral_gguf_tensors(hidden: int = 4096, ffn: int = 14336, layers: int = 32, experts: int = 8, vocab: int = 32000, kv_dim: int = 1024,
+                         qtype: str = "Q4_K"):
+    """llama.cpp naming, merged experts: 10*layers + 3 tensors. Shapes outermost-first.
+    qtype: block type of the 2-D weights (Q4_K is the BASELINE config; the others measure the remaining dequantisers at the same shapes)."""
+    t = [("token_embd.weight", qtype, [vocab, hidden])]
     for i in range(layers):
         p = f"blk.{i}."
-        t += [(p + "attn_norm.weight", "F32", [hidden]), (p + "attn_q.weight", "Q4_K", [hidden, hidden]),
-              (p + "attn_k.weight", "Q4_K", [kv_dim, hidden]), (p + "attn_v.weight", "Q4_K", [kv_dim, hidden]),
-              (p + "attn_output.weight", "Q4_K", [hidden, hidden]), (p + "ffn_norm.weight", "F32", [hidden]),
+        t += [(p + "attn_norm.weight", "F32", [hidden]), (p + "attn_q.weight", qtype, [hidden, hidden]),
+              (p + "attn_k.weight", qtype, [kv_dim, hidden]), (p + "attn_v.weight", qtype, [kv_dim, hidden]),
+              (p + "attn_output.weight", qtype, [hidden, hidden]), (p + "ffn_norm.weight", "F32", [hidden]),
               (p + "ffn_gate_inp.weight", "F32", [experts, hidden]),
-              (p + "ffn_gate_exps.weight", "Q4_K", [experts, ffn, hidden]), (p + "ffn_up_exps.weight", "Q4_K", [experts, ffn, hidden]),
-              (p + "ffn_down_exps.weight", "Q4_K", [experts, hidden, ffn])]
-    t += [("output_norm.weight", "F32", [hidden]), ("output.weight", "Q4_K", [vocab, hidden])]
+              (p + "ffn_gate_exps.weight", qtype, [experts, ffn, hidden]), (p + "ffn_up_exps.weight", qtype, [experts, ffn, hidden]),
+              (p + "ffn_down_exps.weight", qtype, [experts, hidden, ffn])]
+    t += [("output_norm.weight", "F32", [hidden]), ("output.weight", qtype, [vocab, hidden])]
     return t
 
 
