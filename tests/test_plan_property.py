@@ -67,3 +67,54 @@ def test_random_inventories_plan_to_the_oracle_pool(native, inv, mode, n_parts, 
                 cover += mask
             assert (cover == helpers.expected_mask(pl, len(exp)).astype(np.int32)).all()
             assert (acc == exp).all()
+
+
+GG_TYPES = ["F32", "F16", "BF16", "Q4_0", "Q4_1", "Q5_0", "Q5_1", "Q8_0", "Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K", "IQ4_NL", "IQ4_XS", "MXFP4"]
+GG_NAMES = ["attn_q.weight", "attn_output.weight", "ffn_up.weight", "ffn_down.weight", "attn_norm.weight", "ffn_gate_exps.weight", "misc.weight"]
+
+
+@st.composite
+def gguf_inventories(draw):
+    n = draw(st.integers(1, 6))
+    out = []
+    for i in range(n):
+        dt = draw(st.sampled_from(GG_TYPES))
+        blk = synth.GGML[dt][1]
+        nd = draw(st.integers(1, 3))
+        inner = blk * draw(st.sampled_from([1, 2, 3, 8])) if blk > 1 else draw(st.sampled_from([1, 3, 8, 40, 130]))
+        shape = [draw(st.sampled_from([1, 2, 3, 4, 8, 12])) for _ in range(nd - 1)] + [inner]
+        out.append((f"blk.{i}.{draw(st.sampled_from(GG_NAMES))}", dt, shape))
+    return out
+
+
+@settings(max_examples=50, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@given(inv=gguf_inventories(), mode=st.sampled_from([0, 1, 2]), n_parts=st.integers(1, 8), alignment=st.sampled_from([8, 32, 64]), chunk_mb=st.sampled_from([1, 2]))
+def test_random_gguf_inventories_plan_to_the_oracle_pool(native, inv, mode, n_parts, alignment, chunk_mb):
+    """Every block-quantised type the kernel dequantises, at random shapes / file alignments / modes / rank counts: index == oracle,
+    layouts == oracle, and replaying the planned reads + segments with the oracle's arithmetic reproduces the oracle's pools."""
+    if mode == 0:
+        n_parts = 1
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "m.gguf")
+        synth.write_gguf(p, inv, seed=6, alignment=alignment)
+        shards, recs = oracle.index_path(p)
+        assert gpupool.index(p) == recs
+        plan = gpupool.plan_describe(p, mode=mode, n_parts=n_parts, chunk_bytes=chunk_mb << 20)
+        if mode == 2:
+            for g in range(n_parts):
+                exp, pl = oracle.expected_pool(shards, recs, 2, 0, n_parts, g)
+                assert plan["layouts"][g]["pool_bytes"] == len(exp)
+                got, mask = helpers.emulate_part(plan, g, len(exp))
+                assert (mask == helpers.expected_mask(pl, len(exp))).all()
+                assert (got == exp).all()
+        else:
+            exp, pl = oracle.expected_pool(shards, recs, mode, 0)
+            assert plan["layouts"][0]["pool_bytes"] == len(exp)
+            acc = np.zeros(len(exp), np.uint8)
+            cover = np.zeros(len(exp), np.int32)
+            for g in range(n_parts):
+                got, mask = helpers.emulate_part(plan, g, len(exp))
+                acc[mask] = got[mask]
+                cover += mask
+            assert (cover == helpers.expected_mask(pl, len(exp)).astype(np.int32)).all()
+            assert (acc == exp).all()
