@@ -515,7 +515,18 @@ def main():
             traffic = ratio * alg_per_launch if ratio and world == 1 else None
         except Exception:  # noqa: BLE001
             traffic = None
+    # HBM-write roofline: bytes WRITTEN per launch against what a store-only kernel sustains on this box, measured now.
+    # A probe failure must never fail the bench: the keys are null then.
+    write_peak = copy_probe = None
+    if world == 1 and not args.kernel_only:
+        try:
+            write_peak = max(pool.probe_hbm(local, gpupool.PROBE_WRITE, 4 << 30) for _ in range(3))
+            copy_probe = max(pool.probe_hbm(local, gpupool.PROBE_COPY, 2 << 30) for _ in range(3))
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] HBM probe failed: {e}", file=sys.stderr)
     roofline = {"bound": "hbm", "kernel": "kk_convert_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "write_peak_GBps": write_peak, "ldst_copy_probe_GBps": copy_probe,
+                "hbm_write_frac": ((part["out_bytes"] / max(n_launch, 1)) / (avg_launch_ms / 1e3) / 1e9 / write_peak) if write_peak and avg_launch_ms > 0 else None,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_per_launch, "avg_launch_ms": avg_launch_ms,
                 "launches_per_step": n_launch,
                 "write_only_frac_of_peak": (part["out_bytes"] / max(n_launch, 1)) / (avg_launch_ms / 1e3) / 1e9 / peak if avg_launch_ms > 0 else 0.0}

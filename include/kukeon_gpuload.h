@@ -264,6 +264,14 @@ int kk_stage_resident(kk_model* m);
 int kk_convert_resident(kk_model* m, float* ms_total, float* ms_per_launch, size_t cap, size_t* n_launches);
 int kk_unstage_resident(kk_model* m);
 
+/* ---- Roofline probes (measurement only) ------------------------------------------------------- */
+/* Time one launch of a probe kernel over a scratch buffer of `nbytes` (rounded down to 16) on `device`, after one untimed warm-up launch,
+ * with CUDA events on the launching stream.  kind KK_PROBE_WRITE: store-only fill (the HBM-write roofline a conversion's output is
+ * measured against); KK_PROBE_COPY: plain ld.global / st.global copy of nbytes (reads nbytes, writes nbytes). */
+#define KK_PROBE_WRITE 0
+#define KK_PROBE_COPY 1
+int kk_probe_hbm(kk_ctx* ctx, int device, int kind, uint64_t nbytes, float* ms);
+
 #ifdef __cplusplus
 }
 #endif

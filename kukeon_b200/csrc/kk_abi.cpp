@@ -399,5 +399,44 @@ int kk_unstage_resident(kk_model* m) {
   });
 }
 
+int kk_probe_hbm(kk_ctx* ctx, int device, int kind, uint64_t nbytes, float* ms) {
+  return guard([&] {
+    need(ctx, "ctx");
+    need(ms, "ms");
+    *ms = 0.f;
+    if (kind != KK_PROBE_WRITE && kind != KK_PROBE_COPY) kk::fail(KK_EINVAL, "unknown probe kind %d", kind);
+    kk::Device* d = nullptr;
+    for (auto& x : ctx->devs)
+      if (x.ordinal == device) d = &x;
+    if (!d) kk::fail(KK_EINVAL, "device %d is not part of this context", device);
+    nbytes &= ~(uint64_t)15;
+    if (nbytes == 0) kk::fail(KK_EINVAL, "probe needs at least 16 bytes");
+    KK_CUDA(cudaSetDevice(device));
+    struct Buf {
+      void* p = nullptr;
+      ~Buf() { if (p) cudaFree(p); }
+    } dst, src;
+    struct Ev {
+      cudaEvent_t e = nullptr;
+      ~Ev() { if (e) cudaEventDestroy(e); }
+    } e0, e1;
+    if (cudaMalloc(&dst.p, nbytes) != cudaSuccess) { cudaGetLastError(); kk::fail(KK_ENOMEM, "device %d: cudaMalloc(%llu) for the probe failed", device, (unsigned long long)nbytes); }
+    if (kind == KK_PROBE_COPY) {
+      if (cudaMalloc(&src.p, nbytes) != cudaSuccess) { cudaGetLastError(); kk::fail(KK_ENOMEM, "device %d: cudaMalloc(%llu) for the probe failed", device, (unsigned long long)nbytes); }
+      KK_CUDA(cudaMemsetAsync(src.p, 0x3C, nbytes, d->stream));
+    }
+    KK_CUDA(cudaEventCreate(&e0.e));
+    KK_CUDA(cudaEventCreate(&e1.e));
+    for (int pass = 0; pass < 2; ++pass) {  // pass 0 warms up (first touch of the scratch pages), pass 1 is timed
+      if (pass) KK_CUDA(cudaEventRecord(e0.e, d->stream));
+      if (kind == KK_PROBE_WRITE) KK_CUDA(kk::launch_fill((uint8_t*)dst.p, nbytes, d->sm_count, d->stream));
+      else KK_CUDA(kk::launch_ldg_copy((const uint8_t*)src.p, (uint8_t*)dst.p, nbytes, d->sm_count, d->stream));
+      if (pass) KK_CUDA(cudaEventRecord(e1.e, d->stream));
+    }
+    KK_CUDA(cudaStreamSynchronize(d->stream));
+    KK_CUDA(cudaEventElapsedTime(ms, e0.e, e1.e));
+  });
+}
+
 }  // extern "C"
 #pragma GCC visibility pop

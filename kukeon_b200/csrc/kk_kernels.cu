@@ -708,6 +708,16 @@ __global__ void __launch_bounds__(256) kk_ldg_copy_kernel(const uint4* __restric
   for (; i < nvec; i += stride) __stcs(dst + i, __ldcs(src + i));
 }
 
+// Store-only probe: what the box's HBM sustains when a kernel does nothing but write (the "HBM-write roofline" of SURVEY.md §8(d)).
+__global__ void __launch_bounds__(256) kk_fill_kernel(uint4* __restrict__ dst, uint64_t nvec, uint4 v) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < nvec; i += 4 * stride) {
+    __stcs(dst + i, v); __stcs(dst + i + stride, v); __stcs(dst + i + 2 * stride, v); __stcs(dst + i + 3 * stride, v);
+  }
+  for (; i < nvec; i += stride) __stcs(dst + i, v);
+}
+
 }  // namespace
 
 cudaError_t kernels_init_device() {
@@ -739,4 +749,13 @@ cudaError_t launch_ldg_copy(const uint8_t* src, uint8_t* dst, uint64_t nbytes, i
   return cudaGetLastError();
 }
 
+}  // namespace kk
+
+namespace kk {
+cudaError_t launch_fill(uint8_t* dst, uint64_t nbytes, int sm_count, cudaStream_t stream) {
+  if (nbytes == 0) return cudaSuccess;
+  if ((nbytes & 15) || ((uintptr_t)dst & 15)) return cudaErrorInvalidValue;
+  kk_fill_kernel<<<sm_count * 8, 256, 0, stream>>>(reinterpret_cast<uint4*>(dst), nbytes >> 4, make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u));
+  return cudaGetLastError();
+}
 }  // namespace kk

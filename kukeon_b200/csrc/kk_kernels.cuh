@@ -36,6 +36,9 @@ cudaError_t launch_checksum(const uint8_t* p, uint64_t nbytes, unsigned long lon
 // Plain ld.global.v4 / st.global.v4 copy, kept for A/B measurement against the TMA path.
 cudaError_t launch_ldg_copy(const uint8_t* src, uint8_t* dst, uint64_t nbytes, int sm_count, cudaStream_t stream);
 
+// Store-only probe (no reads): nbytes and dst multiples of 16.
+cudaError_t launch_fill(uint8_t* dst, uint64_t nbytes, int sm_count, cudaStream_t stream);
+
 // One-time per-device function attribute setup (dynamic shared memory opt-in).
 cudaError_t kernels_init_device();
 

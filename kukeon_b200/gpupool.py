@@ -25,6 +25,7 @@ FANOUT_P2P, FANOUT_NVLS, FANOUT_NONE, FANOUT_RAW, FANOUT_PULL = 0, 1, 2, 3, 4
 CFG_ZEROCOPY, CFG_NO_PEER_ACCESS, CFG_NO_NUMA_PIN, CFG_PEER_ALL = 0x1, 0x2, 0x4, 0x8
 LOAD_GPT2_CONV1D_T, LOAD_KEEP_F32, LOAD_DEFER, LOAD_SCATTER_EXCHANGE, LOAD_F8_TO_BF16, LOAD_T8_TILES, LOAD_TW_TILES = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20, 0x40
 BUF_POOL, BUF_RAW, BUF_POOL_PTR, BUF_SLICE, BUF_SLICE_PTR = 0, 1, 2, 3, 4
+PROBE_WRITE, PROBE_COPY = 0, 1
 
 DTYPE_NAMES = {
     0: "BOOL", 1: "F4", 2: "F6_E2M3", 3: "F6_E3M2", 4: "U8", 5: "I8", 6: "F8_E5M2", 7: "F8_E4M3", 8: "F8_E8M0",
@@ -101,7 +102,7 @@ ABI_SYMBOLS = [
     "kk_export_buffer", "kk_peer_attach_buffer", "kk_convert_local",
     "kk_model_get_info", "kk_placements", "kk_model_tensor", "kk_export", "kk_export_size", "kk_pool_ptr",
     "kk_acquire", "kk_release", "kk_stats", "kk_read", "kk_checksum", "kk_stage_resident", "kk_convert_resident",
-    "kk_unstage_resident",
+    "kk_unstage_resident", "kk_probe_hbm",
 ]
 
 
@@ -127,6 +128,7 @@ def lib():
     L.kk_status_name.argtypes = [C.c_int]
     L.kk_open.argtypes = [C.POINTER(KKConfig), C.POINTER(vp)]
     L.kk_close.argtypes = [vp]
+    L.kk_probe_hbm.argtypes = [vp, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_float)]
     L.kk_index.argtypes = [vp, C.c_char_p, C.POINTER(C.POINTER(KKTensorMeta)), C.POINTER(C.c_size_t)]
     L.kk_free_index.argtypes = [C.POINTER(KKTensorMeta)]
     L.kk_index_shard.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
@@ -385,6 +387,14 @@ class Pool:
         h = C.c_void_p()
         _check(lib().kk_load_ex(self._h, os.fsencode(path), C.byref(o), C.byref(h)))
         return Model(self, h.value)
+
+    def probe_hbm(self, device: int, kind: int = 0, nbytes: int = 4 << 30) -> float:
+        """GB/s of one probe launch over `nbytes` of scratch HBM: kind 0 (PROBE_WRITE) store-only — bytes written / time;
+        kind 1 (PROBE_COPY) ld/st copy — bytes read + written / time."""
+        ms = C.c_float()
+        _check(lib().kk_probe_hbm(self._h, device, kind, nbytes, C.byref(ms)))
+        moved = nbytes * (2 if kind == PROBE_COPY else 1)
+        return moved / (ms.value / 1e3) / 1e9 if ms.value > 0 else 0.0
 
     def close(self) -> None:
         if self._h:

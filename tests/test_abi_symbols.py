@@ -46,6 +46,7 @@ def test_null_arguments_are_rejected_not_crashed(native):
     assert native.kk_close(None) == -1
     assert native.kk_release(None) == -1
     assert native.kk_index(None, None, None, None) == -1
+    assert native.kk_probe_hbm(None, 0, 0, 1 << 20, None) == -1
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

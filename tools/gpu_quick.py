@@ -96,6 +96,12 @@ def main():
                     m.release()
         except Exception as e:  # noqa: BLE001
             say(f"ERROR KK_FANOUT_PULL: {e!r}")
+    try:
+        w = max(pool.probe_hbm(0, gpupool.PROBE_WRITE, 4 << 30) for _ in range(3))
+        c = max(pool.probe_hbm(0, gpupool.PROBE_COPY, 2 << 30) for _ in range(3))
+        say(f"INFO HBM probes: store-only {w:.0f} GB/s, ld/st copy {c:.0f} GB/s (read + write)")
+    except Exception as e:  # noqa: BLE001
+        say(f"ERROR HBM probe: {e!r}")
     pool.close()
     say("done")
 
