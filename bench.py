@@ -61,6 +61,8 @@ def parse():
     ap.add_argument("--zerocopy", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nccl-compare", action="store_true", help="also time an NCCL all-gather of the pools (comparison collective)")
+    ap.add_argument("--nvls-compare", action="store_true", help="N > 1: also time the kernel stage with KK_FANOUT_NVLS (multimem.st through the NVSwitch multicast object) "
+                    "against KK_FANOUT_P2P, both in the one-process-all-GPUs shape (rank 0)")
     ap.add_argument("--kernel-only", action="store_true", help="profiling aid: skip the streaming load / e2e legs (every kk_convert launch is a resident one)")
     ap.add_argument("--e2e-only", action="store_true", help="tuning aid: skip the resident kernel leg")
     ap.add_argument("--no-numa-pin", action="store_true")
@@ -627,6 +629,23 @@ def main():
                 sp_ready2 = time.time() - t0
                 st2 = m3.stats()
                 m3.release()
+                if args.nvls_compare and mode == gpupool.MODE_BROADCAST:
+                    cmpres = {}
+                    for label, fo in (("p2p", gpupool.FANOUT_P2P), ("nvls", gpupool.FANOUT_NVLS)):
+                        try:
+                            mc = modelhub.Load(sp, ref2, mode=mode, fanout=fo, flags=spf | gpupool.LOAD_DEFER)
+                            try:
+                                mc.stage_resident()
+                                for _ in range(max(args.warmup, 3)):
+                                    mc.convert_resident()
+                                ts = [mc.convert_resident()[0] for _ in range(args.steps)]
+                                sums = {mc.checksum(dev, 0, mc.info()["pool_bytes"] // 8 * 8) for dev in range(world)}
+                                cmpres[label] = {"ms_per_step": sum(ts) / len(ts), "ms_min": min(ts), "pools_identical": len(sums) == 1}
+                            finally:
+                                mc.release()
+                        except Exception as e:  # noqa: BLE001
+                            cmpres[label] = {"error": str(e)}
+                    line["nvls_compare"] = cmpres
                 sp.close()
                 line["time_to_agent_ready_single_process_s"] = min(sp_ready, sp_ready2)
                 line["single_process"] = {"what": "one process, one kk_ctx over all N GPUs (kukeond's shape): Pull + kk_load(mode) + kk_export x N; pinned ring and peer access set up in kk_open",

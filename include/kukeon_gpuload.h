@@ -82,7 +82,10 @@ typedef enum kk_mode {
 
 typedef enum kk_fanout {
   KK_FANOUT_P2P = 0,  /* convert kernel stores every output vector to all peer-mapped pools (NVLink/NVSwitch) */
-  KK_FANOUT_NVLS = 1, /* multimem.st on an NVLS multicast mapping of the pools (when the host exposes it) */
+  KK_FANOUT_NVLS = 1, /* BROADCAST, one process owning >= 2 devices: the pools are VMM allocations bound to one NVSwitch multicast object and the
+                         convert kernel stores every vector once with multimem.st.  KK_EUNSUPPORTED where the host does not expose NVLS, for
+                         checkpoints with tensors that are not whole 16-byte vectors, and for kk_export's IPC handle (VMM memory has none):
+                         the comparison the north_star names, not the default (an all-gather is ingress-bound either way) */
   KK_FANOUT_NONE = 2, /* local pool only; the caller runs its own collective (e.g. the NCCL comparison) */
   KK_FANOUT_RAW = 3,  /* BROADCAST only: all-gather the *file* bytes (e.g. q4_K blocks, 3.56x smaller than their bf16)
                          into a per-device raw image over NVLink, then every device converts everything locally */

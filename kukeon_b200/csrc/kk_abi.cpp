@@ -185,6 +185,7 @@ int kk_export_buffer(kk_model* m, int device, int which, void* h) {
     need(h, "ipc_handle");
     int li = kk::model_local_device(m, device);
     if (which == KK_BUF_POOL) {
+      if (m->nvls) kk::fail(KK_EUNSUPPORTED, "pools of a KK_FANOUT_NVLS model cannot be exported over CUDA IPC");
       KK_CUDA(cudaSetDevice(device));
       cudaIpcMemHandle_t ih;
       KK_CUDA(cudaIpcGetMemHandle(&ih, m->pools[(size_t)li]));
@@ -296,6 +297,7 @@ int kk_export(kk_model* m, int device, void* ipc_handle_64B, char* manifest_json
       memcpy(manifest_json, s.c_str(), s.size() + 1);
     }
     if (ipc_handle_64B) {
+      if (m->nvls) kk::fail(KK_EUNSUPPORTED, "pools of a KK_FANOUT_NVLS model are VMM allocations: there is no cudaIpcMemHandle for them (export the manifest only, or load with KK_FANOUT_P2P)");
       KK_CUDA(cudaSetDevice(device));
       cudaIpcMemHandle_t h;
       KK_CUDA(cudaIpcGetMemHandle(&h, m->pools[(size_t)li]));

@@ -151,8 +151,8 @@ __device__ __forceinline__ void store16_all(const Dsts& D, uint64_t off, const u
 }
 __device__ __forceinline__ void store2_all(const Dsts& D, uint64_t off, uint16_t v) {
   if (D.multimem) {
-    // multimem.st has no 16-bit form: scalar tails go through a 32-bit read-free path is impossible, so
-    // the host never selects multimem for launches whose segments have sub-4-byte tails (planner rule).
+    // multimem.st has no 8- or 16-bit form: the host only selects KK_LAUNCH_MULTIMEM for plans whose segments never need a
+    // sub-4-byte store (kk_loader.cpp plan_allows_multimem), so this is unreachable there.
     return;
   }
 #pragma unroll

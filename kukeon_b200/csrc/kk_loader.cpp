@@ -201,6 +201,28 @@ void pad_dsts_for_test(ConvertLaunch& L) {
   while (L.n_dst < (uint32_t)want && L.n_dst < KK_MAX_DST) { L.dst[L.n_dst] = L.dst[L.n_dst % have]; L.n_dst++; }
 }
 
+bool is_nvls(const kk_model* m) { return m->opts.fanout == KK_FANOUT_NVLS && m->plan.mode == KK_MODE_BROADCAST && m->nvls; }
+
+// multimem.st exists for 4-, 8- and 16-byte accesses only: a plan qualifies for KK_LAUNCH_MULTIMEM when no segment ever needs a 1- or
+// 2-byte store — every tile of it is whole 16-byte output vectors.  (Block dequantisers and the FP8/F16/F32 casts of whole groups
+// always are; verbatim copies need a multiple of 16 bytes; transposes store single elements at tile edges and are excluded.)
+bool plan_allows_multimem(const Plan& P, std::string* why) {
+  for (auto& pp : P.parts)
+    for (auto& s : pp.segs) {
+      bool ok;
+      switch (s.op) {
+        case KK_OP_COPY: case KK_OP_F8E4M3_BF16: case KK_OP_F8E5M2_BF16: ok = s.units % 16 == 0; break;
+        case KK_OP_F32_BF16: case KK_OP_F16_BF16: ok = s.units % 8 == 0; break;
+        default: ok = kk_block_geom(s.op).block_bytes != 0; break;
+      }
+      if (!ok) {
+        if (why) *why = "a tensor's size is not a whole number of 16-byte output vectors (or the load transposes); multimem.st cannot store its tail";
+        return false;
+      }
+    }
+  return true;
+}
+
 bool is_pull(const kk_model* m) { return m->opts.fanout == KK_FANOUT_PULL && m->plan.mode == KK_MODE_BROADCAST; }
 
 // Pool bytes [lo, hi) that plan part `part` produces.  Pool order equals file order, so for every op that writes its output
@@ -246,6 +268,12 @@ void fill_dsts(kk_model* m, int li, ConvertLaunch& L) {
       L.xdst[j] = p;
     }
     L.n_xdst = (uint32_t)n;
+  }
+  if (is_nvls(m)) {  // one multimem.st per vector reaches every pool through the switch
+    L.dst[0] = m->nvls->multicast();
+    L.n_dst = 1;
+    L.flags |= KK_LAUNCH_MULTIMEM;
+    return;
   }
   if (is_pull(m)) {  // stage 1 of a pull load: the same bytes into the slice buffer the peers will read (pool offset -> slice_buf - slice_base)
     if (m->slice_buf) L.dst[L.n_dst++] = (uint8_t*)((uintptr_t)m->slice_buf - (uintptr_t)m->slice_base);
@@ -606,12 +634,13 @@ void destroy_model(kk_model* m) {
     Device& d = c->devs[(size_t)m->dev_idx[i]];
     cudaSetDevice(d.ordinal);
     if (m->pools[i]) {
-      cudaFree(m->pools[i]);
+      if (!m->nvls) cudaFree(m->pools[i]);  // NVLS pools are unmapped / released by ~NvlsPools below
       std::lock_guard<std::mutex> g(c->mu);  // model_load checks the budget under the same lock
       d.pool_in_use -= m->pool_bytes[i];
     }
     if (i < m->d_segs.size() && m->d_segs[i]) cudaFree(m->d_segs[i]);
   }
+  m->nvls.reset();
   delete m;
 }
 
@@ -788,8 +817,15 @@ kk_model* model_load(kk_ctx* c, const std::string& path, const kk_load_opts& opt
     fail(KK_EINVAL, "part %d of %d out of range", opts.part_index, opts.part_count);
   if (opts.mode < KK_MODE_SINGLE || opts.mode > KK_MODE_SCATTER) fail(KK_EINVAL, "unknown mode %d", opts.mode);
   if (opts.fanout < KK_FANOUT_P2P || opts.fanout > KK_FANOUT_PULL) fail(KK_EINVAL, "unknown fanout %d", opts.fanout);
-  if (opts.fanout == KK_FANOUT_NVLS)
-    fail(KK_EUNSUPPORTED, "fan-out NVLS is not available in this build (an all-gather is ingress-bound either way; see DESIGN.md)");
+  if (opts.fanout == KK_FANOUT_NVLS) {
+    // every "cannot do NVLS here" is KK_EUNSUPPORTED (the contract since the first ABI version), whatever the reason
+    if (opts.mode != KK_MODE_BROADCAST) fail(KK_EUNSUPPORTED, "fan-out NVLS only applies to KK_MODE_BROADCAST");
+    if (opts.part_count > 1) fail(KK_EUNSUPPORTED, "fan-out NVLS needs one process owning all devices (sharing a multicast object across processes is not implemented)");
+    if (c->cfg.n_devices < 2) fail(KK_EUNSUPPORTED, "fan-out NVLS needs at least two devices in the context");
+    std::vector<int> ords(c->cfg.devices, c->cfg.devices + c->cfg.n_devices);
+    std::string why;
+    if (!NvlsPools::supported(ords, &why)) fail(KK_EUNSUPPORTED, "fan-out NVLS: this host does not expose it: %s", why.c_str());
+  }
   if (opts.fanout == KK_FANOUT_RAW && opts.mode != KK_MODE_BROADCAST) fail(KK_EINVAL, "KK_FANOUT_RAW only applies to KK_MODE_BROADCAST");
   const bool multi_proc = opts.part_count > 1;
   if (opts.fanout == KK_FANOUT_PULL && opts.mode != KK_MODE_BROADCAST) fail(KK_EINVAL, "KK_FANOUT_PULL only applies to KK_MODE_BROADCAST");
@@ -843,6 +879,14 @@ kk_model* model_load(kk_ctx* c, const std::string& path, const kk_load_opts& opt
     m->pools.assign(m->dev_idx.size(), nullptr);
     m->pool_bytes.assign(m->dev_idx.size(), 0);
     m->d_segs.assign(m->dev_idx.size(), nullptr);
+    if (opts.fanout == KK_FANOUT_NVLS) {
+      std::string why;
+      if (!plan_allows_multimem(m->plan, &why)) fail(KK_EUNSUPPORTED, "fan-out NVLS: %s", why.c_str());
+      std::vector<int> ords;
+      for (int di : m->dev_idx) ords.push_back(c->devs[(size_t)di].ordinal);
+      m->nvls.reset(new NvlsPools);
+      m->nvls->create(ords, m->plan.pool_bytes_of_part(0));
+    }
     for (size_t li = 0; li < m->dev_idx.size(); ++li) {
       Device& d = c->devs[(size_t)m->dev_idx[li]];
       KK_CUDA(cudaSetDevice(d.ordinal));
@@ -855,7 +899,9 @@ kk_model* model_load(kk_ctx* c, const std::string& path, const kk_load_opts& opt
         d.pool_in_use += pb;
         m->pool_bytes[li] = pb;
       }
-      cudaError_t e = cudaMalloc((void**)&m->pools[li], pb);
+      cudaError_t e = cudaSuccess;
+      if (m->nvls) m->pools[li] = m->nvls->pool(li);  // already allocated, bound and mapped
+      else e = cudaMalloc((void**)&m->pools[li], pb);
       if (e != cudaSuccess) {
         cudaGetLastError();
         m->pools[li] = nullptr;

@@ -12,6 +12,7 @@
 
 #include "kk_common.hpp"
 #include "kk_kernels.cuh"
+#include "kk_nvls.hpp"
 #include "kk_plan.hpp"
 
 namespace kk {
@@ -104,6 +105,9 @@ struct kk_model {
   void* peer_slice_ptr[KK_MAX_DEVICES] = {};
   bool peer_slice_is_ipc[KK_MAX_DEVICES] = {};
   bool raw_staged = false;                      // stage 1 complete on this process since the last conversion
+  // KK_FANOUT_NVLS (one process, >= 2 devices): the pools are VMM allocations bound to one multicast object; pools[i] then
+  // aliases nvls->pool(i) and must not be cudaFree'd
+  std::unique_ptr<kk::NvlsPools> nvls;
   // state
   std::mutex op_mu;  // serialises the data-moving calls on ONE model (kk_load_part, kk_convert_local, kk_*_resident) against each other
   int refcount = 0;

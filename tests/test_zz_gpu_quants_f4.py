@@ -299,3 +299,49 @@ def test_pull_one_process_per_gpu_over_ipc(native, tmp_path):
     os.makedirs(out)
     mp.spawn(_pull_rank_main, args=(world, _free_port(), d, out), nprocs=world, join=True)
     assert sorted(os.listdir(out)) == [f"ok{r}" for r in range(world)]
+
+
+# ---- KK_FANOUT_NVLS: multimem.st through an NVSwitch multicast object (one process, >= 2 GPUs; skipped where the host has no NVLS) --------
+@pytest.mark.multigpu
+def test_nvls_broadcast_single_process(native, tmp_path):
+    import torch
+    ngpu = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = min(ngpu, 8)
+    d = str(tmp_path / "llama")
+    synth.make_llama(d, dict(hidden=256, ffn=704, layers=3, kv_dim=64, vocab=3000), max_shard_bytes=3_000_000)
+    g = str(tmp_path / "mix.gguf")
+    synth.write_gguf(g, synth.mixtral_gguf_tensors(hidden=256, ffn=768, layers=2, experts=2, vocab=512, kv_dim=256), 7)
+    odd = str(tmp_path / "odd.safetensors")
+    synth.write_safetensors(odd, [("a", "BF16", [7])], 1)  # 14 bytes: not a whole 16-byte vector
+    with gpupool.Pool(list(range(n)), n_staging_buffers=4, staging_buffer_bytes=1 * MB, n_reader_threads=2) as pl:
+        try:
+            m = pl.load(d, mode=gpupool.MODE_BROADCAST, fanout=gpupool.FANOUT_NVLS)
+        except gpupool.ErrUnsupported as e:
+            pytest.skip(f"host does not expose NVLS: {e}")
+        try:
+            shards, recs = oracle.index_path(d)
+            for dev in range(n):
+                assert_pool_matches(m, dev, shards, recs)
+            assert len({m.checksum(dev, 0, m.info()["pool_bytes"] // 8 * 8) for dev in range(n)}) == 1
+            with pytest.raises(gpupool.ErrUnsupported, match="cudaIpcMemHandle"):
+                m.export(0)
+            m.stage_resident()
+            m.convert_resident()
+            for dev in range(n):
+                assert_pool_matches(m, dev, shards, recs)
+        finally:
+            m.release()
+        m = pl.load(g, mode=gpupool.MODE_BROADCAST, fanout=gpupool.FANOUT_NVLS)
+        try:
+            shards, recs = oracle.index_path(g)
+            for dev in range(n):
+                assert_pool_matches(m, dev, shards, recs)
+        finally:
+            m.release()
+        with pytest.raises(gpupool.ErrUnsupported, match="16-byte"):
+            pl.load(odd, mode=gpupool.MODE_BROADCAST, fanout=gpupool.FANOUT_NVLS)
+    with gpupool.Pool([0], n_staging_buffers=2, staging_buffer_bytes=1 * MB, n_reader_threads=1) as one:
+        with pytest.raises(gpupool.ErrUnsupported, match="at least two devices"):
+            one.load(d, mode=gpupool.MODE_BROADCAST, fanout=gpupool.FANOUT_NVLS)
