@@ -884,6 +884,7 @@ kk_model* model_load(kk_ctx* c, const std::string& path, const kk_load_opts& opt
       if (!plan_allows_multimem(m->plan, &why)) fail(KK_EUNSUPPORTED, "fan-out NVLS: %s", why.c_str());
       std::vector<int> ords;
       for (int di : m->dev_idx) ords.push_back(c->devs[(size_t)di].ordinal);
+      KK_CUDA(cudaSetDevice(ords[0]));  // the driver entry points below want a current context on the calling thread
       m->nvls.reset(new NvlsPools);
       m->nvls->create(ords, m->plan.pool_bytes_of_part(0));
     }
