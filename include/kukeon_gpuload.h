@@ -71,7 +71,8 @@ typedef enum kk_dtype {
   KK_F8_E4M3 = 7, KK_F8_E8M0 = 8, KK_I16 = 9, KK_U16 = 10, KK_F16 = 11, KK_BF16 = 12, KK_I32 = 13,
   KK_U32 = 14, KK_F32 = 15, KK_C64 = 16, KK_F64 = 17, KK_I64 = 18, KK_U64 = 19,
   KK_Q4_0 = 32, KK_Q4_1 = 33, KK_Q5_0 = 34, KK_Q5_1 = 35, KK_Q8_0 = 36, KK_Q2_K = 37, KK_Q3_K = 38,
-  KK_Q4_K = 39, KK_Q5_K = 40, KK_Q6_K = 41, KK_Q8_K = 42, KK_IQ4_NL = 43, KK_IQ4_XS = 44, KK_MXFP4 = 45
+  KK_Q4_K = 39, KK_Q5_K = 40, KK_Q6_K = 41, KK_Q8_K = 42, KK_IQ4_NL = 43, KK_IQ4_XS = 44, KK_MXFP4 = 45,
+  KK_IQ2_XXS = 46, KK_IQ2_XS = 47, KK_IQ2_S = 48, KK_IQ3_XXS = 49, KK_IQ3_S = 50, KK_IQ1_S = 51, KK_IQ1_M = 52, KK_TQ1_0 = 53, KK_TQ2_0 = 54, KK_NVFP4 = 55
 } kk_dtype;
 
 typedef enum kk_mode {

@@ -17,6 +17,8 @@
 //     uint32_t kk_f8x2_to_f16x2<E5M2>(u16)       two FP8 -> two fp16 (exact; cvt.rn.f16x2.e4m3x2 / .e5m2x2 on the device)
 //     float    kk_bits2f(u32)                    bit cast
 //     uint32_t kk_byte_perm(a, b, sel)           PRMT: byte (sel & 7) of the 8 bytes {b:a} in the low byte of the result
+//     uint32_t kk_f2bits(f), kk_popc(u)          bit cast, population count
+//     uint64_t kk_grid_iq2xxs/iq2xs/iq2s/iq1s(i), uint32_t kk_grid_iq3xxs/iq3s(i)   codebook entry i (kk_iq_grids.h; __ldg on the device)
 //     void     sts16(a, v) / sts32(a, v)         stores into the stage (gather fallback of the 8-row transposes)
 //     uint32_t kk_ldg8(p)                        one byte from global memory (same fallback)
 //     Dsts, uint4, make_uint4, kConsumerWarps, KK_DQ_DEV (function attributes)
@@ -402,6 +404,179 @@ KK_DQ_DEV void consume_tw(const Dsts& D, uint32_t sbase, uint32_t pitch, uint32_
         const uint32_t kr = (k + 2u * rg) & 7u;
         if (rbase + kr < nr) store2_all(D, off + 2u * kr, (uint16_t)(t8_pack2<ES, CONV>(u[k], 0u) & 0xFFFFu));
       }
+    }
+  }
+}
+
+// ---- §8(f4): lattice i-quants, ternary types, NVFP4 --------------------------------------------------------------------------------------
+// Common shape of the IQ2 / IQ3 types: 8 weights = one codebook entry of 8 unsigned bytes (IQ3: two entries of 4), a sign byte (bit k
+// negates weight k) and a group scale db; y = (db * value) * (+-1), which is the product with its sign bit flipped.  Lane l always
+// handles weights 8l .. 8l+7 of the super-block (one block per warp iteration), so its 8 outputs are one entry.
+KK_DQ_DEV uint32_t ksigns7(uint32_t i7) { return i7 | ((kk_popc(i7) & 1u) << 7); }  // 7 stored bits + their parity (ggml ksigns_iq2xs)
+KK_DQ_DEV float signed_mul(float db, uint32_t w, int k, uint32_t signs, int bit) {
+  return kk_bits2f(kk_f2bits(__fmul_rn(db, byte_to_float<0>(w, k))) ^ (((signs >> bit) & 1u) << 31));
+}
+KK_DQ_DEV void store_entry(const Dsts& D, uint64_t off, float db, uint32_t lo, uint32_t hi, uint32_t signs) {
+  float y[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) y[e] = signed_mul(db, e < 4 ? lo : hi, e & 3, signs, e);
+  store_bf16x8(D, off, y);
+}
+// db = (d * (0.5 + s)) * K — two roundings, like gguf-py (K is a power of two, the second product is exact)
+KK_DQ_DEV float iq_scale(float d, uint32_t s, float k) { return __fmul_rn(__fmul_rn(d, __fadd_rn(0.5f, (float)s)), k); }
+
+// IQ2_XXS (66 B): d f16 | 8 x { u32: four grid indices (bytes) | u32: four 7-bit sign indices, scale in the top 4 bits }
+KK_DQ_DEV void consume_iq2xxs(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
+  const uint32_t g = (uint32_t)(lane >> 2), k = (uint32_t)(lane & 3);
+  for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
+    const uint32_t blk = pay + b * KK_IQ2XXS_BLOCK_BYTES;
+    const float d = lds_f16(blk);
+    const uint32_t q1 = lds32_any(blk + 6u + 8u * g);
+    const uint64_t grid = kk_grid_iq2xxs(lds8(blk + 2u + 8u * g + k));
+    store_entry(D, dst_off + (uint64_t)b * 512u + (uint32_t)lane * 16u, iq_scale(d, q1 >> 28, 0.25f), (uint32_t)grid, (uint32_t)(grid >> 32),
+                ksigns7((q1 >> (7u * k)) & 0x7Fu));
+  }
+}
+// IQ2_XS (74 B): d f16 | 32 x u16 { 9-bit grid index | 7-bit sign index } | scales[8] (a nibble per 16 weights)
+KK_DQ_DEV void consume_iq2xs(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
+  const uint32_t l = (uint32_t)lane;
+  for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
+    const uint32_t blk = pay + b * KK_IQ2XS_BLOCK_BYTES;
+    const float d = lds_f16(blk);
+    const uint32_t q = lds16_any(blk + 2u + 2u * l);
+    const uint32_t s = (lds8(blk + 66u + (l >> 2)) >> (4u * ((l >> 1) & 1u))) & 0xFu;
+    const uint64_t grid = kk_grid_iq2xs(q & 511u);
+    store_entry(D, dst_off + (uint64_t)b * 512u + l * 16u, iq_scale(d, s, 0.25f), (uint32_t)grid, (uint32_t)(grid >> 32), ksigns7(q >> 9));
+  }
+}
+// IQ2_S (82 B): d f16 | qs[32] | signs[32] | qh[8] (2 more index bits per entry) | scales[8]
+KK_DQ_DEV void consume_iq2s(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
+  const uint32_t l = (uint32_t)lane;
+  for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
+    const uint32_t blk = pay + b * KK_IQ2S_BLOCK_BYTES;
+    const float d = lds_f16(blk);
+    const uint32_t idx = lds8(blk + 2u + l) | (((lds8(blk + 66u + (l >> 2)) >> (2u * (l & 3u))) & 3u) << 8);
+    const uint32_t s = (lds8(blk + 74u + (l >> 2)) >> (4u * ((l >> 1) & 1u))) & 0xFu;
+    const uint64_t grid = kk_grid_iq2s(idx);
+    store_entry(D, dst_off + (uint64_t)b * 512u + l * 16u, iq_scale(d, s, 0.25f), (uint32_t)grid, (uint32_t)(grid >> 32), lds8(blk + 34u + l));
+  }
+}
+// IQ3_XXS (98 B): d f16 | qs[64] (one 4-value entry per byte) | 8 x u32 { four 7-bit sign indices, scale in the top 4 bits }
+KK_DQ_DEV void consume_iq3xxs(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
+  const uint32_t l = (uint32_t)lane, g = l >> 2, k = l & 3u;
+  for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
+    const uint32_t blk = pay + b * KK_IQ3XXS_BLOCK_BYTES;
+    const float d = lds_f16(blk);
+    const uint32_t w = lds32_any(blk + 66u + 4u * g);
+    const uint32_t lo = kk_grid_iq3xxs(lds8(blk + 2u + 2u * l)), hi = kk_grid_iq3xxs(lds8(blk + 3u + 2u * l));
+    store_entry(D, dst_off + (uint64_t)b * 512u + l * 16u, iq_scale(d, w >> 28, 0.5f), lo, hi, ksigns7((w >> (7u * k)) & 0x7Fu));
+  }
+}
+// IQ3_S (110 B): d f16 | qs[64] | qh[8] (a ninth index bit per entry) | signs[32] | scales[4] (a nibble per 32 weights); db = d * (1 + 2s)
+KK_DQ_DEV void consume_iq3s(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
+  const uint32_t l = (uint32_t)lane, g = l >> 2;
+  for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
+    const uint32_t blk = pay + b * KK_IQ3S_BLOCK_BYTES;
+    const float d = lds_f16(blk);
+    const uint32_t qh = lds8(blk + 66u + (l >> 2));  // entries 2l and 2l+1 live in byte (2l)/8, bits (2l)%8 and +1
+    const uint32_t i0 = lds8(blk + 2u + 2u * l) | (((qh >> ((2u * l) & 7u)) & 1u) << 8);
+    const uint32_t i1 = lds8(blk + 3u + 2u * l) | (((qh >> (((2u * l) & 7u) + 1u)) & 1u) << 8);
+    const uint32_t s = (lds8(blk + 106u + (g >> 1)) >> (4u * (g & 1u))) & 0xFu;
+    store_entry(D, dst_off + (uint64_t)b * 512u + l * 16u, __fmul_rn(d, (float)(1u + 2u * s)), kk_grid_iq3s(i0), kk_grid_iq3s(i1), lds8(blk + 74u + l));
+  }
+}
+// IQ1_S / IQ1_M: codebook values in {-1, 0, 1} (stored + 1), y = dl * (value + delta), delta = +-0.125
+KK_DQ_DEV void store_entry_iq1(const Dsts& D, uint64_t off, float dl, uint64_t grid, float delta) {
+  const uint32_t lo = (uint32_t)grid, hi = (uint32_t)(grid >> 32);
+  float y[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) y[e] = __fmul_rn(dl, __fadd_rn(byte_to_float<1>(e < 4 ? lo : hi, e & 3), delta));
+  store_bf16x8(D, off, y);
+}
+// IQ1_S (50 B): d f16 | qs[32] | 8 x u16 { four 3-bit index extensions | 3-bit scale << 12 | delta sign << 15 }
+KK_DQ_DEV void consume_iq1s(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
+  const uint32_t l = (uint32_t)lane, g = l >> 2, k = l & 3u;
+  for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
+    const uint32_t blk = pay + b * KK_IQ1S_BLOCK_BYTES;
+    const float d = lds_f16(blk);
+    const uint32_t qh = lds16_any(blk + 34u + 2u * g);
+    const uint32_t idx = lds8(blk + 2u + l) | (((qh >> (3u * k)) & 7u) << 8);
+    store_entry_iq1(D, dst_off + (uint64_t)b * 512u + l * 16u, __fmul_rn(d, (float)(2u * ((qh >> 12) & 7u) + 1u)), kk_grid_iq1s(idx),
+                    (qh & 0x8000u) ? -0.125f : 0.125f);
+  }
+}
+// IQ1_M (56 B): qs[32] | qh[16] (a nibble per entry: 3 index bits, bit 3 = delta sign) | 4 x u16 { four 3-bit scales | a nibble of the fp16 d }
+KK_DQ_DEV void consume_iq1m(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
+  const uint32_t l = (uint32_t)lane, k16 = l >> 1;
+  for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
+    const uint32_t blk = pay + b * KK_IQ1M_BLOCK_BYTES;
+    const uint32_t s0 = lds16_any(blk + 48u), s1 = lds16_any(blk + 50u), s2 = lds16_any(blk + 52u), s3 = lds16_any(blk + 54u);
+    const float d = kk_h2f((s0 >> 12) | ((s1 >> 12) << 4) | ((s2 >> 12) << 8) | ((s3 >> 12) << 12));
+    const uint32_t sw = (k16 >> 2) == 0 ? s0 : (k16 >> 2) == 1 ? s1 : (k16 >> 2) == 2 ? s2 : s3;
+    const uint32_t sc = (sw >> (3u * (k16 & 3u))) & 7u;
+    const uint32_t nib = (lds8(blk + 32u + (l >> 1)) >> (4u * (l & 1u))) & 0xFu;
+    store_entry_iq1(D, dst_off + (uint64_t)b * 512u + l * 16u, __fmul_rn(d, (float)(2u * sc + 1u)), kk_grid_iq1s(lds8(blk + l) | ((nib & 7u) << 8)),
+                    (nib & 8u) ? -0.125f : 0.125f);
+  }
+}
+// TQ2_0 (66 B): qs[64] | d f16; weight 128h + 32s + i = ((qs[32h+i] >> 2s) & 3) - 1 — Q2_K's bit layout without scales
+KK_DQ_DEV void consume_tq2_0(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
+  const uint32_t q_off = 32u * (uint32_t)(lane >> 4) + 8u * (uint32_t)(lane & 3);
+  const uint32_t sh = 2u * (uint32_t)((lane >> 2) & 3);
+  for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
+    const uint32_t blk = pay + b * KK_TQ2_0_BLOCK_BYTES;
+    const float d = lds_f16(blk + 64u);
+    const uint32_t q0 = (lds32_any(blk + q_off) >> sh) & 0x03030303u, q1 = (lds32_any(blk + q_off + 4u) >> sh) & 0x03030303u;
+    float y[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) y[e] = __fmul_rn(d, byte_to_float<1>(e < 4 ? q0 : q1, e & 3));
+    store_bf16x8(D, dst_off + (uint64_t)b * 512u + (uint32_t)lane * 16u, y);
+  }
+}
+// TQ1_0 (54 B): qs[48] | qh[4] | d f16 — base-3 digits: trit = (((B * 3^p) & 255) * 3) >> 8.  Four source bytes are processed as two
+// 16-bit lanes per multiply (B * 81 < 2^16): returns the four trits as bytes of one word.
+KK_DQ_DEV uint32_t tq1_trits4(uint32_t w, uint32_t m) {
+  const uint32_t ev = ((((w & 0x00FF00FFu) * m) & 0x00FF00FFu) * 3u >> 8) & 0x00030003u;         // bytes 0 and 2
+  const uint32_t od = (((((w >> 8) & 0x00FF00FFu) * m) & 0x00FF00FFu) * 3u >> 8) & 0x00030003u;  // bytes 1 and 3
+  return ev | (od << 8);
+}
+KK_DQ_DEV void consume_tq1_0(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
+  // weights 8l..8l+7: lanes 0-19 read qs[0..31] with power l/4, lanes 20-29 qs[32..47] with power (l-20)/2, lanes 30-31 all of qh with
+  // powers 2(l-30) (first four weights) and 2(l-30)+1 (last four)
+  const uint32_t l = (uint32_t)lane;
+  uint32_t a0, a1, p0, p1;
+  if (l < 20u) { a0 = 8u * (l & 3u); a1 = a0 + 4u; p0 = p1 = l >> 2; }
+  else if (l < 30u) { a0 = 32u + 8u * ((l - 20u) & 1u); a1 = a0 + 4u; p0 = p1 = (l - 20u) >> 1; }
+  else { a0 = a1 = 48u; p0 = 2u * (l - 30u); p1 = p0 + 1u; }
+  const uint32_t m0 = (uint32_t)((0x000000511B090301ull >> (8u * p0)) & 0xFFu), m1 = (uint32_t)((0x000000511B090301ull >> (8u * p1)) & 0xFFu);  // 3^p
+  for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
+    const uint32_t blk = pay + b * KK_TQ1_0_BLOCK_BYTES;
+    const float d = lds_f16(blk + 52u);
+    const uint32_t t0 = tq1_trits4(lds32_any(blk + a0), m0), t1 = tq1_trits4(lds32_any(blk + a1), m1);
+    float y[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) y[e] = __fmul_rn(d, byte_to_float<1>(e < 4 ? t0 : t1, e & 3));
+    store_bf16x8(D, dst_off + (uint64_t)b * 512u + l * 16u, y);
+  }
+}
+// NVFP4 (36 B, 64 weights): 4 x UE4M3 scale (one per 16 weights) | qs[32]; sub-block s uses qs[8s..8s+7]: low nibbles = its first 8 weights,
+// high nibbles the next 8; y = (scale / 2) * kMXFP4[q4] (doubled e2m1 table).  Lane l: block l>>3 of four per warp iteration, sub-block (l>>1)&3,
+// half l&1.
+KK_DQ_DEV void consume_nvfp4(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
+  const uint32_t l = (uint32_t)lane, sb = (l >> 1) & 3u, nsh = 4u * (l & 1u);
+  for (uint32_t b0 = (uint32_t)cwarp * 4u; b0 < nblk; b0 += kConsumerWarps * 4u) {
+    const uint32_t b = b0 + (l >> 3);
+    if (b < nblk) {
+      const uint32_t blk = pay + b * KK_NVFP4_BLOCK_BYTES;
+      const uint32_t x = lds8(blk + sb), e = (x >> 3) & 0xFu, m = x & 7u;
+      // half the unsigned-E4M3 value: (1 + m/8) * 2^(e-8) built as bits; e == 0: m * 2^-10; 0x00 and 0x7F decode to 0
+      float d = e ? kk_bits2f(((e + 119u) << 23) | (m << 20)) : __fmul_rn((float)m, 0.0009765625f);
+      if (x == 0u || x == 0x7Fu) d = 0.0f;
+      const uint32_t q0 = (lds32_any(blk + 4u + 8u * sb) >> nsh) & 0x0F0F0F0Fu, q1 = (lds32_any(blk + 8u + 8u * sb) >> nsh) & 0x0F0F0F0Fu;
+      float y[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) y[k] = __fmul_rn(d, lut16<1>(((k < 4 ? q0 : q1) >> (8 * (k & 3))) & 0xFu));
+      store_bf16x8(D, dst_off + (uint64_t)b * 128u + (l & 7u) * 16u, y);
     }
   }
 }

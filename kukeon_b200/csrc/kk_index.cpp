@@ -47,6 +47,11 @@ const DtRow kDt[] = {
     {KK_Q5_K, {"Q5_K", 256, 176, true}, 0},    {KK_Q6_K, {"Q6_K", 256, 210, true}, 0},
     {KK_Q8_K, {"Q8_K", 256, 292, true}, 0},    {KK_IQ4_NL, {"IQ4_NL", 32, 18, true}, 0},
     {KK_IQ4_XS, {"IQ4_XS", 256, 136, true}, 0}, {KK_MXFP4, {"MXFP4", 32, 17, true}, 0},
+    {KK_IQ2_XXS, {"IQ2_XXS", 256, 66, true}, 0}, {KK_IQ2_XS, {"IQ2_XS", 256, 74, true}, 0},
+    {KK_IQ2_S, {"IQ2_S", 256, 82, true}, 0}, {KK_IQ3_XXS, {"IQ3_XXS", 256, 98, true}, 0},
+    {KK_IQ3_S, {"IQ3_S", 256, 110, true}, 0}, {KK_IQ1_S, {"IQ1_S", 256, 50, true}, 0},
+    {KK_IQ1_M, {"IQ1_M", 256, 56, true}, 0}, {KK_TQ1_0, {"TQ1_0", 256, 54, true}, 0},
+    {KK_TQ2_0, {"TQ2_0", 256, 66, true}, 0}, {KK_NVFP4, {"NVFP4", 64, 36, true}, 0},
 };
 const DtRow* dt_row(uint32_t dt) {
   for (auto& r : kDt)
@@ -72,6 +77,8 @@ int dtype_from_ggml(uint32_t t) {
     case 6: return KK_Q5_0;  case 7: return KK_Q5_1;  case 8: return KK_Q8_0;  case 10: return KK_Q2_K;
     case 11: return KK_Q3_K; case 12: return KK_Q4_K; case 13: return KK_Q5_K; case 14: return KK_Q6_K;
     case 20: return KK_IQ4_NL; case 23: return KK_IQ4_XS; case 39: return KK_MXFP4;
+    case 16: return KK_IQ2_XXS; case 17: return KK_IQ2_XS; case 22: return KK_IQ2_S; case 18: return KK_IQ3_XXS; case 21: return KK_IQ3_S;
+    case 19: return KK_IQ1_S; case 29: return KK_IQ1_M; case 34: return KK_TQ1_0; case 35: return KK_TQ2_0; case 40: return KK_NVFP4;
     case 15: return KK_Q8_K; case 24: return KK_I8;   case 25: return KK_I16;  case 26: return KK_I32;
     case 27: return KK_I64;  case 28: return KK_F64;  case 30: return KK_BF16;
     default: return -1;

@@ -19,6 +19,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include "kk_iq_grids.h"
 #include "kk_kernels.cuh"
 
 namespace kk {
@@ -208,6 +209,21 @@ __device__ __forceinline__ void kk_h2x2f(uint32_t w, float& x, float& y) {
   x = f.x;
   y = f.y;
 }
+__device__ __forceinline__ uint32_t kk_f2bits(float f) { return __float_as_uint(f); }
+__device__ __forceinline__ uint32_t kk_popc(uint32_t u) { return (uint32_t)__popc(u); }
+// i-quant codebooks (33 KB, read through the read-only path; hot entries stay in L1)
+__device__ const uint64_t kGridIq2xxs[KK_GRID_IQ2XXS_SIZE] = {KK_GRID_IQ2XXS_VALUES};
+__device__ const uint64_t kGridIq2xs[KK_GRID_IQ2XS_SIZE] = {KK_GRID_IQ2XS_VALUES};
+__device__ const uint64_t kGridIq2s[KK_GRID_IQ2S_SIZE] = {KK_GRID_IQ2S_VALUES};
+__device__ const uint32_t kGridIq3xxs[KK_GRID_IQ3XXS_SIZE] = {KK_GRID_IQ3XXS_VALUES};
+__device__ const uint32_t kGridIq3s[KK_GRID_IQ3S_SIZE] = {KK_GRID_IQ3S_VALUES};
+__device__ const uint64_t kGridIq1s[KK_GRID_IQ1S_SIZE] = {KK_GRID_IQ1S_VALUES};
+__device__ __forceinline__ uint64_t kk_grid_iq2xxs(uint32_t i) { return __ldg(&kGridIq2xxs[i]); }
+__device__ __forceinline__ uint64_t kk_grid_iq2xs(uint32_t i) { return __ldg(&kGridIq2xs[i]); }
+__device__ __forceinline__ uint64_t kk_grid_iq2s(uint32_t i) { return __ldg(&kGridIq2s[i]); }
+__device__ __forceinline__ uint32_t kk_grid_iq3xxs(uint32_t i) { return __ldg(&kGridIq3xxs[i]); }
+__device__ __forceinline__ uint32_t kk_grid_iq3s(uint32_t i) { return __ldg(&kGridIq3s[i]); }
+__device__ __forceinline__ uint64_t kk_grid_iq1s(uint32_t i) { return __ldg(&kGridIq1s[i]); }
 #define KK_DQ_DEV __device__ __forceinline__
 #include "kk_consume_core.cuh"
 #include "kk_dequant.cuh"
@@ -428,6 +444,16 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
           case KK_OP_Q5K_BF16:
           case KK_OP_IQ4NL_BF16:
           case KK_OP_IQ4XS_BF16:
+          case KK_OP_IQ2XXS_BF16:
+          case KK_OP_IQ2XS_BF16:
+          case KK_OP_IQ2S_BF16:
+          case KK_OP_IQ3XXS_BF16:
+          case KK_OP_IQ3S_BF16:
+          case KK_OP_IQ1S_BF16:
+          case KK_OP_IQ1M_BF16:
+          case KK_OP_TQ1_0_BF16:
+          case KK_OP_TQ2_0_BF16:
+          case KK_OP_NVFP4_BF16:
           case KK_OP_MXFP4_BF16: {  // the other block quants: same tiling, geometry from kk_ops.h
             const KKBlockTile bt = kk_block_tile(seg, t);
             d.n_units = bt.n_blocks;
@@ -648,6 +674,16 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
         case KK_OP_IQ4NL_BF16: consume_codebook32<KK_IQ4NL_BLOCK_BYTES, 0>(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
         case KK_OP_MXFP4_BF16: consume_codebook32<KK_MXFP4_BLOCK_BYTES, 1>(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
         case KK_OP_IQ4XS_BF16: consume_iq4xs(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
+        case KK_OP_IQ2XXS_BF16: consume_iq2xxs(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
+        case KK_OP_IQ2XS_BF16: consume_iq2xs(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
+        case KK_OP_IQ2S_BF16: consume_iq2s(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
+        case KK_OP_IQ3XXS_BF16: consume_iq3xxs(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
+        case KK_OP_IQ3S_BF16: consume_iq3s(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
+        case KK_OP_IQ1S_BF16: consume_iq1s(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
+        case KK_OP_IQ1M_BF16: consume_iq1m(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
+        case KK_OP_TQ1_0_BF16: consume_tq1_0(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
+        case KK_OP_TQ2_0_BF16: consume_tq2_0(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
+        case KK_OP_NVFP4_BF16: consume_nvfp4(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
         case KK_OP_T8_F32_BF16: run_t8<4, 1>(D, L.src, t, sbase, ctid); break;
         case KK_OP_T8_F16_BF16: run_t8<2, 2>(D, L.src, t, sbase, ctid); break;
         case KK_OP_T8_B16: run_t8<2, 0>(D, L.src, t, sbase, ctid); break;

@@ -39,6 +39,27 @@
 #define KK_IQ4XS_TILE_BLOCKS 240u  /* 32640 B in */
 #define KK_MXFP4_BLOCK_BYTES 17u
 #define KK_MXFP4_TILE_BLOCKS 1920u /* 32640 B in */
+/* lattice i-quants, ternary types, NVFP4: blocks per tile chosen like the others (full tile <= KK_TILE_SRC_BYTES, a multiple of 16 bytes) */
+#define KK_IQ2XXS_BLOCK_BYTES 66u
+#define KK_IQ2XXS_TILE_BLOCKS 496u /* 32736 B in */
+#define KK_IQ2XS_BLOCK_BYTES 74u
+#define KK_IQ2XS_TILE_BLOCKS 440u /* 32560 B in */
+#define KK_IQ2S_BLOCK_BYTES 82u
+#define KK_IQ2S_TILE_BLOCKS 392u /* 32144 B in */
+#define KK_IQ3XXS_BLOCK_BYTES 98u
+#define KK_IQ3XXS_TILE_BLOCKS 328u /* 32144 B in */
+#define KK_IQ3S_BLOCK_BYTES 110u
+#define KK_IQ3S_TILE_BLOCKS 296u /* 32560 B in */
+#define KK_IQ1S_BLOCK_BYTES 50u
+#define KK_IQ1S_TILE_BLOCKS 648u /* 32400 B in */
+#define KK_IQ1M_BLOCK_BYTES 56u
+#define KK_IQ1M_TILE_BLOCKS 584u /* 32704 B in */
+#define KK_TQ1_0_BLOCK_BYTES 54u
+#define KK_TQ1_0_TILE_BLOCKS 600u /* 32400 B in */
+#define KK_TQ2_0_BLOCK_BYTES 66u
+#define KK_TQ2_0_TILE_BLOCKS 496u /* 32736 B in */
+#define KK_NVFP4_BLOCK_BYTES 36u
+#define KK_NVFP4_TILE_BLOCKS 908u /* 32688 B in */
 #define KK_T_ROWS 32u            /* transpose tile: 32 source rows ... */
 #define KK_T_COLS 128u           /* ... x 128 source columns (elements) */
 #define KK_T_PITCH_PAD 16u       /* TMA-staged transpose rows sit KK_T_COLS*es + 16 bytes apart (bank spread) */
@@ -101,7 +122,19 @@ enum KKOp : uint32_t {
   KK_OP_TW_F32_BF16 = 26,
   KK_OP_TW_F16_BF16 = 27,
   KK_OP_TW_B16 = 28,
-  KK_OP_COUNT = 29
+  // lattice i-quants (256-weight super-blocks; 8 weights = one grid entry of kk_iq_grids.h, or two 4-value entries for IQ3), the ternary
+  // types, and NVFP4 (64-weight blocks: 4 UE4M3 scales | 32 nibble bytes)
+  KK_OP_IQ2XXS_BF16 = 29,
+  KK_OP_IQ2XS_BF16 = 30,
+  KK_OP_IQ2S_BF16 = 31,
+  KK_OP_IQ3XXS_BF16 = 32,
+  KK_OP_IQ3S_BF16 = 33,
+  KK_OP_IQ1S_BF16 = 34,
+  KK_OP_IQ1M_BF16 = 35,
+  KK_OP_TQ1_0_BF16 = 36,
+  KK_OP_TQ2_0_BF16 = 37,
+  KK_OP_NVFP4_BF16 = 38,
+  KK_OP_COUNT = 39
 };
 
 struct KKSeg {
@@ -142,6 +175,16 @@ static inline KK_HD KKBlockGeom kk_block_geom(uint32_t op) {
     case KK_OP_IQ4NL_BF16: return {KK_IQ4NL_BLOCK_BYTES, 64u, KK_IQ4NL_TILE_BLOCKS};
     case KK_OP_IQ4XS_BF16: return {KK_IQ4XS_BLOCK_BYTES, 512u, KK_IQ4XS_TILE_BLOCKS};
     case KK_OP_MXFP4_BF16: return {KK_MXFP4_BLOCK_BYTES, 64u, KK_MXFP4_TILE_BLOCKS};
+    case KK_OP_IQ2XXS_BF16: return {KK_IQ2XXS_BLOCK_BYTES, 512u, KK_IQ2XXS_TILE_BLOCKS};
+    case KK_OP_IQ2XS_BF16: return {KK_IQ2XS_BLOCK_BYTES, 512u, KK_IQ2XS_TILE_BLOCKS};
+    case KK_OP_IQ2S_BF16: return {KK_IQ2S_BLOCK_BYTES, 512u, KK_IQ2S_TILE_BLOCKS};
+    case KK_OP_IQ3XXS_BF16: return {KK_IQ3XXS_BLOCK_BYTES, 512u, KK_IQ3XXS_TILE_BLOCKS};
+    case KK_OP_IQ3S_BF16: return {KK_IQ3S_BLOCK_BYTES, 512u, KK_IQ3S_TILE_BLOCKS};
+    case KK_OP_IQ1S_BF16: return {KK_IQ1S_BLOCK_BYTES, 512u, KK_IQ1S_TILE_BLOCKS};
+    case KK_OP_IQ1M_BF16: return {KK_IQ1M_BLOCK_BYTES, 512u, KK_IQ1M_TILE_BLOCKS};
+    case KK_OP_TQ1_0_BF16: return {KK_TQ1_0_BLOCK_BYTES, 512u, KK_TQ1_0_TILE_BLOCKS};
+    case KK_OP_TQ2_0_BF16: return {KK_TQ2_0_BLOCK_BYTES, 512u, KK_TQ2_0_TILE_BLOCKS};
+    case KK_OP_NVFP4_BF16: return {KK_NVFP4_BLOCK_BYTES, 128u, KK_NVFP4_TILE_BLOCKS};
     default: return {0u, 0u, 0u};
   }
 }
@@ -169,7 +212,12 @@ static_assert(KK_TILE_OK(KK_Q4K_BLOCK_BYTES, KK_Q4K_TILE_BLOCKS) && KK_TILE_OK(K
                   KK_TILE_OK(KK_Q5_1_BLOCK_BYTES, KK_Q5_1_TILE_BLOCKS) && KK_TILE_OK(KK_Q2K_BLOCK_BYTES, KK_Q2K_TILE_BLOCKS) &&
                   KK_TILE_OK(KK_Q3K_BLOCK_BYTES, KK_Q3K_TILE_BLOCKS) && KK_TILE_OK(KK_Q5K_BLOCK_BYTES, KK_Q5K_TILE_BLOCKS) &&
                   KK_TILE_OK(KK_IQ4NL_BLOCK_BYTES, KK_IQ4NL_TILE_BLOCKS) && KK_TILE_OK(KK_IQ4XS_BLOCK_BYTES, KK_IQ4XS_TILE_BLOCKS) &&
-                  KK_TILE_OK(KK_MXFP4_BLOCK_BYTES, KK_MXFP4_TILE_BLOCKS),
+                  KK_TILE_OK(KK_MXFP4_BLOCK_BYTES, KK_MXFP4_TILE_BLOCKS) &&
+                  KK_TILE_OK(KK_IQ2XXS_BLOCK_BYTES, KK_IQ2XXS_TILE_BLOCKS) && KK_TILE_OK(KK_IQ2XS_BLOCK_BYTES, KK_IQ2XS_TILE_BLOCKS) &&
+                  KK_TILE_OK(KK_IQ2S_BLOCK_BYTES, KK_IQ2S_TILE_BLOCKS) && KK_TILE_OK(KK_IQ3XXS_BLOCK_BYTES, KK_IQ3XXS_TILE_BLOCKS) &&
+                  KK_TILE_OK(KK_IQ3S_BLOCK_BYTES, KK_IQ3S_TILE_BLOCKS) && KK_TILE_OK(KK_IQ1S_BLOCK_BYTES, KK_IQ1S_TILE_BLOCKS) &&
+                  KK_TILE_OK(KK_IQ1M_BLOCK_BYTES, KK_IQ1M_TILE_BLOCKS) && KK_TILE_OK(KK_TQ1_0_BLOCK_BYTES, KK_TQ1_0_TILE_BLOCKS) &&
+                  KK_TILE_OK(KK_TQ2_0_BLOCK_BYTES, KK_TQ2_0_TILE_BLOCKS) && KK_TILE_OK(KK_NVFP4_BLOCK_BYTES, KK_NVFP4_TILE_BLOCKS),
               "a full tile of every block op fits one stage and keeps the next tile 16-byte aligned");
 
 // Units one tile covers, and the number of tiles of a segment (host + device).
@@ -193,6 +241,16 @@ static inline KK_HD uint64_t kk_seg_tiles(uint32_t op, uint64_t units, uint32_t 
     case KK_OP_Q5K_BF16:
     case KK_OP_IQ4NL_BF16:
     case KK_OP_IQ4XS_BF16:
+    case KK_OP_IQ2XXS_BF16:
+    case KK_OP_IQ2XS_BF16:
+    case KK_OP_IQ2S_BF16:
+    case KK_OP_IQ3XXS_BF16:
+    case KK_OP_IQ3S_BF16:
+    case KK_OP_IQ1S_BF16:
+    case KK_OP_IQ1M_BF16:
+    case KK_OP_TQ1_0_BF16:
+    case KK_OP_TQ2_0_BF16:
+    case KK_OP_NVFP4_BF16:
     case KK_OP_MXFP4_BF16: {
       const uint32_t tb = kk_block_geom(op).tile_blocks;
       return (units + tb - 1) / tb;

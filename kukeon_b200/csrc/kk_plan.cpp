@@ -58,6 +58,16 @@ OpInfo op_for(uint32_t dt, uint32_t flags, const std::string& name) {
     case KK_IQ4_NL: qop = KK_OP_IQ4NL_BF16; break;
     case KK_IQ4_XS: qop = KK_OP_IQ4XS_BF16; break;
     case KK_MXFP4: qop = KK_OP_MXFP4_BF16; break;
+    case KK_IQ2_XXS: qop = KK_OP_IQ2XXS_BF16; break;
+    case KK_IQ2_XS: qop = KK_OP_IQ2XS_BF16; break;
+    case KK_IQ2_S: qop = KK_OP_IQ2S_BF16; break;
+    case KK_IQ3_XXS: qop = KK_OP_IQ3XXS_BF16; break;
+    case KK_IQ3_S: qop = KK_OP_IQ3S_BF16; break;
+    case KK_IQ1_S: qop = KK_OP_IQ1S_BF16; break;
+    case KK_IQ1_M: qop = KK_OP_IQ1M_BF16; break;
+    case KK_TQ1_0: qop = KK_OP_TQ1_0_BF16; break;
+    case KK_TQ2_0: qop = KK_OP_TQ2_0_BF16; break;
+    case KK_NVFP4: qop = KK_OP_NVFP4_BF16; break;
     default: break;
   }
   if (qop != KK_OP_COUNT) {
@@ -67,7 +77,7 @@ OpInfo op_for(uint32_t dt, uint32_t flags, const std::string& name) {
   const DtypeInfo* di = dtype_info(dt);
   if (!di) fail(KK_EINVAL, "tensor %s: unknown dtype %u", name.c_str(), dt);
   if (di->block_elems > 1 && dt >= 32)
-    fail(KK_EUNSUPPORTED, "tensor %s: %s -> bf16 dequantisation is not implemented (Q4_0, Q4_1, Q5_0, Q5_1, Q8_0, Q2_K .. Q6_K, IQ4_NL, IQ4_XS and MXFP4 are)", name.c_str(), di->name);
+    fail(KK_EUNSUPPORTED, "tensor %s: %s -> bf16 dequantisation is not implemented (every GGUF weight type except Q8_K / Q8_1 is)", name.c_str(), di->name);
   return {KK_OP_COPY, dt, 1, 1, KK_TILE_SRC_BYTES};  // integers, bool, fp8, f64, sub-byte: verbatim bytes
 }
 

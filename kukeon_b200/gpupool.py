@@ -32,6 +32,7 @@ DTYPE_NAMES = {
     9: "I16", 10: "U16", 11: "F16", 12: "BF16", 13: "I32", 14: "U32", 15: "F32", 16: "C64", 17: "F64", 18: "I64",
     19: "U64", 32: "Q4_0", 33: "Q4_1", 34: "Q5_0", 35: "Q5_1", 36: "Q8_0", 37: "Q2_K", 38: "Q3_K", 39: "Q4_K",
     40: "Q5_K", 41: "Q6_K", 42: "Q8_K", 43: "IQ4_NL", 44: "IQ4_XS", 45: "MXFP4",
+    46: "IQ2_XXS", 47: "IQ2_XS", 48: "IQ2_S", 49: "IQ3_XXS", 50: "IQ3_S", 51: "IQ1_S", 52: "IQ1_M", 53: "TQ1_0", 54: "TQ2_0", 55: "NVFP4",
 }
 
 

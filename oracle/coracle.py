@@ -18,7 +18,9 @@ OP_DEQUANT = 0x100  # | ggml type id
 # file dtype -> (ggml type id, weights per block, bytes per block)   (gguf/constants.py GGML_QUANT_SIZES)
 GGML_BLOCK = {"Q4_0": (2, 32, 18), "Q4_1": (3, 32, 20), "Q5_0": (6, 32, 22), "Q5_1": (7, 32, 24), "Q8_0": (8, 32, 34),
               "Q2_K": (10, 256, 84), "Q3_K": (11, 256, 110), "Q4_K": (12, 256, 144), "Q5_K": (13, 256, 176), "Q6_K": (14, 256, 210),
-              "IQ4_NL": (20, 32, 18), "IQ4_XS": (23, 256, 136), "MXFP4": (39, 32, 17)}
+              "IQ4_NL": (20, 32, 18), "IQ4_XS": (23, 256, 136), "MXFP4": (39, 32, 17), "IQ2_XXS": (16, 256, 66), "IQ2_XS": (17, 256, 74),
+              "IQ3_XXS": (18, 256, 98), "IQ1_S": (19, 256, 50), "IQ3_S": (21, 256, 110), "IQ2_S": (22, 256, 82), "IQ1_M": (29, 256, 56),
+              "TQ1_0": (34, 256, 54), "TQ2_0": (35, 256, 66), "NVFP4": (40, 64, 36)}
 
 
 class OrcJob(C.Structure):
@@ -27,7 +29,8 @@ class OrcJob(C.Structure):
 
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "kk_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    newest = max(os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "iq_grids_c.h")))
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
         subprocess.run(["make", "-C", _HERE, "-s"], check=True)
     return _SO
 

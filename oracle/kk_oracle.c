@@ -260,6 +260,136 @@ static void mxfp4_block(const uint8_t* b, uint16_t* out) {
   for (int i = 0; i < 32; ++i) out[i] = f32_to_bf16(d * (float)kMXFP4[legacy_nibble(b + 1, i)]);
 }
 
+/* ---- lattice i-quants, ternary types, NVFP4 (element formulas as in oracle/oracle.py; codebooks: oracle/iq_grids_c.h, generated) ---- */
+#include "iq_grids_c.h"
+static const uint64_t g_iq2xxs[KK_GRID_IQ2XXS_SIZE] = {KK_GRID_IQ2XXS_VALUES};
+static const uint64_t g_iq2xs[KK_GRID_IQ2XS_SIZE] = {KK_GRID_IQ2XS_VALUES};
+static const uint64_t g_iq2s[KK_GRID_IQ2S_SIZE] = {KK_GRID_IQ2S_VALUES};
+static const uint32_t g_iq3xxs[KK_GRID_IQ3XXS_SIZE] = {KK_GRID_IQ3XXS_VALUES};
+static const uint32_t g_iq3s[KK_GRID_IQ3S_SIZE] = {KK_GRID_IQ3S_VALUES};
+static const uint64_t g_iq1s[KK_GRID_IQ1S_SIZE] = {KK_GRID_IQ1S_VALUES};
+
+static inline uint32_t ld_u32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static inline uint16_t ld_u16(const uint8_t* p) { uint16_t v; memcpy(&v, p, 2); return v; }
+/* 7 stored sign bits, the 8th is their parity (ggml ksigns_iq2xs) */
+static inline uint32_t ksigns(uint32_t i7) { return i7 | ((uint32_t)(__builtin_popcount(i7) & 1) << 7); }
+/* eight weights: (db * grid byte k) * (+1 | -1 by bit k of signs) */
+static inline void put8(uint16_t* out, float db, uint64_t grid, uint32_t signs) {
+  for (int k = 0; k < 8; ++k) {
+    volatile float p = db * (float)((grid >> (8 * k)) & 0xFF);
+    out[k] = f32_to_bf16((signs >> k) & 1 ? -p : p);
+  }
+}
+static void iq2xxs_block(const uint8_t* b, uint16_t* out) {
+  const float d = ld_f16(b);
+  for (int g = 0; g < 8; ++g) {
+    const uint32_t q0 = ld_u32(b + 2 + 8 * g), q1 = ld_u32(b + 6 + 8 * g);
+    volatile float t = d * (0.5f + (float)(q1 >> 28));
+    const float db = t * 0.25f;
+    for (int k = 0; k < 4; ++k) put8(out + 32 * g + 8 * k, db, g_iq2xxs[(q0 >> (8 * k)) & 0xFF], ksigns((q1 >> (7 * k)) & 0x7F));
+  }
+}
+static void iq2xs_block(const uint8_t* b, uint16_t* out) {
+  const float d = ld_f16(b);
+  for (int j = 0; j < 32; ++j) {
+    const uint32_t q = ld_u16(b + 2 + 2 * j);
+    const uint32_t s = (b[66 + (j >> 2)] >> (4 * ((j >> 1) & 1))) & 0x0F;
+    volatile float t = d * (0.5f + (float)s);
+    put8(out + 8 * j, t * 0.25f, g_iq2xs[q & 511], ksigns(q >> 9));
+  }
+}
+static void iq2s_block(const uint8_t* b, uint16_t* out) {
+  const float d = ld_f16(b);
+  for (int j = 0; j < 32; ++j) {
+    const uint32_t idx = b[2 + j] | (((b[66 + (j >> 2)] >> (2 * (j & 3))) & 3u) << 8);
+    const uint32_t s = (b[74 + (j >> 2)] >> (4 * ((j >> 1) & 1))) & 0x0F;
+    volatile float t = d * (0.5f + (float)s);
+    put8(out + 8 * j, t * 0.25f, g_iq2s[idx], b[34 + j]);
+  }
+}
+static void iq3xxs_block(const uint8_t* b, uint16_t* out) {
+  const float d = ld_f16(b);
+  for (int g = 0; g < 8; ++g) {
+    const uint32_t w = ld_u32(b + 66 + 4 * g);
+    volatile float t = d * (0.5f + (float)(w >> 28));
+    const float db = t * 0.5f;
+    for (int k = 0; k < 4; ++k) {
+      const uint64_t grid = (uint64_t)g_iq3xxs[b[2 + 8 * g + 2 * k]] | ((uint64_t)g_iq3xxs[b[2 + 8 * g + 2 * k + 1]] << 32);
+      put8(out + 32 * g + 8 * k, db, grid, ksigns((w >> (7 * k)) & 0x7F));
+    }
+  }
+}
+static void iq3s_block(const uint8_t* b, uint16_t* out) {
+  const float d = ld_f16(b);
+  for (int m = 0; m < 32; ++m) { /* 8 weights = two 4-value grid entries */
+    const int j0 = 2 * m, j1 = 2 * m + 1, g = m >> 2;
+    const uint32_t i0 = b[2 + j0] | (((b[66 + (j0 >> 3)] >> (j0 & 7)) & 1u) << 8);
+    const uint32_t i1 = b[2 + j1] | (((b[66 + (j1 >> 3)] >> (j1 & 7)) & 1u) << 8);
+    const uint32_t s = (b[106 + (g >> 1)] >> (4 * (g & 1))) & 0x0F;
+    const float db = d * (float)(1 + 2 * (int)s);
+    put8(out + 8 * m, db, (uint64_t)g_iq3s[i0] | ((uint64_t)g_iq3s[i1] << 32), b[74 + m]);
+  }
+}
+/* IQ1: grid bytes are value + 1; y = dl * ((value) + delta) */
+static inline void put8_iq1(uint16_t* out, float dl, uint64_t grid, float delta) {
+  for (int k = 0; k < 8; ++k) {
+    volatile float v = (float)((int)((grid >> (8 * k)) & 0xFF) - 1) + delta;
+    out[k] = f32_to_bf16(dl * v);
+  }
+}
+static void iq1s_block(const uint8_t* b, uint16_t* out) {
+  const float d = ld_f16(b);
+  for (int g = 0; g < 8; ++g) {
+    const uint32_t qh = ld_u16(b + 34 + 2 * g);
+    const float dl = d * (float)(2 * (int)((qh >> 12) & 7) + 1);
+    const float delta = (qh & 0x8000) ? -0.125f : 0.125f;
+    for (int k = 0; k < 4; ++k) put8_iq1(out + 32 * g + 8 * k, dl, g_iq1s[b[2 + 4 * g + k] | (((qh >> (3 * k)) & 7u) << 8)], delta);
+  }
+}
+static void iq1m_block(const uint8_t* b, uint16_t* out) {
+  uint16_t sc[4];
+  for (int i = 0; i < 4; ++i) sc[i] = ld_u16(b + 48 + 2 * i);
+  const uint16_t dbits = (uint16_t)((sc[0] >> 12) | ((sc[1] >> 12) << 4) | ((sc[2] >> 12) << 8) | ((sc[3] >> 12) << 12));
+  const float d = f16bits_to_f32(dbits);
+  for (int j = 0; j < 32; ++j) {
+    const int k = j >> 1;
+    const uint32_t s3 = (sc[k >> 2] >> (3 * (k & 3))) & 7u;
+    const float dl = d * (float)(2 * (int)s3 + 1);
+    const uint32_t nib = (b[32 + (j >> 1)] >> (4 * (j & 1))) & 0x0F;
+    put8_iq1(out + 8 * j, dl, g_iq1s[b[j] | ((nib & 7u) << 8)], (nib & 8) ? -0.125f : 0.125f);
+  }
+}
+static void tq2_0_block(const uint8_t* b, uint16_t* out) {
+  const float d = ld_f16(b + 64);
+  for (int e = 0; e < 256; ++e) {
+    const int h = e >> 7, s = (e >> 5) & 3, i = e & 31;
+    out[e] = f32_to_bf16(d * (float)((int)((b[32 * h + i] >> (2 * s)) & 3) - 1));
+  }
+}
+static void tq1_0_block(const uint8_t* b, uint16_t* out) {
+  static const uint32_t pow3[5] = {1, 3, 9, 27, 81};
+  const float d = ld_f16(b + 52);
+  for (int e = 0; e < 256; ++e) {
+    int byte, p;
+    if (e < 160) { byte = e % 32; p = e / 32; }
+    else if (e < 240) { byte = 32 + (e - 160) % 16; p = (e - 160) / 16; }
+    else { byte = 48 + (e - 240) % 4; p = (e - 240) / 4; }
+    const uint32_t v = (b[byte] * pow3[p]) & 0xFF;
+    out[e] = f32_to_bf16(d * (float)((int)((v * 3) >> 8) - 1));
+  }
+}
+static void nvfp4_block(const uint8_t* b, uint16_t* out) {
+  for (int s = 0; s < 4; ++s) {
+    const uint32_t x = b[s], e = (x >> 3) & 0xF, m = x & 7;
+    float d; /* HALF the unsigned-E4M3 scale; 0x00 and 0x7F decode to 0 */
+    if (x == 0 || x == 0x7F) d = 0.0f;
+    else if (e == 0) d = (float)m * 0.0009765625f; /* m * 2^-9 * 0.5 */
+    else { const uint32_t bits = ((e + 119u) << 23) | (m << 20); memcpy(&d, &bits, 4); } /* (1 + m/8) * 2^(e-8) */
+    const uint8_t* qs = b + 4 + 8 * s;
+    for (int i = 0; i < 16; ++i) out[16 * s + i] = f32_to_bf16(d * (float)kMXFP4[i < 8 ? (qs[i] & 0x0F) : (qs[i - 8] >> 4)]);
+  }
+}
+
 /* Dispatch by ggml type id (gguf/constants.py GGMLQuantizationType): block bytes / weights per block / function. */
 typedef void (*orc_block_fn)(const uint8_t*, uint16_t*);
 static orc_block_fn block_fn(uint32_t ggml_type, uint32_t* bytes, uint32_t* elems) {
@@ -277,6 +407,16 @@ static orc_block_fn block_fn(uint32_t ggml_type, uint32_t* bytes, uint32_t* elem
     case 20: *bytes = 18; *elems = 32; return iq4nl_block;
     case 23: *bytes = 136; *elems = 256; return iq4xs_block;
     case 39: *bytes = 17; *elems = 32; return mxfp4_block;
+    case 16: *bytes = 66; *elems = 256; return iq2xxs_block;
+    case 17: *bytes = 74; *elems = 256; return iq2xs_block;
+    case 18: *bytes = 98; *elems = 256; return iq3xxs_block;
+    case 19: *bytes = 50; *elems = 256; return iq1s_block;
+    case 21: *bytes = 110; *elems = 256; return iq3s_block;
+    case 22: *bytes = 82; *elems = 256; return iq2s_block;
+    case 29: *bytes = 56; *elems = 256; return iq1m_block;
+    case 34: *bytes = 54; *elems = 256; return tq1_0_block;
+    case 35: *bytes = 66; *elems = 256; return tq2_0_block;
+    case 40: *bytes = 36; *elems = 64; return nvfp4_block;
     default: return 0;
   }
 }

@@ -41,7 +41,9 @@ GGML_TYPES = {
     0: ("F32", 1, 4), 1: ("F16", 1, 2), 2: ("Q4_0", 32, 18), 3: ("Q4_1", 32, 20), 6: ("Q5_0", 32, 22),
     7: ("Q5_1", 32, 24), 8: ("Q8_0", 32, 34), 10: ("Q2_K", 256, 84), 11: ("Q3_K", 256, 110),
     12: ("Q4_K", 256, 144), 13: ("Q5_K", 256, 176), 14: ("Q6_K", 256, 210), 15: ("Q8_K", 256, 292),
-    20: ("IQ4_NL", 32, 18), 23: ("IQ4_XS", 256, 136), 39: ("MXFP4", 32, 17),
+    20: ("IQ4_NL", 32, 18), 23: ("IQ4_XS", 256, 136), 39: ("MXFP4", 32, 17), 16: ("IQ2_XXS", 256, 66), 17: ("IQ2_XS", 256, 74),
+    18: ("IQ3_XXS", 256, 98), 19: ("IQ1_S", 256, 50), 21: ("IQ3_S", 256, 110), 22: ("IQ2_S", 256, 82), 29: ("IQ1_M", 256, 56),
+    34: ("TQ1_0", 256, 54), 35: ("TQ2_0", 256, 66), 40: ("NVFP4", 64, 36),
     24: ("I8", 1, 1), 25: ("I16", 1, 2), 26: ("I32", 1, 4), 27: ("I64", 1, 8), 28: ("F64", 1, 8),
     30: ("BF16", 1, 2),
 }
@@ -556,13 +558,215 @@ def dequant_mxfp4_f32(blocks: np.ndarray) -> np.ndarray:
         return (e8m0_to_f32_half(b[:, 0:1]) * kv).astype(np.float32)
 
 
+# ---- lattice i-quants, ternary types, NVFP4 (SURVEY.md §8(f4)) -------------------------------------------------------------------
+# Codebooks: oracle/iq_grids.py (generated from the published ggml constants by tools/gen_iq_grids.py; pinned to gguf-py's in the tests).
+def _grid(name: str) -> np.ndarray:
+    from .iq_grids import GRIDS
+    g = _GRID_CACHE.get(name)
+    if g is None:
+        g = _GRID_CACHE[name] = np.frombuffer(b"".join(GRIDS[name]), np.uint8).reshape(len(GRIDS[name]), -1).copy()
+    return g
+
+
+_GRID_CACHE: Dict[str, np.ndarray] = {}
+# sign patterns of the IQ2/IQ3 "xxs/xs" types: 7 stored bits, the 8th is their parity (ggml ksigns_iq2xs)
+KSIGNS = np.array([i | ((bin(i).count("1") & 1) << 7) for i in range(128)], np.uint8)
+
+
+def _sign_from_bits(bits8: np.ndarray) -> np.ndarray:
+    """[..] uint8 -> [.., 8] float32 of +1 / -1: bit k set means weight k is negated."""
+    b = (bits8[..., None] >> np.arange(8, dtype=np.uint8)) & 1
+    return np.where(b == 0, np.float32(1), np.float32(-1))
+
+
+def dequant_iq2xxs_f32(blocks: np.ndarray) -> np.ndarray:
+    """[n,66] (d f16 | 8 x (u32 idx4 | u32 signs+scale)) -> [n,256].  Group g (32 weights): four grid indices = the bytes of the first
+    word; the second word holds four 7-bit sign-pattern indices and, in its top 4 bits, the scale s: db = d*(0.5+s)*0.25;
+    y = (db * grid[idx][k]) * sign (gguf/quants.py IQ2_XXS)."""
+    b = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, 66)
+    n = b.shape[0]
+    d = _f16(b[:, 0:2])
+    q = np.ascontiguousarray(b[:, 2:66]).view("<u4").reshape(n, 8, 2)
+    idx = np.ascontiguousarray(q[:, :, 0]).view(np.uint8).reshape(n, 8, 4)
+    sidx = (q[:, :, 1:2] >> np.array([0, 7, 14, 21], np.uint32)) & np.uint32(0x7F)
+    with np.errstate(all="ignore"):
+        db = ((d * (np.float32(0.5) + (q[:, :, 1] >> 28).astype(np.float32))).astype(np.float32) * np.float32(0.25)).astype(np.float32)
+        y = ((db[:, :, None, None] * _grid("iq2xxs")[idx].astype(np.float32)).astype(np.float32) * _sign_from_bits(KSIGNS[sidx])).astype(np.float32)
+    return y.reshape(n, 256)
+
+
+def dequant_iq2xs_f32(blocks: np.ndarray) -> np.ndarray:
+    """[n,74] (d f16 | 32 x u16 (9-bit grid index | 7-bit sign index << 9) | scales[8]) -> [n,256].  Entry j covers weights 8j..8j+7;
+    scale of weights 16k..16k+15 is nibble k%2 of scales[k//2]: db = d*(0.5+s)*0.25 (gguf/quants.py IQ2_XS)."""
+    b = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, 74)
+    n = b.shape[0]
+    d = _f16(b[:, 0:2])
+    q = np.ascontiguousarray(b[:, 2:66]).view("<u2").reshape(n, 32)
+    sc = np.stack([b[:, 66:74] & 0x0F, b[:, 66:74] >> 4], axis=-1).reshape(n, 16)
+    with np.errstate(all="ignore"):
+        db = ((d * (np.float32(0.5) + sc.astype(np.float32))).astype(np.float32) * np.float32(0.25)).astype(np.float32)
+        g = _grid("iq2xs")[q & 511].astype(np.float32).reshape(n, 16, 2, 8)
+        sg = _sign_from_bits(KSIGNS[q >> 9]).reshape(n, 16, 2, 8)
+        y = ((db[:, :, None, None] * g).astype(np.float32) * sg).astype(np.float32)
+    return y.reshape(n, 256)
+
+
+def dequant_iq2s_f32(blocks: np.ndarray) -> np.ndarray:
+    """[n,82] (d f16 | qs[32] | signs[32] | qh[8] | scales[8]) -> [n,256].  Entry j: index qs[j] | ((qh[j//4] >> 2(j%4)) & 3) << 8,
+    sign bits signs[j]; scales as IQ2_XS (gguf/quants.py IQ2_S)."""
+    b = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, 82)
+    n = b.shape[0]
+    d = _f16(b[:, 0:2])
+    qs, signs, qh, scb = b[:, 2:34], b[:, 34:66], b[:, 66:74], b[:, 74:82]
+    j = np.arange(32)
+    idx = qs.astype(np.uint16) | (((qh[:, j // 4] >> (2 * (j % 4)).astype(np.uint8)) & 3).astype(np.uint16) << 8)
+    sc = np.stack([scb & 0x0F, scb >> 4], axis=-1).reshape(n, 16)
+    with np.errstate(all="ignore"):
+        db = ((d * (np.float32(0.5) + sc.astype(np.float32))).astype(np.float32) * np.float32(0.25)).astype(np.float32)
+        g = _grid("iq2s")[idx].astype(np.float32).reshape(n, 16, 2, 8)
+        y = ((db[:, :, None, None] * g).astype(np.float32) * _sign_from_bits(signs).reshape(n, 16, 2, 8)).astype(np.float32)
+    return y.reshape(n, 256)
+
+
+def dequant_iq3xxs_f32(blocks: np.ndarray) -> np.ndarray:
+    """[n,98] (d f16 | qs[64] | 8 x u32 signs+scale) -> [n,256].  Grid entries hold 4 values: weights 4j..4j+3 = grid[qs[j]]; group g
+    (32 weights) has four 7-bit sign indices (8 weights each) and a 4-bit scale in its u32: db = d*(0.5+s)*0.5 (gguf/quants.py IQ3_XXS)."""
+    b = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, 98)
+    n = b.shape[0]
+    d = _f16(b[:, 0:2])
+    qs = b[:, 2:66]
+    w = np.ascontiguousarray(b[:, 66:98]).view("<u4").reshape(n, 8)
+    sidx = (w[:, :, None] >> np.array([0, 7, 14, 21], np.uint32)) & np.uint32(0x7F)
+    with np.errstate(all="ignore"):
+        db = ((d * (np.float32(0.5) + (w >> 28).astype(np.float32))).astype(np.float32) * np.float32(0.5)).astype(np.float32)
+        g = _grid("iq3xxs")[qs].astype(np.float32).reshape(n, 8, 4, 8)
+        y = ((db[:, :, None, None] * g).astype(np.float32) * _sign_from_bits(KSIGNS[sidx])).astype(np.float32)
+    return y.reshape(n, 256)
+
+
+def dequant_iq3s_f32(blocks: np.ndarray) -> np.ndarray:
+    """[n,110] (d f16 | qs[64] | qh[8] | signs[32] | scales[4]) -> [n,256].  Weights 4j..4j+3 = grid[qs[j] | ((qh[j//8] >> j%8) & 1) << 8];
+    sign bits of weights 8m..8m+7 = signs[m]; scale of group g (32 weights) = nibble g%2 of scales[g//2]: db = d*(1+2s)
+    (gguf/quants.py IQ3_S)."""
+    b = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, 110)
+    n = b.shape[0]
+    d = _f16(b[:, 0:2])
+    qs, qh, signs, scb = b[:, 2:66], b[:, 66:74], b[:, 74:106], b[:, 106:110]
+    j = np.arange(64)
+    idx = qs.astype(np.uint16) | (((qh[:, j // 8] >> (j % 8).astype(np.uint8)) & 1).astype(np.uint16) << 8)
+    sc = np.stack([scb & 0x0F, scb >> 4], axis=-1).reshape(n, 8)
+    with np.errstate(all="ignore"):
+        db = (d * (1 + 2 * sc).astype(np.float32)).astype(np.float32)
+        g = _grid("iq3s")[idx].astype(np.float32).reshape(n, 8, 4, 8)
+        y = ((db[:, :, None, None] * g).astype(np.float32) * _sign_from_bits(signs).reshape(n, 8, 4, 8)).astype(np.float32)
+    return y.reshape(n, 256)
+
+
+IQ1_DELTA = np.float32(0.125)
+
+
+def dequant_iq1s_f32(blocks: np.ndarray) -> np.ndarray:
+    """[n,50] (d f16 | qs[32] | 8 x u16 qh) -> [n,256].  Group g (32 weights), entry k<4 (8 weights): 11-bit index
+    qs[4g+k] | ((qh[g] >> 3k) & 7) << 8 into a grid of values in {-1,0,1}; dl = d*(2*((qh[g]>>12)&7)+1); delta = -0.125 when bit 15 of
+    qh[g] is set else +0.125; y = dl * (grid + delta) (gguf/quants.py IQ1_S)."""
+    b = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, 50)
+    n = b.shape[0]
+    d = _f16(b[:, 0:2])
+    qs = b[:, 2:34].reshape(n, 8, 4)
+    qh = np.ascontiguousarray(b[:, 34:50]).view("<u2").reshape(n, 8)
+    idx = qs.astype(np.uint16) | (((qh[:, :, None] >> np.array([0, 3, 6, 9], np.uint16)) & 7) << 8)
+    with np.errstate(all="ignore"):
+        dl = (d * (2 * ((qh >> 12) & 7) + 1).astype(np.float32)).astype(np.float32)
+        delta = np.where((qh & 0x8000) == 0, IQ1_DELTA, -IQ1_DELTA).astype(np.float32)
+        g = _grid("iq1s")[idx].astype(np.float32) - np.float32(1)  # stored + 1
+        y = (dl[:, :, None, None] * (g + delta[:, :, None, None]).astype(np.float32)).astype(np.float32)
+    return y.reshape(n, 256)
+
+
+def dequant_iq1m_f32(blocks: np.ndarray) -> np.ndarray:
+    """[n,56] (qs[32] | qh[16] | 4 x u16 scales) -> [n,256].  The fp16 super-scale d is spread over the top nibbles of the four scale
+    words (word i holds bits 4i..4i+3); 3-bit scale of weights 16k..16k+15 = (scales16[k//4] >> 3(k%4)) & 7, dl = d*(2s+1).  Entry j
+    (8 weights): nibble j%2 of qh[j//2]: low 3 bits extend the index qs[j] to 11 bits (grid shared with IQ1_S), bit 3 selects
+    delta = -0.125 (gguf/quants.py IQ1_M)."""
+    b = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, 56)
+    n = b.shape[0]
+    qs, qh = b[:, 0:32], b[:, 32:48]
+    sc16 = np.ascontiguousarray(b[:, 48:56]).view("<u2").reshape(n, 4)
+    dbits = ((sc16[:, 0] >> 12) | ((sc16[:, 1] >> 12) << 4) | ((sc16[:, 2] >> 12) << 8) | ((sc16[:, 3] >> 12) << 12)).astype(np.uint16)
+    d = dbits.view(np.float16).astype(np.float32).reshape(n, 1)
+    k = np.arange(16)
+    s3 = (sc16[:, k // 4] >> (3 * (k % 4)).astype(np.uint16)) & 7
+    j = np.arange(32)
+    nib = (qh[:, j // 2] >> (4 * (j % 2)).astype(np.uint8)) & 0x0F
+    idx = qs.astype(np.uint16) | ((nib & 7).astype(np.uint16) << 8)
+    with np.errstate(all="ignore"):
+        dl = (d * (2 * s3 + 1).astype(np.float32)).astype(np.float32)            # [n,16]
+        delta = np.where((nib & 8) == 0, IQ1_DELTA, -IQ1_DELTA).astype(np.float32)  # [n,32]
+        g = _grid("iq1s")[idx].astype(np.float32) - np.float32(1)
+        y = (np.repeat(dl, 2, axis=1)[:, :, None] * (g + delta[:, :, None]).astype(np.float32)).astype(np.float32)
+    return y.reshape(n, 256)
+
+
+def dequant_tq2_0_f32(blocks: np.ndarray) -> np.ndarray:
+    """[n,66] (qs[64] | d f16) -> [n,256]: weight 128h + 32s + i = ((qs[32h+i] >> 2s) & 3) - 1, times d (gguf/quants.py TQ2_0)."""
+    b = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, 66)
+    n = b.shape[0]
+    q = np.empty((n, 2, 4, 32), np.int8)
+    for h in range(2):
+        for s in range(4):
+            q[:, h, s, :] = ((b[:, 32 * h: 32 * h + 32] >> (2 * s)) & 3).astype(np.int8) - np.int8(1)
+    with np.errstate(all="ignore"):
+        return (_f16(b[:, 64:66]) * q.reshape(n, 256).astype(np.float32)).astype(np.float32)
+
+
+def dequant_tq1_0_f32(blocks: np.ndarray) -> np.ndarray:
+    """[n,54] (qs[48] | qh[4] | d f16) -> [n,256].  Base-3 digits, five per byte (four per qh byte): weight e takes byte B and power p,
+    v = (B * 3^p) mod 256, trit = (v * 3) >> 8, y = d * (trit - 1).  e < 160: B = qs[e%32], p = e//32; 160 <= e < 240: B = qs[32 + (e-160)%16],
+    p = (e-160)//16; e >= 240: B = qh[(e-240)%4], p = (e-240)//4 (gguf/quants.py TQ1_0)."""
+    b = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, 54)
+    n = b.shape[0]
+    e = np.arange(256)
+    byte = np.where(e < 160, e % 32, np.where(e < 240, 32 + (e - 160) % 16, 48 + (e - 240) % 4))
+    powr = np.where(e < 160, e // 32, np.where(e < 240, (e - 160) // 16, (e - 240) // 4))
+    v = (b[:, byte].astype(np.uint16) * (3 ** powr).astype(np.uint16)) & 0xFF
+    trit = ((v * 3) >> 8).astype(np.int8) - np.int8(1)
+    with np.errstate(all="ignore"):
+        return (_f16(b[:, 52:54]) * trit.astype(np.float32)).astype(np.float32)
+
+
+NVFP4_VALUES = MXFP4_VALUES  # the same doubled e2m1 code points
+
+
+def ue4m3_to_f32_half(x: np.ndarray) -> np.ndarray:
+    """Unsigned E4M3 scale byte (bias 7; bit 7 ignored) -> HALF its value as fp32; 0x00 and 0x7F decode to 0 (gguf/quants.py NVFP4.ue4m3_to_fp32)."""
+    x = x.astype(np.uint8)
+    e = ((x >> 3) & 0xF).astype(np.int32)
+    m = (x & 7).astype(np.float32)
+    raw = np.where(e == 0, m * np.float32(2.0 ** -9), (np.float32(1) + m / np.float32(8)) * np.exp2(e.astype(np.float32) - np.float32(7)))
+    return np.where((x == 0) | (x == 0x7F), np.float32(0), raw.astype(np.float32) * np.float32(0.5)).astype(np.float32)
+
+
+def dequant_nvfp4_f32(blocks: np.ndarray) -> np.ndarray:
+    """[n,36] (4 x UE4M3 scale | qs[32]) -> [n,64]: sub-block s (16 weights) uses scale byte s and qs[8s..8s+7]: its first 8 weights are the
+    low nibbles, the next 8 the high nibbles; y = scale_half * NVFP4_VALUES[q4] (gguf/quants.py NVFP4)."""
+    b = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, 36)
+    n = b.shape[0]
+    qs = b[:, 4:36].reshape(n, 4, 8)
+    q = np.concatenate([qs & 0x0F, qs >> 4], axis=-1)
+    with np.errstate(all="ignore"):
+        return (ue4m3_to_f32_half(b[:, 0:4])[:, :, None] * NVFP4_VALUES[q].astype(np.float32)).astype(np.float32).reshape(n, 64)
+
+
 # file dtype -> (weights per block, bytes per block, fp32 dequantiser).  Everything the product dequantises to bf16.
 BLOCK_QUANTS = {
     "Q4_0": (32, 18, dequant_q4_0_f32), "Q4_1": (32, 20, dequant_q4_1_f32), "Q5_0": (32, 22, dequant_q5_0_f32),
     "Q5_1": (32, 24, dequant_q5_1_f32), "Q8_0": (32, 34, dequant_q8_0_f32), "Q2_K": (256, 84, dequant_q2k_f32),
     "Q3_K": (256, 110, dequant_q3k_f32), "Q4_K": (256, 144, dequant_q4k_f32), "Q5_K": (256, 176, dequant_q5k_f32),
     "Q6_K": (256, 210, dequant_q6k_f32), "IQ4_NL": (32, 18, dequant_iq4nl_f32), "IQ4_XS": (256, 136, dequant_iq4xs_f32),
-    "MXFP4": (32, 17, dequant_mxfp4_f32),
+    "MXFP4": (32, 17, dequant_mxfp4_f32), "IQ2_XXS": (256, 66, dequant_iq2xxs_f32), "IQ2_XS": (256, 74, dequant_iq2xs_f32),
+    "IQ2_S": (256, 82, dequant_iq2s_f32), "IQ3_XXS": (256, 98, dequant_iq3xxs_f32), "IQ3_S": (256, 110, dequant_iq3s_f32),
+    "IQ1_S": (256, 50, dequant_iq1s_f32), "IQ1_M": (256, 56, dequant_iq1m_f32), "TQ1_0": (256, 54, dequant_tq1_0_f32),
+    "TQ2_0": (256, 66, dequant_tq2_0_f32), "NVFP4": (64, 36, dequant_nvfp4_f32),
 }
 
 

@@ -13,6 +13,8 @@
 #include <cstring>
 #include <vector>
 
+#include "../../kukeon_b200/csrc/kk_iq_grids.h"
+
 namespace {
 
 struct uint4 { uint32_t x, y, z, w; };
@@ -86,6 +88,21 @@ inline float __shfl_sync(unsigned, float v, int src) {
   flag(7);  // a shuffle outside record/replay cannot be emulated
   return v;
 }
+inline uint32_t kk_f2bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+inline uint32_t kk_popc(uint32_t u) { return (uint32_t)__builtin_popcount(u); }
+const uint64_t kGridIq2xxs[KK_GRID_IQ2XXS_SIZE] = {KK_GRID_IQ2XXS_VALUES};
+const uint64_t kGridIq2xs[KK_GRID_IQ2XS_SIZE] = {KK_GRID_IQ2XS_VALUES};
+const uint64_t kGridIq2s[KK_GRID_IQ2S_SIZE] = {KK_GRID_IQ2S_VALUES};
+const uint32_t kGridIq3xxs[KK_GRID_IQ3XXS_SIZE] = {KK_GRID_IQ3XXS_VALUES};
+const uint32_t kGridIq3s[KK_GRID_IQ3S_SIZE] = {KK_GRID_IQ3S_VALUES};
+const uint64_t kGridIq1s[KK_GRID_IQ1S_SIZE] = {KK_GRID_IQ1S_VALUES};
+// an index outside the table is a bug in the code under test, not something to read through
+inline uint64_t kk_grid_iq2xxs(uint32_t i) { if (i >= KK_GRID_IQ2XXS_SIZE) { flag(8); return 0; } return kGridIq2xxs[i]; }
+inline uint64_t kk_grid_iq2xs(uint32_t i) { if (i >= KK_GRID_IQ2XS_SIZE) { flag(8); return 0; } return kGridIq2xs[i]; }
+inline uint64_t kk_grid_iq2s(uint32_t i) { if (i >= KK_GRID_IQ2S_SIZE) { flag(8); return 0; } return kGridIq2s[i]; }
+inline uint32_t kk_grid_iq3xxs(uint32_t i) { if (i >= KK_GRID_IQ3XXS_SIZE) { flag(8); return 0; } return kGridIq3xxs[i]; }
+inline uint32_t kk_grid_iq3s(uint32_t i) { if (i >= KK_GRID_IQ3S_SIZE) { flag(8); return 0; } return kGridIq3s[i]; }
+inline uint64_t kk_grid_iq1s(uint32_t i) { if (i >= KK_GRID_IQ1S_SIZE) { flag(8); return 0; } return kGridIq1s[i]; }
 inline uint32_t kk_ldg8(const uint8_t* p) { return *p; }
 // PRMT (default mode) as the code under test uses it: selector nibble 0 picks byte (sel & 7) of {b:a}; the msb-replicate bit is never set
 inline uint32_t kk_byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
@@ -185,6 +202,16 @@ inline bool run_op(uint32_t op, const Dsts& D, uint32_t pay, uint32_t n, uint64_
     case KK_OP_IQ4NL_BF16: consume_codebook32<KK_IQ4NL_BLOCK_BYTES, 0>(D, pay, n, dst_off, cwarp, lane); return true;
     case KK_OP_MXFP4_BF16: consume_codebook32<KK_MXFP4_BLOCK_BYTES, 1>(D, pay, n, dst_off, cwarp, lane); return true;
     case KK_OP_IQ4XS_BF16: consume_iq4xs(D, pay, n, dst_off, cwarp, lane); return true;
+    case KK_OP_IQ2XXS_BF16: consume_iq2xxs(D, pay, n, dst_off, cwarp, lane); return true;
+    case KK_OP_IQ2XS_BF16: consume_iq2xs(D, pay, n, dst_off, cwarp, lane); return true;
+    case KK_OP_IQ2S_BF16: consume_iq2s(D, pay, n, dst_off, cwarp, lane); return true;
+    case KK_OP_IQ3XXS_BF16: consume_iq3xxs(D, pay, n, dst_off, cwarp, lane); return true;
+    case KK_OP_IQ3S_BF16: consume_iq3s(D, pay, n, dst_off, cwarp, lane); return true;
+    case KK_OP_IQ1S_BF16: consume_iq1s(D, pay, n, dst_off, cwarp, lane); return true;
+    case KK_OP_IQ1M_BF16: consume_iq1m(D, pay, n, dst_off, cwarp, lane); return true;
+    case KK_OP_TQ1_0_BF16: consume_tq1_0(D, pay, n, dst_off, cwarp, lane); return true;
+    case KK_OP_TQ2_0_BF16: consume_tq2_0(D, pay, n, dst_off, cwarp, lane); return true;
+    case KK_OP_NVFP4_BF16: consume_nvfp4(D, pay, n, dst_off, cwarp, lane); return true;
     case KK_OP_Q4K_BF16: consume_q4k(D, pay, n, dst_off, cwarp, lane); return true;
     // elementwise ops: n = elements (COPY: bytes) of the tile, threads indexed 0..511 across the consumer warps
     case KK_OP_COPY: consume_copy(D, pay, n, dst_off, cwarp * 32 + lane); return true;

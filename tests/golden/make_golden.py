@@ -202,6 +202,54 @@ def make_gguf_codebook_quants():
     np.savez_compressed(p + ".bf16.npz", **outs)
 
 
+def make_gguf_lattice_quants():
+    """The lattice i-quants (IQ2_XXS, IQ2_XS, IQ2_S, IQ3_XXS, IQ3_S, IQ1_S, IQ1_M), the ternary types (TQ1_0, TQ2_0) and NVFP4, written by
+    gguf-py's GGUFWriter from random block bytes; expected values from quants.dequantize."""
+    import gguf
+    from gguf import GGMLQuantizationType as Q
+    rng = np.random.Generator(np.random.Philox(key=81))
+
+    def blocks(nblk, bsz, d_off=None):
+        b = rng.integers(0, 256, size=(nblk, bsz), dtype=np.uint8)
+        if d_off is not None:
+            e = rng.integers(5, 12, size=nblk, dtype=np.uint16)
+            m = rng.integers(0, 1024, size=nblk, dtype=np.uint16)
+            sgn = rng.integers(0, 2, size=nblk, dtype=np.uint16) << 15
+            b[:, d_off:d_off + 2] = ((e << 10) | m | sgn).astype("<u2").view(np.uint8).reshape(nblk, 2)
+        return b
+
+    def iq1m(nblk):
+        b = blocks(nblk, 56)
+        d = ((rng.integers(5, 12, size=nblk, dtype=np.uint16) << 10) | rng.integers(0, 1024, size=nblk, dtype=np.uint16)).astype(np.uint16)
+        for i in range(4):  # the fp16 super-scale lives in the top nibbles of the four scale words
+            b[:, 48 + 2 * i + 1] = (b[:, 48 + 2 * i + 1] & 0x0F) | ((((d >> (4 * i)) & 0xF) << 4).astype(np.uint8))
+        return b
+
+    p = os.path.join(HERE, "quants_iq.gguf")
+    w = gguf.GGUFWriter(p, "llama")
+    w.add_tensor("blk.0.attn_q.weight", blocks(2 * 2, 66, 0).reshape(2, 2 * 66), raw_dtype=Q.IQ2_XXS)      # [2, 512]
+    w.add_tensor("blk.0.attn_k.weight", blocks(3 * 1, 74, 0).reshape(3, 74), raw_dtype=Q.IQ2_XS)           # [3, 256]
+    w.add_tensor("blk.0.attn_v.weight", blocks(2 * 1, 82, 0).reshape(2, 82), raw_dtype=Q.IQ2_S)            # [2, 256]
+    w.add_tensor("blk.0.attn_output.weight", blocks(3 * 1, 98, 0).reshape(3, 98), raw_dtype=Q.IQ3_XXS)     # [3, 256]
+    w.add_tensor("blk.0.ffn_gate.weight", blocks(2 * 2, 110, 0).reshape(2, 2 * 110), raw_dtype=Q.IQ3_S)    # [2, 512]
+    w.add_tensor("blk.0.ffn_up.weight", blocks(3 * 1, 50, 0).reshape(3, 50), raw_dtype=Q.IQ1_S)            # [3, 256]
+    w.add_tensor("blk.0.ffn_down.weight", iq1m(2 * 1).reshape(2, 56), raw_dtype=Q.IQ1_M)                   # [2, 256]
+    w.add_tensor("blk.1.attn_q.weight", blocks(3 * 1, 54, 52).reshape(3, 54), raw_dtype=Q.TQ1_0)           # [3, 256]
+    w.add_tensor("blk.1.attn_k.weight", blocks(2 * 1, 66, 64).reshape(2, 66), raw_dtype=Q.TQ2_0)           # [2, 256]
+    w.add_tensor("blk.1.attn_v.weight", blocks(5 * 3, 36).reshape(5, 3 * 36), raw_dtype=Q.NVFP4)           # [5, 192]
+    w.add_tensor("blk.0.attn_norm.weight", rng.standard_normal(12).astype(np.float32))
+    w.write_header_to_file(); w.write_kv_data_to_file(); w.write_tensors_to_file(); w.close()
+    r = gguf.GGUFReader(p)
+    exp, outs = [], {}
+    for t in r.tensors:
+        shape = [int(x) for x in reversed(t.shape.tolist())]
+        exp.append(dict(name=t.name, dtype=t.tensor_type.name, shape=shape, file_offset=int(t.data_offset), nbytes=int(t.n_bytes)))
+        f32 = gguf.quants.dequantize(np.array(t.data), t.tensor_type)
+        outs[t.name] = bits16(torch.from_numpy(np.ascontiguousarray(f32, dtype=np.float32)).to(torch.bfloat16)).reshape(-1)
+    json.dump(dict(tensors=exp, alignment=int(r.alignment), data_offset=int(r.data_offset)), open(p + ".expected.json", "w"), indent=1)
+    np.savez_compressed(p + ".bf16.npz", **outs)
+
+
 def make_sharded():
     from huggingface_hub import save_torch_state_dict
     d = os.path.join(HERE, "sharded")
@@ -232,7 +280,7 @@ def make_cast_vectors():
 
 
 if __name__ == "__main__":
-    make_safetensors(); make_gguf(); make_gguf_mixed_quants(); make_gguf_legacy_and_k_quants(); make_gguf_codebook_quants(); make_sharded(); make_cast_vectors()
+    make_safetensors(); make_gguf(); make_gguf_mixed_quants(); make_gguf_legacy_and_k_quants(); make_gguf_codebook_quants(); make_gguf_lattice_quants(); make_sharded(); make_cast_vectors()
     for r, _, fs in os.walk(HERE):
         for f in sorted(fs):
             p = os.path.join(r, f)

@@ -12,12 +12,17 @@ from oracle import oracle
 
 OP_COPY, OP_F32, OP_F16, OP_Q4K, OP_T_F32_BF16, OP_T_F16_BF16, OP_T_B16, OP_T_B32, OP_Q8_0, OP_Q6K, OP_ROWSPLIT = range(11)
 OP_Q4_0, OP_Q4_1, OP_Q5_0, OP_Q5_1, OP_Q2K, OP_Q3K, OP_Q5K, OP_F8E4M3, OP_F8E5M2, OP_T8_F32_BF16, OP_T8_F16_BF16, OP_T8_B16, OP_IQ4NL, OP_IQ4XS, OP_MXFP4, OP_TW_F32_BF16, OP_TW_F16_BF16, OP_TW_B16 = range(11, 29)
+OP_IQ2XXS, OP_IQ2XS, OP_IQ2S, OP_IQ3XXS, OP_IQ3S, OP_IQ1S, OP_IQ1M, OP_TQ1_0, OP_TQ2_0, OP_NVFP4 = range(29, 39)
 # block-dequantising ops: op -> (source bytes per block, bf16 bytes per block, blocks per tile)   (csrc/kk_ops.h kk_block_geom)
 BLOCK_GEOM = {OP_Q4K: (144, 512, 224), OP_Q8_0: (34, 64, 960), OP_Q6K: (210, 512, 152), OP_Q4_0: (18, 64, 1816), OP_Q4_1: (20, 64, 1632),
               OP_Q5_0: (22, 64, 1488), OP_Q5_1: (24, 64, 1360), OP_Q2K: (84, 512, 388), OP_Q3K: (110, 512, 296), OP_Q5K: (176, 512, 186),
-              OP_IQ4NL: (18, 64, 1816), OP_IQ4XS: (136, 512, 240), OP_MXFP4: (17, 64, 1920)}
+              OP_IQ4NL: (18, 64, 1816), OP_IQ4XS: (136, 512, 240), OP_MXFP4: (17, 64, 1920), OP_IQ2XXS: (66, 512, 496), OP_IQ2XS: (74, 512, 440),
+              OP_IQ2S: (82, 512, 392), OP_IQ3XXS: (98, 512, 328), OP_IQ3S: (110, 512, 296), OP_IQ1S: (50, 512, 648), OP_IQ1M: (56, 512, 584),
+              OP_TQ1_0: (54, 512, 600), OP_TQ2_0: (66, 512, 496), OP_NVFP4: (36, 128, 908)}
 BLOCK_DTYPE = {OP_Q4K: "Q4_K", OP_Q8_0: "Q8_0", OP_Q6K: "Q6_K", OP_Q4_0: "Q4_0", OP_Q4_1: "Q4_1", OP_Q5_0: "Q5_0", OP_Q5_1: "Q5_1",
-               OP_Q2K: "Q2_K", OP_Q3K: "Q3_K", OP_Q5K: "Q5_K", OP_IQ4NL: "IQ4_NL", OP_IQ4XS: "IQ4_XS", OP_MXFP4: "MXFP4"}
+               OP_Q2K: "Q2_K", OP_Q3K: "Q3_K", OP_Q5K: "Q5_K", OP_IQ4NL: "IQ4_NL", OP_IQ4XS: "IQ4_XS", OP_MXFP4: "MXFP4",
+               OP_IQ2XXS: "IQ2_XXS", OP_IQ2XS: "IQ2_XS", OP_IQ2S: "IQ2_S", OP_IQ3XXS: "IQ3_XXS", OP_IQ3S: "IQ3_S", OP_IQ1S: "IQ1_S", OP_IQ1M: "IQ1_M",
+               OP_TQ1_0: "TQ1_0", OP_TQ2_0: "TQ2_0", OP_NVFP4: "NVFP4"}
 
 
 def emulate_part(plan: dict, part: int, pool_bytes: int, exchange: dict | None = None) -> Tuple[np.ndarray, np.ndarray]:

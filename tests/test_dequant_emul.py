@@ -18,8 +18,10 @@ from tools import synth
 _HERE = os.path.dirname(os.path.abspath(__file__))
 OPS = {"Q4_K": helpers.OP_Q4K, "Q8_0": helpers.OP_Q8_0, "Q6_K": helpers.OP_Q6K, "Q4_0": helpers.OP_Q4_0, "Q4_1": helpers.OP_Q4_1, "Q5_0": helpers.OP_Q5_0,
        "Q5_1": helpers.OP_Q5_1, "Q2_K": helpers.OP_Q2K, "Q3_K": helpers.OP_Q3K, "Q5_K": helpers.OP_Q5K, "IQ4_NL": helpers.OP_IQ4NL,
-       "IQ4_XS": helpers.OP_IQ4XS, "MXFP4": helpers.OP_MXFP4}
-ERR = {1: "shared-memory load outside the staged tile", 2: "misaligned 16/32-bit shared-memory load", 3: "store outside the output window or not 16-byte aligned",
+       "IQ4_XS": helpers.OP_IQ4XS, "MXFP4": helpers.OP_MXFP4, "IQ2_XXS": helpers.OP_IQ2XXS, "IQ2_XS": helpers.OP_IQ2XS, "IQ2_S": helpers.OP_IQ2S,
+       "IQ3_XXS": helpers.OP_IQ3XXS, "IQ3_S": helpers.OP_IQ3S, "IQ1_S": helpers.OP_IQ1S, "IQ1_M": helpers.OP_IQ1M, "TQ1_0": helpers.OP_TQ1_0,
+       "TQ2_0": helpers.OP_TQ2_0, "NVFP4": helpers.OP_NVFP4}
+ERR = {8: "codebook index outside its table", 1: "shared-memory load outside the staged tile", 2: "misaligned 16/32-bit shared-memory load", 3: "store outside the output window or not 16-byte aligned",
        4: "two lanes stored the same 16 bytes"}
 
 
@@ -79,7 +81,7 @@ def test_full_tile_finite_scales(emul, dtype):
 def test_ragged_counts_and_every_alignment_random_bytes(emul, dtype):
     """Fully random bytes (Inf/NaN scales included: NaN -> 0x7FFF on both sides) at every start alignment a tile can have."""
     nel, nb, _ = oracle.BLOCK_QUANTS[dtype]
-    per_iter = 8 if nel == 32 else 4 if dtype == "Q4_K" else 1  # blocks one warp iteration covers
+    per_iter = 8 if nel == 32 else 4 if dtype in ("Q4_K", "NVFP4") else 1  # blocks one warp iteration covers
     rng = np.random.default_rng(5)
     counts = [1, 2, per_iter - 1 or 1, per_iter, per_iter + 1, 16 * per_iter - 1, 16 * per_iter, 16 * per_iter + 1, 16 * per_iter + 5, 37 * per_iter + 3]
     for k, n in enumerate(counts):

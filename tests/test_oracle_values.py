@@ -146,9 +146,35 @@ F4_TYPES = ["Q4_0", "Q4_1", "Q5_0", "Q5_1", "Q2_K", "Q3_K", "Q5_K"]
 
 
 CB_TYPES = ["IQ4_NL", "IQ4_XS", "MXFP4"]
+IQ_TYPES = ["IQ2_XXS", "IQ2_XS", "IQ2_S", "IQ3_XXS", "IQ3_S", "IQ1_S", "IQ1_M", "TQ1_0", "TQ2_0", "NVFP4"]
+SCALE_OFFS = {"Q4_0": [0], "Q4_1": [0, 2], "Q5_0": [0], "Q5_1": [0, 2], "Q2_K": [80, 82], "Q3_K": [108], "Q5_K": [0, 2], "Q4_K": [0, 2], "Q6_K": [208], "Q8_0": [0],
+              "IQ4_NL": [0], "IQ4_XS": [0], "MXFP4": [], "IQ2_XXS": [0], "IQ2_XS": [0], "IQ2_S": [0], "IQ3_XXS": [0], "IQ3_S": [0], "IQ1_S": [0], "IQ1_M": [],
+              "TQ1_0": [52], "TQ2_0": [64], "NVFP4": []}
 
 
-@pytest.mark.parametrize("dtype", F4_TYPES + CB_TYPES + ["Q4_K", "Q6_K", "Q8_0"])
+def test_generated_codebooks_equal_gguf_py():
+    """oracle/iq_grids.py, oracle/iq_grids_c.h and kukeon_b200/csrc/kk_iq_grids.h are generated files: re-derive them from gguf-py here."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_iq_grids", os.path.join(root, "tools", "gen_iq_grids.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    from oracle.iq_grids import GRIDS
+    T = gen.tables()
+    assert set(T) == set(GRIDS)
+    for name, g in T.items():
+        assert [bytes(r.tolist()) for r in g] == GRIDS[name], name
+    h1 = open(os.path.join(root, "kukeon_b200", "csrc", "kk_iq_grids.h")).read()
+    assert h1 == open(os.path.join(root, "oracle", "iq_grids_c.h")).read()
+    for name, g in T.items():
+        w = g.shape[1]
+        words = [int.from_bytes(bytes(r.tolist()), "little") for r in g]
+        for x in (words[0], words[len(words) // 2], words[-1]):
+            assert (f"0x{x:016x}ull" if w == 8 else f"0x{x:08x}u") in h1
+    assert (oracle.KSIGNS == np.frombuffer(__import__("gguf").quants.IQ2_XXS.ksigns, np.uint8)).all()
+
+
+@pytest.mark.parametrize("dtype", F4_TYPES + CB_TYPES + IQ_TYPES + ["Q4_K", "Q6_K", "Q8_0"])
 def test_every_block_quant_vs_gguf_py_live_bit_exact(coracle, dtype):
     """§8(f4): numpy restatement and C twin against gguf.quants.dequantize on (a) fully random bytes — Inf/NaN scales
     included, compared as fp32 bit patterns with NaN == NaN — and (b) finite-scale synthetic blocks after RNE to bf16."""
@@ -168,8 +194,7 @@ def test_every_block_quant_vs_gguf_py_live_bit_exact(coracle, dtype):
     for fill in (0x00, 0xFF):
         for h in (0x3C00, 0x7BFF, 0xBC00):
             e = np.full((2, nb), fill, np.uint8)
-            for off in {"Q4_0": [0], "Q4_1": [0, 2], "Q5_0": [0], "Q5_1": [0, 2], "Q2_K": [80, 82], "Q3_K": [108], "Q5_K": [0, 2], "Q4_K": [0, 2],
-                        "Q6_K": [208], "Q8_0": [0], "IQ4_NL": [0], "IQ4_XS": [0], "MXFP4": []}[dtype]:
+            for off in SCALE_OFFS[dtype]:
                 e[:, off:off + 2] = np.array([h], "<u2").view(np.uint8)
             with np.errstate(all="ignore"):
                 ref = bits16(torch.from_numpy(quants.dequantize(e, qt)).to(torch.bfloat16))
@@ -190,7 +215,7 @@ def test_mxfp4_every_shared_exponent_vs_gguf_py(coracle):
     assert (oracle.dequant_bf16("MXFP4", b) == ref).all() and (coracle.dequant_to_bf16("MXFP4", b) == ref).all()
 
 
-@pytest.mark.parametrize("fixture,types", [("quants_f4.gguf", F4_TYPES), ("quants_cb.gguf", CB_TYPES)])
+@pytest.mark.parametrize("fixture,types", [("quants_f4.gguf", F4_TYPES), ("quants_cb.gguf", CB_TYPES), ("quants_iq.gguf", IQ_TYPES)])
 def test_legacy_k_and_codebook_quant_golden_files_vs_gguf_py(fixture, types):
     import json
     p = os.path.join(G, fixture)

@@ -241,7 +241,8 @@ def test_unsupported_quant_is_refused_at_plan_time(native, tmp_path):
         gpupool.plan_describe(p)
 
 
-F4_MIX = ["Q4_0", "Q4_1", "Q5_0", "Q5_1", "Q2_K", "Q3_K", "Q5_K", "IQ4_NL", "IQ4_XS", "MXFP4"]
+F4_MIX = ["Q4_0", "Q4_1", "Q5_0", "Q5_1", "Q2_K", "Q3_K", "Q5_K", "IQ4_NL", "IQ4_XS", "MXFP4", "IQ2_XXS", "IQ2_XS", "IQ2_S", "IQ3_XXS", "IQ3_S", "IQ1_S",
+          "IQ1_M", "TQ1_0", "TQ2_0", "NVFP4"]
 
 
 def f4_tensors(hidden=256, ffn=768, layers=2, vocab=512):
@@ -253,7 +254,11 @@ def f4_tensors(hidden=256, ffn=768, layers=2, vocab=512):
               (p + "attn_v.weight", "Q5_0", [hidden // 4, hidden]), (p + "attn_output.weight", "Q5_1", [hidden, hidden]),
               (p + "ffn_gate.weight", "Q3_K", [ffn, hidden]), (p + "ffn_up.weight", "Q5_K", [ffn, hidden]), (p + "ffn_down.weight", "Q2_K", [hidden, ffn]),
               (p + "ffn_gate_exps.weight", "MXFP4", [2, ffn, hidden]), (p + "ffn_up_exps.weight", "IQ4_XS", [2, ffn, hidden]),
-              (p + "ffn_down_exps.weight", "IQ4_NL", [2, hidden, ffn])]
+              (p + "ffn_down_exps.weight", "IQ4_NL", [2, hidden, ffn]),
+              (p + "a.weight", "IQ2_XXS", [hidden, hidden]), (p + "b.weight", "IQ2_XS", [hidden // 4, hidden]), (p + "c.weight", "IQ2_S", [hidden // 4, hidden]),
+              (p + "d.weight", "IQ3_XXS", [hidden, hidden]), (p + "e.weight", "IQ3_S", [ffn, hidden]), (p + "f.weight", "IQ1_S", [ffn, hidden]),
+              (p + "g.weight", "IQ1_M", [hidden, ffn]), (p + "h.weight", "TQ1_0", [hidden, hidden]), (p + "i.weight", "TQ2_0", [hidden, hidden]),
+              (p + "j.weight", "NVFP4", [hidden, hidden])]
     t += [("output_norm.weight", "F32", [hidden]), ("output.weight", "Q5_K", [vocab, hidden])]
     return t
 
@@ -264,7 +269,8 @@ def test_legacy_and_k_quant_plan(native, tmp_path):
     plan = run_case(p, chunk=1 * MB)
     ops = {sg["op"] for ch in plan["parts"][0]["chunks"] for sg in ch["segs"]}
     assert {helpers.OP_Q4_0, helpers.OP_Q4_1, helpers.OP_Q5_0, helpers.OP_Q5_1, helpers.OP_Q2K, helpers.OP_Q3K, helpers.OP_Q5K, helpers.OP_IQ4NL,
-            helpers.OP_IQ4XS, helpers.OP_MXFP4} <= ops
+            helpers.OP_IQ4XS, helpers.OP_MXFP4, helpers.OP_IQ2XXS, helpers.OP_IQ2XS, helpers.OP_IQ2S, helpers.OP_IQ3XXS, helpers.OP_IQ3S, helpers.OP_IQ1S,
+            helpers.OP_IQ1M, helpers.OP_TQ1_0, helpers.OP_TQ2_0, helpers.OP_NVFP4} <= ops
     run_case(p, mode=gpupool.MODE_BROADCAST, n_parts=3, chunk=1 * MB)
     plan = run_case(p, mode=gpupool.MODE_SCATTER, n_parts=4, chunk=1 * MB)
     lay = {t["name"]: t for t in plan["layouts"][1]["tensors"]}
@@ -272,6 +278,7 @@ def test_legacy_and_k_quant_plan(native, tmp_path):
     assert lay["blk.0.ffn_down.weight"]["slice_dim"] is None  # dim-1 slices would cut quantised blocks
     run_case(os.path.join(G, "quants_f4.gguf"))
     run_case(os.path.join(G, "quants_cb.gguf"))
+    run_case(os.path.join(G, "quants_iq.gguf"))
     # tensors bigger than one tile of every type, so that tile boundaries inside a tensor are exercised (Q4_0: 1816 blocks/tile)
     big = [(f"blk.{i}.ffn_up.weight", dt, [96, 2048]) for i, dt in enumerate(F4_MIX)]
     p2 = str(tmp_path / "f4big.gguf")

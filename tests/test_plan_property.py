@@ -69,7 +69,8 @@ def test_random_inventories_plan_to_the_oracle_pool(native, inv, mode, n_parts, 
             assert (acc == exp).all()
 
 
-GG_TYPES = ["F32", "F16", "BF16", "Q4_0", "Q4_1", "Q5_0", "Q5_1", "Q8_0", "Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K", "IQ4_NL", "IQ4_XS", "MXFP4"]
+GG_TYPES = ["F32", "F16", "BF16", "Q4_0", "Q4_1", "Q5_0", "Q5_1", "Q8_0", "Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K", "IQ4_NL", "IQ4_XS", "MXFP4", "IQ2_XXS",
+            "IQ2_XS", "IQ2_S", "IQ3_XXS", "IQ3_S", "IQ1_S", "IQ1_M", "TQ1_0", "TQ2_0", "NVFP4"]
 GG_NAMES = ["attn_q.weight", "attn_output.weight", "ffn_up.weight", "ffn_down.weight", "attn_norm.weight", "ffn_gate_exps.weight", "misc.weight"]
 
 

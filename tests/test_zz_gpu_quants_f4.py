@@ -22,7 +22,7 @@ G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 MB = 1 << 20
 
 
-@pytest.mark.parametrize("fixture", ["quants_f4.gguf", "quants_cb.gguf"])
+@pytest.mark.parametrize("fixture", ["quants_f4.gguf", "quants_cb.gguf", "quants_iq.gguf"])
 def test_golden_fixture_values_vs_gguf_py(pool, fixture):
     g = os.path.join(G, fixture)
     load_and_check(pool, g)
@@ -50,7 +50,7 @@ def test_llama_shaped_mix_of_every_type(pool, tmp_path):
     p = str(tmp_path / "f4.gguf")
     synth.write_gguf(p, f4_tensors(hidden=512, ffn=1536, layers=2, vocab=1024), 11)
     st = load_and_check(pool, p)
-    assert st["n_tensors"] == 2 * 11 + 3
+    assert st["n_tensors"] == 2 * 21 + 3
 
 
 def a8_file(path):

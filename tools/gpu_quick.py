@@ -50,6 +50,7 @@ def main():
 
     check("golden quants_f4 (Q4_0 Q4_1 Q5_0 Q5_1 Q2_K Q3_K Q5_K)", os.path.join(G, "quants_f4.gguf"))
     check("golden quants_cb (IQ4_NL IQ4_XS MXFP4)", os.path.join(G, "quants_cb.gguf"))
+    check("golden quants_iq (IQ2_XXS IQ2_XS IQ2_S IQ3_XXS IQ3_S IQ1_S IQ1_M TQ1_0 TQ2_0 NVFP4)", os.path.join(G, "quants_iq.gguf"))
     with tempfile.TemporaryDirectory() as d:
         from tests.test_plan import f4_tensors
         p = os.path.join(d, "f4.gguf")

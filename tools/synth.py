@@ -24,9 +24,11 @@ ST_ITEMSIZE = {"F32": 4, "F16": 2, "BF16": 2, "I64": 8, "I32": 4, "U8": 1, "I8":
                "F8_E4M3": 1, "F8_E5M2": 1}
 GGML = {"F32": (0, 1, 4), "F16": (1, 1, 2), "Q4_K": (12, 256, 144), "BF16": (30, 1, 2), "Q8_0": (8, 32, 34), "Q6_K": (14, 256, 210),
         "Q4_0": (2, 32, 18), "Q4_1": (3, 32, 20), "Q5_0": (6, 32, 22), "Q5_1": (7, 32, 24), "Q2_K": (10, 256, 84), "Q3_K": (11, 256, 110),
-        "Q5_K": (13, 256, 176), "IQ4_NL": (20, 32, 18), "IQ4_XS": (23, 256, 136), "MXFP4": (39, 32, 17)}
+        "Q5_K": (13, 256, 176), "IQ4_NL": (20, 32, 18), "IQ4_XS": (23, 256, 136), "MXFP4": (39, 32, 17),
+        "IQ2_XXS": (16, 256, 66), "IQ2_XS": (17, 256, 74), "IQ2_S": (22, 256, 82), "IQ3_XXS": (18, 256, 98), "IQ3_S": (21, 256, 110), "IQ1_S": (19, 256, 50), "IQ1_M": (29, 256, 56), "TQ1_0": (34, 256, 54), "TQ2_0": (35, 256, 66), "NVFP4": (40, 64, 36)}
 _KIND = {"BF16": 1, "F16": 2, "F32": 3, "Q4_K": 4, "Q8_0": 5, "Q6_K": 6, "Q4_0": 7, "Q4_1": 8, "Q5_0": 9, "Q5_1": 10, "Q2_K": 11, "Q3_K": 12,
-         "Q5_K": 13, "IQ4_NL": 14, "IQ4_XS": 15, "MXFP4": 16}
+         "Q5_K": 13, "IQ4_NL": 14, "IQ4_XS": 15, "MXFP4": 16,
+         "IQ2_XXS": 17, "IQ2_XS": 18, "IQ2_S": 19, "IQ3_XXS": 20, "IQ3_S": 21, "IQ1_S": 22, "IQ1_M": 23, "TQ1_0": 24, "TQ2_0": 25, "NVFP4": 26}
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libkk_synth.so")
 _lib = None

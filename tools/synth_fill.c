@@ -16,7 +16,8 @@
 
 enum { K_BYTES = 0, K_BF16 = 1, K_F16 = 2, K_F32 = 3, K_Q4K = 4, K_Q8_0 = 5, K_Q6K = 6,
        K_Q4_0 = 7, K_Q4_1 = 8, K_Q5_0 = 9, K_Q5_1 = 10, K_Q2K = 11, K_Q3K = 12, K_Q5K = 13,
-       K_IQ4NL = 14, K_IQ4XS = 15, K_MXFP4 = 16 };
+       K_IQ4NL = 14, K_IQ4XS = 15, K_MXFP4 = 16,
+       K_IQ2XXS = 17, K_IQ2XS = 18, K_IQ2S = 19, K_IQ3XXS = 20, K_IQ3S = 21, K_IQ1S = 22, K_IQ1M = 23, K_TQ1_0 = 24, K_TQ2_0 = 25, K_NVFP4 = 26 };
 
 static inline uint64_t mix64(uint64_t x) {
   x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
@@ -84,6 +85,16 @@ static blk_geom geom_of(int kind) {
     case K_Q5K: return (blk_geom){176, 0, 2};
     case K_IQ4NL: return (blk_geom){18, 0, -1};
     case K_IQ4XS: return (blk_geom){136, 0, -1};
+    case K_IQ2XXS: return (blk_geom){66, 0, -1};
+    case K_IQ2XS: return (blk_geom){74, 0, -1};
+    case K_IQ2S: return (blk_geom){82, 0, -1};
+    case K_IQ3XXS: return (blk_geom){98, 0, -1};
+    case K_IQ3S: return (blk_geom){110, 0, -1};
+    case K_IQ1S: return (blk_geom){50, 0, -1};
+    case K_IQ1M: return (blk_geom){56, -1, -1}; /* fp16 scale spread over four nibbles, fixed up below */
+    case K_TQ1_0: return (blk_geom){54, 52, -1};
+    case K_TQ2_0: return (blk_geom){66, 64, -1};
+    case K_NVFP4: return (blk_geom){36, -1, -1}; /* four UE4M3 scale bytes: any byte is finite */
     case K_MXFP4: return (blk_geom){17, -1, -1}; /* no fp16 scale: byte 0 is an E8M0 exponent, fixed up below */
     default: return (blk_geom){0, 0, -1};
   }
@@ -103,6 +114,18 @@ static void fix_blocks(uint8_t* buf, uint64_t first_block, uint64_t nblocks, int
       for (uint64_t b = 0; b < nblocks; ++b) buf[g.bsz * b] = (uint8_t)(108 + rnd(seed ^ 0xE8E8ull, idx, first_block + b) % 30);
       return;
     }
+    if (kind == K_IQ1M) { /* a finite fp16 in [2^-10, 2^-4], one nibble into the top of each of the four scale words at byte 48 */
+      for (uint64_t b = 0; b < nblocks; ++b) {
+        uint64_t r = rnd(seed ^ 0x1713ull, idx, first_block + b);
+        uint16_t d = (uint16_t)((((r & 0xFF) % 7 + 5) << 10) | ((r >> 8) & 0x3FF));
+        for (int i = 0; i < 4; ++i) {
+          uint8_t* hi = buf + g.bsz * b + 48 + 2 * i + 1;
+          *hi = (uint8_t)((*hi & 0x0F) | (((d >> (4 * i)) & 0xF) << 4));
+        }
+      }
+      return;
+    }
+    if (g.d_off < 0) return;
     fix_scale(buf, first_block, nblocks, g.bsz, (uint64_t)g.d_off, seed, idx);
     if (g.m_off >= 0) fix_scale(buf, first_block, nblocks, g.bsz, (uint64_t)g.m_off, seed ^ 0x3117ull, idx);
   }
