@@ -241,6 +241,32 @@ inline bool run_warps(uint32_t op, const Dsts& D, uint32_t pay, uint32_t n, uint
   return true;
 }
 
+// Shared-memory wavefronts of per-lane load traces: the k-th recorded load of every lane of a warp is one warp instruction; it needs as
+// many wavefronts as the worst bank has distinct 4-byte words (same word = broadcast).  Adds to wavefronts / ideal.
+void count_wavefronts(const std::vector<std::vector<uint32_t>>& traces, uint64_t& wavefronts, uint64_t& ideal) {
+  for (size_t w = 0; w + 31 < traces.size(); w += 32) {
+    size_t longest = 0;
+    for (int l = 0; l < 32; ++l) longest = std::max(longest, traces[w + l].size());
+    for (size_t k = 0; k < longest; ++k) {
+      std::vector<uint32_t> words[32];
+      bool any = false;
+      for (int l = 0; l < 32; ++l) {
+        const auto& tr = traces[w + l];
+        if (k >= tr.size()) continue;
+        any = true;
+        const uint32_t word = tr[k] >> 2;
+        auto& v = words[word & 31u];
+        if (std::find(v.begin(), v.end(), word) == v.end()) v.push_back(word);
+      }
+      if (!any) continue;
+      size_t worst = 1;
+      for (auto& v : words) worst = std::max(worst, v.size());
+      wavefronts += worst;
+      ideal += 1;
+    }
+  }
+}
+
 // Run the consumer side of one tile of block op `op` (KKOp): `nblk` blocks whose first byte sits at tile[pay_off].
 // out receives nblk * out_bytes_per_block bytes; hits (out_bytes/16 counters, zeroed here) how often each 16-byte unit
 // was stored.  Returns 0, a positive Emu::err code, or -1 for an op this harness does not cover.
@@ -254,6 +280,38 @@ extern "C" int kk_emul_dequant_tile(uint32_t op, const uint8_t* tile, uint32_t t
   g.byte_mask = bmask.data();
   const Dsts D{0};
   if (!run_warps(op, D, pay_off, nblk, 0)) return -1;
+  return g.err;
+}
+
+// Same as kk_emul_dequant_tile, additionally reporting the shared-memory wavefronts of the 16/32-bit loads (stats[0]) against one per warp
+// load instruction (stats[1]).  Only meaningful when all lanes of a warp execute the same loads (full warps of a full tile); byte loads
+// (lds8) and vector loads (lds64 / lds128) are not traced.  Ops that shuffle are traced in their replay pass.
+extern "C" int kk_emul_dequant_tile_stats(uint32_t op, const uint8_t* tile, uint32_t tile_bytes, uint32_t pay_off, uint32_t nblk, uint8_t* out,
+                                          uint64_t out_bytes, uint8_t* hits, uint64_t* stats) {
+  g = Emu{};
+  g.tile = tile; g.tile_bytes = tile_bytes; g.out = out; g.out_bytes = out_bytes; g.hits = hits;
+  memset(hits, 0, (out_bytes + 15) / 16);
+  std::vector<uint8_t> mask(out_bytes / 2 + 1, 0), bmask(out_bytes + 1, 0);
+  g.out_mask = mask.data();
+  g.byte_mask = bmask.data();
+  const Dsts D{0};
+  const bool shuffles = op == KK_OP_Q4K_BF16;
+  std::vector<std::vector<uint32_t>> traces((size_t)kConsumerWarps * 32);
+  for (int cwarp = 0; cwarp < kConsumerWarps; ++cwarp)
+    for (int pass = shuffles ? 1 : 0; pass <= (shuffles ? 2 : 0); ++pass) {
+      g.shfl_mode = pass;
+      for (int lane = 0; lane < 32; ++lane) {
+        g.lane = lane;
+        g.shfl_calls = 0;
+        g.trace = pass == 1 ? nullptr : &traces[(size_t)(cwarp * 32 + lane)];
+        if (!run_op(op, D, pay_off, nblk, 0, cwarp, lane)) return -1;
+      }
+    }
+  g.trace = nullptr;
+  g.shfl_mode = 0;
+  uint64_t wf = 0, ideal = 0;
+  count_wavefronts(traces, wf, ideal);
+  if (stats) { stats[0] = wf; stats[1] = ideal; }
   return g.err;
 }
 

@@ -35,6 +35,8 @@ def emul():
     L.kk_emul_dequant_segment.restype = C.c_int
     L.kk_emul_t8_tile.argtypes = [C.c_uint32, C.c_void_p] + [C.c_uint32] * 6 + [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]  # T8 and TW ops
     L.kk_emul_t8_tile.restype = C.c_int
+    L.kk_emul_dequant_tile_stats.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]
+    L.kk_emul_dequant_tile_stats.restype = C.c_int
     L.kk_emul_block_geom.argtypes = [C.c_uint32] + [C.POINTER(C.c_uint32)] * 3
     L.kk_emul_block_geom.restype = None
     return L
