@@ -213,6 +213,72 @@ def test_tw_wide_store_tiles_values_write_once_conflicts_and_store_width(emul, d
     assert tw_lines_per_kb * 3.9 < t8_lines_per_kb, (t8, tw)
 
 
+def _run_elementwise(emul, op, src_bytes, n_units, pay_off, out_bytes):
+    tile = np.full(pay_off + src_bytes.size, 0x5A, np.uint8)
+    tile[pay_off:] = src_bytes
+    out = np.zeros(out_bytes, np.uint8)
+    hits = np.zeros((out_bytes + 15) // 16, np.uint8)
+    rc = emul.kk_emul_dequant_tile(op, tile.ctypes.data, tile.size, pay_off, n_units, out.ctypes.data, out.size, hits.ctypes.data)
+    assert rc == 0, ERR.get(rc, rc)
+    want_hits = np.full(hits.size, 16, np.uint8)
+    if out_bytes % 16:
+        want_hits[-1] = out_bytes % 16
+    assert (hits == want_hits).all(), "every output byte stored exactly once"
+    return out
+
+
+def test_copy_and_casts_register_paths_every_alignment_and_tail(emul):
+    """The non-TMA consumer paths of the headline ops: COPY (misaligned / ragged tiles), F32 -> bf16 and F16 -> bf16 — aligned vector
+    loads and byte-assembled ones, counts that end inside a 16-byte group, a full 32 KiB tile."""
+    rng = np.random.default_rng(4)
+    for n in (1, 15, 16, 17, 255, 8191 * 4 + 3, 32768):
+        src = rng.integers(0, 256, n, dtype=np.uint8)
+        for pay_off in (0, 1, 4, 8, 15):
+            if pay_off + n > 32768 + 128:
+                continue
+            assert (_run_elementwise(emul, helpers.OP_COPY, src, n, pay_off, n) == src).all(), ("COPY", n, pay_off)
+    for n in (1, 7, 8, 9, 513, 8192):
+        f32 = synth.gen_bytes("F32", 4 * n, 6, n)
+        f32[:4 * min(n, 4)] = np.array([0x7F800000, 0xFF800001, 0x3F808000, 0x00000001], "<u4").view(np.uint8)[:4 * min(n, 4)]  # inf, NaN, tie, subnormal
+        f16 = synth.gen_bytes("F16", 2 * n, 7, n)
+        for pay_off in (0, 2, 4, 6, 8, 12) + ((1, 3) if n < 600 else ()):
+            got = _run_elementwise(emul, helpers.OP_F32, f32, n, pay_off, 2 * n).view(np.uint16)
+            assert (got == oracle.f32_bits_to_bf16(f32.view("<u4"))).all(), ("F32", n, pay_off)
+            got = _run_elementwise(emul, helpers.OP_F16, f16, n, pay_off, 2 * n).view(np.uint16)
+            assert (got == oracle.f16_bits_to_bf16(f16.view("<u2"))).all(), ("F16", n, pay_off)
+
+
+def test_q4k_shuffle_emulation_is_live(emul):
+    """Q4_K is the one consumer whose lanes trade values (__shfl_sync, emulated by record/replay): swapping two sub-block scale bytes
+    of one block must change exactly that block's output."""
+    blocks = synth.gen_bytes("Q4_K", 144 * 9, 2, 1).reshape(9, 144)
+    base = run_tile(emul, "Q4_K", blocks, 0)
+    mut = blocks.copy()
+    mut[5, 4], mut[5, 5] = blocks[5, 5] ^ 0x15, blocks[5, 4] ^ 0x2A
+    got = run_tile(emul, "Q4_K", mut, 0)
+    assert (got == oracle.dequant_bf16("Q4_K", mut)).all()
+    assert (got[5] != base[5]).any() and (np.delete(got, 5, 0) == np.delete(base, 5, 0)).all()
+
+
+def test_super_block_dequantisers_read_shared_memory_conflict_free(emul):
+    """Bank-conflict accounting from the recorded addresses of the 16/32-bit shared loads: every 256-weight type (one block per warp
+    iteration, lanes side by side inside the block) needs exactly one wavefront per warp load; the 32-weight legacy blocks straddle
+    more than 128 bytes per warp iteration and stay below 2.5."""
+    for dt, op in sorted(OPS.items()):
+        nel, nb, _ = oracle.BLOCK_QUANTS[dt]
+        if dt == "Q4_K":
+            continue  # vector loads (lds128 / lds64), not traced
+        per_sweep = 16 * (8 if nel == 32 else 4 if dt == "NVFP4" else 1)
+        n = geom(emul, op)[2] // per_sweep * per_sweep  # whole sweeps: every lane of every warp executes the same loads
+        blocks = synth.gen_bytes(dt, nb * n, 1, 1)
+        out = np.zeros(n * nel * 2, np.uint8)
+        hits = np.zeros(out.size // 16, np.uint8)
+        st = (C.c_uint64 * 2)()
+        assert emul.kk_emul_dequant_tile_stats(op, blocks.ctypes.data, blocks.size, 0, n, out.ctypes.data, out.size, hits.ctypes.data, st) == 0
+        ratio = st[0] / st[1]
+        assert (ratio == 1.0) if nel >= 64 else (ratio < 2.5), (dt, st[0], st[1])
+
+
 def test_harness_sees_wrong_answers(emul):
     """The checker is live: feeding Q5_0 blocks to the Q4_0 function must not reproduce the Q5_0 oracle."""
     blocks = synth.gen_bytes("Q5_0", 22 * 9 * 8, 2, 1).reshape(-1, 22)
