@@ -42,6 +42,23 @@ KK_DQ_DEV uint32_t lds32_any(uint32_t a) {
   if ((a & 3u) == 0) return lds32(a);
   return lds32_h(a);
 }
+// Eight payload bytes at address a -> two words.  Blocks of 18..210 bytes put them on 2-byte boundaries half of the time: then two aligned
+// 32-bit loads (the first starts 2 bytes early: an address that is 2 mod 4 always has two staged bytes in front of it — the previous block's, or
+// the tile's alignment slack) and one 16-bit
+// load are merged with PRMT, instead of four 16-bit loads.  Odd addresses (17-byte MXFP4 blocks, odd tile offsets) go byte by byte.
+KK_DQ_DEV void lds64_funnel(uint32_t a, uint32_t& q0, uint32_t& q1) {
+  if ((a & 3u) == 0) {
+    q0 = lds32(a);
+    q1 = lds32(a + 4u);
+  } else if ((a & 1u) == 0) {
+    const uint32_t w0 = lds32(a - 2u), w1 = lds32(a + 2u), h = lds16(a + 6u);
+    q0 = kk_byte_perm(w0, w1, 0x5432u);  // bytes 2,3 of w0 then 0,1 of w1
+    q1 = kk_byte_perm(w1, h, 0x5432u);
+  } else {
+    q0 = lds32_bytes(a);
+    q1 = lds32_bytes(a + 4u);
+  }
+}
 KK_DQ_DEV float lds_f16(uint32_t a) { return kk_h2f(lds16_any(a)); }
 KK_DQ_DEV void store_bf16x8(const Dsts& D, uint64_t off, const float (&y)[8]) {
   store16_all(D, off, make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7])));
@@ -65,7 +82,10 @@ KK_DQ_DEV void consume_q8_0(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t
       const uint32_t blk = pay + b * KK_Q8_0_BLOCK_BYTES;
       const float d = kk_h2f(lds16_any(blk));
       const uint32_t qa = blk + 2u + 8u * (uint32_t)(lane & 3);
-      const uint32_t q0 = lds32_h(qa) ^ 0x80808080u, q1 = lds32_h(qa + 4) ^ 0x80808080u;  // int8 -> value + 128, unsigned
+      uint32_t q0, q1;
+      lds64_funnel(qa, q0, q1);
+      q0 ^= 0x80808080u;  // int8 -> value + 128, unsigned
+      q1 ^= 0x80808080u;
       float y[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) y[e] = __fmul_rn(byte_to_float<128>(e < 4 ? q0 : q1, e & 3), d);
@@ -89,8 +109,9 @@ KK_DQ_DEV void consume_q6k(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t 
     const float d = kk_h2f(lds16_any(blk + 208u));
     const int sc = (int)(signed char)lds8(blk + 192u + (uint32_t)(lane >> 1));
     const float dsc = __fmul_rn(d, (float)sc);
-    const uint32_t l0 = lds32_h(blk + ql_off), l1 = lds32_h(blk + ql_off + 4);
-    const uint32_t h0 = lds32_h(blk + qh_off), h1 = lds32_h(blk + qh_off + 4);
+    uint32_t l0, l1, h0, h1;
+    lds64_funnel(blk + ql_off, l0, l1);
+    lds64_funnel(blk + qh_off, h0, h1);
     // four 6-bit values per word: low nibble | high two bits << 4 (q + 32, unsigned)
     const uint32_t w0 = ((l0 >> lsh) & 0x0F0F0F0Fu) | (((h0 >> hsh) & 0x03030303u) << 4);
     const uint32_t w1 = ((l1 >> lsh) & 0x0F0F0F0Fu) | (((h1 >> hsh) & 0x03030303u) << 4);
@@ -124,8 +145,10 @@ KK_DQ_DEV void consume_legacy32(const Dsts& D, uint32_t pay, uint32_t nblk, uint
       const uint32_t blk = pay + b * BYTES;
       const float d = lds_f16(blk);
       const float m = HAS_M ? lds_f16(blk + 2u) : 0.f;
-      uint32_t q0 = (lds32_any(blk + q_off) >> nsh) & 0x0F0F0F0Fu;
-      uint32_t q1 = (lds32_any(blk + q_off + 4u) >> nsh) & 0x0F0F0F0Fu;
+      uint32_t q0, q1;
+      lds64_funnel(blk + q_off, q0, q1);
+      q0 = (q0 >> nsh) & 0x0F0F0F0Fu;
+      q1 = (q1 >> nsh) & 0x0F0F0F0Fu;
       if (HAS_QH) {  // bit 4 of element e0 + k is bit k of this byte of qh
         const uint32_t hbits = (lds32_any(blk + kQhOff) >> e0) & 0xFFu;
         q0 |= spread4(hbits) << 4;
@@ -339,8 +362,10 @@ KK_DQ_DEV void consume_codebook32(const Dsts& D, uint32_t pay, uint32_t nblk, ui
       } else {
         d = lds_f16(blk);
       }
-      const uint32_t q0 = (lds32_any(blk + q_off) >> nsh) & 0x0F0F0F0Fu;
-      const uint32_t q1 = (lds32_any(blk + q_off + 4u) >> nsh) & 0x0F0F0F0Fu;
+      uint32_t q0, q1;
+      lds64_funnel(blk + q_off, q0, q1);
+      q0 = (q0 >> nsh) & 0x0F0F0F0Fu;
+      q1 = (q1 >> nsh) & 0x0F0F0F0Fu;
       float y[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) y[e] = __fmul_rn(d, lut16<TABLE>(((e < 4 ? q0 : q1) >> (8 * (e & 3))) & 0xFu));
