@@ -106,21 +106,53 @@ def _atomic_write(path: str, data: bytes, mode: int = 0o644) -> None:
         pass
 
 
-def Mount(model: gpupool.Model, device: int, container_dir: str, with_devices: bool = False, stat=os.stat) -> MountSpec:
+def _env_suffix(name: str) -> str:
+    """`llama-3.8b` -> `_LLAMA_3_8B` (POSIX environment names: upper-case letters, digits, underscore)."""
+    return "_" + "".join(c.upper() if c.isalnum() else "_" for c in name)
+
+
+def Mount(model: gpupool.Model, device: int, container_dir: str, with_devices: bool = False, stat=os.stat, name: str = "",
+          target: str = CONTAINER_GPUPOOL_DIR) -> MountSpec:
     """Export `device`'s pool for one agent container: write the manifest + IPC handle under
-    `<container_dir>/gpupool/` and describe the read-only bind mount and env that expose them."""
+    `<container_dir>/gpupool/` and describe the read-only bind mount and env that expose them.
+
+    `name` (the `models[].name` of the manifest schema, kukeon_b200/schema.py) gives the model its own sub-directory and
+    env names — `<container_dir>/gpupool/<name>/`, `<target>/<name>/`, `KUKEON_GPUPOOL_MANIFEST_<NAME>` — so that one container can
+    attach several models; without it the single-model layout above is used."""
+    if name and (name in (".", "..") or "/" in name or "\0" in name):
+        raise ValueError(f"model name {name!r} cannot be used as a directory name")
     handle, manifest = model.export(device)
-    host_dir = os.path.join(container_dir, "gpupool")
+    host_dir = os.path.join(container_dir, "gpupool", name) if name else os.path.join(container_dir, "gpupool")
+    dest = f"{target.rstrip('/')}/{name}" if name else target
+    sfx = _env_suffix(name) if name else ""
     os.makedirs(host_dir, mode=0o750, exist_ok=True)
     _atomic_write(os.path.join(host_dir, "manifest.json"), json.dumps(manifest, separators=(",", ":")).encode())
     _atomic_write(os.path.join(host_dir, "ipc.handle"), handle, 0o640)
     devs, rules = device_nodes([device], stat) if with_devices else ([], [])
     return MountSpec(
-        mounts=[{"destination": CONTAINER_GPUPOOL_DIR, "type": "bind", "source": host_dir, "options": ["rbind", "ro"]}],
-        env=[f"{ENV_MANIFEST}={CONTAINER_GPUPOOL_DIR}/manifest.json", f"{ENV_IPC_HANDLE}={CONTAINER_GPUPOOL_DIR}/ipc.handle",
-             f"{ENV_DEVICE}={device}"],
+        mounts=[{"destination": dest, "type": "bind", "source": host_dir, "options": ["rbind", "ro"]}],
+        env=[f"{ENV_MANIFEST}{sfx}={dest}/manifest.json", f"{ENV_IPC_HANDLE}{sfx}={dest}/ipc.handle", f"{ENV_DEVICE}{sfx}={device}"],
         host_dir=host_dir, devices=devs, device_cgroup=rules,
     )
+
+
+def merge_mounts(specs: List[MountSpec]) -> MountSpec:
+    """What the container's BuildOptions add up to when several models are mounted: all mounts and env entries, device nodes and
+    cgroup rules de-duplicated (two models on the same GPU need /dev/nvidia0 once)."""
+    out = MountSpec()
+    for s in specs:
+        out.mounts += s.mounts
+        out.env += s.env
+        for d in s.devices:
+            if d not in out.devices:
+                out.devices.append(d)
+        for r in s.device_cgroup:
+            if r not in out.device_cgroup:
+                out.device_cgroup.append(r)
+    dests = [m["destination"] for m in out.mounts]
+    if len(set(dests)) != len(dests):
+        raise ValueError(f"two models would be mounted at the same container path: {sorted(d for d in dests if dests.count(d) > 1)[0]}")
+    return out
 
 
 class CellHooks:

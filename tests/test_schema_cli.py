@@ -131,3 +131,57 @@ def test_model_validate_and_errors(models_dir, tmp_path, capsys):
 
 def test_format_size_matches_the_reference_helper():
     assert [cli.format_size(n) for n in (-1, 0, 1023, 1024, 1536, 16060522496)] == ["-", "0 B", "1023 B", "1.0 KiB", "1.5 KiB", "15.0 GiB"]
+
+
+class _StubModel:
+    """Mount only needs export(device) -> (64-byte handle, manifest dict)."""
+
+    def __init__(self, tag):
+        self.tag = tag
+
+    def export(self, device):
+        return bytes([self.tag]) * 64, {"apiVersion": "kukeon.gpupool/v1", "device": device, "tensors": [{"name": f"w{self.tag}"}]}
+
+
+def test_mount_single_and_named_models(tmp_path):
+    from kukeon_b200 import modelhub
+    cdir = str(tmp_path / "cell" / "work")
+    one = modelhub.Mount(_StubModel(1), 0, cdir)
+    assert one.mounts == [{"destination": "/run/kukeon/gpupool", "type": "bind", "source": f"{cdir}/gpupool", "options": ["rbind", "ro"]}]
+    assert one.env == ["KUKEON_GPUPOOL_MANIFEST=/run/kukeon/gpupool/manifest.json", "KUKEON_GPUPOOL_IPC_HANDLE=/run/kukeon/gpupool/ipc.handle", "KUKEON_GPUPOOL_DEVICE=0"]
+    assert open(f"{cdir}/gpupool/ipc.handle", "rb").read() == b"\x01" * 64
+    a = modelhub.Mount(_StubModel(2), 0, cdir, name="llama-3.8b")
+    b = modelhub.Mount(_StubModel(3), 1, cdir, name="gpt2", target="/weights/")
+    assert a.mounts[0]["destination"] == "/run/kukeon/gpupool/llama-3.8b" and a.mounts[0]["source"] == f"{cdir}/gpupool/llama-3.8b"
+    assert a.env[0] == "KUKEON_GPUPOOL_MANIFEST_LLAMA_3_8B=/run/kukeon/gpupool/llama-3.8b/manifest.json" and a.env[2] == "KUKEON_GPUPOOL_DEVICE_LLAMA_3_8B=0"
+    assert b.mounts[0]["destination"] == "/weights/gpt2" and b.env[1] == "KUKEON_GPUPOOL_IPC_HANDLE_GPT2=/weights/gpt2/ipc.handle"
+    assert json.load(open(f"{cdir}/gpupool/gpt2/manifest.json"))["tensors"][0]["name"] == "w3"
+    assert oct(os.stat(f"{cdir}/gpupool/gpt2/ipc.handle").st_mode & 0o777) == "0o640"
+    merged = modelhub.merge_mounts([a, b])
+    assert len(merged.mounts) == 2 and len(merged.env) == 6
+    with pytest.raises(ValueError, match="same container path"):
+        modelhub.merge_mounts([a, a])
+    for bad in ("..", "a/b"):
+        with pytest.raises(ValueError, match="directory name"):
+            modelhub.Mount(_StubModel(4), 0, cdir, name=bad)
+
+
+def test_merge_mounts_deduplicates_device_nodes(tmp_path):
+    import stat as st_mod
+    from types import SimpleNamespace
+
+    from kukeon_b200 import modelhub
+
+    def fake_stat(p):
+        table = {"/dev/nvidiactl": (195, 255), "/dev/nvidia-uvm": (510, 0), "/dev/nvidia0": (195, 0), "/dev/nvidia1": (195, 1)}
+        if p not in table:
+            raise FileNotFoundError(p)
+        return SimpleNamespace(st_mode=st_mod.S_IFCHR | 0o666, st_rdev=os.makedev(*table[p]))
+
+    cdir = str(tmp_path / "c")
+    a = modelhub.Mount(_StubModel(1), 0, cdir, with_devices=True, stat=fake_stat, name="a")
+    b = modelhub.Mount(_StubModel(2), 0, cdir, with_devices=True, stat=fake_stat, name="b")
+    c = modelhub.Mount(_StubModel(3), 1, cdir, with_devices=True, stat=fake_stat, name="c")
+    merged = modelhub.merge_mounts([a, b, c])
+    assert [d["path"] for d in merged.devices] == ["/dev/nvidiactl", "/dev/nvidia-uvm", "/dev/nvidia0", "/dev/nvidia1"]
+    assert len(merged.device_cgroup) == 4 and all(r["allow"] and r["access"] == "rw" for r in merged.device_cgroup)
