@@ -1,0 +1,13 @@
+#!/bin/bash
+# First GPU call of the next round (1 GPU, ~5 minutes of box time): everything written after round 1's budget ran out, in the order
+# "cheapest and most informative first", each step under its own timeout so a hang cannot eat the call.  Results land in gpurun_out/.
+#   /usr/local/graft/bin/gpurun --timeout 480 -- 'bash tools/gpu_next_first.sh'
+mkdir -p gpurun_out
+echo "== 1. torch-free parity of the new paths (rewritten dequantisers, wide-store tiles, NVLS is multi-GPU and not here)"
+timeout 60 python tools/gpu_quick.py > gpurun_out/next_quick.stdout 2>&1; echo "rc=$?"; tail -25 gpurun_out/quick.log
+echo "== 2. transpose geometry A/B/C on GPT-2-small"
+timeout 60 python tools/gpu_quick_t8.py > gpurun_out/next_t8.stdout 2>&1; echo "rc=$?"; tail -c 1200 gpurun_out/t8_ab.json
+echo "== 3. roofline table of every dequantiser"
+timeout 150 python tools/gpu_quick_types.py --weights-m 512 > gpurun_out/next_types.stdout 2>&1; echo "rc=$?"; tail -30 gpurun_out/next_types.stdout | cut -c1-220
+echo "== 4. the queued parity file (skips the multi-GPU cases on one GPU)"
+timeout 200 python -m pytest tests/test_zz_gpu_quants_f4.py -x -q -m gpu -p no:cacheprovider > gpurun_out/next_zz_pytest.log 2>&1; echo "rc=$?"; tail -8 gpurun_out/next_zz_pytest.log | cut -c1-220
