@@ -279,6 +279,18 @@ def test_super_block_dequantisers_read_shared_memory_conflict_free(emul):
         assert (ratio == 1.0) if nel >= 64 else (ratio < 2.5), (dt, st[0], st[1])
 
 
+def test_q4k_balanced_partition_variant(emul):
+    """The KK_Q4K_BALANCED=1 A/B variant of consume_q4k (contiguous blocks per warp instead of strided quads), built into a second
+    emulator library: same results for every block count a tile can have around the partition edges."""
+    L = C.CDLL(os.path.join(_HERE, "emul", "_build", "libkk_dequant_emul_q4k_balanced.so"))
+    L.kk_emul_dequant_tile.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
+    L.kk_emul_dequant_tile.restype = C.c_int
+    for n in (1, 3, 4, 5, 15, 16, 17, 63, 64, 65, 100, 223, 224):
+        blocks = synth.gen_bytes("Q4_K", 144 * n, 9, n).reshape(n, 144)
+        for pay_off in (0, 8):
+            assert (run_tile(L, "Q4_K", blocks, pay_off) == oracle.dequant_bf16("Q4_K", blocks)).all(), (n, pay_off)
+
+
 def test_harness_sees_wrong_answers(emul):
     """The checker is live: feeding Q5_0 blocks to the Q4_0 function must not reproduce the Q5_0 oracle."""
     blocks = synth.gen_bytes("Q5_0", 22 * 9 * 8, 2, 1).reshape(-1, 22)
