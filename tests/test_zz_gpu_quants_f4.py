@@ -135,11 +135,17 @@ def test_t8_gpt2_every_dtype_and_odd_shapes(pool, tmp_path, T8):
         load_and_check(pool, q, flags=T8)
 
 
+@pytest.fixture(scope="module")
+def gpt2_full(tmp_path_factory):
+    p = str(tmp_path_factory.mktemp("gpt2") / "gpt2_full.safetensors")
+    synth.make_gpt2(p)  # 0.5 GB, generated once for both geometries
+    return p
+
+
 @pytest.mark.parametrize("T8", [T8, TW], ids=["t8", "tw"])
-def test_t8_full_size_gpt2_matches_the_32x128_tiles(pool, tmp_path, T8):
+def test_t8_full_size_gpt2_matches_the_32x128_tiles(pool, gpt2_full, T8):
     """GPT-2-small at full size (0.5 GB): checksum of every tensor equal between the two tile geometries and equal to the oracle."""
-    p = str(tmp_path / "gpt2_full.safetensors")
-    synth.make_gpt2(p)
+    p = gpt2_full
     a = pool.load(p, flags=gpupool.LOAD_GPT2_CONV1D_T)
     try:
         sums = {t["name"]: a.checksum(0, a.placements(t["name"])[0].pool_offset, a.placements(t["name"])[0].nbytes) for t in a.tensors()}
