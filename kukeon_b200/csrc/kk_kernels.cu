@@ -21,6 +21,7 @@
 
 #include "kk_iq_grids.h"
 #include "kk_kernels.cuh"
+#include "kk_tile.h"
 
 namespace kk {
 
@@ -35,6 +36,13 @@ constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kThreads = 32 + kConsumerThreads;  // 288
 constexpr uint32_t kStageBytes = KK_TILE_SRC_BYTES + KK_STAGE_PAD;
 
+#ifndef KK_PRODUCER_SHARED
+#define KK_PRODUCER_SHARED 0  // 1: the producer warp computes every tile with kk_make_tile (kk_tile.h, the function tests/emul replays launches
+                              // through) instead of the in-line switch below; an A/B build until it has had its own run on hardware
+#endif
+#if KK_PRODUCER_SHARED
+using TileDesc = KKTileDesc;
+#else
 struct __align__(16) TileDesc {
   uint32_t op;
   uint32_t pay_off;  // payload offset inside the stage buffer (0..15 for TMA tiles)
@@ -49,6 +57,7 @@ struct __align__(16) TileDesc {
   uint32_t row0;     // transposes: first destination column (= global source row) of the tile
   uint32_t pad[4];
 };
+#endif
 static_assert(sizeof(TileDesc) == 64, "TileDesc");
 
 constexpr uint32_t kSmemFixed = kStages * kStageBytes + kStages * sizeof(TileDesc) + 2 * kStages * 8;
@@ -366,6 +375,24 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
         while (nxt + 1 < L.n_segs && tile_begin[nxt + 1] <= tile) ++nxt;
         if (nxt != cur) { cur = nxt; seg = load_seg(L.segs + cur); }
         const uint32_t t = tile - seg.tile_begin;
+#if KK_PRODUCER_SHARED
+        {
+          KKTileDesc sd;
+          KKTileLoad ld;
+          kk_make_tile(seg, t, (uint64_t)(uintptr_t)L.src, L.flags, sd, ld);
+          descs[s] = sd;
+          const uint32_t sb = smem_u32(stage_buf + s * kStageBytes);
+          if (ld.kind == 0) {
+            mbar_arrive(full0 + 8 * s);
+          } else {
+            mbar_arrive_expect_tx(full0 + 8 * s, ld.tx);
+            if (ld.kind == 1) bulk_g2s(sb, L.src + ld.g_off, ld.tx, full0 + 8 * s);
+            else
+              for (uint32_t r = 0; r < ld.nrows; ++r) bulk_g2s(sb + r * ld.spitch, L.src + ld.g_off + (uint64_t)r * ld.gpitch, ld.row_bytes, full0 + 8 * s);
+          }
+          continue;
+        }
+#endif
         TileDesc d;
         d.op = seg.op; d.bulk = 0; d.C = 0; d.R = 0; d.col0 = 0; d.row0 = 0; d.src_off = 0;
         uint32_t in_bytes = 0;          // source bytes of this tile (TMA ops)

@@ -20,8 +20,7 @@ struct ConvertLaunch {
   uint32_t pad_;
 };
 
-#define KK_LAUNCH_NO_BULK_STORE 0x1u  // force the register path for aligned copies (A/B measurement)
-#define KK_LAUNCH_MULTIMEM 0x2u       // dst[0] is an NVLS multicast address: store with multimem.st
+// KK_LAUNCH_* flag values: kk_ops.h
 
 // Max segments one launch may carry (tile_begin[] is cached in shared memory).
 constexpr uint32_t kMaxSegsPerLaunch = 4096;

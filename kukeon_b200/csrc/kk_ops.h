@@ -77,6 +77,9 @@
 #define KK_TW_ROW_BYTES 960u
 #define KK_TW_PITCH 976u
 #define KK_MAX_DST 8
+/* ConvertLaunch::flags */
+#define KK_LAUNCH_NO_BULK_STORE 0x1u  /* force the register path for aligned copies (A/B measurement) */
+#define KK_LAUNCH_MULTIMEM 0x2u       /* dst[0] is an NVLS multicast address: store with multimem.st */
 
 enum KKOp : uint32_t {
   KK_OP_COPY = 0,      // units = bytes

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../kukeon_b200/csrc/kk_iq_grids.h"
+#include "../../kukeon_b200/csrc/kk_tile.h"
 
 namespace {
 
@@ -27,7 +28,9 @@ struct Emu {
   std::vector<uint32_t>* trace = nullptr;  // when set: every 16/32-bit shared load appends its address (bank-conflict accounting)
   std::vector<uint64_t>* strace = nullptr; // when set: every 16-byte store appends its destination offset (store-transaction accounting)
   uint32_t tile_bytes = 0;
-  uint8_t* out = nullptr;
+  uint8_t* out = nullptr;         // destination pool 0 (the one hits / masks describe)
+  uint8_t* more_out[KK_MAX_DST - 1] = {};  // further destination pools of a fan-out launch: every store is replicated into them
+  int n_more = 0;
   uint64_t out_bytes = 0;
   uint8_t* hits = nullptr;  // one counter per 16 output bytes
   uint8_t* out_mask = nullptr;  // per 2 output bytes: written by a scalar (tail) store (per byte for store1_all: see byte_mask)
@@ -138,6 +141,7 @@ inline void store16_all(const Dsts&, uint64_t off, const uint4& v) {
   g.hits[off >> 4] += 16;
   if (g.strace) g.strace->push_back(off);
   memcpy(g.out + off, &v, 16);
+  for (int i = 0; i < g.n_more; ++i) memcpy(g.more_out[i] + off, &v, 16);
 }
 inline void store1_all(const Dsts&, uint64_t off, uint8_t v) {
   if (g.shfl_mode == 1) return;
@@ -146,6 +150,7 @@ inline void store1_all(const Dsts&, uint64_t off, uint8_t v) {
   g.byte_mask[off] = 1;
   g.hits[off >> 4] += 1;
   g.out[off] = v;
+  for (int i = 0; i < g.n_more; ++i) g.more_out[i][off] = v;
 }
 inline void store2_all(const Dsts&, uint64_t off, uint16_t v) {
   if (g.shfl_mode == 1) return;
@@ -154,6 +159,7 @@ inline void store2_all(const Dsts&, uint64_t off, uint16_t v) {
   g.out_mask[off >> 1] = 1;
   g.hits[off >> 4] += 2;
   memcpy(g.out + off, &v, 2);
+  for (int i = 0; i < g.n_more; ++i) memcpy(g.more_out[i] + off, &v, 2);
 }
 inline uint4 lds128(uint32_t a) {
   uint4 v{0, 0, 0, 0};
@@ -442,6 +448,104 @@ extern "C" int kk_emul_t8_tile(uint32_t op, const uint8_t* src, uint32_t C, uint
   }
   if (stats) { stats[0] = wavefronts; stats[1] = ideal; stats[2] = st_instr; stats[3] = st_lines; stats[4] = st_sectors; }
   return g.err;
+}
+
+// A whole launch of kk_convert_kernel, tile by tile: resolve the tile's segment from tile_begin[] (as the producer does), kk_make_tile (the
+// function the kernel's producer calls when built with KK_PRODUCER_SHARED), perform the bulk copies it asks for into a stage buffer with the
+// hardware's constraints checked (16-byte aligned source, destination and size; bytes issued == bytes announced), then the consumer side: the
+// aligned-copy bulk stores, or the same per-lane device functions the other entry points run, for all 16 x 32 consumer lanes.
+// src: the staged chunk (src base assumed 256-byte aligned like the staging buffers); dst[0..n_dst): destination pools of pool_bytes each;
+// hits / masks describe dst[0] and ACCUMULATE across calls (the caller zeroes them once per pool).  Not covered: the 32x128 transposes and the
+// scatter row exchange (return -2).
+extern "C" int kk_emul_launch(const uint8_t* src, uint64_t src_bytes, const KKSeg* segs, uint32_t n_segs, uint32_t n_tiles, uint32_t flags,
+                              uint8_t* const* dst, uint32_t n_dst, uint64_t pool_bytes, uint8_t* hits, uint8_t* mask2, uint8_t* mask1) {
+  if (n_dst < 1 || n_dst > KK_MAX_DST) return -1;
+  static thread_local uint8_t stage[KK_TILE_SRC_BYTES + KK_STAGE_PAD];
+  const uint64_t src_addr = 0x100000;  // only the alignment of the src base matters
+  uint32_t cur = 0;
+  for (uint32_t tile = 0; tile < n_tiles; ++tile) {
+    while (cur + 1 < n_segs && segs[cur + 1].tile_begin <= tile) ++cur;
+    const KKSeg& seg = segs[cur];
+    if (tile < seg.tile_begin) return 9;  // tile_begin[] not monotone from 0
+    KKTileDesc d;
+    KKTileLoad ld;
+    kk_make_tile(seg, tile - seg.tile_begin, src_addr, flags, d, ld);
+    memset(stage, 0xEE, sizeof stage);
+    uint32_t staged = 0;
+    if (ld.kind == 1) {
+      if (((src_addr + ld.g_off) & 15u) || (ld.tx & 15u) || ld.tx > sizeof stage) return 10;
+      if (ld.g_off > src_bytes) return 11;
+      // the last tile of a chunk may over-read up to 15 bytes of slack behind the staged bytes (the planner leaves room for it)
+      const uint64_t avail = src_bytes - ld.g_off;
+      if (ld.tx > avail + 15) return 11;
+      memcpy(stage, src + ld.g_off, (size_t)std::min<uint64_t>(ld.tx, avail));
+      staged = ld.tx;
+    } else if (ld.kind == 2) {
+      uint32_t sum = 0;
+      for (uint32_t r = 0; r < ld.nrows; ++r) {
+        const uint64_t go = ld.g_off + (uint64_t)r * ld.gpitch;
+        const uint32_t so = r * ld.spitch;
+        if (((src_addr + go) & 15u) || (so & 15u) || (ld.row_bytes & 15u) || so + ld.row_bytes > sizeof stage) return 10;
+        if (go + ld.row_bytes > src_bytes) return 11;
+        memcpy(stage + so, src + go, ld.row_bytes);
+        sum += ld.row_bytes;
+        staged = std::max(staged, so + ld.row_bytes);
+      }
+      if (sum != ld.tx) return 12;  // the mbarrier would never complete (or complete early)
+    }
+    g = Emu{};
+    g.tile = stage; g.wtile = stage; g.tile_bytes = ld.kind ? staged : (uint32_t)sizeof stage;
+    g.out = dst[0]; g.out_bytes = pool_bytes; g.hits = hits; g.out_mask = mask2; g.byte_mask = mask1;
+    g.n_more = (int)n_dst - 1;
+    for (int i = 0; i < g.n_more; ++i) g.more_out[i] = dst[i + 1];
+    const Dsts D{0};
+    const uint32_t nr = d.n_units & 0xFFFFu, nc = d.n_units >> 16;
+    if (d.bulk == 1) {  // aligned verbatim copy: one bulk store from the stage to every pool
+      if ((d.dst_off & 15u) || (d.n_units & 15u) || (d.pay_off & 15u) || d.dst_off + d.n_units > pool_bytes) return 13;
+      for (uint32_t u = 0; u < d.n_units; u += 16) {
+        if (hits[(d.dst_off + u) >> 4]) return 4;
+        hits[(d.dst_off + u) >> 4] += 16;
+      }
+      for (uint32_t i = 0; i < n_dst; ++i) memcpy(dst[i] + d.dst_off, stage + d.pay_off, d.n_units);
+      continue;
+    }
+    if (d.bulk == 3 || d.op == KK_OP_ROWSPLIT) return -2;
+    switch (d.op) {
+      case KK_OP_T_F32_BF16: case KK_OP_T_F16_BF16: case KK_OP_T_B16: case KK_OP_T_B32: return -2;
+      case KK_OP_T8_F32_BF16: case KK_OP_T8_F16_BF16: case KK_OP_T8_B16:
+      case KK_OP_TW_F32_BF16: case KK_OP_TW_F16_BF16: case KK_OP_TW_B16: {
+        const bool tw = d.op >= KK_OP_TW_F32_BF16;
+        const uint32_t es = (d.op == KK_OP_T8_F32_BF16 || d.op == KK_OP_TW_F32_BF16) ? 4u : 2u;
+        uint32_t pitch = tw ? KK_TW_PITCH : nc * es;
+        if (d.bulk != (tw ? 5u : 4u)) {  // run_t8 / run_tw of the kernel: gather, (barrier), consume
+          if (!tw) pitch = (pitch + 3u) & ~3u;
+          g.tile_bytes = (uint32_t)sizeof stage;
+          if (d.src_off + ((uint64_t)(nr ? nr - 1 : 0) * d.C + nc) * es > src_bytes) return 11;
+          for (int t = 0; t < kConsumerThreads; ++t) {
+            if (es == 4) t8_gather<4>(src + d.src_off, 0, pitch, nr, nc, d.C, t);
+            else t8_gather<2>(src + d.src_off, 0, pitch, nr, nc, d.C, t);
+          }
+        }
+        for (int t = 0; t < kConsumerThreads; ++t) {
+          const int cw = t >> 5, ln = t & 31;
+          switch (d.op) {
+            case KK_OP_T8_F32_BF16: consume_t8<4, 1>(D, 0, pitch, nr, nc, d.R, d.col0, d.row0, d.dst_off, t); break;
+            case KK_OP_T8_F16_BF16: consume_t8<2, 2>(D, 0, pitch, nr, nc, d.R, d.col0, d.row0, d.dst_off, t); break;
+            case KK_OP_T8_B16: consume_t8<2, 0>(D, 0, pitch, nr, nc, d.R, d.col0, d.row0, d.dst_off, t); break;
+            case KK_OP_TW_F32_BF16: consume_tw<4, 1>(D, 0, pitch, nr, nc, d.R, d.col0, d.row0, d.dst_off, cw, ln); break;
+            case KK_OP_TW_F16_BF16: consume_tw<2, 2>(D, 0, pitch, nr, nc, d.R, d.col0, d.row0, d.dst_off, cw, ln); break;
+            default: consume_tw<2, 0>(D, 0, pitch, nr, nc, d.R, d.col0, d.row0, d.dst_off, cw, ln); break;
+          }
+        }
+        break;
+      }
+      default:
+        if (!run_warps(d.op, D, d.pay_off, d.n_units, d.dst_off)) return -1;
+        break;
+    }
+    if (g.err) return g.err;
+  }
+  return 0;
 }
 
 // Geometry the kernel and the planner share (kk_ops.h), exported so the test can cross-check the Python-side tables.
