@@ -170,3 +170,38 @@ def test_the_replay_notices_a_wrong_plan(emul, tmp_path):
     seg = (KKSeg * 1)(KKSeg(s["src_off"], s["dst_off"], s["units"], s["op"], 0, 0, 0, 0, 0))
     pools = Pools(1, len(exp))
     assert emul.kk_emul_launch(buf.ctypes.data, buf.size // 2, seg, 1, ch["n_tiles"], 0, pools.ptrs, 1, len(exp), pools.hits.ctypes.data, pools.m2.ctypes.data, pools.m1.ctypes.data) == 11
+
+
+# ---- property tests: random inventories through whole launches of the device code ---------------------------------------------------------
+from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
+
+from tests.test_plan_property import gguf_inventories, inventories  # noqa: E402
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@given(inv=inventories(), mode=st.sampled_from([0, 1, 2]), n_parts=st.integers(1, 6), pad=st.booleans(),
+       flags=st.sampled_from([0, 2, 16, 18, 33, 35, 49, 65, 67, 81]))  # every flag set whose ops the replay covers (no 32x128 transposes, no row exchange)
+def test_random_safetensors_inventories_replayed_through_the_device_code(emul, inv, mode, n_parts, pad, flags):
+    import tempfile
+    if mode == 0:
+        n_parts = 1
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "m.safetensors")
+        synth.write_safetensors(p, inv, seed=7, pad_header=pad)
+        plan = gpupool.plan_describe(p, mode=mode, flags=flags, n_parts=n_parts, chunk_bytes=1 * MB)
+        ops = {sg["op"] for part in plan["parts"] for ch in part["chunks"] for sg in ch["segs"]}
+        if ops & {helpers.OP_T_F32_BF16, helpers.OP_T_F16_BF16, helpers.OP_T_B16, helpers.OP_T_B32, helpers.OP_ROWSPLIT}:
+            return  # R % 8 != 0 or 4-byte outputs keep the 32x128 ops, whose consumer is not in the shared headers
+        replay(emul, p, mode=mode, flags=flags, n_parts=n_parts)
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@given(inv=gguf_inventories(), mode=st.sampled_from([0, 1, 2]), n_parts=st.integers(1, 6), alignment=st.sampled_from([8, 32, 64]))
+def test_random_gguf_inventories_replayed_through_the_device_code(emul, inv, mode, n_parts, alignment):
+    import tempfile
+    if mode == 0:
+        n_parts = 1
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "m.gguf")
+        synth.write_gguf(p, inv, seed=8, alignment=alignment)
+        replay(emul, p, mode=mode, n_parts=n_parts)
