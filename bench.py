@@ -604,8 +604,11 @@ def main():
         line["nvlink"] = nvlink
     if nccl:
         line["nccl_compare"] = nccl
-    m.release()
-    pool.close()
+    try:  # the measurements are complete: a teardown error is reported, never allowed to swallow the line
+        m.release()
+        pool.close()
+    except Exception as e:  # noqa: BLE001
+        line["teardown_error"] = str(e)
     barrier()
     # ---- time-to-agent-ready in kukeond's real shape: ONE process owning all N GPUs (no CUDA IPC between ranks) ------
     if world > 1 and not args.no_single_process:
