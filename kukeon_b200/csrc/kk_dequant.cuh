@@ -68,7 +68,10 @@ KK_DQ_DEV void store_bf16x8(const Dsts& D, uint64_t off, const float (&y)[8]) {
 // Every dequantiser below first assembles four small UNSIGNED values per 32-bit word (SIMD-in-word), then calls this per element.
 template <int BIAS>
 KK_DQ_DEV float byte_to_float(uint32_t w, int k) {
-  return __fsub_rn(kk_bits2f(kk_byte_perm(w, 0x4B000000u, 0x7440u | (uint32_t)k)), 8388608.0f + (float)BIAS);
+  // the constant is PRMT's FIRST source: a register operand, loaded once outside the loop, with the selector as the immediate.  With the
+  // operands the other way round ptxas kept 0x4B000000 as the immediate and re-materialised the four selectors in registers inside
+  // every loop iteration (12 extra instructions per 8 elements in the lattice dequantisers; tools/sass_budget.py).
+  return __fsub_rn(kk_bits2f(kk_byte_perm(0x4B000000u, w, 0x3004u | (uint32_t)k)), 8388608.0f + (float)BIAS);
 }
 // bits 0..3 of x -> bit 0 of bytes 0..3 (the multiplier's four set bits are 7 apart, so no partial products overlap)
 KK_DQ_DEV uint32_t spread4(uint32_t x) { return ((x & 0xFu) * 0x00204081u) & 0x01010101u; }
@@ -334,15 +337,31 @@ KK_DQ_DEV void t8_gather(const uint8_t* src, uint32_t sbase, uint32_t pitch, uin
 //                 ls = ((scales_l[j/2] >> 4(j%2)) & 15) | (((scales_h >> 2j) & 3) << 4), y = (d*(ls-32)) * kIQ4NL[q4]; its elements
 //                 i < 16 are the low nibbles of qs[16j + i], i >= 16 the high nibbles of qs[16j + i - 16]   (gguf/quants.py:1351-1380)
 // MXFP4 (17 B):   e u8 (E8M0) | qs[16]; y = 2^(e-128) * kMXFP4[q4] (the table holds DOUBLED e2m1 values)   (gguf/quants.py:656-708)
-// The 16-entry tables live in four registers each; a lookup is one PRMT over a register pair picked by bit 3 of the index.
+// The 16-entry tables live in four registers each and are read EIGHT indices at a time with PRMT as the lookup instruction: the lane's
+// eight 4-bit indices are squeezed into the nibbles of one word (the PRMT selector format), bits 2:0 of every index select a byte from
+// the low half {K0,K1} and from the high half {K2,K3} of the table (two PRMTs per four indices), and a third PRMT takes byte e from the
+// one or the other according to bit 3 of index e.  18 instructions per eight lookups; one PRMT + compare + select PER INDEX before.
 template <int TABLE>  // 0: IQ4_NL values, 1: MXFP4 (e2m1 x 2)
-KK_DQ_DEV float lut16(uint32_t idx) {
+KK_DQ_DEV void lut16x8(uint32_t x0, uint32_t x1, uint32_t& r0, uint32_t& r1) {
+  // x0, x1: four indices each, one per byte (0x0i0j0k0l).  r0, r1: the table entries (+ 128, unsigned bytes) in the same byte order.
   // little-endian packing of {-127,-104,-83,-65, -49,-35,-22,-10, 1,13,25,38, 53,69,89,113} and {0,1,2,3, 4,6,8,12, 0,-1,-2,-3, -4,-6,-8,-12},
-  // every entry + 128 so that the bytes are unsigned and the second PRMT + FADD (byte_to_float<128>) yields the signed value
+  // every entry + 128 so that the bytes are unsigned and byte_to_float<128> (PRMT + FADD) yields the signed value
   constexpr uint32_t K0 = (TABLE ? 0x03020100u : 0xBFAD9881u) ^ 0x80808080u, K1 = (TABLE ? 0x0C080604u : 0xF6EADDCFu) ^ 0x80808080u;
   constexpr uint32_t K2 = (TABLE ? 0xFDFEFF00u : 0x26190D01u) ^ 0x80808080u, K3 = (TABLE ? 0xF4F8FAFCu : 0x71594535u) ^ 0x80808080u;
-  const uint32_t b = (idx & 8u) ? kk_byte_perm(K2, K3, idx & 7u) : kk_byte_perm(K0, K1, idx & 7u);
-  return byte_to_float<128>(b, 0);
+  const uint32_t t0 = x0 | (x0 >> 4), t1 = x1 | (x1 >> 4);            // byte 0 = k<<4 | l, byte 2 = i<<4 | j
+  const uint32_t sel = kk_byte_perm(t0, t1, 0x6420u);                  // nibble e = index e: x0's four in the low half, x1's in the high half
+  const uint32_t s7 = sel & 0x77777777u;                               // a selector nibble's bit 3 would ask PRMT for sign replication
+  const uint32_t pick = ((sel >> 1) & 0x44444444u) | 0x32103210u;      // nibble e = e + 4 * (bit 3 of index e)
+  r0 = kk_byte_perm(kk_byte_perm(K0, K1, s7), kk_byte_perm(K2, K3, s7), pick);  // PRMT reads only the low 16 bits of its selector
+  r1 = kk_byte_perm(kk_byte_perm(K0, K1, s7 >> 16), kk_byte_perm(K2, K3, s7 >> 16), pick >> 16);
+}
+// y[e] = scale * table[index e], one rounding each (gguf-py multiplies the looked-up value by the block scale)
+template <int TABLE>
+KK_DQ_DEV void codebook8(float scale, uint32_t x0, uint32_t x1, float (&y)[8]) {
+  uint32_t r0, r1;
+  lut16x8<TABLE>(x0, x1, r0, r1);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) y[e] = __fmul_rn(scale, byte_to_float<128>(e < 4 ? r0 : r1, e & 3));
 }
 // 32-weight codebook blocks: lane l takes elements 8(l&3)..+8 of block (l>>2), eight blocks per warp iteration (as consume_legacy32).
 template <uint32_t BYTES, int TABLE>
@@ -367,8 +386,7 @@ KK_DQ_DEV void consume_codebook32(const Dsts& D, uint32_t pay, uint32_t nblk, ui
       q0 = (q0 >> nsh) & 0x0F0F0F0Fu;
       q1 = (q1 >> nsh) & 0x0F0F0F0Fu;
       float y[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) y[e] = __fmul_rn(d, lut16<TABLE>(((e < 4 ? q0 : q1) >> (8 * (e & 3))) & 0xFu));
+      codebook8<TABLE>(d, q0, q1, y);
       store_bf16x8(D, dst_off + (uint64_t)b * 64u + (uint32_t)(lane & 3) * 16u, y);
     }
   }
@@ -388,8 +406,7 @@ KK_DQ_DEV void consume_iq4xs(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_
     const uint32_t q0 = (lds32_any(blk + q_off) >> nsh) & 0x0F0F0F0Fu;
     const uint32_t q1 = (lds32_any(blk + q_off + 4u) >> nsh) & 0x0F0F0F0Fu;
     float y[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) y[e] = __fmul_rn(dl, lut16<0>(((e < 4 ? q0 : q1) >> (8 * (e & 3))) & 0xFu));
+    codebook8<0>(dl, q0, q1, y);
     store_bf16x8(D, dst_off + (uint64_t)b * 512u + (uint32_t)lane * 16u, y);
   }
 }
@@ -599,8 +616,7 @@ KK_DQ_DEV void consume_nvfp4(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_
       if (x == 0u || x == 0x7Fu) d = 0.0f;
       const uint32_t q0 = (lds32_any(blk + 4u + 8u * sb) >> nsh) & 0x0F0F0F0Fu, q1 = (lds32_any(blk + 8u + 8u * sb) >> nsh) & 0x0F0F0F0Fu;
       float y[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) y[k] = __fmul_rn(d, lut16<1>(((k < 4 ? q0 : q1) >> (8 * (k & 3))) & 0xFu));
+      codebook8<1>(d, q0, q1, y);
       store_bf16x8(D, dst_off + (uint64_t)b * 128u + (l & 7u) * 16u, y);
     }
   }

@@ -107,8 +107,11 @@ inline uint32_t kk_grid_iq3xxs(uint32_t i) { if (i >= KK_GRID_IQ3XXS_SIZE) { fla
 inline uint32_t kk_grid_iq3s(uint32_t i) { if (i >= KK_GRID_IQ3S_SIZE) { flag(8); return 0; } return kGridIq3s[i]; }
 inline uint64_t kk_grid_iq1s(uint32_t i) { if (i >= KK_GRID_IQ1S_SIZE) { flag(8); return 0; } return kGridIq1s[i]; }
 inline uint32_t kk_ldg8(const uint8_t* p) { return *p; }
-// PRMT (default mode) as the code under test uses it: selector nibble 0 picks byte (sel & 7) of {b:a}; the msb-replicate bit is never set
+// PRMT (default mode) as the code under test uses it: selector nibble k (low 16 bits; the hardware ignores the rest) picks byte
+// (nibble & 7) of {b:a}.  Bit 3 of a nibble asks the hardware to replicate the byte's sign bit instead — never what this code wants, so a
+// selector that has it set is a failure (9), not something to mask away.
 inline uint32_t kk_byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
+  if (sel & 0x8888u) flag(9);
   const uint64_t v = ((uint64_t)b << 32) | a;
   uint32_t r = 0;
   for (int k = 0; k < 4; ++k) r |= (uint32_t)((v >> (8 * ((sel >> (4 * k)) & 7u))) & 0xFFu) << (8 * k);
