@@ -18,6 +18,7 @@
 //     float    kk_bits2f(u32)                    bit cast
 //     uint32_t kk_byte_perm(a, b, sel)           PRMT: byte (sel & 7) of the 8 bytes {b:a} in the low byte of the result
 //     uint32_t kk_f2bits(f), kk_popc(u)          bit cast, population count
+//     uint32_t kk_funnel_r(lo, hi, sh)           bits [sh, sh+32) of hi:lo (SHF.R.W); lds32_slack(a): aligned word that may end in the stage's slack
 //     uint64_t kk_grid_iq2xxs/iq2xs/iq2s/iq1s(i), uint32_t kk_grid_iq3xxs/iq3s(i)   codebook entry i (kk_iq_grids.h; __ldg on the device)
 //     void     sts16(a, v) / sts32(a, v)         stores into the stage (gather fallback of the 8-row transposes)
 //     uint32_t kk_ldg8(p)                        one byte from global memory (same fallback)
@@ -42,22 +43,17 @@ KK_DQ_DEV uint32_t lds32_any(uint32_t a) {
   if ((a & 3u) == 0) return lds32(a);
   return lds32_h(a);
 }
-// Eight payload bytes at address a -> two words.  Blocks of 18..210 bytes put them on 2-byte boundaries half of the time: then two aligned
-// 32-bit loads (the first starts 2 bytes early: an address that is 2 mod 4 always has two staged bytes in front of it — the previous block's, or
-// the tile's alignment slack) and one 16-bit
-// load are merged with PRMT, instead of four 16-bit loads.  Odd addresses (17-byte MXFP4 blocks, odd tile offsets) go byte by byte.
+// Eight payload bytes at ANY address a -> two words: the three aligned words that cover them, funnel-shifted into place (SHF.R.W).
+// There are no alignment cases, so the lanes of a warp whose blocks sit at different alignments — eight 17-, 18-, 22- or 34-byte blocks
+// per warp iteration — do not diverge (the first version branched three ways: aligned / 2-byte funnel / byte by byte, and such a warp
+// executed all three).  The third word is read only when a is unaligned; its last 1-3 bytes may lie behind the payload, inside the
+// stage's slack (KK_STAGE_PAD), and are shifted out.  The first word may start up to 3 bytes before a: the previous block, the block
+// header, or the tile's alignment skew — staged bytes in every case.
 KK_DQ_DEV void lds64_funnel(uint32_t a, uint32_t& q0, uint32_t& q1) {
-  if ((a & 3u) == 0) {
-    q0 = lds32(a);
-    q1 = lds32(a + 4u);
-  } else if ((a & 1u) == 0) {
-    const uint32_t w0 = lds32(a - 2u), w1 = lds32(a + 2u), h = lds16(a + 6u);
-    q0 = kk_byte_perm(w0, w1, 0x5432u);  // bytes 2,3 of w0 then 0,1 of w1
-    q1 = kk_byte_perm(w1, h, 0x5432u);
-  } else {
-    q0 = lds32_bytes(a);
-    q1 = lds32_bytes(a + 4u);
-  }
+  const uint32_t base = a & ~3u, sh = (a & 3u) * 8u;
+  const uint32_t w0 = lds32(base), w1 = lds32(base + 4u), w2 = sh ? lds32_slack(base + 8u) : 0u;
+  q0 = kk_funnel_r(w0, w1, sh);
+  q1 = kk_funnel_r(w1, w2, sh);
 }
 KK_DQ_DEV float lds_f16(uint32_t a) { return kk_h2f(lds16_any(a)); }
 KK_DQ_DEV void store_bf16x8(const Dsts& D, uint64_t off, const float (&y)[8]) {

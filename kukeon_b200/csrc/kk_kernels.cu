@@ -220,6 +220,10 @@ __device__ __forceinline__ void kk_h2x2f(uint32_t w, float& x, float& y) {
 }
 __device__ __forceinline__ uint32_t kk_f2bits(float f) { return __float_as_uint(f); }
 __device__ __forceinline__ uint32_t kk_popc(uint32_t u) { return (uint32_t)__popc(u); }
+// SHF.R.W: bits [sh, sh + 32) of the 64-bit value hi:lo (sh taken mod 32)
+__device__ __forceinline__ uint32_t kk_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
+// an aligned word whose first byte is payload but whose last 1-3 bytes may lie in the stage's slack behind it (KK_STAGE_PAD): same load
+__device__ __forceinline__ uint32_t lds32_slack(uint32_t a) { return lds32(a); }
 // i-quant codebooks (33 KB, read through the read-only path; hot entries stay in L1)
 __device__ const uint64_t kGridIq2xxs[KK_GRID_IQ2XXS_SIZE] = {KK_GRID_IQ2XXS_VALUES};
 __device__ const uint64_t kGridIq2xs[KK_GRID_IQ2XS_SIZE] = {KK_GRID_IQ2XS_VALUES};

@@ -93,6 +93,20 @@ inline float __shfl_sync(unsigned, float v, int src) {
 }
 inline uint32_t kk_f2bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 inline uint32_t kk_popc(uint32_t u) { return (uint32_t)__builtin_popcount(u); }
+inline uint32_t kk_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {
+  sh &= 31u;
+  return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
+}
+// Aligned word that starts inside the payload and may end up to 3 bytes behind it: on the device those bytes are whatever the stage's
+// slack holds, so here they are poison — a result that depends on them fails the comparison with the oracle.
+inline uint32_t lds32_slack(uint32_t a) {
+  if (a & 3u) { flag(2); return 0; }
+  if (a >= g.tile_bytes) { flag(1); return 0; }
+  if (g.trace) g.trace->push_back(a);
+  uint32_t v = 0;
+  for (uint32_t k = 0; k < 4; ++k) v |= (uint32_t)(a + k < g.tile_bytes ? g.tile[a + k] : (uint8_t)(0xA5u ^ (a + k))) << (8 * k);
+  return v;
+}
 const uint64_t kGridIq2xxs[KK_GRID_IQ2XXS_SIZE] = {KK_GRID_IQ2XXS_VALUES};
 const uint64_t kGridIq2xs[KK_GRID_IQ2XS_SIZE] = {KK_GRID_IQ2XS_VALUES};
 const uint64_t kGridIq2s[KK_GRID_IQ2S_SIZE] = {KK_GRID_IQ2S_VALUES};
