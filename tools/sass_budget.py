@@ -51,11 +51,22 @@ CLASSES = [("lds", r"^LDS"), ("ldg", r"^LDG"), ("stg", r"^STG"), ("prmt", r"^PRM
            ("shfl", r"^SHFL"), ("branch/sync", r"^(BRA|BSSY|BSYNC|WARPSYNC|NANOSLEEP|SYNCS|BAR|EXIT|CALL|RET|BREAK|YIELD|NOP)")]
 
 
-def disassemble():
+def fresh_object():
+    """csrc/build/kk_kernels.o when the Makefile's last build is newer than every source it depends on (same flags: -O3 -lineinfo)."""
+    obj = os.path.join(CSRC, "build", "kk_kernels.o")
+    if not os.path.exists(obj):
+        return None
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
+    return obj if all(os.path.getmtime(x) <= os.path.getmtime(obj) for x in deps) else None
+
+
+def disassemble(obj=None):
     with tempfile.TemporaryDirectory() as d:
-        obj = os.path.join(d, "k.o")
-        subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-I" + os.path.join(ROOT, "include"),
-                               "-c", KERNEL_CU, "-o", obj], cwd=CSRC, stderr=subprocess.DEVNULL)
+        obj = obj or fresh_object()
+        if obj is None:
+            obj = os.path.join(d, "k.o")
+            subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-I" + os.path.join(ROOT, "include"),
+                                   "-c", KERNEL_CU, "-o", obj], cwd=CSRC, stderr=subprocess.DEVNULL)
         subprocess.check_call(["cuobjdump", "-xelf", "all", obj], cwd=d, stdout=subprocess.DEVNULL)
         cubin = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
         return subprocess.check_output(["nvdisasm", "-gi", "-c", os.path.join(d, cubin)], text=True)
@@ -202,14 +213,14 @@ def analyse():
         inner = [(n2, a2, b2) for n2, a2, b2 in cand if a2 >= a and b2 <= b and (a2, b2) != (a, b)]
         hot, hot_math = hot_path(ins, labels, a, b, "vec" if op.startswith(("KK_OP_T8_", "KK_OP_TW_")) else "math")
         rows.append({"op": op, "static": len(mine), "loop": n, "hot": hot, "hot_math": hot_math, "mix": mix, "inner_loops": sorted(n2 for n2, _, _ in inner), "n_loops": len(cand)})
-    return rows, len(ins)
+    return rows, len(ins), collections.Counter(x["mn"].split(".")[0] for x in ins)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--md")
     args = ap.parse_args()
-    rows, total = analyse()
+    rows, total, _ = analyse()
     issue_rate = SM_COUNT * SM_GHZ * ISSUE_PER_CLK  # G warp instructions / s
     names = [c for c, _ in CLASSES] + ["other"]
     out = []
