@@ -37,7 +37,7 @@ constexpr int kThreads = 32 + kConsumerThreads;  // 288
 constexpr uint32_t kStageBytes = KK_TILE_SRC_BYTES + KK_STAGE_PAD;
 
 #ifndef KK_PRODUCER_SHARED
-#define KK_PRODUCER_SHARED 0  // 1: the producer warp computes every tile with kk_make_tile (kk_tile.h, the function tests/emul replays launches
+#define KK_PRODUCER_SHARED 0  // 2: as 1, with all 32 producer lanes issuing the per-row bulk copies.  1: the producer warp computes every tile with kk_make_tile (kk_tile.h, the function tests/emul replays launches
                               // through) instead of the in-line switch below; an A/B build until it has had its own run on hardware
 #endif
 #if KK_PRODUCER_SHARED
@@ -368,6 +368,40 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
 
   if (warp == 0) {
     // ===== producer =====
+#if KK_PRODUCER_SHARED == 2
+    // Warp-cooperative producer (A/B build): all 32 lanes walk the tiles in lock step — the tile arithmetic is uniform, so running it on
+    // every lane costs no extra issue slots — lane 0 alone publishes the descriptor and arms the barrier, and the per-row bulk copies of
+    // the transposing tiles (32-64 per tile with the 32x128 geometry, 34 with the wide-store one) are issued by 32 lanes side by side
+    // instead of one after the other by a single thread.
+    {
+      uint32_t cur = 0;
+      KKSeg seg = load_seg(L.segs);
+      uint32_t it = 0;
+      for (uint32_t tile = blockIdx.x; tile < L.n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+        mbar_wait(empty0 + 8 * s, ph ^ 1u);
+        uint32_t nxt = cur;
+        while (nxt + 1 < L.n_segs && tile_begin[nxt + 1] <= tile) ++nxt;
+        if (nxt != cur) { cur = nxt; seg = load_seg(L.segs + cur); }
+        KKTileDesc sd;
+        KKTileLoad ld;
+        kk_make_tile(seg, tile - seg.tile_begin, (uint64_t)(uintptr_t)L.src, L.flags, sd, ld);
+        const uint32_t sb = smem_u32(stage_buf + s * kStageBytes);
+        if (lane == 0) {
+          descs[s] = sd;
+          if (ld.kind == 0) mbar_arrive(full0 + 8 * s);
+          else mbar_arrive_expect_tx(full0 + 8 * s, ld.tx);
+        }
+        __syncwarp();  // the transaction count is armed before any lane's copy can complete against it
+        if (ld.kind == 1) {
+          if (lane == 0) bulk_g2s(sb, L.src + ld.g_off, ld.tx, full0 + 8 * s);
+        } else if (ld.kind != 0) {
+          for (uint32_t r = (uint32_t)lane; r < ld.nrows; r += 32u)
+            bulk_g2s(sb + r * ld.spitch, L.src + ld.g_off + (uint64_t)r * ld.gpitch, ld.row_bytes, full0 + 8 * s);
+        }
+      }
+    }
+#else
     if (lane == 0) {
       uint32_t cur = 0;
       KKSeg seg = load_seg(L.segs);
@@ -611,6 +645,7 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
         }
       }
     }
+#endif
   } else {
     // ===== consumers =====
     const int cwarp = warp - 1, ctid = tid - 32;

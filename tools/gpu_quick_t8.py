@@ -36,5 +36,5 @@ with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") els
 out["speedup"] = out["tiles_32x128"]["ms_median"] / out["tiles_8row"]["ms_median"]
 out["speedup_wide_store"] = out["tiles_32x128"]["ms_median"] / out["tiles_32row_wide_store"]["ms_median"]
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", "t8_ab.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", os.environ.get("KK_QUICK_OUT", "t8_ab.json")), "w"), indent=1)
 print(json.dumps(out))

@@ -68,7 +68,7 @@ def main():
                 if os.path.exists(p):
                     os.remove(p)
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-            json.dump(out, open(os.path.join(ROOT, "gpurun_out", "types_roofline.json"), "w"), indent=1)
+            json.dump(out, open(os.path.join(ROOT, "gpurun_out", os.environ.get("KK_QUICK_OUT", "types_roofline.json")), "w"), indent=1)
     pool.close()
 
 
