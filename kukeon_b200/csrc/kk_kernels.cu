@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
           case KK_OP_T8_F16_BF16:
           case KK_OP_T8_B16: {  // 8 source rows x up to KK_T8_ROW_BYTES per row
             const uint32_t es = seg.op == KK_OP_T8_F32_BF16 ? 4u : 2u;
-            const uint32_t C = seg.p0, W = KK_T8_ROW_BYTES / es;
+            const uint32_t C = seg.p0, W = kk_t8_width(seg.op, C);
             const uint32_t ct = (C + W - 1) / W;
             const uint32_t tr = t / ct, tc = t % ct;
             const uint64_t r0 = (uint64_t)tr * KK_T8_ROWS;

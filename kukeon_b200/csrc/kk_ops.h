@@ -163,6 +163,26 @@ static_assert(sizeof(KKSeg) == 48, "KKSeg layout is shared with the device");
 struct KKBlockGeom {
   uint32_t block_bytes, out_bytes, tile_blocks;
 };
+/* Columns per 8-row tile of a tensor with C source columns.  Default: as many as a staged row holds (1024 f32 / 2048 16-bit), so a row of
+ * 2304 columns is cut 1024 + 1024 + 256 and every third tile of it is a quarter full.  -DKK_T8_BALANCED=1 (A/B build) cuts it into the same
+ * number of EQUAL pieces (768 + 768 + 768), rounded up to 8 columns so that row pieces stay whole 16-byte units for either element size. */
+#ifndef KK_T8_BALANCED
+#define KK_T8_BALANCED 0
+#endif
+static inline KK_HD uint32_t kk_t8_width(uint32_t op, uint32_t C) {
+  const uint32_t wmax = KK_T8_ROW_BYTES / (op == KK_OP_T8_F32_BF16 ? 4u : 2u);
+#if KK_T8_BALANCED
+  if (C > wmax) {
+    const uint32_t n = (C + wmax - 1u) / wmax;
+    const uint32_t w = ((C + n - 1u) / n + 7u) & ~7u;
+    return w < wmax ? w : wmax;
+  }
+#else
+  (void)C;
+#endif
+  return wmax;
+}
+
 static inline KK_HD KKBlockGeom kk_block_geom(uint32_t op) {
   switch (op) {
     case KK_OP_Q4K_BF16: return {KK_Q4K_BLOCK_BYTES, 512u, KK_Q4K_TILE_BLOCKS};
@@ -268,7 +288,7 @@ static inline KK_HD uint64_t kk_seg_tiles(uint32_t op, uint64_t units, uint32_t 
     case KK_OP_T8_F32_BF16:
     case KK_OP_T8_F16_BF16:
     case KK_OP_T8_B16: {
-      const uint64_t w = KK_T8_ROW_BYTES / (op == KK_OP_T8_F32_BF16 ? 4u : 2u);
+      const uint64_t w = kk_t8_width(op, p0);
       return ((units + KK_T8_ROWS - 1) / KK_T8_ROWS) * (((uint64_t)p0 + w - 1) / w);
     }
     case KK_OP_TW_F32_BF16:

@@ -84,8 +84,8 @@ static inline KK_HD void kk_make_tile(const KKSeg& seg, uint32_t t, uint64_t src
     }
     case KK_OP_T_F32_BF16: case KK_OP_T_B32: t_es = 4; t_rows = KK_T_ROWS; t_row_bytes = KK_T_COLS * 4u; t_spitch = KK_T_COLS * 4u + KK_T_PITCH_PAD; t_bulk = 2; break;
     case KK_OP_T_F16_BF16: case KK_OP_T_B16: t_es = 2; t_rows = KK_T_ROWS; t_row_bytes = KK_T_COLS * 2u; t_spitch = KK_T_COLS * 2u + KK_T_PITCH_PAD; t_bulk = 2; break;
-    case KK_OP_T8_F32_BF16: t_es = 4; t_rows = KK_T8_ROWS; t_row_bytes = KK_T8_ROW_BYTES; t_compact = true; t_bulk = 4; break;
-    case KK_OP_T8_F16_BF16: case KK_OP_T8_B16: t_es = 2; t_rows = KK_T8_ROWS; t_row_bytes = KK_T8_ROW_BYTES; t_compact = true; t_bulk = 4; break;
+    case KK_OP_T8_F32_BF16: t_es = 4; t_rows = KK_T8_ROWS; t_row_bytes = kk_t8_width(seg.op, seg.p0) * 4u; t_compact = true; t_bulk = 4; break;
+    case KK_OP_T8_F16_BF16: case KK_OP_T8_B16: t_es = 2; t_rows = KK_T8_ROWS; t_row_bytes = kk_t8_width(seg.op, seg.p0) * 2u; t_compact = true; t_bulk = 4; break;
     case KK_OP_TW_F32_BF16: t_es = 4; t_rows = KK_TW_ROWS; t_row_bytes = KK_TW_ROW_BYTES; t_spitch = KK_TW_PITCH; t_bulk = 5; break;
     case KK_OP_TW_F16_BF16: case KK_OP_TW_B16: t_es = 2; t_rows = KK_TW_ROWS; t_row_bytes = KK_TW_ROW_BYTES; t_spitch = KK_TW_PITCH; t_bulk = 5; break;
     default: {  // block-dequantising ops

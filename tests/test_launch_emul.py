@@ -37,7 +37,7 @@ class KKSeg(C.Structure):
 @pytest.fixture(scope="module")
 def emul():
     subprocess.run(["make", "-C", os.path.join(_HERE, "emul"), "-s"], check=True)
-    L = C.CDLL(os.path.join(_HERE, "emul", "_build", "libkk_dequant_emul.so"))
+    L = C.CDLL(os.environ.get("KK_EMUL_LIB") or os.path.join(_HERE, "emul", "_build", "libkk_dequant_emul.so"))  # override: A/B variants below
     L.kk_emul_launch.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(KKSeg), C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.c_uint32, C.c_uint64,
                                  C.c_void_p, C.c_void_p, C.c_void_p]
     L.kk_emul_launch.restype = C.c_int
@@ -205,3 +205,20 @@ def test_random_gguf_inventories_replayed_through_the_device_code(emul, inv, mod
         p = os.path.join(d, "m.gguf")
         synth.write_gguf(p, inv, seed=8, alignment=alignment)
         replay(emul, p, mode=mode, n_parts=n_parts)
+
+
+# ---- A/B build variants whose tile geometry differs from the default (make -C kukeon_b200/csrc variants) ----------------------------------
+@pytest.mark.parametrize("name,emul_lib,select", [("t8bal", "libkk_dequant_emul_t8_balanced.so", "candidate_transpose or random_safetensors")], ids=["t8bal"])
+def test_geometry_variant_replays_through_its_own_planner_and_device_code(name, emul_lib, select):
+    """The variant library's planner (KUKEON_GPULOAD_LIB) and the emulator built with the same switch must agree tile for tile, and the pools
+    must still equal the oracle's.  Skipped when the variant has not been built (they are A/B artefacts, not part of build())."""
+    if os.environ.get("KK_EMUL_LIB"):
+        pytest.skip("nested run")  # the inner pytest must never start another one
+    lib = os.path.join(os.path.dirname(_HERE), "kukeon_b200", "variants", f"libkukeon_gpuload.{name}.so")
+    if not os.path.exists(lib):
+        pytest.skip(f"{lib} not built (make -C kukeon_b200/csrc variants)")
+    subprocess.run(["make", "-C", os.path.join(_HERE, "emul"), "-s"], check=True)
+    env = dict(os.environ, KUKEON_GPULOAD_LIB=lib, KK_EMUL_LIB=os.path.join(_HERE, "emul", "_build", emul_lib))
+    r = subprocess.run([os.sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-p", "no:cacheprovider", "-k", select],
+                       env=env, cwd=os.path.dirname(_HERE), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]

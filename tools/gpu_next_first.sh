@@ -11,8 +11,8 @@ echo "== 3. roofline table of every dequantiser"
 timeout 150 python tools/gpu_quick_types.py --weights-m 512 > gpurun_out/next_types.stdout 2>&1; echo "rc=$?"; tail -30 gpurun_out/next_types.stdout | cut -c1-220
 echo "== 4. the queued parity file (skips the multi-GPU cases on one GPU)"
 timeout 200 python -m pytest tests/test_zz_gpu_quants_f4.py -x -q -m gpu -p no:cacheprovider > gpurun_out/next_zz_pytest.log 2>&1; echo "rc=$?"; tail -8 gpurun_out/next_zz_pytest.log | cut -c1-220
-echo "== 5. A/B builds (make -C kukeon_b200/csrc variants; loaded with KUKEON_GPULOAD_LIB): producer on kk_make_tile (ps1), warp-cooperative row copies (ps2)"
-for v in ps1 ps2; do
+echo "== 5. A/B builds (make -C kukeon_b200/csrc variants; loaded with KUKEON_GPULOAD_LIB): producer on kk_make_tile (ps1), warp-cooperative row copies (ps2), equal-width 8-row tiles (t8bal)"
+for v in ps1 ps2 t8bal; do
   lib=kukeon_b200/variants/libkukeon_gpuload.$v.so
   [ -f $lib ] || { echo "$lib missing (make -C kukeon_b200/csrc variants)"; continue; }
   KUKEON_GPULOAD_LIB=$PWD/$lib timeout 60 python tools/gpu_quick.py > gpurun_out/next_quick_$v.stdout 2>&1; echo "$v parity rc=$?"
