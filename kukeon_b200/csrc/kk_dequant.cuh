@@ -43,6 +43,21 @@ KK_DQ_DEV uint32_t lds32_any(uint32_t a) {
   if ((a & 3u) == 0) return lds32(a);
   return lds32_h(a);
 }
+// Four payload bytes at any address, branch-free: the two aligned words that cover them, funnel-shifted (the scheme of lds64_funnel below;
+// the second word is read only when a is unaligned and may end in the stage's slack).
+KK_DQ_DEV uint32_t lds32_funnel(uint32_t a) {
+  const uint32_t base = a & ~3u, sh = (a & 3u) * 8u;
+  const uint32_t w0 = lds32(base), w1 = sh ? lds32_slack(base + 4u) : 0u;
+  return kk_funnel_r(w0, w1, sh);
+}
+// Which of the two a block type wants is a compile-time matter (tools/sass_budget.py has the counts).  Tile payloads start on 8-byte
+// boundaries in every real file (GGUF aligns tensor data to >= 8 bytes, tiles are multiples of 16 bytes), so blocks whose size is a
+// multiple of 4 are ALWAYS word aligned and the aligned arm of lds32_any is one predicated load (Q5_K: 94 instructions per iteration
+// against 104 with the funnel).  A 256-weight block of 4k + 2 bytes is handled by a whole warp, so its alignment is warp-uniform and
+// alternates from block to block: 1 load or 2 half loads + merge, the same 3 instructions on average as the funnel's 2 loads + shift.  Only
+// the small blocks — eight per warp iteration, each at its own alignment — make the branchy form DIVERGE (both arms run): those take the funnel.
+template <uint32_t BLOCK_BYTES>
+KK_DQ_DEV uint32_t lds32_blk(uint32_t a) { return (BLOCK_BYTES % 4u != 0u && BLOCK_BYTES < 40u /* 32-weight blocks: 17..34 bytes; the smallest 256-weight block has 50 */) ? lds32_funnel(a) : lds32_any(a); }
 // Eight payload bytes at ANY address a -> two words: the three aligned words that cover them, funnel-shifted into place (SHF.R.W).
 // There are no alignment cases, so the lanes of a warp whose blocks sit at different alignments — eight 17-, 18-, 22- or 34-byte blocks
 // per warp iteration — do not diverge (the first version branched three ways: aligned / 2-byte funnel / byte by byte, and such a warp
@@ -149,7 +164,7 @@ KK_DQ_DEV void consume_legacy32(const Dsts& D, uint32_t pay, uint32_t nblk, uint
       q0 = (q0 >> nsh) & 0x0F0F0F0Fu;
       q1 = (q1 >> nsh) & 0x0F0F0F0Fu;
       if (HAS_QH) {  // bit 4 of element e0 + k is bit k of this byte of qh
-        const uint32_t hbits = (lds32_any(blk + kQhOff) >> e0) & 0xFFu;
+        const uint32_t hbits = (lds32_blk<BYTES>(blk + kQhOff) >> e0) & 0xFFu;
         q0 |= spread4(hbits) << 4;
         q1 |= spread4(hbits >> 4) << 4;
       }
@@ -177,8 +192,8 @@ KK_DQ_DEV void consume_q2k(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t 
     const uint32_t sc = lds8(blk + (uint32_t)(lane >> 1));
     const float dl = __fmul_rn(d, (float)(sc & 0xFu));
     const float ml = __fmul_rn(dmin, (float)(sc >> 4));
-    const uint32_t q0 = (lds32_any(blk + q_off) >> sh) & 0x03030303u;
-    const uint32_t q1 = (lds32_any(blk + q_off + 4u) >> sh) & 0x03030303u;
+    const uint32_t q0 = (lds32_blk<KK_Q2K_BLOCK_BYTES>(blk + q_off) >> sh) & 0x03030303u;
+    const uint32_t q1 = (lds32_blk<KK_Q2K_BLOCK_BYTES>(blk + q_off + 4u) >> sh) & 0x03030303u;
     float y[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) y[e] = __fsub_rn(__fmul_rn(dl, byte_to_float<0>(e < 4 ? q0 : q1, e & 3)), ml);
@@ -203,8 +218,8 @@ KK_DQ_DEV void consume_q3k(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t 
     const uint32_t hi2 = (lds8(blk + hi_off) >> hi_sh) & 0x3u;
     const float dl = __fmul_rn(d, (float)((int)(lo4 | (hi2 << 4)) - 32));
     // q = low - 4 when the mask bit is clear = (low | maskbit << 2) - 4: four 3-bit values per word, bias 4
-    const uint32_t w0 = ((lds32_any(blk + q_off) >> sh) & 0x03030303u) | (((lds32_any(blk + i0) >> g) & 0x01010101u) << 2);
-    const uint32_t w1 = ((lds32_any(blk + q_off + 4u) >> sh) & 0x03030303u) | (((lds32_any(blk + i0 + 4u) >> g) & 0x01010101u) << 2);
+    const uint32_t w0 = ((lds32_blk<KK_Q3K_BLOCK_BYTES>(blk + q_off) >> sh) & 0x03030303u) | (((lds32_blk<KK_Q3K_BLOCK_BYTES>(blk + i0) >> g) & 0x01010101u) << 2);
+    const uint32_t w1 = ((lds32_blk<KK_Q3K_BLOCK_BYTES>(blk + q_off + 4u) >> sh) & 0x03030303u) | (((lds32_blk<KK_Q3K_BLOCK_BYTES>(blk + i0 + 4u) >> g) & 0x01010101u) << 2);
     float y[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) y[e] = __fmul_rn(dl, byte_to_float<4>(e < 4 ? w0 : w1, e & 3));
@@ -234,8 +249,8 @@ KK_DQ_DEV void consume_q5k(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t 
     }
     const float dsc = __fmul_rn(d, (float)sc);
     const float dmn = __fmul_rn(dmin, (float)mn);
-    const uint32_t w0 = ((lds32_any(blk + q_off) >> nsh) & 0x0F0F0F0Fu) | (((lds32_any(blk + 16u + i0) >> j) & 0x01010101u) << 4);
-    const uint32_t w1 = ((lds32_any(blk + q_off + 4u) >> nsh) & 0x0F0F0F0Fu) | (((lds32_any(blk + 16u + i0 + 4u) >> j) & 0x01010101u) << 4);
+    const uint32_t w0 = ((lds32_blk<KK_Q5K_BLOCK_BYTES>(blk + q_off) >> nsh) & 0x0F0F0F0Fu) | (((lds32_blk<KK_Q5K_BLOCK_BYTES>(blk + 16u + i0) >> j) & 0x01010101u) << 4);
+    const uint32_t w1 = ((lds32_blk<KK_Q5K_BLOCK_BYTES>(blk + q_off + 4u) >> nsh) & 0x0F0F0F0Fu) | (((lds32_blk<KK_Q5K_BLOCK_BYTES>(blk + 16u + i0 + 4u) >> j) & 0x01010101u) << 4);
     float y[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) y[e] = __fsub_rn(__fmul_rn(dsc, byte_to_float<0>(e < 4 ? w0 : w1, e & 3)), dmn);
@@ -399,8 +414,8 @@ KK_DQ_DEV void consume_iq4xs(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_
     const uint32_t sl = lds8(blk + 4u + (j >> 1));
     const uint32_t ls = ((sl >> (4u * (j & 1u))) & 0xFu) | (((sh >> (2u * j)) & 3u) << 4);
     const float dl = __fmul_rn(d, (float)((int)ls - 32));
-    const uint32_t q0 = (lds32_any(blk + q_off) >> nsh) & 0x0F0F0F0Fu;
-    const uint32_t q1 = (lds32_any(blk + q_off + 4u) >> nsh) & 0x0F0F0F0Fu;
+    const uint32_t q0 = (lds32_blk<KK_IQ4XS_BLOCK_BYTES>(blk + q_off) >> nsh) & 0x0F0F0F0Fu;
+    const uint32_t q1 = (lds32_blk<KK_IQ4XS_BLOCK_BYTES>(blk + q_off + 4u) >> nsh) & 0x0F0F0F0Fu;
     float y[8];
     codebook8<0>(dl, q0, q1, y);
     store_bf16x8(D, dst_off + (uint64_t)b * 512u + (uint32_t)lane * 16u, y);
@@ -469,7 +484,7 @@ KK_DQ_DEV void consume_iq2xxs(const Dsts& D, uint32_t pay, uint32_t nblk, uint64
   for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
     const uint32_t blk = pay + b * KK_IQ2XXS_BLOCK_BYTES;
     const float d = lds_f16(blk);
-    const uint32_t q1 = lds32_any(blk + 6u + 8u * g);
+    const uint32_t q1 = lds32_blk<KK_IQ2XXS_BLOCK_BYTES>(blk + 6u + 8u * g);
     const uint64_t grid = kk_grid_iq2xxs(lds8(blk + 2u + 8u * g + k));
     store_entry(D, dst_off + (uint64_t)b * 512u + (uint32_t)lane * 16u, iq_scale(d, q1 >> 28, 0.25f), (uint32_t)grid, (uint32_t)(grid >> 32),
                 ksigns7((q1 >> (7u * k)) & 0x7Fu));
@@ -505,7 +520,7 @@ KK_DQ_DEV void consume_iq3xxs(const Dsts& D, uint32_t pay, uint32_t nblk, uint64
   for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
     const uint32_t blk = pay + b * KK_IQ3XXS_BLOCK_BYTES;
     const float d = lds_f16(blk);
-    const uint32_t w = lds32_any(blk + 66u + 4u * g);
+    const uint32_t w = lds32_blk<KK_IQ3XXS_BLOCK_BYTES>(blk + 66u + 4u * g);
     const uint32_t lo = kk_grid_iq3xxs(lds8(blk + 2u + 2u * l)), hi = kk_grid_iq3xxs(lds8(blk + 3u + 2u * l));
     store_entry(D, dst_off + (uint64_t)b * 512u + l * 16u, iq_scale(d, w >> 28, 0.5f), lo, hi, ksigns7((w >> (7u * k)) & 0x7Fu));
   }
@@ -564,7 +579,7 @@ KK_DQ_DEV void consume_tq2_0(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_
   for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
     const uint32_t blk = pay + b * KK_TQ2_0_BLOCK_BYTES;
     const float d = lds_f16(blk + 64u);
-    const uint32_t q0 = (lds32_any(blk + q_off) >> sh) & 0x03030303u, q1 = (lds32_any(blk + q_off + 4u) >> sh) & 0x03030303u;
+    const uint32_t q0 = (lds32_blk<KK_TQ2_0_BLOCK_BYTES>(blk + q_off) >> sh) & 0x03030303u, q1 = (lds32_blk<KK_TQ2_0_BLOCK_BYTES>(blk + q_off + 4u) >> sh) & 0x03030303u;
     float y[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) y[e] = __fmul_rn(d, byte_to_float<1>(e < 4 ? q0 : q1, e & 3));
@@ -590,7 +605,7 @@ KK_DQ_DEV void consume_tq1_0(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_
   for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
     const uint32_t blk = pay + b * KK_TQ1_0_BLOCK_BYTES;
     const float d = lds_f16(blk + 52u);
-    const uint32_t t0 = tq1_trits4(lds32_any(blk + a0), m0), t1 = tq1_trits4(lds32_any(blk + a1), m1);
+    const uint32_t t0 = tq1_trits4(lds32_blk<KK_TQ1_0_BLOCK_BYTES>(blk + a0), m0), t1 = tq1_trits4(lds32_blk<KK_TQ1_0_BLOCK_BYTES>(blk + a1), m1);
     float y[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) y[e] = __fmul_rn(d, byte_to_float<1>(e < 4 ? t0 : t1, e & 3));
@@ -610,7 +625,7 @@ KK_DQ_DEV void consume_nvfp4(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_
       // half the unsigned-E4M3 value: (1 + m/8) * 2^(e-8) built as bits; e == 0: m * 2^-10; 0x00 and 0x7F decode to 0
       float d = e ? kk_bits2f(((e + 119u) << 23) | (m << 20)) : __fmul_rn((float)m, 0.0009765625f);
       if (x == 0u || x == 0x7Fu) d = 0.0f;
-      const uint32_t q0 = (lds32_any(blk + 4u + 8u * sb) >> nsh) & 0x0F0F0F0Fu, q1 = (lds32_any(blk + 8u + 8u * sb) >> nsh) & 0x0F0F0F0Fu;
+      const uint32_t q0 = (lds32_blk<KK_NVFP4_BLOCK_BYTES>(blk + 4u + 8u * sb) >> nsh) & 0x0F0F0F0Fu, q1 = (lds32_blk<KK_NVFP4_BLOCK_BYTES>(blk + 8u + 8u * sb) >> nsh) & 0x0F0F0F0Fu;
       float y[8];
       codebook8<1>(d, q0, q1, y);
       store_bf16x8(D, dst_off + (uint64_t)b * 128u + (l & 7u) * 16u, y);

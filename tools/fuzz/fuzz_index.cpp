@@ -37,7 +37,10 @@ int main(int argc, char** argv) {
   if (!d) { perror("opendir"); return 2; }
   while (dirent* e = readdir(d)) {
     std::string n = e->d_name;
-    if (n.size() > 5 && (n.rfind(".gguf") == n.size() - 5 || n.rfind(".safetensors") == n.size() - 12)) seeds.emplace_back(n, slurp(dir + "/" + n));
+    auto ends_with = [&](const char* suf) { const size_t k = strlen(suf); return n.size() > k && n.compare(n.size() - k, k, suf) == 0; };
+    struct stat st;
+    if ((ends_with(".gguf") || ends_with(".safetensors")) && stat((dir + "/" + n).c_str(), &st) == 0 && S_ISREG(st.st_mode))
+      seeds.emplace_back(n, slurp(dir + "/" + n));
   }
   closedir(d);
   if (seeds.empty()) { fprintf(stderr, "no seed files\n"); return 2; }
