@@ -201,7 +201,10 @@ inline uint32_t f8_to_f16_bits(uint32_t b, bool e5m2) {
 template <bool E5M2>
 inline uint32_t kk_f8x2_to_f16x2(uint32_t v) { return f8_to_f16_bits(v, E5M2) | (f8_to_f16_bits(v >> 8, E5M2) << 16); }
 
-constexpr int kConsumerWarps = 16;  // must equal KK_CONSUMER_WARPS of the kernel build
+#ifndef KK_CONSUMER_WARPS
+#define KK_CONSUMER_WARPS 16
+#endif
+constexpr int kConsumerWarps = KK_CONSUMER_WARPS;  // must equal KK_CONSUMER_WARPS of the kernel build (the cw20 A/B variant has its own emulator library)
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 #define KK_DQ_DEV static inline
 #define min(a, b) ((a) < (b) ? (a) : (b))

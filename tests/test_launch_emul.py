@@ -208,7 +208,9 @@ def test_random_gguf_inventories_replayed_through_the_device_code(emul, inv, mod
 
 
 # ---- A/B build variants whose tile geometry differs from the default (make -C kukeon_b200/csrc variants) ----------------------------------
-@pytest.mark.parametrize("name,emul_lib,select", [("t8bal", "libkk_dequant_emul_t8_balanced.so", "candidate_transpose or random_safetensors")], ids=["t8bal"])
+@pytest.mark.parametrize("name,emul_lib,select", [("t8bal", "libkk_dequant_emul_t8_balanced.so", "candidate_transpose or random_safetensors"),
+                                                  ("cw20", "libkk_dequant_emul_cw20.so", "llama_bf16 or mixed_safetensors or every_gguf or candidate_transpose or random_")],
+                         ids=["t8bal", "cw20"])
 def test_geometry_variant_replays_through_its_own_planner_and_device_code(name, emul_lib, select):
     """The variant library's planner (KUKEON_GPULOAD_LIB) and the emulator built with the same switch must agree tile for tile, and the pools
     must still equal the oracle's.  Skipped when the variant has not been built (they are A/B artefacts, not part of build())."""
