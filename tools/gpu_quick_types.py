@@ -31,6 +31,13 @@ def main():
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         peak = json.load(open(pk)).get("hbm_gbs")
+    # static prediction committed next to the profiles (tools/sass_budget.py --json): hot-path instructions -> issue ceiling per op
+    pred = {}
+    pj = os.path.join(ROOT, "profiles", "r01", "sass_budget.json")
+    if os.path.exists(pj):
+        pred = json.load(open(pj)).get("ops", {})
+    opname = lambda dt: "KK_OP_" + dt.replace("_K", "K").replace("IQ4_NL", "IQ4NL").replace("IQ4_XS", "IQ4XS").replace("IQ2_XXS", "IQ2XXS").replace("IQ2_XS", "IQ2XS") \
+        .replace("IQ2_S", "IQ2S").replace("IQ3_XXS", "IQ3XXS").replace("IQ3_S", "IQ3S").replace("IQ1_S", "IQ1S").replace("IQ1_M", "IQ1M") + "_BF16"  # noqa: E731
     rows = (args.weights_m << 20) // 8192 // 4 * 4
     out = {"weights": rows * 8192, "peak_GBps": peak, "types": {}}
     pool = gpupool.Pool([0])
@@ -57,6 +64,10 @@ def main():
                            "write_GBps": st["out_bytes"] / (med / 1e3) / 1e9, "setup_s": time.time() - t0}
                     if peak:
                         row["frac_of_copy_peak"] = row["GBps"] / peak
+                    pr = pred.get(opname(dt))
+                    if pr:  # fraction of the issue slots the measured rate would need if only the hot path issued (Q4_K calibrates: 0.50 predicted, 0.62 measured)
+                        row["predicted_issue_ceiling_GBps"] = pr["issue_ceiling_GBps"]
+                        row["issue_fraction_at_measured_rate"] = row["GBps"] / pr["issue_ceiling_GBps"]
                     out["types"][dt] = row
                     print(dt, json.dumps(row), flush=True)
                 finally:

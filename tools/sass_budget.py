@@ -219,6 +219,7 @@ def analyse():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--md")
+    ap.add_argument("--json", help="write {op: {hot, bytes_in, bytes_out, issue_ceiling_GBps}} (read by tools/gpu_quick_types.py to print prediction next to measurement)")
     args = ap.parse_args()
     rows, total, _ = analyse()
     issue_rate = SM_COUNT * SM_GHZ * ISSUE_PER_CLK  # G warp instructions / s
@@ -246,6 +247,15 @@ def main():
         mix = [str(r["mix"].get(n, 0)) for n in names]
         extra = f" (+{len(r['inner_loops'])} inner: {r['inner_loops']})" if r["inner_loops"] else ""
         out.append(f"| {r['op']} | {r['static']} | {r['loop']}{extra} | " + " | ".join(cols + mix) + " |")
+    if args.json:
+        import json
+        js = {}
+        for r in rows:
+            ib = ITER_BYTES.get(r["op"])
+            if ib and r.get("hot"):
+                js[r["op"]] = {"hot": r["hot"], "bytes_in": ib[0], "bytes_out": ib[1], "issue_ceiling_GBps": issue_rate / r["hot"] * (ib[0] + ib[1])}
+        with open(args.json, "w") as f:
+            json.dump({"issue_rate_Ginstr_s": issue_rate, "hbm_peak_GBps": HBM_PEAK_GBS, "ops": js}, f, indent=1)
     text = "\n".join(out) + "\n"
     sys.stdout.write(text)
     if args.md:
