@@ -36,6 +36,9 @@ constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kThreads = 32 + kConsumerThreads;  // 288
 constexpr uint32_t kStageBytes = KK_TILE_SRC_BYTES + KK_STAGE_PAD;
 
+#ifndef KK_Q4K_ROTATE
+#define KK_Q4K_ROTATE 0
+#endif
 #ifndef KK_PRODUCER_SHARED
 #define KK_PRODUCER_SHARED 0  // 2: as 1, with all 32 producer lanes issuing the per-row bulk copies.  1: the producer warp computes every tile with kk_make_tile (kk_tile.h, the function tests/emul replays launches
                               // through) instead of the in-line switch below; an A/B build until it has had its own run on hardware
@@ -727,7 +730,13 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
         case KK_OP_COPY: consume_copy(D, pay, t.n_units, t.dst_off, ctid); break;
         case KK_OP_F32_BF16: consume_f32(D, pay, t.n_units, t.dst_off, ctid); break;
         case KK_OP_F16_BF16: consume_f16(D, pay, t.n_units, t.dst_off, ctid); break;
+#if KK_Q4K_ROTATE
+        // A/B build: a 224-block tile is 56 quads for 16 warps — warps 0-7 run four iterations, warps 8-15 three, on every tile.  Rotating the
+        // warp numbering by half the warps on odd tiles gives every warp 4 + 3 over two tiles (outputs depend on the quad, not on the warp).
+        case KK_OP_Q4K_BF16: consume_q4k(D, pay, t.n_units, t.dst_off, (cwarp + (int)(it & 1u) * (kConsumerWarps / 2)) % kConsumerWarps, lane); break;
+#else
         case KK_OP_Q4K_BF16: consume_q4k(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
+#endif
         case KK_OP_Q8_0_BF16: consume_q8_0(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
         case KK_OP_Q6K_BF16: consume_q6k(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
         case KK_OP_Q4_0_BF16: consume_legacy32<KK_Q4_0_BLOCK_BYTES, false, false>(D, pay, t.n_units, t.dst_off, cwarp, lane); break;

@@ -19,7 +19,7 @@ for v in ps1 ps2 t8bal cw20; do
   KUKEON_GPULOAD_LIB=$PWD/$lib KK_QUICK_OUT=t8_ab_$v.json timeout 60 python tools/gpu_quick_t8.py > gpurun_out/next_t8_$v.stdout 2>&1; echo "$v t8 rc=$?"; tail -c 600 gpurun_out/t8_ab_$v.json
 done
 echo "== 6. A/B builds of the Q4_K tile geometry (q4k192: 192-block tiles; q4kbal: 14 contiguous blocks per warp) against the default"
-for v in default q4k192 q4kbal cw20; do
+for v in default q4k192 q4kbal q4krot cw20; do
   lib=kukeon_b200/variants/libkukeon_gpuload.$v.so; [ $v = default ] && lib=kukeon_b200/libkukeon_gpuload.so
   [ -f $lib ] || { echo "$lib missing"; continue; }
   KUKEON_GPULOAD_LIB=$PWD/$lib KK_QUICK_OUT=q4k_$v.json timeout 90 python tools/gpu_quick_types.py --types Q4_K --weights-m 2048 --passes 20 > gpurun_out/next_q4k_$v.stdout 2>&1; echo "$v rc=$?"; tail -3 gpurun_out/next_q4k_$v.stdout | cut -c1-200
