@@ -30,7 +30,7 @@ def inventories(draw):
     return out
 
 
-@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@settings(max_examples=int(os.environ.get("KK_HYP_EXAMPLES", 60)), deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
 @given(inv=inventories(), mode=st.sampled_from([0, 1, 2]), n_parts=st.integers(1, 8), flags=st.sampled_from([0, 1, 2, 3, 8, 9, 16, 19, 24, 33, 35, 49, 65, 67]),
        pad=st.booleans(), chunk_mb=st.sampled_from([1, 2]))
 def test_random_inventories_plan_to_the_oracle_pool(native, inv, mode, n_parts, flags, pad, chunk_mb):
@@ -88,7 +88,7 @@ def gguf_inventories(draw):
     return out
 
 
-@settings(max_examples=50, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@settings(max_examples=int(os.environ.get("KK_HYP_EXAMPLES", 50)), deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
 @given(inv=gguf_inventories(), mode=st.sampled_from([0, 1, 2]), n_parts=st.integers(1, 8), alignment=st.sampled_from([8, 32, 64]), chunk_mb=st.sampled_from([1, 2]))
 def test_random_gguf_inventories_plan_to_the_oracle_pool(native, inv, mode, n_parts, alignment, chunk_mb):
     """Every block-quantised type the kernel dequantises, at random shapes / file alignments / modes / rank counts: index == oracle,
