@@ -178,7 +178,7 @@ from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E
 from tests.test_plan_property import gguf_inventories, inventories  # noqa: E402
 
 
-@settings(max_examples=int(os.environ.get("KK_HYP_EXAMPLES", 40)), deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@settings(max_examples=int(os.environ.get("KK_HYP_EXAMPLES", 120)), deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
 @given(inv=inventories(), mode=st.sampled_from([0, 1, 2]), n_parts=st.integers(1, 6), pad=st.booleans(),
        flags=st.sampled_from([0, 2, 16, 18, 33, 35, 49, 65, 67, 81]))  # every flag set whose ops the replay covers (no 32x128 transposes, no row exchange)
 def test_random_safetensors_inventories_replayed_through_the_device_code(emul, inv, mode, n_parts, pad, flags):
@@ -195,7 +195,7 @@ def test_random_safetensors_inventories_replayed_through_the_device_code(emul, i
         replay(emul, p, mode=mode, flags=flags, n_parts=n_parts)
 
 
-@settings(max_examples=int(os.environ.get("KK_HYP_EXAMPLES", 40)), deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@settings(max_examples=int(os.environ.get("KK_HYP_EXAMPLES", 120)), deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
 @given(inv=gguf_inventories(), mode=st.sampled_from([0, 1, 2]), n_parts=st.integers(1, 6), alignment=st.sampled_from([8, 32, 64]))
 def test_random_gguf_inventories_replayed_through_the_device_code(emul, inv, mode, n_parts, alignment):
     import tempfile
