@@ -58,3 +58,26 @@ def test_reference_arm_prints_one_json_line(tmp_path):
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0} and d["gpu_launches"] == 0
     assert d["config"]["workload"].startswith("GPT-2-small") and d["n_gpus"] == 1 and d["steps"] == 1
+
+
+def test_next_round_gpu_script_points_at_things_that_exist():
+    """tools/gpu_next_first.sh is the first command of the next round's GPU budget: every script it runs must exist, parse, and every A/B
+    variant it loads must be one the csrc Makefile builds."""
+    import ast
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sh = os.path.join(root, "tools", "gpu_next_first.sh")
+    assert subprocess.run(["bash", "-n", sh]).returncode == 0
+    text = open(sh).read()
+    for rel in sorted(set(re.findall(r"\b((?:tools|tests)/[\w/]+\.py)\b", text))):
+        path = os.path.join(root, rel)
+        assert os.path.exists(path), rel
+        ast.parse(open(path).read(), rel)
+    mk = open(os.path.join(root, "kukeon_b200", "csrc", "Makefile")).read()
+    built = set(re.findall(r"(\w+):-D", re.search(r"^VARIANTS := (.*)$", mk, re.M).group(1)))
+    wanted = set()
+    for m in re.finditer(r"for v in ([\w ]+); do", text):
+        wanted |= set(m.group(1).split())
+    wanted.discard("default")
+    assert wanted and wanted <= built, (wanted, built)
