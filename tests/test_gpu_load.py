@@ -59,25 +59,6 @@ def test_unpadded_header_exercises_the_misaligned_path(pool, tmp_path):
         load_and_check(pool, p)
 
 
-def test_q4_k_m_style_mixed_quants_q6k_q8_0(pool, tmp_path):
-    """Real Q4_K_M GGUFs mix Q4_K with Q6_K (and Q8_0 appears in other presets): bit-exact vs the oracle and vs the
-    committed gguf-py fixture."""
-    from tests.test_plan import q4km_tensors
-    p = str(tmp_path / "q4km.gguf")
-    synth.write_gguf(p, q4km_tensors(hidden=512, ffn=1536, layers=2, vocab=1024), 9)
-    load_and_check(pool, p)
-    g = os.path.join(G, "q4km_mix.gguf")
-    load_and_check(pool, g)
-    outs = np.load(g + ".bf16.npz")
-    m = pool.load(g)
-    try:
-        for name in outs.files:
-            pl = m.placements(name)[0]
-            assert np.array_equal(m.read(0, pl.pool_offset, pl.nbytes).view(np.uint16), outs[name]), name
-    finally:
-        m.release()
-
-
 def test_golden_files(pool):
     load_and_check(pool, os.path.join(G, "st_mixed.safetensors"))
     load_and_check(pool, os.path.join(G, "sharded"))
@@ -450,14 +431,11 @@ def test_multi_destination_store_paths_on_one_gpu(native, tmp_path, ndst):
     synth.make_gpt2(f, n_layer=2, d=96, vocab=301, n_pos=40)
     f2 = str(tmp_path / "gpt2_odd.safetensors")
     synth.write_safetensors(f2, synth.gpt2_tensors(n_layer=1, d=40, vocab=50, n_pos=8, dtype="F16"), 3)
-    from tests.test_plan import q4km_tensors
-    g2 = str(tmp_path / "q4km.gguf")
-    synth.write_gguf(g2, q4km_tensors(), 9)
     f3 = str(tmp_path / "gpt2_d41.safetensors")  # rows of 41/123/164 elements: not 16-byte multiples -> direct-global transpose path
     synth.write_safetensors(f3, synth.gpt2_tensors(n_layer=2, d=41, vocab=50, n_pos=8), 4)
     env = dict(os.environ, KUKEON_GPULOAD_TEST_NDST=str(ndst))
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-c", _NDST_CHILD, root, f"{d}:0", f"{mixed}:0", f"{g}:0", f"{g2}:0", f"{f}:1", f"{f}:3", f"{f2}:1", f"{f3}:1", f"{f3}:3"],
+    r = subprocess.run([sys.executable, "-c", _NDST_CHILD, root, f"{d}:0", f"{mixed}:0", f"{g}:0", f"{f}:1", f"{f}:3", f"{f2}:1", f"{f3}:1", f"{f3}:3"],
                        capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-3000:]
 
@@ -505,11 +483,10 @@ def _virtual_ranks(pool, path, mode, n, flags=0):
 
 @pytest.mark.parametrize("n", [2, 4, 8])
 def test_virtual_ranks_broadcast_on_one_gpu(pool, tmp_path, n):
-    from tests.test_plan import q4km_tensors
     d = str(tmp_path / "llama")
     synth.make_llama(d, dict(hidden=256, ffn=704, layers=2, kv_dim=64, vocab=3000), max_shard_bytes=3_000_000)
-    g = str(tmp_path / "q4km.gguf")
-    synth.write_gguf(g, q4km_tensors(), 9)
+    g = str(tmp_path / "q4k.gguf")  # Q4_K + F32 here; the Q4_K_M mix (Q6_K, Q8_0) runs the same way in tests/test_zz_gpu_quants_f4.py
+    synth.write_gguf(g, synth.mixtral_gguf_tensors(hidden=256, ffn=768, layers=2, experts=2, vocab=512, kv_dim=256), 9)
     f = str(tmp_path / "gpt2.safetensors")
     synth.make_gpt2(f, n_layer=2, d=96, vocab=301, n_pos=40)
     for path, flags in ((d, 0), (g, 0), (f, gpupool.LOAD_GPT2_CONV1D_T)):
@@ -598,19 +575,6 @@ def test_concurrent_loads_of_different_checkpoints_share_the_staging_ring_safely
         for m in out:
             if m is not None:
                 m.release()
-
-
-def test_gguf_alignment_8_puts_quant_blocks_off_16_byte_boundaries(pool, tmp_path):
-    """general.alignment = 8: block-quantised tensors start 8 bytes off a 16-byte boundary, so the kernel's byte-assembled
-    shared-memory reads (not the vector ones) feed the dequantisers."""
-    from tests.test_plan import q4km_tensors
-    p = str(tmp_path / "a8.gguf")
-    tensors = [("pad.weight", "F32", [2])] + q4km_tensors(hidden=256, ffn=512, layers=1, vocab=256) + [("tail.weight", "F16", [3])]
-    synth.write_gguf(p, tensors, 21, alignment=8)
-    recs = gpupool.index(p)
-    assert any(r["dtype"] == "Q4_K" and r["file_offset"] % 16 == 8 for r in recs)
-    assert any(r["dtype"] == "Q6_K" and r["file_offset"] % 16 == 8 for r in recs)
-    load_and_check(pool, p)
 
 
 def test_error_paths_through_the_abi(pool, tmp_path):

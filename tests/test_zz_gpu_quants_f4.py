@@ -5,7 +5,8 @@ against the oracle and against the committed gguf-py fixtures.
 STATUS: these kernels were written after round 1's profiling budget was spent, against the host emulation of their device source
 (tests/test_dequant_emul.py).  The round's last GPU seconds ran tools/gpu_quick.py (all PASS) and the first 18 cases of this file
 (all passed; profiles/r01/late_hw_check.log, late_zz_pytest.log).  The file sorts after every other GPU test file on purpose, so a
-surprise in the cases that have not run yet cannot mask the long-verified suite under `pytest -x`."""
+surprise in the cases that have not run yet cannot mask the long-verified suite under `pytest -x`.  For the same reason the Q4_K_M
+cases (Q6_K / Q8_0) of tests/test_gpu_load.py live at the end of this file since those two device functions were rewritten."""
 import os
 
 import numpy as np
@@ -13,7 +14,7 @@ import pytest
 
 from kukeon_b200 import gpupool
 from oracle import oracle
-from tests.test_gpu_load import assert_pool_matches, load_and_check
+from tests.test_gpu_load import _NDST_CHILD, _virtual_ranks, assert_pool_matches, load_and_check
 from tests.test_plan import F4_MIX, f4_tensors
 from tools import synth
 
@@ -351,3 +352,66 @@ def test_nvls_broadcast_single_process(native, tmp_path):
     with gpupool.Pool([0], n_staging_buffers=2, staging_buffer_bytes=1 * MB, n_reader_threads=1) as one:
         with pytest.raises(gpupool.ErrUnsupported, match="at least two devices"):
             one.load(d, mode=gpupool.MODE_BROADCAST, fanout=gpupool.FANOUT_NVLS)
+
+
+# ---- Q4_K_M mixes (Q4_K + Q6_K + Q8_0).  These cases ran green on hardware with the first Q6_K / Q8_0 device functions and lived in
+# tests/test_gpu_load.py; they moved here when those two functions were rewritten (word-wide value assembly, branch-free unaligned loads)
+# against the emulation tier only, so that the core file depends on nothing that has not had its own hardware run. -------------------------
+def test_q4_k_m_style_mixed_quants_q6k_q8_0(pool, tmp_path):
+    """Real Q4_K_M GGUFs mix Q4_K with Q6_K (and Q8_0 appears in other presets): bit-exact vs the oracle and vs the
+    committed gguf-py fixture."""
+    from tests.test_plan import q4km_tensors
+    p = str(tmp_path / "q4km.gguf")
+    synth.write_gguf(p, q4km_tensors(hidden=512, ffn=1536, layers=2, vocab=1024), 9)
+    load_and_check(pool, p)
+    g = os.path.join(G, "q4km_mix.gguf")
+    load_and_check(pool, g)
+    outs = np.load(g + ".bf16.npz")
+    m = pool.load(g)
+    try:
+        for name in outs.files:
+            pl = m.placements(name)[0]
+            assert np.array_equal(m.read(0, pl.pool_offset, pl.nbytes).view(np.uint16), outs[name]), name
+    finally:
+        m.release()
+
+
+def test_gguf_alignment_8_puts_quant_blocks_off_16_byte_boundaries(pool, tmp_path):
+    """general.alignment = 8: block-quantised tensors start 8 bytes off a 16-byte boundary, so the kernel's byte-assembled
+    shared-memory reads (not the vector ones) feed the dequantisers."""
+    from tests.test_plan import q4km_tensors
+    p = str(tmp_path / "a8.gguf")
+    tensors = [("pad.weight", "F32", [2])] + q4km_tensors(hidden=256, ffn=512, layers=1, vocab=256) + [("tail.weight", "F16", [3])]
+    synth.write_gguf(p, tensors, 21, alignment=8)
+    recs = gpupool.index(p)
+    assert any(r["dtype"] == "Q4_K" and r["file_offset"] % 16 == 8 for r in recs)
+    assert any(r["dtype"] == "Q6_K" and r["file_offset"] % 16 == 8 for r in recs)
+    load_and_check(pool, p)
+
+
+def test_q4_k_m_mix_through_the_eight_destination_ladder(native, tmp_path):
+    import subprocess
+    import sys
+    from tests.test_plan import q4km_tensors
+    g2 = str(tmp_path / "q4km.gguf")
+    synth.write_gguf(g2, q4km_tensors(), 9)
+    env = dict(os.environ, KUKEON_GPULOAD_TEST_NDST="8")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", _NDST_CHILD, root, f"{g2}:0"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-3000:]
+
+
+def test_q4_k_m_mix_virtual_rank_broadcast(pool, tmp_path):
+    from tests.test_plan import q4km_tensors
+    g = str(tmp_path / "q4km.gguf")
+    synth.write_gguf(g, q4km_tensors(), 9)
+    shards, recs = oracle.index_path(g)
+    ms = _virtual_ranks(pool, g, gpupool.MODE_BROADCAST, 4, 0)
+    try:
+        for m in ms:
+            m.load_part()
+        for m in ms:
+            assert_pool_matches(m, 0, shards, recs, flags=0)
+    finally:
+        for m in ms:
+            m.release()
