@@ -538,12 +538,13 @@ void pull_slices(kk_model* m, float* ms_total) {
   Device& dev = c->devs[(size_t)m->dev_idx[0]];
   const int n = m->opts.part_count, me = m->opts.part_index;
   std::vector<int> peers;
+  // Every rank owns a slice buffer (never smaller than 256 B) and every peer's must be attached before stage 2, whether or not the
+  // planner gave that rank any bytes: a rank that skipped the exchange is a protocol error of the caller, and reporting success for it
+  // only because its part happened to be empty (a checkpoint smaller than one staging chunk) would hide the same mistake at full size.
   for (int k = 1; k < n; ++k) {
     const int r = (me + k) % n;
-    if (m->part_range[(size_t)r].second > m->part_range[(size_t)r].first) {
-      if (!m->peer_slice_ptr[r]) fail(KK_ESTATE, "KK_FANOUT_PULL: the slice buffer of rank %d is not attached (kk_peer_attach_buffer, KK_BUF_SLICE)", r);
-      peers.push_back(r);
-    }
+    if (!m->peer_slice_ptr[r]) fail(KK_ESTATE, "KK_FANOUT_PULL: the slice buffer of rank %d is not attached (kk_peer_attach_buffer, KK_BUF_SLICE)", r);
+    if (m->part_range[(size_t)r].second > m->part_range[(size_t)r].first) peers.push_back(r);
   }
   KK_CUDA(cudaSetDevice(dev.ordinal));
   EventSet ev(2);

@@ -61,15 +61,19 @@ def test_reference_arm_prints_one_json_line(tmp_path):
 
 
 def test_next_round_gpu_script_points_at_things_that_exist():
-    """tools/gpu_next_first.sh is the first command of the next round's GPU budget: every script it runs must exist, parse, and every A/B
-    variant it loads must be one the csrc Makefile builds."""
+    """The GPU command files of the current round (tools/r02/*.sh) each cost box minutes: every script they run must exist and parse, and every
+    A/B variant they load must be one the csrc Makefile builds."""
     import ast
     import re
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    sh = os.path.join(root, "tools", "gpu_next_first.sh")
-    assert subprocess.run(["bash", "-n", sh]).returncode == 0
-    text = open(sh).read()
+    import glob
+    scripts = sorted(glob.glob(os.path.join(root, "tools", "r02", "*.sh")))
+    assert scripts
+    text = ""
+    for sh in scripts:
+        assert subprocess.run(["bash", "-n", sh]).returncode == 0, sh
+        text += open(sh).read()
     for rel in sorted(set(re.findall(r"\b((?:tools|tests)/[\w/]+\.py)\b", text))):
         path = os.path.join(root, rel)
         assert os.path.exists(path), rel

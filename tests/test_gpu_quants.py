@@ -1,12 +1,7 @@
-"""GPU parity for the §8(f4) quant types (Q4_0, Q4_1, Q5_0, Q5_1, Q2_K, Q3_K, Q5_K, IQ4_NL, IQ4_XS, MXFP4, FP8 widening) and for the
-other paths written after round 1's GPU budget was spent (8-row transpose tiles, KK_FANOUT_PULL), through the C ABI, bit for bit
-against the oracle and against the committed gguf-py fixtures.
-
-STATUS: these kernels were written after round 1's profiling budget was spent, against the host emulation of their device source
-(tests/test_dequant_emul.py).  The round's last GPU seconds ran tools/gpu_quick.py (all PASS) and the first 18 cases of this file
-(all passed; profiles/r01/late_hw_check.log, late_zz_pytest.log).  The file sorts after every other GPU test file on purpose, so a
-surprise in the cases that have not run yet cannot mask the long-verified suite under `pytest -x`.  For the same reason the Q4_K_M
-cases (Q6_K / Q8_0) of tests/test_gpu_load.py live at the end of this file since those two device functions were rewritten."""
+"""GPU parity for the §8(f4) quant types (Q4_0, Q4_1, Q5_0, Q5_1, Q2_K, Q3_K, Q5_K, the codebook and lattice i-quants, ternary types, MXFP4 / NVFP4,
+FP8 widening), the transposing loads and KK_FANOUT_PULL / KK_FANOUT_NVLS, through the C ABI, bit for bit against the oracle and against the
+committed gguf-py fixtures.  Error paths live in tests/test_zz_gpu_errors.py (sorted last); the Q4_K_M mixes (Q6_K / Q8_0) are at the
+front of tests/test_gpu_load.py."""
 import os
 
 import numpy as np
@@ -14,7 +9,7 @@ import pytest
 
 from kukeon_b200 import gpupool
 from oracle import oracle
-from tests.test_gpu_load import _NDST_CHILD, _virtual_ranks, assert_pool_matches, load_and_check
+from tests.test_gpu_load import _virtual_ranks, assert_pool_matches, load_and_check
 from tests.test_plan import F4_MIX, f4_tensors
 from tools import synth
 
@@ -232,29 +227,6 @@ def test_pull_fan_out_virtual_ranks_on_one_gpu(pool, tmp_path, n):
                 m.release()
 
 
-def test_pull_argument_and_state_errors(pool, tmp_path):
-    d = str(tmp_path / "llama")
-    synth.make_llama(d, dict(hidden=128, ffn=352, layers=1, kv_dim=32, vocab=500), max_shard_bytes=3_000_000)
-    with pytest.raises(gpupool.ErrInvalid, match="one-process-per-GPU"):
-        pool.load(d, mode=gpupool.MODE_BROADCAST, fanout=gpupool.FANOUT_PULL)
-    with pytest.raises(gpupool.ErrInvalid):
-        pool.load(d, mode=gpupool.MODE_SCATTER, fanout=gpupool.FANOUT_PULL, part_index=0, part_count=2)
-    f = str(tmp_path / "gpt2.safetensors")
-    synth.make_gpt2(f, n_layer=1, d=96, vocab=301, n_pos=40)
-    with pytest.raises(gpupool.ErrUnsupported, match="transposing"):
-        pool.load(f, mode=gpupool.MODE_BROADCAST, fanout=gpupool.FANOUT_PULL, flags=gpupool.LOAD_GPT2_CONV1D_T | gpupool.LOAD_DEFER, part_index=0, part_count=2)
-    m = pool.load(d, mode=gpupool.MODE_BROADCAST, fanout=gpupool.FANOUT_PULL, flags=gpupool.LOAD_DEFER, part_index=0, part_count=2)
-    try:
-        m.load_part()
-        with pytest.raises(gpupool.ErrState, match="not attached"):
-            m.convert_local()  # the other rank's slice was never attached: refuse, do not leave half a pool marked loaded
-        assert not m.info()["loaded"]
-        with pytest.raises(gpupool.ErrState):
-            m.peer_attach_buffer(1, gpupool.BUF_RAW, b"\0" * 64)
-    finally:
-        m.release()
-
-
 def _pull_rank_main(rank, world, port, path, out_dir):
     import torch
     import torch.distributed as dist
@@ -352,66 +324,3 @@ def test_nvls_broadcast_single_process(native, tmp_path):
     with gpupool.Pool([0], n_staging_buffers=2, staging_buffer_bytes=1 * MB, n_reader_threads=1) as one:
         with pytest.raises(gpupool.ErrUnsupported, match="at least two devices"):
             one.load(d, mode=gpupool.MODE_BROADCAST, fanout=gpupool.FANOUT_NVLS)
-
-
-# ---- Q4_K_M mixes (Q4_K + Q6_K + Q8_0).  These cases ran green on hardware with the first Q6_K / Q8_0 device functions and lived in
-# tests/test_gpu_load.py; they moved here when those two functions were rewritten (word-wide value assembly, branch-free unaligned loads)
-# against the emulation tier only, so that the core file depends on nothing that has not had its own hardware run. -------------------------
-def test_q4_k_m_style_mixed_quants_q6k_q8_0(pool, tmp_path):
-    """Real Q4_K_M GGUFs mix Q4_K with Q6_K (and Q8_0 appears in other presets): bit-exact vs the oracle and vs the
-    committed gguf-py fixture."""
-    from tests.test_plan import q4km_tensors
-    p = str(tmp_path / "q4km.gguf")
-    synth.write_gguf(p, q4km_tensors(hidden=512, ffn=1536, layers=2, vocab=1024), 9)
-    load_and_check(pool, p)
-    g = os.path.join(G, "q4km_mix.gguf")
-    load_and_check(pool, g)
-    outs = np.load(g + ".bf16.npz")
-    m = pool.load(g)
-    try:
-        for name in outs.files:
-            pl = m.placements(name)[0]
-            assert np.array_equal(m.read(0, pl.pool_offset, pl.nbytes).view(np.uint16), outs[name]), name
-    finally:
-        m.release()
-
-
-def test_gguf_alignment_8_puts_quant_blocks_off_16_byte_boundaries(pool, tmp_path):
-    """general.alignment = 8: block-quantised tensors start 8 bytes off a 16-byte boundary, so the kernel's byte-assembled
-    shared-memory reads (not the vector ones) feed the dequantisers."""
-    from tests.test_plan import q4km_tensors
-    p = str(tmp_path / "a8.gguf")
-    tensors = [("pad.weight", "F32", [2])] + q4km_tensors(hidden=256, ffn=512, layers=1, vocab=256) + [("tail.weight", "F16", [3])]
-    synth.write_gguf(p, tensors, 21, alignment=8)
-    recs = gpupool.index(p)
-    assert any(r["dtype"] == "Q4_K" and r["file_offset"] % 16 == 8 for r in recs)
-    assert any(r["dtype"] == "Q6_K" and r["file_offset"] % 16 == 8 for r in recs)
-    load_and_check(pool, p)
-
-
-def test_q4_k_m_mix_through_the_eight_destination_ladder(native, tmp_path):
-    import subprocess
-    import sys
-    from tests.test_plan import q4km_tensors
-    g2 = str(tmp_path / "q4km.gguf")
-    synth.write_gguf(g2, q4km_tensors(), 9)
-    env = dict(os.environ, KUKEON_GPULOAD_TEST_NDST="8")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-c", _NDST_CHILD, root, f"{g2}:0"], capture_output=True, text=True, env=env, timeout=600)
-    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-3000:]
-
-
-def test_q4_k_m_mix_virtual_rank_broadcast(pool, tmp_path):
-    from tests.test_plan import q4km_tensors
-    g = str(tmp_path / "q4km.gguf")
-    synth.write_gguf(g, q4km_tensors(), 9)
-    shards, recs = oracle.index_path(g)
-    ms = _virtual_ranks(pool, g, gpupool.MODE_BROADCAST, 4, 0)
-    try:
-        for m in ms:
-            m.load_part()
-        for m in ms:
-            assert_pool_matches(m, 0, shards, recs, flags=0)
-    finally:
-        for m in ms:
-            m.release()
