@@ -14,9 +14,13 @@ content, files warm in tmpfs/page cache.  A "step" = one pass of the hot path ov
 * `e2e`    (GB/s): the same through the public call a user makes (modelhub.Load -> kk_load_part) with HOST
   buffers: pread from the warm files into the pinned ring, H2D copies, kernels, and a device->host read of a
   result (pool checksum word) plus kk_export, all inside the timed region.
-* `roofline`: dominant kernel kk_convert_kernel; algorithmic bytes = 2 x shard bytes (2 B read + 2 B written per
-  bf16 element) / its CUDA-event duration, against MEASURED_PEAKS.json's hbm_gbs.
-* `cpu_baseline`: the oracle's C port (oracle/kk_oracle.c, OpenMP, all host threads) on a bounded sample.
+* `roofline`: dominant kernel kk_convert_kernel.  N = 1: bound "hbm", algorithmic bytes = 2 x shard bytes (2 B read + 2 B written
+  per bf16 element) / its CUDA-event duration, against MEASURED_PEAKS.json's hbm_gbs.  N > 1 broadcast: bound "nvlink", the
+  bytes every GPU has to receive ((N-1)/N of the pool) / the fan-out stage's CUDA-event time, against a peer-copy rate measured
+  in the same run (every rank reading from its ring neighbour at once, kk_probe_peer) and against 900 GB/s nominal.
+* `cpu_baseline`: the oracle's C port (oracle/kk_oracle.c, OpenMP, all host threads) over the WHOLE checkpoint.
+* `secondary` (N = 1, default workload): the same kernel stage on a 4-layer Mixtral q4_K GGUF — the expanding conversion for which
+  the north_star's HBM-write fraction is meaningful (a bf16 copy has to read what it writes and tops out near 0.5 of it).
 
 The reference (eminwux/kukeon) has no loader and Go is absent, so `--impl reference` times that same CPU port
 (kind "port") — see DESIGN.md.
@@ -69,12 +73,15 @@ def parse():
     ap.add_argument("--eager-peers", action="store_true", help="enable peer access to every GPU in kk_open (A/B for time-to-ready)")
     ap.add_argument("--no-exchange", action="store_true", help="scatter: every rank gathers its own column runs from the file (no NVLink row exchange)")
     ap.add_argument("--no-single-process", action="store_true", help="skip the one-process-all-GPUs time-to-ready measurement at N > 1")
-    ap.add_argument("--t8", action="store_true", help="gpt2: transpose on 8-row tiles (KK_LOAD_T8_TILES), A/B against the 32x128 tiles")
-    ap.add_argument("--tw", action="store_true", help="gpt2: transpose on 32-row wide-store tiles (KK_LOAD_TW_TILES), A/B against the other two")
-    ap.add_argument("--fanout", default="p2p", choices=["p2p", "raw", "pull"],
-                    help="broadcast order: fused convert+fan-out (p2p), all-gather the file bytes then convert locally (raw), or convert into own pool + "
-                         "slice buffer and pull the peers' slices (pull: peers map 1/N of the bytes, for one-process-per-GPU time-to-ready)")
-    return ap.parse_args()
+    ap.add_argument("--no-secondary", action="store_true", help="N = 1 default workload: skip the short Mixtral q4_K record (`secondary`)")
+    ap.add_argument("--fanout", default="auto", choices=["auto", "p2p", "raw", "pull"],
+                    help="broadcast order: fused convert+fan-out by P2P stores (p2p), all-gather the file bytes then convert locally (raw), or convert into own "
+                         "pool + slice buffer and pull the peers' slices (pull: peers map 1/N of the bytes).  auto = pull in the one-process-per-GPU shape "
+                         "this script runs in (its peer mappings are what time-to-ready is made of), p2p for transposing loads")
+    a = ap.parse_args()
+    if a.fanout == "auto":
+        a.fanout = "p2p" if a.workload == "gpt2" else "pull"
+    return a
 
 
 # ---------------------------------------------------------------------------------------------
@@ -176,14 +183,17 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU arm (oracle port) — the only place bench.py touches oracle/
 # ---------------------------------------------------------------------------------------------
-def cpu_port_setup(path: str, sample_bytes: int):
+def cpu_port_setup(path: str, sample_bytes: int | None = None):
+    """Jobs over the whole checkpoint (sample_bytes None) and an UNTOUCHED output buffer: its pages are first touched by the untimed warm-up
+    pass, i.e. by the OpenMP thread that writes them in every later pass (orc_cpu_load schedules jobs statically), so the buffer ends up
+    spread over both sockets.  Round 1 touched it from one thread — everything on one NUMA node — and the same port read 9 GB/s on one box
+    and 50 GB/s on the next."""
     from oracle import coracle, oracle
     shards, recs = oracle.index_path(path)
     plan, total = oracle.plan_pool(recs)
     jobs, src = coracle.make_jobs(recs, plan, job_bytes=8 << 20, max_src_bytes=sample_bytes)
     hi = max((j.dst_off + j.nbytes // coracle._UNITS[j.op][0] * coracle._UNITS[j.op][1] for j in jobs), default=0)
     pool = np.empty(min(total, hi) + 4096, np.uint8)
-    pool[::4096] = 0  # first touch outside the timed region
     return coracle, shards, jobs, src, pool
 
 
@@ -200,10 +210,9 @@ def run_reference(args, spec, path, file_bytes):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = min(file_bytes, 4 << 30)
-    ctx = cpu_port_setup(path, sample)
+    ctx = cpu_port_setup(path, None if file_bytes <= (40 << 30) else 40 << 30)  # whole checkpoint for every BASELINE config that fits a step into seconds
     cores = os.cpu_count() or 1
-    for _ in range(max(args.warmup, 1)):
+    for _ in range(max(min(args.warmup, 3), 1)):  # the first pass is also the parallel first touch of the output buffer
         cpu_port_step(ctx)
     ts = [cpu_port_step(ctx) for _ in range(args.steps)]
     tot = sum(ts)
@@ -211,9 +220,12 @@ def run_reference(args, spec, path, file_bytes):
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": tot / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-        "data": "synthetic", "config": {"workload": spec["name"], "file_bytes": file_bytes, "files": "warm in tmpfs/page cache"},
+        "data": "synthetic", "config": {"workload": spec["name"], "file_bytes": file_bytes, "files": "warm in tmpfs/page cache",
+                                        "same_config": ctx[3] == file_bytes},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"first {ctx[3] / 1e9:.2f} GB of the checkpoint per step, pread + convert into host memory (oracle/kk_oracle.c, OpenMP)"},
+                         "sample": (("the whole checkpoint" if ctx[3] == file_bytes else f"first {ctx[3] / 1e9:.2f} GB of the checkpoint") +
+                                    f" ({ctx[3] / 1e9:.2f} GB) per step, pread + convert into host memory (oracle/kk_oracle.c, OpenMP static schedule, "
+                                    "output pages first-touched by their writers)")},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -317,7 +329,7 @@ def main():
     brk = {}
     ref = modelhub.Pull(path)
     brk["pull_s"] = time.time() - t_ready0
-    lflags = gpupool.LOAD_DEFER | (gpupool.LOAD_GPT2_CONV1D_T if spec["kind"] == "gpt2" else 0) | (gpupool.LOAD_T8_TILES if args.t8 else 0) | (gpupool.LOAD_TW_TILES if args.tw else 0)
+    lflags = gpupool.LOAD_DEFER | (gpupool.LOAD_GPT2_CONV1D_T if spec["kind"] == "gpt2" else 0)
     exchange = world > 1 and mode == gpupool.MODE_SCATTER and not args.no_exchange
     if exchange:
         lflags |= gpupool.LOAD_SCATTER_EXCHANGE
@@ -329,27 +341,47 @@ def main():
                       part_index=rank if world > 1 else 0, part_count=world if world > 1 else 0)
     brk["plan_alloc_s"] = time.time() - t1
     t1 = time.time()
+    which = gpupool.BUF_RAW if raw_order else gpupool.BUF_SLICE if pull_order else gpupool.BUF_POOL
+    attach_thread = None
     if world > 1 and (mode == gpupool.MODE_BROADCAST or exchange):
-        which = gpupool.BUF_RAW if raw_order else gpupool.BUF_SLICE if pull_order else gpupool.BUF_POOL
         h = m.export_buffer(local, which)
         hs = [None] * world
         dist.all_gather_object(hs, h, group=gloo)
         brk["handle_exchange_s"] = time.time() - t1
         t1 = time.time()
-        for r, hh in enumerate(hs):
-            if r != rank:
-                m.peer_attach_buffer(r, which, hh)
-        brk["peer_attach_s"] = time.time() - t1
+
+        def attach_all():
+            ta = time.time()
+            for k in range(1, world):  # ring order: the ranks do not all open rank 0's buffer first
+                r = (rank + k) % world
+                m.peer_attach_buffer(r, which, hs[r])
+            brk["peer_attach_s"] = time.time() - ta
+
+        if pull_order and not args.kernel_only:
+            # PULL: stage 1 writes only this rank's own pool and slice buffer, so the peers' slice buffers are mapped (cudaIpcOpenMemHandle,
+            # the expensive part of time-to-ready in this shape) on a second thread WHILE the part is being read, copied and converted
+            attach_thread = threading.Thread(target=attach_all)
+            attach_thread.start()
+        else:
+            attach_all()
     t1 = time.time()
-    barrier()
+    if attach_thread is None:
+        barrier()
     if args.kernel_only:
         m.stage_resident()
         barrier()
         m.convert_resident()
+        if two_stage:
+            barrier()
+            m.convert_local()
     else:
         brk["barrier_s"] = time.time() - t1
         t1 = time.time()
         m.load_part()
+        brk["stage1_s"] = time.time() - t1
+        if attach_thread is not None:
+            attach_thread.join()
+            brk["attach_wait_after_stage1_s"] = time.time() - t1 - brk["stage1_s"]
         if two_stage:
             barrier()
             m.convert_local()
@@ -359,6 +391,7 @@ def main():
     brk["export_s"] = time.time() - t1
     barrier()
     t_ready = None if args.kernel_only else allmax(time.time() - t_ready0)
+    t_ready_incl_open = None if t_ready is None else allmax(time.time() - t_ready0 + t_open)
     st0 = m.stats()
 
     # pinned H2D probe (plumbing; tells what the PCIe link of this box can do for the e2e leg)
@@ -438,6 +471,7 @@ def main():
     if mode == gpupool.MODE_SCATTER:
         delivered = allsum(float(part["out_bytes"]))
     e2e_val = delivered * args.steps / e2e_time / 1e9
+    file_read = allsum(float(local_src))  # bytes all ranks read from the files per step (= the checkpoint once, whatever N)
     chunks_per_load = part["chunks"]
 
     # ---- value: kernel stage from the HBM-resident image ---------------------------------------------------
@@ -508,13 +542,17 @@ def main():
         alg_per_step = local_src + 2 * part["out_bytes"] + (pool_bytes - part["out_bytes"])
     alg_per_launch = alg_per_step / max(n_launch, 1)
     achieved = alg_per_launch / (avg_launch_ms / 1e3) / 1e9 if avg_launch_ms > 0 else 0.0
-    traffic = None
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of THIS kernel build (profiles/traffic.json names the capture and
+    # the build it was taken from): dram__bytes_read.sum + dram__bytes_write.sum of one launch as a ratio to that launch's algorithmic bytes, scaled to
+    # this run's launch.  Never measured inside a timed run (nothing here runs under a profiler).
+    traffic = traffic_src = None
     tf = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tf):
+    if os.path.exists(tf) and world == 1:
         try:
             key = args.workload if (args.workload != "mixtral-q4k" or args.qtype == "Q4_K") else None  # the capture is of the Q4_K kernel only
-            ratio = json.load(open(tf)).get(key, {}).get("ratio") if key else None
-            traffic = ratio * alg_per_launch if ratio and world == 1 else None
+            ent = json.load(open(tf)).get(key, {}) if key else {}
+            if ent.get("ratio"):
+                traffic, traffic_src = ent["ratio"] * alg_per_launch, ent.get("source")
         except Exception:  # noqa: BLE001
             traffic = None
     # HBM-write roofline: bytes WRITTEN per launch against what a store-only kernel sustains on this box, measured now.
@@ -526,18 +564,50 @@ def main():
             copy_probe = max(pool.probe_hbm(local, gpupool.PROBE_COPY, 2 << 30) for _ in range(3))
         except Exception as e:  # noqa: BLE001
             print(f"[bench] HBM probe failed: {e}", file=sys.stderr)
-    roofline = {"bound": "hbm", "kernel": "kk_convert_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "write_peak_GBps": write_peak, "ldst_copy_probe_GBps": copy_probe,
-                "hbm_write_frac": ((part["out_bytes"] / max(n_launch, 1)) / (avg_launch_ms / 1e3) / 1e9 / write_peak) if write_peak and avg_launch_ms > 0 else None,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_per_launch, "avg_launch_ms": avg_launch_ms,
-                "launches_per_step": n_launch,
-                "write_only_frac_of_peak": (part["out_bytes"] / max(n_launch, 1)) / (avg_launch_ms / 1e3) / 1e9 / peak if avg_launch_ms > 0 else 0.0}
+    hbm_roofline = {"bound": "hbm", "kernel": "kk_convert_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "write_peak_GBps": write_peak, "ldst_copy_probe_GBps": copy_probe,
+                    "hbm_write_frac": ((part["out_bytes"] / max(n_launch, 1)) / (avg_launch_ms / 1e3) / 1e9 / write_peak) if write_peak and avg_launch_ms > 0 else None,
+                    "hbm_write_note": "a device-resident bf16 copy reads what it writes: half its traffic is reads, so its write fraction is capped near 0.5 and the "
+                                      ">= 0.70 HBM-write target only applies to expanding conversions (see `secondary`)" if spec["kind"] == "llama" else None,
+                    "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_per_launch, "avg_launch_ms": avg_launch_ms,
+                    "launches_per_step": n_launch,
+                    "write_only_frac_of_peak": (part["out_bytes"] / max(n_launch, 1)) / (avg_launch_ms / 1e3) / 1e9 / peak if avg_launch_ms > 0 else 0.0}
+    roofline = hbm_roofline
     nvlink = None
     if world > 1 and mode == gpupool.MODE_BROADCAST:
-        egress = part["out_bytes"] * (world - 1)
-        gbps = egress / (sum(step_ms) / len(step_ms) / 1e3) / 1e9
-        nvlink = {"egress_bytes_per_step_per_gpu": egress, "achieved_GBps_per_gpu": gbps, "peak_measured": 770.0, "peak_nominal": 900.0,
-                  "frac_of_measured": gbps / 770.0, "frac_of_nominal": gbps / 900.0, "form": "sharded ingest + fused P2P all-gather stores"}
+        # peer-copy peak measured NOW: every rank reads from its ring neighbour's attached buffer at the same moment (copy engine, CUDA events)
+        probes = []
+        try:
+            for _ in range(3):
+                barrier()
+                probes.append(m.probe_peer((rank + 1) % world, which, 1 << 30))
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] peer probe failed: {e}", file=sys.stderr)
+        mine = max(probes) if probes else 0.0
+        probe_mean = allsum(mine) / world
+        probe_min = -allmax(-mine)
+        step = sum(step_ms) / len(step_ms)
+        if pull_order:
+            moved = pool_bytes - part["out_bytes"]  # ingress: every other rank's slice
+            stage_ms = sum(b for _, b in raw_ms) / len(raw_ms)
+            form = "all-gather by P2P bulk LOADS from the peers' slice buffers (stage 2; bytes are NVLink ingress per GPU)"
+        elif raw_order:
+            moved = local_src * (world - 1)
+            stage_ms = sum(a for a, _ in raw_ms) / len(raw_ms)
+            form = "all-gather of the file bytes by P2P bulk stores (stage 1; bytes are NVLink egress per GPU)"
+        else:
+            moved = part["out_bytes"] * (world - 1)
+            stage_ms = step
+            form = "sharded ingest + fused P2P all-gather stores (bytes are NVLink egress per GPU)"
+        gbps = moved / (stage_ms / 1e3) / 1e9 if stage_ms > 0 else 0.0
+        pk_meas = probe_mean if probe_mean > 0 else None
+        nvlink = {"bytes_per_step_per_gpu": moved, "stage_ms": stage_ms, "achieved_GBps_per_gpu": gbps, "peak_measured": pk_meas, "peak_measured_min_over_ranks": probe_min or None,
+                  "peak_measured_how": "cudaMemcpyAsync D2D of 1 GiB from the ring neighbour's attached buffer, all ranks at once, best of 3, mean over ranks",
+                  "peak_nominal": 900.0, "frac_of_measured": gbps / pk_meas if pk_meas else None, "frac_of_nominal": gbps / 900.0, "form": form}
+        roofline = {"bound": "nvlink", "kernel": "kk_convert_kernel", "achieved": gbps, "peak": pk_meas or 900.0, "unit": "GB/s",
+                    "frac": gbps / (pk_meas or 900.0), "peak_source": "peer-copy probe measured in this run (see nvlink.peak_measured_how)" if pk_meas else "nominal 900 GB/s per direction (probe failed)",
+                    "peak_nominal": 900.0, "frac_of_nominal": gbps / 900.0, "traffic": None, "bytes_per_step_per_gpu": moved, "stage_ms": stage_ms, "form": form,
+                    "hbm_side": {k: hbm_roofline[k] for k in ("achieved", "peak", "frac", "algorithmic_bytes_per_launch", "avg_launch_ms", "launches_per_step")}}
 
     # ---- optional NCCL comparison collective ----------------------------------------------------------------
     nccl = None
@@ -549,14 +619,25 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             m.unstage_resident()
-            ctx = cpu_port_setup(path, min(file_bytes, 4 << 30))
+            ctx = cpu_port_setup(path, None if file_bytes <= (40 << 30) else 40 << 30)
+            cpu_port_step(ctx)  # untimed: parallel first touch of the output buffer
             cpu_port_step(ctx)
             ts = [cpu_port_step(ctx) for _ in range(5)]
             cpu = {"value": ctx[3] / statistics.median(ts) / 1e9, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                   "sample": f"first {ctx[3] / 1e9:.2f} GB of the checkpoint, median of {len(ts)} passes, pread + convert into host memory, all OpenMP threads",
+                   "sample": (("the whole checkpoint" if ctx[3] == file_bytes else f"first {ctx[3] / 1e9:.2f} GB of the checkpoint") +
+                              f" ({ctx[3] / 1e9:.2f} GB), median of {len(ts)} passes after 2 untimed ones, pread + convert into host memory, all OpenMP threads"),
                    "best": ctx[3] / min(ts) / 1e9, "worst": ctx[3] / max(ts) / 1e9}
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+
+    # ---- secondary record (N = 1, default workload): an EXPANDING conversion, where the HBM-write fraction means something ------------------
+    secondary = None
+    if rank == 0 and world == 1 and args.workload == "llama3-8b" and not args.layers and not args.no_secondary and not args.kernel_only:
+        try:
+            m.unstage_resident()
+            secondary = secondary_q4k(args, pool, gpupool, modelhub, peak, write_peak)
+        except Exception as e:  # noqa: BLE001
+            secondary = {"error": str(e)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -567,14 +648,17 @@ def main():
                             2: "scatter" + (" (row-parallel tensors exchanged over NVLink: KK_LOAD_SCATTER_EXCHANGE)" if exchange else "")}[mode], "pool_bytes_per_gpu": pool_bytes,
                    "l2": "inputs (>= 2 GB per GPU) far larger than the 126 MB L2; no flush needed", "files": f"warm in {os.path.dirname(d) or d}",
                    "staging": "zero-copy pinned reads" if args.zerocopy else "pinned ring + H2D copy engine", "verified_vs_files": verified,
-                   **({"transpose_tiles": "32 rows x 960 B, 64-byte stores (KK_LOAD_TW_TILES)" if args.tw else "8 rows x 4 KiB (KK_LOAD_T8_TILES)" if args.t8 else "32 x 128"} if spec["kind"] == "gpt2" else {})},
+                   **({"transpose_tiles": "8 source rows x <= 4 KiB, thread = column, 16-byte stores"} if spec["kind"] == "gpt2" else {})},
         "clocks": ck,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(allsum(float(local_src))), "d2h_bytes_per_step": 8 * world,
-                "ms_per_step": e2e_time / args.steps * 1e3, "what": "kk_load_part (pread->pinned->H2D->kernels) + kk_export + checksum word D2H"},
+                "ms_per_step": e2e_time / args.steps * 1e3, "file_GBps": file_read * args.steps / e2e_time / 1e9 if e2e_time == e2e_time else None,
+                "what": "kk_load_part (pread->pinned->H2D->kernels) + kk_export + checksum word D2H; `value` counts the bytes made resident in all N pools "
+                        "(N x checkpoint for a broadcast), `file_GBps` the checkpoint bytes read from the files once per step"},
         "gpu_launches": n_launch * args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "time_to_agent_ready_s": t_ready,
+        "time_to_agent_ready_incl_kk_open_s": t_ready_incl_open,
         "time_to_agent_ready_breakdown_rank0": brk,
         "wall_ms_per_step": wall / args.steps * 1e3,
         "setup": {"synth_s": t_gen, "kk_open_s": t_open, "index_s": st0["index_s"], "plan_s": st0["plan_s"], "alloc_s": st0["alloc_s"],
@@ -583,23 +667,15 @@ def main():
     if pull_order:
         line["config"]["mode"] = "broadcast, PULL order: convert into own pool + slice buffer (stage 1), pull the peers' slices over NVLink (stage 2)"
         line["pull_stages_ms_rank0"] = {"convert_ms": sum(a for a, _ in raw_ms) / len(raw_ms), "pull_ms": sum(b for _, b in raw_ms) / len(raw_ms)}
-        if nvlink:
-            ing = pool_bytes - part["out_bytes"]
-            pm = line["pull_stages_ms_rank0"]["pull_ms"]
-            nvlink.update(egress_bytes_per_step_per_gpu=ing, achieved_GBps_per_gpu=ing / (pm / 1e3) / 1e9 if pm > 0 else 0.0,
-                          form="all-gather by P2P bulk LOADS from the peers' slice buffers (stage 2 only; bytes are ingress per GPU)")
-            nvlink["frac_of_measured"] = nvlink["achieved_GBps_per_gpu"] / 770.0
-            nvlink["frac_of_nominal"] = nvlink["achieved_GBps_per_gpu"] / 900.0
     if raw_order:
         line["config"]["mode"] = "broadcast, RAW order: all-gather file bytes over NVLink (stage 1) + local convert (stage 2)"
         line["raw_stages_ms_rank0"] = {"fanout_ms": sum(a for a, _ in raw_ms) / len(raw_ms), "convert_ms": sum(b for _, b in raw_ms) / len(raw_ms)}
-        if nvlink:
-            eg = local_src * (world - 1)
-            fm = line["raw_stages_ms_rank0"]["fanout_ms"]
-            nvlink.update(egress_bytes_per_step_per_gpu=eg, achieved_GBps_per_gpu=eg / (fm / 1e3) / 1e9 if fm > 0 else 0.0,
-                          form="all-gather of the file bytes by P2P bulk stores (stage 1 only)")
-            nvlink["frac_of_measured"] = nvlink["achieved_GBps_per_gpu"] / 770.0
-            nvlink["frac_of_nominal"] = nvlink["achieved_GBps_per_gpu"] / 900.0
+    if world > 1 and mode == gpupool.MODE_BROADCAST:
+        line["scaling_note"] = ("value(N) / (N x value(1)) is not a parallel efficiency here: at N = 1 a step is a copy inside one GPU's HBM, at N > 1 it is a "
+                                "broadcast whose floor is NVLink ingress, (N-1)/N x checkpoint bytes per GPU at the link rate — at most ~0.28 of N x value(1) "
+                                "for N = 8.  The per-N figure is roofline.frac (bound nvlink); end to end it is e2e.file_GBps and time_to_agent_ready_s.")
+    if secondary is not None:
+        line["secondary"] = secondary
     if nvlink:
         line["nvlink"] = nvlink
     if nccl:
@@ -619,7 +695,7 @@ def main():
                 sp_open = time.time() - t0
                 t0 = time.time()
                 ref2 = modelhub.Pull(path)
-                spf = (gpupool.LOAD_GPT2_CONV1D_T if spec["kind"] == "gpt2" else 0) | (gpupool.LOAD_SCATTER_EXCHANGE if exchange else 0) | (gpupool.LOAD_T8_TILES if args.t8 else 0) | (gpupool.LOAD_TW_TILES if args.tw else 0)
+                spf = (gpupool.LOAD_GPT2_CONV1D_T if spec["kind"] == "gpt2" else 0) | (gpupool.LOAD_SCATTER_EXCHANGE if exchange else 0)
                 m2 = modelhub.Load(sp, ref2, mode=mode, fanout=gpupool.FANOUT_RAW if raw_order else gpupool.FANOUT_P2P, flags=spf)
                 for dev in range(world):
                     m2.export(dev)
@@ -651,7 +727,9 @@ def main():
                     line["nvls_compare"] = cmpres
                 sp.close()
                 line["time_to_agent_ready_single_process_s"] = min(sp_ready, sp_ready2)
-                line["single_process"] = {"what": "one process, one kk_ctx over all N GPUs (kukeond's shape): Pull + kk_load(mode) + kk_export x N; pinned ring and peer access set up in kk_open",
+                line["time_to_agent_ready_single_process_incl_kk_open_s"] = sp_open + sp_ready  # a daemon that opens the pool only when the first model arrives
+                line["single_process"] = {"what": "one process, one kk_ctx over all N GPUs (kukeond's shape): Pull + kk_load(mode) + kk_export x N; pinned ring and peer access are "
+                                                  "set up in kk_open, once per daemon lifetime — reported both without it (a running daemon) and with it (cold daemon, first model)",
                                           "kk_open_s": sp_open, "first_s": sp_ready, "second_s": sp_ready2, "load_s": st2["load_s"], "alloc_s": st2["alloc_s"]}
             except Exception as e:  # noqa: BLE001
                 line["single_process"] = {"error": str(e)}
@@ -662,6 +740,44 @@ def main():
             shutil.rmtree(d, ignore_errors=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def secondary_q4k(args, pool, gpupool, modelhub, peak, write_peak):
+    """Kernel stage of a 4-layer Mixtral-8x7B q4_K GGUF (3.4 GB of blocks -> 12.1 GB of bf16) from the HBM-resident image, same timing rules as
+    `value`: >= 3 warm-ups, CUDA events on the launching stream inside the library, inputs far larger than L2."""
+    from tools import synth
+    t0 = time.time()
+    spec = dict(kind="gguf", tensors=synth.mixtral_gguf_tensors(layers=4), name="Mixtral-8x7B GGUF q4_k -> bf16 (REDUCED to 4 layers)")
+    base = os.path.dirname(pick_data_dir(args, synth.total_bytes(spec["tensors"])))
+    d = os.path.join(base, "kk_bench_secondary_q4k_l4")
+    path = make_files(spec, d)
+    synth_s = time.time() - t0
+    try:
+        ref = modelhub.Pull(path)
+        m = modelhub.Load(pool, ref, mode=gpupool.MODE_SINGLE, fanout=gpupool.FANOUT_P2P, flags=gpupool.LOAD_DEFER)
+        try:
+            m.stage_resident()
+            for _ in range(3):
+                m.convert_resident()
+            steps = 10
+            runs = [m.convert_resident() for _ in range(steps)]
+            part = m.stats()["parts"][0]
+        finally:
+            m.release()
+    finally:
+        if not args.keep_data:
+            shutil.rmtree(d, ignore_errors=True)
+    ms = sum(t for t, _ in runs) / steps
+    n_launch = len(runs[0][1])
+    alg = part["src_bytes"] + part["out_bytes"]
+    ach = alg / (ms / 1e3) / 1e9
+    wr = part["out_bytes"] / (ms / 1e3) / 1e9
+    return {"workload": spec["name"], "what": "kernel stage only (resident image), the expanding conversion of BASELINE config 4 at reduced depth", "steps": steps, "warmup": 3,
+            "ms_per_step": ms, "launches_per_step": n_launch, "src_bytes": part["src_bytes"], "out_bytes": part["out_bytes"], "synth_s": synth_s,
+            "value": part["out_bytes"] / (ms / 1e3) / 1e9, "unit": "GB/s of bf16 made resident",
+            "roofline": {"bound": "hbm", "kernel": "kk_convert_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "algorithmic_bytes_per_step": alg, "write_GBps": wr, "write_peak_GBps": write_peak,
+                         "hbm_write_frac": wr / write_peak if write_peak else None}}
 
 
 def nccl_compare(torch, dist, file_bytes, world, local, args):

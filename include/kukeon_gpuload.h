@@ -115,11 +115,7 @@ typedef enum kk_fanout {
 #define KK_LOAD_F8_TO_BF16 0x10u    /* widen safetensors F8_E4M3 / F8_E5M2 tensors to bf16 (exact; NaN -> 0x7FFF).  Default: FP8 stays
                                       verbatim in the pool — FP8 engines want the bytes, and the per-block scale tensors that FP8
                                       checkpoints carry are model-specific and are not applied here */
-#define KK_LOAD_T8_TILES 0x20u      /* KK_LOAD_GPT2_CONV1D_T: transpose on 8-row x 4 KiB tiles (8x fewer bulk copies per byte, bank-conflict-free
-                                      reads, 16-byte stores).  Candidate geometry, bit-identical results; opt-in until it has been
-                                      measured against the 32x128 tiles on hardware, then it becomes the default */
-#define KK_LOAD_TW_TILES 0x40u      /* second candidate: 32-row x 960-byte tiles whose lane mapping stores full 64-byte segments (fewer, wider
-                                      store transactions than the 8-row tiles, more bulk copies).  Takes precedence over KK_LOAD_T8_TILES */
+/* 0x20 and 0x40 selected round 1's two candidate transpose geometries; the 8-row tiles won the A/B and are what KK_LOAD_GPT2_CONV1D_T uses now */
 
 typedef struct kk_ctx kk_ctx;     /* one per process (kukeond lifetime) */
 typedef struct kk_model kk_model; /* refcounted; one per (checkpoint identity, mode, flags) */
@@ -275,6 +271,10 @@ int kk_unstage_resident(kk_model* m);
 #define KK_PROBE_WRITE 0
 #define KK_PROBE_COPY 1
 int kk_probe_hbm(kk_ctx* ctx, int device, int kind, uint64_t nbytes, float* ms);
+/* NVLink probe for multi-process models: one copy-engine read of up to *nbytes from the buffer of rank `rank` that this model has attached
+ * (which = KK_BUF_POOL, KK_BUF_RAW or KK_BUF_SLICE) into a local scratch, after one untimed pass.  *nbytes returns the bytes actually copied, *ms their
+ * CUDA-event time.  Every rank probing its ring neighbour at the same moment measures the per-GPU NVLink ingress the fan-out is bounded by. */
+int kk_probe_peer(kk_model* m, int rank, int which, uint64_t* nbytes, float* ms);
 
 #ifdef __cplusplus
 }

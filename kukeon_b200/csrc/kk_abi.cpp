@@ -440,5 +440,15 @@ int kk_probe_hbm(kk_ctx* ctx, int device, int kind, uint64_t nbytes, float* ms) 
   });
 }
 
+int kk_probe_peer(kk_model* m, int rank, int which, uint64_t* nbytes, float* ms) {
+  return guard([&] {
+    need(m, "model");
+    need(nbytes, "nbytes");
+    need(ms, "ms");
+    *ms = 0.f;
+    kk::model_probe_peer(m, rank, which, *nbytes, ms);
+  });
+}
+
 }  // extern "C"
 #pragma GCC visibility pop

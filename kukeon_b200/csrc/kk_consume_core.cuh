@@ -157,26 +157,12 @@ KK_DQ_DEV void q4k_quad(const Dsts& D, uint32_t pay, uint32_t b0, uint32_t nb, u
   }
 }
 
-#ifndef KK_Q4K_BALANCED
-#define KK_Q4K_BALANCED 0  // A/B build switch: 1 = every warp takes ceil(nblk / warps) contiguous blocks (224 -> 14 = 4+4+4+2 per warp) instead of
-                           // striding quads across warps (224 -> 16 blocks for warps 0-7, 12 for warps 8-15: the critical path is the 16)
-#endif
 KK_DQ_DEV void consume_q4k(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
   const bool al = (pay & 15u) == 0;  // 144-byte blocks keep the tile's alignment class
-#if KK_Q4K_BALANCED
-  const uint32_t per = (nblk + (uint32_t)kConsumerWarps - 1u) / (uint32_t)kConsumerWarps;
-  const uint32_t lo = (uint32_t)cwarp * per, hi = min(nblk, lo + per);
-  for (uint32_t b0 = lo; b0 < hi; b0 += 4u) {
-    const uint32_t nb = min(4u, hi - b0);
-    if (al) q4k_quad<true>(D, pay, b0, nb, dst_off, lane);
-    else q4k_quad<false>(D, pay, b0, nb, dst_off, lane);
-  }
-#else
   for (uint32_t b0 = (uint32_t)cwarp * 4u; b0 < nblk; b0 += kConsumerWarps * 4u) {
     const uint32_t nb = min(4u, nblk - b0);
     if (al) q4k_quad<true>(D, pay, b0, nb, dst_off, lane);
     else q4k_quad<false>(D, pay, b0, nb, dst_off, lane);
   }
-#endif
 }
 

@@ -1,7 +1,7 @@
 // Consumer bodies of kk_convert_kernel, part 2 (part 1 — copy, casts, Q4_K — is kk_consume_core.cuh):
 //   * block dequantisers of every other GGUF type: Q8_0, Q6_K, Q4_0, Q4_1, Q5_0, Q5_1, Q2_K, Q3_K, Q5_K, IQ4_NL, IQ4_XS, MXFP4;
 //   * the FP8 -> bf16 widening (safetensors F8_E4M3 / F8_E5M2, opt-in);
-//   * the two candidate transpose geometries (8-row tiles, 32-row wide-store tiles) and their gather fallback.
+//   * the 2-D transposes (8-row tiles) and their gather fallback.
 //
 // Each function is written from the point of view of ONE lane and touches nothing but the primitives below, which the
 // including translation unit provides:
@@ -12,7 +12,7 @@
 //                                                bit-identical to gguf-py's numpy arithmetic (oracle/oracle.py)
 //     uint32_t pack_bf16x2(a, b)                 two floats -> bf16x2, RNE, NaN -> 0x7FFF
 //     void     store16_all(D, off, uint4)        16 output bytes to every destination pool
-//     void     store2_all(D, off, u16)           one bf16 (ragged tails)
+//     void     store2_all(D, off, u16)           one bf16 (ragged tails); store4_all(D, off, u32): one 32-bit element (verbatim transposes)
 //     uint4    lds128(a)                         16-byte aligned vector load
 //     uint32_t kk_f8x2_to_f16x2<E5M2>(u16)       two FP8 -> two fp16 (exact; cvt.rn.f16x2.e4m3x2 / .e5m2x2 on the device)
 //     float    kk_bits2f(u32)                    bit cast
@@ -293,44 +293,55 @@ KK_DQ_DEV void consume_f8(const Dsts& D, uint32_t pay, uint32_t n, uint64_t dst_
   }
 }
 
-// ---- 8-row transpose tiles (KK_LOAD_T8_TILES; KK_OP_T8_*) ---------------------------------------------------------------------------
+// ---- 2-D transposes on 8-row tiles (KK_OP_T_*) ---------------------------------------------------------------------------------------
 // The stage holds nr <= 8 source rows of nc columns, row r at sbase + r * pitch (staged by the producer's bulk copies, or gathered
-// by t8_gather when the source rows are not 16-byte aligned).  Thread t takes columns t, t + 512, ...: its 8 loads walk DOWN one
+// by t_gather when the source rows are not 16-byte aligned).  Thread t takes columns t, t + 512, ...: its 8 loads walk DOWN one
 // column while the lanes of its warp sit side by side ALONG the row — consecutive shared-memory words, conflict-free whatever
-// the pitch — and the 8 converted values are the 16 contiguous destination bytes dst[(col0 + c) * R + row0 .. + 8).
+// the pitch — and the 8 converted values are the 8 * OES contiguous destination bytes dst[(col0 + c) * R + row0 .. + 8).
 template <int ES, int CONV>  // CONV: 0 verbatim 16-bit, 1 f32 -> bf16, 2 f16 -> bf16
-KK_DQ_DEV uint32_t t8_pack2(uint32_t a, uint32_t b) {
+KK_DQ_DEV uint32_t t_pack2(uint32_t a, uint32_t b) {
   if (CONV == 1) return pack_bf16x2(kk_bits2f(a), kk_bits2f(b));
   if (CONV == 2) return pack_bf16x2(kk_h2f(a), kk_h2f(b));
   return (a & 0xFFFFu) | (b << 16);
 }
-template <int ES, int CONV>
-KK_DQ_DEV void consume_t8(const Dsts& D, uint32_t sbase, uint32_t pitch, uint32_t nr, uint32_t nc, uint32_t R, uint32_t col0, uint32_t row0,
-                          uint64_t dst_off, int ctid) {
-  const bool vec = nr == KK_T8_ROWS && (R & 7u) == 0 && (row0 & 7u) == 0 && (dst_off & 15u) == 0;
+template <int ES, int CONV>  // CONV 3: verbatim 32-bit (ES == 4, 4-byte outputs); otherwise 2-byte outputs
+KK_DQ_DEV void consume_t(const Dsts& D, uint32_t sbase, uint32_t pitch, uint32_t nr, uint32_t nc, uint32_t R, uint32_t col0, uint32_t row0,
+                         uint64_t dst_off, int ctid) {
+  constexpr uint32_t OES = CONV == 3 ? 4u : 2u;
+  // whole 16-byte stores need every column's 8-row group to start on a 16-byte boundary of the pool
+  const bool vec = nr == KK_T_ROWS && ((R * OES) & 15u) == 0 && ((row0 * OES) & 15u) == 0 && (dst_off & 15u) == 0;
   for (uint32_t c = (uint32_t)ctid; c < nc; c += kConsumerWarps * 32u) {
-    uint32_t v[KK_T8_ROWS];
+    uint32_t v[KK_T_ROWS];
 #pragma unroll
-    for (uint32_t k = 0; k < KK_T8_ROWS; ++k) {
+    for (uint32_t k = 0; k < KK_T_ROWS; ++k) {
       const uint32_t a = sbase + k * pitch + c * (uint32_t)ES;
       v[k] = k < nr ? (ES == 4 ? lds32(a) : lds16(a)) : 0u;
     }
-    const uint64_t off = dst_off + ((uint64_t)(col0 + c) * R + row0) * 2u;
-    if (vec) {
-      store16_all(D, off, make_uint4(t8_pack2<ES, CONV>(v[0], v[1]), t8_pack2<ES, CONV>(v[2], v[3]), t8_pack2<ES, CONV>(v[4], v[5]),
-                                     t8_pack2<ES, CONV>(v[6], v[7])));
+    const uint64_t off = dst_off + ((uint64_t)(col0 + c) * R + row0) * OES;
+    if (CONV == 3) {
+      if (vec) {
+        store16_all(D, off, make_uint4(v[0], v[1], v[2], v[3]));
+        store16_all(D, off + 16u, make_uint4(v[4], v[5], v[6], v[7]));
+      } else {
+#pragma unroll
+        for (uint32_t k = 0; k < KK_T_ROWS; ++k)
+          if (k < nr) store4_all(D, off + 4u * k, v[k]);
+      }
+    } else if (vec) {
+      store16_all(D, off, make_uint4(t_pack2<ES, CONV>(v[0], v[1]), t_pack2<ES, CONV>(v[2], v[3]), t_pack2<ES, CONV>(v[4], v[5]),
+                                     t_pack2<ES, CONV>(v[6], v[7])));
     } else {
 #pragma unroll
-      for (uint32_t k = 0; k < KK_T8_ROWS; ++k)
-        if (k < nr) store2_all(D, off + 2u * k, (uint16_t)(t8_pack2<ES, CONV>(v[k], 0u) & 0xFFFFu));
+      for (uint32_t k = 0; k < KK_T_ROWS; ++k)
+        if (k < nr) store2_all(D, off + 2u * k, (uint16_t)(t_pack2<ES, CONV>(v[k], 0u) & 0xFFFFu));
     }
   }
 }
 // Fallback when the producer could not stage the tile with bulk copies (rows not 16-byte aligned / not a whole number of 16-byte
 // units): every consumer thread copies elements from global memory into the same [row][col] layout; the caller puts a barrier
-// between this and consume_t8.  src points at source element (r0, c0); C = source columns of the tensor.
+// between this and consume_t.  src points at source element (r0, c0); C = source columns of the tensor.
 template <int ES>
-KK_DQ_DEV void t8_gather(const uint8_t* src, uint32_t sbase, uint32_t pitch, uint32_t nr, uint32_t nc, uint32_t C, int ctid) {
+KK_DQ_DEV void t_gather(const uint8_t* src, uint32_t sbase, uint32_t pitch, uint32_t nr, uint32_t nc, uint32_t C, int ctid) {
   for (uint32_t i = (uint32_t)ctid; i < nr * nc; i += kConsumerWarps * 32u) {
     const uint32_t r = i / nc, c = i - r * nc;
     const uint8_t* p = src + ((uint64_t)r * C + c) * (uint32_t)ES;
@@ -419,45 +430,6 @@ KK_DQ_DEV void consume_iq4xs(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_
     float y[8];
     codebook8<0>(dl, q0, q1, y);
     store_bf16x8(D, dst_off + (uint64_t)b * 512u + (uint32_t)lane * 16u, y);
-  }
-}
-
-// ---- 32-row wide-store transpose tiles (KK_LOAD_TW_TILES; KK_OP_TW_*) --------------------------------------------------------------------
-// Stage: nr <= 32 source rows of nc columns, row r at sbase + r * pitch (pitch = KK_TW_PITCH when staged by bulk copies).  A warp
-// takes 8 columns at a time; lane = (cc = lane & 7, rg = lane >> 3) produces rows 8rg .. 8rg+7 of column cb + cc, i.e. 16 of the 64
-// contiguous destination bytes that column has in this tile, so the four rg-lanes of a column write one full 64-byte segment per store
-// instruction.  Reading row 8rg + ((k + 2rg) & 7) at step k spreads the four row groups over different banks (see kk_ops.h).
-template <int ES, int CONV>
-KK_DQ_DEV void consume_tw(const Dsts& D, uint32_t sbase, uint32_t pitch, uint32_t nr, uint32_t nc, uint32_t R, uint32_t col0, uint32_t row0,
-                          uint64_t dst_off, int cwarp, int lane) {
-  const uint32_t cc = (uint32_t)(lane & 7), rg = (uint32_t)(lane >> 3);
-  const uint32_t rbase = 8u * rg;
-  const bool vec = rbase + 8u <= nr && (R & 7u) == 0 && (row0 & 7u) == 0 && (dst_off & 15u) == 0;
-  for (uint32_t cb = (uint32_t)cwarp * 8u; cb < nc; cb += kConsumerWarps * 8u) {
-    const uint32_t c = cb + cc;
-    if (c >= nc || rbase >= nr) continue;
-    uint32_t u[8];  // u[k] = source row rbase + ((k + 2rg) & 7): the rotated order keeps the four row groups on different banks
-#pragma unroll
-    for (uint32_t k = 0; k < 8; ++k) {
-      const uint32_t row = rbase + ((k + 2u * rg) & 7u);
-      const uint32_t a = sbase + row * pitch + c * (uint32_t)ES;
-      u[k] = row < nr ? (ES == 4 ? lds32(a) : lds16(a)) : 0u;
-    }
-    const uint64_t off = dst_off + ((uint64_t)(col0 + c) * R + row0 + rbase) * 2u;
-    if (vec) {
-      // an even rotation keeps row pairs together: word i holds rows (2i + 2rg) & 7 and the next one; undo the rotation on the packed words
-      uint32_t p0 = t8_pack2<ES, CONV>(u[0], u[1]), p1 = t8_pack2<ES, CONV>(u[2], u[3]), p2 = t8_pack2<ES, CONV>(u[4], u[5]),
-               p3 = t8_pack2<ES, CONV>(u[6], u[7]);
-      if (rg & 1u) { const uint32_t t = p3; p3 = p2; p2 = p1; p1 = p0; p0 = t; }            // output word j = packed word (j - 1) & 3
-      if (rg & 2u) { uint32_t t = p0; p0 = p2; p2 = t; t = p1; p1 = p3; p3 = t; }          // output word j = packed word (j - 2) & 3
-      store16_all(D, off, make_uint4(p0, p1, p2, p3));
-    } else {
-#pragma unroll
-      for (uint32_t k = 0; k < 8; ++k) {
-        const uint32_t kr = (k + 2u * rg) & 7u;
-        if (rbase + kr < nr) store2_all(D, off + 2u * kr, (uint16_t)(t8_pack2<ES, CONV>(u[k], 0u) & 0xFFFFu));
-      }
-    }
   }
 }
 

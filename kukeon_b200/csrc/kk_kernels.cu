@@ -12,8 +12,8 @@
 //       Q4_K -> BF16      : one warp per 256-weight super-block; the 8 (scale,min) pairs are decoded once
 //                           and handed to the lanes with __shfl_sync; nibbles become floats with a PRMT
 //                           + FADD magic-number trick; every lane stores 16 B of bf16;
-//       other GGUF quants : Q4_0/Q4_1/Q5_0/Q5_1/Q8_0/Q2_K/Q3_K/Q5_K/Q6_K, one lane per 8 weights (kk_dequant.cuh);
-//       2-D transposes    : shared-memory tile transpose (GPT-2 Conv1D weights).
+//       other GGUF quants : every other block type, one lane per 8 weights (kk_dequant.cuh);
+//       2-D transposes    : 8-row tiles staged by bulk copies, thread = column, one 16-byte store per column (GPT-2 Conv1D weights).
 //   Every output vector is stored to n_dst pools; dst[1..] are NVLink peer mappings, so conversion and
 //   broadcast are ONE kernel and the source bytes are read from HBM exactly once.
 #include <cuda_bf16.h>
@@ -28,39 +28,12 @@ namespace kk {
 namespace {
 
 constexpr int kStages = 4;
-#ifndef KK_CONSUMER_WARPS
-#define KK_CONSUMER_WARPS 16
-#endif
-constexpr int kConsumerWarps = KK_CONSUMER_WARPS;
+constexpr int kConsumerWarps = 16;  // 16 rather than 8: +4 % on q4_K, 1.7x on the transposes; 20 (80 registers) measured no faster (profiles/r02)
 constexpr int kConsumerThreads = kConsumerWarps * 32;
-constexpr int kThreads = 32 + kConsumerThreads;  // 288
+constexpr int kThreads = 32 + kConsumerThreads;  // 544
 constexpr uint32_t kStageBytes = KK_TILE_SRC_BYTES + KK_STAGE_PAD;
 
-#ifndef KK_Q4K_ROTATE
-#define KK_Q4K_ROTATE 0
-#endif
-#ifndef KK_PRODUCER_SHARED
-#define KK_PRODUCER_SHARED 0  // 2: as 1, with all 32 producer lanes issuing the per-row bulk copies.  1: the producer warp computes every tile with kk_make_tile (kk_tile.h, the function tests/emul replays launches
-                              // through) instead of the in-line switch below; an A/B build until it has had its own run on hardware
-#endif
-#if KK_PRODUCER_SHARED
-using TileDesc = KKTileDesc;
-#else
-struct __align__(16) TileDesc {
-  uint32_t op;
-  uint32_t pay_off;  // payload offset inside the stage buffer (0..15 for TMA tiles)
-  uint32_t n_units;  // units in this tile (bytes / elements / blocks); transposes: rows | cols<<16
-  uint32_t bulk;     // 1: aligned copy, bulk-store from shared memory; 2: transpose tile staged row by row with TMA; 3: row-split exchange;
-                     // 4: 8-row transpose tile staged with TMA, rows nc*es bytes apart; 5: 32-row wide-store tile, rows KK_TW_PITCH apart
-  uint64_t dst_off;  // pool byte offset of the tile's first output (transposes: dst tensor origin)
-  uint64_t src_off;  // transposes: byte offset of source element (r0, c0) from L.src
-  uint32_t C;        // transposes: source columns
-  uint32_t R;        // transposes: destination row length
-  uint32_t col0;     // transposes: first source column of the tile
-  uint32_t row0;     // transposes: first destination column (= global source row) of the tile
-  uint32_t pad[4];
-};
-#endif
+using TileDesc = KKTileDesc;  // kk_tile.h: the producer computes every tile with kk_make_tile, the function tests/emul replays launches through
 static_assert(sizeof(TileDesc) == 64, "TileDesc");
 
 constexpr uint32_t kSmemFixed = kStages * kStageBytes + kStages * sizeof(TileDesc) + 2 * kStages * 8;
@@ -244,96 +217,17 @@ __device__ __forceinline__ uint64_t kk_grid_iq1s(uint32_t i) { return __ldg(&kGr
 #include "kk_consume_core.cuh"
 #include "kk_dequant.cuh"
 
-// 2-D transpose tile.  Source elements come either from the TMA-staged tile (t.bulk == 2: the producer pulled
-// the tile's rows into the stage with one cp.async.bulk per row, KK_T_COLS*ES + 16 bytes apart) or, when a row
-// is not 16-byte aligned, straight from global memory through a [col][row] scratch in the stage buffer.
-template <int ES, int OES, int CONV>  // CONV: 0 verbatim, 1 f32->bf16, 2 f16->bf16
-__device__ __forceinline__ void consume_transpose(const Dsts& D, const uint8_t* src, const TileDesc& t, uint32_t sbase, int ctid) {
-  const uint32_t nr = t.n_units & 0xFFFFu, nc = t.n_units >> 16;
-  const bool staged = t.bulk == 2;
-  constexpr uint32_t kPitch = KK_T_COLS * ES + KK_T_PITCH_PAD;
-  if (!staged) {
-    const uint8_t* s0 = src + t.src_off;
-    for (uint32_t i = ctid; i < KK_T_ROWS * KK_T_COLS; i += kConsumerThreads) {
-      const uint32_t r = i / KK_T_COLS, c = i % KK_T_COLS;
-      if (r < nr && c < nc) {
-        const uint8_t* p = s0 + ((uint64_t)r * t.C + c) * ES;
-        uint32_t w = 0;
-        if (((uintptr_t)p & (ES - 1)) == 0) {
-          if (ES == 4) w = *reinterpret_cast<const uint32_t*>(p);
-          else w = *reinterpret_cast<const uint16_t*>(p);
-        } else {
-#pragma unroll
-          for (int k = 0; k < ES; ++k) w |= (uint32_t)p[k] << (8 * k);
-        }
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(sbase + 4 * (c * (KK_T_ROWS + 1) + r)), "r"(w) : "memory");
-      }
-    }
-    named_bar_consumers();
-  }
-  auto elem = [&](uint32_t r, uint32_t c) -> uint32_t {
-    uint32_t w;
-    if (staged) {
-      if (ES == 4) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(sbase + r * kPitch + c * ES));
-      else asm volatile("ld.shared.u16 %0, [%1];" : "=r"(w) : "r"(sbase + r * kPitch + c * ES));
-    } else {
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(sbase + 4 * (c * (KK_T_ROWS + 1) + r)));
-    }
-    return w;
-  };
-  auto conv16 = [&](uint32_t w) -> uint32_t {
-    if (CONV == 1) return to_bf16(__uint_as_float(w));
-    if (CONV == 2) return to_bf16(__half2float(__ushort_as_half((unsigned short)w)));
-    return w & 0xFFFFu;
-  };
-  if (OES == 2 && (t.R & 1u) == 0 && (t.dst_off & 3u) == 0 && (t.row0 & 1u) == 0) {
-    // two adjacent destination elements (source rows 2k, 2k+1) per 4-byte store
-    const uint32_t npair = (nr + 1) / 2;
-    for (uint32_t i = ctid; i < (KK_T_ROWS / 2) * KK_T_COLS; i += kConsumerThreads) {
-      const uint32_t c = i / (KK_T_ROWS / 2), rp = i % (KK_T_ROWS / 2);
-      if (rp < npair && c < nc) {
-        const uint32_t r = 2 * rp;
-        const uint64_t off = t.dst_off + ((uint64_t)(t.col0 + c) * t.R + t.row0 + r) * 2;
-        const uint32_t lo = conv16(elem(r, c));
-        if (r + 1 < nr) store4_all(D, off, lo | (conv16(elem(r + 1, c)) << 16));
-        else store2_all(D, off, (uint16_t)lo);
-      }
-    }
-  } else {
-    for (uint32_t i = ctid; i < KK_T_ROWS * KK_T_COLS; i += kConsumerThreads) {
-      const uint32_t c = i / KK_T_ROWS, r = i % KK_T_ROWS;
-      if (r < nr && c < nc) {
-        const uint32_t w = elem(r, c);
-        const uint64_t off = t.dst_off + ((uint64_t)(t.col0 + c) * t.R + t.row0 + r) * OES;
-        if (OES == 2) store2_all(D, off, (uint16_t)conv16(w));
-        else store4_all(D, off, w);
-      }
-    }
-  }
-}
-
-// 8-row transpose tile (KK_OP_T8_*): staged by the producer (t.bulk == 4) or gathered here.
+// 2-D transpose tile (KK_OP_T_*): staged by the producer (t.bulk == 4) or, when a source row is not 16-byte aligned, gathered here.
 template <int ES, int CONV>
-__device__ __forceinline__ void run_t8(const Dsts& D, const uint8_t* src, const TileDesc& t, uint32_t sbase, int ctid) {
+__device__ __forceinline__ void run_t(const Dsts& D, const uint8_t* src, const TileDesc& t, uint32_t sbase, int ctid) {
   const uint32_t nr = t.n_units & 0xFFFFu, nc = t.n_units >> 16;
   uint32_t pitch = nc * ES;
   if (t.bulk != 4) {
     pitch = (pitch + 3u) & ~3u;
-    t8_gather<ES>(src + t.src_off, sbase, pitch, nr, nc, t.C, ctid);
+    t_gather<ES>(src + t.src_off, sbase, pitch, nr, nc, t.C, ctid);
     named_bar_consumers();
   }
-  consume_t8<ES, CONV>(D, sbase, pitch, nr, nc, t.R, t.col0, t.row0, t.dst_off, ctid);
-}
-
-// 32-row wide-store transpose tile (KK_OP_TW_*): staged by the producer (t.bulk == 5, rows KK_TW_PITCH apart) or gathered here.
-template <int ES, int CONV>
-__device__ __forceinline__ void run_tw(const Dsts& D, const uint8_t* src, const TileDesc& t, uint32_t sbase, int cwarp, int lane, int ctid) {
-  const uint32_t nr = t.n_units & 0xFFFFu, nc = t.n_units >> 16;
-  if (t.bulk != 5) {
-    t8_gather<ES>(src + t.src_off, sbase, KK_TW_PITCH, nr, nc, t.C, ctid);
-    named_bar_consumers();
-  }
-  consume_tw<ES, CONV>(D, sbase, KK_TW_PITCH, nr, nc, t.R, t.col0, t.row0, t.dst_off, cwarp, lane);
+  consume_t<ES, CONV>(D, sbase, pitch, nr, nc, t.R, t.col0, t.row0, t.dst_off, ctid);
 }
 
 __device__ __forceinline__ KKSeg load_seg(const KKSeg* p) {
@@ -371,12 +265,7 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
 
   if (warp == 0) {
     // ===== producer =====
-#if KK_PRODUCER_SHARED == 2
-    // Warp-cooperative producer (A/B build): all 32 lanes walk the tiles in lock step — the tile arithmetic is uniform, so running it on
-    // every lane costs no extra issue slots — lane 0 alone publishes the descriptor and arms the barrier, and the per-row bulk copies of
-    // the transposing tiles (32-64 per tile with the 32x128 geometry, 34 with the wide-store one) are issued by 32 lanes side by side
-    // instead of one after the other by a single thread.
-    {
+    if (lane == 0) {
       uint32_t cur = 0;
       KKSeg seg = load_seg(L.segs);
       uint32_t it = 0;
@@ -389,266 +278,18 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
         KKTileDesc sd;
         KKTileLoad ld;
         kk_make_tile(seg, tile - seg.tile_begin, (uint64_t)(uintptr_t)L.src, L.flags, sd, ld);
+        descs[s] = sd;
         const uint32_t sb = smem_u32(stage_buf + s * kStageBytes);
-        if (lane == 0) {
-          descs[s] = sd;
-          if (ld.kind == 0) mbar_arrive(full0 + 8 * s);
-          else mbar_arrive_expect_tx(full0 + 8 * s, ld.tx);
-        }
-        __syncwarp();  // the transaction count is armed before any lane's copy can complete against it
-        if (ld.kind == 1) {
-          if (lane == 0) bulk_g2s(sb, L.src + ld.g_off, ld.tx, full0 + 8 * s);
-        } else if (ld.kind != 0) {
-          for (uint32_t r = (uint32_t)lane; r < ld.nrows; r += 32u)
-            bulk_g2s(sb + r * ld.spitch, L.src + ld.g_off + (uint64_t)r * ld.gpitch, ld.row_bytes, full0 + 8 * s);
-        }
-      }
-    }
-#else
-    if (lane == 0) {
-      uint32_t cur = 0;
-      KKSeg seg = load_seg(L.segs);
-      uint32_t it = 0;
-      for (uint32_t tile = blockIdx.x; tile < L.n_tiles; tile += gridDim.x, ++it) {
-        const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
-        mbar_wait(empty0 + 8 * s, ph ^ 1u);
-        uint32_t nxt = cur;
-        while (nxt + 1 < L.n_segs && tile_begin[nxt + 1] <= tile) ++nxt;
-        if (nxt != cur) { cur = nxt; seg = load_seg(L.segs + cur); }
-        const uint32_t t = tile - seg.tile_begin;
-#if KK_PRODUCER_SHARED
-        {
-          KKTileDesc sd;
-          KKTileLoad ld;
-          kk_make_tile(seg, t, (uint64_t)(uintptr_t)L.src, L.flags, sd, ld);
-          descs[s] = sd;
-          const uint32_t sb = smem_u32(stage_buf + s * kStageBytes);
-          if (ld.kind == 0) {
-            mbar_arrive(full0 + 8 * s);
-          } else {
-            mbar_arrive_expect_tx(full0 + 8 * s, ld.tx);
-            if (ld.kind == 1) bulk_g2s(sb, L.src + ld.g_off, ld.tx, full0 + 8 * s);
-            else
-              for (uint32_t r = 0; r < ld.nrows; ++r) bulk_g2s(sb + r * ld.spitch, L.src + ld.g_off + (uint64_t)r * ld.gpitch, ld.row_bytes, full0 + 8 * s);
-          }
-          continue;
-        }
-#endif
-        TileDesc d;
-        d.op = seg.op; d.bulk = 0; d.C = 0; d.R = 0; d.col0 = 0; d.row0 = 0; d.src_off = 0;
-        uint32_t in_bytes = 0;          // source bytes of this tile (TMA ops)
-        uint64_t in_off = 0;            // their offset from L.src
-        switch (seg.op) {
-          case KK_OP_COPY: {
-            const uint64_t o = (uint64_t)t * KK_TILE_SRC_BYTES;
-            const uint64_t rem = seg.units - o;
-            d.n_units = rem < KK_TILE_SRC_BYTES ? (uint32_t)rem : KK_TILE_SRC_BYTES;
-            in_bytes = d.n_units; in_off = seg.src_off + o; d.dst_off = seg.dst_off + o;
-            break;
-          }
-          case KK_OP_ROWSPLIT: {
-            const uint64_t o = (uint64_t)t * KK_TILE_SRC_BYTES;
-            const uint64_t rem = seg.units - o;
-            d.n_units = rem < KK_TILE_SRC_BYTES ? (uint32_t)rem : KK_TILE_SRC_BYTES;
-            in_bytes = d.n_units; in_off = seg.src_off + o; d.dst_off = seg.dst_off;
-            d.C = seg.p0;                      // row bytes
-            d.R = seg.p1;                      // slice bytes
-            d.row0 = seg.p2;                   // first row of this rank's piece
-            d.col0 = seg.p3 + (uint32_t)o;     // byte position of the tile inside the piece
-            break;
-          }
-          case KK_OP_F8E4M3_BF16:
-          case KK_OP_F8E5M2_BF16: {
-            const uint64_t e = (uint64_t)t * KK_TILE_SRC_BYTES;
-            const uint64_t rem = seg.units - e;
-            d.n_units = rem < KK_TILE_SRC_BYTES ? (uint32_t)rem : KK_TILE_SRC_BYTES;
-            in_bytes = d.n_units; in_off = seg.src_off + e; d.dst_off = seg.dst_off + e * 2;
-            break;
-          }
-          case KK_OP_F32_BF16: {
-            const uint64_t e = (uint64_t)t * (KK_TILE_SRC_BYTES / 4);
-            const uint64_t rem = seg.units - e;
-            d.n_units = rem < KK_TILE_SRC_BYTES / 4 ? (uint32_t)rem : KK_TILE_SRC_BYTES / 4;
-            in_bytes = d.n_units * 4; in_off = seg.src_off + e * 4; d.dst_off = seg.dst_off + e * 2;
-            break;
-          }
-          case KK_OP_F16_BF16: {
-            const uint64_t e = (uint64_t)t * (KK_TILE_SRC_BYTES / 2);
-            const uint64_t rem = seg.units - e;
-            d.n_units = rem < KK_TILE_SRC_BYTES / 2 ? (uint32_t)rem : KK_TILE_SRC_BYTES / 2;
-            in_bytes = d.n_units * 2; in_off = seg.src_off + e * 2; d.dst_off = seg.dst_off + e * 2;
-            break;
-          }
-          case KK_OP_Q4K_BF16: {
-            const uint64_t b = (uint64_t)t * KK_Q4K_TILE_BLOCKS;
-            const uint64_t rem = seg.units - b;
-            d.n_units = rem < KK_Q4K_TILE_BLOCKS ? (uint32_t)rem : KK_Q4K_TILE_BLOCKS;
-            in_bytes = d.n_units * KK_Q4K_BLOCK_BYTES; in_off = seg.src_off + b * KK_Q4K_BLOCK_BYTES;
-            d.dst_off = seg.dst_off + b * 512u;
-            break;
-          }
-          case KK_OP_Q8_0_BF16: {
-            const uint64_t b = (uint64_t)t * KK_Q8_0_TILE_BLOCKS;
-            const uint64_t rem = seg.units - b;
-            d.n_units = rem < KK_Q8_0_TILE_BLOCKS ? (uint32_t)rem : KK_Q8_0_TILE_BLOCKS;
-            in_bytes = d.n_units * KK_Q8_0_BLOCK_BYTES; in_off = seg.src_off + b * KK_Q8_0_BLOCK_BYTES;
-            d.dst_off = seg.dst_off + b * 64u;
-            break;
-          }
-          case KK_OP_Q6K_BF16: {
-            const uint64_t b = (uint64_t)t * KK_Q6K_TILE_BLOCKS;
-            const uint64_t rem = seg.units - b;
-            d.n_units = rem < KK_Q6K_TILE_BLOCKS ? (uint32_t)rem : KK_Q6K_TILE_BLOCKS;
-            in_bytes = d.n_units * KK_Q6K_BLOCK_BYTES; in_off = seg.src_off + b * KK_Q6K_BLOCK_BYTES;
-            d.dst_off = seg.dst_off + b * 512u;
-            break;
-          }
-          case KK_OP_Q4_0_BF16:
-          case KK_OP_Q4_1_BF16:
-          case KK_OP_Q5_0_BF16:
-          case KK_OP_Q5_1_BF16:
-          case KK_OP_Q2K_BF16:
-          case KK_OP_Q3K_BF16:
-          case KK_OP_Q5K_BF16:
-          case KK_OP_IQ4NL_BF16:
-          case KK_OP_IQ4XS_BF16:
-          case KK_OP_IQ2XXS_BF16:
-          case KK_OP_IQ2XS_BF16:
-          case KK_OP_IQ2S_BF16:
-          case KK_OP_IQ3XXS_BF16:
-          case KK_OP_IQ3S_BF16:
-          case KK_OP_IQ1S_BF16:
-          case KK_OP_IQ1M_BF16:
-          case KK_OP_TQ1_0_BF16:
-          case KK_OP_TQ2_0_BF16:
-          case KK_OP_NVFP4_BF16:
-          case KK_OP_MXFP4_BF16: {  // the other block quants: same tiling, geometry from kk_ops.h
-            const KKBlockTile bt = kk_block_tile(seg, t);
-            d.n_units = bt.n_blocks;
-            in_bytes = bt.in_bytes; in_off = bt.in_off;
-            d.dst_off = bt.dst_off;
-            break;
-          }
-          case KK_OP_T8_F32_BF16:
-          case KK_OP_T8_F16_BF16:
-          case KK_OP_T8_B16: {  // 8 source rows x up to KK_T8_ROW_BYTES per row
-            const uint32_t es = seg.op == KK_OP_T8_F32_BF16 ? 4u : 2u;
-            const uint32_t C = seg.p0, W = kk_t8_width(seg.op, C);
-            const uint32_t ct = (C + W - 1) / W;
-            const uint32_t tr = t / ct, tc = t % ct;
-            const uint64_t r0 = (uint64_t)tr * KK_T8_ROWS;
-            const uint32_t c0 = tc * W;
-            const uint64_t rrem = seg.units - r0;
-            const uint32_t nr = rrem < KK_T8_ROWS ? (uint32_t)rrem : KK_T8_ROWS;
-            const uint32_t nc = (C - c0) < W ? (C - c0) : W;
-            d.n_units = nr | (nc << 16);
-            d.C = C; d.R = seg.p1; d.col0 = c0; d.row0 = seg.p2 + (uint32_t)r0;
-            d.src_off = seg.src_off + (r0 * C + c0) * es;
-            d.dst_off = seg.dst_off;
-            const uint64_t row_pitch = (uint64_t)C * es;
-            const uint32_t rb = nc * es;
-            if ((((uintptr_t)(L.src + d.src_off)) & 15u) == 0 && (row_pitch & 15u) == 0 && (rb & 15u) == 0) {
-              d.bulk = 4;
-              d.pay_off = 0;
-              descs[s] = d;
-              mbar_arrive_expect_tx(full0 + 8 * s, nr * rb);
-              const uint8_t* gp = L.src + d.src_off;
-              const uint32_t sb = smem_u32(stage_buf + s * kStageBytes);
-              if (nc == C) {  // the tile spans whole rows: they are contiguous in the source, one bulk copy brings all of them
-                bulk_g2s(sb, gp, nr * rb, full0 + 8 * s);
-              } else {
-                for (uint32_t r = 0; r < nr; ++r) bulk_g2s(sb + r * rb, gp + r * row_pitch, rb, full0 + 8 * s);
-              }
-              continue;
-            }
-            break;  // unaligned rows: publish the descriptor only, the consumers gather the tile themselves
-          }
-          case KK_OP_TW_F32_BF16:
-          case KK_OP_TW_F16_BF16:
-          case KK_OP_TW_B16: {  // 32 source rows x up to KK_TW_ROW_BYTES per row, KK_TW_PITCH apart in the stage
-            const uint32_t es = seg.op == KK_OP_TW_F32_BF16 ? 4u : 2u;
-            const uint32_t C = seg.p0, W = KK_TW_ROW_BYTES / es;
-            const uint32_t ct = (C + W - 1) / W;
-            const uint32_t tr = t / ct, tc = t % ct;
-            const uint64_t r0 = (uint64_t)tr * KK_TW_ROWS;
-            const uint32_t c0 = tc * W;
-            const uint64_t rrem = seg.units - r0;
-            const uint32_t nr = rrem < KK_TW_ROWS ? (uint32_t)rrem : KK_TW_ROWS;
-            const uint32_t nc = (C - c0) < W ? (C - c0) : W;
-            d.n_units = nr | (nc << 16);
-            d.C = C; d.R = seg.p1; d.col0 = c0; d.row0 = seg.p2 + (uint32_t)r0;
-            d.src_off = seg.src_off + (r0 * C + c0) * es;
-            d.dst_off = seg.dst_off;
-            const uint64_t row_pitch = (uint64_t)C * es;
-            const uint32_t rb = nc * es;
-            if ((((uintptr_t)(L.src + d.src_off)) & 15u) == 0 && (row_pitch & 15u) == 0 && (rb & 15u) == 0) {
-              d.bulk = 5;
-              d.pay_off = 0;
-              descs[s] = d;
-              mbar_arrive_expect_tx(full0 + 8 * s, nr * rb);
-              const uint8_t* gp = L.src + d.src_off;
-              const uint32_t sb = smem_u32(stage_buf + s * kStageBytes);
-              for (uint32_t r = 0; r < nr; ++r) bulk_g2s(sb + r * KK_TW_PITCH, gp + r * row_pitch, rb, full0 + 8 * s);
-              continue;
-            }
-            break;
-          }
-          default: {  // transposes
-            const uint32_t C = seg.p0;
-            const uint32_t ct = (C + KK_T_COLS - 1) / KK_T_COLS;
-            const uint32_t tr = t / ct, tc = t % ct;
-            const uint64_t r0 = (uint64_t)tr * KK_T_ROWS;
-            const uint32_t c0 = tc * KK_T_COLS;
-            const uint64_t rrem = seg.units - r0;
-            const uint32_t nr = rrem < KK_T_ROWS ? (uint32_t)rrem : KK_T_ROWS;
-            const uint32_t nc = (C - c0) < KK_T_COLS ? (C - c0) : KK_T_COLS;
-            const uint32_t es = (seg.op == KK_OP_T_F32_BF16 || seg.op == KK_OP_T_B32) ? 4u : 2u;
-            d.n_units = nr | (nc << 16);
-            d.C = C; d.R = seg.p1; d.col0 = c0; d.row0 = seg.p2 + (uint32_t)r0;
-            d.src_off = seg.src_off + (r0 * C + c0) * es;
-            d.dst_off = seg.dst_off;
-            // rows 16-byte aligned and a whole number of 16-byte units wide: stage the tile with one bulk copy per row
-            const uint64_t row_pitch = (uint64_t)C * es;
-            if ((((uintptr_t)(L.src + d.src_off)) & 15u) == 0 && (row_pitch & 15u) == 0 && ((nc * es) & 15u) == 0) {
-              d.bulk = 2;
-              d.pay_off = 0;
-              descs[s] = d;
-              const uint32_t rb = nc * es, spitch = KK_T_COLS * es + KK_T_PITCH_PAD;
-              mbar_arrive_expect_tx(full0 + 8 * s, nr * rb);
-              const uint8_t* gp = L.src + d.src_off;
-              const uint32_t sb = smem_u32(stage_buf + s * kStageBytes);
-              for (uint32_t r = 0; r < nr; ++r) bulk_g2s(sb + r * spitch, gp + r * row_pitch, rb, full0 + 8 * s);
-              continue;
-            }
-            break;
-          }
-        }
-        uint32_t tx = 0;
-        const uint8_t* g = L.src + in_off;
-        if (in_bytes) {
-          const uint32_t mis = (uint32_t)((uintptr_t)g & 15u);
-          d.pay_off = mis;
-          tx = (mis + in_bytes + 15u) & ~15u;
-          if (seg.op == KK_OP_COPY && mis == 0 && (in_bytes & 15u) == 0 && !(L.flags & (KK_LAUNCH_NO_BULK_STORE | KK_LAUNCH_MULTIMEM)))
-            d.bulk = 1;
-          // row-split exchange: every (row, destination) piece must be a whole number of 16-byte units on both sides
-          if (seg.op == KK_OP_ROWSPLIT && mis == 0 && (seg.p0 & 15u) == 0 && (seg.p1 & 15u) == 0 && (in_bytes & 15u) == 0 &&
-              (seg.dst_off & 15u) == 0 && !(L.flags & KK_LAUNCH_NO_BULK_STORE))
-            d.bulk = 3;
-          g -= mis;
-        } else {
-          d.pay_off = 0;
-        }
-        descs[s] = d;
-        if (tx) {
-          mbar_arrive_expect_tx(full0 + 8 * s, tx);
-          bulk_g2s(smem_u32(stage_buf + s * kStageBytes), g, tx, full0 + 8 * s);
-        } else {
+        if (ld.kind == 0) {
           mbar_arrive(full0 + 8 * s);
+        } else {
+          mbar_arrive_expect_tx(full0 + 8 * s, ld.tx);
+          if (ld.kind == 1) bulk_g2s(sb, L.src + ld.g_off, ld.tx, full0 + 8 * s);
+          else
+            for (uint32_t r = 0; r < ld.nrows; ++r) bulk_g2s(sb + r * ld.spitch, L.src + ld.g_off + (uint64_t)r * ld.gpitch, ld.row_bytes, full0 + 8 * s);
         }
       }
     }
-#endif
   } else {
     // ===== consumers =====
     const int cwarp = warp - 1, ctid = tid - 32;
@@ -730,13 +371,7 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
         case KK_OP_COPY: consume_copy(D, pay, t.n_units, t.dst_off, ctid); break;
         case KK_OP_F32_BF16: consume_f32(D, pay, t.n_units, t.dst_off, ctid); break;
         case KK_OP_F16_BF16: consume_f16(D, pay, t.n_units, t.dst_off, ctid); break;
-#if KK_Q4K_ROTATE
-        // A/B build: a 224-block tile is 56 quads for 16 warps — warps 0-7 run four iterations, warps 8-15 three, on every tile.  Rotating the
-        // warp numbering by half the warps on odd tiles gives every warp 4 + 3 over two tiles (outputs depend on the quad, not on the warp).
-        case KK_OP_Q4K_BF16: consume_q4k(D, pay, t.n_units, t.dst_off, (cwarp + (int)(it & 1u) * (kConsumerWarps / 2)) % kConsumerWarps, lane); break;
-#else
         case KK_OP_Q4K_BF16: consume_q4k(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
-#endif
         case KK_OP_Q8_0_BF16: consume_q8_0(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
         case KK_OP_Q6K_BF16: consume_q6k(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
         case KK_OP_Q4_0_BF16: consume_legacy32<KK_Q4_0_BLOCK_BYTES, false, false>(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
@@ -759,18 +394,12 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
         case KK_OP_TQ1_0_BF16: consume_tq1_0(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
         case KK_OP_TQ2_0_BF16: consume_tq2_0(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
         case KK_OP_NVFP4_BF16: consume_nvfp4(D, pay, t.n_units, t.dst_off, cwarp, lane); break;
-        case KK_OP_T8_F32_BF16: run_t8<4, 1>(D, L.src, t, sbase, ctid); break;
-        case KK_OP_T8_F16_BF16: run_t8<2, 2>(D, L.src, t, sbase, ctid); break;
-        case KK_OP_T8_B16: run_t8<2, 0>(D, L.src, t, sbase, ctid); break;
-        case KK_OP_TW_F32_BF16: run_tw<4, 1>(D, L.src, t, sbase, cwarp, lane, ctid); break;
-        case KK_OP_TW_F16_BF16: run_tw<2, 2>(D, L.src, t, sbase, cwarp, lane, ctid); break;
-        case KK_OP_TW_B16: run_tw<2, 0>(D, L.src, t, sbase, cwarp, lane, ctid); break;
         case KK_OP_F8E4M3_BF16: consume_f8<false>(D, pay, t.n_units, t.dst_off, ctid); break;
         case KK_OP_F8E5M2_BF16: consume_f8<true>(D, pay, t.n_units, t.dst_off, ctid); break;
-        case KK_OP_T_F32_BF16: consume_transpose<4, 2, 1>(D, L.src, t, sbase, ctid); break;
-        case KK_OP_T_F16_BF16: consume_transpose<2, 2, 2>(D, L.src, t, sbase, ctid); break;
-        case KK_OP_T_B16: consume_transpose<2, 2, 0>(D, L.src, t, sbase, ctid); break;
-        case KK_OP_T_B32: consume_transpose<4, 4, 0>(D, L.src, t, sbase, ctid); break;
+        case KK_OP_T_F32_BF16: run_t<4, 1>(D, L.src, t, sbase, ctid); break;
+        case KK_OP_T_F16_BF16: run_t<2, 2>(D, L.src, t, sbase, ctid); break;
+        case KK_OP_T_B16: run_t<2, 0>(D, L.src, t, sbase, ctid); break;
+        case KK_OP_T_B32: run_t<4, 3>(D, L.src, t, sbase, ctid); break;
         default: break;
       }
       __syncwarp();

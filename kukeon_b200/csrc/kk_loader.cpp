@@ -538,6 +538,7 @@ void pull_slices(kk_model* m, float* ms_total) {
   Device& dev = c->devs[(size_t)m->dev_idx[0]];
   const int n = m->opts.part_count, me = m->opts.part_index;
   std::vector<int> peers;
+  std::lock_guard<std::mutex> peer_lock(m->peer_mu);
   // Every rank owns a slice buffer (never smaller than 256 B) and every peer's must be attached before stage 2, whether or not the
   // planner gave that rank any bytes: a rank that skipped the exchange is a protocol error of the caller, and reporting success for it
   // only because its part happened to be empty (a checkpoint smaller than one staging chunk) would hide the same mistake at full size.
@@ -1013,10 +1014,15 @@ void model_export_slice(kk_model* m, void* handle_out, bool as_pointer) {
 }
 
 void model_peer_attach_slice(kk_model* m, int rank, const void* handle, bool is_ipc) {
-  std::lock_guard<std::mutex> op(m->op_mu);
+  // Not under op_mu: stage 1 of a PULL load (kk_load_part) writes only this rank's own pool and slice buffer, so the caller may map the
+  // peers' slice buffers on another thread while it runs.  The mapping itself happens outside peer_mu (it is the slow part; several
+  // ranks may be attached concurrently), only the table update is locked.
   if (!is_pull(m)) fail(KK_ESTATE, "slice attach needs a KK_FANOUT_PULL model");
   if (rank < 0 || rank >= m->opts.part_count || rank == m->opts.part_index) fail(KK_EINVAL, "bad peer rank %d", rank);
-  if (m->peer_slice_ptr[rank]) fail(KK_ESTATE, "peer rank %d already attached", rank);
+  {
+    std::lock_guard<std::mutex> g(m->peer_mu);
+    if (m->peer_slice_ptr[rank]) fail(KK_ESTATE, "peer rank %d already attached", rank);
+  }
   KK_CUDA(cudaSetDevice(m->ctx->devs[(size_t)m->dev_idx[0]].ordinal));
   void* p = nullptr;
   if (is_ipc) {
@@ -1027,8 +1033,55 @@ void model_peer_attach_slice(kk_model* m, int rank, const void* handle, bool is_
     memcpy(&p, handle, sizeof p);
     if (!p) fail(KK_EINVAL, "null device pointer");
   }
+  std::lock_guard<std::mutex> g(m->peer_mu);
+  if (m->peer_slice_ptr[rank]) {  // lost a race against another attach of the same rank
+    if (is_ipc) cudaIpcCloseMemHandle(p);
+    fail(KK_ESTATE, "peer rank %d already attached", rank);
+  }
   m->peer_slice_ptr[rank] = p;
   m->peer_slice_is_ipc[rank] = is_ipc;
+}
+
+// NVLink probe (measurement only): copy-engine read of `nbytes` from the attached buffer of rank `rank` (its pool, or its slice buffer
+// in a PULL load) into a local scratch, one untimed pass first, CUDA events on the device's stream.  Run by every rank at once against
+// its ring neighbour this is the per-GPU ingress rate the fan-out's roofline is quoted against — measured in the run, not assumed.
+void model_probe_peer(kk_model* m, int rank, int which, uint64_t& nbytes, float* ms) {
+  std::lock_guard<std::mutex> op(m->op_mu);
+  if (rank < 0 || rank >= KK_MAX_DEVICES) fail(KK_EINVAL, "bad peer rank %d", rank);
+  const uint8_t* src = nullptr;
+  uint64_t avail = 0;
+  if (which == KK_BUF_SLICE) {
+    std::lock_guard<std::mutex> g(m->peer_mu);
+    src = (const uint8_t*)m->peer_slice_ptr[rank];
+    if (src && (size_t)rank < m->part_range.size()) {
+      const auto& pr = m->part_range[(size_t)rank];
+      avail = pr.second > (pr.first & ~(uint64_t)255) ? pr.second - (pr.first & ~(uint64_t)255) : 0;
+    }
+  } else if (which == KK_BUF_POOL) {
+    src = (const uint8_t*)m->peer_ptr[rank];
+    avail = m->pool_bytes.empty() ? 0 : m->pool_bytes[0];
+  } else if (which == KK_BUF_RAW) {
+    src = (const uint8_t*)m->peer_raw_ptr[rank];
+    avail = m->raw.empty() ? 0 : m->raw[0].bytes;
+  } else {
+    fail(KK_EINVAL, "probe: buffer kind %d (KK_BUF_POOL, KK_BUF_RAW or KK_BUF_SLICE)", which);
+  }
+  if (!src) fail(KK_ESTATE, "probe: rank %d has no attached buffer of that kind", rank);
+  nbytes = std::min(nbytes, avail) & ~(uint64_t)255;
+  if (!nbytes) fail(KK_EINVAL, "probe: nothing to copy from rank %d", rank);
+  Device& dev = m->ctx->devs[(size_t)m->dev_idx[0]];
+  KK_CUDA(cudaSetDevice(dev.ordinal));
+  DevScratch tmp;
+  if (cudaMalloc(&tmp.p, nbytes) != cudaSuccess) { cudaGetLastError(); fail(KK_ENOMEM, "probe: cudaMalloc(%llu) failed", (unsigned long long)nbytes); }
+  EventSet ev(2);
+  ev.create_all();
+  KK_CUDA(cudaMemcpyAsync(tmp.p, src, nbytes, cudaMemcpyDeviceToDevice, dev.stream));
+  KK_CUDA(cudaEventRecord(ev[0], dev.stream));
+  KK_CUDA(cudaMemcpyAsync(tmp.p, src, nbytes, cudaMemcpyDeviceToDevice, dev.stream));
+  KK_CUDA(cudaEventRecord(ev[1], dev.stream));
+  KK_CUDA(cudaStreamSynchronize(dev.stream));
+  KK_CUDA(cudaEventElapsedTime(ms, ev[0], ev[1]));
+  if (*ms < 0.f) *ms = 0.f;
 }
 
 void model_release(kk_model* m) {
@@ -1066,6 +1119,7 @@ void model_peer_attach(kk_model* m, int rank, const void* handle, bool is_ipc) {
 
 void model_peer_detach_all(kk_model* m) {
   std::lock_guard<std::mutex> op(m->op_mu);  // the destination tables are read by a running load
+  std::lock_guard<std::mutex> pg(m->peer_mu);
   Device& d = m->ctx->devs[(size_t)m->dev_idx[0]];
   cudaSetDevice(d.ordinal);
   for (int r = 0; r < KK_MAX_DEVICES; ++r) {
@@ -1136,9 +1190,7 @@ std::string model_stats(kk_model* m) {
         case KK_OP_COPY: e = b + s.units; break;
         case KK_OP_F32_BF16: case KK_OP_F16_BF16: case KK_OP_F8E4M3_BF16: case KK_OP_F8E5M2_BF16: e = b + s.units * 2; break;
         case KK_OP_T_B32: e = b + (uint64_t)s.p0 * s.p1 * 4; break;
-        case KK_OP_T_F32_BF16: case KK_OP_T_F16_BF16: case KK_OP_T_B16:
-        case KK_OP_T8_F32_BF16: case KK_OP_T8_F16_BF16: case KK_OP_T8_B16:
-        case KK_OP_TW_F32_BF16: case KK_OP_TW_F16_BF16: case KK_OP_TW_B16: e = b + (uint64_t)s.p0 * s.p1 * 2; break;
+        case KK_OP_T_F32_BF16: case KK_OP_T_F16_BF16: case KK_OP_T_B16: e = b + (uint64_t)s.p0 * s.p1 * 2; break;
         default: e = b + s.units * kk_block_geom(s.op).out_bytes; break;  // block-dequantising ops
       }
       if (b < lo) lo = b;

@@ -110,6 +110,8 @@ struct kk_model {
   std::unique_ptr<kk::NvlsPools> nvls;
   // state
   std::mutex op_mu;  // serialises the data-moving calls on ONE model (kk_load_part, kk_convert_local, kk_*_resident) against each other
+  std::mutex peer_mu;  // guards peer_slice_ptr[]: stage 1 of a PULL load never reads it, so slice buffers may be attached WHILE kk_load_part runs
+                       // (cudaIpcOpenMemHandle is the expensive part of time-to-ready in the one-process-per-GPU shape); lock order op_mu -> peer_mu
   int refcount = 0;
   bool loading = true;
   bool loaded = false;
@@ -135,6 +137,7 @@ void model_export_raw(kk_model* m, int local, void* handle_out);
 void model_export_slice(kk_model* m, void* handle_out, bool as_pointer);
 void model_peer_attach_slice(kk_model* m, int rank, const void* handle, bool is_ipc);
 void model_convert_local(kk_model* m, float* ms_total);
+void model_probe_peer(kk_model* m, int rank, int which, uint64_t& nbytes, float* ms);
 void model_peer_detach_all(kk_model* m);
 int model_local_device(kk_model* m, int ordinal);  // index into m->dev_idx or throws
 std::string model_manifest(kk_model* m, int local);

@@ -8,10 +8,9 @@
 #define KK_STAGE_PAD 128u        /* slack so a 16-B-aligned superset of a misaligned tile still fits */
 #define KK_Q4K_BLOCK_BYTES 144u
 #define KK_Q4K_BLOCK_ELEMS 256u
-#ifndef KK_Q4K_TILE_BLOCKS        /* overridable for A/B builds: 16 consumer warps x 4 blocks = 64 blocks per sweep, so 224 = 3.5 sweeps (half the
-                                     warps idle in the last one) against 192 = 3 full sweeps of a smaller tile */
-#define KK_Q4K_TILE_BLOCKS 224u  /* 224*144 = 32256 B in, 224*512 = 114688 B out */
-#endif
+#define KK_Q4K_TILE_BLOCKS 224u  /* 224*144 = 32256 B in, 224*512 = 114688 B out.  16 consumer warps x 4 blocks = 64 blocks per sweep, so 3.5 sweeps; measured
+                                    against 192-block tiles (3 full sweeps), contiguous 14-block runs per warp, a rotated warp order and 20 warps
+                                    (profiles/r02/q4k_ab_*.json): all within 2 % and none faster, so the simplest form stays */
 #define KK_Q8_0_BLOCK_BYTES 34u
 #define KK_Q8_0_BLOCK_ELEMS 32u
 #define KK_Q8_0_TILE_BLOCKS 960u /* 960*34 = 32640 B in (a multiple of 16), 960*64 = 61440 B out */
@@ -60,22 +59,12 @@
 #define KK_TQ2_0_TILE_BLOCKS 496u /* 32736 B in */
 #define KK_NVFP4_BLOCK_BYTES 36u
 #define KK_NVFP4_TILE_BLOCKS 908u /* 32688 B in */
-#define KK_T_ROWS 32u            /* transpose tile: 32 source rows ... */
-#define KK_T_COLS 128u           /* ... x 128 source columns (elements) */
-#define KK_T_PITCH_PAD 16u       /* TMA-staged transpose rows sit KK_T_COLS*es + 16 bytes apart (bank spread) */
-/* Candidate transpose geometry (KK_LOAD_T8_TILES): 8 source rows x (KK_T8_ROW_BYTES / es) columns.  Eight bulk copies bring in a full
- * 32 KiB stage (ONE when the tile spans whole rows, which are then contiguous in the source); consumers read along rows — conflict-free
- * at any pitch — and every thread packs the 8 rows of one column into a single 16-byte store. */
-#define KK_T8_ROWS 8u
-#define KK_T8_ROW_BYTES 4096u    /* per staged row: 1024 f32 or 2048 16-bit columns */
-/* Second candidate (KK_LOAD_TW_TILES): 32 source rows x (KK_TW_ROW_BYTES / es) columns, rows KK_TW_PITCH bytes apart in the stage.
- * Costs 32 bulk copies per 30 KiB (half of what the 32x128 tiles need per byte, 4x what the 8-row tiles need) but every column of a
- * tile is 64 contiguous destination bytes: a warp = 8 columns x 4 row groups stores 8 full 64-byte segments per instruction instead of
- * 32 scattered 16-byte ones.  Pitch 976 B = 244 words: with lane (cc, rg) reading row 8*rg + ((k + 2*rg) & 7) at step k the bank is
- * (20*k + 8*rg + cc) mod 32 — all 32 lanes distinct. */
-#define KK_TW_ROWS 32u
-#define KK_TW_ROW_BYTES 960u
-#define KK_TW_PITCH 976u
+/* 2-D transposes (GPT-2 Conv1D): a tile is 8 source rows x up to KK_T_ROW_BYTES of each.  Eight bulk copies bring in a full 32 KiB stage (ONE when the
+ * tile spans whole rows, which are then contiguous in the source); consumers read along rows — conflict-free at any pitch — and every thread packs
+ * the 8 rows of one column into a single 16-byte store.  Measured on GPT-2-small against 32x128 tiles (0.36 of the copy peak) and 32-row x 960-byte
+ * wide-store tiles (0.58): 0.80 (profiles/r02/t8_ab_*.json) — the other two geometries are gone. */
+#define KK_T_ROWS 8u
+#define KK_T_ROW_BYTES 4096u     /* per staged row: 1024 32-bit or 2048 16-bit columns */
 #define KK_MAX_DST 8
 /* ConvertLaunch::flags */
 #define KK_LAUNCH_NO_BULK_STORE 0x1u  /* force the register path for aligned copies (A/B measurement) */
@@ -86,13 +75,13 @@ enum KKOp : uint32_t {
   KK_OP_F32_BF16 = 1,  // units = elements
   KK_OP_F16_BF16 = 2,  // units = elements
   KK_OP_Q4K_BF16 = 3,  // units = 256-weight blocks
-  // 2-D transposes: units = source rows in this segment, p0 = source columns (elements),
+  // 2-D transposes on 8-row tiles: units = source rows in this segment, p0 = source columns (elements),
   // p1 = destination row length in elements (= total source rows of the tensor),
   // p2 = index of this segment's first source row (destination column offset).
   KK_OP_T_F32_BF16 = 4,
   KK_OP_T_F16_BF16 = 5,
   KK_OP_T_B16 = 6,     // 2-byte elements moved verbatim (bf16, i16, ...)
-  KK_OP_T_B32 = 7,     // 4-byte elements moved verbatim
+  KK_OP_T_B32 = 7,     // 4-byte elements moved verbatim (F32 under KK_LOAD_KEEP_F32, i32, ...)
   KK_OP_Q8_0_BF16 = 8, // units = 32-weight blocks (34 B: d f16 | 32 x int8)
   KK_OP_Q6K_BF16 = 9,  // units = 256-weight super-blocks (210 B: ql[128] | qh[64] | scales[16] int8 | d f16)
   // SCATTER exchange: units = bytes of whole source rows; every row is cut into N column slices of p1 bytes and slice j
@@ -112,19 +101,11 @@ enum KKOp : uint32_t {
   // units = elements (1 byte each): FP8 widened to bf16 (KK_LOAD_F8_TO_BF16)
   KK_OP_F8E4M3_BF16 = 18,
   KK_OP_F8E5M2_BF16 = 19,
-  // 2-D transposes on 8-row tiles (same units / p0 / p1 / p2 as KK_OP_T_*); chosen by the planner under KK_LOAD_T8_TILES when the
-  // destination row length (p1) is a multiple of 8, so that every 8-row group of a column is one aligned 16-byte store
-  KK_OP_T8_F32_BF16 = 20,
-  KK_OP_T8_F16_BF16 = 21,
-  KK_OP_T8_B16 = 22,
+  // 20..22 and 26..28 were the two candidate transpose geometries of round 1 (retired after the round-2 A/B; numbers not reused)
   // codebook 4-bit types: IQ4_NL (18 B: d f16 | qs[16]), IQ4_XS (136 B: d | scales_h u16 | scales_l[4] | qs[128]), MXFP4 (17 B: E8M0 | qs[16])
   KK_OP_IQ4NL_BF16 = 23,
   KK_OP_IQ4XS_BF16 = 24,
   KK_OP_MXFP4_BF16 = 25,
-  // 2-D transposes on 32-row wide-store tiles (KK_LOAD_TW_TILES); units / p0 / p1 / p2 as KK_OP_T_*
-  KK_OP_TW_F32_BF16 = 26,
-  KK_OP_TW_F16_BF16 = 27,
-  KK_OP_TW_B16 = 28,
   // lattice i-quants (256-weight super-blocks; 8 weights = one grid entry of kk_iq_grids.h, or two 4-value entries for IQ3), the ternary
   // types, and NVFP4 (64-weight blocks: 4 UE4M3 scales | 32 nibble bytes)
   KK_OP_IQ2XXS_BF16 = 29,
@@ -163,23 +144,18 @@ static_assert(sizeof(KKSeg) == 48, "KKSeg layout is shared with the device");
 struct KKBlockGeom {
   uint32_t block_bytes, out_bytes, tile_blocks;
 };
-/* Columns per 8-row tile of a tensor with C source columns.  Default: as many as a staged row holds (1024 f32 / 2048 16-bit), so a row of
- * 2304 columns is cut 1024 + 1024 + 256 and every third tile of it is a quarter full.  -DKK_T8_BALANCED=1 (A/B build) cuts it into the same
- * number of EQUAL pieces (768 + 768 + 768), rounded up to 8 columns so that row pieces stay whole 16-byte units for either element size. */
-#ifndef KK_T8_BALANCED
-#define KK_T8_BALANCED 0
-#endif
-static inline KK_HD uint32_t kk_t8_width(uint32_t op, uint32_t C) {
-  const uint32_t wmax = KK_T8_ROW_BYTES / (op == KK_OP_T8_F32_BF16 ? 4u : 2u);
-#if KK_T8_BALANCED
+static inline KK_HD bool kk_is_transpose(uint32_t op) { return op >= KK_OP_T_F32_BF16 && op <= KK_OP_T_B32; }
+static inline KK_HD uint32_t kk_t_src_es(uint32_t op) { return (op == KK_OP_T_F32_BF16 || op == KK_OP_T_B32) ? 4u : 2u; }
+/* Columns per 8-row tile of a tensor with C source columns: at most what a staged row holds (1024 32-bit / 2048 16-bit), and rows wider than that
+ * are cut into EQUAL pieces (2304 columns -> 768 + 768 + 768, not 1024 + 1024 + 256: with a fixed width every third tile of GPT-2's c_attn would be a
+ * quarter full and still cost a pipeline slot), rounded up to 8 columns so that row pieces stay whole 16-byte units for either element size. */
+static inline KK_HD uint32_t kk_t_width(uint32_t op, uint32_t C) {
+  const uint32_t wmax = KK_T_ROW_BYTES / kk_t_src_es(op);
   if (C > wmax) {
     const uint32_t n = (C + wmax - 1u) / wmax;
     const uint32_t w = ((C + n - 1u) / n + 7u) & ~7u;
     return w < wmax ? w : wmax;
   }
-#else
-  (void)C;
-#endif
   return wmax;
 }
 
@@ -282,23 +258,11 @@ static inline KK_HD uint64_t kk_seg_tiles(uint32_t op, uint64_t units, uint32_t 
     case KK_OP_T_B32:
     case KK_OP_T_F16_BF16:
     case KK_OP_T_B16: {
-      uint64_t ct = ((uint64_t)p0 + KK_T_COLS - 1) / KK_T_COLS;
-      return ((units + KK_T_ROWS - 1) / KK_T_ROWS) * ct;
-    }
-    case KK_OP_T8_F32_BF16:
-    case KK_OP_T8_F16_BF16:
-    case KK_OP_T8_B16: {
-      const uint64_t w = kk_t8_width(op, p0);
-      return ((units + KK_T8_ROWS - 1) / KK_T8_ROWS) * (((uint64_t)p0 + w - 1) / w);
-    }
-    case KK_OP_TW_F32_BF16:
-    case KK_OP_TW_F16_BF16:
-    case KK_OP_TW_B16: {
-      const uint64_t w = KK_TW_ROW_BYTES / (op == KK_OP_TW_F32_BF16 ? 4u : 2u);
-      return ((units + KK_TW_ROWS - 1) / KK_TW_ROWS) * (((uint64_t)p0 + w - 1) / w);
+      const uint64_t w = kk_t_width(op, p0);
+      return ((units + KK_T_ROWS - 1) / KK_T_ROWS) * (((uint64_t)p0 + w - 1) / w);
     }
     default: return 0;
   }
 }
-static_assert(KK_TW_ROWS * KK_TW_PITCH <= KK_TILE_SRC_BYTES + KK_STAGE_PAD && KK_TW_PITCH % 16u == 0 && KK_TW_ROW_BYTES <= KK_TW_PITCH, "TW tile fits a stage");
+static_assert(KK_T_ROWS * KK_T_ROW_BYTES <= KK_TILE_SRC_BYTES, "a transpose tile fits a stage");
 #endif

@@ -311,11 +311,6 @@ Plan build_plan(Index index, int mode, uint32_t flags, int n_parts, uint64_t chu
         else if (t.dtype == KK_F16) { op = KK_OP_T_F16_BF16; pdt = KK_BF16; es = 2; oes = 2; }
         else if (t.dtype == KK_F32 || t.dtype == KK_I32 || t.dtype == KK_U32) { op = KK_OP_T_B32; pdt = t.dtype; es = 4; oes = 4; }
         else { op = KK_OP_T_B16; pdt = t.dtype; es = 2; oes = 2; }
-        // candidate 8-row tiles: only when every 8-row group of a destination row is an aligned 16-byte store
-        if ((flags & KK_LOAD_TW_TILES) && R % 8 == 0 && oes == 2)
-          op = op == KK_OP_T_F32_BF16 ? KK_OP_TW_F32_BF16 : op == KK_OP_T_F16_BF16 ? KK_OP_TW_F16_BF16 : KK_OP_TW_B16;
-        else if ((flags & KK_LOAD_T8_TILES) && R % 8 == 0 && oes == 2)
-          op = op == KK_OP_T_F32_BF16 ? KK_OP_T8_F32_BF16 : op == KK_OP_T_F16_BF16 ? KK_OP_T8_F16_BF16 : KK_OP_T8_B16;
         pc.oi = {op, pdt, es, oes, KK_T_ROWS};
         pc.transpose = true;
         pc.row_src_bytes = C * es;

@@ -1,8 +1,7 @@
-// Per-tile work description of kk_convert_kernel, as ONE function the device and the host can both run: which bytes a tile pulls into its
+// Per-tile work description of kk_convert_kernel, as ONE function the device and the host both run: which bytes a tile pulls into its
 // stage (one bulk copy of a 16-byte aligned superset, or one bulk copy per source row for the transposes) and the descriptor the consumer
-// warps act on.  tests/emul replays whole launches through it (kk_emul_launch) — planner output in, pool bytes out, device source in
-// between.  The kernel's producer warp calls it when built with -DKK_PRODUCER_SHARED=1; the default build still carries the in-line switch
-// this was transcribed from (round-1 verified on hardware), until the shared form has had its own GPU run.
+// warps act on.  The kernel's producer warp calls it for every tile, and tests/emul replays whole launches through the same function
+// (kk_emul_launch) — planner output in, pool bytes out, device source in between — so the CPU tier and the GPU run one transcription.
 #pragma once
 #include "kk_ops.h"
 
@@ -10,8 +9,8 @@ struct alignas(16) KKTileDesc {
   uint32_t op;
   uint32_t pay_off;  // payload offset inside the stage buffer (0..15 for TMA tiles)
   uint32_t n_units;  // units in this tile (bytes / elements / blocks); transposes: rows | cols<<16
-  uint32_t bulk;     // 1: aligned copy, bulk-store from shared memory; 2: 32x128 transpose tile staged row by row; 3: row-split exchange;
-                     // 4: 8-row transpose tile staged, rows nc*es bytes apart; 5: 32-row wide-store tile, rows KK_TW_PITCH apart
+  uint32_t bulk;     // 1: aligned copy, bulk-store from shared memory; 3: row-split exchange; 4: transpose tile staged by bulk copies, rows nc*es bytes apart
+                     // (0 for a transpose tile = not staged: the consumers gather it themselves)
   uint64_t dst_off;  // pool byte offset of the tile's first output (transposes: dst tensor origin)
   uint64_t src_off;  // transposes: byte offset of source element (r0, c0) from the launch's src base
   uint32_t C;        // transposes: source columns
@@ -39,9 +38,7 @@ static inline KK_HD void kk_make_tile(const KKSeg& seg, uint32_t t, uint64_t src
   ld.kind = 0; ld.tx = 0; ld.g_off = 0; ld.nrows = 0; ld.row_bytes = 0; ld.spitch = 0; ld.pad_ = 0; ld.gpitch = 0;
   uint32_t in_bytes = 0;  // source bytes of this tile (single-copy ops)
   uint64_t in_off = 0;    // their offset from the src base
-  // transposes: rows x columns window, staged row by row when every row is a whole number of aligned 16-byte units
-  uint32_t t_rows = 0, t_row_bytes = 0, t_spitch = 0, t_bulk = 0, t_es = 0;
-  bool t_compact = false;  // 8-row tiles: stage pitch = the tile's own row bytes; whole-row tiles are one copy
+  uint32_t t_es = 0;  // transposes: source element size
   switch (seg.op) {
     case KK_OP_COPY:
     case KK_OP_ROWSPLIT: {
@@ -82,12 +79,7 @@ static inline KK_HD void kk_make_tile(const KKSeg& seg, uint32_t t, uint64_t src
       in_bytes = d.n_units * 2; in_off = seg.src_off + e * 2; d.dst_off = seg.dst_off + e * 2;
       break;
     }
-    case KK_OP_T_F32_BF16: case KK_OP_T_B32: t_es = 4; t_rows = KK_T_ROWS; t_row_bytes = KK_T_COLS * 4u; t_spitch = KK_T_COLS * 4u + KK_T_PITCH_PAD; t_bulk = 2; break;
-    case KK_OP_T_F16_BF16: case KK_OP_T_B16: t_es = 2; t_rows = KK_T_ROWS; t_row_bytes = KK_T_COLS * 2u; t_spitch = KK_T_COLS * 2u + KK_T_PITCH_PAD; t_bulk = 2; break;
-    case KK_OP_T8_F32_BF16: t_es = 4; t_rows = KK_T8_ROWS; t_row_bytes = kk_t8_width(seg.op, seg.p0) * 4u; t_compact = true; t_bulk = 4; break;
-    case KK_OP_T8_F16_BF16: case KK_OP_T8_B16: t_es = 2; t_rows = KK_T8_ROWS; t_row_bytes = kk_t8_width(seg.op, seg.p0) * 2u; t_compact = true; t_bulk = 4; break;
-    case KK_OP_TW_F32_BF16: t_es = 4; t_rows = KK_TW_ROWS; t_row_bytes = KK_TW_ROW_BYTES; t_spitch = KK_TW_PITCH; t_bulk = 5; break;
-    case KK_OP_TW_F16_BF16: case KK_OP_TW_B16: t_es = 2; t_rows = KK_TW_ROWS; t_row_bytes = KK_TW_ROW_BYTES; t_spitch = KK_TW_PITCH; t_bulk = 5; break;
+    case KK_OP_T_F32_BF16: case KK_OP_T_B32: case KK_OP_T_F16_BF16: case KK_OP_T_B16: t_es = kk_t_src_es(seg.op); break;
     default: {  // block-dequantising ops
       const KKBlockGeom g = kk_block_geom(seg.op);
       if (g.block_bytes) {
@@ -99,14 +91,14 @@ static inline KK_HD void kk_make_tile(const KKSeg& seg, uint32_t t, uint64_t src
       break;
     }
   }
-  if (t_bulk) {
-    const uint32_t C = seg.p0, W = t_row_bytes / t_es;
+  if (t_es) {  // rows x columns window of the source matrix, staged row by row when every row piece is a whole number of aligned 16-byte units
+    const uint32_t C = seg.p0, W = kk_t_width(seg.op, C);
     const uint32_t ct = (C + W - 1) / W;
     const uint32_t tr = t / ct, tc = t % ct;
-    const uint64_t r0 = (uint64_t)tr * t_rows;
+    const uint64_t r0 = (uint64_t)tr * KK_T_ROWS;
     const uint32_t c0 = tc * W;
     const uint64_t rrem = seg.units - r0;
-    const uint32_t nr = rrem < t_rows ? (uint32_t)rrem : t_rows;
+    const uint32_t nr = rrem < KK_T_ROWS ? (uint32_t)rrem : KK_T_ROWS;
     const uint32_t nc = (C - c0) < W ? (C - c0) : W;
     d.n_units = nr | (nc << 16);
     d.C = C; d.R = seg.p1; d.col0 = c0; d.row0 = seg.p2 + (uint32_t)r0;
@@ -115,14 +107,14 @@ static inline KK_HD void kk_make_tile(const KKSeg& seg, uint32_t t, uint64_t src
     const uint64_t row_pitch = (uint64_t)C * t_es;
     const uint32_t rb = nc * t_es;
     if (((src_addr + d.src_off) & 15u) == 0 && (row_pitch & 15u) == 0 && (rb & 15u) == 0) {
-      d.bulk = t_bulk;
+      d.bulk = 4;
       ld.tx = nr * rb;
       ld.g_off = d.src_off;
-      if (t_compact && nc == C) {  // the tile spans whole rows: they are contiguous in the source, one bulk copy brings all of them
+      if (nc == C) {  // the tile spans whole rows: they are contiguous in the source, one bulk copy brings all of them
         ld.kind = 1;
       } else {
         ld.kind = 2;
-        ld.nrows = nr; ld.row_bytes = rb; ld.spitch = t_compact ? rb : t_spitch; ld.gpitch = row_pitch;
+        ld.nrows = nr; ld.row_bytes = rb; ld.spitch = rb; ld.gpitch = row_pitch;
       }
     }
     return;  // not staged: descriptor only, the consumers gather the tile themselves

@@ -23,7 +23,7 @@ KK_POOL_ALIGN = 256
 MODE_SINGLE, MODE_BROADCAST, MODE_SCATTER = 0, 1, 2
 FANOUT_P2P, FANOUT_NVLS, FANOUT_NONE, FANOUT_RAW, FANOUT_PULL = 0, 1, 2, 3, 4
 CFG_ZEROCOPY, CFG_NO_PEER_ACCESS, CFG_NO_NUMA_PIN, CFG_PEER_ALL = 0x1, 0x2, 0x4, 0x8
-LOAD_GPT2_CONV1D_T, LOAD_KEEP_F32, LOAD_DEFER, LOAD_SCATTER_EXCHANGE, LOAD_F8_TO_BF16, LOAD_T8_TILES, LOAD_TW_TILES = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20, 0x40
+LOAD_GPT2_CONV1D_T, LOAD_KEEP_F32, LOAD_DEFER, LOAD_SCATTER_EXCHANGE, LOAD_F8_TO_BF16 = 0x1, 0x2, 0x4, 0x8, 0x10
 BUF_POOL, BUF_RAW, BUF_POOL_PTR, BUF_SLICE, BUF_SLICE_PTR = 0, 1, 2, 3, 4
 PROBE_WRITE, PROBE_COPY = 0, 1
 
@@ -103,7 +103,7 @@ ABI_SYMBOLS = [
     "kk_export_buffer", "kk_peer_attach_buffer", "kk_convert_local",
     "kk_model_get_info", "kk_placements", "kk_model_tensor", "kk_export", "kk_export_size", "kk_pool_ptr",
     "kk_acquire", "kk_release", "kk_stats", "kk_read", "kk_checksum", "kk_stage_resident", "kk_convert_resident",
-    "kk_unstage_resident", "kk_probe_hbm",
+    "kk_unstage_resident", "kk_probe_hbm", "kk_probe_peer",
 ]
 
 
@@ -130,6 +130,7 @@ def lib():
     L.kk_open.argtypes = [C.POINTER(KKConfig), C.POINTER(vp)]
     L.kk_close.argtypes = [vp]
     L.kk_probe_hbm.argtypes = [vp, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_float)]
+    L.kk_probe_peer.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_float)]
     L.kk_index.argtypes = [vp, C.c_char_p, C.POINTER(C.POINTER(KKTensorMeta)), C.POINTER(C.c_size_t)]
     L.kk_free_index.argtypes = [C.POINTER(KKTensorMeta)]
     L.kk_index_shard.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
@@ -315,6 +316,13 @@ class Model:
         ms = C.c_float()
         _check(lib().kk_convert_local(self._h, C.byref(ms)))
         return float(ms.value)
+
+    def probe_peer(self, rank: int, which: int = BUF_POOL, nbytes: int = 1 << 30) -> float:
+        """GB/s of one copy-engine read of up to `nbytes` from the attached buffer of rank `rank` (NVLink ingress probe)."""
+        n = C.c_uint64(nbytes)
+        ms = C.c_float()
+        _check(lib().kk_probe_peer(self._h, rank, which, C.byref(n), C.byref(ms)))
+        return n.value / (ms.value / 1e3) / 1e9 if ms.value > 0 else 0.0
 
     def peer_detach_all(self) -> None:
         _check(lib().kk_peer_detach_all(self._h))

@@ -560,7 +560,7 @@ int orc_cpu_load(const char* const* shard_paths, uint32_t n_shards, const orc_jo
 #pragma omp parallel
     {
       uint8_t* scratch = (uint8_t*)malloc(scratch_bytes ? scratch_bytes : 1);
-#pragma omp for schedule(dynamic, 1)
+#pragma omp for schedule(static, 1) /* job j always runs on thread j mod T: the pages a thread first-touches are the pages it rewrites in every later pass */
       for (uint64_t j = 0; j < n_jobs; ++j) {
         const orc_job* J = &jobs[j];
         if (J->nbytes > scratch_bytes && J->op != ORC_COPY) { err = -1; continue; }

@@ -178,6 +178,15 @@ inline void store2_all(const Dsts&, uint64_t off, uint16_t v) {
   memcpy(g.out + off, &v, 2);
   for (int i = 0; i < g.n_more; ++i) memcpy(g.more_out[i] + off, &v, 2);
 }
+inline void store4_all(const Dsts&, uint64_t off, uint32_t v) {  // one 32-bit element (verbatim transposes): two entries of the 2-byte mask
+  if (g.shfl_mode == 1) return;
+  if ((off & 3u) || off + 4 > g.out_bytes) { flag(3); return; }
+  if (g.out_mask[off >> 1] || g.out_mask[(off >> 1) + 1]) flag(4);
+  g.out_mask[off >> 1] = g.out_mask[(off >> 1) + 1] = 1;
+  g.hits[off >> 4] += 4;
+  memcpy(g.out + off, &v, 4);
+  for (int i = 0; i < g.n_more; ++i) memcpy(g.more_out[i] + off, &v, 4);
+}
 inline uint4 lds128(uint32_t a) {
   uint4 v{0, 0, 0, 0};
   if (a & 15u) { flag(2); return v; }
@@ -201,10 +210,7 @@ inline uint32_t f8_to_f16_bits(uint32_t b, bool e5m2) {
 template <bool E5M2>
 inline uint32_t kk_f8x2_to_f16x2(uint32_t v) { return f8_to_f16_bits(v, E5M2) | (f8_to_f16_bits(v >> 8, E5M2) << 16); }
 
-#ifndef KK_CONSUMER_WARPS
-#define KK_CONSUMER_WARPS 16
-#endif
-constexpr int kConsumerWarps = KK_CONSUMER_WARPS;  // must equal KK_CONSUMER_WARPS of the kernel build (the cw20 A/B variant has its own emulator library)
+constexpr int kConsumerWarps = 16;  // must equal kConsumerWarps of kk_kernels.cu
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 #define KK_DQ_DEV static inline
 #define min(a, b) ((a) < (b) ? (a) : (b))
@@ -376,24 +382,21 @@ extern "C" int kk_emul_dequant_segment(uint32_t op, const uint8_t* src, uint64_t
   return 0;
 }
 
-// One transpose tile of the candidate geometries (KK_OP_T8_*: 8 rows, compact rows; KK_OP_TW_*: 32 rows, KK_TW_PITCH apart) the way the
+// One transpose tile (KK_OP_T_*: 8 rows, compact rows) the way the
 // kernel runs it.  `src` points at source element (r0, c0) of a row-major [*, C] tensor of ES-byte elements; staged != 0 lays the tile out
 // as the producer's bulk copies do, staged == 0 runs the consumers' gather fallback first.  `dst` is the destination tensor's origin
-// ([C_total, R] row-major, 2-byte elements), dst_bytes its size; hits as in kk_emul_dequant_tile over dst.
+// ([C_total, R] row-major, 2-byte elements — 4-byte for KK_OP_T_B32), dst_bytes its size; hits as in kk_emul_dequant_tile over dst.
 // stats: [0] shared-memory wavefronts the consumers' loads need (one per distinct 4-byte word per bank per warp instruction), [1] the
 // ideal (one per warp load), [2] warp-level 16-byte store instructions, [3] distinct 128-byte lines and [4] distinct 32-byte sectors those
 // touch, summed over instructions (what the LSU / L2 see as transactions).
-extern "C" int kk_emul_t8_tile(uint32_t op, const uint8_t* src, uint32_t C, uint32_t nr, uint32_t nc, uint32_t R, uint32_t col0, uint32_t row0,
-                               int staged, uint8_t* dst, uint64_t dst_bytes, uint8_t* hits, uint64_t* stats) {
-  const bool t8 = op == KK_OP_T8_F32_BF16 || op == KK_OP_T8_F16_BF16 || op == KK_OP_T8_B16;
-  const bool tw = op == KK_OP_TW_F32_BF16 || op == KK_OP_TW_F16_BF16 || op == KK_OP_TW_B16;
-  if (!t8 && !tw) return -1;
-  const uint32_t es = (op == KK_OP_T8_F32_BF16 || op == KK_OP_TW_F32_BF16) ? 4u : 2u;
-  if (t8 && (nr > KK_T8_ROWS || nc * es > KK_T8_ROW_BYTES)) return 5;
-  if (tw && (nr > KK_TW_ROWS || nc * es > KK_TW_ROW_BYTES)) return 5;
+extern "C" int kk_emul_t_tile(uint32_t op, const uint8_t* src, uint32_t C, uint32_t nr, uint32_t nc, uint32_t R, uint32_t col0, uint32_t row0,
+                              int staged, uint8_t* dst, uint64_t dst_bytes, uint8_t* hits, uint64_t* stats) {
+  if (!kk_is_transpose(op)) return -1;
+  const uint32_t es = kk_t_src_es(op);
+  if (nr > KK_T_ROWS || nc * es > KK_T_ROW_BYTES) return 5;
   static thread_local uint8_t stage[KK_TILE_SRC_BYTES + KK_STAGE_PAD];
   memset(stage, 0xEE, sizeof stage);
-  uint32_t pitch = tw ? KK_TW_PITCH : nc * es;
+  uint32_t pitch = nc * es;
   std::vector<uint8_t> mask(dst_bytes / 2 + 1, 0), bmask(dst_bytes + 1, 0);
   memset(hits, 0, (dst_bytes + 15) / 16);
   g = Emu{};
@@ -404,10 +407,10 @@ extern "C" int kk_emul_t8_tile(uint32_t op, const uint8_t* src, uint32_t C, uint
   if (staged) {
     for (uint32_t r = 0; r < nr; ++r) memcpy(stage + r * pitch, src + (uint64_t)r * C * es, (size_t)nc * es);
   } else {
-    if (t8) pitch = (pitch + 3u) & ~3u;
+    pitch = (pitch + 3u) & ~3u;
     for (int t = 0; t < nthreads; ++t) {
-      if (es == 4) t8_gather<4>(src, 0, pitch, nr, nc, C, t);
-      else t8_gather<2>(src, 0, pitch, nr, nc, C, t);
+      if (es == 4) t_gather<4>(src, 0, pitch, nr, nc, C, t);
+      else t_gather<2>(src, 0, pitch, nr, nc, C, t);
     }
     // (the kernel has a named barrier here)
   }
@@ -416,14 +419,11 @@ extern "C" int kk_emul_t8_tile(uint32_t op, const uint8_t* src, uint32_t C, uint
   for (int t = 0; t < nthreads; ++t) {
     g.trace = &traces[(size_t)t];
     g.strace = &straces[(size_t)t];
-    const int cwarp = t >> 5, lane = t & 31;
     switch (op) {
-      case KK_OP_T8_F32_BF16: consume_t8<4, 1>(D, 0, pitch, nr, nc, R, col0, row0, 0, t); break;
-      case KK_OP_T8_F16_BF16: consume_t8<2, 2>(D, 0, pitch, nr, nc, R, col0, row0, 0, t); break;
-      case KK_OP_T8_B16: consume_t8<2, 0>(D, 0, pitch, nr, nc, R, col0, row0, 0, t); break;
-      case KK_OP_TW_F32_BF16: consume_tw<4, 1>(D, 0, pitch, nr, nc, R, col0, row0, 0, cwarp, lane); break;
-      case KK_OP_TW_F16_BF16: consume_tw<2, 2>(D, 0, pitch, nr, nc, R, col0, row0, 0, cwarp, lane); break;
-      default: consume_tw<2, 0>(D, 0, pitch, nr, nc, R, col0, row0, 0, cwarp, lane); break;
+      case KK_OP_T_F32_BF16: consume_t<4, 1>(D, 0, pitch, nr, nc, R, col0, row0, 0, t); break;
+      case KK_OP_T_F16_BF16: consume_t<2, 2>(D, 0, pitch, nr, nc, R, col0, row0, 0, t); break;
+      case KK_OP_T_B16: consume_t<2, 0>(D, 0, pitch, nr, nc, R, col0, row0, 0, t); break;
+      default: consume_t<4, 3>(D, 0, pitch, nr, nc, R, col0, row0, 0, t); break;
     }
   }
   g.trace = nullptr;
@@ -475,8 +475,7 @@ extern "C" int kk_emul_t8_tile(uint32_t op, const uint8_t* src, uint32_t C, uint
 // hardware's constraints checked (16-byte aligned source, destination and size; bytes issued == bytes announced), then the consumer side: the
 // aligned-copy bulk stores, or the same per-lane device functions the other entry points run, for all 16 x 32 consumer lanes.
 // src: the staged chunk (src base assumed 256-byte aligned like the staging buffers); dst[0..n_dst): destination pools of pool_bytes each;
-// hits / masks describe dst[0] and ACCUMULATE across calls (the caller zeroes them once per pool).  Not covered: the 32x128 transposes and the
-// scatter row exchange (return -2).
+// hits / masks describe dst[0] and ACCUMULATE across calls (the caller zeroes them once per pool).  Not covered: the scatter row exchange (return -2).
 extern "C" int kk_emul_launch(const uint8_t* src, uint64_t src_bytes, const KKSeg* segs, uint32_t n_segs, uint32_t n_tiles, uint32_t flags,
                               uint8_t* const* dst, uint32_t n_dst, uint64_t pool_bytes, uint8_t* hits, uint8_t* mask2, uint8_t* mask1) {
   if (n_dst < 1 || n_dst > KK_MAX_DST) return -1;
@@ -531,30 +530,24 @@ extern "C" int kk_emul_launch(const uint8_t* src, uint64_t src_bytes, const KKSe
     }
     if (d.bulk == 3 || d.op == KK_OP_ROWSPLIT) return -2;
     switch (d.op) {
-      case KK_OP_T_F32_BF16: case KK_OP_T_F16_BF16: case KK_OP_T_B16: case KK_OP_T_B32: return -2;
-      case KK_OP_T8_F32_BF16: case KK_OP_T8_F16_BF16: case KK_OP_T8_B16:
-      case KK_OP_TW_F32_BF16: case KK_OP_TW_F16_BF16: case KK_OP_TW_B16: {
-        const bool tw = d.op >= KK_OP_TW_F32_BF16;
-        const uint32_t es = (d.op == KK_OP_T8_F32_BF16 || d.op == KK_OP_TW_F32_BF16) ? 4u : 2u;
-        uint32_t pitch = tw ? KK_TW_PITCH : nc * es;
-        if (d.bulk != (tw ? 5u : 4u)) {  // run_t8 / run_tw of the kernel: gather, (barrier), consume
-          if (!tw) pitch = (pitch + 3u) & ~3u;
+      case KK_OP_T_F32_BF16: case KK_OP_T_F16_BF16: case KK_OP_T_B16: case KK_OP_T_B32: {
+        const uint32_t es = kk_t_src_es(d.op);
+        uint32_t pitch = nc * es;
+        if (d.bulk != 4u) {  // run_t of the kernel: gather, (barrier), consume
+          pitch = (pitch + 3u) & ~3u;
           g.tile_bytes = (uint32_t)sizeof stage;
           if (d.src_off + ((uint64_t)(nr ? nr - 1 : 0) * d.C + nc) * es > src_bytes) return 11;
           for (int t = 0; t < kConsumerThreads; ++t) {
-            if (es == 4) t8_gather<4>(src + d.src_off, 0, pitch, nr, nc, d.C, t);
-            else t8_gather<2>(src + d.src_off, 0, pitch, nr, nc, d.C, t);
+            if (es == 4) t_gather<4>(src + d.src_off, 0, pitch, nr, nc, d.C, t);
+            else t_gather<2>(src + d.src_off, 0, pitch, nr, nc, d.C, t);
           }
         }
         for (int t = 0; t < kConsumerThreads; ++t) {
-          const int cw = t >> 5, ln = t & 31;
           switch (d.op) {
-            case KK_OP_T8_F32_BF16: consume_t8<4, 1>(D, 0, pitch, nr, nc, d.R, d.col0, d.row0, d.dst_off, t); break;
-            case KK_OP_T8_F16_BF16: consume_t8<2, 2>(D, 0, pitch, nr, nc, d.R, d.col0, d.row0, d.dst_off, t); break;
-            case KK_OP_T8_B16: consume_t8<2, 0>(D, 0, pitch, nr, nc, d.R, d.col0, d.row0, d.dst_off, t); break;
-            case KK_OP_TW_F32_BF16: consume_tw<4, 1>(D, 0, pitch, nr, nc, d.R, d.col0, d.row0, d.dst_off, cw, ln); break;
-            case KK_OP_TW_F16_BF16: consume_tw<2, 2>(D, 0, pitch, nr, nc, d.R, d.col0, d.row0, d.dst_off, cw, ln); break;
-            default: consume_tw<2, 0>(D, 0, pitch, nr, nc, d.R, d.col0, d.row0, d.dst_off, cw, ln); break;
+            case KK_OP_T_F32_BF16: consume_t<4, 1>(D, 0, pitch, nr, nc, d.R, d.col0, d.row0, d.dst_off, t); break;
+            case KK_OP_T_F16_BF16: consume_t<2, 2>(D, 0, pitch, nr, nc, d.R, d.col0, d.row0, d.dst_off, t); break;
+            case KK_OP_T_B16: consume_t<2, 0>(D, 0, pitch, nr, nc, d.R, d.col0, d.row0, d.dst_off, t); break;
+            default: consume_t<4, 3>(D, 0, pitch, nr, nc, d.R, d.col0, d.row0, d.dst_off, t); break;
           }
         }
         break;

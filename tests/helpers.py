@@ -11,7 +11,8 @@ import numpy as np
 from oracle import oracle
 
 OP_COPY, OP_F32, OP_F16, OP_Q4K, OP_T_F32_BF16, OP_T_F16_BF16, OP_T_B16, OP_T_B32, OP_Q8_0, OP_Q6K, OP_ROWSPLIT = range(11)
-OP_Q4_0, OP_Q4_1, OP_Q5_0, OP_Q5_1, OP_Q2K, OP_Q3K, OP_Q5K, OP_F8E4M3, OP_F8E5M2, OP_T8_F32_BF16, OP_T8_F16_BF16, OP_T8_B16, OP_IQ4NL, OP_IQ4XS, OP_MXFP4, OP_TW_F32_BF16, OP_TW_F16_BF16, OP_TW_B16 = range(11, 29)
+OP_Q4_0, OP_Q4_1, OP_Q5_0, OP_Q5_1, OP_Q2K, OP_Q3K, OP_Q5K, OP_F8E4M3, OP_F8E5M2 = range(11, 20)
+OP_IQ4NL, OP_IQ4XS, OP_MXFP4 = 23, 24, 25  # 20..22 and 26..28: round 1's candidate transpose geometries (retired, numbers not reused)
 OP_IQ2XXS, OP_IQ2XS, OP_IQ2S, OP_IQ3XXS, OP_IQ3S, OP_IQ1S, OP_IQ1M, OP_TQ1_0, OP_TQ2_0, OP_NVFP4 = range(29, 39)
 # block-dequantising ops: op -> (source bytes per block, bf16 bytes per block, blocks per tile)   (csrc/kk_ops.h kk_block_geom)
 BLOCK_GEOM = {OP_Q4K: (144, 512, 224), OP_Q8_0: (34, 64, 960), OP_Q6K: (210, 512, 152), OP_Q4_0: (18, 64, 1816), OP_Q4_1: (20, 64, 1632),
@@ -23,6 +24,15 @@ BLOCK_DTYPE = {OP_Q4K: "Q4_K", OP_Q8_0: "Q8_0", OP_Q6K: "Q6_K", OP_Q4_0: "Q4_0",
                OP_Q2K: "Q2_K", OP_Q3K: "Q3_K", OP_Q5K: "Q5_K", OP_IQ4NL: "IQ4_NL", OP_IQ4XS: "IQ4_XS", OP_MXFP4: "MXFP4",
                OP_IQ2XXS: "IQ2_XXS", OP_IQ2XS: "IQ2_XS", OP_IQ2S: "IQ2_S", OP_IQ3XXS: "IQ3_XXS", OP_IQ3S: "IQ3_S", OP_IQ1S: "IQ1_S", OP_IQ1M: "IQ1_M",
                OP_TQ1_0: "TQ1_0", OP_TQ2_0: "TQ2_0", OP_NVFP4: "NVFP4"}
+
+
+def t_width(C: int, es: int) -> int:
+    """Columns per transpose tile (csrc/kk_ops.h kk_t_width)."""
+    wmax = 4096 // es
+    if C > wmax:
+        n = -(-C // wmax)
+        return min((-(-C // n) + 7) & ~7, wmax)
+    return wmax
 
 
 def emulate_part(plan: dict, part: int, pool_bytes: int, exchange: dict | None = None) -> Tuple[np.ndarray, np.ndarray]:
@@ -54,8 +64,7 @@ def emulate_part(plan: dict, part: int, pool_bytes: int, exchange: dict | None =
                     src_bytes = BLOCK_GEOM[op][0] * u
                 else:
                     src_bytes = {OP_COPY: u, OP_F32: 4 * u, OP_F16: 2 * u, OP_ROWSPLIT: u, OP_F8E4M3: u, OP_F8E5M2: u,
-                                 OP_T8_F32_BF16: 4 * u * sg["p0"], OP_T8_F16_BF16: 2 * u * sg["p0"], OP_T8_B16: 2 * u * sg["p0"],
-                                 OP_TW_F32_BF16: 4 * u * sg["p0"], OP_TW_F16_BF16: 2 * u * sg["p0"], OP_TW_B16: 2 * u * sg["p0"], OP_T_F32_BF16: 4 * u * sg["p0"], OP_T_B32: 4 * u * sg["p0"],
+                                 OP_T_F32_BF16: 4 * u * sg["p0"], OP_T_B32: 4 * u * sg["p0"],
                                  OP_T_F16_BF16: 2 * u * sg["p0"], OP_T_B16: 2 * u * sg["p0"]}[op]
                 assert so + src_bytes <= ch["buf_bytes"], "segment reads past the bytes staged for its chunk"
                 assert covered[so:so + src_bytes].all(), "segment consumes bytes no read put there"
@@ -94,11 +103,11 @@ def emulate_part(plan: dict, part: int, pool_bytes: int, exchange: dict | None =
                     tiles += -(-u // tb)
                 else:
                     C, R, r0 = sg["p0"], sg["p1"], sg["p2"]
-                    es = 4 if op in (OP_T_F32_BF16, OP_T_B32, OP_T8_F32_BF16, OP_TW_F32_BF16) else 2
+                    es = 4 if op in (OP_T_F32_BF16, OP_T_B32) else 2
                     src = buf[so:so + u * C * es].reshape(u, C, es)
-                    if op in (OP_T_F32_BF16, OP_T8_F32_BF16, OP_TW_F32_BF16):
+                    if op == OP_T_F32_BF16:
                         v = oracle.f32_bits_to_bf16(src.reshape(-1).copy().view("<u4")).view(np.uint8).reshape(u, C, 2)
-                    elif op in (OP_T_F16_BF16, OP_T8_F16_BF16, OP_TW_F16_BF16):
+                    elif op == OP_T_F16_BF16:
                         v = oracle.f16_bits_to_bf16(src.reshape(-1).copy().view("<u2")).view(np.uint8).reshape(u, C, 2)
                     else:
                         v = src
@@ -106,14 +115,7 @@ def emulate_part(plan: dict, part: int, pool_bytes: int, exchange: dict | None =
                     dst = pool[do:do + C * R * oes].reshape(C, R, oes)
                     dst[:, r0:r0 + u, :] = v.transpose(1, 0, 2)
                     mask[do:do + C * R * oes].reshape(C, R, oes)[:, r0:r0 + u, :] = True
-                    if op in (OP_T8_F32_BF16, OP_T8_F16_BF16, OP_T8_B16):
-                        assert R % 8 == 0 and r0 % 8 == 0, "8-row tiles need 16-byte aligned destination groups"
-                        tiles += -(-u // 8) * -(-C // (4096 // es))
-                    elif op in (OP_TW_F32_BF16, OP_TW_F16_BF16, OP_TW_B16):
-                        assert R % 8 == 0 and r0 % 8 == 0, "wide-store tiles need 16-byte aligned destination groups"
-                        tiles += -(-u // 32) * -(-C // (960 // es))
-                    else:
-                        tiles += -(-u // 32) * -(-C // 128)
+                    tiles += -(-u // 8) * -(-C // t_width(C, es))  # 8-row tiles, rows wider than a stage row cut into equal pieces (kk_t_width)
                     continue
                 assert do + out.size <= pool_bytes, "segment writes past the end of the pool"
                 assert not mask[do:do + out.size].any(), "segment overlaps an earlier one"

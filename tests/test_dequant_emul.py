@@ -33,8 +33,8 @@ def emul():
     L.kk_emul_dequant_tile.restype = C.c_int
     L.kk_emul_dequant_segment.argtypes = [C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
     L.kk_emul_dequant_segment.restype = C.c_int
-    L.kk_emul_t8_tile.argtypes = [C.c_uint32, C.c_void_p] + [C.c_uint32] * 6 + [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]  # T8 and TW ops
-    L.kk_emul_t8_tile.restype = C.c_int
+    L.kk_emul_t_tile.argtypes = [C.c_uint32, C.c_void_p] + [C.c_uint32] * 6 + [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]
+    L.kk_emul_t_tile.restype = C.c_int
     L.kk_emul_dequant_tile_stats.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]
     L.kk_emul_dequant_tile_stats.restype = C.c_int
     L.kk_emul_block_geom.argtypes = [C.c_uint32] + [C.POINTER(C.c_uint32)] * 3
@@ -130,8 +130,7 @@ def test_fp8_widening_every_byte_value_every_alignment_and_tail(emul, dtype, op,
             assert (out.view(np.uint16) == fn(src)).all(), (dtype, n, pay_off)
 
 
-T8 = {"F32": (helpers.OP_T8_F32_BF16, 4), "F16": (helpers.OP_T8_F16_BF16, 2), "BF16": (helpers.OP_T8_B16, 2)}
-TW = {"F32": (helpers.OP_TW_F32_BF16, 4), "F16": (helpers.OP_TW_F16_BF16, 2), "BF16": (helpers.OP_TW_B16, 2)}
+T8 = {"F32": (helpers.OP_T_F32_BF16, 4), "F16": (helpers.OP_T_F16_BF16, 2), "BF16": (helpers.OP_T_B16, 2), "B32": (helpers.OP_T_B32, 4)}  # B32: 4-byte verbatim
 
 
 def t8_expected(dtype, src_rc):
@@ -150,25 +149,26 @@ def run_transpose_tile(emul, op, es, dtype, nr, nc, R, row0, staged, seed=21):
     written exactly once and nothing else touched.  Returns the emulator's statistics."""
     rng = np.random.default_rng(seed)
     udt = np.uint32 if es == 4 else np.uint16
+    odt, oes, fill = (np.uint32, 4, 0xCDCDCDCD) if dtype == "B32" else (np.uint16, 2, 0xCDCD)
     Cs = nc + 24  # the tile is a window of a wider source tensor
     col0 = 8
-    if dtype == "BF16":
-        src = rng.integers(0, 1 << 16, (nr, Cs), dtype=np.uint64).astype(udt)
+    if dtype in ("BF16", "B32"):
+        src = rng.integers(0, 1 << (8 * es), (nr, Cs), dtype=np.uint64).astype(udt)
     else:
         src = synth.gen_bytes(dtype, nr * Cs * es, 3, nr + nc).view(udt).reshape(nr, Cs)
     c_total = col0 + nc + 3
-    dst = np.full(c_total * R, 0xCDCD, np.uint16)
+    dst = np.full(c_total * R, fill, odt)
     hits = np.zeros((dst.nbytes + 15) // 16, np.uint8)
     stats = (C.c_uint64 * 5)()
     win = np.ascontiguousarray(src)  # element (0, 0) of the window is src[0, 0]; only the first nc columns belong to the tile
-    rc = emul.kk_emul_t8_tile(op, win.ctypes.data, Cs, nr, nc, R, col0, row0, staged, dst.ctypes.data, dst.nbytes, hits.ctypes.data, stats)
+    rc = emul.kk_emul_t_tile(op, win.ctypes.data, Cs, nr, nc, R, col0, row0, staged, dst.ctypes.data, dst.nbytes, hits.ctypes.data, stats)
     assert rc == 0, f"{dtype} {nr}x{nc}: {ERR.get(rc, rc)}"
-    want = np.full((c_total, R), 0xCDCD, np.uint16)
+    want = np.full((c_total, R), fill, odt)
     want[col0:col0 + nc, row0:row0 + nr] = t8_expected(dtype, win[:, :nc])
     assert (dst.reshape(c_total, R) == want).all(), (dtype, nr, nc, R, row0)
     m = np.zeros((c_total, R), bool)
     m[col0:col0 + nc, row0:row0 + nr] = True
-    per16 = np.add.reduceat(np.repeat(m.reshape(-1), 2).astype(np.uint8), np.arange(0, dst.nbytes, 16))
+    per16 = np.add.reduceat(np.repeat(m.reshape(-1), oes).astype(np.uint8), np.arange(0, dst.nbytes, 16))
     assert (hits == per16).all(), "bytes stored per 16-byte unit differ from the tile's footprint"
     return list(stats)
 
@@ -177,7 +177,7 @@ def run_transpose_tile(emul, op, es, dtype, nr, nc, R, row0, staged, seed=21):
 @pytest.mark.parametrize("staged", [1, 0])
 def test_t8_transpose_tiles_values_write_once_and_bank_conflicts(emul, dtype, staged):
     """8-row transpose tiles: full width, ragged width, fewer than 8 rows, destination rows that defeat the 16-byte store
-    (R % 8 != 0).  Staged full tiles must read shared memory conflict-free."""
+    (R % 8 != 0), 4-byte verbatim elements.  Staged full tiles must read shared memory conflict-free."""
     op, es = T8[dtype]
     W = 4096 // es
     cases = [(8, W, 768, 0), (8, W, 768, 16), (8, 768, 3072, 8), (8, 40, 24, 0), (5, 72, 64, 8), (8, 129 if not staged else 136, 20, 0), (8, 16, 36, 4), (1, 8, 8, 0)]
@@ -187,30 +187,6 @@ def test_t8_transpose_tiles_values_write_once_and_bank_conflicts(emul, dtype, st
         st = run_transpose_tile(emul, op, es, dtype, nr, nc, R, row0, staged)
         if staged and nr == 8 and nc % 32 == 0:
             assert st[0] == st[1], f"{dtype} {nr}x{nc}: {st[0]} shared-memory wavefronts for {st[1]} warp loads"
-
-
-@pytest.mark.parametrize("dtype", sorted(TW))
-@pytest.mark.parametrize("staged", [1, 0])
-def test_tw_wide_store_tiles_values_write_once_conflicts_and_store_width(emul, dtype, staged):
-    """32-row wide-store tiles: same checks, plus what the geometry is for — on a full tile every warp store instruction writes whole
-    64-byte segments (8 lines, 16 sectors for its 32 lanes) where the 8-row tiles touch 32 lines with 32 half-filled sectors."""
-    op, es = TW[dtype]
-    W = 960 // es
-    cases = [(32, W, 768, 0), (32, W, 768, 32), (32, 128, 3072, 64), (32, 40, 40, 0), (13, 72, 64, 8), (24, 16, 48, 8), (32, 16, 36, 4), (1, 8, 8, 0), (32, 8, 32, 0)]
-    for nr, nc, R, row0 in cases:
-        if staged and (nc * es) % 16:
-            continue
-        st = run_transpose_tile(emul, op, es, dtype, nr, nc, R, row0, staged)
-        if nr == 32 and nc % 8 == 0 and R % 8 == 0 and row0 % 8 == 0:
-            assert st[0] == st[1], f"{dtype} {nr}x{nc}: {st[0]} shared-memory wavefronts for {st[1]} warp loads"
-            if R % 64 == 0 and row0 % 64 == 0:
-                assert st[3] == 8 * st[2] and st[4] == 16 * st[2], st
-    # the comparison the two candidates are about, on a GPT-2 sized destination row (R = 768): store transactions per output byte
-    t8 = run_transpose_tile(emul, T8[dtype][0], es, dtype, 8, 4096 // es, 768, 0, 1)
-    tw = run_transpose_tile(emul, op, es, dtype, 32, W, 768, 0, 1)
-    t8_lines_per_kb = t8[3] / (8 * (4096 // es) * 2 / 1024)
-    tw_lines_per_kb = tw[3] / (32 * W * 2 / 1024)
-    assert tw_lines_per_kb * 3.9 < t8_lines_per_kb, (t8, tw)
 
 
 def _run_elementwise(emul, op, src_bytes, n_units, pay_off, out_bytes):
@@ -277,18 +253,6 @@ def test_super_block_dequantisers_read_shared_memory_conflict_free(emul):
         assert emul.kk_emul_dequant_tile_stats(op, blocks.ctypes.data, blocks.size, 0, n, out.ctypes.data, out.size, hits.ctypes.data, st) == 0
         ratio = st[0] / st[1]
         assert (ratio == 1.0) if nel >= 64 else (ratio < 2.5), (dt, st[0], st[1])
-
-
-def test_q4k_balanced_partition_variant(emul):
-    """The KK_Q4K_BALANCED=1 A/B variant of consume_q4k (contiguous blocks per warp instead of strided quads), built into a second
-    emulator library: same results for every block count a tile can have around the partition edges."""
-    L = C.CDLL(os.path.join(_HERE, "emul", "_build", "libkk_dequant_emul_q4k_balanced.so"))
-    L.kk_emul_dequant_tile.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
-    L.kk_emul_dequant_tile.restype = C.c_int
-    for n in (1, 3, 4, 5, 15, 16, 17, 63, 64, 65, 100, 223, 224):
-        blocks = synth.gen_bytes("Q4_K", 144 * n, 9, n).reshape(n, 144)
-        for pay_off in (0, 8):
-            assert (run_tile(L, "Q4_K", blocks, pay_off) == oracle.dequant_bf16("Q4_K", blocks)).all(), (n, pay_off)
 
 
 def test_harness_sees_wrong_answers(emul):

@@ -1,6 +1,6 @@
 """Torch-free quick hardware check of the paths written after round 1's GPU budget ran out (new quant types, FP8 widening,
 8-row transpose tiles, KK_FANOUT_PULL).  Appends one line per check to gpurun_out/quick.log as it goes, so a run that is cut
-short still reports what it reached.  The full versions of these checks are tests/test_zz_gpu_quants_f4.py."""
+short still reports what it reached.  The full versions of these checks are tests/test_gpu_quants.py."""
 import os
 import sys
 import tempfile
@@ -62,13 +62,14 @@ def main():
         check("FP8 -> bf16 widening", p, flags=gpupool.LOAD_F8_TO_BF16)
         p = os.path.join(d, "gpt2.safetensors")
         synth.make_gpt2(p, n_layer=2, d=96, vocab=301, n_pos=40)
-        check("GPT-2 transposes, 32x128 tiles (verified path, control)", p, flags=gpupool.LOAD_GPT2_CONV1D_T)
-        check("GPT-2 transposes, 8-row tiles", p, flags=gpupool.LOAD_GPT2_CONV1D_T | gpupool.LOAD_T8_TILES)
+        check("GPT-2 transposes", p, flags=gpupool.LOAD_GPT2_CONV1D_T)
+        check("GPT-2 transposes, 4-byte outputs (KEEP_F32)", p, flags=gpupool.LOAD_GPT2_CONV1D_T | gpupool.LOAD_KEEP_F32)
         q = os.path.join(d, "gpt2w.safetensors")
         synth.write_safetensors(q, synth.gpt2_tensors(n_layer=1, d=1032, vocab=50, n_pos=8, dtype="F32"), 3)
-        check("8-row tiles, rows wider than one tile (d=1032)", q, flags=gpupool.LOAD_GPT2_CONV1D_T | gpupool.LOAD_T8_TILES)
-        check("GPT-2 transposes, 32-row wide-store tiles", p, flags=gpupool.LOAD_GPT2_CONV1D_T | gpupool.LOAD_TW_TILES)
-        check("32-row wide-store tiles, d=1032", q, flags=gpupool.LOAD_GPT2_CONV1D_T | gpupool.LOAD_TW_TILES)
+        check("transposes, rows wider than one tile (d=1032)", q, flags=gpupool.LOAD_GPT2_CONV1D_T)
+        q = os.path.join(d, "gpt2o.safetensors")
+        synth.write_safetensors(q, synth.gpt2_tensors(n_layer=1, d=43, vocab=50, n_pos=8, dtype="F16"), 3)
+        check("transposes, destination rows off 16 bytes (d=43)", q, flags=gpupool.LOAD_GPT2_CONV1D_T)
         # KK_FANOUT_PULL with 4 virtual ranks on this GPU
         try:
             ld = os.path.join(d, "llama")

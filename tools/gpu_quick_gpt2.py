@@ -1,4 +1,4 @@
-"""Torch-free A/B of the transpose tile geometries on GPT-2-small (resident image, CUDA-event timed inside the library)."""
+"""Torch-free timing of the transposing load on GPT-2-small (resident image, CUDA-event timed inside the library)."""
 import json
 import os
 import sys
@@ -17,14 +17,13 @@ with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") els
     nbytes = synth.make_gpt2(p)
     out["synth_s"] = time.time() - t0
     pool = gpupool.Pool([0])
-    for name, flags in (("tiles_32x128", gpupool.LOAD_GPT2_CONV1D_T), ("tiles_8row", gpupool.LOAD_GPT2_CONV1D_T | gpupool.LOAD_T8_TILES),
-                        ("tiles_32row_wide_store", gpupool.LOAD_GPT2_CONV1D_T | gpupool.LOAD_TW_TILES)):
+    for name, flags in (("transposed_bf16", gpupool.LOAD_GPT2_CONV1D_T), ("plain_cast_bf16", 0), ("transposed_keep_f32", gpupool.LOAD_GPT2_CONV1D_T | gpupool.LOAD_KEEP_F32)):
         m = pool.load(p, flags=flags | gpupool.LOAD_DEFER)
         try:
             m.stage_resident()
             for _ in range(3):
                 m.convert_resident()
-            runs = [m.convert_resident() for _ in range(10)]
+            runs = [m.convert_resident() for _ in range(20)]
             ms = sorted(t for t, _ in runs)
             st = m.stats()
             alg = st["parts"][0]["src_bytes"] + st["parts"][0]["out_bytes"]
@@ -33,8 +32,12 @@ with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") els
         finally:
             m.release()
     pool.close()
-out["speedup"] = out["tiles_32x128"]["ms_median"] / out["tiles_8row"]["ms_median"]
-out["speedup_wide_store"] = out["tiles_32x128"]["ms_median"] / out["tiles_32row_wide_store"]["ms_median"]
+pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+if os.path.exists(pk):
+    peak = json.load(open(pk)).get("hbm_gbs")
+    for v in out.values():
+        if isinstance(v, dict):
+            v["frac_of_copy_peak"] = v["GBps_at_median"] / peak
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", os.environ.get("KK_QUICK_OUT", "t8_ab.json")), "w"), indent=1)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", os.environ.get("KK_QUICK_OUT", "gpt2_quick.json")), "w"), indent=1)
 print(json.dumps(out))

@@ -40,9 +40,8 @@ ITER_BYTES = {
     "KK_OP_IQ4NL_BF16": (8 * 18, 512), "KK_OP_MXFP4_BF16": (8 * 17, 512), "KK_OP_IQ4XS_BF16": (136, 512),
     "KK_OP_IQ2XXS_BF16": (66, 512), "KK_OP_IQ2XS_BF16": (74, 512), "KK_OP_IQ2S_BF16": (82, 512), "KK_OP_IQ3XXS_BF16": (98, 512),
     "KK_OP_IQ3S_BF16": (110, 512), "KK_OP_IQ1S_BF16": (50, 512), "KK_OP_IQ1M_BF16": (56, 512),
-    # candidate transposes: a warp iteration turns 256 elements (T8: 32 columns x 8 rows; TW: 8 columns x 32 rows) into 32 16-byte stores
-    "KK_OP_T8_F32_BF16": (1024, 512), "KK_OP_T8_F16_BF16": (512, 512), "KK_OP_T8_B16": (512, 512),
-    "KK_OP_TW_F32_BF16": (1024, 512), "KK_OP_TW_F16_BF16": (512, 512), "KK_OP_TW_B16": (512, 512),
+    # transposes: a warp iteration turns 256 elements (32 columns x 8 rows) into 32 16-byte stores (64 for the 4-byte verbatim form)
+    "KK_OP_T_F32_BF16": (1024, 512), "KK_OP_T_F16_BF16": (512, 512), "KK_OP_T_B16": (512, 512), "KK_OP_T_B32": (1024, 1024),
     "KK_OP_TQ1_0_BF16": (54, 512), "KK_OP_TQ2_0_BF16": (66, 512), "KK_OP_NVFP4_BF16": (4 * 36, 512),
 }
 
@@ -211,7 +210,7 @@ def analyse():
         n, a, b = max(cand)
         mix = collections.Counter(classify(ins[i]["mn"]) for i in range(a, b + 1))
         inner = [(n2, a2, b2) for n2, a2, b2 in cand if a2 >= a and b2 <= b and (a2, b2) != (a, b)]
-        hot, hot_math = hot_path(ins, labels, a, b, "vec" if op.startswith(("KK_OP_T8_", "KK_OP_TW_")) else "math")
+        hot, hot_math = hot_path(ins, labels, a, b, "vec" if op.startswith("KK_OP_T_") else "math")
         rows.append({"op": op, "static": len(mine), "loop": n, "hot": hot, "hot_math": hot_math, "mix": mix, "inner_loops": sorted(n2 for n2, _, _ in inner), "n_loops": len(cand)})
     return rows, len(ins), collections.Counter(x["mn"].split(".")[0] for x in ins)
 
