@@ -128,32 +128,37 @@ KK_DQ_DEV void q4k_quad(const Dsts& D, uint32_t pay, uint32_t b0, uint32_t nb, u
   const int myj = lane >> 2;
   const uint32_t qoff = 16u + 32u * (uint32_t)(myj >> 1) + 8u * (uint32_t)(lane & 3);
   const int nsh = (myj & 1) * 4;
+  // all four blocks' nibble words first (a block past the end re-reads the last valid one: in bounds, discarded), so that the four
+  // load -> expand -> store chains overlap instead of each waiting for its own shared-memory round trip behind the previous block's store
+  uint32_t qw0[4], qw1[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t kb = min((uint32_t)k, nb - 1);
+    const uint32_t qa = pay + (b0 + kb) * KK_Q4K_BLOCK_BYTES + qoff;
+    if (ALIGNED) {
+      const uint2 q = lds64(qa);
+      qw0[k] = q.x; qw1[k] = q.y;
+    } else {
+      qw0[k] = lds32_bytes(qa); qw1[k] = lds32_bytes(qa + 4);
+    }
+  }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const float dsc = __shfl_sync(0xffffffffu, dsc_j, 8 * k + myj);
     const float dmn = __shfl_sync(0xffffffffu, dmn_j, 8 * k + myj);
-    if ((uint32_t)k < nb) {
-      const uint32_t qa = pay + (b0 + k) * KK_Q4K_BLOCK_BYTES + qoff;
-      uint32_t q0, q1;
-      if (ALIGNED) {
-        const uint2 q = lds64(qa);
-        q0 = q.x; q1 = q.y;
-      } else {
-        q0 = lds32_bytes(qa); q1 = lds32_bytes(qa + 4);
-      }
-      q0 = (q0 >> nsh) & 0x0F0F0F0Fu;
-      q1 = (q1 >> nsh) & 0x0F0F0F0Fu;
-      float y[8];
+    const uint32_t q0 = (qw0[k] >> nsh) & 0x0F0F0F0Fu;
+    const uint32_t q1 = (qw1[k] >> nsh) & 0x0F0F0F0Fu;
+    float y[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        // 0x4B0000qq is the float 2^23 + q; subtracting 2^23 gives q exactly (PRMT + FADD, no I2F).
-        const uint32_t bits = kk_byte_perm(e < 4 ? q0 : q1, 0x4B000000u, 0x7440u | (uint32_t)(e & 3));
-        const float q = __fsub_rn(kk_bits2f(bits), 8388608.0f);
-        y[e] = __fsub_rn(__fmul_rn(dsc, q), dmn);
-      }
+    for (int e = 0; e < 8; ++e) {
+      // 0x4B0000qq is the float 2^23 + q; subtracting 2^23 gives q exactly (PRMT + FADD, no I2F).
+      const uint32_t bits = kk_byte_perm(e < 4 ? q0 : q1, 0x4B000000u, 0x7440u | (uint32_t)(e & 3));
+      const float q = __fsub_rn(kk_bits2f(bits), 8388608.0f);
+      y[e] = __fsub_rn(__fmul_rn(dsc, q), dmn);
+    }
+    if ((uint32_t)k < nb)
       store16_all(D, dst_off + (uint64_t)(b0 + k) * 512u + (uint32_t)lane * 16u,
                   make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7])));
-    }
   }
 }
 

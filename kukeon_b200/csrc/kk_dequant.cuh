@@ -50,14 +50,14 @@ KK_DQ_DEV uint32_t lds32_funnel(uint32_t a) {
   const uint32_t w0 = lds32(base), w1 = sh ? lds32_slack(base + 4u) : 0u;
   return kk_funnel_r(w0, w1, sh);
 }
-// Which of the two a block type wants is a compile-time matter (tools/sass_budget.py has the counts).  Tile payloads start on 8-byte
-// boundaries in every real file (GGUF aligns tensor data to >= 8 bytes, tiles are multiples of 16 bytes), so blocks whose size is a
-// multiple of 4 are ALWAYS word aligned and the aligned arm of lds32_any is one predicated load (Q5_K: 94 instructions per iteration
-// against 104 with the funnel).  A 256-weight block of 4k + 2 bytes is handled by a whole warp, so its alignment is warp-uniform and
-// alternates from block to block: 1 load or 2 half loads + merge, the same 3 instructions on average as the funnel's 2 loads + shift.  Only
-// the small blocks — eight per warp iteration, each at its own alignment — make the branchy form DIVERGE (both arms run): those take the funnel.
+// Which of the two a block type wants is a compile-time matter.  Tile payloads start on 8-byte boundaries in every real file (GGUF aligns
+// tensor data to >= 8 bytes, tiles are multiples of 16 bytes), so blocks whose size is a multiple of 4 are ALWAYS word aligned and
+// lds32_any is one load.  Every other size takes the funnel: branch-free, so all of a block's loads issue back to back.  (Round 1 kept the
+// branchy form for the 256-weight blocks of 4k + 2 bytes — their alignment is warp-uniform, so it costs no divergence and one
+// instruction less on average — but each of its four loads sat in its own BSSY / BRA / BSYNC region and exposed its shared-memory latency
+// separately; measured on hardware that put Q3_K at 0.54 of the copy peak, TQ1_0 and IQ2_XXS at 0.70.)
 template <uint32_t BLOCK_BYTES>
-KK_DQ_DEV uint32_t lds32_blk(uint32_t a) { return (BLOCK_BYTES % 4u != 0u && BLOCK_BYTES < 40u /* 32-weight blocks: 17..34 bytes; the smallest 256-weight block has 50 */) ? lds32_funnel(a) : lds32_any(a); }
+KK_DQ_DEV uint32_t lds32_blk(uint32_t a) { return (BLOCK_BYTES % 4u != 0u) ? lds32_funnel(a) : lds32_any(a); }
 // Eight payload bytes at ANY address a -> two words: the three aligned words that cover them, funnel-shifted into place (SHF.R.W).
 // There are no alignment cases, so the lanes of a warp whose blocks sit at different alignments — eight 17-, 18-, 22- or 34-byte blocks
 // per warp iteration — do not diverge (the first version branched three ways: aligned / 2-byte funnel / byte by byte, and such a warp
@@ -90,10 +90,11 @@ KK_DQ_DEV uint32_t spread4(uint32_t x) { return ((x & 0xFu) * 0x00204081u) & 0x0
 // Q8_0 block (34 B): d f16 | qs[32] int8 -> 32 bf16, y = q * d in fp32 (gguf/quants.py Q8_0.dequantize_blocks).
 // Lane l of a warp handles elements 8*(l&3)..+8 of block (l>>2): 8 blocks and 512 contiguous output bytes per iteration.
 KK_DQ_DEV void consume_q8_0(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
+#pragma unroll 2
   for (uint32_t b0 = (uint32_t)cwarp * 8u; b0 < nblk; b0 += kConsumerWarps * 8u) {
     const uint32_t b = b0 + (uint32_t)(lane >> 2);
-    if (b < nblk) {
-      const uint32_t blk = pay + b * KK_Q8_0_BLOCK_BYTES;
+    {  // lanes past the last block recompute it (in bounds) and skip the store: no branch around the loads, so two iterations' loads overlap
+      const uint32_t blk = pay + min(b, nblk - 1u) * KK_Q8_0_BLOCK_BYTES;
       const float d = kk_h2f(lds16_any(blk));
       const uint32_t qa = blk + 2u + 8u * (uint32_t)(lane & 3);
       uint32_t q0, q1;
@@ -103,8 +104,9 @@ KK_DQ_DEV void consume_q8_0(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t
       float y[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) y[e] = __fmul_rn(byte_to_float<128>(e < 4 ? q0 : q1, e & 3), d);
-      store16_all(D, dst_off + (uint64_t)b * 64u + (uint32_t)(lane & 3) * 16u,
-                  make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7])));
+      if (b < nblk)
+        store16_all(D, dst_off + (uint64_t)b * 64u + (uint32_t)(lane & 3) * 16u,
+                    make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7])));
     }
   }
 }
@@ -118,6 +120,7 @@ KK_DQ_DEV void consume_q6k(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t 
   const uint32_t ql_off = 64u * (uint32_t)(g >> 2) + 32u * (uint32_t)(g & 1) + (uint32_t)i0;
   const uint32_t qh_off = 128u + 32u * (uint32_t)(g >> 2) + (uint32_t)i0;
   const int lsh = 4 * ((g & 3) >> 1), hsh = 2 * (g & 3);
+#pragma unroll 2
   for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
     const uint32_t blk = pay + b * KK_Q6K_BLOCK_BYTES;
     const float d = kk_h2f(lds16_any(blk + 208u));
@@ -153,10 +156,11 @@ KK_DQ_DEV void consume_legacy32(const Dsts& D, uint32_t pay, uint32_t nblk, uint
   const uint32_t e0 = 8u * (uint32_t)(lane & 3);
   const uint32_t q_off = kQsOff + (e0 & 15u);
   const uint32_t nsh = (e0 >> 4) * 4u;  // 0: low nibbles (elements 0..15), 4: high nibbles (elements 16..31)
+#pragma unroll 2
   for (uint32_t b0 = (uint32_t)cwarp * 8u; b0 < nblk; b0 += kConsumerWarps * 8u) {
     const uint32_t b = b0 + (uint32_t)(lane >> 2);
-    if (b < nblk) {
-      const uint32_t blk = pay + b * BYTES;
+    {  // lanes past the last block recompute it (in bounds) and skip the store: no branch around the loads, so two iterations' loads overlap
+      const uint32_t blk = pay + min(b, nblk - 1u) * BYTES;
       const float d = lds_f16(blk);
       const float m = HAS_M ? lds_f16(blk + 2u) : 0.f;
       uint32_t q0, q1;
@@ -174,7 +178,7 @@ KK_DQ_DEV void consume_legacy32(const Dsts& D, uint32_t pay, uint32_t nblk, uint
         if (HAS_M) y[e] = __fadd_rn(__fmul_rn(d, byte_to_float<0>(e < 4 ? q0 : q1, e & 3)), m);
         else y[e] = __fmul_rn(d, byte_to_float<(HAS_QH ? 16 : 8)>(e < 4 ? q0 : q1, e & 3));
       }
-      store_bf16x8(D, dst_off + (uint64_t)b * 64u + (uint32_t)(lane & 3) * 16u, y);
+      if (b < nblk) store_bf16x8(D, dst_off + (uint64_t)b * 64u + (uint32_t)(lane & 3) * 16u, y);
     }
   }
 }
@@ -186,6 +190,7 @@ KK_DQ_DEV void consume_legacy32(const Dsts& D, uint32_t pay, uint32_t nblk, uint
 KK_DQ_DEV void consume_q2k(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
   const uint32_t q_off = 16u + 32u * (uint32_t)(lane >> 4) + 8u * (uint32_t)(lane & 3);
   const uint32_t sh = 2u * (uint32_t)((lane >> 2) & 3);
+#pragma unroll 2
   for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
     const uint32_t blk = pay + b * KK_Q2K_BLOCK_BYTES;
     const float d = lds_f16(blk + 80u), dmin = lds_f16(blk + 82u);
@@ -211,6 +216,7 @@ KK_DQ_DEV void consume_q3k(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t 
   const uint32_t sh = 2u * (g & 3u);
   const uint32_t lo_off = 96u + (k & 7u), lo_sh = (k >> 3) * 4u;
   const uint32_t hi_off = 104u + (k & 3u), hi_sh = 2u * (k >> 2);
+#pragma unroll 2
   for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
     const uint32_t blk = pay + b * KK_Q3K_BLOCK_BYTES;
     const float d = lds_f16(blk + 108u);
@@ -234,6 +240,7 @@ KK_DQ_DEV void consume_q5k(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t 
   const uint32_t j = (uint32_t)(lane >> 2), i0 = 8u * (uint32_t)(lane & 3);
   const uint32_t q_off = 48u + 32u * (j >> 1) + i0;
   const uint32_t nsh = 4u * (j & 1u);
+#pragma unroll 2
   for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
     const uint32_t blk = pay + b * KK_Q5K_BLOCK_BYTES;
     const float d = lds_f16(blk), dmin = lds_f16(blk + 2u);
@@ -392,10 +399,11 @@ KK_DQ_DEV void consume_codebook32(const Dsts& D, uint32_t pay, uint32_t nblk, ui
   const uint32_t e0 = 8u * (uint32_t)(lane & 3);
   const uint32_t q_off = kQsOff + (e0 & 15u);
   const uint32_t nsh = (e0 >> 4) * 4u;
+#pragma unroll 2
   for (uint32_t b0 = (uint32_t)cwarp * 8u; b0 < nblk; b0 += kConsumerWarps * 8u) {
     const uint32_t b = b0 + (uint32_t)(lane >> 2);
-    if (b < nblk) {
-      const uint32_t blk = pay + b * BYTES;
+    {  // lanes past the last block recompute it (in bounds) and skip the store: no branch around the loads, so two iterations' loads overlap
+      const uint32_t blk = pay + min(b, nblk - 1u) * BYTES;
       float d;
       if (TABLE == 1) {
         const uint32_t e = lds8(blk);
@@ -409,7 +417,7 @@ KK_DQ_DEV void consume_codebook32(const Dsts& D, uint32_t pay, uint32_t nblk, ui
       q1 = (q1 >> nsh) & 0x0F0F0F0Fu;
       float y[8];
       codebook8<TABLE>(d, q0, q1, y);
-      store_bf16x8(D, dst_off + (uint64_t)b * 64u + (uint32_t)(lane & 3) * 16u, y);
+      if (b < nblk) store_bf16x8(D, dst_off + (uint64_t)b * 64u + (uint32_t)(lane & 3) * 16u, y);
     }
   }
 }
@@ -418,6 +426,7 @@ KK_DQ_DEV void consume_iq4xs(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_
   const uint32_t j = (uint32_t)(lane >> 2), i0 = 8u * (uint32_t)(lane & 3);
   const uint32_t q_off = 8u + 16u * j + (i0 & 15u);
   const uint32_t nsh = (i0 >> 4) * 4u;
+#pragma unroll 2
   for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
     const uint32_t blk = pay + b * KK_IQ4XS_BLOCK_BYTES;
     const float d = lds_f16(blk);
@@ -453,6 +462,7 @@ KK_DQ_DEV float iq_scale(float d, uint32_t s, float k) { return __fmul_rn(__fmul
 // IQ2_XXS (66 B): d f16 | 8 x { u32: four grid indices (bytes) | u32: four 7-bit sign indices, scale in the top 4 bits }
 KK_DQ_DEV void consume_iq2xxs(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
   const uint32_t g = (uint32_t)(lane >> 2), k = (uint32_t)(lane & 3);
+#pragma unroll 2
   for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
     const uint32_t blk = pay + b * KK_IQ2XXS_BLOCK_BYTES;
     const float d = lds_f16(blk);
@@ -465,6 +475,7 @@ KK_DQ_DEV void consume_iq2xxs(const Dsts& D, uint32_t pay, uint32_t nblk, uint64
 // IQ2_XS (74 B): d f16 | 32 x u16 { 9-bit grid index | 7-bit sign index } | scales[8] (a nibble per 16 weights)
 KK_DQ_DEV void consume_iq2xs(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
   const uint32_t l = (uint32_t)lane;
+#pragma unroll 2
   for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
     const uint32_t blk = pay + b * KK_IQ2XS_BLOCK_BYTES;
     const float d = lds_f16(blk);
@@ -477,6 +488,7 @@ KK_DQ_DEV void consume_iq2xs(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_
 // IQ2_S (82 B): d f16 | qs[32] | signs[32] | qh[8] (2 more index bits per entry) | scales[8]
 KK_DQ_DEV void consume_iq2s(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
   const uint32_t l = (uint32_t)lane;
+#pragma unroll 2
   for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
     const uint32_t blk = pay + b * KK_IQ2S_BLOCK_BYTES;
     const float d = lds_f16(blk);
@@ -489,6 +501,7 @@ KK_DQ_DEV void consume_iq2s(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t
 // IQ3_XXS (98 B): d f16 | qs[64] (one 4-value entry per byte) | 8 x u32 { four 7-bit sign indices, scale in the top 4 bits }
 KK_DQ_DEV void consume_iq3xxs(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
   const uint32_t l = (uint32_t)lane, g = l >> 2, k = l & 3u;
+#pragma unroll 2
   for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
     const uint32_t blk = pay + b * KK_IQ3XXS_BLOCK_BYTES;
     const float d = lds_f16(blk);
@@ -500,6 +513,7 @@ KK_DQ_DEV void consume_iq3xxs(const Dsts& D, uint32_t pay, uint32_t nblk, uint64
 // IQ3_S (110 B): d f16 | qs[64] | qh[8] (a ninth index bit per entry) | signs[32] | scales[4] (a nibble per 32 weights); db = d * (1 + 2s)
 KK_DQ_DEV void consume_iq3s(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
   const uint32_t l = (uint32_t)lane, g = l >> 2;
+#pragma unroll 2
   for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
     const uint32_t blk = pay + b * KK_IQ3S_BLOCK_BYTES;
     const float d = lds_f16(blk);
@@ -521,6 +535,7 @@ KK_DQ_DEV void store_entry_iq1(const Dsts& D, uint64_t off, float dl, uint64_t g
 // IQ1_S (50 B): d f16 | qs[32] | 8 x u16 { four 3-bit index extensions | 3-bit scale << 12 | delta sign << 15 }
 KK_DQ_DEV void consume_iq1s(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
   const uint32_t l = (uint32_t)lane, g = l >> 2, k = l & 3u;
+#pragma unroll 2
   for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
     const uint32_t blk = pay + b * KK_IQ1S_BLOCK_BYTES;
     const float d = lds_f16(blk);
@@ -533,6 +548,7 @@ KK_DQ_DEV void consume_iq1s(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t
 // IQ1_M (56 B): qs[32] | qh[16] (a nibble per entry: 3 index bits, bit 3 = delta sign) | 4 x u16 { four 3-bit scales | a nibble of the fp16 d }
 KK_DQ_DEV void consume_iq1m(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
   const uint32_t l = (uint32_t)lane, k16 = l >> 1;
+#pragma unroll 2
   for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
     const uint32_t blk = pay + b * KK_IQ1M_BLOCK_BYTES;
     const uint32_t s0 = lds16_any(blk + 48u), s1 = lds16_any(blk + 50u), s2 = lds16_any(blk + 52u), s3 = lds16_any(blk + 54u);
@@ -548,6 +564,7 @@ KK_DQ_DEV void consume_iq1m(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t
 KK_DQ_DEV void consume_tq2_0(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
   const uint32_t q_off = 32u * (uint32_t)(lane >> 4) + 8u * (uint32_t)(lane & 3);
   const uint32_t sh = 2u * (uint32_t)((lane >> 2) & 3);
+#pragma unroll 2
   for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
     const uint32_t blk = pay + b * KK_TQ2_0_BLOCK_BYTES;
     const float d = lds_f16(blk + 64u);
@@ -574,6 +591,7 @@ KK_DQ_DEV void consume_tq1_0(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_
   else if (l < 30u) { a0 = 32u + 8u * ((l - 20u) & 1u); a1 = a0 + 4u; p0 = p1 = (l - 20u) >> 1; }
   else { a0 = a1 = 48u; p0 = 2u * (l - 30u); p1 = p0 + 1u; }
   const uint32_t m0 = (uint32_t)((0x000000511B090301ull >> (8u * p0)) & 0xFFu), m1 = (uint32_t)((0x000000511B090301ull >> (8u * p1)) & 0xFFu);  // 3^p
+#pragma unroll 2
   for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
     const uint32_t blk = pay + b * KK_TQ1_0_BLOCK_BYTES;
     const float d = lds_f16(blk + 52u);
@@ -589,10 +607,11 @@ KK_DQ_DEV void consume_tq1_0(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_
 // half l&1.
 KK_DQ_DEV void consume_nvfp4(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
   const uint32_t l = (uint32_t)lane, sb = (l >> 1) & 3u, nsh = 4u * (l & 1u);
+#pragma unroll 2
   for (uint32_t b0 = (uint32_t)cwarp * 4u; b0 < nblk; b0 += kConsumerWarps * 4u) {
     const uint32_t b = b0 + (l >> 3);
-    if (b < nblk) {
-      const uint32_t blk = pay + b * KK_NVFP4_BLOCK_BYTES;
+    {
+      const uint32_t blk = pay + min(b, nblk - 1u) * KK_NVFP4_BLOCK_BYTES;
       const uint32_t x = lds8(blk + sb), e = (x >> 3) & 0xFu, m = x & 7u;
       // half the unsigned-E4M3 value: (1 + m/8) * 2^(e-8) built as bits; e == 0: m * 2^-10; 0x00 and 0x7F decode to 0
       float d = e ? kk_bits2f(((e + 119u) << 23) | (m << 20)) : __fmul_rn((float)m, 0.0009765625f);
@@ -600,7 +619,7 @@ KK_DQ_DEV void consume_nvfp4(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_
       const uint32_t q0 = (lds32_blk<KK_NVFP4_BLOCK_BYTES>(blk + 4u + 8u * sb) >> nsh) & 0x0F0F0F0Fu, q1 = (lds32_blk<KK_NVFP4_BLOCK_BYTES>(blk + 8u + 8u * sb) >> nsh) & 0x0F0F0F0Fu;
       float y[8];
       codebook8<1>(d, q0, q1, y);
-      store_bf16x8(D, dst_off + (uint64_t)b * 128u + (l & 7u) * 16u, y);
+      if (b < nblk) store_bf16x8(D, dst_off + (uint64_t)b * 128u + (l & 7u) * 16u, y);
     }
   }
 }

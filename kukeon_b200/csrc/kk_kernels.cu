@@ -81,24 +81,20 @@ __device__ __forceinline__ void bulk_wait_read() {
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ uint4 lds128(uint32_t a) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-  return v;
+// Loads from the staged tile are PLAIN C++ loads (the compiler infers ld.shared from the cvta intrinsic), not volatile asm: the compiler may then
+// hoist the loads of the next block above the arithmetic and the global store of the previous one — the stores below carry no "memory" clobber
+// for the same reason — which is where a warp's instruction-level parallelism comes from (with volatile asm every block's load -> math -> store
+// chain ran strictly after the previous block's: Q3_K sat at 0.54 of the copy peak, latency-bound with 4 warps per scheduler).  Ordering against
+// the pipeline is kept by the "memory" clobbers of mbar_wait (acquire of the stage), mbar_arrive (release) and the named barrier.
+template <typename T>
+__device__ __forceinline__ T lds_plain(uint32_t a) {
+  return *reinterpret_cast<const T*>(__cvta_shared_to_generic((size_t)a));
 }
-__device__ __forceinline__ uint2 lds64(uint32_t a) {
-  uint2 v;
-  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ uint32_t lds8(uint32_t a) {
-  uint32_t v;
-  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
-  return v;
-}
+__device__ __forceinline__ uint4 lds128(uint32_t a) { return lds_plain<uint4>(a); }
+__device__ __forceinline__ uint2 lds64(uint32_t a) { return lds_plain<uint2>(a); }
+__device__ __forceinline__ uint32_t lds8(uint32_t a) { return lds_plain<uint8_t>(a); }
 __device__ __forceinline__ void stg128(void* p, const uint4& v) {
-  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
-               : "memory");
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));  // no "memory" clobber: see lds_plain
 }
 __device__ __forceinline__ void stmm128(void* p, const uint4& v) {  // NVLS multicast store
   asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(__uint_as_float(v.x)),
@@ -164,16 +160,8 @@ __device__ __forceinline__ void store4_all(const Dsts& D, uint64_t off, uint32_t
 // ---- consumer bodies ------------------------------------------------------------------------------------------------------------
 // Every per-lane consumer function lives in kk_consume_core.cuh (copy, casts, Q4_K) and kk_dequant.cuh (the other block types, FP8,
 // 8-row transposes), written against the primitives bound here so that tests/emul can compile the same source for the host.
-__device__ __forceinline__ uint32_t lds16(uint32_t a) {
-  uint32_t v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ uint32_t lds32(uint32_t a) {
-  uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-  return v;
-}
+__device__ __forceinline__ uint32_t lds16(uint32_t a) { return lds_plain<uint16_t>(a); }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { return lds_plain<uint32_t>(a); }
 __device__ __forceinline__ float kk_h2f(uint32_t h) { return __half2float(__ushort_as_half((unsigned short)h)); }
 // two FP8 (low 16 bits of v) -> two fp16, exact (sm_89+ pair conversion)
 template <bool E5M2>
