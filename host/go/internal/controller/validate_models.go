@@ -8,6 +8,7 @@
 package controller
 
 import (
+	"regexp"
 	"fmt"
 	"os"
 	"path/filepath"
@@ -41,6 +42,8 @@ var modelOptionFlags = map[string]uint32{
 //   - mode: "", single, broadcast, scatter (case-insensitive).
 //   - devices: distinct non-negative ordinals, at most 8; empty means every device of the daemon's pool.
 //   - options: gpt2Conv1dTranspose, keepF32, f8ToBf16.
+var modelNameRE = regexp.MustCompile(`^[A-Za-z0-9][A-Za-z0-9._-]*$`)
+
 func validateModels(in []intmodel.ModelMount) ([]intmodel.ModelMount, error) {
 	if len(in) == 0 {
 		return nil, nil
@@ -51,6 +54,11 @@ func validateModels(in []intmodel.ModelMount) ([]intmodel.ModelMount, error) {
 		name := strings.TrimSpace(m.Name)
 		if name == "" {
 			return nil, fmt.Errorf("%w (model[%d])", errdefs.ErrModelNameRequired, i)
+		}
+		// The name is joined into <cell dir>/gpupool/<name> on the host and into the mount target inside the container: a "/", ".." or NUL
+		// in it would let a manifest write outside the cell directory.  One path component of [A-Za-z0-9._-], not starting with '.'.
+		if !modelNameRE.MatchString(name) {
+			return nil, fmt.Errorf("%w (model[%d] name %q)", errdefs.ErrModelNameInvalid, i, name)
 		}
 		if _, dup := seen[name]; dup {
 			return nil, fmt.Errorf("%w (model[%d] name %q)", errdefs.ErrModelNameDuplicate, i, name)

@@ -8,6 +8,7 @@
 package ctr
 
 import (
+	"strconv"
 	"context"
 	"fmt"
 	"os"
@@ -25,7 +26,8 @@ const (
 	GPUPoolContainerDir = "/run/kukeon/gpupool"
 	envGPUPoolManifest  = "KUKEON_GPUPOOL_MANIFEST"
 	envGPUPoolIPCHandle = "KUKEON_GPUPOOL_IPC_HANDLE"
-	envGPUPoolDevice    = "KUKEON_GPUPOOL_DEVICE"
+	envGPUPoolDeviceUUID = "KUKEON_GPUPOOL_DEVICE_UUID" // "GPU-xxxxxxxx-...": the same string cudaGetDeviceProperties().uuid / nvidia-smi -L give inside the container
+	envGPUPoolPCIBusID   = "KUKEON_GPUPOOL_PCI_BUS_ID"
 )
 
 // GPUWeightsInjection is one mounted model.  HostDir holds manifest.json and ipc.handle, written by modelhub.Mount with the atomic
@@ -34,7 +36,10 @@ type GPUWeightsInjection struct {
 	Name    string // models[].name; empty = the single-model layout (no sub-directory, unsuffixed env names)
 	HostDir string // <cell metadata dir>/<container>/gpupool[/<name>]
 	Target  string // container path of the mount; empty = GPUPoolContainerDir
-	Device  int    // CUDA ordinal whose pool the handle refers to
+	// Identity of the GPU whose pool the handle refers to, from gpupool.DeviceIdentity (kk_device_identity).  NOT the daemon's CUDA ordinal: ordinals
+	// follow CUDA_DEVICE_ORDER / CUDA_VISIBLE_DEVICES and a container that sees only one /dev/nvidia<N> enumerates that GPU as ordinal 0.
+	DeviceUUID string // "GPU-..."; the agent selects the CUDA device whose UUID matches
+	PCIBusID   string // "dddd:bb:dd.f" (lower case): key of /proc/driver/nvidia/gpus/<id>/information, where the device-node minor is read
 }
 
 // WithGPUWeights appends one model to the container being built.  Repeatable: one option per models[] entry.
@@ -88,16 +93,38 @@ func withGPUWeights(inj GPUWeightsInjection) []oci.SpecOpts {
 		oci.WithEnv([]string{
 			fmt.Sprintf("%s%s=%s/manifest.json", envGPUPoolManifest, sfx, dest),
 			fmt.Sprintf("%s%s=%s/ipc.handle", envGPUPoolIPCHandle, sfx, dest),
-			fmt.Sprintf("%s%s=%d", envGPUPoolDevice, sfx, inj.Device),
+			fmt.Sprintf("%s%s=%s", envGPUPoolDeviceUUID, sfx, inj.DeviceUUID),
+			fmt.Sprintf("%s%s=%s", envGPUPoolPCIBusID, sfx, inj.PCIBusID),
 		}),
-		withNvidiaDevices(inj.Device),
+		withNvidiaDevices(inj.PCIBusID),
 	}
 }
 
-// withNvidiaDevices adds /dev/nvidiactl, /dev/nvidia-uvm, /dev/nvidia-uvm-tools and /dev/nvidia<N> (those that exist) to Linux.Devices and
+// nvidiaDeviceMinor reads the minor number of the GPU's /dev/nvidia<N> node from the driver's table.  The CUDA ordinal is not that number
+// (round-1 review): ordinals are sorted fastest-first and filtered by CUDA_VISIBLE_DEVICES, minors follow PCI enumeration.
+func nvidiaDeviceMinor(pciBusID string) (int, error) {
+	p := path.Join("/proc/driver/nvidia/gpus", strings.ToLower(pciBusID), "information")
+	b, err := os.ReadFile(p)
+	if err != nil {
+		return 0, fmt.Errorf("read %s: %w", p, err)
+	}
+	for _, line := range strings.Split(string(b), "\n") {
+		k, v, ok := strings.Cut(line, ":")
+		if ok && strings.TrimSpace(k) == "Device Minor" {
+			return strconv.Atoi(strings.TrimSpace(v))
+		}
+	}
+	return 0, fmt.Errorf("%s: no Device Minor line", p)
+}
+
+// withNvidiaDevices adds /dev/nvidiactl, /dev/nvidia-uvm, /dev/nvidia-uvm-tools and the GPU's /dev/nvidia<minor> (those that exist) to Linux.Devices and
 // allows them in the device cgroup.  Idempotent across several models on the same GPU: a node already present is skipped.
-func withNvidiaDevices(device int) oci.SpecOpts {
+func withNvidiaDevices(pciBusID string) oci.SpecOpts {
 	return func(_ context.Context, _ oci.Client, _ *containers.Container, s *runtimespec.Spec) error {
+		device, err := nvidiaDeviceMinor(pciBusID)
+		if err != nil {
+			return err
+		}
 		if s.Linux == nil {
 			s.Linux = &runtimespec.Linux{}
 		}

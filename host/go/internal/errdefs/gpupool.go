@@ -20,6 +20,7 @@ var (
 var (
 	ErrModelNameRequired         = errors.New("model name is required")
 	ErrModelNameDuplicate        = errors.New("model name is declared more than once in the container")
+	ErrModelNameInvalid          = errors.New("model name must be one path component of letters, digits, '.', '_' or '-' (it becomes a directory and an env-name suffix)")
 	ErrModelSourceRequired       = errors.New("model source is required")
 	ErrModelSourceNotAbsolute    = errors.New("model source must be an absolute host path")
 	ErrModelSourceNotFound       = errors.New("model source does not exist on the host")

@@ -16,6 +16,7 @@ import "C"
 
 import (
 	"fmt"
+	"runtime"
 	"unsafe"
 
 	"github.com/eminwux/kukeon/internal/errdefs"
@@ -47,9 +48,17 @@ type Config struct {
 type Pool struct{ h *C.kk_ctx }
 type Model struct{ h *C.kk_model }
 
-// wrap maps a negative kk_status onto an errdefs sentinel, the way internal/ctr wraps containerd errors
-// (internal/ctr/container.go:561,586).  kk_last_error is thread-local and cgo keeps the goroutine on its OS thread between the
-// failing call and this read, so no runtime.LockOSThread is needed.
+// call runs one library entry point and maps a negative kk_status onto an errdefs sentinel, the way internal/ctr wraps containerd errors
+// (internal/ctr/container.go:561,586).  kk_last_error is THREAD-local and the Go scheduler may move a goroutine to another OS thread
+// between two cgo calls, so the failing call and the read of its message are bracketed by runtime.LockOSThread (round-1 review: without
+// it the text could belong to another goroutine's failure).
+func call(f func() C.int) error {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	return wrap(f())
+}
+
+// wrap must run on the OS thread that made the failing call: only call() uses it.
 func wrap(rc C.int) error {
 	if rc == C.KK_OK {
 		return nil
@@ -85,13 +94,13 @@ func Open(cfg Config) (*Pool, error) {
 	c.staging_buffer_bytes = C.uint64_t(cfg.StagingBufferBytes)
 	c.n_reader_threads = C.uint32_t(cfg.ReaderThreads)
 	p := &Pool{}
-	if err := wrap(C.kk_open(&c, &p.h)); err != nil {
+	if err := call(func() C.int { return C.kk_open(&c, &p.h) }); err != nil {
 		return nil, err
 	}
 	return p, nil
 }
 
-func (p *Pool) Close() error { return wrap(C.kk_close(p.h)) }
+func (p *Pool) Close() error { return call(func() C.int { return C.kk_close(p.h) }) }
 
 // TensorMeta is one record of the tensor index (kk_tensor_meta).
 type TensorMeta struct {
@@ -109,7 +118,7 @@ func Index(path string) ([]TensorMeta, error) {
 	defer C.free(unsafe.Pointer(cs))
 	var recs *C.kk_tensor_meta
 	var n C.size_t
-	if err := wrap(C.kk_index(nil, cs, &recs, &n)); err != nil {
+	if err := call(func() C.int { return C.kk_index(nil, cs, &recs, &n) }); err != nil {
 		return nil, err
 	}
 	defer C.kk_free_index(recs)
@@ -133,11 +142,11 @@ func Plan(path string, mode Mode, flags uint32, gpus int) ([]byte, error) {
 	o.mode = C.int32_t(mode)
 	o.flags = C.uint32_t(flags)
 	var need C.size_t
-	if err := wrap(C.kk_plan_describe(nil, cs, &o, C.int(gpus), 0, nil, 0, &need)); err != nil {
+	if err := call(func() C.int { return C.kk_plan_describe(nil, cs, &o, C.int(gpus), 0, nil, 0, &need) }); err != nil {
 		return nil, err
 	}
 	buf := make([]byte, need)
-	if err := wrap(C.kk_plan_describe(nil, cs, &o, C.int(gpus), 0, (*C.char)(unsafe.Pointer(&buf[0])), need, nil)); err != nil {
+	if err := call(func() C.int { return C.kk_plan_describe(nil, cs, &o, C.int(gpus), 0, (*C.char)(unsafe.Pointer(&buf[0])), need, nil) }); err != nil {
 		return nil, err
 	}
 	return buf[:need-1], nil
@@ -153,24 +162,24 @@ func (p *Pool) Load(path string, mode Mode, flags uint32) (*Model, error) {
 	o.fanout = C.KK_FANOUT_P2P
 	o.flags = C.uint32_t(flags)
 	m := &Model{}
-	if err := wrap(C.kk_load_ex(p.h, cs, &o, &m.h)); err != nil {
+	if err := call(func() C.int { return C.kk_load_ex(p.h, cs, &o, &m.h) }); err != nil {
 		return nil, err
 	}
 	return m, nil
 }
 
-func (m *Model) Acquire() error { return wrap(C.kk_acquire(m.h)) }
-func (m *Model) Release() error { return wrap(C.kk_release(m.h)) }
+func (m *Model) Acquire() error { return call(func() C.int { return C.kk_acquire(m.h) }) }
+func (m *Model) Release() error { return call(func() C.int { return C.kk_release(m.h) }) }
 
 // Export returns the 64-byte CUDA IPC handle and the pool manifest JSON for one device (what Mount stages for the container).
 func (m *Model) Export(device int) ([]byte, []byte, error) {
 	var need C.size_t
-	if err := wrap(C.kk_export_size(m.h, C.int(device), &need)); err != nil {
+	if err := call(func() C.int { return C.kk_export_size(m.h, C.int(device), &need) }); err != nil {
 		return nil, nil, err
 	}
 	handle := make([]byte, C.KK_IPC_HANDLE_BYTES)
 	manifest := make([]byte, need)
-	if err := wrap(C.kk_export(m.h, C.int(device), unsafe.Pointer(&handle[0]), (*C.char)(unsafe.Pointer(&manifest[0])), need)); err != nil {
+	if err := call(func() C.int { return C.kk_export(m.h, C.int(device), unsafe.Pointer(&handle[0]), (*C.char)(unsafe.Pointer(&manifest[0])), need) }); err != nil {
 		return nil, nil, err
 	}
 	return handle, manifest[:need-1], nil

@@ -238,8 +238,11 @@ inline MountSpec Mount(const gpupool::Model& m, int device, const std::string& c
   detail::atomic_write(s.host_dir + "/manifest.json", ex.second, 0644);
   detail::atomic_write(s.host_dir + "/ipc.handle", ex.first, 0640);
   s.mounts.push_back({"/run/kukeon/gpupool", "bind", s.host_dir, {"rbind", "ro"}});
+  // the GPU is named by UUID / PCI bus id (kk_device_identity): the daemon's CUDA ordinal means nothing inside the container
+  char bus[32] = "", uuid[64] = "";
+  if (kk_device_identity(device, bus, sizeof bus, uuid, sizeof uuid) != KK_OK) throw errdefs::ErrGPUPoolLoad(KK_ECUDA, std::string("kk_device_identity: ") + kk_last_error());
   s.env = {"KUKEON_GPUPOOL_MANIFEST=/run/kukeon/gpupool/manifest.json", "KUKEON_GPUPOOL_IPC_HANDLE=/run/kukeon/gpupool/ipc.handle",
-           "KUKEON_GPUPOOL_DEVICE=" + std::to_string(device)};
+           std::string("KUKEON_GPUPOOL_DEVICE_UUID=") + uuid, std::string("KUKEON_GPUPOOL_PCI_BUS_ID=") + bus};
   return s;
 }
 

@@ -102,6 +102,11 @@ typedef enum kk_fanout {
 #define KK_CFG_PEER_ALL 0x8u       /* kk_open enables peer access from the context's devices to EVERY visible GPU (one-rank-
                                       per-GPU deployments: moves the one-time peer setup out of the first kk_peer_attach) */
 #define KK_CFG_NO_NUMA_PIN 0x4u    /* do not bind reader threads / pinned slots to the device's NUMA node */
+#define KK_CFG_VMM_POOLS 0x10u     /* allocate pools with the driver's virtual-memory API (cuMemCreate) instead of cudaMalloc.  Such a pool is exported as a
+                                      POSIX file descriptor (kk_export_fd) which the consumer maps READ-ONLY (kk_import_fd): agent cells that share one
+                                      HBM copy can then not overwrite it.  A cudaIpcMemHandle (kk_export) always maps read-write in the opener — use VMM
+                                      pools whenever the cells mounting a model do not trust each other.  Not available for one-process-per-GPU
+                                      fan-out (kk_peer_attach takes IPC handles) */
 
 /* kk_load_opts.flags */
 #define KK_LOAD_GPT2_CONV1D_T 0x1u /* transpose HF GPT-2 Conv1D weights ([in,out] -> [out,in]) while loading */
@@ -240,8 +245,23 @@ int kk_model_tensor(kk_model* m, size_t i, kk_tensor_meta* out);
  * required != NULL, the needed size.  Either output may be NULL to skip it. */
 int kk_export(kk_model* m, int device, void* ipc_handle_64B, char* manifest_json, size_t cap);
 int kk_export_size(kk_model* m, int device, size_t* required);
+/* KK_CFG_VMM_POOLS only: a new file descriptor for `device`'s pool (the caller owns it: pass it over a Unix socket with SCM_RIGHTS, then close it) and
+ * the mapped size.  KK_EUNSUPPORTED for cudaMalloc pools.  Consumer side, possibly another process that received the fd: kk_import_fd maps the
+ * allocation on CUDA device `device` of THAT process — read-only when flags has KK_IMPORT_READONLY — and returns its address; kk_import_close
+ * unmaps it.  Neither needs a kk_ctx. */
+#define KK_IMPORT_READONLY 0x1u
+typedef struct kk_import kk_import;
+int kk_export_fd(kk_model* m, int device, int* fd_out, uint64_t* mapped_bytes);
+int kk_import_fd(int fd, int device, uint64_t mapped_bytes, uint32_t flags, void** dev_ptr, kk_import** out);
+int kk_import_close(kk_import* im);
 /* Same-process consumers: raw device pointer of the pool. */
 int kk_pool_ptr(kk_model* m, int device, void** dev_ptr, uint64_t* nbytes);
+
+/* Stable identity of a CUDA device, for everything that leaves this process: CUDA ordinals follow CUDA_DEVICE_ORDER / CUDA_VISIBLE_DEVICES and mean
+ * nothing in another process or container, and they are NOT the minor number of /dev/nvidia<N>.  pci_bus_id receives "dddd:bb:dd.f" (>= 16 bytes),
+ * uuid receives "GPU-xxxxxxxx-xxxx-xxxx-xxxx-xxxxxxxxxxxx" (>= 41 bytes).  Either may be NULL.  The host side maps the bus id to the device node through
+ * /proc/driver/nvidia/gpus/<bus id>/information ("Device Minor"), internal/ctr's WithGPUWeights exports the UUID to the container. */
+int kk_device_identity(int device, char* pci_bus_id, size_t pci_cap, char* uuid, size_t uuid_cap);
 
 /* ---- Session refcount ------------------------------------------------------------------------ */
 int kk_acquire(kk_model* m);

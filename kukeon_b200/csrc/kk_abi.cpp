@@ -298,12 +298,57 @@ int kk_export(kk_model* m, int device, void* ipc_handle_64B, char* manifest_json
     }
     if (ipc_handle_64B) {
       if (m->nvls) kk::fail(KK_EUNSUPPORTED, "pools of a KK_FANOUT_NVLS model are VMM allocations: there is no cudaIpcMemHandle for them (export the manifest only, or load with KK_FANOUT_P2P)");
+      if (!m->vmm.empty()) kk::fail(KK_EUNSUPPORTED, "pools of a KK_CFG_VMM_POOLS context are VMM allocations: there is no cudaIpcMemHandle for them, export the file descriptor (kk_export_fd)");
       KK_CUDA(cudaSetDevice(device));
       cudaIpcMemHandle_t h;
       KK_CUDA(cudaIpcGetMemHandle(&h, m->pools[(size_t)li]));
       static_assert(sizeof h == KK_IPC_HANDLE_BYTES, "ipc handle size");
       memcpy(ipc_handle_64B, &h, sizeof h);
     }
+  });
+}
+
+struct kk_import {
+  kk::VmmImport im;
+};
+
+int kk_export_fd(kk_model* m, int device, int* fd_out, uint64_t* mapped_bytes) {
+  return guard([&] {
+    need(m, "model");
+    need(fd_out, "fd_out");
+    *fd_out = -1;
+    int li = kk::model_local_device(m, device);
+    if (m->vmm.size() <= (size_t)li || !m->vmm[(size_t)li]) kk::fail(KK_EUNSUPPORTED, "this pool is a cudaMalloc allocation: open the context with KK_CFG_VMM_POOLS to export file descriptors");
+    *fd_out = m->vmm[(size_t)li]->export_fd();
+    if (mapped_bytes) *mapped_bytes = m->vmm[(size_t)li]->bytes();
+  });
+}
+
+int kk_import_fd(int fd, int device, uint64_t mapped_bytes, uint32_t flags, void** dev_ptr, kk_import** out) {
+  return guard([&] {
+    need(dev_ptr, "dev_ptr");
+    need(out, "out");
+    *dev_ptr = nullptr;
+    *out = nullptr;
+    if (fd < 0 || mapped_bytes == 0) kk::fail(KK_EINVAL, "bad fd / size");
+    if (flags & ~KK_IMPORT_READONLY) kk::fail(KK_EINVAL, "unknown import flags 0x%x", flags);
+    kk_import* im = new kk_import;
+    try {
+      im->im = kk::vmm_import_fd(fd, device, mapped_bytes, (flags & KK_IMPORT_READONLY) != 0);
+    } catch (...) {
+      delete im;
+      throw;
+    }
+    *dev_ptr = (void*)(uintptr_t)im->im.va;
+    *out = im;
+  });
+}
+
+int kk_import_close(kk_import* im) {
+  return guard([&] {
+    need(im, "import");
+    kk::vmm_import_close(im->im);
+    delete im;
   });
 }
 
@@ -437,6 +482,28 @@ int kk_probe_hbm(kk_ctx* ctx, int device, int kind, uint64_t nbytes, float* ms) 
     }
     KK_CUDA(cudaStreamSynchronize(d->stream));
     KK_CUDA(cudaEventElapsedTime(ms, e0.e, e1.e));
+  });
+}
+
+int kk_device_identity(int device, char* pci_bus_id, size_t pci_cap, char* uuid, size_t uuid_cap) {
+  return guard([&] {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); kk::fail(KK_ECUDA, "no usable CUDA device"); }
+    if (device < 0 || device >= count) kk::fail(KK_EINVAL, "device %d out of range (0..%d)", device, count - 1);
+    if (pci_bus_id) {
+      if (pci_cap < 16) kk::fail(KK_ERANGE, "pci_bus_id needs 16 bytes");
+      KK_CUDA(cudaDeviceGetPCIBusId(pci_bus_id, (int)pci_cap, device));
+      for (char* c = pci_bus_id; *c; ++c)
+        if (*c >= 'A' && *c <= 'F') *c = (char)(*c - 'A' + 'a');  // /proc/driver/nvidia/gpus/ uses lower case
+    }
+    if (uuid) {
+      if (uuid_cap < 41) kk::fail(KK_ERANGE, "uuid needs 41 bytes");
+      cudaDeviceProp pr;
+      KK_CUDA(cudaGetDeviceProperties(&pr, device));
+      const unsigned char* b = (const unsigned char*)pr.uuid.bytes;
+      snprintf(uuid, uuid_cap, "GPU-%02x%02x%02x%02x-%02x%02x-%02x%02x-%02x%02x-%02x%02x%02x%02x%02x%02x", b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7], b[8],
+               b[9], b[10], b[11], b[12], b[13], b[14], b[15]);
+    }
   });
 }
 

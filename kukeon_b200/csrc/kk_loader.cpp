@@ -636,13 +636,14 @@ void destroy_model(kk_model* m) {
     Device& d = c->devs[(size_t)m->dev_idx[i]];
     cudaSetDevice(d.ordinal);
     if (m->pools[i]) {
-      if (!m->nvls) cudaFree(m->pools[i]);  // NVLS pools are unmapped / released by ~NvlsPools below
+      if (!m->nvls && m->vmm.empty()) cudaFree(m->pools[i]);  // NVLS / VMM pools are unmapped and released by their owners below
       std::lock_guard<std::mutex> g(c->mu);  // model_load checks the budget under the same lock
       d.pool_in_use -= m->pool_bytes[i];
     }
     if (i < m->d_segs.size() && m->d_segs[i]) cudaFree(m->d_segs[i]);
   }
   m->nvls.reset();
+  m->vmm.clear();
   delete m;
 }
 
@@ -903,8 +904,31 @@ kk_model* model_load(kk_ctx* c, const std::string& path, const kk_load_opts& opt
         m->pool_bytes[li] = pb;
       }
       cudaError_t e = cudaSuccess;
-      if (m->nvls) m->pools[li] = m->nvls->pool(li);  // already allocated, bound and mapped
-      else e = cudaMalloc((void**)&m->pools[li], pb);
+      if (m->nvls) {
+        m->pools[li] = m->nvls->pool(li);  // already allocated, bound and mapped
+      } else if (c->cfg.flags & KK_CFG_VMM_POOLS) {
+        // cuMemCreate memory: exported as a POSIX fd (kk_export_fd) that another process maps READ-ONLY, which a cudaIpcMemHandle cannot offer.
+        // Mapped read-write here for this device and, in a peer-enabled context, for the other devices (fan-out stores land in it).
+        std::vector<int> acc;
+        if (c->peer_ok)
+          for (auto& dv : c->devs) acc.push_back(dv.ordinal);
+        if (m->vmm.size() < m->dev_idx.size()) m->vmm.resize(m->dev_idx.size());
+        try {
+          m->vmm[li].reset(new VmmAlloc);
+          m->vmm[li]->create(d.ordinal, pb, acc);
+          m->pools[li] = m->vmm[li]->ptr();
+        } catch (...) {
+          m->vmm[li].reset();
+          std::lock_guard<std::mutex> g(c->mu);
+          d.pool_in_use -= pb;
+          m->pool_bytes[li] = 0;
+          throw;
+        }
+      } else {
+        // whole 2 MiB multiples: the driver sub-allocates smaller requests out of shared 2 MiB blocks, and an IPC handle maps the whole block —
+        // a pool that owns its blocks outright cannot expose a neighbouring allocation through its handle (round-1 review)
+        e = cudaMalloc((void**)&m->pools[li], align_up(pb ? pb : 1, 2u << 20));
+      }
       if (e != cudaSuccess) {
         cudaGetLastError();
         m->pools[li] = nullptr;
@@ -1148,8 +1172,24 @@ std::string model_manifest(kk_model* m, int li) {
   const auto& pl = m->plan.placement_of_part(m->local_parts[(size_t)li]);
   const auto& T = m->plan.index.tensors;
   std::ostringstream o;
-  o << "{\"apiVersion\":\"kukeon.gpupool/v1\",\"kind\":\"PoolManifest\",\"device\":" << m->ctx->devs[(size_t)m->dev_idx[(size_t)li]].ordinal
-    << ",\"poolBytes\":" << m->pool_bytes[(size_t)li] << ",\"mode\":" << m->plan.mode << ",\"format\":\"" << m->plan.index.format
+  // "device" is the ordinal in THIS process (diagnostics only); a consumer in another process or container finds the GPU by its UUID / PCI bus id
+  const int ordinal = m->ctx->devs[(size_t)m->dev_idx[(size_t)li]].ordinal;
+  char bus[32] = "", uuid[48] = "";
+  {
+    cudaDeviceProp pr;
+    if (cudaDeviceGetPCIBusId(bus, (int)sizeof bus, ordinal) != cudaSuccess) { cudaGetLastError(); bus[0] = 0; }
+    for (char* c = bus; *c; ++c)
+      if (*c >= 'A' && *c <= 'F') *c = (char)(*c - 'A' + 'a');
+    if (cudaGetDeviceProperties(&pr, ordinal) == cudaSuccess) {
+      const unsigned char* b = (const unsigned char*)pr.uuid.bytes;
+      snprintf(uuid, sizeof uuid, "GPU-%02x%02x%02x%02x-%02x%02x-%02x%02x-%02x%02x-%02x%02x%02x%02x%02x%02x", b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7],
+               b[8], b[9], b[10], b[11], b[12], b[13], b[14], b[15]);
+    } else {
+      cudaGetLastError();
+    }
+  }
+  o << "{\"apiVersion\":\"kukeon.gpupool/v1\",\"kind\":\"PoolManifest\",\"device\":" << ordinal << ",\"deviceUUID\":\"" << uuid << "\",\"pciBusId\":\"" << bus
+    << "\",\"poolBytes\":" << m->pool_bytes[(size_t)li] << ",\"mode\":" << m->plan.mode << ",\"format\":\"" << m->plan.index.format
     << "\",\"align\":" << KK_POOL_ALIGN << ",\"tensors\":[";
   for (size_t i = 0; i < T.size(); ++i) {
     const DtypeInfo* di = dtype_info(pl[i].dtype);

@@ -14,6 +14,7 @@
 #include "kk_kernels.cuh"
 #include "kk_nvls.hpp"
 #include "kk_plan.hpp"
+#include "kk_vmm.hpp"
 
 namespace kk {
 
@@ -108,6 +109,8 @@ struct kk_model {
   // KK_FANOUT_NVLS (one process, >= 2 devices): the pools are VMM allocations bound to one multicast object; pools[i] then
   // aliases nvls->pool(i) and must not be cudaFree'd
   std::unique_ptr<kk::NvlsPools> nvls;
+  // KK_CFG_VMM_POOLS: pools[i] aliases vmm[i]->ptr() (cuMemCreate memory, exportable as a POSIX fd and mappable read-only elsewhere); never cudaFree'd
+  std::vector<std::unique_ptr<kk::VmmAlloc>> vmm;
   // state
   std::mutex op_mu;  // serialises the data-moving calls on ONE model (kk_load_part, kk_convert_local, kk_*_resident) against each other
   std::mutex peer_mu;  // guards peer_slice_ptr[]: stage 1 of a PULL load never reads it, so slice buffers may be attached WHILE kk_load_part runs

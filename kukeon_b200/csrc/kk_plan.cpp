@@ -263,11 +263,13 @@ uint32_t scatter_slice_dim(const TensorRec& t, int n_parts) {
   if (t.shape[0] == 0 || t.shape[1] == 0) return kNoSlice;  // empty tensors are "replicated" (nothing to slice)
   if (t.shape[dim] % (uint64_t)n_parts != 0) return kNoSlice;
   const DtypeInfo* di = dtype_info(t.dtype);
+  // sub-byte safetensors dtypes (F4: 2 elements per byte, F6: 4 per 3 bytes) FIRST — their table rows also have block_elems > 1, so they used to
+  // fall into the block-quantised branch below and a row of cols * bits not divisible by 8 was sliced mid-byte: never slice them
+  if (t.dtype == KK_F4 || t.dtype == KK_F6_E2M3 || t.dtype == KK_F6_E3M2) return kNoSlice;
+  if (di->block_bytes == 0) return kNoSlice;
   if (di->block_elems > 1) {
     // block-quantised rows: dim-0 slices stay whole rows of blocks; dim-1 slices would cut blocks.
     if (dim == 1) return kNoSlice;
-  } else if (di->block_bytes == 0 || (t.dtype < 32 && (t.dtype == KK_F4 || t.dtype == KK_F6_E2M3 || t.dtype == KK_F6_E3M2))) {
-    return kNoSlice;
   }
   return dim;
 }

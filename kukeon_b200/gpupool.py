@@ -22,7 +22,8 @@ KK_POOL_ALIGN = 256
 
 MODE_SINGLE, MODE_BROADCAST, MODE_SCATTER = 0, 1, 2
 FANOUT_P2P, FANOUT_NVLS, FANOUT_NONE, FANOUT_RAW, FANOUT_PULL = 0, 1, 2, 3, 4
-CFG_ZEROCOPY, CFG_NO_PEER_ACCESS, CFG_NO_NUMA_PIN, CFG_PEER_ALL = 0x1, 0x2, 0x4, 0x8
+CFG_ZEROCOPY, CFG_NO_PEER_ACCESS, CFG_NO_NUMA_PIN, CFG_PEER_ALL, CFG_VMM_POOLS = 0x1, 0x2, 0x4, 0x8, 0x10
+IMPORT_READONLY = 0x1
 LOAD_GPT2_CONV1D_T, LOAD_KEEP_F32, LOAD_DEFER, LOAD_SCATTER_EXCHANGE, LOAD_F8_TO_BF16 = 0x1, 0x2, 0x4, 0x8, 0x10
 BUF_POOL, BUF_RAW, BUF_POOL_PTR, BUF_SLICE, BUF_SLICE_PTR = 0, 1, 2, 3, 4
 PROBE_WRITE, PROBE_COPY = 0, 1
@@ -103,7 +104,8 @@ ABI_SYMBOLS = [
     "kk_export_buffer", "kk_peer_attach_buffer", "kk_convert_local",
     "kk_model_get_info", "kk_placements", "kk_model_tensor", "kk_export", "kk_export_size", "kk_pool_ptr",
     "kk_acquire", "kk_release", "kk_stats", "kk_read", "kk_checksum", "kk_stage_resident", "kk_convert_resident",
-    "kk_unstage_resident", "kk_probe_hbm", "kk_probe_peer",
+    "kk_unstage_resident", "kk_probe_hbm", "kk_probe_peer", "kk_device_identity",
+    "kk_export_fd", "kk_import_fd", "kk_import_close",
 ]
 
 
@@ -131,6 +133,10 @@ def lib():
     L.kk_close.argtypes = [vp]
     L.kk_probe_hbm.argtypes = [vp, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_float)]
     L.kk_probe_peer.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_float)]
+    L.kk_device_identity.argtypes = [C.c_int, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+    L.kk_export_fd.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
+    L.kk_import_fd.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.POINTER(vp), C.POINTER(vp)]
+    L.kk_import_close.argtypes = [vp]
     L.kk_index.argtypes = [vp, C.c_char_p, C.POINTER(C.POINTER(KKTensorMeta)), C.POINTER(C.c_size_t)]
     L.kk_free_index.argtypes = [C.POINTER(KKTensorMeta)]
     L.kk_index_shard.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
@@ -164,6 +170,34 @@ def lib():
         raise ImportError(f"{p}: ABI version {L.kk_abi_version()} != 1")
     _lib = L
     return L
+
+
+class ImportedPool:
+    """Consumer side of a VMM pool: the allocation behind `fd` mapped on CUDA device `device` of THIS process, read-only by default
+    (stores through the mapping fault here and never reach the exporter's weights)."""
+
+    def __init__(self, fd: int, device: int, mapped_bytes: int, readonly: bool = True):
+        p, h = C.c_void_p(), C.c_void_p()
+        _check(lib().kk_import_fd(fd, device, mapped_bytes, IMPORT_READONLY if readonly else 0, C.byref(p), C.byref(h)))
+        self.ptr, self._h, self.nbytes = int(p.value or 0), h, mapped_bytes
+
+    def close(self) -> None:
+        if self._h:
+            _check(lib().kk_import_close(self._h))
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def device_identity(ordinal: int) -> dict:
+    """{"pci_bus_id": "0000:1b:00.0", "uuid": "GPU-..."} of CUDA device `ordinal` in this process (kk_device_identity)."""
+    bus, uuid = C.create_string_buffer(32), C.create_string_buffer(64)
+    _check(lib().kk_device_identity(ordinal, bus, len(bus), uuid, len(uuid)))
+    return {"pci_bus_id": bus.value.decode(), "uuid": uuid.value.decode()}
 
 
 def _check(rc: int) -> None:
@@ -282,6 +316,13 @@ class Model:
         man = C.create_string_buffer(need.value)
         _check(lib().kk_export(self._h, device, None, man, need.value))
         return json.loads(man.value.decode("utf-8"))
+
+    def export_fd(self, device: int) -> tuple[int, int]:
+        """(file descriptor, mapped bytes) of `device`'s pool — KK_CFG_VMM_POOLS contexts only.  The caller owns the fd: send it to the consumer
+        over a Unix socket (socket.send_fds) and close it."""
+        fd, n = C.c_int(-1), C.c_uint64()
+        _check(lib().kk_export_fd(self._h, device, C.byref(fd), C.byref(n)))
+        return int(fd.value), int(n.value)
 
     def pool_ptr(self, device: int) -> tuple[int, int]:
         p = C.c_void_p()

@@ -93,6 +93,16 @@ class RegistryError(RuntimeError):
     pass
 
 
+def _is_staged_dir(path: str) -> bool:
+    """Directories Mount stages: <container>/gpupool (unnamed model) or <container>/gpupool/<name> (models[].name, validated to a single
+    path component by schema.validate_models).  Anything else in a registry file is not ours to delete."""
+    p = os.path.normpath(path)
+    if os.path.basename(p) == "gpupool":
+        return True
+    parent = os.path.dirname(p)
+    return os.path.basename(parent) == "gpupool" and os.path.basename(p) not in ("", ".", "..")
+
+
 class PoolRegistry:
     def __init__(self, run_path: str, epoch: Optional[str] = None):
         self.run_path = run_path
@@ -135,7 +145,7 @@ class PoolRegistry:
         stale = list(prior.values())
         for e in stale:
             for m in e.mounts:
-                if os.path.basename(os.path.normpath(m)) == "gpupool":  # only ever delete directories we staged
+                if _is_staged_dir(m):  # only ever delete directories we staged
                     shutil.rmtree(m, ignore_errors=True)
         self.entries = {}
         self._save()

@@ -20,6 +20,7 @@ the offending index and value, `"%w (model[%d] source %q)"`.  Nothing here touch
 from __future__ import annotations
 
 import os
+import re
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
@@ -30,10 +31,14 @@ MODES = {"": gpupool.MODE_SINGLE, "single": gpupool.MODE_SINGLE, "broadcast": gp
 OPTION_FLAGS = {"gpt2Conv1dTranspose": gpupool.LOAD_GPT2_CONV1D_T, "keepF32": gpupool.LOAD_KEEP_F32, "f8ToBf16": gpupool.LOAD_F8_TO_BF16}
 
 
+MODEL_NAME_RE = re.compile(r"^[A-Za-z0-9][A-Za-z0-9._-]*$")
+
+
 class Err:
     """Sentinels, worded like internal/errdefs/errdefs.go's volume block."""
     ModelNameRequired = "model name is required"
     ModelNameDuplicate = "model name is declared more than once in the container"
+    ModelNameInvalid = "model name must be one path component of letters, digits, '.', '_' or '-' (it becomes a directory and an env-name suffix)"
     ModelSourceRequired = "model source is required"
     ModelSourceNotAbsolute = "model source must be an absolute host path"
     ModelSourceNotFound = "model source does not exist on the host"
@@ -73,6 +78,10 @@ def validate_models(models: Optional[List[dict]], stat=os.stat) -> List[ModelSpe
         name = str(m.get("name") or "").strip()
         if not name:
             raise SchemaError(Err.ModelNameRequired, f"model[{i}]")
+        if not MODEL_NAME_RE.match(name) or name in (".", ".."):
+            # the name is joined into <cell dir>/gpupool/<name> on the host and into the mount target in the container: "../x", "a/b" or a NUL
+            # would let a manifest write outside the cell directory.  Refused here, before anything is loaded or a refcount is taken.
+            raise SchemaError(Err.ModelNameInvalid, f"model[{i}] name {_q(name)}")
         if name in seen:
             raise SchemaError(Err.ModelNameDuplicate, f"model[{i}] name {_q(name)}")
         seen.add(name)

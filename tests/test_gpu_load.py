@@ -266,9 +266,18 @@ def test_eight_concurrent_sessions_share_one_load(pool, tmp_path):
 _CHILD = r'''
 import sys, json, numpy as np
 from cuda.bindings import runtime as cudart
-hpath, off, n = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+hpath, off, n, want_uuid = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
 h = cudart.cudaIpcMemHandle_t(); h.reserved = open(hpath, "rb").read()
-err, = cudart.cudaSetDevice(0); assert err == 0, err
+# the agent finds the GPU by the UUID the daemon exported (KUKEON_GPUPOOL_DEVICE_UUID), not by the daemon's ordinal
+err, cnt = cudart.cudaGetDeviceCount(); assert err == 0, err
+dev = None
+for i in range(cnt):
+    err, pr = cudart.cudaGetDeviceProperties(i); assert err == 0, err
+    b = bytes(pr.uuid.bytes)
+    u = "GPU-%s-%s-%s-%s-%s" % (b[0:4].hex(), b[4:6].hex(), b[6:8].hex(), b[8:10].hex(), b[10:16].hex())
+    if u == want_uuid: dev = i
+assert dev is not None, ("no device with uuid", want_uuid)
+err, = cudart.cudaSetDevice(dev); assert err == 0, err
 err, ptr = cudart.cudaIpcOpenMemHandle(h, cudart.cudaIpcMemLazyEnablePeerAccess); assert err == 0, err
 buf = np.empty(n, np.uint8)
 err, = cudart.cudaMemcpy(buf.ctypes.data, ptr + off, n, cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost); assert err == 0, err
@@ -291,9 +300,17 @@ def test_mount_exports_manifest_and_ipc_handle_to_another_process(pool, tmp_path
             assert (g["name"], g["dtype"], g["shape"], g["offset"], g["nbytes"]) == (w["name"], w["dtype"], w["shape"], w["pool_offset"], w["nbytes"])
         assert spec.mounts == [{"destination": "/run/kukeon/gpupool", "type": "bind", "source": spec.host_dir, "options": ["rbind", "ro"]}]
         assert any(e.startswith("KUKEON_GPUPOOL_MANIFEST=") for e in spec.env)
+        ident = gpupool.device_identity(0)
+        env = dict(e.split("=", 1) for e in spec.env)
+        assert env["KUKEON_GPUPOOL_DEVICE_UUID"] == ident["uuid"] == man["deviceUUID"] and ident["uuid"].startswith("GPU-") and len(ident["uuid"]) == 40
+        assert env["KUKEON_GPUPOOL_PCI_BUS_ID"] == ident["pci_bus_id"] == man["pciBusId"]
+        if os.path.isdir(modelhub.NVIDIA_PROC_GPUS):  # device node from the driver's table, not from the ordinal
+            minor = modelhub.device_minor(ident["pci_bus_id"])
+            wd = modelhub.Mount(m, 0, str(tmp_path / "cell" / "container2"), with_devices=True)
+            assert f"/dev/nvidia{minor}" in [d["path"] for d in wd.devices] and "/dev/nvidiactl" in [d["path"] for d in wd.devices]
         assert os.path.getsize(os.path.join(spec.host_dir, "ipc.handle")) == 64
         t = want[7]  # h.bf16.big
-        r = subprocess.run([sys.executable, "-c", _CHILD, os.path.join(spec.host_dir, "ipc.handle"), str(t["pool_offset"]), "4096"],
+        r = subprocess.run([sys.executable, "-c", _CHILD, os.path.join(spec.host_dir, "ipc.handle"), str(t["pool_offset"]), "4096", ident["uuid"]],
                            capture_output=True, text=True, timeout=120)
         assert r.returncode == 0, r.stderr[-2000:]
         exp, _ = oracle.expected_pool(shards, recs)

@@ -346,3 +346,20 @@ def test_scatter_of_empty_2d_tensors_does_not_divide_by_zero(native, tmp_path):
         assert lay["model.layers.0.self_attn.q_proj.weight"]["slice_dim"] is None and lay["model.layers.0.self_attn.q_proj.weight"]["nbytes"] == 0
         assert lay["model.layers.0.mlp.down_proj.weight"]["slice_dim"] == 1
     run_case(p, mode=gpupool.MODE_SCATTER, n_parts=4, chunk=1 * MB)
+
+
+def test_scatter_never_slices_sub_byte_dtypes(native, tmp_path):
+    """an F4 q_proj.weight of shape [4, 3] (6 bytes) in SCATTER with n = 2 was sliced along dim 0 as if rows were byte aligned (two
+    2-byte slices at +0 and +2 instead of 3-byte rows): the sub-byte check sat in a dead branch.  F4 / F6 tensors are replicated whole."""
+    p = str(tmp_path / "f4.safetensors")
+    hdr = {"model.layers.0.self_attn.q_proj.weight": {"dtype": "F4", "shape": [4, 3], "data_offsets": [0, 6]},
+           "model.layers.0.self_attn.k_proj.weight": {"dtype": "F6_E2M3", "shape": [4, 4], "data_offsets": [6, 18]},
+           "model.layers.0.self_attn.v_proj.weight": {"dtype": "BF16", "shape": [4, 4], "data_offsets": [18, 50]}}
+    helpers.write_raw_safetensors(p, hdr, bytes(range(50)))
+    plan = gpupool.plan_describe(p, mode=gpupool.MODE_SCATTER, n_parts=2, chunk_bytes=1 * MB)
+    for g in range(2):
+        lay = {t["name"]: t for t in plan["layouts"][g]["tensors"]}
+        assert lay["model.layers.0.self_attn.q_proj.weight"]["slice_dim"] is None and lay["model.layers.0.self_attn.q_proj.weight"]["nbytes"] == 6
+        assert lay["model.layers.0.self_attn.k_proj.weight"]["slice_dim"] is None and lay["model.layers.0.self_attn.k_proj.weight"]["nbytes"] == 12
+        assert lay["model.layers.0.self_attn.v_proj.weight"]["slice_dim"] == 0 and lay["model.layers.0.self_attn.v_proj.weight"]["nbytes"] == 16
+    run_case(p, mode=gpupool.MODE_SCATTER, n_parts=2, chunk=1 * MB)

@@ -59,6 +59,27 @@ def test_restarted_daemon_invalidates_pools_of_the_previous_instance(tmp_path):
     assert new.entries == {} and json.load(open(os.path.join(run, registry.FILE_NAME)))["epoch"] == "boot:2:999"
 
 
+def test_restart_also_removes_the_staged_directories_of_named_models(tmp_path):
+    """Multi-model layout: Mount stages into <container>/gpupool/<name>.  After a daemon restart those directories — dead ipc.handle and
+    manifest.json — must go too (reconcile only matched a basename of exactly 'gpupool'); a look-alike elsewhere stays."""
+    run = str(tmp_path / "run")
+    shards = make_shards(tmp_path)
+    named = tmp_path / "cell" / "agent" / "gpupool" / "llama"
+    os.makedirs(named)
+    (named / "ipc.handle").write_bytes(b"\0" * 64)
+    sibling = tmp_path / "cell" / "agent" / "gpupool" / "other-model"
+    os.makedirs(sibling)
+    lookalike = tmp_path / "cell" / "agent" / "data" / "llama"
+    os.makedirs(lookalike)
+    old = registry.PoolRegistry(run, epoch="boot:1:100")
+    old.reconcile()
+    old.record("k1", "/models/a", 1, 1, 2, [0], shards, mount_dir=str(named))
+    old.record("k2", "/models/b", 1, 1, 2, [0], shards, mount_dir=str(lookalike))
+    new = registry.PoolRegistry(run, epoch="boot:2:999")
+    assert sorted(e.key for e in new.reconcile()) == ["k1", "k2"]
+    assert not named.exists() and sibling.exists() and lookalike.exists()
+
+
 def test_changed_on_disk_and_corrupt_file(tmp_path):
     run = str(tmp_path / "run")
     shards = make_shards(tmp_path)

@@ -8,7 +8,7 @@ import pytest
 import yaml
 
 from kukeon_b200 import cli, gpupool, schema
-from kukeon_b200.schema import Err
+from kukeon_b200.schema import Err, SchemaError, validate_models
 from tools import synth
 
 TD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "testdata")
@@ -63,6 +63,15 @@ def test_duplicate_names_and_index_of_the_offender():
 def load_manifest(models_dir):
     text = open(os.path.join(TD, "cell_with_models.yaml")).read().replace("__MODELS__", models_dir)
     return text, yaml.safe_load(text)
+
+
+@pytest.mark.parametrize("bad", ["../escape", "a/b", "..", ".", ".hidden", "nul\0byte", "sp ace", "semi;colon"])
+def test_model_names_that_could_leave_the_cell_directory_are_refused(bad):
+    """models[].name becomes <cell dir>/gpupool/<name> on the host and a mount target in the container (path traversal): one path
+    component of [A-Za-z0-9._-], refused at validation time — before anything is loaded or a refcount is taken."""
+    with pytest.raises(SchemaError) as ei:
+        validate_models([{"name": bad, "source": "/x"}], stat=lambda p: None)
+    assert ei.value.sentinel == Err.ModelNameInvalid and "model[0]" in str(ei.value)
 
 
 def test_cell_manifest_models_per_container(models_dir):
@@ -140,7 +149,8 @@ class _StubModel:
         self.tag = tag
 
     def export(self, device):
-        return bytes([self.tag]) * 64, {"apiVersion": "kukeon.gpupool/v1", "device": device, "tensors": [{"name": f"w{self.tag}"}]}
+        return bytes([self.tag]) * 64, {"apiVersion": "kukeon.gpupool/v1", "device": device, "deviceUUID": f"GPU-0000000{device}-aaaa-bbbb-cccc-dddddddddddd",
+                                        "pciBusId": f"0000:{0x1b + device:02x}:00.0", "tensors": [{"name": f"w{self.tag}"}]}
 
 
 def test_mount_single_and_named_models(tmp_path):
@@ -148,17 +158,19 @@ def test_mount_single_and_named_models(tmp_path):
     cdir = str(tmp_path / "cell" / "work")
     one = modelhub.Mount(_StubModel(1), 0, cdir)
     assert one.mounts == [{"destination": "/run/kukeon/gpupool", "type": "bind", "source": f"{cdir}/gpupool", "options": ["rbind", "ro"]}]
-    assert one.env == ["KUKEON_GPUPOOL_MANIFEST=/run/kukeon/gpupool/manifest.json", "KUKEON_GPUPOOL_IPC_HANDLE=/run/kukeon/gpupool/ipc.handle", "KUKEON_GPUPOOL_DEVICE=0"]
+    # the container is told WHICH GPU by UUID / PCI bus id — never by the daemon's CUDA ordinal, which means nothing in another process
+    assert one.env == ["KUKEON_GPUPOOL_MANIFEST=/run/kukeon/gpupool/manifest.json", "KUKEON_GPUPOOL_IPC_HANDLE=/run/kukeon/gpupool/ipc.handle",
+                       "KUKEON_GPUPOOL_DEVICE_UUID=GPU-00000000-aaaa-bbbb-cccc-dddddddddddd", "KUKEON_GPUPOOL_PCI_BUS_ID=0000:1b:00.0"]
     assert open(f"{cdir}/gpupool/ipc.handle", "rb").read() == b"\x01" * 64
     a = modelhub.Mount(_StubModel(2), 0, cdir, name="llama-3.8b")
     b = modelhub.Mount(_StubModel(3), 1, cdir, name="gpt2", target="/weights/")
     assert a.mounts[0]["destination"] == "/run/kukeon/gpupool/llama-3.8b" and a.mounts[0]["source"] == f"{cdir}/gpupool/llama-3.8b"
-    assert a.env[0] == "KUKEON_GPUPOOL_MANIFEST_LLAMA_3_8B=/run/kukeon/gpupool/llama-3.8b/manifest.json" and a.env[2] == "KUKEON_GPUPOOL_DEVICE_LLAMA_3_8B=0"
+    assert a.env[0] == "KUKEON_GPUPOOL_MANIFEST_LLAMA_3_8B=/run/kukeon/gpupool/llama-3.8b/manifest.json" and a.env[2] == "KUKEON_GPUPOOL_DEVICE_UUID_LLAMA_3_8B=GPU-00000000-aaaa-bbbb-cccc-dddddddddddd"
     assert b.mounts[0]["destination"] == "/weights/gpt2" and b.env[1] == "KUKEON_GPUPOOL_IPC_HANDLE_GPT2=/weights/gpt2/ipc.handle"
     assert json.load(open(f"{cdir}/gpupool/gpt2/manifest.json"))["tensors"][0]["name"] == "w3"
     assert oct(os.stat(f"{cdir}/gpupool/gpt2/ipc.handle").st_mode & 0o777) == "0o640"
     merged = modelhub.merge_mounts([a, b])
-    assert len(merged.mounts) == 2 and len(merged.env) == 6
+    assert len(merged.mounts) == 2 and len(merged.env) == 8
     with pytest.raises(ValueError, match="same container path"):
         modelhub.merge_mounts([a, a])
     for bad in ("..", "a/b"):
@@ -178,10 +190,21 @@ def test_merge_mounts_deduplicates_device_nodes(tmp_path):
             raise FileNotFoundError(p)
         return SimpleNamespace(st_mode=st_mod.S_IFCHR | 0o666, st_rdev=os.makedev(*table[p]))
 
+    # the driver's own table: CUDA ordinal 0 sits at bus 1b = /dev/nvidia1, ordinal 1 at bus 1c = /dev/nvidia0 (ordinals follow CUDA_DEVICE_ORDER,
+    # minors follow PCI enumeration — ADVICE r1: treating the ordinal as the minor exposes the wrong node)
+    proc = tmp_path / "proc"
+    for bus, minor in (("0000:1b:00.0", 1), ("0000:1c:00.0", 0)):
+        os.makedirs(proc / bus)
+        (proc / bus / "information").write_text(f"Model: \t\t NVIDIA B200\nIRQ:   \t\t 16\nGPU UUID: \t GPU-x\nBus Location: \t {bus}\nDevice Minor: \t {minor}\n")
+    minor_of = lambda bus: modelhub.device_minor(bus, proc_root=str(proc))  # noqa: E731
+    assert minor_of("0000:1B:00.0") == 1
+    with pytest.raises(OSError):
+        minor_of("0000:ff:00.0")
     cdir = str(tmp_path / "c")
-    a = modelhub.Mount(_StubModel(1), 0, cdir, with_devices=True, stat=fake_stat, name="a")
-    b = modelhub.Mount(_StubModel(2), 0, cdir, with_devices=True, stat=fake_stat, name="b")
-    c = modelhub.Mount(_StubModel(3), 1, cdir, with_devices=True, stat=fake_stat, name="c")
+    a = modelhub.Mount(_StubModel(1), 0, cdir, with_devices=True, stat=fake_stat, name="a", minor_of=minor_of)
+    b = modelhub.Mount(_StubModel(2), 0, cdir, with_devices=True, stat=fake_stat, name="b", minor_of=minor_of)
+    c = modelhub.Mount(_StubModel(3), 1, cdir, with_devices=True, stat=fake_stat, name="c", minor_of=minor_of)
+    assert [d["path"] for d in a.devices][-1] == "/dev/nvidia1" and [d["path"] for d in c.devices][-1] == "/dev/nvidia0"
     merged = modelhub.merge_mounts([a, b, c])
-    assert [d["path"] for d in merged.devices] == ["/dev/nvidiactl", "/dev/nvidia-uvm", "/dev/nvidia0", "/dev/nvidia1"]
+    assert [d["path"] for d in merged.devices] == ["/dev/nvidiactl", "/dev/nvidia-uvm", "/dev/nvidia1", "/dev/nvidia0"]
     assert len(merged.device_cgroup) == 4 and all(r["allow"] and r["access"] == "rw" for r in merged.device_cgroup)
