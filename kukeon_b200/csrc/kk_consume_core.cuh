@@ -104,11 +104,70 @@ KK_DQ_DEV void consume_f16(const Dsts& D, uint32_t pay, uint32_t n, uint64_t dst
 // sub-block (l & 7) of block (l >> 3) — so the unpack runs once per four blocks instead of once per block —
 // and __shfl_sync hands every lane the pair of the sub-block its 8 outputs belong to.  The four blocks'
 // dependency chains are independent and fully unrolled (ILP hides the ALU latency with only 2 warps/SMSP).
-template <bool ALIGNED>
+// Expansion of one quad.  FAST: c = -(d*sc) * 2^23 (exact: a power-of-two scaling) lets ONE FMA turn the magic-number float 2^23 + q straight
+// into the rounded product — fma(dsc, 2^23 + q, c) = round(dsc * q), the same single rounding as __fmul_rn(dsc, (float)q) — instead of
+// FADD + FMUL per element (the loop is issue-bound: 70 % issue-active at 0.87 of the copy peak, profiles/r02/prof_Q4_K).  The identity
+// holds bit for bit only for a finite scale that is not negative: with +-inf the FMA sees inf - inf (NaN, where the two-step form gives
+// +-inf for q > 0), and for q = 0 under a negative scale it yields +0 where the product is -0 (visible when the sub-block minimum is 0).
+// Real checkpoints have d >= 0 and finite — every quad takes the fast form — but random bytes are part of the parity tests, so the warp
+// votes once per quad and a quad with any other scale takes the two-step form.
+// Q5: the same quad for Q5_K (176 B: d | dmin | scales[12] | qh[32] | qs[128]) — identical header and scale packing, the nibbles start 32 bytes
+// later and element i of sub-block j takes its fifth bit from bit j of qh[i].
+template <bool ALIGNED, bool FAST, bool Q5>
+KK_DQ_DEV void q4k_expand(const Dsts& D, uint32_t pay, uint32_t b0, uint32_t nb, uint64_t dst_off, int lane, float dsc_j, float dsc_c, float dmn_j) {
+  constexpr uint32_t BB = Q5 ? 176u : KK_Q4K_BLOCK_BYTES;
+  // this lane's 8 outputs of every block live in sub-block myj = lane >> 2
+  const int myj = lane >> 2;
+  const uint32_t qoff = (Q5 ? 48u : 16u) + 32u * (uint32_t)(myj >> 1) + 8u * (uint32_t)(lane & 3);
+  const uint32_t hoff = 16u + 8u * (uint32_t)(lane & 3);
+  const int nsh = (myj & 1) * 4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float dsc = __shfl_sync(0xffffffffu, dsc_j, 8 * k + myj);
+    const float dsc2 = __shfl_sync(0xffffffffu, dsc_c, 8 * k + myj);
+    const float dmn = __shfl_sync(0xffffffffu, dmn_j, 8 * k + myj);
+    if ((uint32_t)k < nb) {
+      const uint32_t blk = pay + (b0 + k) * BB;
+      const uint32_t qa = blk + qoff;
+      uint32_t q0, q1;
+      if (ALIGNED) {
+        const uint2 q = lds64(qa);
+        q0 = q.x; q1 = q.y;
+      } else {
+        q0 = lds32_bytes(qa); q1 = lds32_bytes(qa + 4);
+      }
+      q0 = (q0 >> nsh) & 0x0F0F0F0Fu;
+      q1 = (q1 >> nsh) & 0x0F0F0F0Fu;
+      if (Q5) {
+        uint32_t h0, h1;
+        if (ALIGNED) {
+          const uint2 h = lds64(blk + hoff);
+          h0 = h.x; h1 = h.y;
+        } else {
+          h0 = lds32_bytes(blk + hoff); h1 = lds32_bytes(blk + hoff + 4);
+        }
+        q0 |= ((h0 >> myj) & 0x01010101u) << 4;
+        q1 |= ((h1 >> myj) & 0x01010101u) << 4;
+      }
+      float y[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        // 0x4B0000qq is the float 2^23 + q (PRMT, no I2F)
+        const float big = kk_bits2f(kk_byte_perm(e < 4 ? q0 : q1, 0x4B000000u, 0x7440u | (uint32_t)(e & 3)));
+        const float prod = FAST ? kk_fma(dsc, big, dsc2) : __fmul_rn(dsc, __fsub_rn(big, 8388608.0f));
+        y[e] = __fsub_rn(prod, dmn);
+      }
+      store16_all(D, dst_off + (uint64_t)(b0 + k) * 512u + (uint32_t)lane * 16u,
+                  make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7])));
+    }
+  }
+}
+
+template <bool ALIGNED, bool Q5>
 KK_DQ_DEV void q4k_quad(const Dsts& D, uint32_t pay, uint32_t b0, uint32_t nb, uint64_t dst_off, int lane) {
   // --- decode: lane -> (block b0 + min(lane>>3, nb-1), sub-block lane&7)
   const uint32_t hb = min((uint32_t)(lane >> 3), nb - 1);
-  const uint32_t hblk = pay + (b0 + hb) * KK_Q4K_BLOCK_BYTES;
+  const uint32_t hblk = pay + (b0 + hb) * (Q5 ? 176u : KK_Q4K_BLOCK_BYTES);
   uint32_t h0, s0, s1, s2;
   if (ALIGNED) {
     const uint4 h = lds128(hblk);
@@ -124,50 +183,29 @@ KK_DQ_DEV void q4k_quad(const Dsts& D, uint32_t pay, uint32_t b0, uint32_t nb, u
   const uint32_t mn = (j < 4) ? (b_mid & 63u) : ((b_hi >> 4) | ((b_mid >> 6) << 4));
   const float dsc_j = __fmul_rn(d, (float)sc);
   const float dmn_j = __fmul_rn(dmin, (float)mn);
-  // --- expand: this lane's 8 outputs of every block live in sub-block myj = lane >> 2
-  const int myj = lane >> 2;
-  const uint32_t qoff = 16u + 32u * (uint32_t)(myj >> 1) + 8u * (uint32_t)(lane & 3);
-  const int nsh = (myj & 1) * 4;
-  // all four blocks' nibble words first (a block past the end re-reads the last valid one: in bounds, discarded), so that the four
-  // load -> expand -> store chains overlap instead of each waiting for its own shared-memory round trip behind the previous block's store
-  uint32_t qw0[4], qw1[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const uint32_t kb = min((uint32_t)k, nb - 1);
-    const uint32_t qa = pay + (b0 + kb) * KK_Q4K_BLOCK_BYTES + qoff;
-    if (ALIGNED) {
-      const uint2 q = lds64(qa);
-      qw0[k] = q.x; qw1[k] = q.y;
-    } else {
-      qw0[k] = lds32_bytes(qa); qw1[k] = lds32_bytes(qa + 4);
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float dsc = __shfl_sync(0xffffffffu, dsc_j, 8 * k + myj);
-    const float dmn = __shfl_sync(0xffffffffu, dmn_j, 8 * k + myj);
-    const uint32_t q0 = (qw0[k] >> nsh) & 0x0F0F0F0Fu;
-    const uint32_t q1 = (qw1[k] >> nsh) & 0x0F0F0F0Fu;
-    float y[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      // 0x4B0000qq is the float 2^23 + q; subtracting 2^23 gives q exactly (PRMT + FADD, no I2F).
-      const uint32_t bits = kk_byte_perm(e < 4 ? q0 : q1, 0x4B000000u, 0x7440u | (uint32_t)(e & 3));
-      const float q = __fsub_rn(kk_bits2f(bits), 8388608.0f);
-      y[e] = __fsub_rn(__fmul_rn(dsc, q), dmn);
-    }
-    if ((uint32_t)k < nb)
-      store16_all(D, dst_off + (uint64_t)(b0 + k) * 512u + (uint32_t)lane * 16u,
-                  make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7])));
-  }
+  const float dsc_c = __fmul_rn(dsc_j, -8388608.0f);
+  // fast form iff every scale of the quad is finite and >= +0: then c is -|x| or -0, i.e. its bits lie in [0x80000000, 0xFF800000)
+  const bool ok = (kk_f2bits(dsc_c) - 0x80000000u) < 0x7F800000u;
+  if (kk_all(ok)) q4k_expand<ALIGNED, true, Q5>(D, pay, b0, nb, dst_off, lane, dsc_j, dsc_c, dmn_j);
+  else q4k_expand<ALIGNED, false, Q5>(D, pay, b0, nb, dst_off, lane, dsc_j, dsc_c, dmn_j);
 }
 
 KK_DQ_DEV void consume_q4k(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
   const bool al = (pay & 15u) == 0;  // 144-byte blocks keep the tile's alignment class
   for (uint32_t b0 = (uint32_t)cwarp * 4u; b0 < nblk; b0 += kConsumerWarps * 4u) {
     const uint32_t nb = min(4u, nblk - b0);
-    if (al) q4k_quad<true>(D, pay, b0, nb, dst_off, lane);
-    else q4k_quad<false>(D, pay, b0, nb, dst_off, lane);
+    if (al) q4k_quad<true, false>(D, pay, b0, nb, dst_off, lane);
+    else q4k_quad<false, false>(D, pay, b0, nb, dst_off, lane);
+  }
+}
+// Q5_K through the same quads (round 1 gave it one block per warp iteration with ten shared loads per lane: 0.74 of the copy peak, the slowest
+// dequantiser; the header decode is now amortised over four blocks and handed out by shuffles like Q4_K's)
+KK_DQ_DEV void consume_q5k(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
+  const bool al = (pay & 15u) == 0;  // 176-byte blocks keep the tile's alignment class
+  for (uint32_t b0 = (uint32_t)cwarp * 4u; b0 < nblk; b0 += kConsumerWarps * 4u) {
+    const uint32_t nb = min(4u, nblk - b0);
+    if (al) q4k_quad<true, true>(D, pay, b0, nb, dst_off, lane);
+    else q4k_quad<false, true>(D, pay, b0, nb, dst_off, lane);
   }
 }
 

@@ -235,35 +235,7 @@ KK_DQ_DEV void consume_q3k(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t 
 
 // Q5_K (176 B): d f16 | dmin f16 | scales[12] | qh[32] | qs[128]  (gguf/quants.py:525-548).  Sub-block j (32 weights), element i:
 // q = ((qs[32*(j/2) + i] >> 4*(j%2)) & 15) | (((qh[i] >> j) & 1) << 4); (scale, min) of sub-block j packed as in Q4_K;
-// y = (d*sc_j)*q - dmin*m_j.  Lane l: j = l>>2, i = 8*(l&3)..+8.
-KK_DQ_DEV void consume_q5k(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
-  const uint32_t j = (uint32_t)(lane >> 2), i0 = 8u * (uint32_t)(lane & 3);
-  const uint32_t q_off = 48u + 32u * (j >> 1) + i0;
-  const uint32_t nsh = 4u * (j & 1u);
-#pragma unroll 2
-  for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
-    const uint32_t blk = pay + b * KK_Q5K_BLOCK_BYTES;
-    const float d = lds_f16(blk), dmin = lds_f16(blk + 2u);
-    const uint32_t s = blk + 4u;
-    uint32_t sc, mn;
-    if (j < 4u) {
-      sc = lds8(s + j) & 63u;
-      mn = lds8(s + j + 4u) & 63u;
-    } else {
-      const uint32_t hi = lds8(s + j + 4u);
-      sc = (hi & 0xFu) | ((lds8(s + j - 4u) >> 6) << 4);
-      mn = (hi >> 4) | ((lds8(s + j) >> 6) << 4);
-    }
-    const float dsc = __fmul_rn(d, (float)sc);
-    const float dmn = __fmul_rn(dmin, (float)mn);
-    const uint32_t w0 = ((lds32_blk<KK_Q5K_BLOCK_BYTES>(blk + q_off) >> nsh) & 0x0F0F0F0Fu) | (((lds32_blk<KK_Q5K_BLOCK_BYTES>(blk + 16u + i0) >> j) & 0x01010101u) << 4);
-    const uint32_t w1 = ((lds32_blk<KK_Q5K_BLOCK_BYTES>(blk + q_off + 4u) >> nsh) & 0x0F0F0F0Fu) | (((lds32_blk<KK_Q5K_BLOCK_BYTES>(blk + 16u + i0 + 4u) >> j) & 0x01010101u) << 4);
-    float y[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) y[e] = __fsub_rn(__fmul_rn(dsc, byte_to_float<0>(e < 4 ? w0 : w1, e & 3)), dmn);
-    store_bf16x8(D, dst_off + (uint64_t)b * 512u + (uint32_t)lane * 16u, y);
-  }
-}
+// y = (d*sc_j)*q - dmin*m_j.  Implemented by consume_q5k in kk_consume_core.cuh: Q4_K's four-blocks-per-iteration quads with a fifth bit.
 
 // ---- §8(f4): FP8 (safetensors F8_E4M3 / F8_E5M2) widened to bf16, opt-in through KK_LOAD_F8_TO_BF16 -----------------------------
 // Elementwise and exact: FP8 -> fp16 with the hardware pair conversion, fp16 -> fp32 -> bf16 (RNE never rounds: every FP8 value

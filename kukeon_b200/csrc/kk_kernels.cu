@@ -173,6 +173,8 @@ __device__ __forceinline__ uint32_t kk_f8x2_to_f16x2(uint32_t v) {
   return r;
 }
 __device__ __forceinline__ float kk_bits2f(uint32_t u) { return __uint_as_float(u); }
+__device__ __forceinline__ float kk_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }  // one rounding
+__device__ __forceinline__ bool kk_all(bool p) { return __all_sync(0xffffffffu, p) != 0; }  // warp vote
 __device__ __forceinline__ uint32_t kk_byte_perm(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
 __device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }

@@ -8,6 +8,7 @@
 // shared load, a read outside the staged tile, a store outside the tile's output window or two stores to the same 16 bytes
 // all fail the run.  It does not check PTX spelling, memory ordering or anything about the producer warp; the -m gpu
 // parity tests do.  The product never links this file and has no CPU path.
+#include <cmath>
 #include <cstdint>
 #include <algorithm>
 #include <cstring>
@@ -91,6 +92,23 @@ inline float __shfl_sync(unsigned, float v, int src) {
   flag(7);  // a shuffle outside record/replay cannot be emulated
   return v;
 }
+// Warp vote, by the same record / replay: pass 1 records every lane's predicate (and returns it: both arms of a vote-guarded branch must
+// issue the same shuffles, which they do — the vote only selects the arithmetic), pass 2 returns the AND over the 32 lanes.
+inline bool kk_all(bool p) {
+  if (g.shfl_mode == 1) {
+    if (g.shfl_calls >= Emu::kMaxShfl) { flag(7); return p; }
+    g.shfl_table[g.shfl_calls++][g.lane] = p ? 1.0f : 0.0f;
+    return p;
+  }
+  if (g.shfl_mode == 2) {
+    if (g.shfl_calls >= Emu::kMaxShfl) { flag(7); return p; }
+    bool all = true;
+    for (int l = 0; l < 32; ++l) all = all && g.shfl_table[g.shfl_calls][l] != 0.0f;
+    g.shfl_calls++;
+    return all;
+  }
+  return p;
+}
 inline uint32_t kk_f2bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 inline uint32_t kk_popc(uint32_t u) { return (uint32_t)__builtin_popcount(u); }
 inline uint32_t kk_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {
@@ -132,6 +150,7 @@ inline uint32_t kk_byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
   return r;
 }
 inline float kk_bits2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+inline float kk_fma(float a, float b, float c) { return std::fmaf(a, b, c); }  // correctly rounded single rounding (glibc, -ffp-contract=off)
 inline float kk_h2f(uint32_t h) {
   uint16_t b = (uint16_t)h;
   _Float16 x; memcpy(&x, &b, 2);
@@ -258,7 +277,7 @@ inline bool run_op(uint32_t op, const Dsts& D, uint32_t pay, uint32_t n, uint64_
 }  // namespace
 
 inline bool run_warps(uint32_t op, const Dsts& D, uint32_t pay, uint32_t n, uint64_t dst_off) {
-  const bool shuffles = op == KK_OP_Q4K_BF16;
+  const bool shuffles = op == KK_OP_Q4K_BF16 || op == KK_OP_Q5K_BF16;
   for (int cwarp = 0; cwarp < kConsumerWarps; ++cwarp) {
     for (int pass = shuffles ? 1 : 0; pass <= (shuffles ? 2 : 0); ++pass) {
       g.shfl_mode = pass;
@@ -327,7 +346,7 @@ extern "C" int kk_emul_dequant_tile_stats(uint32_t op, const uint8_t* tile, uint
   g.out_mask = mask.data();
   g.byte_mask = bmask.data();
   const Dsts D{0};
-  const bool shuffles = op == KK_OP_Q4K_BF16;
+  const bool shuffles = op == KK_OP_Q4K_BF16 || op == KK_OP_Q5K_BF16;
   std::vector<std::vector<uint32_t>> traces((size_t)kConsumerWarps * 32);
   for (int cwarp = 0; cwarp < kConsumerWarps; ++cwarp)
     for (int pass = shuffles ? 1 : 0; pass <= (shuffles ? 2 : 0); ++pass) {

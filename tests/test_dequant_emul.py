@@ -83,7 +83,7 @@ def test_full_tile_finite_scales(emul, dtype):
 def test_ragged_counts_and_every_alignment_random_bytes(emul, dtype):
     """Fully random bytes (Inf/NaN scales included: NaN -> 0x7FFF on both sides) at every start alignment a tile can have."""
     nel, nb, _ = oracle.BLOCK_QUANTS[dtype]
-    per_iter = 8 if nel == 32 else 4 if dtype in ("Q4_K", "NVFP4") else 1  # blocks one warp iteration covers
+    per_iter = 8 if nel == 32 else 4 if dtype in ("Q4_K", "Q5_K", "NVFP4") else 1  # blocks one warp iteration covers
     rng = np.random.default_rng(5)
     counts = [1, 2, per_iter - 1 or 1, per_iter, per_iter + 1, 16 * per_iter - 1, 16 * per_iter, 16 * per_iter + 1, 16 * per_iter + 5, 37 * per_iter + 3]
     for k, n in enumerate(counts):
@@ -242,7 +242,7 @@ def test_super_block_dequantisers_read_shared_memory_conflict_free(emul):
     more than 128 bytes per warp iteration and stay below 2.5."""
     for dt, op in sorted(OPS.items()):
         nel, nb, _ = oracle.BLOCK_QUANTS[dt]
-        if dt == "Q4_K":
+        if dt in ("Q4_K", "Q5_K"):
             continue  # vector loads (lds128 / lds64), not traced
         per_sweep = 16 * (8 if nel == 32 else 4 if dt == "NVFP4" else 1)
         n = geom(emul, op)[2] // per_sweep * per_sweep  # whole sweeps: every lane of every warp executes the same loads

@@ -37,7 +37,7 @@ _ITER_BYTES_1X = {
     "KK_OP_F8E4M3_BF16": (512, 1024), "KK_OP_F8E5M2_BF16": (512, 1024),
     "KK_OP_Q4K_BF16": (4 * 144, 2048), "KK_OP_Q6K_BF16": (210, 512), "KK_OP_Q8_0_BF16": (8 * 34, 512),
     "KK_OP_Q4_0_BF16": (8 * 18, 512), "KK_OP_Q4_1_BF16": (8 * 20, 512), "KK_OP_Q5_0_BF16": (8 * 22, 512), "KK_OP_Q5_1_BF16": (8 * 24, 512),
-    "KK_OP_Q2K_BF16": (84, 512), "KK_OP_Q3K_BF16": (110, 512), "KK_OP_Q5K_BF16": (176, 512),
+    "KK_OP_Q2K_BF16": (84, 512), "KK_OP_Q3K_BF16": (110, 512), "KK_OP_Q5K_BF16": (4 * 176, 2048),
     "KK_OP_IQ4NL_BF16": (8 * 18, 512), "KK_OP_MXFP4_BF16": (8 * 17, 512), "KK_OP_IQ4XS_BF16": (136, 512),
     "KK_OP_IQ2XXS_BF16": (66, 512), "KK_OP_IQ2XS_BF16": (74, 512), "KK_OP_IQ2S_BF16": (82, 512), "KK_OP_IQ3XXS_BF16": (98, 512),
     "KK_OP_IQ3S_BF16": (110, 512), "KK_OP_IQ1S_BF16": (50, 512), "KK_OP_IQ1M_BF16": (56, 512),
@@ -46,7 +46,7 @@ _ITER_BYTES_1X = {
     "KK_OP_TQ1_0_BF16": (54, 512), "KK_OP_TQ2_0_BF16": (66, 512), "KK_OP_NVFP4_BF16": (4 * 36, 512),
 }
 
-ITER_BYTES = {op: ((2 * v[0], 2 * v[1]) if op.startswith(("KK_OP_Q", "KK_OP_IQ", "KK_OP_TQ", "KK_OP_MXFP4", "KK_OP_NVFP4")) and op != "KK_OP_Q4K_BF16" else v)
+ITER_BYTES = {op: ((2 * v[0], 2 * v[1]) if op.startswith(("KK_OP_Q", "KK_OP_IQ", "KK_OP_TQ", "KK_OP_MXFP4", "KK_OP_NVFP4")) and op not in ("KK_OP_Q4K_BF16", "KK_OP_Q5K_BF16") else v)
               for op, v in _ITER_BYTES_1X.items()}
 
 CLASSES = [("lds", r"^LDS"), ("ldg", r"^LDG"), ("stg", r"^STG"), ("prmt", r"^PRMT"), ("fadd/fmul", r"^(FADD|FMUL|FFMA)"), ("f2fp/cvt", r"^(F2FP|F2F|I2F|HADD2|HMUL2|HFMA2)"),
@@ -149,12 +149,13 @@ def hot_path(ins, labels, a, b, mode="math"):
     The loop body without its backward branches is a DAG (edges: fall-through, forward branches inside the loop).  Predicated non-branch
     instructions count: they issue.
     mode "math": paths that skip the work (out-of-range lanes, ragged-tail variants) carry fewer conversion instructions, so the hot path is
-    the one that maximises the count of F2FP/FMUL/FADD and, among those, minimises the total — i.e. one destination pool (the n_dst > 1
-    ladder is a longer alternative) and the cheapest of the alignment variants of the loads.
+    the one that maximises the count of F2FP (the bf16 packs: one per two outputs, the same in every arithmetic variant) and, among those,
+    minimises the total — i.e. one destination pool (the n_dst > 1 ladder is a longer alternative), the cheapest of the alignment variants of
+    the loads, and for Q4_K / Q5_K the FMA form that every quad with finite non-negative scales takes (the two-step form is the longer one).
     mode "vec" (the transposes, whose ragged path converts element by element and so carries MORE arithmetic than the vector path): the
     cheapest path that performs a 128-bit store."""
     if mode == "math":
-        math = re.compile(r"^(F2FP|FMUL|FADD|FFMA)")
+        math = re.compile(r"^F2FP")
         best = {}
         for i in range(b, a - 1, -1):
             own = (1 if math.match(ins[i]["mn"]) else 0, -1)
