@@ -190,7 +190,7 @@ KK_DQ_DEV void consume_legacy32(const Dsts& D, uint32_t pay, uint32_t nblk, uint
 KK_DQ_DEV void consume_q2k(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
   const uint32_t q_off = 16u + 32u * (uint32_t)(lane >> 4) + 8u * (uint32_t)(lane & 3);
   const uint32_t sh = 2u * (uint32_t)((lane >> 2) & 3);
-#pragma unroll 2
+  // (no `#pragma unroll 2` here: measured slower with it on a B200, profiles/r02/types_roofline_{a,b}.json — this loop was not latency-bound)
   for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
     const uint32_t blk = pay + b * KK_Q2K_BLOCK_BYTES;
     const float d = lds_f16(blk + 80u), dmin = lds_f16(blk + 82u);
@@ -460,7 +460,7 @@ KK_DQ_DEV void consume_iq2xs(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_
 // IQ2_S (82 B): d f16 | qs[32] | signs[32] | qh[8] (2 more index bits per entry) | scales[8]
 KK_DQ_DEV void consume_iq2s(const Dsts& D, uint32_t pay, uint32_t nblk, uint64_t dst_off, int cwarp, int lane) {
   const uint32_t l = (uint32_t)lane;
-#pragma unroll 2
+  // (no `#pragma unroll 2` here: measured slower with it on a B200, profiles/r02/types_roofline_{a,b}.json — this loop was not latency-bound)
   for (uint32_t b = (uint32_t)cwarp; b < nblk; b += kConsumerWarps) {
     const uint32_t blk = pay + b * KK_IQ2S_BLOCK_BYTES;
     const float d = lds_f16(blk);
