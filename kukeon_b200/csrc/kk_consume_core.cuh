@@ -44,25 +44,26 @@ KK_DQ_DEV float lds_f16_any(uint32_t a) {
 }
 
 KK_DQ_DEV void consume_f32(const Dsts& D, uint32_t pay, uint32_t n, uint64_t dst_off, int ctid) {
-  const uint32_t ngrp = n >> 3;  // 8 elements -> 16 B out
   if ((pay & 15u) == 0) {
-    for (uint32_t g = ctid; g < ngrp; g += kConsumerThreads) {
-      uint4 a = lds128(pay + (g << 5)), b = lds128(pay + (g << 5) + 16);
-      uint4 o;
-      o.x = pack_bf16x2(kk_bits2f(a.x), kk_bits2f(a.y));
-      o.y = pack_bf16x2(kk_bits2f(a.z), kk_bits2f(a.w));
-      o.z = pack_bf16x2(kk_bits2f(b.x), kk_bits2f(b.y));
-      o.w = pack_bf16x2(kk_bits2f(b.z), kk_bits2f(b.w));
-      store16_all(D, dst_off + ((uint64_t)g << 4), o);
+    // 4 elements per thread and step: one 16-byte load at a 16-byte lane stride (a warp reads 512 contiguous bytes: 4 wavefronts, the minimum)
+    // and one 8-byte store (a warp writes 256 contiguous bytes).  Round 1 took 8 elements per thread — two 16-byte loads at a 32-byte lane
+    // stride, a 2-way bank conflict on each (1.23 M excessive wavefronts in the GPT-2 load, profiles/r02/prof_gpt2: all of them here).
+    const uint32_t nq = n >> 2;
+    for (uint32_t g = ctid; g < nq; g += kConsumerThreads) {
+      const uint4 a = lds128(pay + (g << 4));
+      store8_all(D, dst_off + ((uint64_t)g << 3), pack_bf16x2(kk_bits2f(a.x), kk_bits2f(a.y)), pack_bf16x2(kk_bits2f(a.z), kk_bits2f(a.w)));
     }
-  } else {
-    for (uint32_t g = ctid; g < ngrp; g += kConsumerThreads) {
-      float f[8];
+    const uint32_t tail = n & 3u, base = nq << 2;
+    if (ctid < (int)tail) store2_all(D, dst_off + 2ull * (base + ctid), to_bf16(lds_f32_any(pay + 4 * (base + ctid))));
+    return;
+  }
+  const uint32_t ngrp = n >> 3;  // 8 elements -> 16 B out
+  for (uint32_t g = ctid; g < ngrp; g += kConsumerThreads) {
+    float f[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) f[k] = lds_f32_any(pay + (g << 5) + 4 * k);
-      store16_all(D, dst_off + ((uint64_t)g << 4),
-                  make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7])));
-    }
+    for (int k = 0; k < 8; ++k) f[k] = lds_f32_any(pay + (g << 5) + 4 * k);
+    store16_all(D, dst_off + ((uint64_t)g << 4),
+                make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7])));
   }
   const uint32_t tail = n & 7u, base = ngrp << 3;
   if (ctid < (int)tail) store2_all(D, dst_off + 2ull * (base + ctid), to_bf16(lds_f32_any(pay + 4 * (base + ctid))));

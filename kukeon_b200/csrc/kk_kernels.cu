@@ -131,6 +131,16 @@ __device__ __forceinline__ void store16_all(const Dsts& D, uint64_t off, const u
   for (int d = 0; d < KK_MAX_DST; ++d)
     if (d < (int)D.n) stg128(D.p[d] + off, v);
 }
+// 8-byte store of half an output vector (the aligned F32 -> bf16 cast: 4 elements per thread) to every destination pool
+__device__ __forceinline__ void store8_all(const Dsts& D, uint64_t off, uint32_t lo, uint32_t hi) {
+  if (D.multimem) {
+    asm volatile("multimem.st.weak.global.v2.f32 [%0], {%1,%2};" ::"l"(D.p[0] + off), "f"(__uint_as_float(lo)), "f"(__uint_as_float(hi)) : "memory");
+    return;
+  }
+#pragma unroll
+  for (int d = 0; d < KK_MAX_DST; ++d)
+    if (d < (int)D.n) asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(D.p[d] + off), "r"(lo), "r"(hi));
+}
 __device__ __forceinline__ void store2_all(const Dsts& D, uint64_t off, uint16_t v) {
   if (D.multimem) {
     // multimem.st has no 8- or 16-bit form: the host only selects KK_LAUNCH_MULTIMEM for plans whose segments never need a

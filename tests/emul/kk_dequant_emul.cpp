@@ -197,6 +197,18 @@ inline void store2_all(const Dsts&, uint64_t off, uint16_t v) {
   memcpy(g.out + off, &v, 2);
   for (int i = 0; i < g.n_more; ++i) memcpy(g.more_out[i] + off, &v, 2);
 }
+inline void store8_all(const Dsts&, uint64_t off, uint32_t lo, uint32_t hi) {  // half an output vector: four entries of the 2-byte mask
+  if (g.shfl_mode == 1) return;
+  if ((off & 7u) || off + 8 > g.out_bytes) { flag(3); return; }
+  for (int k = 0; k < 4; ++k) {
+    if (g.out_mask[(off >> 1) + k]) flag(4);
+    g.out_mask[(off >> 1) + k] = 1;
+  }
+  g.hits[off >> 4] += 8;
+  const uint32_t v[2] = {lo, hi};
+  memcpy(g.out + off, v, 8);
+  for (int i = 0; i < g.n_more; ++i) memcpy(g.more_out[i] + off, v, 8);
+}
 inline void store4_all(const Dsts&, uint64_t off, uint32_t v) {  // one 32-bit element (verbatim transposes): two entries of the 2-byte mask
   if (g.shfl_mode == 1) return;
   if ((off & 3u) || off + 4 > g.out_bytes) { flag(3); return; }
