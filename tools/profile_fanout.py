@@ -18,7 +18,7 @@ if not os.path.exists(os.path.join(d, ".ok")):
 with gpupool.Pool(list(range(n))) as pool:
     m = pool.load(d, mode=gpupool.MODE_BROADCAST, fanout=gpupool.FANOUT_P2P, flags=gpupool.LOAD_DEFER)
     m.stage_resident()
-    for i in range(4):
+    for i in range(6):
         tot, per = m.convert_resident()
         print(f"round {i}: {tot:.3f} ms, launches {[round(x, 3) for x in per]}", flush=True)
     info = m.info()

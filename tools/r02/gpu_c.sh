@@ -23,7 +23,7 @@ for f in ("bench_n2_pull", "bench_n2_p2p"):
         print(f, "unreadable:", e)
 PY
 echo "== 4. ncu --set full of one fused convert + fan-out launch at N = 2 (one process owning both GPUs; never a multi-rank command)"
-timeout 300 ncu --set full --section Nvlink --section Nvlink_Tables --section Nvlink_Topology --clock-control none --import-source on -k regex:kk_convert_kernel --devices 0 -s 4 -c 1 \
+timeout 300 ncu --set full --section Nvlink --section Nvlink_Tables --section Nvlink_Topology --clock-control none --import-source on -k regex:kk_convert_kernel --devices 0 -s 2 -c 1 \
   -o $O/prof_fanout_n2 -f python tools/profile_fanout.py 2 8 > $O/ncu_fanout_n2.log 2>&1; echo "ncu rc=$?"; tail -4 $O/ncu_fanout_n2.log
 ncu -i $O/prof_fanout_n2.ncu-rep --page raw --csv > $O/prof_fanout_n2.raw.csv 2>/dev/null
 ncu -i $O/prof_fanout_n2.ncu-rep --page details > $O/prof_fanout_n2.details.txt 2>/dev/null
