@@ -58,6 +58,8 @@ def parse():
                     "measure the other dequantisers at the same shapes)")
     ap.add_argument("--layers", type=int, default=0, help="override the layer count (reported in config; 0 = full size)")
     ap.add_argument("--data-dir", default="")
+    ap.add_argument("--gen-only", action="store_true", help="internal: write the synthetic checkpoint into --data-dir and exit (run as a child process by make_files)")
+    ap.add_argument("--no-interleave", action="store_true", help="do not spread the synthetic files' page-cache pages over the NUMA nodes")
     ap.add_argument("--keep-data", action="store_true")
     ap.add_argument("--readers", type=int, default=0)
     ap.add_argument("--slots", type=int, default=0)
@@ -127,21 +129,65 @@ def pick_data_dir(args, need_bytes: int) -> str:
     raise SystemExit(f"no directory with {need_bytes / 1e9:.1f} GB free for the synthetic checkpoint")
 
 
-def make_files(spec, d: str) -> str:
-    from tools import synth
+def interleave_new_pages(on: bool) -> bool:
+    """set_mempolicy(MPOL_INTERLEAVE over every online node) for this thread while the synthetic checkpoint is written, so that its tmpfs /
+    page-cache pages are spread over the host's NUMA nodes — the neutral placement for a file that N readers on both sockets are about to read
+    (a checkpoint read from disk by the per-GPU reader threads would even land on each reader's own node).  Written from one process without
+    this, every page sits on the writer's node and the four ranks of the other socket pull their parts through the inter-socket link.
+    Returns whether the policy was applied (False: single node, or the syscall is unavailable)."""
+    import ctypes
+    try:
+        nodes = []
+        for part in open("/sys/devices/system/node/online").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            nodes += list(range(int(lo), int(hi or lo) + 1))
+        if len(nodes) < 2:
+            return False
+        mask = ctypes.c_ulong(sum(1 << n for n in nodes) if on else 0)
+        libc = ctypes.CDLL(None, use_errno=True)
+        rc = libc.syscall(238, 3 if on else 0, ctypes.byref(mask) if on else None, 65 if on else 0)  # x86-64 set_mempolicy; MPOL_INTERLEAVE = 3, MPOL_DEFAULT = 0
+        return rc == 0
+    except Exception:  # noqa: BLE001
+        return False
+
+
+_INTERLEAVED = None
+
+
+def make_files(spec, d: str, args=None) -> str:
+    """Synthetic checkpoint under d (once; `.complete` marks it).  Written by a CHILD process (`bench.py --gen-only`): the NUMA interleave policy
+    it sets — inherited by the generator's OpenMP workers — must not stay on this process's threads, whose first-touch placement the CPU arm
+    depends on."""
+    global _INTERLEAVED
     marker = os.path.join(d, ".complete")
-    if os.path.exists(marker):
-        return d if spec["kind"] != "gguf" else os.path.join(d, "model.gguf")
+    if not os.path.exists(marker):
+        if args is None or getattr(args, "gen_only", False):
+            generate_files_here(spec, d)
+        else:
+            cmd = [sys.executable, os.path.abspath(__file__), "--gen-only", "--workload", args.workload, "--qtype", args.qtype, "--layers", str(args.layers), "--data-dir", d]
+            if getattr(args, "no_interleave", False):
+                cmd.append("--no-interleave")
+            subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
+    _INTERLEAVED = open(marker).read().strip() == "interleaved"
+    return d if spec["kind"] != "gguf" else os.path.join(d, "model.gguf")
+
+
+def generate_files_here(spec, d: str, interleave: bool = True) -> None:
+    from tools import synth
     shutil.rmtree(d, ignore_errors=True)
     os.makedirs(d)
+    il = interleave_new_pages(True) if interleave else False
+    _write_files(spec, d, synth)
+    open(os.path.join(d, ".complete"), "w").write("interleaved" if il else "ok")
+
+
+def _write_files(spec, d: str, synth) -> None:
     if spec["kind"] == "llama":
         synth.write_sharded(d, spec["tensors"], 8001, 5_000_000_000)
     elif spec["kind"] == "gguf":
         synth.write_gguf(os.path.join(d, "model.gguf"), spec["tensors"], 8007)
     else:
         synth.write_safetensors(os.path.join(d, "model.safetensors"), spec["tensors"], 1234)
-    open(marker, "w").write("ok")
-    return d if spec["kind"] != "gguf" else os.path.join(d, "model.gguf")
 
 
 # ---------------------------------------------------------------------------------------------
@@ -220,7 +266,8 @@ def run_reference(args, spec, path, file_bytes):
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": tot / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-        "data": "synthetic", "config": {"workload": spec["name"], "file_bytes": file_bytes, "files": "warm in tmpfs/page cache",
+        "data": "synthetic", "config": {"workload": spec["name"], "file_bytes": file_bytes,
+                                        "files": "warm in tmpfs/page cache" + (", pages interleaved over the host's NUMA nodes" if _INTERLEAVED else ""),
                                         "same_config": ctx[3] == file_bytes},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": (("the whole checkpoint" if ctx[3] == file_bytes else f"first {ctx[3] / 1e9:.2f} GB of the checkpoint") +
@@ -257,6 +304,9 @@ def main():
     os.dup2(2, 1)
     spec = workload_spec(args)
     from tools import synth
+    if args.gen_only:
+        generate_files_here(spec, args.data_dir, interleave=not args.no_interleave)
+        return
     file_bytes = synth.total_bytes(spec["tensors"])
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -271,7 +321,7 @@ def main():
     d = pick_data_dir(args, file_bytes)
     if args.impl == "reference":
         if rank == 0:
-            path = make_files(spec, d)
+            path = make_files(spec, d, args)
             run_reference(args, spec, path, file_bytes)
             if not args.keep_data:
                 shutil.rmtree(d, ignore_errors=True)
@@ -310,7 +360,7 @@ def main():
 
     t_gen = time.time()
     if rank == 0:
-        path = make_files(spec, d)
+        path = make_files(spec, d, args)
     barrier()
     path = d if spec["kind"] != "gguf" else os.path.join(d, "model.gguf")
     t_gen = time.time() - t_gen
@@ -646,7 +696,7 @@ def main():
         "config": {"workload": spec["name"], "file_bytes": file_bytes, "tensors": len(ref.tensors), "shards": len(ref.shards),
                    "mode": {0: "single", 1: "broadcast (sharded ingest + fused P2P fan-out)",
                             2: "scatter" + (" (row-parallel tensors exchanged over NVLink: KK_LOAD_SCATTER_EXCHANGE)" if exchange else "")}[mode], "pool_bytes_per_gpu": pool_bytes,
-                   "l2": "inputs (>= 2 GB per GPU) far larger than the 126 MB L2; no flush needed", "files": f"warm in {os.path.dirname(d) or d}",
+                   "l2": "inputs (>= 2 GB per GPU) far larger than the 126 MB L2; no flush needed", "files": f"warm in {os.path.dirname(d) or d}" + (", pages interleaved over the host's NUMA nodes (set_mempolicy while writing)" if _INTERLEAVED else ""),
                    "staging": "zero-copy pinned reads" if args.zerocopy else "pinned ring + H2D copy engine", "verified_vs_files": verified,
                    **({"transpose_tiles": "8 source rows x <= 4 KiB, thread = column, 16-byte stores"} if spec["kind"] == "gpt2" else {})},
         "clocks": ck,
@@ -742,6 +792,13 @@ def main():
         dist.destroy_process_group()
 
 
+def args_for_secondary(args):
+    import copy
+    a = copy.copy(args)
+    a.workload, a.qtype, a.layers = "mixtral-q4k", "Q4_K", 4
+    return a
+
+
 def secondary_q4k(args, pool, gpupool, modelhub, peak, write_peak):
     """Kernel stage of a 4-layer Mixtral-8x7B q4_K GGUF (3.4 GB of blocks -> 12.1 GB of bf16) from the HBM-resident image, same timing rules as
     `value`: >= 3 warm-ups, CUDA events on the launching stream inside the library, inputs far larger than L2."""
@@ -750,7 +807,7 @@ def secondary_q4k(args, pool, gpupool, modelhub, peak, write_peak):
     spec = dict(kind="gguf", tensors=synth.mixtral_gguf_tensors(layers=4), name="Mixtral-8x7B GGUF q4_k -> bf16 (REDUCED to 4 layers)")
     base = os.path.dirname(pick_data_dir(args, synth.total_bytes(spec["tensors"])))
     d = os.path.join(base, "kk_bench_secondary_q4k_l4")
-    path = make_files(spec, d)
+    path = make_files(spec, d, args_for_secondary(args))
     synth_s = time.time() - t0
     try:
         ref = modelhub.Pull(path)

@@ -469,7 +469,7 @@ void setup_raw(kk_model* m) {
     Device& d = m->ctx->devs[(size_t)m->dev_idx[li]];
     KK_CUDA(cudaSetDevice(d.ordinal));
     auto& R = m->raw[li];
-    R.bytes = tot ? tot : 256;
+    R.bytes = align_up(tot ? tot : 256, 2u << 20);  // 2 MiB multiples: cheap to map over CUDA IPC (see the slice buffer in model_load)
     cudaError_t e = cudaMalloc((void**)&R.image, R.bytes);
     if (e != cudaSuccess) { cudaGetLastError(); R.image = nullptr; fail(KK_ENOMEM, "device %d: cudaMalloc(%llu) for the raw image failed", d.ordinal, (unsigned long long)R.bytes); }
     if (!copy_segs.empty()) {
@@ -952,7 +952,10 @@ kk_model* model_load(kk_ctx* c, const std::string& path, const kk_load_opts& opt
       m->slice_base = mine.first & ~(uint64_t)255;
       const uint64_t sb = mine.second > m->slice_base ? mine.second - m->slice_base : 0;
       KK_CUDA(cudaSetDevice(c->devs[(size_t)m->dev_idx[0]].ordinal));
-      cudaError_t se = cudaMalloc((void**)&m->slice_buf, align_up(sb ? sb : 256, 256));
+      // whole 2 MiB multiples, like the pools: cudaIpcOpenMemHandle of such an allocation is ~50x cheaper than of one the driver carved out of
+      // shared blocks (measured at N = 8: seven 16 GB pools map in 0.07 s, seven 2 GB slice buffers of odd size took 0.66 s — and in round 1,
+      // before the pools were rounded, seven pools took 3.6 s; profiles/r02/bench_n8_*.json)
+      cudaError_t se = cudaMalloc((void**)&m->slice_buf, align_up(sb ? sb : 256, 2u << 20));
       if (se != cudaSuccess) { cudaGetLastError(); m->slice_buf = nullptr; fail(KK_ENOMEM, "cudaMalloc(%llu) for the slice buffer failed", (unsigned long long)sb); }
     }
     m->t_alloc = now_s() - t0;
