@@ -43,6 +43,10 @@ type Config struct {
 	StagingBuffers     uint32
 	StagingBufferBytes uint64
 	ReaderThreads      uint32
+	// VMMPools allocates pools with the driver's virtual-memory API (KK_CFG_VMM_POOLS): they are exported as POSIX file descriptors that agent
+	// containers map READ-ONLY (Model.ExportFD + the staged pool.sock) instead of as cudaIpcMemHandles, which map read-write in every opener.
+	// Set it whenever the cells that mount a model do not trust each other.
+	VMMPools bool
 }
 
 type Pool struct{ h *C.kk_ctx }
@@ -93,6 +97,9 @@ func Open(cfg Config) (*Pool, error) {
 	c.n_staging_buffers = C.uint32_t(cfg.StagingBuffers)
 	c.staging_buffer_bytes = C.uint64_t(cfg.StagingBufferBytes)
 	c.n_reader_threads = C.uint32_t(cfg.ReaderThreads)
+	if cfg.VMMPools {
+		c.flags |= C.KK_CFG_VMM_POOLS
+	}
 	p := &Pool{}
 	if err := call(func() C.int { return C.kk_open(&c, &p.h) }); err != nil {
 		return nil, err
@@ -166,6 +173,30 @@ func (p *Pool) Load(path string, mode Mode, flags uint32) (*Model, error) {
 		return nil, err
 	}
 	return m, nil
+}
+
+// ExportFD returns a new file descriptor for the VMM pool of `device` and its mapped size (KK_CFG_VMM_POOLS contexts only).  The caller sends it to
+// the agent over the staged Unix socket (SCM_RIGHTS) and closes it; the agent maps it with kk_import_fd(..., KK_IMPORT_READONLY).
+func (m *Model) ExportFD(device int) (int, uint64, error) {
+	var fd C.int
+	var size C.uint64_t
+	if err := call(func() C.int { return C.kk_export_fd(m.h, C.int(device), &fd, &size) }); err != nil {
+		return -1, 0, err
+	}
+	return int(fd), uint64(size), nil
+}
+
+// DeviceIdentity is what leaves the process instead of a CUDA ordinal: the PCI bus id (key of /proc/driver/nvidia/gpus/<id>/information, where
+// the /dev/nvidia<minor> number is read) and the GPU UUID (how the agent picks the device inside its container).
+func DeviceIdentity(ordinal int) (pciBusID, uuid string, err error) {
+	bus := make([]byte, 32)
+	id := make([]byte, 64)
+	if err = call(func() C.int {
+		return C.kk_device_identity(C.int(ordinal), (*C.char)(unsafe.Pointer(&bus[0])), C.size_t(len(bus)), (*C.char)(unsafe.Pointer(&id[0])), C.size_t(len(id)))
+	}); err != nil {
+		return "", "", err
+	}
+	return C.GoString((*C.char)(unsafe.Pointer(&bus[0]))), C.GoString((*C.char)(unsafe.Pointer(&id[0]))), nil
 }
 
 func (m *Model) Acquire() error { return call(func() C.int { return C.kk_acquire(m.h) }) }
