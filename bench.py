@@ -681,13 +681,17 @@ def main():
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
 
     # ---- secondary record (N = 1, default workload): an EXPANDING conversion, where the HBM-write fraction means something ------------------
-    secondary = None
+    secondary = secondary_g = None
     if rank == 0 and world == 1 and args.workload == "llama3-8b" and not args.layers and not args.no_secondary and not args.kernel_only:
         try:
             m.unstage_resident()
             secondary = secondary_q4k(args, pool, gpupool, modelhub, peak, write_peak)
         except Exception as e:  # noqa: BLE001
             secondary = {"error": str(e)}
+        try:
+            secondary_g = secondary_gpt2(args, pool, gpupool, modelhub, peak, write_peak)
+        except Exception as e:  # noqa: BLE001
+            secondary_g = {"error": str(e)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -726,6 +730,8 @@ def main():
                                 "for N = 8.  The per-N figure is roofline.frac (bound nvlink); end to end it is e2e.file_GBps and time_to_agent_ready_s.")
     if secondary is not None:
         line["secondary"] = secondary
+    if secondary_g is not None:
+        line["secondary_gpt2"] = secondary_g
     if nvlink:
         line["nvlink"] = nvlink
     if nccl:
@@ -792,26 +798,27 @@ def main():
         dist.destroy_process_group()
 
 
-def args_for_secondary(args):
+def args_for_secondary(args, workload="mixtral-q4k", layers=4):
     import copy
     a = copy.copy(args)
-    a.workload, a.qtype, a.layers = "mixtral-q4k", "Q4_K", 4
+    a.workload, a.qtype, a.layers = workload, "Q4_K", layers
     return a
 
 
-def secondary_q4k(args, pool, gpupool, modelhub, peak, write_peak):
-    """Kernel stage of a 4-layer Mixtral-8x7B q4_K GGUF (3.4 GB of blocks -> 12.1 GB of bf16) from the HBM-resident image, same timing rules as
-    `value`: >= 3 warm-ups, CUDA events on the launching stream inside the library, inputs far larger than L2."""
+def secondary_kernel_stage(args, pool, gpupool, modelhub, peak, write_peak, workload, layers, load_flags, what):
+    """Kernel stage of a second BASELINE workload from the HBM-resident image, same timing rules as `value`: >= 3 warm-ups, CUDA events on the
+    launching stream inside the library, inputs larger than L2."""
     from tools import synth
     t0 = time.time()
-    spec = dict(kind="gguf", tensors=synth.mixtral_gguf_tensors(layers=4), name="Mixtral-8x7B GGUF q4_k -> bf16 (REDUCED to 4 layers)")
+    a2 = args_for_secondary(args, workload, layers)
+    spec = workload_spec(a2)
     base = os.path.dirname(pick_data_dir(args, synth.total_bytes(spec["tensors"])))
-    d = os.path.join(base, "kk_bench_secondary_q4k_l4")
-    path = make_files(spec, d, args_for_secondary(args))
+    d = os.path.join(base, f"kk_bench_secondary_{workload}_{layers}")
+    path = make_files(spec, d, a2)
     synth_s = time.time() - t0
     try:
         ref = modelhub.Pull(path)
-        m = modelhub.Load(pool, ref, mode=gpupool.MODE_SINGLE, fanout=gpupool.FANOUT_P2P, flags=gpupool.LOAD_DEFER)
+        m = modelhub.Load(pool, ref, mode=gpupool.MODE_SINGLE, fanout=gpupool.FANOUT_P2P, flags=gpupool.LOAD_DEFER | load_flags)
         try:
             m.stage_resident()
             for _ in range(3):
@@ -829,12 +836,25 @@ def secondary_q4k(args, pool, gpupool, modelhub, peak, write_peak):
     alg = part["src_bytes"] + part["out_bytes"]
     ach = alg / (ms / 1e3) / 1e9
     wr = part["out_bytes"] / (ms / 1e3) / 1e9
-    return {"workload": spec["name"], "what": "kernel stage only (resident image), the expanding conversion of BASELINE config 4 at reduced depth", "steps": steps, "warmup": 3,
+    return {"workload": spec["name"], "what": what, "steps": steps, "warmup": 3,
             "ms_per_step": ms, "launches_per_step": n_launch, "src_bytes": part["src_bytes"], "out_bytes": part["out_bytes"], "synth_s": synth_s,
-            "value": part["out_bytes"] / (ms / 1e3) / 1e9, "unit": "GB/s of bf16 made resident",
+            "value": part["out_bytes"] / (ms / 1e3) / 1e9, "unit": "GB/s of pool bytes made resident",
             "roofline": {"bound": "hbm", "kernel": "kk_convert_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "algorithmic_bytes_per_step": alg, "write_GBps": wr, "write_peak_GBps": write_peak,
                          "hbm_write_frac": wr / write_peak if write_peak else None}}
+
+
+def secondary_q4k(args, pool, gpupool, modelhub, peak, write_peak):
+    """4-layer Mixtral-8x7B q4_K GGUF (3.4 GB of blocks -> 12.1 GB of bf16): the expanding conversion of BASELINE config 4 at reduced depth."""
+    return secondary_kernel_stage(args, pool, gpupool, modelhub, peak, write_peak, "mixtral-q4k", 4, 0,
+                                  "kernel stage only (resident image), the expanding conversion of BASELINE config 4 at reduced depth")
+
+
+def secondary_gpt2(args, pool, gpupool, modelhub, peak, write_peak):
+    """GPT-2-small f32 -> bf16 with the Conv1D weights transposed (BASELINE config 1's checkpoint, 0.5 GB; small: ~105 tiles per SM, so launch
+    ramp-up and tail are a visible part of its 0.15 ms)."""
+    return secondary_kernel_stage(args, pool, gpupool, modelhub, peak, write_peak, "gpt2", 0, gpupool.LOAD_GPT2_CONV1D_T,
+                                  "kernel stage only (resident image): BASELINE config 1's checkpoint, f32 -> bf16 casts + Conv1D transposes")
 
 
 def nccl_compare(torch, dist, file_bytes, world, local, args):
