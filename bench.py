@@ -78,11 +78,13 @@ def parse():
     ap.add_argument("--no-secondary", action="store_true", help="N = 1 default workload: skip the short Mixtral q4_K record (`secondary`)")
     ap.add_argument("--fanout", default="auto", choices=["auto", "p2p", "raw", "pull"],
                     help="broadcast order: fused convert+fan-out by P2P stores (p2p), all-gather the file bytes then convert locally (raw), or convert into own "
-                         "pool + slice buffer and pull the peers' slices (pull: peers map 1/N of the bytes).  auto = pull in the one-process-per-GPU shape "
-                         "this script runs in (its peer mappings are what time-to-ready is made of), p2p for transposing loads")
+                         "pool + slice buffer and pull the peers' slices (pull: peers map 1/N of the bytes).  auto = p2p (measured best on every count at N = 8)")
     a = ap.parse_args()
     if a.fanout == "auto":
-        a.fanout = "p2p" if a.workload == "gpt2" else "pull"
+        # Measured at N = 8 (profiles/README.md, round 2): with pools in 2 MiB multiples the seven 16 GB pool mappings of the P2P-store order take
+        # 0.05-0.07 s (3.6 s in round 1), so it has the shorter time-to-ready, the faster kernel stage (20.0 vs 25.2 ms) and the faster e2e step
+        # (156 vs 183 ms: its fan-out overlaps the ingest).  PULL stays available for deployments where peers must not map whole pools.
+        a.fanout = "p2p"
     return a
 
 
@@ -439,10 +441,20 @@ def main():
     t1 = time.time()
     handle, manifest = m.export(local)
     brk["export_s"] = time.time() - t1
+    brk["wall_before_final_barrier_s"] = time.time() - t_ready0
     barrier()
     t_ready = None if args.kernel_only else allmax(time.time() - t_ready0)
     t_ready_incl_open = None if t_ready is None else allmax(time.time() - t_ready0 + t_open)
     st0 = m.stats()
+    rd = st0.get("readers") or {}
+    if rd.get("threads"):  # where the reader threads of the cold load spent their time: average seconds per thread
+        for k in ("slot_wait_s", "pread_s", "issue_s", "drain_s"):
+            brk["readers_avg_" + k] = rd[k] / rd["threads"]
+    brk_max = None
+    if world > 1:  # the slowest rank decides time-to-ready: per component, the maximum over ranks and the rank that had it
+        allb = [None] * world
+        dist.all_gather_object(allb, brk, group=gloo)
+        brk_max = {k: (lambda vals: {"s": max(vals), "rank": vals.index(max(vals))})([b.get(k, 0.0) for b in allb]) for k in brk}
 
     # pinned H2D probe (plumbing; tells what the PCIe link of this box can do for the e2e leg)
     h2d_probe = None
@@ -714,6 +726,7 @@ def main():
         "time_to_agent_ready_s": t_ready,
         "time_to_agent_ready_incl_kk_open_s": t_ready_incl_open,
         "time_to_agent_ready_breakdown_rank0": brk,
+        "time_to_agent_ready_breakdown_max_over_ranks": brk_max,
         "wall_ms_per_step": wall / args.steps * 1e3,
         "setup": {"synth_s": t_gen, "kk_open_s": t_open, "index_s": st0["index_s"], "plan_s": st0["plan_s"], "alloc_s": st0["alloc_s"],
                   "first_load_s": st0["load_s"], "chunks_per_load": chunks_per_load, "h2d_probe_GBps": h2d_probe},

@@ -306,19 +306,24 @@ void run_part(kk_model* m, int li, int part, const FdSet& fds) {
   const bool zerocopy = (c->cfg.flags & KK_CFG_ZEROCOPY) != 0;
   std::atomic<size_t> next{0};
   ErrorSink sink;
+  auto ns = [] { return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   auto worker = [&](Reader* rd) {
     try {
       if (!(c->cfg.flags & KK_CFG_NO_NUMA_PIN)) pin_this_thread(dev.numa_cpus);
       KK_CUDA(cudaSetDevice(dev.ordinal));
       size_t k = 0;
+      uint64_t w_ns = 0, p_ns = 0, i_ns = 0;
       for (;;) {
         if (sink.stop) break;
         size_t ci = next.fetch_add(1);
         if (ci >= pp.chunks.size()) break;
         const Chunk& ch = pp.chunks[ci];
         Slot& s = rd->slots[k++ % rd->slots.size()];
+        const uint64_t t0 = ns();
         KK_CUDA(cudaEventSynchronize(s.done));
+        const uint64_t t1 = ns();
         read_chunk(ch, fds, m->plan.index, s.pinned);
+        const uint64_t t2 = ns();
         ConvertLaunch L = base;
         if (zerocopy) {
           L.src = s.pinned;
@@ -331,12 +336,18 @@ void run_part(kk_model* m, int li, int part, const FdSet& fds) {
         L.n_tiles = ch.n_tiles;
         KK_CUDA(launch_convert(L, dev.sm_count, rd->stream));
         KK_CUDA(cudaEventRecord(s.done, rd->stream));
+        w_ns += t1 - t0; p_ns += t2 - t1; i_ns += ns() - t2;
       }
+      const uint64_t t3 = ns();
       KK_CUDA(cudaStreamSynchronize(rd->stream));
+      m->rd_drain_ns += ns() - t3;
+      m->rd_wait_ns += w_ns; m->rd_pread_ns += p_ns; m->rd_issue_ns += i_ns;
     } catch (...) {
       sink.capture();
     }
   };
+  m->rd_wait_ns = 0; m->rd_pread_ns = 0; m->rd_issue_ns = 0; m->rd_drain_ns = 0;
+  m->rd_threads = (uint32_t)dev.readers.size();
   std::vector<std::thread> th;
   // every reader runs on its own (NUMA-pinned) thread; the caller's thread affinity is left alone
   for (size_t r = 0; r < dev.readers.size(); ++r) th.emplace_back(worker, &dev.readers[r]);
@@ -1220,7 +1231,8 @@ std::string model_stats(kk_model* m) {
     << ",\"file_bytes\":" << m->plan.file_bytes << ",\"pool_bytes\":" << m->plan.pool_bytes_of_part(m->local_parts[0])
     << ",\"n_parts\":" << m->plan.n_parts << ",\"local_src_bytes\":" << src << ",\"local_out_bytes\":" << out
     << ",\"index_s\":" << m->t_index << ",\"plan_s\":" << m->t_plan << ",\"alloc_s\":" << m->t_alloc << ",\"load_s\":" << m->t_load
-    << ",\"n_loads\":" << m->n_loads << ",\"load_gbps\":" << (m->t_load > 0 ? (double)src / m->t_load / 1e9 : 0.0) << ",\"parts\":[";
+    << ",\"n_loads\":" << m->n_loads << ",\"readers\":{\"threads\":" << m->rd_threads << ",\"slot_wait_s\":" << m->rd_wait_ns.load() / 1e9 << ",\"pread_s\":" << m->rd_pread_ns.load() / 1e9
+    << ",\"issue_s\":" << m->rd_issue_ns.load() / 1e9 << ",\"drain_s\":" << m->rd_drain_ns.load() / 1e9 << "},\"load_gbps\":" << (m->t_load > 0 ? (double)src / m->t_load / 1e9 : 0.0) << ",\"parts\":[";
   for (size_t li = 0; li < m->local_parts.size(); ++li) {
     const int part = m->local_parts[li];
     const PartPlan& pp = m->plan.parts[(size_t)part];

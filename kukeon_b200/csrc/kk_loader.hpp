@@ -124,6 +124,10 @@ struct kk_model {
   double t_index = 0, t_plan = 0, t_alloc = 0, t_load = 0;
   uint64_t n_loads = 0;
   std::vector<double> t_part;  // per local device wall seconds of the last load
+  // where the reader threads of the last kk_load_part spent their time, summed over threads (seconds): waiting for a free slot (= for the GPU
+  // to finish the chunk that used it), in pread, issuing the H2D copy + launch, and in the final stream synchronise; plus the thread count
+  std::atomic<uint64_t> rd_wait_ns{0}, rd_pread_ns{0}, rd_issue_ns{0}, rd_drain_ns{0};
+  uint32_t rd_threads = 0;
 };
 
 namespace kk {

@@ -24,9 +24,9 @@ def args_for(*argv):
 
 def test_defaults_follow_the_contract():
     a = args_for()
-    assert (a.gpus, a.impl, a.workload, a.fanout) == (1, "ours", "llama3-8b", "pull") and a.warmup >= 3 and a.steps >= 1  # fan-out only matters at N > 1
+    assert (a.gpus, a.impl, a.workload, a.fanout) == (1, "ours", "llama3-8b", "p2p") and a.warmup >= 3 and a.steps >= 1  # fan-out only matters at N > 1
     assert not (a.nvls_compare or a.kernel_only or a.no_secondary) and a.qtype == "Q4_K"
-    assert args_for("--workload", "gpt2").fanout == "p2p" and args_for("--fanout", "raw").fanout == "raw"  # transposing loads cannot be pulled slice by slice
+    assert args_for("--workload", "gpt2").fanout == "p2p" and args_for("--fanout", "raw").fanout == "raw" and args_for("--fanout", "pull").fanout == "pull"
 
 
 def test_workload_inventories_match_the_baseline_configs():
