@@ -202,6 +202,8 @@ def test_pull_fan_out_virtual_ranks_on_one_gpu(pool, tmp_path, n):
             for m in ms:
                 assert m.convert_local() >= 0.0
                 assert m.info()["loaded"]
+            if ms[0].stats()["parts"] and ms[1].stats()["parts"][0]["out_bytes"] >= 4096:
+                assert ms[0].probe_peer(1, gpupool.BUF_SLICE, 1 << 20) > 0.0  # copy-engine read of rank 1's attached slice buffer (here: the same GPU)
             for m in ms:
                 assert_pool_matches(m, 0, shards, recs)
             for m in ms:  # again through the resident image (what bench.py times)

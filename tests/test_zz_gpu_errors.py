@@ -81,5 +81,9 @@ def test_pull_argument_and_state_errors(pool, tmp_path):
         assert not m.info()["loaded"]
         with pytest.raises(gpupool.ErrState):
             m.peer_attach_buffer(1, gpupool.BUF_RAW, b"\0" * 64)
+        with pytest.raises(gpupool.ErrState, match="no attached buffer"):
+            m.probe_peer(1, gpupool.BUF_SLICE)
+        with pytest.raises(gpupool.ErrInvalid):
+            m.probe_peer(1, 99)
     finally:
         m.release()
