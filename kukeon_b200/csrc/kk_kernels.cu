@@ -266,10 +266,18 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
   if (warp == 0) {
     // ===== producer =====
     if (lane == 0) {
+      // Tile scheduling.  Static round-robin (tile = blockIdx.x + k * gridDim.x) leaves the SMs unevenly loaded although every CTA gets the same
+      // number of tiles: ncu showed sm__cycles_active at 0.86 of the kernel's duration for Q4_K and 0.92 for the bf16 copy, the fastest SM done
+      // at 0.80 — SMs do not all see the same memory (two dies, their own HBM stacks), and the kernel ends with the slowest CTA.  So after its
+      // first, static tile a CTA draws batches of kBatch tiles from a global counter; the draw for batch b + 1 is issued while batch b is being
+      // produced, so the atomic's round trip is off the critical path even for the copy op (0.75 us per tile).
+      constexpr uint32_t kBatch = 2;
       uint32_t cur = 0;
       KKSeg seg = load_seg(L.segs);
       uint32_t it = 0;
-      for (uint32_t tile = blockIdx.x; tile < L.n_tiles; tile += gridDim.x, ++it) {
+      uint32_t tile = blockIdx.x, batch_next = 0, batch_left = 0;
+      uint32_t pre = L.sched ? atomicAdd(L.sched, kBatch) : 0u;
+      for (; tile < L.n_tiles; ++it) {
         const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
         mbar_wait(empty0 + 8 * s, ph ^ 1u);
         uint32_t nxt = cur;
@@ -288,6 +296,32 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
           else
             for (uint32_t r = 0; r < ld.nrows; ++r) bulk_g2s(sb + r * ld.spitch, L.src + ld.g_off + (uint64_t)r * ld.gpitch, ld.row_bytes, full0 + 8 * s);
         }
+        if (!L.sched) {
+          tile += gridDim.x;
+        } else {
+          if (batch_left == 0) {
+            batch_next = gridDim.x + pre;
+            batch_left = kBatch;
+            pre = atomicAdd(L.sched, kBatch);
+          }
+          tile = batch_next++;
+          --batch_left;
+        }
+      }
+      // end marker for the consumers (they no longer know their tile count in advance)
+      {
+        const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+        mbar_wait(empty0 + 8 * s, ph ^ 1u);
+        descs[s].op = KK_OP_END;
+        mbar_arrive(full0 + 8 * s);
+      }
+      if (L.sched) {  // the last CTA to get here leaves the counters zeroed for the next launch on this stream
+        __threadfence();
+        if (atomicAdd(L.sched + 1, 1u) == gridDim.x - 1u) {
+          L.sched[0] = 0u;
+          L.sched[1] = 0u;
+          __threadfence();
+        }
       }
     }
   } else {
@@ -300,11 +334,11 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
     D.multimem = (L.flags & KK_LAUNCH_MULTIMEM) != 0;
     D.single = (L.n_dst == 1) && !D.multimem;
     int pending = -1;  // stage whose bulk stores may still be reading shared memory (warp 1 lane 0 only)
-    uint32_t it = 0;
-    for (uint32_t tile = blockIdx.x; tile < L.n_tiles; tile += gridDim.x, ++it) {
+    for (uint32_t it = 0;; ++it) {
       const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
       mbar_wait(full0 + 8 * s, ph);
       const TileDesc t = descs[s];
+      if (t.op == KK_OP_END) break;  // the producer's end marker
       const uint32_t sbase = smem_u32(stage_buf + s * kStageBytes);
       const uint32_t pay = sbase + t.pay_off;
       if (t.bulk == 1) {

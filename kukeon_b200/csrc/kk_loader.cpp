@@ -334,6 +334,7 @@ void run_part(kk_model* m, int li, int part, const FdSet& fds) {
         L.segs = d_segs + ch.seg_begin;
         L.n_segs = ch.seg_count;
         L.n_tiles = ch.n_tiles;
+        L.sched = rd->sched;
         KK_CUDA(launch_convert(L, dev.sm_count, rd->stream));
         KK_CUDA(cudaEventRecord(s.done, rd->stream));
         w_ns += t1 - t0; p_ns += t2 - t1; i_ns += ns() - t2;
@@ -412,7 +413,8 @@ void run_part_raw(kk_model* m, int li, int part, const FdSet& fds, bool fan_out)
           L.segs = R.d_copy_segs + m->chunk_base[(size_t)part] + ci;
           L.n_segs = 1;
           L.n_tiles = (uint32_t)kk_seg_tiles(KK_OP_COPY, align_up(ch.buf_bytes, 16), 0);
-          KK_CUDA(launch_convert(L, dev.sm_count, rd->stream));
+          L.sched = rd->sched;
+        KK_CUDA(launch_convert(L, dev.sm_count, rd->stream));
         }
         KK_CUDA(cudaEventRecord(s.done, rd->stream));
       }
@@ -526,6 +528,7 @@ void convert_local_all(kk_model* m, float* ms_total) {
       L.n_tiles = La.n_tiles;
       L.n_dst = 1;
       L.dst[0] = m->pools[li];
+      L.sched = dev.sched;
       KK_CUDA(launch_convert(L, dev.sm_count, dev.stream));
     }
     KK_CUDA(cudaEventRecord(e1[li], dev.stream));
@@ -594,7 +597,8 @@ void pull_slices(kk_model* m, float* ms_total) {
     L.n_dst = 1;
     L.dst[0] = m->pools[0];
     KK_CUDA(cudaEventRecord(ev[0], dev.stream));
-    KK_CUDA(launch_convert(L, dev.sm_count, dev.stream));
+    L.sched = dev.sched;
+      KK_CUDA(launch_convert(L, dev.sm_count, dev.stream));
     KK_CUDA(cudaEventRecord(ev[1], dev.stream));
     KK_CUDA(cudaStreamSynchronize(dev.stream));  // tmp outlives the launch
   }
@@ -704,6 +708,8 @@ kk_ctx* ctx_open(const kk_config& cfg_in) {
       KK_CUDA(kernels_init_device());
       d.kernels_ready = true;
       KK_CUDA(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+      KK_CUDA(cudaMalloc((void**)&d.sched, 256));
+      KK_CUDA(cudaMemset(d.sched, 0, 256));
       d.numa_cpus = numa_cpus_of_device(d.ordinal);
       d.readers.resize(cfg.n_reader_threads);
       // allocate (and thereby first-touch / pin) the slots from a thread bound to the device's NUMA node
@@ -714,6 +720,8 @@ kk_ctx* ctx_open(const kk_config& cfg_in) {
       for (uint32_t r = 0; r < cfg.n_reader_threads; ++r) {
         Reader& rd = d.readers[r];
         KK_CUDA(cudaStreamCreateWithFlags(&rd.stream, cudaStreamNonBlocking));
+        KK_CUDA(cudaMalloc((void**)&rd.sched, 256));
+        KK_CUDA(cudaMemset(rd.sched, 0, 256));
         uint32_t ns = cfg.n_staging_buffers / cfg.n_reader_threads + (r < cfg.n_staging_buffers % cfg.n_reader_threads ? 1 : 0);
         rd.slots.resize(ns);
         for (auto& s : rd.slots) {
@@ -775,8 +783,10 @@ void ctx_close(kk_ctx* c) {
         if (s.pinned) cudaFreeHost(s.pinned);
       }
       if (rd.stream) cudaStreamDestroy(rd.stream);
+      if (rd.sched) cudaFree(rd.sched);
     }
     if (d.stream) cudaStreamDestroy(d.stream);
+    if (d.sched) cudaFree(d.sched);
   }
   delete c;
 }
@@ -1376,6 +1386,7 @@ static void raw_fanout_resident(kk_model* m, float* ms_total, float* ms_per_laun
       L.segs = d_tmp;
       L.n_segs = (uint32_t)segs.size();
       L.n_tiles = tiles;
+      L.sched = dev.sched;
       KK_CUDA(launch_convert(L, dev.sm_count, dev.stream));
       KK_CUDA(cudaEventRecord(e1[li], dev.stream));
       KK_CUDA(cudaStreamSynchronize(dev.stream));  // tmp is freed on scope exit, after the launch that reads it has finished
@@ -1427,6 +1438,7 @@ void model_convert_resident(kk_model* m, float* ms_total, float* ms_per_launch, 
       L.segs = R.d_segs + R.launches[k].seg_begin;
       L.n_segs = R.launches[k].n_segs;
       L.n_tiles = R.launches[k].n_tiles;
+      L.sched = dev.sched;
       KK_CUDA(launch_convert(L, dev.sm_count, dev.stream));
     }
     KK_CUDA(cudaEventRecord(evs[li][R.launches.size()], dev.stream));

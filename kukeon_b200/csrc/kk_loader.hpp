@@ -32,6 +32,7 @@ struct Slot {
 
 struct Reader {
   cudaStream_t stream = nullptr;
+  uint32_t* sched = nullptr;  // two zeroed device words: the tile-scheduling counters of the launches on `stream` (ConvertLaunch::sched)
   std::vector<Slot> slots;
 };
 
@@ -43,6 +44,7 @@ struct Device {
   int sm_count = 0;
   std::vector<Reader> readers;
   cudaStream_t stream = nullptr;  // resident launches, checksum, misc
+  uint32_t* sched = nullptr;      // tile-scheduling counters of the launches on `stream`
   uint64_t pool_in_use = 0;
   bool kernels_ready = false;
   std::vector<int> numa_cpus;  // CPUs local to the device's PCIe root (reader threads are pinned there)

@@ -120,7 +120,8 @@ enum KKOp : uint32_t {
   KK_OP_TQ1_0_BF16 = 36,
   KK_OP_TQ2_0_BF16 = 37,
   KK_OP_NVFP4_BF16 = 38,
-  KK_OP_COUNT = 39
+  KK_OP_COUNT = 39,
+  KK_OP_END = 0xFFFFFFFFu  // never in a segment table: the producer warp's end-of-work marker in the stage descriptor ring
 };
 
 struct KKSeg {
