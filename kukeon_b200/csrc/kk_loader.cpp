@@ -293,6 +293,13 @@ void fill_dsts(kk_model* m, int li, ConvertLaunch& L) {
   pad_dsts_for_test(L);
 }
 
+// Tile scheduling of a launch: dynamic (counters of the launching stream) except for transposing loads.  Their 16-byte column stores fill a
+// 32-byte sector only together with the neighbouring row group's tile, and under static round-robin those two tiles run at about the same time
+// on different SMs and meet in L2; with dynamic draws GPT-2-small measured 0.173 ms against 0.146 ms static (profiles/r02/gpt2_quick_{e,h}.json).
+uint32_t* sched_for(const kk_model* m, uint32_t* stream_counters) {
+  return (m->plan.flags & KK_LOAD_GPT2_CONV1D_T) ? nullptr : stream_counters;
+}
+
 // Ingest plan part `part` on local device `li`.
 void run_part(kk_model* m, int li, int part, const FdSet& fds) {
   kk_ctx* c = m->ctx;
@@ -334,7 +341,7 @@ void run_part(kk_model* m, int li, int part, const FdSet& fds) {
         L.segs = d_segs + ch.seg_begin;
         L.n_segs = ch.seg_count;
         L.n_tiles = ch.n_tiles;
-        L.sched = rd->sched;
+        L.sched = sched_for(m, rd->sched);
         KK_CUDA(launch_convert(L, dev.sm_count, rd->stream));
         KK_CUDA(cudaEventRecord(s.done, rd->stream));
         w_ns += t1 - t0; p_ns += t2 - t1; i_ns += ns() - t2;
@@ -413,7 +420,7 @@ void run_part_raw(kk_model* m, int li, int part, const FdSet& fds, bool fan_out)
           L.segs = R.d_copy_segs + m->chunk_base[(size_t)part] + ci;
           L.n_segs = 1;
           L.n_tiles = (uint32_t)kk_seg_tiles(KK_OP_COPY, align_up(ch.buf_bytes, 16), 0);
-          L.sched = rd->sched;
+          L.sched = sched_for(m, rd->sched);
         KK_CUDA(launch_convert(L, dev.sm_count, rd->stream));
         }
         KK_CUDA(cudaEventRecord(s.done, rd->stream));
@@ -528,7 +535,7 @@ void convert_local_all(kk_model* m, float* ms_total) {
       L.n_tiles = La.n_tiles;
       L.n_dst = 1;
       L.dst[0] = m->pools[li];
-      L.sched = dev.sched;
+      L.sched = sched_for(m, dev.sched);
       KK_CUDA(launch_convert(L, dev.sm_count, dev.stream));
     }
     KK_CUDA(cudaEventRecord(e1[li], dev.stream));
@@ -597,7 +604,7 @@ void pull_slices(kk_model* m, float* ms_total) {
     L.n_dst = 1;
     L.dst[0] = m->pools[0];
     KK_CUDA(cudaEventRecord(ev[0], dev.stream));
-    L.sched = dev.sched;
+    L.sched = sched_for(m, dev.sched);
       KK_CUDA(launch_convert(L, dev.sm_count, dev.stream));
     KK_CUDA(cudaEventRecord(ev[1], dev.stream));
     KK_CUDA(cudaStreamSynchronize(dev.stream));  // tmp outlives the launch
@@ -1386,7 +1393,7 @@ static void raw_fanout_resident(kk_model* m, float* ms_total, float* ms_per_laun
       L.segs = d_tmp;
       L.n_segs = (uint32_t)segs.size();
       L.n_tiles = tiles;
-      L.sched = dev.sched;
+      L.sched = sched_for(m, dev.sched);
       KK_CUDA(launch_convert(L, dev.sm_count, dev.stream));
       KK_CUDA(cudaEventRecord(e1[li], dev.stream));
       KK_CUDA(cudaStreamSynchronize(dev.stream));  // tmp is freed on scope exit, after the launch that reads it has finished
@@ -1438,7 +1445,7 @@ void model_convert_resident(kk_model* m, float* ms_total, float* ms_per_launch, 
       L.segs = R.d_segs + R.launches[k].seg_begin;
       L.n_segs = R.launches[k].n_segs;
       L.n_tiles = R.launches[k].n_tiles;
-      L.sched = dev.sched;
+      L.sched = sched_for(m, dev.sched);
       KK_CUDA(launch_convert(L, dev.sm_count, dev.stream));
     }
     KK_CUDA(cudaEventRecord(evs[li][R.launches.size()], dev.stream));

@@ -8,11 +8,10 @@
 #define KK_STAGE_PAD 128u        /* slack so a 16-B-aligned superset of a misaligned tile still fits */
 #define KK_Q4K_BLOCK_BYTES 144u
 #define KK_Q4K_BLOCK_ELEMS 256u
-#ifndef KK_Q4K_TILE_BLOCKS /* overridable only for the tile-size sweep of tools/r02 (make EXTRA=-DKK_Q4K_TILE_BLOCKS=..) */
 #define KK_Q4K_TILE_BLOCKS 224u  /* 224*144 = 32256 B in, 224*512 = 114688 B out.  16 consumer warps x 4 blocks = 64 blocks per sweep, so 3.5 sweeps; measured
                                     against 192-block tiles (3 full sweeps), contiguous 14-block runs per warp, a rotated warp order and 20 warps
-                                    (profiles/r02/q4k_ab_*.json): all within 2 % and none faster, so the simplest form stays */
-#endif
+                                    (profiles/r02/q4k_ab_*.json): all within 2 % and none faster, so the simplest form stays.  Swept again under dynamic tile
+                                    scheduling (186 / 200 / 208 / 216 / 221 / 223 blocks, profiles/r02/q4k_tile_sweep_h.txt): 1.642 - 1.671 ms against 1.651 */
 #define KK_Q8_0_BLOCK_BYTES 34u
 #define KK_Q8_0_BLOCK_ELEMS 32u
 #define KK_Q8_0_TILE_BLOCKS 960u /* 960*34 = 32640 B in (a multiple of 16), 960*64 = 61440 B out */
