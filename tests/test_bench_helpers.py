@@ -77,3 +77,16 @@ def test_pending_gpu_scripts_point_at_things_that_exist():
             path = os.path.join(root, rel)
             assert os.path.exists(path), (sh, rel)
             ast.parse(open(path).read(), rel)
+
+
+def test_page_cache_warm_up_stripes_every_byte_over_the_ranks(tmp_path):
+    """bench.warm_page_cache: the ranks' stripes (32 MiB blocks dealt round-robin) cover every byte of every file exactly once; hidden files
+    (the .complete marker) are not data."""
+    d = tmp_path / "ck"
+    d.mkdir()
+    (d / "a.bin").write_bytes(b"x" * (70 << 20))
+    (d / "b.bin").write_bytes(b"y" * (5 << 20))
+    (d / ".complete").write_text("ok")
+    per_rank = [bench.warm_page_cache(str(d), r, 3, passes=1, threads=2) for r in range(3)]
+    assert sum(per_rank) == (70 << 20) + (5 << 20) and all(per_rank)
+    assert bench.warm_page_cache(str(d), 0, 1, passes=1, threads=3) == (75 << 20)
