@@ -297,6 +297,13 @@ void fill_dsts(kk_model* m, int li, ConvertLaunch& L) {
 // 32-byte sector only together with the neighbouring row group's tile, and under static round-robin those two tiles run at about the same time
 // on different SMs and meet in L2; with dynamic draws GPT-2-small measured 0.173 ms against 0.146 ms static (profiles/r02/gpt2_quick_{e,h}.json).
 uint32_t* sched_for(const kk_model* m, uint32_t* stream_counters) {
+  // measurement knob (A/B of the two schedulers on one box; not part of the API): KUKEON_GPULOAD_SCHED=static | dynamic forces one
+  static const int forced = [] {
+    const char* e = getenv("KUKEON_GPULOAD_SCHED");
+    return !e ? 0 : !strcmp(e, "static") ? 1 : !strcmp(e, "dynamic") ? 2 : 0;
+  }();
+  if (forced == 1) return nullptr;
+  if (forced == 2) return stream_counters;
   return (m->plan.flags & KK_LOAD_GPT2_CONV1D_T) ? nullptr : stream_counters;
 }
 
@@ -704,43 +711,50 @@ kk_ctx* ctx_open(const kk_config& cfg_in) {
   c->slot_bytes = align_up(cfg.staging_buffer_bytes, 2ull << 20);
   c->devs.resize((size_t)cfg.n_devices);
   try {
+    // One thread per device, all at once: the pinned ring (cudaHostAlloc pins and maps 0.5 GiB per device by default) dominates kk_open, and eight
+    // devices set up one after the other cost 4.7 s in the one-process shape (profiles/r02/bench_n8_head.json: single_process.kk_open_s).  Each
+    // thread is bound to its device's NUMA node, so the slots are first-touched / pinned there.
+    std::vector<std::exception_ptr> errs((size_t)cfg.n_devices);
+    std::vector<std::thread> setup;
     for (int i = 0; i < cfg.n_devices; ++i) {
-      Device& d = c->devs[(size_t)i];
-      d.ordinal = cfg.devices[i];
-      KK_CUDA(cudaSetDevice(d.ordinal));
-      cudaDeviceProp prop;
-      KK_CUDA(cudaGetDeviceProperties(&prop, d.ordinal));
-      if (prop.major < 10) fail(KK_EUNSUPPORTED, "device %d is sm_%d%d; this build carries sm_100a code only", d.ordinal, prop.major, prop.minor);
-      d.sm_count = prop.multiProcessorCount;
-      KK_CUDA(kernels_init_device());
-      d.kernels_ready = true;
-      KK_CUDA(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
-      KK_CUDA(cudaMalloc((void**)&d.sched, 256));
-      KK_CUDA(cudaMemset(d.sched, 0, 256));
-      d.numa_cpus = numa_cpus_of_device(d.ordinal);
-      d.readers.resize(cfg.n_reader_threads);
-      // allocate (and thereby first-touch / pin) the slots from a thread bound to the device's NUMA node
-      std::exception_ptr alloc_err;
-      std::thread alloc([&] { try {
-      if (!(cfg.flags & KK_CFG_NO_NUMA_PIN)) pin_this_thread(d.numa_cpus);
-      KK_CUDA(cudaSetDevice(d.ordinal));
-      for (uint32_t r = 0; r < cfg.n_reader_threads; ++r) {
-        Reader& rd = d.readers[r];
-        KK_CUDA(cudaStreamCreateWithFlags(&rd.stream, cudaStreamNonBlocking));
-        KK_CUDA(cudaMalloc((void**)&rd.sched, 256));
-        KK_CUDA(cudaMemset(rd.sched, 0, 256));
-        uint32_t ns = cfg.n_staging_buffers / cfg.n_reader_threads + (r < cfg.n_staging_buffers % cfg.n_reader_threads ? 1 : 0);
-        rd.slots.resize(ns);
-        for (auto& s : rd.slots) {
-          KK_CUDA(cudaHostAlloc((void**)&s.pinned, c->slot_bytes + 256, cudaHostAllocPortable | cudaHostAllocMapped));
-          if (!(cfg.flags & KK_CFG_ZEROCOPY)) KK_CUDA(cudaMalloc((void**)&s.dev, c->slot_bytes + 256));
-          KK_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+      c->devs[(size_t)i].ordinal = cfg.devices[i];
+      setup.emplace_back([&, i] {
+        try {
+          Device& d = c->devs[(size_t)i];
+          KK_CUDA(cudaSetDevice(d.ordinal));
+          cudaDeviceProp prop;
+          KK_CUDA(cudaGetDeviceProperties(&prop, d.ordinal));
+          if (prop.major < 10) fail(KK_EUNSUPPORTED, "device %d is sm_%d%d; this build carries sm_100a code only", d.ordinal, prop.major, prop.minor);
+          d.sm_count = prop.multiProcessorCount;
+          KK_CUDA(kernels_init_device());
+          d.kernels_ready = true;
+          KK_CUDA(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+          KK_CUDA(cudaMalloc((void**)&d.sched, 256));
+          KK_CUDA(cudaMemset(d.sched, 0, 256));
+          d.numa_cpus = numa_cpus_of_device(d.ordinal);
+          d.readers.resize(cfg.n_reader_threads);
+          if (!(cfg.flags & KK_CFG_NO_NUMA_PIN)) pin_this_thread(d.numa_cpus);
+          for (uint32_t r = 0; r < cfg.n_reader_threads; ++r) {
+            Reader& rd = d.readers[r];
+            KK_CUDA(cudaStreamCreateWithFlags(&rd.stream, cudaStreamNonBlocking));
+            KK_CUDA(cudaMalloc((void**)&rd.sched, 256));
+            KK_CUDA(cudaMemset(rd.sched, 0, 256));
+            uint32_t ns = cfg.n_staging_buffers / cfg.n_reader_threads + (r < cfg.n_staging_buffers % cfg.n_reader_threads ? 1 : 0);
+            rd.slots.resize(ns);
+            for (auto& s : rd.slots) {
+              KK_CUDA(cudaHostAlloc((void**)&s.pinned, c->slot_bytes + 256, cudaHostAllocPortable | cudaHostAllocMapped));
+              if (!(cfg.flags & KK_CFG_ZEROCOPY)) KK_CUDA(cudaMalloc((void**)&s.dev, c->slot_bytes + 256));
+              KK_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+            }
+          }
+        } catch (...) {
+          errs[(size_t)i] = std::current_exception();
         }
-      }
-      } catch (...) { alloc_err = std::current_exception(); } });
-      alloc.join();
-      if (alloc_err) std::rethrow_exception(alloc_err);
+      });
     }
+    for (auto& t : setup) t.join();
+    for (auto& e : errs)
+      if (e) std::rethrow_exception(e);
     if (cfg.flags & KK_CFG_PEER_ALL) {
       for (int i = 0; i < cfg.n_devices; ++i) {
         KK_CUDA(cudaSetDevice(cfg.devices[i]));
