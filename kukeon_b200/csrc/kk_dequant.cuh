@@ -299,16 +299,18 @@ KK_DQ_DEV void consume_t(const Dsts& D, uint32_t sbase, uint32_t pitch, uint32_t
     const uint64_t off = dst_off + ((uint64_t)(col0 + c) * R + row0) * OES;
     if (CONV == 3) {
       if (vec) {
-        store16_all(D, off, make_uint4(v[0], v[1], v[2], v[3]));
-        store16_all(D, off + 16u, make_uint4(v[4], v[5], v[6], v[7]));
+#pragma unroll
+        for (uint32_t g = 0; g < KK_T_ROWS / 4u; ++g) store16_all(D, off + 16u * g, make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]));
       } else {
 #pragma unroll
         for (uint32_t k = 0; k < KK_T_ROWS; ++k)
           if (k < nr) store4_all(D, off + 4u * k, v[k]);
       }
     } else if (vec) {
-      store16_all(D, off, make_uint4(t_pack2<ES, CONV>(v[0], v[1]), t_pack2<ES, CONV>(v[2], v[3]), t_pack2<ES, CONV>(v[4], v[5]),
-                                     t_pack2<ES, CONV>(v[6], v[7])));
+#pragma unroll
+      for (uint32_t g = 0; g < KK_T_ROWS / 8u; ++g)
+        store16_all(D, off + 16u * g, make_uint4(t_pack2<ES, CONV>(v[8 * g], v[8 * g + 1]), t_pack2<ES, CONV>(v[8 * g + 2], v[8 * g + 3]),
+                                                 t_pack2<ES, CONV>(v[8 * g + 4], v[8 * g + 5]), t_pack2<ES, CONV>(v[8 * g + 6], v[8 * g + 7])));
     } else {
 #pragma unroll
       for (uint32_t k = 0; k < KK_T_ROWS; ++k)
