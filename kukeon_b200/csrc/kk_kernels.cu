@@ -243,6 +243,10 @@ __device__ __forceinline__ KKSeg load_seg(const KKSeg* p) {
   return s;
 }
 
+// DYN: tiles after the first are drawn from L.sched (see the producer); !DYN: static round-robin, the consumers count their tiles themselves —
+// exactly the round-1 loops.  Two instantiations rather than a run-time switch: with the switch the STATIC path of the transposing load measured
+// 0.161 ms where the dedicated loops take 0.148 ms (same box, libraries built from the commits in between: profiles/r02/gpu_call_m.log).
+template <bool DYN>
 __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLaunch L) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* stage_buf = smem;
@@ -276,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
       KKSeg seg = load_seg(L.segs);
       uint32_t it = 0;
       uint32_t tile = blockIdx.x, batch_next = 0, batch_left = 0;
-      uint32_t pre = L.sched ? atomicAdd(L.sched, kBatch) : 0u;
+      uint32_t pre = DYN ? atomicAdd(L.sched, kBatch) : 0u;
       for (; tile < L.n_tiles; ++it) {
         const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
         mbar_wait(empty0 + 8 * s, ph ^ 1u);
@@ -296,7 +300,7 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
           else
             for (uint32_t r = 0; r < ld.nrows; ++r) bulk_g2s(sb + r * ld.spitch, L.src + ld.g_off + (uint64_t)r * ld.gpitch, ld.row_bytes, full0 + 8 * s);
         }
-        if (!L.sched) {
+        if (!DYN) {
           tile += gridDim.x;
         } else {
           if (batch_left == 0) {
@@ -308,14 +312,14 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
           --batch_left;
         }
       }
-      // end marker for the consumers (they no longer know their tile count in advance)
-      {
+      // end marker for the consumers (under dynamic draws they do not know their tile count in advance)
+      if (DYN) {
         const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
         mbar_wait(empty0 + 8 * s, ph ^ 1u);
         descs[s].op = KK_OP_END;
         mbar_arrive(full0 + 8 * s);
       }
-      if (L.sched) {  // the last CTA to get here leaves the counters zeroed for the next launch on this stream
+      if (DYN) {  // the last CTA to get here leaves the counters zeroed for the next launch on this stream
         __threadfence();
         if (atomicAdd(L.sched + 1, 1u) == gridDim.x - 1u) {
           L.sched[0] = 0u;
@@ -334,11 +338,12 @@ __global__ void __launch_bounds__(kThreads, 1) kk_convert_kernel(const ConvertLa
     D.multimem = (L.flags & KK_LAUNCH_MULTIMEM) != 0;
     D.single = (L.n_dst == 1) && !D.multimem;
     int pending = -1;  // stage whose bulk stores may still be reading shared memory (warp 1 lane 0 only)
-    for (uint32_t it = 0;; ++it) {
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; DYN || tile < L.n_tiles; tile += gridDim.x, ++it) {
       const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
       mbar_wait(full0 + 8 * s, ph);
       const TileDesc t = descs[s];
-      if (t.op == KK_OP_END) break;  // the producer's end marker
+      if (DYN && t.op == KK_OP_END) break;  // the producer's end marker
       const uint32_t sbase = smem_u32(stage_buf + s * kStageBytes);
       const uint32_t pay = sbase + t.pay_off;
       if (t.bulk == 1) {
@@ -500,8 +505,9 @@ __global__ void __launch_bounds__(256) kk_fill_kernel(uint4* __restrict__ dst, u
 }  // namespace
 
 cudaError_t kernels_init_device() {
-  return cudaFuncSetAttribute(kk_convert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)(kSmemFixed + 4 * kMaxSegsPerLaunch + 128));
+  cudaError_t e = cudaFuncSetAttribute(kk_convert_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemFixed + 4 * kMaxSegsPerLaunch + 128));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(kk_convert_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemFixed + 4 * kMaxSegsPerLaunch + 128));
 }
 
 cudaError_t launch_convert(const ConvertLaunch& L, int sm_count, cudaStream_t stream) {
@@ -509,7 +515,8 @@ cudaError_t launch_convert(const ConvertLaunch& L, int sm_count, cudaStream_t st
   if (L.n_segs == 0 || L.n_segs > kMaxSegsPerLaunch || L.n_dst == 0 || L.n_dst > KK_MAX_DST) return cudaErrorInvalidValue;
   const uint32_t grid = L.n_tiles < (uint32_t)sm_count ? L.n_tiles : (uint32_t)sm_count;
   const size_t smem = kSmemFixed + 4 * (size_t)L.n_segs + 16;
-  kk_convert_kernel<<<grid, kThreads, smem, stream>>>(L);
+  if (L.sched) kk_convert_kernel<true><<<grid, kThreads, smem, stream>>>(L);
+  else kk_convert_kernel<false><<<grid, kThreads, smem, stream>>>(L);
   return cudaGetLastError();
 }
 

@@ -64,10 +64,8 @@
  * tile spans whole rows, which are then contiguous in the source); consumers read along rows — conflict-free at any pitch — and every thread packs
  * the 8 rows of one column into a single 16-byte store.  Measured on GPT-2-small against 32x128 tiles (0.36 of the copy peak) and 32-row x 960-byte
  * wide-store tiles (0.58): 0.80 (profiles/r02/t8_ab_*.json) — the other two geometries are gone. */
-#ifndef KK_T_ROWS                /* (overridable together with KK_T_ROW_BYTES for the tile-shape A/B of tools/r02; rows a multiple of 8, rows x bytes <= 32 KiB) */
-#define KK_T_ROWS 8u
-#define KK_T_ROW_BYTES 4096u     /* per staged row: 1024 32-bit or 2048 16-bit columns */
-#endif
+#define KK_T_ROWS 8u             /* a multiple of 8; 16 x 2 KiB and 32 x 1 KiB tiles (whole-sector stores per thread) measured SLOWER: 0.195 / 0.211 ms */
+#define KK_T_ROW_BYTES 4096u     /* against 0.160 ms on GPT-2-small, profiles/r02/gpu_call_l.log.  Per staged row: 1024 32-bit or 2048 16-bit columns */
 #define KK_MAX_DST 8
 /* ConvertLaunch::flags */
 #define KK_LAUNCH_NO_BULK_STORE 0x1u  /* force the register path for aligned copies (A/B measurement) */
