@@ -12,7 +12,7 @@ content, files warm in tmpfs/page cache.  A "step" = one pass of the hot path ov
   ranks.  At N > 1 every rank converts 1/N of the checkpoint and the same kernel stores it into all N pools over
   NVLink (P2P), so value counts N x checkpoint bytes made resident per step ("weak": bytes per pool fixed).
 * `e2e`    (GB/s): the same through the public call a user makes (modelhub.Load -> kk_load_part) with HOST
-  buffers: pread from the warm files into the pinned ring, H2D copies, kernels, and a device->host read of a
+  buffers: CPU copy from the warm files into the pinned ring, H2D copies, kernels, and a device->host read of a
   result (pool checksum word) plus kk_export, all inside the timed region.
 * `roofline`: dominant kernel kk_convert_kernel.  N = 1: bound "hbm", algorithmic bytes = 2 x shard bytes (2 B read + 2 B written
   per bf16 element) / its CUDA-event duration, against MEASURED_PEAKS.json's hbm_gbs.  N > 1 broadcast: bound "nvlink", the
@@ -28,6 +28,7 @@ The reference (eminwux/kukeon) has no loader and Go is absent, so `--impl refere
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import shutil
@@ -553,25 +554,44 @@ def main():
     # ---- e2e: public API with host buffers (pread -> pinned -> H2D -> kernels -> export + D2H result) ---------
     first = m.placements(ref.tensors[0]["name"])[0]
 
+    step_detail = []
+
     def e2e_step():
         barrier()
         t = time.perf_counter()
         m.load_part()
+        t_lp = time.perf_counter() - t
         if two_stage:
             barrier()
             m.convert_local()
         m.export(local)
         m.checksum(local, first.pool_offset, min(first.nbytes, 1 << 20))  # 8-byte D2H result read
         dt = time.perf_counter() - t
+        if args.e2e_only:  # tuning aid: where this step's time went (outside the timed region)
+            st = m.stats()
+            rd = st.get("readers") or {}
+            n = max(rd.get("threads", 1), 1)
+            step_detail.append({"ms": dt * 1e3, "load_part_ms": t_lp * 1e3, "load_s": st.get("load_s"), "files_open_s": rd.get("files_open_s"), "files_close_s": rd.get("files_close_s"),
+                                "reader_avg": {k: rd.get(k, 0) / n for k in ("slot_wait_s", "pread_s", "issue_s", "drain_s")}})
         barrier()
         return dt
 
     if args.kernel_only:
         e2e_ts = [float("nan")]
     else:
-        for _ in range(args.warmup):
-            e2e_step()
-        e2e_ts = [allmax(e2e_step()) for _ in range(args.steps)]
+        # The harness's own garbage collector stays out of the timed steps: a generation-2 pass over a torch-sized heap is 50-150 ms, a third of a
+        # step (it showed as one step in six taking 0.46 s while kk_load_part took its usual 0.30 s, profiles/r02/e2e_read_modes_q.jsonl); a Go or
+        # C++ caller of the C ABI has no such pause.
+        gc.collect()
+        gc.freeze()
+        gc.disable()
+        try:
+            for _ in range(args.warmup):
+                e2e_step()
+            e2e_ts = [allmax(e2e_step()) for _ in range(args.steps)]
+        finally:
+            gc.enable()
+            gc.unfreeze()
     e2e_time = sum(e2e_ts)
     delivered = (pool_bytes if mode == gpupool.MODE_SCATTER else file_bytes) * (1 if mode == gpupool.MODE_SCATTER else world)
     if mode == gpupool.MODE_SCATTER:
@@ -583,7 +603,8 @@ def main():
     # ---- value: kernel stage from the HBM-resident image ---------------------------------------------------
     if args.e2e_only:
         line = {"metric": METRIC, "e2e_only": True, "n_gpus": N, "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_time / args.steps * 1e3},
-                "time_to_agent_ready_s": t_ready, "h2d_probe_GBps": h2d_probe,
+                "time_to_agent_ready_s": t_ready, "h2d_probe_GBps": h2d_probe, "readers_last_step": m.stats().get("readers"),
+                "read_mode": os.environ.get("KUKEON_GPULOAD_READ", "auto"), "e2e_ms_each": [t * 1e3 for t in e2e_ts], "steps_detail": step_detail[-args.steps:],
                 "config": {"readers": args.readers, "slots": args.slots, "slot_mb": args.slot_mb, "zerocopy": args.zerocopy, "numa_pin": not args.no_numa_pin,
                            "chunks_per_load": chunks_per_load, "kk_open_s": t_open}}
         m.release()
@@ -757,12 +778,13 @@ def main():
                    "mode": {0: "single", 1: "broadcast (sharded ingest + fused P2P fan-out)",
                             2: "scatter" + (" (row-parallel tensors exchanged over NVLink: KK_LOAD_SCATTER_EXCHANGE)" if exchange else "")}[mode], "pool_bytes_per_gpu": pool_bytes,
                    "l2": "inputs (>= 2 GB per GPU) far larger than the 126 MB L2; no flush needed", "files": f"warm in {os.path.dirname(d) or d}: written, then read twice by the ranks before anything is timed" + (", pages interleaved over the host's NUMA nodes (set_mempolicy while writing)" if _INTERLEAVED else ""),
-                   "staging": "zero-copy pinned reads" if args.zerocopy else "pinned ring + H2D copy engine", "verified_vs_files": verified,
+                   "staging": "zero-copy pinned reads" if args.zerocopy else "pinned ring + H2D copy engine", "read_mode": os.environ.get("KUKEON_GPULOAD_READ", "auto (tmpfs shards: mapping + streaming stores + per-range MADV_DONTNEED; other file systems: pread)"), "verified_vs_files": verified,
                    **({"transpose_tiles": "8 source rows x <= 4 KiB, thread = column, 16-byte stores"} if spec["kind"] == "gpt2" else {})},
         "clocks": ck,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(allsum(float(local_src))), "d2h_bytes_per_step": 8 * world,
-                "ms_per_step": e2e_time / args.steps * 1e3, "file_GBps": file_read * args.steps / e2e_time / 1e9 if e2e_time == e2e_time else None,
-                "what": "kk_load_part (pread->pinned->H2D->kernels) + kk_export + checksum word D2H; `value` counts the bytes made resident in all N pools "
+                "ms_per_step": e2e_time / args.steps * 1e3, "ms_each": [t * 1e3 for t in e2e_ts], "python_gc": "collected and frozen before, disabled during the e2e steps",
+                "file_GBps": file_read * args.steps / e2e_time / 1e9 if e2e_time == e2e_time else None,
+                "what": "kk_load_part (page cache->pinned->H2D->kernels) + kk_export + checksum word D2H; `value` counts the bytes made resident in all N pools "
                         "(N x checkpoint for a broadcast), `file_GBps` the checkpoint bytes read from the files once per step"},
         "gpu_launches": n_launch * args.steps,
         "roofline": roofline,

@@ -408,20 +408,16 @@ int kk_checksum(kk_model* m, int device, uint64_t off, uint64_t nbytes, uint64_t
     if (off % 8) kk::fail(KK_EINVAL, "pool_offset must be a multiple of 8");
     kk::Device& d = m->ctx->devs[(size_t)m->dev_idx[(size_t)li]];
     KK_CUDA(cudaSetDevice(device));
-    unsigned long long* acc = nullptr;
-    KK_CUDA(cudaMalloc((void**)&acc, 8));
-    try {
-      KK_CUDA(cudaMemsetAsync(acc, 0, 8, d.stream));
-      KK_CUDA(kk::launch_checksum(m->pools[(size_t)li] + off, nbytes, acc, d.sm_count, d.stream));
-      unsigned long long h = 0;
-      KK_CUDA(cudaMemcpyAsync(&h, acc, 8, cudaMemcpyDeviceToHost, d.stream));
-      KK_CUDA(cudaStreamSynchronize(d.stream));
-      *out = h;
-    } catch (...) {
-      cudaFree(acc);
-      throw;
-    }
-    cudaFree(acc);
+    // the accumulator lives in the device's scratch words: a cudaMalloc + cudaFree pair per call synchronises the whole device and measured
+    // 70-170 ms every few calls next to a 16 GB pool (profiles/r02/e2e_read_modes_q.jsonl)
+    std::lock_guard<std::mutex> one(*d.sum_mu);
+    unsigned long long* acc = (unsigned long long*)(d.sched + 32);
+    KK_CUDA(cudaMemsetAsync(acc, 0, 8, d.stream));
+    KK_CUDA(kk::launch_checksum(m->pools[(size_t)li] + off, nbytes, acc, d.sm_count, d.stream));
+    unsigned long long h = 0;
+    KK_CUDA(cudaMemcpyAsync(&h, acc, 8, cudaMemcpyDeviceToHost, d.stream));
+    KK_CUDA(cudaStreamSynchronize(d.stream));
+    *out = h;
   });
 }
 

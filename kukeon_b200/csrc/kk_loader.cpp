@@ -10,10 +10,14 @@
 #include "kk_loader.hpp"
 
 #include <fcntl.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include <pthread.h>
 #include <sched.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/vfs.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -34,10 +38,11 @@ double now_s() {
 }
 
 struct FdSet {
+  enum MapPolicy { kMapNone = 0, kMapTmpfs, kMapAll };  // which shards get a read-only mapping next to their descriptor
   std::vector<int> fds;
-  std::vector<const uint8_t*> maps;  // read-only mappings, used for short strided reads (no syscall per row)
+  std::vector<const uint8_t*> maps;  // read-only mappings (nullptr = none): long ranges are copied out of them with streaming stores, see read_chunk
   std::vector<uint64_t> sizes;
-  explicit FdSet(const std::vector<std::string>& paths, bool want_maps = false) {
+  explicit FdSet(const std::vector<std::string>& paths, MapPolicy policy = kMapNone) {
     for (auto& p : paths) {
       int fd = ::open(p.c_str(), O_RDONLY | O_CLOEXEC);
       if (fd < 0) {
@@ -48,7 +53,12 @@ struct FdSet {
       fds.push_back(fd);
       const uint8_t* mp = nullptr;
       uint64_t sz = 0;
-      if (want_maps) {
+      bool want = policy == kMapAll;
+      if (policy == kMapTmpfs) {
+        struct statfs sf;
+        want = fstatfs(fd, &sf) == 0 && (unsigned long)sf.f_type == 0x01021994ul;  // TMPFS_MAGIC: every byte is in memory, a mapping never waits for a disk
+      }
+      if (want) {
         struct stat st;
         if (fstat(fd, &st) == 0 && st.st_size > 0) {
           void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_SHARED, fd, 0);
@@ -169,15 +179,85 @@ bool want_row_maps(const kk_model* m) {
   static const bool on = [] { const char* e = getenv("KUKEON_GPULOAD_ROW_MMAP"); return e && *e == '1'; }();
   return on && m->plan.mode == KK_MODE_SCATTER;
 }
+// How a chunk's long contiguous ranges travel from the page cache into the pinned slot.  Measured on the B200 box, Llama-3-8B (16 GB) from tmpfs,
+// 16 reader threads (profiles/r02/e2e_read_modes_{o,p,q}.jsonl):
+//   pread                       the kernel's copy_to_user: 0.31-0.33 s of copying per thread, the load is reader-bound at 0.33-0.34 s (47-49 GB/s)
+//   mapping + memcpy            no faster than pread, and the final munmap of a checkpoint-sized mapping is ONE thread tearing down 4 M page-table
+//                               entries: + 0.33 s per load
+//   mapping + streaming stores  0.17-0.19 s per thread (no read-for-ownership of the slot's lines, which only the DMA engine reads next) — with the
+//                               same munmap bill
+//   ... + MADV_DONTNEED of each range right after its copy (the reader threads drop their own page-table entries in parallel, the final munmap
+//                               finds none: 1 ms): the load becomes H2D-bound, 0.303-0.307 s = 52.5 GB/s = 0.96 of the pinned-H2D probe.  DEFAULT for
+//                               shards on tmpfs; other file systems keep pread (a mapping of a cold file would fault page by page into the disk).
+//   MAP_POPULATE mapping per range: 0.9 s per thread (every mmap / munmap takes the process's mm lock exclusively) — removed again.
+// KUKEON_GPULOAD_READ = pread | mmap | mmap_nt | mmap_zap | mmap_nt_zap forces one mode for every shard (measurement knob, not API).
+enum ReadMode { kReadAuto = 0, kReadPread, kReadMmap, kReadMmapNt, kReadMmapZap, kReadMmapNtZap };
+ReadMode read_mode() {
+  static const ReadMode mode = [] {
+    const char* e = getenv("KUKEON_GPULOAD_READ");
+    if (!e) return kReadAuto;
+    if (!strcmp(e, "pread")) return kReadPread;
+    if (!strcmp(e, "mmap")) return kReadMmap;
+    if (!strcmp(e, "mmap_nt")) return kReadMmapNt;
+    if (!strcmp(e, "mmap_zap")) return kReadMmapZap;
+    if (!strcmp(e, "mmap_nt_zap")) return kReadMmapNtZap;
+    return kReadAuto;
+  }();
+  return mode;
+}
+FdSet::MapPolicy map_policy(const kk_model* m) {
+  if (want_row_maps(m)) return FdSet::kMapAll;
+  switch (read_mode()) {
+    case kReadAuto: return FdSet::kMapTmpfs;
+    case kReadPread: return FdSet::kMapNone;
+    default: return FdSet::kMapAll;
+  }
+}
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) void copy_nt_avx2(uint8_t* dst, const uint8_t* src, size_t n) {
+  size_t head = (32u - ((uintptr_t)dst & 31u)) & 31u;
+  if (head > n) head = n;
+  if (head) { memcpy(dst, src, head); dst += head; src += head; n -= head; }
+  size_t i = 0;
+  for (; i + 128 <= n; i += 128) {
+    const __m256i a = _mm256_loadu_si256((const __m256i*)(src + i)), b = _mm256_loadu_si256((const __m256i*)(src + i + 32));
+    const __m256i c = _mm256_loadu_si256((const __m256i*)(src + i + 64)), d = _mm256_loadu_si256((const __m256i*)(src + i + 96));
+    _mm256_stream_si256((__m256i*)(dst + i), a);
+    _mm256_stream_si256((__m256i*)(dst + i + 32), b);
+    _mm256_stream_si256((__m256i*)(dst + i + 64), c);
+    _mm256_stream_si256((__m256i*)(dst + i + 96), d);
+  }
+  if (i < n) memcpy(dst + i, src + i, n - i);
+  _mm_sfence();  // the streaming stores must be globally visible before the H2D copy of the slot is enqueued
+}
+#endif
+void copy_nt(uint8_t* dst, const uint8_t* src, size_t n) {
+#if defined(__x86_64__)
+  static const bool avx2 = __builtin_cpu_supports("avx2");
+  if (avx2) { copy_nt_avx2(dst, src, n); return; }
+#endif
+  memcpy(dst, src, n);
+}
 
 // Fill the slot with the chunk's file bytes.
-void read_chunk(const Chunk& c, const FdSet& fds, const Index& ix, uint8_t* pinned) {
+void read_chunk(const Chunk& c, const FdSet& fds, const Index& ix, uint8_t* pinned, bool row_maps) {
+  static const uint64_t pg = (uint64_t)sysconf(_SC_PAGESIZE);
   const uint8_t* mp = fds.maps.empty() ? nullptr : fds.maps[c.shard];
   const uint64_t msz = mp ? fds.sizes[c.shard] : 0;
+  const ReadMode mode = read_mode();
+  const bool nt = mode == kReadAuto || mode == kReadMmapNt || mode == kReadMmapNtZap, zap = mode == kReadAuto || mode == kReadMmapZap || mode == kReadMmapNtZap;
   for (auto& r : c.reads) {
-    // column-slice rows (SCATTER) are thousands of 2-7 KB runs per chunk: copy them out of the mapping instead
-    // of paying one pread syscall each; long contiguous ranges go through pread (no page-fault / TLB cost)
-    if (mp && r.len <= (256u << 10) && r.file_off <= msz && r.len <= msz - r.file_off) memcpy(pinned + r.buf_off, mp + r.file_off, r.len);
+    const bool in_map = mp && r.file_off <= msz && r.len <= msz - r.file_off;  // (a file that shrank since it was mapped takes pread's error path)
+    if (in_map && r.len > (256u << 10) && mode != kReadPread) {
+      if (nt) copy_nt(pinned + r.buf_off, mp + r.file_off, r.len);
+      else memcpy(pinned + r.buf_off, mp + r.file_off, r.len);
+      const uint64_t a = (r.file_off + pg - 1) & ~(pg - 1), e = (r.file_off + r.len) & ~(pg - 1);  // the whole pages inside the range
+      if (zap && e > a) madvise((void*)(mp + a), (size_t)(e - a), MADV_DONTNEED);  // page-table entries only: the pages stay in the page cache
+      continue;
+    }
+    // column-slice rows (SCATTER) are thousands of 2-7 KB runs per chunk: with KUKEON_GPULOAD_ROW_MMAP=1 they are copied out of the mapping instead
+    // of paying one pread syscall each (measured slower, see want_row_maps)
+    if (in_map && row_maps && r.len <= (256u << 10)) memcpy(pinned + r.buf_off, mp + r.file_off, r.len);
     else pread_full(fds.fds[c.shard], pinned + r.buf_off, r.len, r.file_off, ix.shards[c.shard]);
   }
 }
@@ -336,7 +416,7 @@ void run_part(kk_model* m, int li, int part, const FdSet& fds) {
         const uint64_t t0 = ns();
         KK_CUDA(cudaEventSynchronize(s.done));
         const uint64_t t1 = ns();
-        read_chunk(ch, fds, m->plan.index, s.pinned);
+        read_chunk(ch, fds, m->plan.index, s.pinned, want_row_maps(m));
         const uint64_t t2 = ns();
         ConvertLaunch L = base;
         if (zerocopy) {
@@ -419,7 +499,7 @@ void run_part_raw(kk_model* m, int li, int part, const FdSet& fds, bool fan_out)
         const Chunk& ch = pp.chunks[ci];
         Slot& s = rd->slots[k++ % rd->slots.size()];
         KK_CUDA(cudaEventSynchronize(s.done));
-        read_chunk(ch, fds, m->plan.index, s.pinned);
+        read_chunk(ch, fds, m->plan.index, s.pinned, want_row_maps(m));
         KK_CUDA(cudaMemcpyAsync(R.image + m->img_off[(size_t)part][ci], s.pinned, ch.buf_bytes, cudaMemcpyHostToDevice, rd->stream));
         if (do_fan) {
           ConvertLaunch L = base;
@@ -817,7 +897,8 @@ void ctx_close(kk_ctx* c) {
 // ---------------------------------------------------------------------------------------------
 static void do_load(kk_model* m) {
   const double t0 = now_s();
-  FdSet fds(m->plan.index.shards, want_row_maps(m));
+  FdSet fds(m->plan.index.shards, map_policy(m));
+  m->t_files_open = now_s() - t0;
   const size_t nl = m->dev_idx.size();
   m->t_part.assign(nl, 0.0);
   const bool multi_proc = m->opts.part_count > 1;
@@ -851,6 +932,9 @@ static void do_load(kk_model* m) {
       m->raw_staged = false;
     }
   }
+  const double tc = now_s();
+  fds.cleanup();  // part of the load: unmapping a checkpoint-sized mapping is not free
+  m->t_files_close = now_s() - tc;
   m->t_load = now_s() - t0;
   m->n_loads++;
 }
@@ -1263,7 +1347,7 @@ std::string model_stats(kk_model* m) {
     << ",\"n_parts\":" << m->plan.n_parts << ",\"local_src_bytes\":" << src << ",\"local_out_bytes\":" << out
     << ",\"index_s\":" << m->t_index << ",\"plan_s\":" << m->t_plan << ",\"alloc_s\":" << m->t_alloc << ",\"load_s\":" << m->t_load
     << ",\"n_loads\":" << m->n_loads << ",\"readers\":{\"threads\":" << m->rd_threads << ",\"slot_wait_s\":" << m->rd_wait_ns.load() / 1e9 << ",\"pread_s\":" << m->rd_pread_ns.load() / 1e9
-    << ",\"issue_s\":" << m->rd_issue_ns.load() / 1e9 << ",\"drain_s\":" << m->rd_drain_ns.load() / 1e9 << "},\"load_gbps\":" << (m->t_load > 0 ? (double)src / m->t_load / 1e9 : 0.0) << ",\"parts\":[";
+    << ",\"issue_s\":" << m->rd_issue_ns.load() / 1e9 << ",\"drain_s\":" << m->rd_drain_ns.load() / 1e9 << ",\"files_open_s\":" << m->t_files_open << ",\"files_close_s\":" << m->t_files_close << "},\"load_gbps\":" << (m->t_load > 0 ? (double)src / m->t_load / 1e9 : 0.0) << ",\"parts\":[";
   for (size_t li = 0; li < m->local_parts.size(); ++li) {
     const int part = m->local_parts[li];
     const PartPlan& pp = m->plan.parts[(size_t)part];
@@ -1307,7 +1391,7 @@ void model_stage_resident(kk_model* m) {
   }
   free_resident(m);
   kk_ctx* c = m->ctx;
-  FdSet fds(m->plan.index.shards, want_row_maps(m));
+  FdSet fds(m->plan.index.shards, map_policy(m));
   m->resident.resize(m->dev_idx.size());
   for (size_t li = 0; li < m->dev_idx.size(); ++li) {
     Device& dev = c->devs[(size_t)m->dev_idx[li]];
@@ -1330,7 +1414,7 @@ void model_stage_resident(kk_model* m) {
     for (size_t i = 0; i < pp.chunks.size(); ++i) {
       Slot& s = rd.slots[k++ % rd.slots.size()];
       KK_CUDA(cudaEventSynchronize(s.done));
-      read_chunk(pp.chunks[i], fds, m->plan.index, s.pinned);
+      read_chunk(pp.chunks[i], fds, m->plan.index, s.pinned, want_row_maps(m));
       KK_CUDA(cudaMemcpyAsync(R.image + img_off[i], s.pinned, pp.chunks[i].buf_bytes, cudaMemcpyHostToDevice, rd.stream));
       KK_CUDA(cudaEventRecord(s.done, rd.stream));
     }

@@ -44,7 +44,8 @@ struct Device {
   int sm_count = 0;
   std::vector<Reader> readers;
   cudaStream_t stream = nullptr;  // resident launches, checksum, misc
-  uint32_t* sched = nullptr;      // tile-scheduling counters of the launches on `stream`
+  uint32_t* sched = nullptr;      // tile-scheduling counters of the launches on `stream` (first 8 of 256 zeroed bytes)
+  std::unique_ptr<std::mutex> sum_mu{new std::mutex};  // kk_checksum's accumulator is the 8 bytes at sched + 32 words: no cudaMalloc / cudaFree per call
   uint64_t pool_in_use = 0;
   bool kernels_ready = false;
   std::vector<int> numa_cpus;  // CPUs local to the device's PCIe root (reader threads are pinned there)
@@ -129,6 +130,7 @@ struct kk_model {
   // where the reader threads of the last kk_load_part spent their time, summed over threads (seconds): waiting for a free slot (= for the GPU
   // to finish the chunk that used it), in pread, issuing the H2D copy + launch, and in the final stream synchronise; plus the thread count
   std::atomic<uint64_t> rd_wait_ns{0}, rd_pread_ns{0}, rd_issue_ns{0}, rd_drain_ns{0};
+  double t_files_open = 0, t_files_close = 0;  // of the last load: open + map, unmap + close
   uint32_t rd_threads = 0;
 };
 

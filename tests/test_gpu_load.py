@@ -377,6 +377,41 @@ def test_medium_checkpoint_checksum_of_checksums(native, tmp_path, coracle):
         shutil.rmtree(d, ignore_errors=True)
 
 
+@pytest.mark.skipif(not os.path.isdir("/dev/shm"), reason="the mapped read path is the default for shards on tmpfs only")
+def test_tmpfs_shards_take_the_mapped_streaming_read_path_bit_exact(pool, coracle):
+    """Shards on tmpfs are read through a mapping with streaming stores and per-range MADV_DONTNEED (kk_loader.cpp read_chunk), everything else with
+    pread: both must produce the same pool.  An unpadded header puts every range off page and 32-byte boundaries; tensors of 3 B .. 9 MB mix the
+    long (> 256 KiB, mapped) and short (pread) ranges in one chunk."""
+    d = f"/dev/shm/kk_mapped_{os.getpid()}"
+    os.makedirs(d, exist_ok=True)
+    try:
+        p = os.path.join(d, "m.safetensors")
+        tensors = [("a", "BF16", [7]), ("b", "BF16", [1537, 3001]), ("c", "F32", [1025, 513]), ("d", "U8", [3]), ("e", "F16", [999, 1001]),
+                   ("f", "BF16", [300_001]), ("g", "F32", [5]), ("h", "BF16", [2048, 1024]), ("i", "U8", [1021])]
+        synth.write_safetensors(p, tensors, 11, pad_header=False)
+        st = load_and_check(pool, p)
+        assert st["n_loads"] == 1
+        shards, recs = oracle.index_path(p)
+        m = pool.load(p)
+        try:
+            sums = [m.checksum(pool.devices[0], pl.pool_offset, pl.nbytes) for pl in (m.placements(r["name"])[0] for r in recs)]
+        finally:
+            m.release()
+        code = ("import sys, json; sys.path.insert(0, %r)\n"
+                "from kukeon_b200 import gpupool\n"
+                "with gpupool.Pool([0]) as pl:\n"
+                "    m = pl.load(%r)\n"
+                "    print(json.dumps([m.checksum(0, q.pool_offset, q.nbytes) for q in (m.placements(t['name'])[0] for t in m.tensors())]))\n"
+                "    m.release()\n") % (os.path.dirname(G[:-len('/golden')]), p)
+        for mode in ("pread", "mmap_nt_zap"):
+            out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, KUKEON_GPULOAD_READ=mode), capture_output=True, text=True, timeout=300)
+            assert out.returncode == 0, out.stderr[-2000:]
+            assert json.loads(out.stdout.strip().splitlines()[-1]) == sums, mode
+    finally:
+        import shutil
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def _shm_free() -> int:
     try:
         st = os.statvfs("/dev/shm")
