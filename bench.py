@@ -564,14 +564,16 @@ def main():
         if two_stage:
             barrier()
             m.convert_local()
+        t_e0 = time.perf_counter()
         m.export(local)
+        t_e1 = time.perf_counter()
         m.checksum(local, first.pool_offset, min(first.nbytes, 1 << 20))  # 8-byte D2H result read
         dt = time.perf_counter() - t
-        if args.e2e_only:  # tuning aid: where this step's time went (outside the timed region)
+        if True:  # where this step's time went (recorded outside the timed region)
             st = m.stats()
             rd = st.get("readers") or {}
             n = max(rd.get("threads", 1), 1)
-            step_detail.append({"ms": dt * 1e3, "load_part_ms": t_lp * 1e3, "load_s": st.get("load_s"), "files_open_s": rd.get("files_open_s"), "files_close_s": rd.get("files_close_s"),
+            step_detail.append({"ms": dt * 1e3, "load_part_ms": t_lp * 1e3, "export_ms": (t_e1 - t_e0) * 1e3, "checksum_ms": (time.perf_counter() - t_e1) * 1e3, "load_s": st.get("load_s"), "files_open_s": rd.get("files_open_s"), "files_close_s": rd.get("files_close_s"),
                                 "reader_avg": {k: rd.get(k, 0) / n for k in ("slot_wait_s", "pread_s", "issue_s", "drain_s")}})
         barrier()
         return dt
@@ -782,7 +784,7 @@ def main():
                    **({"transpose_tiles": "8 source rows x <= 4 KiB, thread = column, 16-byte stores"} if spec["kind"] == "gpt2" else {})},
         "clocks": ck,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(allsum(float(local_src))), "d2h_bytes_per_step": 8 * world,
-                "ms_per_step": e2e_time / args.steps * 1e3, "ms_each": [t * 1e3 for t in e2e_ts], "python_gc": "collected and frozen before, disabled during the e2e steps",
+                "ms_per_step": e2e_time / args.steps * 1e3, "ms_each": [t * 1e3 for t in e2e_ts], "steps_detail_rank0": step_detail[-args.steps:], "python_gc": "collected and frozen before, disabled during the e2e steps",
                 "file_GBps": file_read * args.steps / e2e_time / 1e9 if e2e_time == e2e_time else None,
                 "what": "kk_load_part (page cache->pinned->H2D->kernels) + kk_export + checksum word D2H; `value` counts the bytes made resident in all N pools "
                         "(N x checkpoint for a broadcast), `file_GBps` the checkpoint bytes read from the files once per step"},
