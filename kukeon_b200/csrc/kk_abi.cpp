@@ -186,10 +186,7 @@ int kk_export_buffer(kk_model* m, int device, int which, void* h) {
     int li = kk::model_local_device(m, device);
     if (which == KK_BUF_POOL) {
       if (m->nvls) kk::fail(KK_EUNSUPPORTED, "pools of a KK_FANOUT_NVLS model cannot be exported over CUDA IPC");
-      KK_CUDA(cudaSetDevice(device));
-      cudaIpcMemHandle_t ih;
-      KK_CUDA(cudaIpcGetMemHandle(&ih, m->pools[(size_t)li]));
-      memcpy(h, &ih, sizeof ih);
+      kk::model_pool_ipc_handle(m, li, h);
     } else if (which == KK_BUF_RAW) {
       kk::model_export_raw(m, li, h);
     } else if (which == KK_BUF_SLICE || which == KK_BUF_SLICE_PTR) {
@@ -299,11 +296,7 @@ int kk_export(kk_model* m, int device, void* ipc_handle_64B, char* manifest_json
     if (ipc_handle_64B) {
       if (m->nvls) kk::fail(KK_EUNSUPPORTED, "pools of a KK_FANOUT_NVLS model are VMM allocations: there is no cudaIpcMemHandle for them (export the manifest only, or load with KK_FANOUT_P2P)");
       if (!m->vmm.empty()) kk::fail(KK_EUNSUPPORTED, "pools of a KK_CFG_VMM_POOLS context are VMM allocations: there is no cudaIpcMemHandle for them, export the file descriptor (kk_export_fd)");
-      KK_CUDA(cudaSetDevice(device));
-      cudaIpcMemHandle_t h;
-      KK_CUDA(cudaIpcGetMemHandle(&h, m->pools[(size_t)li]));
-      static_assert(sizeof h == KK_IPC_HANDLE_BYTES, "ipc handle size");
-      memcpy(ipc_handle_64B, &h, sizeof h);
+      kk::model_pool_ipc_handle(m, li, ipc_handle_64B);
     }
   });
 }

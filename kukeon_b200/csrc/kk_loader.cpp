@@ -1297,7 +1297,30 @@ int model_local_device(kk_model* m, int ordinal) {
   fail(KK_EINVAL, "device %d holds no pool of this model", ordinal);
 }
 
+void model_pool_ipc_handle(kk_model* m, int li, void* handle_out) {
+  std::lock_guard<std::mutex> g(m->export_mu);
+  if (m->pool_handle_cache.size() < m->pools.size()) m->pool_handle_cache.resize(m->pools.size());
+  auto& c = m->pool_handle_cache[(size_t)li];
+  if (c.empty()) {
+    KK_CUDA(cudaSetDevice(m->ctx->devs[(size_t)m->dev_idx[(size_t)li]].ordinal));
+    cudaIpcMemHandle_t h;
+    KK_CUDA(cudaIpcGetMemHandle(&h, m->pools[(size_t)li]));
+    static_assert(sizeof h == KK_IPC_HANDLE_BYTES, "ipc handle size");
+    c.assign((const uint8_t*)&h, (const uint8_t*)&h + sizeof h);
+  }
+  memcpy(handle_out, c.data(), c.size());
+}
+
+static std::string build_manifest(kk_model* m, int li);
 std::string model_manifest(kk_model* m, int li) {
+  std::lock_guard<std::mutex> g(m->export_mu);
+  if (m->manifest_cache.size() < m->dev_idx.size()) m->manifest_cache.resize(m->dev_idx.size());
+  auto& c = m->manifest_cache[(size_t)li];
+  if (c.empty()) c = build_manifest(m, li);
+  return c;
+}
+
+static std::string build_manifest(kk_model* m, int li) {
   const auto& pl = m->plan.placement_of_part(m->local_parts[(size_t)li]);
   const auto& T = m->plan.index.tensors;
   std::ostringstream o;

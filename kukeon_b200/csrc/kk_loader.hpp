@@ -75,6 +75,12 @@ struct kk_model {
   std::vector<int> local_parts;
   std::vector<uint8_t*> pools;       // per local device
   std::vector<uint64_t> pool_bytes;  // per local device
+  // What kk_export hands out is fixed once the pools exist: the manifest text and the pool's CUDA IPC handle are built on first use and kept.  Every
+  // cell that mounts the model exports again, and the calls underneath (cudaIpcGetMemHandle, cudaGetDeviceProperties) go through the driver's
+  // system-wide lock: 2.5 ms normally, 11-144 ms when another process on the host holds it (profiles/r02/gpu_call_u.log).
+  std::mutex export_mu;
+  std::vector<std::string> manifest_cache;               // per local device, empty = not built yet
+  std::vector<std::vector<uint8_t>> pool_handle_cache;   // per local device, empty = not asked yet
   std::vector<KKSeg*> d_segs;        // per local device: device copy of its part's segment table
   // multi-process fan-out destinations (BROADCAST): IPC-opened peer pools by rank
   void* peer_ptr[KK_MAX_DEVICES] = {};
@@ -152,6 +158,7 @@ void model_probe_peer(kk_model* m, int rank, int which, uint64_t& nbytes, float*
 void model_peer_detach_all(kk_model* m);
 int model_local_device(kk_model* m, int ordinal);  // index into m->dev_idx or throws
 std::string model_manifest(kk_model* m, int local);
+void model_pool_ipc_handle(kk_model* m, int local, void* handle_64B);  // cudaIpcGetMemHandle of the pool, once per model and device
 std::string model_stats(kk_model* m);
 void model_stage_resident(kk_model* m);
 void model_unstage_resident(kk_model* m);
