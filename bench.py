@@ -605,7 +605,7 @@ def main():
     # ---- value: kernel stage from the HBM-resident image ---------------------------------------------------
     if args.e2e_only:
         line = {"metric": METRIC, "e2e_only": True, "n_gpus": N, "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_time / args.steps * 1e3},
-                "time_to_agent_ready_s": t_ready, "h2d_probe_GBps": h2d_probe, "readers_last_step": m.stats().get("readers"),
+                "time_to_agent_ready_s": t_ready, "h2d_probe_GBps": h2d_probe, "verified_vs_files": verified, "readers_last_step": m.stats().get("readers"),
                 "read_mode": os.environ.get("KUKEON_GPULOAD_READ", "auto"), "e2e_ms_each": [t * 1e3 for t in e2e_ts], "steps_detail": step_detail[-args.steps:],
                 "config": {"readers": args.readers, "slots": args.slots, "slot_mb": args.slot_mb, "zerocopy": args.zerocopy, "numa_pin": not args.no_numa_pin,
                            "chunks_per_load": chunks_per_load, "kk_open_s": t_open}}
