@@ -1,0 +1,76 @@
+// Host test of the loader's page-cache -> staging-slot read paths (kk_loader.cpp: FdSet, read_chunk, copy_nt) — test infrastructure only.
+// The functions live in kk_loader.cpp's anonymous namespace, so this translation unit includes the source and links against the library's
+// other objects; no CUDA call is made (no GPU needed).  Usage:
+//   KUKEON_GPULOAD_READ=<mode> kk_read_test <dir> <policy: none|tmpfs|all> [row_maps]
+// Writes a pseudo-random file into <dir>, fills a poisoned buffer through read_chunk with a mix of long (> 256 KiB, unaligned) and short ranges,
+// compares every range with the file and every byte outside the ranges with the poison, and prints one JSON line.
+#include "../../kukeon_b200/csrc/kk_loader.cpp"
+
+#include <cstdio>
+#include <random>
+
+using namespace kk;
+
+int main(int argc, char** argv) {
+  if (argc < 3) return 2;
+  const std::string dir = argv[1], pol = argv[2];
+  const bool row_maps = argc > 3 && !strcmp(argv[3], "row_maps");
+  const std::string path = dir + "/read_test.bin";
+  const size_t fsz = 5u * 1024u * 1024u + 12345u;
+  std::vector<uint8_t> file(fsz);
+  std::mt19937_64 rng(42);
+  for (size_t i = 0; i + 8 <= fsz; i += 8) { uint64_t v = rng(); memcpy(&file[i], &v, 8); }
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f || fwrite(file.data(), 1, fsz, f) != fsz) return 3;
+  fclose(f);
+  int bad = 0, mapped = 0;
+  std::string err;
+  try {
+    Index ix;
+    ix.shards.push_back(path);
+    FdSet fds(ix.shards, pol == "all" ? FdSet::kMapAll : pol == "tmpfs" ? FdSet::kMapTmpfs : FdSet::kMapNone);
+    mapped = fds.maps[0] != nullptr;
+    // ranges: (file_off, len) — long ones off page and 32-byte boundaries, short ones, one ending at the last byte of the file
+    const std::vector<std::pair<uint64_t, uint64_t>> want = {{3, 1000003}, {1000100, 7}, {1000200, 300 * 1024 + 1}, {1400000, 4096}, {1500001, 262144}, {1800007, 262145},
+                                                            {2200000, 2 * 1024 * 1024 + 33}, {fsz - 600000, 600000}};
+    Chunk c;
+    c.shard = 0;
+    uint64_t pos = 0;
+    for (auto& w : want) {
+      const uint64_t at = (pos + 15) & ~15ull;
+      c.reads.push_back({w.first, w.second, at});
+      pos = at + w.second;
+    }
+    c.buf_bytes = pos;
+    std::vector<uint8_t> buf(pos + 64, 0xA5);
+    uint8_t* dst = buf.data() + 1;  // an odd destination: the streaming copy has to find its own 32-byte boundary
+    read_chunk(c, fds, ix, dst, row_maps);
+    std::vector<uint8_t> covered(pos + 64, 0);
+    for (auto& r : c.reads) {
+      if (memcmp(dst + r.buf_off, file.data() + r.file_off, r.len)) ++bad;
+      for (uint64_t i = 0; i < r.len; ++i) covered[1 + r.buf_off + i] = 1;
+    }
+    for (size_t i = 0; i < buf.size(); ++i)
+      if (!covered[i] && buf[i] != 0xA5) { ++bad; break; }
+    // the mapping must still serve reads after the per-range MADV_DONTNEED (pages stay in the page cache): read everything again
+    read_chunk(c, fds, ix, dst, row_maps);
+    for (auto& r : c.reads)
+      if (memcmp(dst + r.buf_off, file.data() + r.file_off, r.len)) ++bad;
+    // a range past the end of the file is refused with KK_EIO whatever the mode
+    Chunk over;
+    over.shard = 0;
+    over.reads.push_back({fsz - 100, 300 * 1024, 0});
+    try {
+      read_chunk(over, fds, ix, dst, row_maps);
+      ++bad;
+    } catch (const Error& e) {
+      if (e.code != KK_EIO) ++bad;
+    }
+  } catch (const Error& e) {
+    err = e.what();
+    ++bad;
+  }
+  unlink(path.c_str());
+  printf("{\"bad\":%d,\"mapped\":%d,\"mode\":%d,\"error\":\"%s\"}\n", bad, mapped, (int)read_mode(), err.c_str());
+  return bad ? 1 : 0;
+}
