@@ -100,3 +100,17 @@ def test_cpu_entry_points_are_thread_safe_and_errors_are_per_thread(native, tmp_
     [t.start() for t in th]
     [t.join() for t in th]
     assert not errs, errs
+
+
+def test_every_environment_knob_of_the_library_is_documented():
+    """The library's getenv() names are measurement / test aids outside the C ABI; DESIGN.md §4 lists them all."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = set()
+    for f in glob.glob(os.path.join(root, "kukeon_b200", "csrc", "*.c*")):
+        names |= set(re.findall(r'getenv\("([A-Z0-9_]+)"\)', open(f).read()))
+    assert names, "no getenv found: the scan is broken"
+    design = open(os.path.join(root, "DESIGN.md")).read()
+    missing = sorted(n for n in names if n not in design)
+    assert not missing, f"undocumented environment knobs: {missing}"
