@@ -69,6 +69,14 @@ struct FdSet {
       sizes.push_back(sz);
     }
   }
+  // Bytes of shard i that may be read through its mapping right now: touching a mapped page past the end of a file that has been truncated since
+  // it was mapped raises SIGBUS, where pread reports a short read.  Asked once per chunk (one fstat per 16 MiB), this narrows that window from the
+  // whole load to one chunk's copy; a range beyond the returned size takes the pread path and its KK_EIO.
+  uint64_t live_size(uint32_t i) const {
+    struct stat st;
+    if (fstat(fds[i], &st) != 0 || st.st_size < 0) return 0;
+    return std::min<uint64_t>((uint64_t)st.st_size, sizes[i]);
+  }
   void cleanup() {
     for (size_t i = 0; i < maps.size(); ++i)
       if (maps[i]) munmap((void*)maps[i], sizes[i]);
@@ -244,7 +252,7 @@ void copy_nt(uint8_t* dst, const uint8_t* src, size_t n) {
 void read_chunk(const Chunk& c, const FdSet& fds, const Index& ix, uint8_t* pinned, bool row_maps) {
   static const uint64_t pg = (uint64_t)sysconf(_SC_PAGESIZE);
   const uint8_t* mp = fds.maps.empty() ? nullptr : fds.maps[c.shard];
-  const uint64_t msz = mp ? fds.sizes[c.shard] : 0;
+  const uint64_t msz = mp ? fds.live_size(c.shard) : 0;
   const ReadMode mode = read_mode();
   // (kReadBounce only changes run_part; the resident-image and RAW paths that come through here behave as in the default mode)
   const bool nt = mode == kReadAuto || mode == kReadBounce || mode == kReadMmapNt || mode == kReadMmapNtZap, zap = mode == kReadAuto || mode == kReadBounce || mode == kReadMmapZap || mode == kReadMmapNtZap;
@@ -281,7 +289,7 @@ uint32_t bounce_ring_len() {
 uint64_t bounce_chunk(const Chunk& c, const FdSet& fds, const Index& ix, Reader* rd, uint8_t* dev_slot) {
   static const uint64_t pg = (uint64_t)sysconf(_SC_PAGESIZE);
   const uint8_t* mp = fds.maps.empty() ? nullptr : fds.maps[c.shard];
-  const uint64_t msz = mp ? fds.sizes[c.shard] : 0;
+  const uint64_t msz = mp ? fds.live_size(c.shard) : 0;
   const uint64_t P = bounce_piece_bytes();
   auto now = [] { return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   uint64_t waited = 0;

@@ -66,6 +66,22 @@ int main(int argc, char** argv) {
     } catch (const Error& e) {
       if (e.code != KK_EIO) ++bad;
     }
+    // a shard truncated AFTER it was mapped: the chunk's ranges beyond the new end must come back as KK_EIO (pread's short read), not as a SIGBUS
+    if (truncate(path.c_str(), 1200000) != 0) ++bad;
+    Chunk late;
+    late.shard = 0;
+    late.reads.push_back({1000200, 300 * 1024 + 1, 0});
+    try {
+      read_chunk(late, fds, ix, dst, row_maps);
+      ++bad;
+    } catch (const Error& e) {
+      if (e.code != KK_EIO) ++bad;
+    }
+    Chunk early;  // what is still inside the file keeps working
+    early.shard = 0;
+    early.reads.push_back({3, 1000003, 0});
+    read_chunk(early, fds, ix, dst, row_maps);
+    if (memcmp(dst, file.data() + 3, 1000003)) ++bad;
   } catch (const Error& e) {
     err = e.what();
     ++bad;
