@@ -197,19 +197,19 @@ bool want_row_maps(const kk_model* m) {
 //   ... + MADV_DONTNEED of each range right after its copy (the reader threads drop their own page-table entries in parallel, the final munmap
 //                               finds none: 1 ms): the load becomes H2D-bound, 0.303-0.307 s = 52.5 GB/s = 0.96 of the pinned-H2D probe.  DEFAULT for
 //                               shards on tmpfs; other file systems keep pread (a mapping of a cold file would fault page by page into the disk).
-//   MAP_POPULATE mapping per range: 0.9 s per thread (every mmap / munmap takes the process's mm lock exclusively) — removed again.
-// KUKEON_GPULOAD_READ = pread | mmap | mmap_nt | mmap_zap | mmap_nt_zap forces one mode for every shard (measurement knob, not API).
-enum ReadMode { kReadAuto = 0, kReadPread, kReadMmap, kReadMmapNt, kReadMmapZap, kReadMmapNtZap, kReadBounce };
+//   MAP_POPULATE mapping per range: 0.9 s per thread (every mmap / munmap takes the process's mm lock exclusively).
+//   cache-resident bounce ring (4 x 256 KiB pinned pieces per reader between mapping and device slot, so that neither the CPU's stores nor the copy
+//                               engine's reads reach DRAM): CPU copy 2x faster again, but 64 K small H2D copies starve the copy engines — 2 GPUs on one
+//                               socket 288.6 -> 382.2 ms per step (profiles/r02/gpu_call_w.log).
+// The measured losers are deleted (git history: ed69c4b..50a97f8 carry them); what is left is the default and one switch:
+// KUKEON_GPULOAD_READ = pread (never map) | mapped (map every shard, whatever the file system).  Measurement knob, not API.
+enum ReadMode { kReadAuto = 0, kReadPread, kReadMapped };
 ReadMode read_mode() {
   static const ReadMode mode = [] {
     const char* e = getenv("KUKEON_GPULOAD_READ");
     if (!e) return kReadAuto;
     if (!strcmp(e, "pread")) return kReadPread;
-    if (!strcmp(e, "mmap")) return kReadMmap;
-    if (!strcmp(e, "mmap_nt")) return kReadMmapNt;
-    if (!strcmp(e, "mmap_zap")) return kReadMmapZap;
-    if (!strcmp(e, "mmap_nt_zap")) return kReadMmapNtZap;
-    if (!strcmp(e, "bounce")) return kReadBounce;
+    if (!strcmp(e, "mapped")) return kReadMapped;
     return kReadAuto;
   }();
   return mode;
@@ -217,7 +217,7 @@ ReadMode read_mode() {
 FdSet::MapPolicy map_policy(const kk_model* m) {
   if (want_row_maps(m)) return FdSet::kMapAll;
   switch (read_mode()) {
-    case kReadAuto: case kReadBounce: return FdSet::kMapTmpfs;
+    case kReadAuto: return FdSet::kMapTmpfs;
     case kReadPread: return FdSet::kMapNone;
     default: return FdSet::kMapAll;
   }
@@ -254,15 +254,12 @@ void read_chunk(const Chunk& c, const FdSet& fds, const Index& ix, uint8_t* pinn
   const uint8_t* mp = fds.maps.empty() ? nullptr : fds.maps[c.shard];
   const uint64_t msz = mp ? fds.live_size(c.shard) : 0;
   const ReadMode mode = read_mode();
-  // (kReadBounce only changes run_part; the resident-image and RAW paths that come through here behave as in the default mode)
-  const bool nt = mode == kReadAuto || mode == kReadBounce || mode == kReadMmapNt || mode == kReadMmapNtZap, zap = mode == kReadAuto || mode == kReadBounce || mode == kReadMmapZap || mode == kReadMmapNtZap;
   for (auto& r : c.reads) {
     const bool in_map = mp && r.file_off <= msz && r.len <= msz - r.file_off;  // (a file that shrank since it was mapped takes pread's error path)
     if (in_map && r.len > (256u << 10) && mode != kReadPread) {
-      if (nt) copy_nt(pinned + r.buf_off, mp + r.file_off, r.len);
-      else memcpy(pinned + r.buf_off, mp + r.file_off, r.len);
+      copy_nt(pinned + r.buf_off, mp + r.file_off, r.len);
       const uint64_t a = (r.file_off + pg - 1) & ~(pg - 1), e = (r.file_off + r.len) & ~(pg - 1);  // the whole pages inside the range
-      if (zap && e > a) madvise((void*)(mp + a), (size_t)(e - a), MADV_DONTNEED);  // page-table entries only: the pages stay in the page cache
+      if (e > a) madvise((void*)(mp + a), (size_t)(e - a), MADV_DONTNEED);  // page-table entries only: the pages stay in the page cache
       continue;
     }
     // column-slice rows (SCATTER) are thousands of 2-7 KB runs per chunk: with KUKEON_GPULOAD_ROW_MMAP=1 they are copied out of the mapping instead
@@ -270,59 +267,6 @@ void read_chunk(const Chunk& c, const FdSet& fds, const Index& ix, uint8_t* pinn
     if (in_map && row_maps && r.len <= (256u << 10)) memcpy(pinned + r.buf_off, mp + r.file_off, r.len);
     else pread_full(fds.fds[c.shard], pinned + r.buf_off, r.len, r.file_off, ix.shards[c.shard]);
   }
-}
-
-// KUKEON_GPULOAD_READ=bounce.  With more than one GPU per socket the staging stage is bound by the socket's DRAM, which sees every file byte three
-// times (page-cache read, slot write, DMA read).  Here the bytes pass through a ring of small pinned pieces per reader (4 x 256 KiB by default:
-// they stay in the reader core's L2 / the LLC between uses) and are DMA'd piece by piece into the device staging slot: the CPU's stores hit lines
-// that are already in cache and the copy engine's reads are served from cache, so DRAM sees each byte once.  The chunk's buffer space is walked in
-// piece-sized windows, every window gathers the (parts of) reads that fall into it — thousands of short column-slice rows become one H2D copy.
-uint32_t bounce_piece_bytes() {
-  static const uint32_t v = [] { const char* e = getenv("KUKEON_GPULOAD_BOUNCE_KB"); int k = e ? atoi(e) : 0; return (uint32_t)((k >= 16 && k <= 16384) ? k : 256) << 10; }();
-  return v;
-}
-uint32_t bounce_ring_len() {
-  static const uint32_t v = [] { const char* e = getenv("KUKEON_GPULOAD_BOUNCE_N"); int k = e ? atoi(e) : 0; return (uint32_t)((k >= 2 && k <= 64) ? k : 4); }();
-  return v;
-}
-// Returns the nanoseconds spent waiting for ring pieces (the rest of the call is copying and enqueueing).
-uint64_t bounce_chunk(const Chunk& c, const FdSet& fds, const Index& ix, Reader* rd, uint8_t* dev_slot) {
-  static const uint64_t pg = (uint64_t)sysconf(_SC_PAGESIZE);
-  const uint8_t* mp = fds.maps.empty() ? nullptr : fds.maps[c.shard];
-  const uint64_t msz = mp ? fds.live_size(c.shard) : 0;
-  const uint64_t P = bounce_piece_bytes();
-  auto now = [] { return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-  uint64_t waited = 0;
-  size_t ri = 0;
-  uint64_t rpos = 0;  // bytes of reads[ri] already moved
-  while (ri < c.reads.size()) {
-    const uint64_t a = c.reads[ri].buf_off + rpos, e = a + P;  // this window of the chunk's buffer space starts at the next byte to move
-    Bounce& b = rd->bounce[rd->bounce_next++ % rd->bounce.size()];
-    const uint64_t t0 = now();
-    KK_CUDA(cudaEventSynchronize(b.done));
-    waited += now() - t0;
-    uint64_t hi = a;
-    while (ri < c.reads.size()) {
-      const ReadOp& r = c.reads[ri];
-      const uint64_t start = r.buf_off + rpos;
-      if (start >= e) break;
-      const uint64_t n = std::min(r.len - rpos, e - start), fo = r.file_off + rpos;
-      if (mp && fo <= msz && n <= msz - fo) memcpy(b.host + (start - a), mp + fo, n);
-      else pread_full(fds.fds[c.shard], b.host + (start - a), n, fo, ix.shards[c.shard]);
-      hi = start + n;
-      rpos += n;
-      if (rpos < r.len) break;  // window full
-      if (mp && r.len > (256u << 10)) {  // the range is done: drop its page-table entries (see read_chunk)
-        const uint64_t za = (r.file_off + pg - 1) & ~(pg - 1), ze = (r.file_off + r.len) & ~(pg - 1);
-        if (ze > za && ze <= msz) madvise((void*)(mp + za), (size_t)(ze - za), MADV_DONTNEED);
-      }
-      ++ri;
-      rpos = 0;
-    }
-    KK_CUDA(cudaMemcpyAsync(dev_slot + a, b.host, hi - a, cudaMemcpyHostToDevice, rd->stream));
-    KK_CUDA(cudaEventRecord(b.done, rd->stream));
-  }
-  return waited;
 }
 
 uint64_t seg_base_of(const Plan& P, int part) {
@@ -461,7 +405,6 @@ void run_part(kk_model* m, int li, int part, const FdSet& fds) {
   ConvertLaunch base{};
   fill_dsts(m, li, base);
   const bool zerocopy = (c->cfg.flags & KK_CFG_ZEROCOPY) != 0;
-  const bool bounce = !zerocopy && read_mode() == kReadBounce && !dev.readers.empty() && !dev.readers[0].bounce.empty();
   std::atomic<size_t> next{0};
   ErrorSink sink;
   auto ns = [] { return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -478,24 +421,16 @@ void run_part(kk_model* m, int li, int part, const FdSet& fds) {
         const Chunk& ch = pp.chunks[ci];
         Slot& s = rd->slots[k++ % rd->slots.size()];
         const uint64_t t0 = ns();
-        uint64_t t1, t2;
+        KK_CUDA(cudaEventSynchronize(s.done));
+        const uint64_t t1 = ns();
+        read_chunk(ch, fds, m->plan.index, s.pinned, want_row_maps(m));
+        const uint64_t t2 = ns();
         ConvertLaunch L = base;
-        if (bounce) {  // no wait for the slot: its device buffer is reused in stream order, the ring pieces carry their own events
-          const uint64_t w = bounce_chunk(ch, fds, m->plan.index, rd, s.dev);
-          t1 = t0 + w;
-          t2 = ns();
-          L.src = s.dev;
+        if (zerocopy) {
+          L.src = s.pinned;
         } else {
-          KK_CUDA(cudaEventSynchronize(s.done));
-          t1 = ns();
-          read_chunk(ch, fds, m->plan.index, s.pinned, want_row_maps(m));
-          t2 = ns();
-          if (zerocopy) {
-            L.src = s.pinned;
-          } else {
-            KK_CUDA(cudaMemcpyAsync(s.dev, s.pinned, ch.buf_bytes, cudaMemcpyHostToDevice, rd->stream));
-            L.src = s.dev;
-          }
+          KK_CUDA(cudaMemcpyAsync(s.dev, s.pinned, ch.buf_bytes, cudaMemcpyHostToDevice, rd->stream));
+          L.src = s.dev;
         }
         L.segs = d_segs + ch.seg_begin;
         L.n_segs = ch.seg_count;
@@ -891,13 +826,6 @@ kk_ctx* ctx_open(const kk_config& cfg_in) {
             KK_CUDA(cudaStreamCreateWithFlags(&rd.stream, cudaStreamNonBlocking));
             KK_CUDA(cudaMalloc((void**)&rd.sched, 256));
             KK_CUDA(cudaMemset(rd.sched, 0, 256));
-            if (!(cfg.flags & KK_CFG_ZEROCOPY) && read_mode() == kReadBounce) {
-              rd.bounce.resize(bounce_ring_len());
-              for (auto& b : rd.bounce) {
-                KK_CUDA(cudaHostAlloc((void**)&b.host, bounce_piece_bytes(), cudaHostAllocPortable));
-                KK_CUDA(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
-              }
-            }
             uint32_t ns = cfg.n_staging_buffers / cfg.n_reader_threads + (r < cfg.n_staging_buffers % cfg.n_reader_threads ? 1 : 0);
             rd.slots.resize(ns);
             for (auto& s : rd.slots) {
@@ -961,10 +889,6 @@ void ctx_close(kk_ctx* c) {
         if (s.done) cudaEventDestroy(s.done);
         if (s.dev) cudaFree(s.dev);
         if (s.pinned) cudaFreeHost(s.pinned);
-      }
-      for (auto& b : rd.bounce) {
-        if (b.done) cudaEventDestroy(b.done);
-        if (b.host) cudaFreeHost(b.host);
       }
       if (rd.stream) cudaStreamDestroy(rd.stream);
       if (rd.sched) cudaFree(rd.sched);

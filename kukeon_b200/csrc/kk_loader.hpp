@@ -30,15 +30,8 @@ struct Slot {
   cudaEvent_t done = nullptr; // recorded after the convert kernel that consumed this slot
 };
 
-struct Bounce {
-  uint8_t* host = nullptr;     // a small pinned piece that stays in the reader core's cache between uses
-  cudaEvent_t done = nullptr;  // recorded after the H2D copy that read it
-};
-
 struct Reader {
   cudaStream_t stream = nullptr;
-  std::vector<Bounce> bounce;  // KUKEON_GPULOAD_READ=bounce: ring of cache-resident pieces the file bytes pass through instead of the big slots
-  size_t bounce_next = 0;
   uint32_t* sched = nullptr;  // two zeroed device words: the tile-scheduling counters of the launches on `stream` (ConvertLaunch::sched)
   std::vector<Slot> slots;
 };

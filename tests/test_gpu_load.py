@@ -403,7 +403,7 @@ def test_tmpfs_shards_take_the_mapped_streaming_read_path_bit_exact(pool, coracl
                 "    m = pl.load(%r)\n"
                 "    print(json.dumps([m.checksum(0, q.pool_offset, q.nbytes) for q in (m.placements(t['name'])[0] for t in m.tensors())]))\n"
                 "    m.release()\n") % (os.path.dirname(G[:-len('/golden')]), p)
-        for mode in ("pread", "mmap_nt_zap"):
+        for mode in ("pread", "mapped"):
             out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, KUKEON_GPULOAD_READ=mode), capture_output=True, text=True, timeout=300)
             assert out.returncode == 0, out.stderr[-2000:]
             assert json.loads(out.stdout.strip().splitlines()[-1]) == sums, mode

@@ -11,7 +11,7 @@ import pytest
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 BIN = os.path.join(_HERE, "emul", "_build", "kk_read_test")
-MODES = ["auto", "pread", "mmap", "mmap_nt", "mmap_zap", "mmap_nt_zap", "bounce"]
+MODES = ["auto", "pread", "mapped"]
 
 
 @pytest.fixture(scope="module")
@@ -47,4 +47,4 @@ def test_every_read_mode_delivers_the_file_bytes_from_tmpfs(binary, mode):
 def test_only_tmpfs_shards_are_mapped_by_default(binary, tmp_path):
     doc = run(binary, str(tmp_path), "tmpfs", "auto")
     assert doc["mapped"] == (1 if _is_tmpfs(str(tmp_path)) else 0)
-    assert run(binary, str(tmp_path), "all", "mmap_nt_zap")["mapped"] == 1  # a forced mode maps whatever the file system
+    assert run(binary, str(tmp_path), "all", "mapped")["mapped"] == 1  # a forced mode maps whatever the file system
