@@ -180,13 +180,6 @@ struct DevScratch {
   }
 };
 
-// Column-slice rows can be copied out of a read-only mapping instead of one pread each.  Measured on the 8xB200 box
-// (Llama-3-70B scatter, tmpfs): 1.99 s per load with the mapping vs 1.51 s with pread — first-touch page faults of the
-// mapping cost more than the syscalls — so pread stays the default; KUKEON_GPULOAD_ROW_MMAP=1 switches.
-bool want_row_maps(const kk_model* m) {
-  static const bool on = [] { const char* e = getenv("KUKEON_GPULOAD_ROW_MMAP"); return e && *e == '1'; }();
-  return on && m->plan.mode == KK_MODE_SCATTER;
-}
 // How a chunk's long contiguous ranges travel from the page cache into the pinned slot.  Measured on the B200 box, Llama-3-8B (16 GB) from tmpfs,
 // 16 reader threads (profiles/r02/e2e_read_modes_{o,p,q}.jsonl):
 //   pread                       the kernel's copy_to_user: 0.31-0.33 s of copying per thread, the load is reader-bound at 0.33-0.34 s (47-49 GB/s)
@@ -215,7 +208,6 @@ ReadMode read_mode() {
   return mode;
 }
 FdSet::MapPolicy map_policy(const kk_model* m) {
-  if (want_row_maps(m)) return FdSet::kMapAll;
   switch (read_mode()) {
     case kReadAuto: return FdSet::kMapTmpfs;
     case kReadPread: return FdSet::kMapNone;
@@ -249,7 +241,7 @@ void copy_nt(uint8_t* dst, const uint8_t* src, size_t n) {
 }
 
 // Fill the slot with the chunk's file bytes.
-void read_chunk(const Chunk& c, const FdSet& fds, const Index& ix, uint8_t* pinned, bool row_maps) {
+void read_chunk(const Chunk& c, const FdSet& fds, const Index& ix, uint8_t* pinned) {
   static const uint64_t pg = (uint64_t)sysconf(_SC_PAGESIZE);
   const uint8_t* mp = fds.maps.empty() ? nullptr : fds.maps[c.shard];
   const uint64_t msz = mp ? fds.live_size(c.shard) : 0;
@@ -262,10 +254,9 @@ void read_chunk(const Chunk& c, const FdSet& fds, const Index& ix, uint8_t* pinn
       if (e > a) madvise((void*)(mp + a), (size_t)(e - a), MADV_DONTNEED);  // page-table entries only: the pages stay in the page cache
       continue;
     }
-    // column-slice rows (SCATTER) are thousands of 2-7 KB runs per chunk: with KUKEON_GPULOAD_ROW_MMAP=1 they are copied out of the mapping instead
-    // of paying one pread syscall each (measured slower, see want_row_maps)
-    if (in_map && row_maps && r.len <= (256u << 10)) memcpy(pinned + r.buf_off, mp + r.file_off, r.len);
-    else pread_full(fds.fds[c.shard], pinned + r.buf_off, r.len, r.file_off, ix.shards[c.shard]);
+    // short ranges (column-slice rows of a SCATTER load: thousands of 2-7 KB runs per chunk) stay on pread: copied out of the mapping the 70B
+    // scatter load measured 1.99 s against 1.51 s — a first-touch page fault per row costs more than the syscall (round 1, 8 x B200)
+    pread_full(fds.fds[c.shard], pinned + r.buf_off, r.len, r.file_off, ix.shards[c.shard]);
   }
 }
 
@@ -423,7 +414,7 @@ void run_part(kk_model* m, int li, int part, const FdSet& fds) {
         const uint64_t t0 = ns();
         KK_CUDA(cudaEventSynchronize(s.done));
         const uint64_t t1 = ns();
-        read_chunk(ch, fds, m->plan.index, s.pinned, want_row_maps(m));
+        read_chunk(ch, fds, m->plan.index, s.pinned);
         const uint64_t t2 = ns();
         ConvertLaunch L = base;
         if (zerocopy) {
@@ -506,7 +497,7 @@ void run_part_raw(kk_model* m, int li, int part, const FdSet& fds, bool fan_out)
         const Chunk& ch = pp.chunks[ci];
         Slot& s = rd->slots[k++ % rd->slots.size()];
         KK_CUDA(cudaEventSynchronize(s.done));
-        read_chunk(ch, fds, m->plan.index, s.pinned, want_row_maps(m));
+        read_chunk(ch, fds, m->plan.index, s.pinned);
         KK_CUDA(cudaMemcpyAsync(R.image + m->img_off[(size_t)part][ci], s.pinned, ch.buf_bytes, cudaMemcpyHostToDevice, rd->stream));
         if (do_fan) {
           ConvertLaunch L = base;
@@ -1444,7 +1435,7 @@ void model_stage_resident(kk_model* m) {
     for (size_t i = 0; i < pp.chunks.size(); ++i) {
       Slot& s = rd.slots[k++ % rd.slots.size()];
       KK_CUDA(cudaEventSynchronize(s.done));
-      read_chunk(pp.chunks[i], fds, m->plan.index, s.pinned, want_row_maps(m));
+      read_chunk(pp.chunks[i], fds, m->plan.index, s.pinned);
       KK_CUDA(cudaMemcpyAsync(R.image + img_off[i], s.pinned, pp.chunks[i].buf_bytes, cudaMemcpyHostToDevice, rd.stream));
       KK_CUDA(cudaEventRecord(s.done, rd.stream));
     }

@@ -1,7 +1,7 @@
 // Host test of the loader's page-cache -> staging-slot read paths (kk_loader.cpp: FdSet, read_chunk, copy_nt) — test infrastructure only.
 // The functions live in kk_loader.cpp's anonymous namespace, so this translation unit includes the source and links against the library's
 // other objects; no CUDA call is made (no GPU needed).  Usage:
-//   KUKEON_GPULOAD_READ=<mode> kk_read_test <dir> <policy: none|tmpfs|all> [row_maps]
+//   KUKEON_GPULOAD_READ=<mode> kk_read_test <dir> <policy: none|tmpfs|all>
 // Writes a pseudo-random file into <dir>, fills a poisoned buffer through read_chunk with a mix of long (> 256 KiB, unaligned) and short ranges,
 // compares every range with the file and every byte outside the ranges with the poison, and prints one JSON line.
 #include "../../kukeon_b200/csrc/kk_loader.cpp"
@@ -14,7 +14,6 @@ using namespace kk;
 int main(int argc, char** argv) {
   if (argc < 3) return 2;
   const std::string dir = argv[1], pol = argv[2];
-  const bool row_maps = argc > 3 && !strcmp(argv[3], "row_maps");
   const std::string path = dir + "/read_test.bin";
   const size_t fsz = 5u * 1024u * 1024u + 12345u;
   std::vector<uint8_t> file(fsz);
@@ -44,7 +43,7 @@ int main(int argc, char** argv) {
     c.buf_bytes = pos;
     std::vector<uint8_t> buf(pos + 64, 0xA5);
     uint8_t* dst = buf.data() + 1;  // an odd destination: the streaming copy has to find its own 32-byte boundary
-    read_chunk(c, fds, ix, dst, row_maps);
+    read_chunk(c, fds, ix, dst);
     std::vector<uint8_t> covered(pos + 64, 0);
     for (auto& r : c.reads) {
       if (memcmp(dst + r.buf_off, file.data() + r.file_off, r.len)) ++bad;
@@ -53,7 +52,7 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i < buf.size(); ++i)
       if (!covered[i] && buf[i] != 0xA5) { ++bad; break; }
     // the mapping must still serve reads after the per-range MADV_DONTNEED (pages stay in the page cache): read everything again
-    read_chunk(c, fds, ix, dst, row_maps);
+    read_chunk(c, fds, ix, dst);
     for (auto& r : c.reads)
       if (memcmp(dst + r.buf_off, file.data() + r.file_off, r.len)) ++bad;
     // a range past the end of the file is refused with KK_EIO whatever the mode
@@ -61,7 +60,7 @@ int main(int argc, char** argv) {
     over.shard = 0;
     over.reads.push_back({fsz - 100, 300 * 1024, 0});
     try {
-      read_chunk(over, fds, ix, dst, row_maps);
+      read_chunk(over, fds, ix, dst);
       ++bad;
     } catch (const Error& e) {
       if (e.code != KK_EIO) ++bad;
@@ -72,7 +71,7 @@ int main(int argc, char** argv) {
     late.shard = 0;
     late.reads.push_back({1000200, 300 * 1024 + 1, 0});
     try {
-      read_chunk(late, fds, ix, dst, row_maps);
+      read_chunk(late, fds, ix, dst);
       ++bad;
     } catch (const Error& e) {
       if (e.code != KK_EIO) ++bad;
@@ -80,7 +79,7 @@ int main(int argc, char** argv) {
     Chunk early;  // what is still inside the file keeps working
     early.shard = 0;
     early.reads.push_back({3, 1000003, 0});
-    read_chunk(early, fds, ix, dst, row_maps);
+    read_chunk(early, fds, ix, dst);
     if (memcmp(dst, file.data() + 3, 1000003)) ++bad;
   } catch (const Error& e) {
     err = e.what();

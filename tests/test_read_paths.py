@@ -38,7 +38,7 @@ def test_every_read_mode_delivers_the_file_bytes_from_tmpfs(binary, mode):
     try:
         doc = run(binary, d, "tmpfs", mode)
         assert doc["mapped"] == 1 and doc["mode"] == MODES.index(mode)
-        run(binary, d, "all", mode, "row_maps")  # short ranges out of the mapping too (KUKEON_GPULOAD_ROW_MMAP=1)
+        run(binary, d, "all", mode)
         assert run(binary, d, "none", mode)["mapped"] == 0  # no mapping: every mode falls back to pread
     finally:
         shutil.rmtree(d, ignore_errors=True)
