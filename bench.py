@@ -115,6 +115,9 @@ def workload_spec(args):
         t = synth.mixtral_gguf_tensors(qtype=args.qtype, **kw)
         name = f"Mixtral-8x7B GGUF {args.qtype.lower()} -> bf16" + (f" (REDUCED to {args.layers} layers)" if args.layers else "")
         return dict(kind="gguf", tensors=t, name=name, mode="broadcast")
+    if args.layers:  # test-sized: the reduced model also gets a 4096-entry vocabulary (wte is 154 of the full model's 498 MB)
+        t = synth.gpt2_tensors(n_layer=args.layers, vocab=4096)
+        return dict(kind="gpt2", tensors=t, name=f"GPT-2-small f32 safetensors (REDUCED to {args.layers} layers, vocabulary 4096)", mode="broadcast")
     t = synth.gpt2_tensors()
     return dict(kind="gpt2", tensors=t, name="GPT-2-small f32 safetensors", mode="broadcast")
 

@@ -49,7 +49,7 @@ def test_workload_inventories_match_the_baseline_configs():
 
 
 def test_reference_arm_prints_one_json_line(tmp_path):
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "gpt2", "--steps", "1", "--warmup", "1",
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "gpt2", "--layers", "2", "--steps", "1", "--warmup", "1",
                         "--data-dir", str(tmp_path)], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
