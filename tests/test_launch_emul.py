@@ -138,17 +138,22 @@ def test_every_gguf_block_type_through_whole_launches(emul, tmp_path):
 
 
 def test_transpose_tiles_through_whole_launches(emul, tmp_path):
-    """GPT-2 Conv1D transposes replayed tile for tile: every dtype, rows wider than one tile (d = 1032), destination rows that are not 16-byte
+    """GPT-2 Conv1D transposes replayed tile for tile: every dtype, rows wider than one tile (3096 / 4128 columns), destination rows that are not 16-byte
     multiples (d = 41, 43 -> scalar stores), an unpadded header (rows not 16-byte aligned -> the consumers' gather fallback), 4-byte outputs
     (KEEP_F32), and a three-way fan-out."""
     T = gpupool.LOAD_GPT2_CONV1D_T
     tr = {helpers.OP_T_F32_BF16, helpers.OP_T_F16_BF16, helpers.OP_T_B16, helpers.OP_T_B32}
-    for dt, d, pad in (("F32", 96, True), ("F16", 40, True), ("BF16", 40, True), ("F32", 1032, True), ("F32", 72, False), ("BF16", 264, True),
+    for dt, d, pad in (("F32", 96, True), ("F16", 40, True), ("BF16", 40, True), ("F32", 72, False), ("BF16", 264, True),
                        ("F32", 41, True), ("F16", 43, True)):
         p = str(tmp_path / f"gpt2_{dt}_{d}_{int(pad)}.safetensors")
         synth.write_safetensors(p, [("x", "U8", [3])] + synth.gpt2_tensors(n_layer=1, d=d, vocab=50, n_pos=8, dtype=dt), 3, pad_header=pad)
         plan = replay(emul, p, flags=T)
         assert {sg["op"] for ch in plan["parts"][0]["chunks"] for sg in ch["segs"]} & tr
+    # rows wider than one tile: 3096 and 4128 columns are cut into equal pieces (a whole d = 1032 layer is 50 MB of pools and hit maps; 72 rows of it do)
+    p = str(tmp_path / "gpt2_wide.safetensors")
+    synth.write_safetensors(p, [("h.0.attn.c_attn.weight", "F32", [72, 3096]), ("h.0.mlp.c_fc.weight", "F32", [72, 4128]), ("h.0.mlp.c_proj.weight", "F16", [4128, 72])], 3)
+    plan = replay(emul, p, flags=T)
+    assert {sg["op"] for ch in plan["parts"][0]["chunks"] for sg in ch["segs"]} & tr
     p = str(tmp_path / "gpt2_b.safetensors")
     synth.make_gpt2(p, n_layer=2, d=96, vocab=301, n_pos=40)
     replay(emul, p, flags=T, mode=gpupool.MODE_BROADCAST, n_parts=3)

@@ -187,7 +187,7 @@ def test_gpt2_conv1d_transpose(native, tmp_path):
 
 def test_gpt2_conv1d_transpose_shapes_dtypes_and_wide_rows(native, tmp_path):
     """One transpose family (8-row tiles): every dtype, destination rows that are not 16-byte multiples (d = 41, 43: scalar stores), rows wider
-    than one tile (d = 1032: c_attn has 3096 columns, cut into equal pieces), KEEP_F32 (4-byte outputs), fan-out over 3 parts."""
+    than one tile (3096 and 4128 columns, cut into equal pieces), KEEP_F32 (4-byte outputs), fan-out over 3 parts."""
     T = gpupool.LOAD_GPT2_CONV1D_T
     tr = {helpers.OP_T_F32_BF16, helpers.OP_T_F16_BF16, helpers.OP_T_B16, helpers.OP_T_B32}
     p = str(tmp_path / "gpt2.safetensors")
@@ -197,11 +197,16 @@ def test_gpt2_conv1d_transpose_shapes_dtypes_and_wide_rows(native, tmp_path):
     run_case(p, flags=T, mode=gpupool.MODE_BROADCAST, n_parts=3, chunk=1 * MB)
     plan = run_case(p, flags=T | gpupool.LOAD_KEEP_F32, chunk=1 * MB)
     assert {sg["op"] for ch in plan["parts"][0]["chunks"] for sg in ch["segs"]} & {helpers.OP_T_B32}
-    for dt, d in (("F16", 40), ("BF16", 40), ("F32", 41), ("F16", 43), ("F32", 1032)):
+    for dt, d in (("F16", 40), ("BF16", 40), ("F32", 41), ("F16", 43)):
         q = str(tmp_path / f"gpt2_{dt}_{d}.safetensors")
         synth.write_safetensors(q, synth.gpt2_tensors(n_layer=1, d=d, vocab=50, n_pos=8, dtype=dt), 3)
         plan = run_case(q, flags=T, chunk=1 * MB)
         assert {sg["op"] for ch in plan["parts"][0]["chunks"] for sg in ch["segs"]} & tr, (dt, d)
+    # rows wider than one tile (a whole d = 1032 layer would be 50 MB of pools and hit maps; 72 rows of it carry the same tile cuts)
+    q = str(tmp_path / "gpt2_wide.safetensors")
+    synth.write_safetensors(q, [("h.0.attn.c_attn.weight", "F32", [72, 3096]), ("h.0.mlp.c_fc.weight", "F32", [72, 4128]), ("h.0.mlp.c_proj.weight", "F16", [4128, 72])], 3)
+    plan = run_case(q, flags=T, chunk=1 * MB)
+    assert {sg["op"] for ch in plan["parts"][0]["chunks"] for sg in ch["segs"]} & tr
 
 
 def test_gpt2_f16_and_bf16_transpose(native, tmp_path):
