@@ -1,7 +1,7 @@
 // Host test of the loader's page-cache -> staging-slot read paths (kk_loader.cpp: FdSet, read_chunk, copy_nt) — test infrastructure only.
 // The functions live in kk_loader.cpp's anonymous namespace, so this translation unit includes the source and links against the library's
 // other objects; no CUDA call is made (no GPU needed).  Usage:
-//   KUKEON_GPULOAD_READ=<mode> kk_read_test <dir> <policy: none|tmpfs|all>
+//   KUKEON_GPULOAD_READ=<mode> kk_read_test <dir> <policy: none|tmpfs|all> [seed of the random chunks]
 // Writes a pseudo-random file into <dir>, fills a poisoned buffer through read_chunk with a mix of long (> 256 KiB, unaligned) and short ranges,
 // compares every range with the file and every byte outside the ranges with the poison, and prints one JSON line.
 #include "../../kukeon_b200/csrc/kk_loader.cpp"
@@ -64,6 +64,30 @@ int main(int argc, char** argv) {
       ++bad;
     } catch (const Error& e) {
       if (e.code != KK_EIO) ++bad;
+    }
+    // seeded random chunks: ranges of 1 B .. 2 MiB at arbitrary file offsets, 16-byte aligned buffer offsets as the planner lays them out
+    {
+      std::mt19937_64 r2(argc > 3 ? strtoull(argv[3], nullptr, 10) : 7);
+      for (int round = 0; round < 6; ++round) {
+        Chunk rc;
+        rc.shard = 0;
+        uint64_t p2 = 0;
+        const int n = 1 + (int)(r2() % 24);
+        for (int i = 0; i < n; ++i) {
+          const uint64_t len = (r2() % 4 == 0) ? 1 + r2() % 300 : 1 + r2() % (2u << 20);
+          const uint64_t off = r2() % (fsz - len);
+          const uint64_t at = (p2 + 15) & ~15ull;
+          rc.reads.push_back({off, len, at});
+          p2 = at + len;
+        }
+        rc.buf_bytes = p2;
+        std::vector<uint8_t> b2(p2 + 64, 0x5A);
+        uint8_t* d2 = b2.data() + (r2() % 32);
+        read_chunk(rc, fds, ix, d2);
+        for (auto& r : rc.reads)
+          if (memcmp(d2 + r.buf_off, file.data() + r.file_off, r.len)) ++bad;
+        if (b2[p2 + 63] != 0x5A) ++bad;
+      }
     }
     // a shard truncated AFTER it was mapped: the chunk's ranges beyond the new end must come back as KK_EIO (pread's short read), not as a SIGBUS
     if (truncate(path.c_str(), 1200000) != 0) ++bad;

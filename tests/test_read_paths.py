@@ -38,7 +38,8 @@ def test_every_read_mode_delivers_the_file_bytes_from_tmpfs(binary, mode):
     try:
         doc = run(binary, d, "tmpfs", mode)
         assert doc["mapped"] == 1 and doc["mode"] == MODES.index(mode)
-        run(binary, d, "all", mode)
+        for seed in ("1", "2", "3"):  # other random chunks (1 B .. 2 MiB ranges at arbitrary offsets)
+            run(binary, d, "all", mode, seed)
         assert run(binary, d, "none", mode)["mapped"] == 0  # no mapping: every mode falls back to pread
     finally:
         shutil.rmtree(d, ignore_errors=True)
